@@ -1,0 +1,132 @@
+/* testudo_b200 -- C ABI of the B200-native BLS12-377 G1 MSM engine for Testudo's commitment hot path.
+ *
+ * This is the drop-in boundary: the entry points are exactly what a Rust `-sys` crate for the reference would
+ * bind (INTEGRATION.md shows the stub). All citations are into the reference tree (/root/reference).
+ *
+ * Data layouts (identical to arkworks' in-memory values, so the Rust side copies limbs verbatim):
+ *   G1 affine point : 12 x u64 = x[6] || y[6], little-endian limbs, Montgomery form (R = 2^384);
+ *                     all-zero == point at infinity ((0,0) is not on y^2 = x^3 + 1).
+ *   Fr scalar       : 4 x u64 little-endian. Canonical (`BigInt<4>`, what `msm_bigint` takes) by default;
+ *                     pass TB200_SCALARS_MONT when handing over `Fr` values as stored by ark-ff
+ *                     (Montgomery, R = 2^256) -- the conversion `into_bigint()` then happens on the GPU.
+ * Results are canonical affine points, i.e. the value of `.into_affine()` on what arkworks returns.
+ *
+ * Return value: 0 on success; negative = argument error (TB200_E_*); positive = cudaError_t.
+ * `tb200_last_error()` gives a thread-local message. All calls are blocking and thread-safe (they are issued
+ * concurrently by rayon workers in the reference: src/sqrt_pst.rs:121-125, src/mipp.rs:77-85 via
+ * src/macros.rs:1-17); the library serialises them on one device context per process.
+ * One process drives one GPU (tb200_init(device)); multi-GPU runs use one process per GPU and combine the
+ * per-GPU partial results with tb200_g1_sum (see testudo_b200/parallel.py for the NCCL all-gather).
+ */
+#ifndef TESTUDO_B200_H
+#define TESTUDO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB200_OK 0
+#define TB200_E_ARG (-1)      /* null pointer / bad size / bad flag */
+#define TB200_E_STATE (-2)    /* library not initialised, bad handle */
+#define TB200_E_LIMIT (-3)    /* problem exceeds an engine limit */
+
+#define TB200_SCALARS_MONT 1u /* scalars are ark-ff Montgomery-form Fr, not canonical BigInt<4> */
+
+/* ---- lifecycle -------------------------------------------------------------------------------------- */
+/* Select `device` (-1 = current) and create the context; idempotent. Fails loudly without a CUDA device:
+ * there is no CPU fallback anywhere in this library. */
+int tb200_init(int device);
+void tb200_shutdown(void);
+const char* tb200_last_error(void);
+/* number of kernels this library has launched since init / reset (bench.py reports it as gpu_launches) */
+uint64_t tb200_launch_count(void);
+void tb200_reset_launch_count(void);
+
+/* ---- single variable-base MSM ------------------------------------------------------------------------
+ * Replaces `<G1Projective as VariableBaseMSM>::msm_bigint(bases, bigints)` /
+ * `msm_unchecked(bases, scalars)` followed by `.into_affine()` (ark-ec 0.4; call sites
+ * src/sqrt_pst.rs:198, src/mipp.rs:385-394, src/commitments.rs:70-86, src/nizk/bullet.rs:93-118).
+ * n == 0 yields the identity. `msm_unchecked`'s truncate-to-min(len) and `msm`'s Err(min_len) length rules
+ * live in the host wrapper (testudo_b200/msm.py, host/msm.hpp), which passes n = min(len). */
+int tb200_msm_g1(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, unsigned flags,
+                 uint64_t out_xy[12]);
+/* Same, all pointers are DEVICE pointers (16-byte aligned); result (96 bytes) written to d_out_xy.
+ * `stream` is a cudaStream_t (NULL = the library's stream); the call returns after enqueueing. */
+int tb200_msm_g1_dev(const void* d_bases_xy, const void* d_scalars, size_t n, unsigned flags,
+                     void* d_out_xy, void* stream);
+
+/* ---- shared-base (SRS) batched MSM -------------------------------------------------------------------
+ * Replaces the row fan-out `self.polys.par_iter().map(|p| MultilinearPC::commit(ck, p))`
+ * (src/sqrt_pst.rs:121-125: 2^m_col MSMs over ck.powers_of_g[0]) and the Hyrax fan-out
+ * `DensePolynomial::commit_inner` (src/dense_mlpoly.rs:315-329 over gens_n.G) by ONE call.
+ * The SRS is uploaded once; window tables 2^(c*w) * G_j are precomputed on the GPU so every row needs a
+ * single bucket set. window_bits = 0 picks c automatically. */
+typedef struct tb200_srs* tb200_srs_t;
+int tb200_srs_load(const uint64_t* bases_xy, size_t n, int window_bits, tb200_srs_t* out);
+int tb200_srs_free(tb200_srs_t srs);
+size_t tb200_srs_size(tb200_srs_t srs);
+/* out_xy[i] = sum_j scalars[i*row_stride + j*col_stride] * G_j, i < rows, j < cols <= srs size.
+ * Strides are in scalars (4 x u64). Un-transposed Z of sqrt_pst (Z[(j << m_col) | i], src/sqrt_pst.rs:58):
+ * row_stride = 1, col_stride = 2^m_col. Contiguous rows (Hyrax, src/dense_mlpoly.rs:325): row_stride = cols,
+ * col_stride = 1. */
+int tb200_msm_g1_batch(tb200_srs_t srs, const uint64_t* scalars, size_t rows, size_t cols, ptrdiff_t row_stride,
+                       ptrdiff_t col_stride, unsigned flags, uint64_t* out_xy);
+/* rows given as separate heap buffers (what `Polynomial::commit` holds: self.polys[i].Z, src/sqrt_pst.rs:48-62) */
+int tb200_msm_g1_batch_ptrs(tb200_srs_t srs, const uint64_t* const* row_ptrs, size_t rows, size_t cols,
+                            unsigned flags, uint64_t* out_xy);
+int tb200_msm_g1_batch_dev(tb200_srs_t srs, const void* d_scalars, size_t rows, size_t cols, ptrdiff_t row_stride,
+                           ptrdiff_t col_stride, unsigned flags, void* d_out_xy, void* stream);
+
+/* ---- MIPP G1 steps, device-resident across rounds --------------------------------------------------------
+ * Replaces the G1 work of `MippProof::prove` (src/mipp.rs:58-120): per round
+ *   cross: comm_u_l = MSM(a_l, y_r), comm_u_r = MSM(a_r, y_l)           (src/mipp.rs:77-85, :385-394)
+ *   fold : a_l[i] += c * a_r[i] (into_affine), y_l[i] += c_inv * y_r[i]  (src/mipp.rs:110-112, :354-383)
+ * The vectors stay on the GPU; only two points per round come back for the transcript. */
+typedef struct tb200_mipp* tb200_mipp_t;
+int tb200_mipp_g1_begin(const uint64_t* a_xy, const uint64_t* y, size_t n, unsigned flags, tb200_mipp_t* out);
+size_t tb200_mipp_g1_len(tb200_mipp_t h);
+int tb200_mipp_g1_cross(tb200_mipp_t h, uint64_t comm_u_l[12], uint64_t comm_u_r[12]);
+/* c and c_inv are Fr scalars in the representation selected by `flags` at begin() */
+int tb200_mipp_g1_fold(tb200_mipp_t h, const uint64_t c[4], const uint64_t c_inv[4]);
+/* current vectors (len() entries): a as affine points, y as scalars in the begin() representation */
+int tb200_mipp_g1_read(tb200_mipp_t h, uint64_t* a_xy, uint64_t* y);
+int tb200_mipp_g1_end(tb200_mipp_t h);
+/* stand-alone `compress` for G1 (src/mipp.rs:354-367): vec[i] = vec[i] + scaler * vec[split + i], i < split */
+int tb200_compress_g1(uint64_t* vec_xy, size_t split, const uint64_t scaler[4], unsigned flags);
+
+/* ---- group utilities ------------------------------------------------------------------------------------ */
+/* out = sum of n affine points (combining per-GPU partial results after the NCCL all-gather) */
+int tb200_g1_sum(const uint64_t* pts_xy, size_t n, uint64_t out_xy[12]);
+int tb200_g1_sum_dev(const void* d_pts_xy, size_t n, void* d_out_xy, void* stream);
+/* d_out[i * nb + j] = A_i + B_j (affine): synthetic bases with known discrete logs */
+int tb200_g1_outer_sum_dev(const void* d_a_xy, size_t na, const void* d_b_xy, size_t nb, void* d_out_xy,
+                           void* stream);
+
+/* ---- profiling / tuning ----------------------------------------------------------------------------------- */
+/* When enabled, every MSM call records CUDA events around its stages on the launching stream. */
+void tb200_set_profiling(int enabled);
+/* milliseconds of the named stage in the most recent profiled call: "digits", "scan", "scatter",
+ * "accumulate", "fixup", "reduce", "finalize", "total". Returns < 0 if unknown / not profiled. */
+double tb200_stage_ms(const char* stage);
+/* geometry of the most recent MSM call: window bits c, windows W, sorted entries M, buckets B, segment K */
+int tb200_last_geometry(int* c, int* windows, uint64_t* entries, uint64_t* buckets, int* segment);
+/* override the automatic window choice for single MSMs (0 = automatic) */
+void tb200_set_window_bits(int c);
+/* integer-pipe microbenchmark: runs `iters` dependent-chain iterations of wide MACs on every SM and returns the
+ * achieved 32x32->64 multiply-accumulates per second in *out_macs_per_s (kind: 0 = IMAD.WIDE.U32 reg-reg,
+ * 1 = IMAD (32-bit lo), 2 = full Fq Montgomery multiplications per second). */
+int tb200_int_pipe_peak(int kind, int iters, double* out_per_s);
+
+/* ---- kernel unit-test hooks (device field / group arithmetic on n independent lanes) ----------------------- */
+int tb200_test_fq_mul(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);      /* 6 u64 each */
+int tb200_test_fq_addsub(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_add, uint64_t* out_sub);
+int tb200_test_g1_add(const uint64_t* p_xy, const uint64_t* q_xy, size_t n, uint64_t* out_xy); /* via XYZZ madd */
+int tb200_test_g1_mul(const uint64_t* p_xy, const uint64_t* k, size_t n, uint64_t* out_xy);    /* k canonical */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TESTUDO_B200_H */

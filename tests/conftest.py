@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """The CUDA engine; fails loudly (no fallback) when the library or the GPU is missing."""
+    from testudo_b200 import _lib
+
+    return _lib.init()
+
+
+@pytest.fixture(scope="session")
+def oracle_c():
+    from oracle import cpu
+
+    cpu.build()
+    return cpu

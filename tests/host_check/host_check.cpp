@@ -1,0 +1,56 @@
+// Test-only shim: compiles the product's __host__ __device__ field/group headers with g++ (carry chains
+// emulated) so the algorithm structure can be checked on a CPU-only box. Not part of the product library.
+#include <cstring>
+#include "../../testudo_b200/csrc/g1.cuh"
+#include "../../testudo_b200/csrc/digits.cuh"
+using namespace tb;
+extern "C" {
+void hc_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul<FqParams>(r, a, b); }
+void hc_fq_sqr(const uint32_t* a, uint32_t* r) { mont_sqr<FqParams>(r, a); }
+void hc_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { mod_add<FqParams>(r, a, b); }
+void hc_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { mod_sub<FqParams>(r, a, b); }
+void hc_fq_neg(const uint32_t* a, uint32_t* r) { mod_neg<FqParams>(r, a); }
+void hc_fq_inv(const uint32_t* a, uint32_t* r) { Fq x, y; memcpy(x.l, a, 48); fq_inv(y, x); memcpy(r, y.l, 48); }
+void hc_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul<FrParams>(r, a, b); }
+void hc_fr_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { mod_add<FrParams>(r, a, b); }
+void hc_fr_to_canonical(const uint32_t* a, uint32_t* r) { mont_to_canonical<FrParams>(r, a); }
+void hc_consts(uint32_t* q, uint32_t* q_one, uint32_t* q_r2, uint32_t* r, uint32_t* r_one, uint32_t* r_r2) {
+  for (int i = 0; i < 12; i++) { q[i] = FqParams::p(i); q_one[i] = FqParams::one(i); q_r2[i] = FqParams::r2(i); }
+  for (int i = 0; i < 8; i++) { r[i] = FrParams::p(i); r_one[i] = FrParams::one(i); r_r2[i] = FrParams::r2(i); }
+}
+// acc (xyzz as affine in, inf allowed) + q -> affine out, exercising madd / add / dbl / to_affine
+void hc_madd(const uint32_t* p_aff, const uint32_t* q_aff, uint32_t* out_aff) {
+  Affine p, q, r; memcpy(&p, p_aff, 96); memcpy(&q, q_aff, 96);
+  Xyzz acc; xyzz_from_affine(acc, p);
+  xyzz_madd(acc, q);
+  xyzz_to_affine(r, acc); memcpy(out_aff, &r, 96);
+}
+// (p scaled to a non-trivial ZZ by adding and subtracting t) + q, through the full XYZZ+XYZZ add
+void hc_add(const uint32_t* p_aff, const uint32_t* q_aff, const uint32_t* t_aff, uint32_t* out_aff) {
+  Affine p, q, t, r; memcpy(&p, p_aff, 96); memcpy(&q, q_aff, 96); memcpy(&t, t_aff, 96);
+  Xyzz a, b; xyzz_from_affine(a, p); xyzz_from_affine(b, q);
+  xyzz_madd(a, t); Affine nt = t; fq_neg(nt.y, nt.y); xyzz_madd(a, nt);   // a == p with ZZ != 1
+  xyzz_madd(b, t); xyzz_madd(b, nt);                                    // b == q with ZZ != 1
+  xyzz_add(a, b);
+  xyzz_to_affine(r, a); memcpy(out_aff, &r, 96);
+}
+void hc_dbl(const uint32_t* p_aff, const uint32_t* t_aff, uint32_t* out_aff) {
+  Affine p, t, r; memcpy(&p, p_aff, 96); memcpy(&t, t_aff, 96);
+  Xyzz a; xyzz_from_affine(a, p);
+  xyzz_madd(a, t); Affine nt = t; fq_neg(nt.y, nt.y); xyzz_madd(a, nt);
+  xyzz_dbl(a);
+  xyzz_to_affine(r, a); memcpy(out_aff, &r, 96);
+}
+void hc_scalar_mul(const uint32_t* p_aff, const uint32_t* k, uint32_t* out_aff) {
+  Affine p, r; memcpy(&p, p_aff, 96);
+  Xyzz a; xyzz_scalar_mul(a, p, k);
+  xyzz_to_affine(r, a); memcpy(out_aff, &r, 96);
+}
+// signed digits of one canonical scalar with window c: out[w] in [-2^(c-1), 2^(c-1)]
+int hc_digits(const uint32_t* s, int c, int32_t* out) {
+  int W = num_windows(c);
+  DigitIter it(s, c);
+  for (int w = 0; w < W; w++) out[w] = it.next(w == W - 1);
+  return W;
+}
+}

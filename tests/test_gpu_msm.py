@@ -1,0 +1,101 @@
+"""GPU parity: single variable-base MSM through the C ABI vs golden vectors, the oracles and closed forms."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import helpers as h
+from oracle import bls12_377 as o
+from testudo_b200 import _lib, msm
+
+pytestmark = pytest.mark.gpu
+GOLD = h.load_golden("msm_golden.json")
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.mark.parametrize("case", GOLD["seeded"], ids=lambda c: f"n{c['n']}")
+def test_msm_seeded_golden(engine, case):
+    pts, _ = o.rand_points(case["n"], case["points_seed"])
+    sc = o.rand_scalars(case["n"], case["scalars_seed"])
+    exp = h.pt_unhex(case["result"])
+    assert h.pt_from_np(msm.msm_bigint(h.pts_to_np(pts), h.scalars_to_np(sc))) == exp
+    assert h.pt_from_np(msm.msm_unchecked(h.pts_to_np(pts), h.scalars_to_np(sc, mont=True))) == exp
+
+
+@pytest.mark.parametrize("case", GOLD["explicit"] + GOLD["edge"], ids=lambda c: c.get("name", "explicit"))
+def test_msm_explicit_and_edge_golden(engine, case):
+    pts = [h.pt_unhex(p) for p in case["points"]]
+    sc = [int(s, 16) for s in case["scalars"]]
+    assert h.pt_from_np(msm.msm_bigint(h.pts_to_np(pts), h.scalars_to_np(sc))) == h.pt_unhex(case["result"])
+
+
+def test_msm_empty_and_length_rules(engine):
+    pts, _ = o.rand_points(4, 1)
+    B = h.pts_to_np(pts)
+    S = h.scalars_to_np([1, 2, 3], mont=True)
+    assert msm.msm(B, S) == ("err", 3)                                    # VariableBaseMSM::msm -> Err(min_len)
+    assert h.pt_from_np(msm.msm_unchecked(B, S)) == o.msm_naive(pts[:3], [1, 2, 3])  # truncates silently
+    ok, val = msm.msm(B[:3], S)
+    assert ok == "ok" and h.pt_from_np(val) == o.msm_naive(pts[:3], [1, 2, 3])
+    assert h.pt_from_np(msm.msm_bigint(B[:0], S[:0])) is None            # n == 0 -> identity
+
+
+@pytest.mark.parametrize("c", [3, 5, 8, 11, 13, 16])
+def test_msm_every_window_width(engine, oracle_c, c):
+    n = 700
+    pts, dl = o.rand_points(n, 300 + c)
+    sc = o.rand_scalars(n, 400 + c)
+    sc[0] = o.R_ORDER - 1; sc[1] = 0; sc[2] = 1 << 252
+    engine.tb200_set_window_bits(c)
+    try:
+        got = msm.msm_bigint(h.pts_to_np(pts), h.scalars_to_np(sc))
+        cc = ctypes.c_int()
+        engine.tb200_last_geometry(ctypes.byref(cc), None, None, None, None)
+        assert cc.value == c
+    finally:
+        engine.tb200_set_window_bits(0)
+    assert h.pt_from_np(got) == o.msm_by_dlog(dl, sc)
+
+
+@pytest.mark.parametrize("logn", [10, 14, 16])
+def test_msm_vs_c_oracle_and_dlog(engine, oracle_c, logn):
+    n = 1 << logn
+    a, step = 1234567 + logn, 0xABCDEF01
+    bases = oracle_c.gen_points(h.pts_to_np([o.mul(a, o.G)])[0], h.pts_to_np([o.mul(step, o.G)])[0], n)
+    sc = h.np_rand_scalars(n, logn)
+    got = msm.msm_bigint(bases, sc)
+    assert np.array_equal(got, oracle_c.msm_g1(bases, sc))
+    ints = h.np_scalars_to_ints(sc)
+    assert h.pt_from_np(got) == o.mul(sum(s * (a + step * k) for k, s in enumerate(ints)) % o.R_ORDER, o.G)
+
+
+def test_msm_skewed_scalars_heavy_buckets(engine, oracle_c):
+    """R1CS-like witness: 50% zeros, 25% ones, 25% uniform, repeated bases -> a few huge
+    buckets that span many accumulation segments and exercise the head/fix-up path and the doubling branch."""
+    n = 1 << 15
+    bases = oracle_c.gen_points(h.pts_to_np([o.mul(99, o.G)])[0], h.pts_to_np([o.mul(31337, o.G)])[0], n)
+    bases[1000:1200] = bases[1000]          # duplicates: P + P inside a bucket
+    bases[5000:5010] = 0                    # identity bases
+    sc = h.np_rand_scalars(n, 5)
+    rng = np.random.default_rng(6)
+    kind = rng.integers(0, 4, size=n)
+    sc[kind < 2] = 0
+    sc[kind == 2] = np.array([1, 0, 0, 0], dtype=np.uint64)
+    got = msm.msm_bigint(bases, sc)
+    assert np.array_equal(got, oracle_c.msm_g1(bases, sc))
+
+
+def test_msm_linearity_property(engine, oracle_c):
+    """MSM(B, s1) + MSM(B, s2) == MSM(B, s1 + s2 mod r) at 2^17 points (size-independent property)."""
+    n = 1 << 17
+    bases = oracle_c.gen_points(h.pts_to_np([o.mul(7, o.G)])[0], h.pts_to_np([o.mul(11, o.G)])[0], n)
+    s1 = h.np_rand_scalars(n, 1)
+    s2 = h.np_rand_scalars(n, 2)
+    i1, i2 = h.np_scalars_to_ints(s1), h.np_scalars_to_ints(s2)
+    s3 = h.scalars_to_np([(x + y) % o.R_ORDER for x, y in zip(i1, i2)])
+    r1, r2, r3 = msm.msm_bigint(bases, s1), msm.msm_bigint(bases, s2), msm.msm_bigint(bases, s3)
+    assert np.array_equal(msm.g1_sum(np.stack([r1, r2])), r3)
+    assert h.pt_from_np(r3) == o.mul(sum((x + y) * (7 + 11 * k) for k, (x, y) in enumerate(zip(i1, i2))) % o.R_ORDER, o.G)

@@ -1,0 +1,103 @@
+"""ctypes binding of include/testudo_b200.h. There is no fallback: if the CUDA library is missing or no GPU is
+present, loading / initialising raises."""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtestudo_b200.so")
+
+SCALARS_MONT = 1
+
+_lib = None
+_lock = threading.Lock()
+_inited = False
+
+c_void_p = ctypes.c_void_p
+c_size_t = ctypes.c_size_t
+c_ssize_t = ctypes.c_ssize_t
+c_uint = ctypes.c_uint
+c_int = ctypes.c_int
+
+# every symbol include/testudo_b200.h declares: (restype, argtypes)
+SIGNATURES = {
+    "tb200_init": (c_int, [c_int]),
+    "tb200_shutdown": (None, []),
+    "tb200_last_error": (ctypes.c_char_p, []),
+    "tb200_launch_count": (ctypes.c_uint64, []),
+    "tb200_reset_launch_count": (None, []),
+    "tb200_msm_g1": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
+    "tb200_msm_g1_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p, c_void_p]),
+    "tb200_srs_load": (c_int, [c_void_p, c_size_t, c_int, ctypes.POINTER(c_void_p)]),
+    "tb200_srs_free": (c_int, [c_void_p]),
+    "tb200_srs_size": (c_size_t, [c_void_p]),
+    "tb200_msm_g1_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_ssize_t, c_ssize_t, c_uint, c_void_p]),
+    "tb200_msm_g1_batch_ptrs": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint, c_void_p]),
+    "tb200_msm_g1_batch_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_ssize_t, c_ssize_t, c_uint,
+                                       c_void_p, c_void_p]),
+    "tb200_mipp_g1_begin": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, ctypes.POINTER(c_void_p)]),
+    "tb200_mipp_g1_len": (c_size_t, [c_void_p]),
+    "tb200_mipp_g1_cross": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "tb200_mipp_g1_fold": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "tb200_mipp_g1_read": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "tb200_mipp_g1_end": (c_int, [c_void_p]),
+    "tb200_compress_g1": (c_int, [c_void_p, c_size_t, c_void_p, c_uint]),
+    "tb200_g1_sum": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "tb200_g1_sum_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "tb200_g1_outer_sum_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "tb200_set_profiling": (None, [c_int]),
+    "tb200_stage_ms": (ctypes.c_double, [ctypes.c_char_p]),
+    "tb200_last_geometry": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_uint64),
+                                    ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(c_int)]),
+    "tb200_set_window_bits": (None, [c_int]),
+    "tb200_int_pipe_peak": (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_double)]),
+    "tb200_test_fq_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tb200_test_fq_addsub": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "tb200_test_g1_add": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tb200_test_g1_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+}
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"testudo_b200 error {code}: {message}")
+        self.code = code
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the library and bind every declared symbol (no CUDA call is made)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -m testudo_b200.build` "
+                    "(testudo_b200 has no CPU fallback)")
+            lib = ctypes.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise EngineError(rc, load().tb200_last_error().decode("utf-8", "replace"))
+
+
+def init(device: int = -1) -> ctypes.CDLL:
+    """Create the CUDA context on `device` (raises without a GPU)."""
+    global _inited
+    lib = load()
+    if not _inited:
+        check(lib.tb200_init(device))
+        _inited = True
+    return lib
+
+
+def engine() -> ctypes.CDLL:
+    return init()

@@ -1,0 +1,816 @@
+// C ABI of the engine (include/testudo_b200.h): context, workspace arena, pipeline orchestration.
+// Everything numerical happens in the kernels of kernels.cuh; there is no CPU arithmetic path in this file --
+// if no CUDA device is present tb200_init fails and every other entry point returns TB200_E_STATE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/testudo_b200.h"
+#include "kernels.cuh"
+
+using namespace tb;
+
+namespace {
+
+thread_local std::string g_err;
+std::mutex g_mu;
+uint64_t g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+#define CU(expr)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess)                                                                              \
+      return fail((int)e__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define LAUNCH(kernel, grid, block, stream, ...)                          \
+  do {                                                                    \
+    kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);                \
+    g_launches++;                                                         \
+    CU(cudaGetLastError());                                               \
+  } while (0)
+
+inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+// grow-only device arena: MSM calls carve their scratch out of one allocation (no cudaMalloc on the hot path)
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (base) {
+      cudaError_t e = cudaFree(base);
+      if (e != cudaSuccess) return (int)e;
+      base = nullptr;
+      cap = 0;
+    }
+    size_t want = bytes + (bytes >> 3);
+    cudaError_t e = cudaMalloc((void**)&base, want);
+    if (e != cudaSuccess) {
+      e = cudaMalloc((void**)&base, bytes);
+      want = bytes;
+      if (e != cudaSuccess) return (int)e;
+    }
+    cap = want;
+    return 0;
+  }
+  void reset() { off = 0; }
+  template <class T>
+  T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+  static size_t pad(size_t bytes) { return (bytes + 255) & ~size_t(255); }
+};
+
+struct Stage {
+  const char* name;
+  cudaEvent_t ev;
+};
+
+struct Ctx {
+  bool ready = false;
+  int device = -1;
+  int sms = 0;
+  cudaStream_t stream = nullptr;
+  Arena arena;
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<Stage> marks;
+  std::map<std::string, double> stage_ms;
+  int forced_c = 0;
+  // geometry of the last call
+  int last_c = 0, last_W = 0, last_K = 0;
+  uint64_t last_entries = 0, last_buckets = 0;
+  uint4* d_result = nullptr;  // 96-byte staging for host-facing calls
+  uint4* h_result = nullptr;  // pinned
+} g;
+
+int mark(cudaStream_t st, const char* name) {
+  if (!g.profiling) return 0;
+  size_t idx = g.marks.size();
+  if (idx >= g.ev_pool.size()) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    g.ev_pool.push_back(e);
+  }
+  CU(cudaEventRecord(g.ev_pool[idx], st));
+  g.marks.push_back({name, g.ev_pool[idx]});
+  return 0;
+}
+int finish_marks(cudaStream_t st) {
+  if (!g.profiling || g.marks.empty()) return 0;
+  CU(cudaStreamSynchronize(st));
+  g.stage_ms.clear();
+  for (size_t i = 1; i < g.marks.size(); i++) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, g.marks[i - 1].ev, g.marks[i].ev));
+    g.stage_ms[g.marks[i].name] += ms;
+  }
+  float tot = 0;
+  CU(cudaEventElapsedTime(&tot, g.marks.front().ev, g.marks.back().ev));
+  g.stage_ms["total"] = tot;
+  g.marks.clear();
+  return 0;
+}
+
+// ---- window selection ---------------------------------------------------------------------------------------
+// cost in mixed-addition units: accumulation entries + ~4 adds per bucket for the hierarchical reduction
+int pick_c_single(uint64_t n) {
+  if (g.forced_c) return g.forced_c;
+  int best = 3;
+  double bestc = 1e300;
+  for (int c = 3; c <= 20; c++) {
+    int W = num_windows(c);
+    double cost = (double)W * ((double)n + 4.0 * (double)(1u << (c - 1)));
+    if (cost < bestc) {
+      bestc = cost;
+      best = c;
+    }
+  }
+  return best;
+}
+int pick_c_batch(uint64_t cols) {
+  int best = 3;
+  double bestc = 1e300;
+  for (int c = 3; c <= 16; c++) {
+    int W = num_windows(c);
+    double cost = (double)W * (double)cols + 4.0 * (double)(1u << (c - 1));
+    if (cost < bestc) {
+      bestc = cost;
+      best = c;
+    }
+  }
+  return best;
+}
+
+// ---- the pipeline --------------------------------------------------------------------------------------------
+struct Plan {
+  MsmGeom geo;
+  uint64_t M_max, B;
+  uint32_t K, S_max, ntiles;
+  std::vector<uint32_t> Ls;  // reduction fan-in per level
+  size_t bytes;
+};
+
+int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs, int c, int batch, unsigned flags) {
+  MsmGeom& q = p.geo;
+  q.rows = rows;
+  q.cols = cols;
+  q.row_stride = rs;
+  q.col_stride = cs;
+  q.c = c;
+  q.W = num_windows(c);
+  q.nb = 1u << (c - 1);
+  q.batch = batch;
+  q.groups = batch ? rows : (uint32_t)q.W;
+  q.mont = (flags & TB200_SCALARS_MONT) ? 1 : 0;
+  p.M_max = (uint64_t)rows * cols * q.W;
+  p.B = (uint64_t)q.groups * q.nb;
+  if (p.M_max >= (1ull << 32) - 512 || p.B >= (1ull << 31))
+    return fail(TB200_E_LIMIT, "MSM too large for one pass: %llu entries, %llu buckets",
+                (unsigned long long)p.M_max, (unsigned long long)p.B);
+  uint64_t target_threads = (uint64_t)g.sms * 3 * ACC_THREADS * 4;
+  uint64_t K = (p.M_max + target_threads - 1) / target_threads;
+  p.K = (uint32_t)std::min<uint64_t>(256, std::max<uint64_t>(4, K));
+  p.S_max = cdiv(std::max<uint64_t>(p.M_max, 1), p.K);
+  p.ntiles = (uint32_t)(p.B / SCAN_TILE + 1);
+  p.Ls.clear();
+  for (uint32_t n = q.nb; n > 1;) {
+    uint32_t L = std::min<uint32_t>(n, 32);
+    p.Ls.push_back(L);
+    n /= L;
+  }
+  // arena size
+  size_t b = 0;
+  b += Arena::pad((p.B + 1) * 4) * 2;  // counts, starts
+  b += Arena::pad(p.B * 4);            // cursors
+  b += Arena::pad((size_t)p.ntiles * 4 + 4);
+  b += Arena::pad(std::max<uint64_t>(p.M_max, 1) * 4);  // entries
+  b += Arena::pad(p.B * 192);                           // buckets
+  b += Arena::pad((size_t)p.S_max * 192) + Arena::pad((size_t)p.S_max * 4);
+  uint64_t n = p.B;
+  for (uint32_t L : p.Ls) {
+    n /= L;
+    b += Arena::pad(n * 192) * 2;
+  }
+  b += Arena::pad((size_t)q.groups * 192) * 2 + 4096;
+  p.bytes = b;
+  return 0;
+}
+
+// Runs the whole pipeline on `st`. d_points: affine points indexed by entry refs. d_out: groups*96 B (batch) or 96 B.
+int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points, uint4* d_out, cudaStream_t st) {
+  const MsmGeom& q = p.geo;
+  int rc = g.arena.reserve(p.bytes);
+  if (rc) return fail(rc, "workspace allocation of %zu bytes failed: %s", p.bytes, cudaGetErrorString((cudaError_t)rc));
+  g.arena.reset();
+  uint32_t* counts = g.arena.take<uint32_t>(p.B + 1);
+  uint32_t* starts = g.arena.take<uint32_t>(p.B + 1);
+  uint32_t* cursors = g.arena.take<uint32_t>(p.B);
+  uint32_t* tile_sums = g.arena.take<uint32_t>(p.ntiles + 1);
+  uint32_t* entries = g.arena.take<uint32_t>(std::max<uint64_t>(p.M_max, 1));
+  uint4* buckets = g.arena.take<uint4>(p.B * 12);
+  uint4* heads = g.arena.take<uint4>((size_t)p.S_max * 12);
+  int32_t* head_bucket = g.arena.take<int32_t>(p.S_max);
+
+  g.last_c = q.c;
+  g.last_W = q.W;
+  g.last_K = (int)p.K;
+  g.last_entries = p.M_max;
+  g.last_buckets = p.B;
+
+  const uint64_t items = (uint64_t)q.rows * q.cols;
+  if (items == 0) {
+    uint32_t cnt = q.batch ? q.rows : 1;
+    if (cnt) LAUNCH(k_write_identity, cdiv(cnt * 6, 128), 128, st, d_out, cnt);
+    return 0;
+  }
+  if (mark(st, "begin")) return 1;
+  CU(cudaMemsetAsync(counts, 0, (p.B + 1) * 4, st));
+  const uint32_t dig_grid = (uint32_t)std::min<uint64_t>(cdiv(items, 256), (uint64_t)g.sms * 16);
+  LAUNCH(k_digits<false>, dig_grid, 256, st, d_scalars, q, counts, (uint32_t*)nullptr);
+  if (mark(st, "digits")) return 1;
+  LAUNCH(k_scan_tile_sums, p.ntiles, SCAN_THREADS, st, counts, (uint32_t)p.B, tile_sums);
+  LAUNCH(k_scan_tile_offsets, 1, SCAN_THREADS, st, tile_sums, p.ntiles, tile_sums + p.ntiles);
+  LAUNCH(k_scan_apply, p.ntiles, SCAN_THREADS, st, counts, (uint32_t)p.B, tile_sums, starts, cursors);
+  if (mark(st, "scan")) return 1;
+  LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, cursors, entries);
+  if (mark(st, "scatter")) return 1;
+  // M is only known on the device (starts[B]); launch for the upper bound, surplus threads exit immediately
+  LAUNCH(k_accumulate, cdiv(p.S_max, ACC_THREADS), ACC_THREADS, st, entries, starts, (uint32_t)p.B, p.K, d_points,
+         buckets, heads, head_bucket);
+  if (mark(st, "accumulate")) return 1;
+  LAUNCH(k_fixup, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket);
+  if (mark(st, "fixup")) return 1;
+  // hierarchical bucket reduction
+  const uint4 *inS = buckets, *inW = nullptr;
+  const uint32_t* level0 = starts;
+  uint64_t n = p.B;
+  int log2_ell = 0;
+  for (uint32_t L : p.Ls) {
+    n /= L;
+    uint4* outS = g.arena.take<uint4>(n * 12);
+    uint4* outW = g.arena.take<uint4>(n * 12);
+    LAUNCH(k_reduce_pass, cdiv(n, 128), 128, st, inS, inW, level0, outS, outW, L, log2_ell, n);
+    inS = outS;
+    inW = outW;
+    level0 = nullptr;
+    for (uint32_t v = L; v > 1; v >>= 1) log2_ell++;
+  }
+  const uint4* group_w = inW ? inW : buckets;  // nb == 1 (c == 1) never happens: c >= 3
+  if (mark(st, "reduce")) return 1;
+  if (q.batch) LAUNCH(k_finalize_batch, cdiv(q.groups, 128), 128, st, group_w, q.groups, d_out);
+  else LAUNCH(k_finalize_single, 1, 32, st, group_w, q.W, q.c, d_out);
+  if (mark(st, "finalize")) return 1;
+  return 0;
+}
+
+int need_ready() {
+  if (!g.ready) return fail(TB200_E_STATE, "tb200_init has not been called (or failed): no CUDA context");
+  return 0;
+}
+
+}  // namespace
+
+struct tb200_srs {
+  uint32_t n = 0;
+  int c = 0, W = 0;
+  uint4* table = nullptr;  // W * n affine points
+};
+struct tb200_mipp {
+  uint32_t n = 0;       // current length
+  unsigned flags = 0;
+  uint4* a = nullptr;   // n0 affine points
+  uint32_t* y = nullptr;  // n0 scalars (8 limbs)
+  uint32_t* scal = nullptr;  // 16 limbs staging for c, c_inv
+};
+
+extern "C" {
+
+int tb200_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g.ready) return 0;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(e != cudaSuccess ? (int)e : TB200_E_STATE,
+                "no CUDA device available (%s): testudo_b200 has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  if (device < 0) CU(cudaGetDevice(&device));
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  g.device = device;
+  g.sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CU(cudaMalloc((void**)&g.d_result, 16384));
+  CU(cudaMallocHost((void**)&g.h_result, 16384));
+  g.ready = true;
+  return 0;
+}
+
+void tb200_shutdown(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g.ready) return;
+  cudaSetDevice(g.device);
+  cudaStreamSynchronize(g.stream);
+  if (g.arena.base) cudaFree(g.arena.base);
+  g.arena = Arena();
+  for (auto e : g.ev_pool) cudaEventDestroy(e);
+  g.ev_pool.clear();
+  cudaFree(g.d_result);
+  cudaFreeHost(g.h_result);
+  cudaStreamDestroy(g.stream);
+  g.ready = false;
+}
+
+const char* tb200_last_error(void) { return g_err.c_str(); }
+uint64_t tb200_launch_count(void) { return g_launches; }
+void tb200_reset_launch_count(void) { g_launches = 0; }
+void tb200_set_profiling(int enabled) { g.profiling = enabled != 0; }
+double tb200_stage_ms(const char* stage) {
+  auto it = g.stage_ms.find(stage ? stage : "");
+  return it == g.stage_ms.end() ? -1.0 : it->second;
+}
+int tb200_last_geometry(int* c, int* windows, uint64_t* entries, uint64_t* buckets, int* segment) {
+  if (c) *c = g.last_c;
+  if (windows) *windows = g.last_W;
+  if (entries) *entries = g.last_entries;
+  if (buckets) *buckets = g.last_buckets;
+  if (segment) *segment = g.last_K;
+  return 0;
+}
+void tb200_set_window_bits(int c) { g.forced_c = (c >= 3 && c <= 22) ? c : 0; }
+
+// ---- single MSM -------------------------------------------------------------------------------------------------
+static int msm_dev_locked(const void* d_bases, const void* d_scalars, size_t n, unsigned flags, void* d_out,
+                          cudaStream_t st) {
+  if (n >= (1ull << 31)) return fail(TB200_E_LIMIT, "n = %zu exceeds 2^31 - 1 points per call", n);
+  if (((uintptr_t)d_bases | (uintptr_t)d_scalars | (uintptr_t)d_out) & 15)
+    return fail(TB200_E_ARG, "device pointers must be 16-byte aligned");
+  Plan p;
+  int c = pick_c_single(std::max<size_t>(n, 1));
+  int rc = make_plan(p, 1, (uint32_t)n, 0, 1, c, 0, flags);
+  while (rc == TB200_E_LIMIT && c > 3) rc = make_plan(p, 1, (uint32_t)n, 0, 1, --c, 0, flags);
+  if (rc) return rc;
+  g.marks.clear();
+  rc = run_pipeline(p, (const uint32_t*)d_scalars, (const uint4*)d_bases, (uint4*)d_out, st);
+  if (rc) return rc;
+  return finish_marks(st);
+}
+
+int tb200_msm_g1_dev(const void* d_bases_xy, const void* d_scalars, size_t n, unsigned flags, void* d_out_xy,
+                     void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_out_xy || (n && (!d_bases_xy || !d_scalars))) return fail(TB200_E_ARG, "null pointer");
+  CU(cudaSetDevice(g.device));
+  return msm_dev_locked(d_bases_xy, d_scalars, n, flags, d_out_xy, stream ? (cudaStream_t)stream : g.stream);
+}
+
+int tb200_msm_g1(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, unsigned flags, uint64_t out_xy[12]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out_xy || (n && (!bases_xy || !scalars))) return fail(TB200_E_ARG, "null pointer");
+  CU(cudaSetDevice(g.device));
+  uint4 *d_b = nullptr, *d_s = nullptr;
+  if (n) {
+    CU(cudaMallocAsync((void**)&d_b, n * 96, g.stream));
+    CU(cudaMallocAsync((void**)&d_s, n * 32, g.stream));
+    // scalars first: the digit/sort stages only need them, the base upload overlaps on the copy engine
+    CU(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
+  }
+  int rc = msm_dev_locked(d_b ? d_b : g.d_result, d_s ? d_s : g.d_result, n, flags, g.d_result, g.stream);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(g.h_result, g.d_result, 96, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
+    else memcpy(out_xy, g.h_result, 96);
+  }
+  if (d_b) cudaFreeAsync(d_b, g.stream);
+  if (d_s) cudaFreeAsync(d_s, g.stream);
+  return rc;
+}
+
+// ---- SRS / batch ----------------------------------------------------------------------------------------------------
+int tb200_srs_load(const uint64_t* bases_xy, size_t n, int window_bits, tb200_srs_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || !bases_xy || n == 0 || n >= (1u << 24)) return fail(TB200_E_ARG, "bad SRS arguments (n = %zu)", n);
+  CU(cudaSetDevice(g.device));
+  tb200_srs* s = new tb200_srs();
+  s->n = (uint32_t)n;
+  s->c = (window_bits >= 3 && window_bits <= 16) ? window_bits : pick_c_batch(n);
+  s->W = num_windows(s->c);
+  uint4* d_b = nullptr;
+  cudaError_t e = cudaMalloc((void**)&s->table, (size_t)s->W * n * 96);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_b, n * 96);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, g.stream);
+  if (e != cudaSuccess) {
+    if (s->table) cudaFree(s->table);
+    if (d_b) cudaFree(d_b);
+    delete s;
+    return fail((int)e, "SRS upload failed: %s", cudaGetErrorString(e));
+  }
+  k_srs_tables<<<cdiv(n, 128), 128, 0, g.stream>>>(d_b, (uint32_t)n, s->c, s->W, s->table);
+  g_launches++;
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  cudaFree(d_b);
+  if (e != cudaSuccess) {
+    cudaFree(s->table);
+    delete s;
+    return fail((int)e, "SRS table kernel failed: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return 0;
+}
+int tb200_srs_free(tb200_srs_t srs) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!srs) return fail(TB200_E_ARG, "null SRS handle");
+  if (g.ready) {
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(g.stream);
+    cudaFree(srs->table);
+  }
+  delete srs;
+  return 0;
+}
+size_t tb200_srs_size(tb200_srs_t srs) { return srs ? srs->n : 0; }
+
+// rows are processed in chunks that respect the per-pass limits of the pipeline
+static int batch_dev_locked(tb200_srs_t srs, const uint32_t* d_scalars, size_t rows, size_t cols, long long rs,
+                            long long cs, unsigned flags, uint4* d_out, cudaStream_t st) {
+  if (cols > srs->n) return fail(TB200_E_ARG, "cols = %zu exceeds the SRS size %u", cols, srs->n);
+  if (((uintptr_t)d_scalars | (uintptr_t)d_out) & 15) return fail(TB200_E_ARG, "device pointers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  const uint64_t per_row = (uint64_t)std::max<size_t>(cols, 1) * srs->W;
+  const uint64_t nb = 1ull << (srs->c - 1);
+  uint64_t chunk = std::min<uint64_t>({(uint64_t)rows, ((1ull << 31) - 1) / per_row, ((1ull << 30)) / nb});
+  if (chunk == 0) return fail(TB200_E_LIMIT, "a single row exceeds the per-pass limits");
+  g.marks.clear();
+  for (size_t r0 = 0; r0 < rows; r0 += chunk) {
+    uint32_t nr = (uint32_t)std::min<uint64_t>(chunk, rows - r0);
+    Plan p;
+    int rc = make_plan(p, nr, (uint32_t)cols, rs, cs, srs->c, 1, flags);
+    if (rc) return rc;
+    // entry refs are w * cols + j and the callers guarantee cols == srs->n, the stride of the window tables
+    rc = run_pipeline(p, d_scalars + 8 * (long long)r0 * rs, srs->table, d_out + 6 * r0, st);
+    if (rc) return rc;
+  }
+  return finish_marks(st);
+}
+
+int tb200_msm_g1_batch_dev(tb200_srs_t srs, const void* d_scalars, size_t rows, size_t cols, ptrdiff_t row_stride,
+                           ptrdiff_t col_stride, unsigned flags, void* d_out_xy, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!srs || (rows && (!d_out_xy || (cols && !d_scalars)))) return fail(TB200_E_ARG, "null pointer");
+  if (cols != srs->n && cols != 0)
+    return fail(TB200_E_ARG, "cols (%zu) must equal the SRS size (%u): window tables are laid out per SRS", cols,
+                srs->n);
+  CU(cudaSetDevice(g.device));
+  return batch_dev_locked(srs, (const uint32_t*)d_scalars, rows, cols, row_stride, col_stride, flags,
+                          (uint4*)d_out_xy, stream ? (cudaStream_t)stream : g.stream);
+}
+
+int tb200_msm_g1_batch(tb200_srs_t srs, const uint64_t* scalars, size_t rows, size_t cols, ptrdiff_t row_stride,
+                       ptrdiff_t col_stride, unsigned flags, uint64_t* out_xy) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!srs || (rows && (!out_xy || (cols && !scalars)))) return fail(TB200_E_ARG, "null pointer");
+  if (cols != srs->n && cols != 0)
+    return fail(TB200_E_ARG, "cols (%zu) must equal the SRS size (%u): window tables are laid out per SRS", cols,
+                srs->n);
+  if (rows == 0) return 0;
+  if (row_stride < 0 || col_stride < 0) return fail(TB200_E_ARG, "negative strides are not supported");
+  CU(cudaSetDevice(g.device));
+  // extent of the strided view in scalars
+  size_t extent = cols ? (rows - 1) * (size_t)row_stride + (cols - 1) * (size_t)col_stride + 1 : 0;
+  uint4 *d_s = nullptr, *d_o = nullptr;
+  CU(cudaMallocAsync((void**)&d_o, rows * 96, g.stream));
+  if (extent) {
+    CU(cudaMallocAsync((void**)&d_s, extent * 32, g.stream));
+    CU(cudaMemcpyAsync(d_s, scalars, extent * 32, cudaMemcpyHostToDevice, g.stream));
+  }
+  int rc = batch_dev_locked(srs, (const uint32_t*)(d_s ? d_s : d_o), rows, cols, row_stride, col_stride, flags, d_o,
+                            g.stream);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out_xy, d_o, rows * 96, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
+  }
+  if (d_s) cudaFreeAsync(d_s, g.stream);
+  cudaFreeAsync(d_o, g.stream);
+  return rc;
+}
+
+int tb200_msm_g1_batch_ptrs(tb200_srs_t srs, const uint64_t* const* row_ptrs, size_t rows, size_t cols,
+                            unsigned flags, uint64_t* out_xy) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!srs || (rows && (!out_xy || !row_ptrs))) return fail(TB200_E_ARG, "null pointer");
+  if (cols != srs->n && cols != 0)
+    return fail(TB200_E_ARG, "cols (%zu) must equal the SRS size (%u)", cols, srs->n);
+  if (rows == 0) return 0;
+  CU(cudaSetDevice(g.device));
+  uint4 *d_s = nullptr, *d_o = nullptr;
+  CU(cudaMallocAsync((void**)&d_o, rows * 96, g.stream));
+  if (cols) {
+    CU(cudaMallocAsync((void**)&d_s, rows * cols * 32, g.stream));
+    for (size_t i = 0; i < rows; i++) {
+      if (!row_ptrs[i]) {
+        cudaFreeAsync(d_s, g.stream);
+        cudaFreeAsync(d_o, g.stream);
+        return fail(TB200_E_ARG, "row pointer %zu is null", i);
+      }
+      CU(cudaMemcpyAsync((char*)d_s + i * cols * 32, row_ptrs[i], cols * 32, cudaMemcpyHostToDevice, g.stream));
+    }
+  }
+  int rc = batch_dev_locked(srs, (const uint32_t*)(d_s ? d_s : d_o), rows, cols, (long long)cols, 1, flags, d_o,
+                            g.stream);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out_xy, d_o, rows * 96, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
+  }
+  if (d_s) cudaFreeAsync(d_s, g.stream);
+  cudaFreeAsync(d_o, g.stream);
+  return rc;
+}
+
+// ---- MIPP -------------------------------------------------------------------------------------------------------
+int tb200_mipp_g1_begin(const uint64_t* a_xy, const uint64_t* y, size_t n, unsigned flags, tb200_mipp_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || !a_xy || !y || n == 0 || (n & (n - 1)) || n >= (1u << 28))
+    return fail(TB200_E_ARG, "MIPP vectors must have a power-of-two length (got %zu)", n);
+  CU(cudaSetDevice(g.device));
+  tb200_mipp* h = new tb200_mipp();
+  h->n = (uint32_t)n;
+  h->flags = flags;
+  cudaError_t e = cudaMalloc((void**)&h->a, n * 96);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->y, n * 32);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->scal, 64);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->a, a_xy, n * 96, cudaMemcpyHostToDevice, g.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->y, y, n * 32, cudaMemcpyHostToDevice, g.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  if (e != cudaSuccess) {
+    cudaFree(h->a);
+    cudaFree(h->y);
+    cudaFree(h->scal);
+    delete h;
+    return fail((int)e, "MIPP upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return 0;
+}
+size_t tb200_mipp_g1_len(tb200_mipp_t h) { return h ? h->n : 0; }
+
+int tb200_mipp_g1_cross(tb200_mipp_t h, uint64_t comm_u_l[12], uint64_t comm_u_r[12]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!h || !comm_u_l || !comm_u_r) return fail(TB200_E_ARG, "null pointer");
+  if (h->n < 2) return fail(TB200_E_STATE, "MIPP vectors are already folded to length 1");
+  CU(cudaSetDevice(g.device));
+  const uint32_t split = h->n / 2;
+  // comm_u_l = MSM(a[:split], y[split:]), comm_u_r = MSM(a[split:], y[:split])   (src/mipp.rs:82-84)
+  int rc = msm_dev_locked(h->a, h->y + 8 * (size_t)split, split, h->flags, g.d_result, g.stream);
+  if (rc) return rc;
+  rc = msm_dev_locked(h->a + 6 * (size_t)split, h->y, split, h->flags, g.d_result + 6, g.stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(g.h_result, g.d_result, 192, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  memcpy(comm_u_l, g.h_result, 96);
+  memcpy(comm_u_r, (char*)g.h_result + 96, 96);
+  return 0;
+}
+
+int tb200_mipp_g1_fold(tb200_mipp_t h, const uint64_t c[4], const uint64_t c_inv[4]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!h || !c || !c_inv) return fail(TB200_E_ARG, "null pointer");
+  if (h->n < 2) return fail(TB200_E_STATE, "MIPP vectors are already folded to length 1");
+  CU(cudaSetDevice(g.device));
+  const uint32_t split = h->n / 2;
+  memcpy(g.h_result, c, 32);
+  memcpy((char*)g.h_result + 32, c_inv, 32);
+  CU(cudaMemcpyAsync(h->scal, g.h_result, 64, cudaMemcpyHostToDevice, g.stream));
+  const int mont = (h->flags & TB200_SCALARS_MONT) ? 1 : 0;
+  LAUNCH(k_compress_g1, cdiv(split, 128), 128, g.stream, h->a, split, h->scal, mont);
+  LAUNCH(k_compress_fr, cdiv(split, 128), 128, g.stream, h->y, split, h->scal + 8, mont);
+  CU(cudaStreamSynchronize(g.stream));
+  h->n = split;
+  return 0;
+}
+
+int tb200_mipp_g1_read(tb200_mipp_t h, uint64_t* a_xy, uint64_t* y) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!h) return fail(TB200_E_ARG, "null handle");
+  CU(cudaSetDevice(g.device));
+  if (a_xy) CU(cudaMemcpyAsync(a_xy, h->a, (size_t)h->n * 96, cudaMemcpyDeviceToHost, g.stream));
+  if (y) CU(cudaMemcpyAsync(y, h->y, (size_t)h->n * 32, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+int tb200_mipp_g1_end(tb200_mipp_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!h) return fail(TB200_E_ARG, "null handle");
+  if (g.ready) {
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(g.stream);
+    cudaFree(h->a);
+    cudaFree(h->y);
+    cudaFree(h->scal);
+  }
+  delete h;
+  return 0;
+}
+
+int tb200_compress_g1(uint64_t* vec_xy, size_t split, const uint64_t scaler[4], unsigned flags) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!vec_xy || !scaler) return fail(TB200_E_ARG, "null pointer");
+  if (split == 0) return 0;
+  if (split >= (1u << 27)) return fail(TB200_E_LIMIT, "split too large");
+  CU(cudaSetDevice(g.device));
+  uint4* d_v = nullptr;
+  uint32_t* d_k = nullptr;
+  CU(cudaMallocAsync((void**)&d_v, 2 * split * 96, g.stream));
+  CU(cudaMallocAsync((void**)&d_k, 32, g.stream));
+  CU(cudaMemcpyAsync(d_v, vec_xy, 2 * split * 96, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(d_k, scaler, 32, cudaMemcpyHostToDevice, g.stream));
+  LAUNCH(k_compress_g1, cdiv(split, 128), 128, g.stream, d_v, (uint32_t)split, d_k,
+         (flags & TB200_SCALARS_MONT) ? 1 : 0);
+  CU(cudaMemcpyAsync(vec_xy, d_v, split * 96, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  cudaFreeAsync(d_v, g.stream);
+  cudaFreeAsync(d_k, g.stream);
+  return 0;
+}
+
+// ---- group utilities ---------------------------------------------------------------------------------------------
+int tb200_g1_sum_dev(const void* d_pts_xy, size_t n, void* d_out_xy, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_out_xy || (n && !d_pts_xy)) return fail(TB200_E_ARG, "null pointer");
+  if (n >= (1u << 20)) return fail(TB200_E_LIMIT, "tb200_g1_sum is meant for a handful of partial results");
+  CU(cudaSetDevice(g.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+  LAUNCH(k_g1_sum, 1, 32, st, (const uint4*)d_pts_xy, (uint32_t)n, (uint4*)d_out_xy);
+  return 0;
+}
+int tb200_g1_sum(const uint64_t* pts_xy, size_t n, uint64_t out_xy[12]) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (need_ready()) return TB200_E_STATE;
+    if (!out_xy || (n && !pts_xy)) return fail(TB200_E_ARG, "null pointer");
+    if (n > 128) return fail(TB200_E_LIMIT, "tb200_g1_sum (host form) takes at most 128 points");
+    CU(cudaSetDevice(g.device));
+    if (n) CU(cudaMemcpyAsync(g.d_result + 6, pts_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
+    LAUNCH(k_g1_sum, 1, 32, g.stream, g.d_result + 6, (uint32_t)n, g.d_result);
+    CU(cudaMemcpyAsync(g.h_result, g.d_result, 96, cudaMemcpyDeviceToHost, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+    memcpy(out_xy, g.h_result, 96);
+  }
+  return 0;
+}
+int tb200_g1_outer_sum_dev(const void* d_a_xy, size_t na, const void* d_b_xy, size_t nb, void* d_out_xy,
+                           void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_a_xy || !d_b_xy || !d_out_xy || na == 0 || nb == 0) return fail(TB200_E_ARG, "bad arguments");
+  if ((uint64_t)na * nb >= (1ull << 31)) return fail(TB200_E_LIMIT, "outer sum too large");
+  CU(cudaSetDevice(g.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+  LAUNCH(k_g1_outer_sum, cdiv((uint64_t)na * nb, 128), 128, st, (const uint4*)d_a_xy, (uint32_t)na,
+         (const uint4*)d_b_xy, (uint32_t)nb, (uint4*)d_out_xy);
+  return 0;
+}
+
+// ---- microbenchmarks / unit-test hooks ------------------------------------------------------------------------------
+int tb200_int_pipe_peak(int kind, int iters, double* out_per_s) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out_per_s || iters <= 0 || kind < 0 || kind > 2) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(g.device));
+  const int threads = kind == 2 ? 128 : 256;
+  const int blocks = g.sms * (kind == 2 ? 3 : 8);
+  void* sink = nullptr;
+  CU(cudaMalloc(&sink, (size_t)blocks * threads * 8));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; rep++) {  // first repetition warms up
+    CU(cudaEventRecord(e0, g.stream));
+    if (kind == 2) LAUNCH(k_fq_mul_peak, blocks, threads, g.stream, iters, 12345u, (uint32_t*)sink);
+    else LAUNCH(k_int_pipe, blocks, threads, g.stream, kind, iters, 12345u, (uint64_t*)sink);
+    CU(cudaEventRecord(e1, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+  }
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  double ops = (double)blocks * threads * (double)iters * (kind == 2 ? 2.0 : 64.0);
+  *out_per_s = ops / (ms * 1e-3);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return 0;
+}
+
+}  // extern "C"
+
+template <class F>
+static int with_buffers(const void* a, size_t abytes, const void* b, size_t bbytes, void* o1, size_t o1bytes,
+                        void* o2, size_t o2bytes, F&& launch) {
+  char *d_a = nullptr, *d_b = nullptr, *d_o1 = nullptr, *d_o2 = nullptr;
+  CU(cudaMalloc((void**)&d_a, std::max<size_t>(abytes, 16)));
+  CU(cudaMalloc((void**)&d_b, std::max<size_t>(bbytes, 16)));
+  CU(cudaMalloc((void**)&d_o1, std::max<size_t>(o1bytes, 16)));
+  CU(cudaMalloc((void**)&d_o2, std::max<size_t>(o2bytes, 16)));
+  CU(cudaMemcpy(d_a, a, abytes, cudaMemcpyHostToDevice));
+  if (b) CU(cudaMemcpy(d_b, b, bbytes, cudaMemcpyHostToDevice));
+  int rc = launch(d_a, d_b, d_o1, d_o2);
+  if (rc == 0) {
+    CU(cudaStreamSynchronize(g.stream));
+    CU(cudaMemcpy(o1, d_o1, o1bytes, cudaMemcpyDeviceToHost));
+    if (o2) CU(cudaMemcpy(o2, d_o2, o2bytes, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_a);
+  cudaFree(d_b);
+  cudaFree(d_o1);
+  cudaFree(d_o2);
+  return rc;
+}
+
+extern "C" {
+
+int tb200_test_fq_mul(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!a || !b || !out || n == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(g.device));
+  return with_buffers(a, n * 48, b, n * 48, out, n * 48, nullptr, 0, [&](char* da, char* db, char* d1, char*) {
+    LAUNCH(k_test_fq_mul, cdiv(n, 128), 128, g.stream, (const uint32_t*)da, (const uint32_t*)db, (uint32_t)n,
+           (uint32_t*)d1);
+    return 0;
+  });
+}
+int tb200_test_fq_addsub(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_add, uint64_t* out_sub) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!a || !b || !out_add || !out_sub || n == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(g.device));
+  return with_buffers(a, n * 48, b, n * 48, out_add, n * 48, out_sub, n * 48,
+                      [&](char* da, char* db, char* d1, char* d2) {
+                        LAUNCH(k_test_fq_addsub, cdiv(n, 128), 128, g.stream, (const uint32_t*)da,
+                               (const uint32_t*)db, (uint32_t)n, (uint32_t*)d1, (uint32_t*)d2);
+                        return 0;
+                      });
+}
+int tb200_test_g1_add(const uint64_t* p_xy, const uint64_t* q_xy, size_t n, uint64_t* out_xy) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!p_xy || !q_xy || !out_xy || n == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(g.device));
+  return with_buffers(p_xy, n * 96, q_xy, n * 96, out_xy, n * 96, nullptr, 0,
+                      [&](char* da, char* db, char* d1, char*) {
+                        LAUNCH(k_test_g1_add, cdiv(n, 64), 64, g.stream, (const uint4*)da, (const uint4*)db,
+                               (uint32_t)n, (uint4*)d1);
+                        return 0;
+                      });
+}
+int tb200_test_g1_mul(const uint64_t* p_xy, const uint64_t* k, size_t n, uint64_t* out_xy) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!p_xy || !k || !out_xy || n == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(g.device));
+  return with_buffers(p_xy, n * 96, k, n * 32, out_xy, n * 96, nullptr, 0,
+                      [&](char* da, char* db, char* d1, char*) {
+                        LAUNCH(k_test_g1_mul, cdiv(n, 64), 64, g.stream, (const uint4*)da, (const uint32_t*)db,
+                               (uint32_t)n, (uint4*)d1);
+                        return 0;
+                      });
+}
+
+}  // extern "C"

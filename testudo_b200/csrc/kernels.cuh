@@ -1,0 +1,608 @@
+// MSM pipeline kernels (sm_100a). One pipeline serves every reference call site:
+//
+//   scalars --k_digits<COUNT>--> bucket histogram --k_scan*--> bucket_start[] --k_digits<SCATTER>--> entries[]
+//   entries[] --k_accumulate--> buckets[] (+ heads[]) --k_fixup--> buckets[] --k_reduce_pass*--> group sums
+//   group sums --k_finalize_single (Horner over windows) | k_finalize_batch--> canonical affine results
+//
+// A "group" is a bucket set that reduces to one point: a window of a single MSM (group sums are combined with
+// 2^(c*w) by Horner), or a whole row of a shared-base batch (window tables 2^(c*w)*G_j are precomputed, so all
+// windows of a row share one bucket set -- SURVEY.md App. D).
+//
+// entries[] holds (sign << 31 | point_ref) sorted by global bucket id = group * nb + |digit| - 1, nb = 2^(c-1).
+// The sort is a counting sort: histogram with L2 atomics, exclusive scan, scatter with returning atomics. The
+// order inside a bucket is arbitrary; the result does not depend on it (group addition is commutative and every
+// output is normalised to the canonical affine point).
+//
+// k_accumulate is the hot kernel (>95% of the time at 2^24): it is load-balanced by construction -- every thread
+// owns exactly K consecutive entries of the sorted array regardless of bucket boundaries (robust against the
+// skewed scalar distributions of real witnesses) and does one XYZZ mixed addition
+// (8M+2S, 2750 IMAD.WIDE) per entry.
+#pragma once
+#include "digits.cuh"
+#include "g1.cuh"
+
+namespace tb {
+
+// ------------------------------------------------------------------------------------------------------------
+// vectorised global <-> register moves (16-byte accesses; all buffers are 16-byte aligned)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_fq2_nc(Affine& p, const uint4* __restrict__ src) {
+  uint32_t* d = p.x.l;  // x and y are contiguous: 24 words
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    uint4 v = __ldg(src + i);
+    d[4 * i + 0] = v.x;
+    d[4 * i + 1] = v.y;
+    d[4 * i + 2] = v.z;
+    d[4 * i + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void load_affine(Affine& p, const uint4* src) {
+  uint32_t* d = p.x.l;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    uint4 v = src[i];
+    d[4 * i + 0] = v.x;
+    d[4 * i + 1] = v.y;
+    d[4 * i + 2] = v.z;
+    d[4 * i + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void store_affine(uint4* dst, const Affine& p) {
+  const uint32_t* s = p.x.l;
+#pragma unroll
+  for (int i = 0; i < 6; i++) dst[i] = make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
+}
+__device__ __forceinline__ void load_xyzz(Xyzz& p, const uint4* src) {
+  uint32_t* d = p.x.l;  // x, y, zz, zzz contiguous: 48 words
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    uint4 v = src[i];
+    d[4 * i + 0] = v.x;
+    d[4 * i + 1] = v.y;
+    d[4 * i + 2] = v.z;
+    d[4 * i + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void store_xyzz(uint4* dst, const Xyzz& p) {
+  const uint32_t* s = p.x.l;
+#pragma unroll
+  for (int i = 0; i < 12; i++) dst[i] = make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
+}
+static_assert(sizeof(Affine) == 96 && sizeof(Xyzz) == 192, "packed layouts");
+
+// out-of-line group operations for the non-hot kernels (keeps their code small; they are latency-, not
+// throughput-bound)
+__device__ __noinline__ void xyzz_add_ni(Xyzz* p, const Xyzz* q) { xyzz_add(*p, *q); }
+__device__ __noinline__ void xyzz_dbl_ni(Xyzz* p) { xyzz_dbl(*p); }
+__device__ __noinline__ void xyzz_madd_ni(Xyzz* p, const Affine* q) { xyzz_madd(*p, *q); }
+__device__ __noinline__ void xyzz_to_affine_ni(Affine* r, const Xyzz* p) { xyzz_to_affine(*r, *p); }
+
+// ------------------------------------------------------------------------------------------------------------
+// geometry of one MSM call
+// ------------------------------------------------------------------------------------------------------------
+struct MsmGeom {
+  uint32_t rows, cols;          // single MSM: rows = 1, cols = n
+  long long row_stride, col_stride;  // in scalars (32 bytes)
+  int c, W;                     // window bits, windows per scalar
+  uint32_t nb;                  // buckets per group = 2^(c-1)
+  uint32_t groups;              // single: W; batch: rows
+  int batch;                    // 1: shared-base batch (group = row, ref = w*cols + j); 0: single (group = w, ref = j)
+  int mont;                     // scalars are Montgomery-form Fr
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// digits: histogram and scatter share one body
+// ------------------------------------------------------------------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ scalars, MsmGeom g,
+                                                uint32_t* __restrict__ counters, uint32_t* __restrict__ entries) {
+  const uint64_t total = (uint64_t)g.rows * g.cols;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t row, col;
+    if (g.col_stride == 1 || g.rows == 1) {  // columns are the unit-stride dimension
+      row = (uint32_t)(t / g.cols);
+      col = (uint32_t)(t % g.cols);
+    } else {  // rows are (un-transposed sqrt_pst matrix: Z[(j << m_col) | i])
+      col = (uint32_t)(t / g.rows);
+      row = (uint32_t)(t % g.rows);
+    }
+    const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * ((long long)row * g.row_stride +
+                                                                   (long long)col * g.col_stride));
+    uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+    uint32_t s[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    if (g.mont) {
+      uint32_t cnv[8];
+      mont_to_canonical<FrParams>(cnv, s);
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = cnv[i];
+    }
+    if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) continue;  // zero scalar: nothing to add
+    DigitIter it(s, g.c);
+    for (int w = 0; w < g.W; w++) {
+      int32_t d = it.next(w == g.W - 1);
+      if (d == 0) continue;
+      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      uint32_t group = g.batch ? row : (uint32_t)w;
+      uint32_t bucket = group * g.nb + (mag - 1);
+      if (SCATTER) {
+        uint32_t ref = g.batch ? (uint32_t)w * g.cols + col : col;
+        uint32_t pos = atomicAdd(&counters[bucket], 1u);
+        entries[pos] = ref | (d < 0 ? 0x80000000u : 0u);
+      } else {
+        atomicAdd(&counters[bucket], 1u);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// exclusive scan of the bucket histogram (3 kernels; B <= 2^31). SCAN_TILE items per block.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total) {
+  __shared__ uint32_t warp_sums[SCAN_THREADS / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += n;
+  }
+  if (lane == 31) warp_sums[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t ws = lane < SCAN_THREADS / 32 ? warp_sums[lane] : 0;
+    uint32_t winc = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += n;
+    }
+    if (lane < SCAN_THREADS / 32) warp_sums[lane] = winc - ws;  // exclusive warp offsets
+    if (lane == 31) *total = winc;                              // lane 31 holds the block total (>= 16 warps padded)
+  }
+  __syncthreads();
+  uint32_t r = warp_sums[wid] + inc - v;
+  __syncthreads();
+  return r;
+}
+
+// pass 1: per-tile totals
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t* __restrict__ in, uint32_t n,
+                                                                 uint32_t* __restrict__ tile_sums) {
+  __shared__ uint32_t total;
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) s += (base + i < n) ? in[base + i] : 0u;
+  block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// pass 2: scan the tile totals in place (single block, loops over chunks)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_offsets(uint32_t* __restrict__ tile_sums, uint32_t ntiles,
+                                                                    uint32_t* __restrict__ grand_total) {
+  __shared__ uint32_t total;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < ntiles; base += SCAN_THREADS) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < ntiles ? tile_sums[i] : 0u;
+    uint32_t ex = block_exclusive_scan(v, &total);
+    if (i < ntiles) tile_sums[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *grand_total = carry;
+}
+// pass 3: out[i] = exclusive prefix; also out[n] = total (written by the last tile)
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __restrict__ in, uint32_t n,
+                                                             const uint32_t* __restrict__ tile_offsets,
+                                                             uint32_t* __restrict__ out, uint32_t* __restrict__ out2) {
+  __shared__ uint32_t total;
+  const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    v[i] = (base + i < n) ? in[base + i] : 0u;
+    s += v[i];
+  }
+  uint32_t ex = block_exclusive_scan(s, &total) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    if (base + i < n) {
+      out[base + i] = ex;
+      out2[base + i] = ex;  // second copy: the scatter cursors
+    }
+    ex += v[i];
+  }
+  if (base <= n && n < base + SCAN_ITEMS) out[n] = ex - 0;  // ex == total prefix at position n
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// bucket accumulation -- the hot kernel
+// ------------------------------------------------------------------------------------------------------------
+// Thread t owns entries [t*K, min((t+1)*K, M)). Runs of equal bucket id inside the segment are summed with
+// mixed additions. A run that begins at its bucket's first entry is written to buckets[b] (each non-empty
+// bucket has exactly one such writer); a run that continues a bucket begun in an earlier segment is the
+// thread's "head" and goes to heads[t] / head_bucket[t] for k_fixup.
+constexpr int ACC_THREADS = 128;
+
+__global__ void __launch_bounds__(ACC_THREADS, 3)
+    k_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ bucket_start, uint32_t B,
+                 uint32_t K, const uint4* __restrict__ points, uint4* __restrict__ buckets,
+                 uint4* __restrict__ heads, int32_t* __restrict__ head_bucket) {
+  const uint32_t M = __ldg(bucket_start + B);  // number of sorted entries: only known on the device
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t lo64 = t * K;
+  if (lo64 >= M) return;
+  const uint32_t lo = (uint32_t)lo64;
+  const uint32_t hi = (uint32_t)min((uint64_t)M, lo64 + K);
+  // b = last bucket with bucket_start[b] <= lo (it is non-empty because bucket_start[b+1] > lo)
+  uint32_t l = 0, r = B;  // invariant: bucket_start[l] <= lo < bucket_start[r]  (bucket_start[B] = M > lo)
+  while (r - l > 1) {
+    uint32_t mid = l + ((r - l) >> 1);
+    if (__ldg(bucket_start + mid) <= lo) l = mid;
+    else r = mid;
+  }
+  uint32_t b = l;
+  bool is_head = __ldg(bucket_start + b) < lo;
+  head_bucket[t] = is_head ? (int32_t)b : -1;
+  uint32_t end_b = __ldg(bucket_start + b + 1);
+  Xyzz acc;
+  xyzz_set_inf(acc);
+  for (uint32_t pos = lo; pos < hi; pos++) {
+    if (pos == end_b) {  // bucket b complete (or its part inside this segment)
+      store_xyzz(is_head ? heads + 12 * t : buckets + 12 * (uint64_t)b, acc);
+      is_head = false;
+      xyzz_set_inf(acc);
+      do {
+        b++;
+        end_b = __ldg(bucket_start + b + 1);
+      } while (end_b == pos);  // skip empty buckets
+    }
+    const uint32_t e = __ldg(entries + pos);
+    Affine q;
+    load_fq2_nc(q, points + 6 * (uint64_t)(e & 0x7fffffffu));
+    if (e >> 31) fq_neg(q.y, q.y);
+    xyzz_madd(acc, q);
+  }
+  store_xyzz(is_head ? heads + 12 * t : buckets + 12 * (uint64_t)b, acc);
+}
+
+// buckets[b] += heads of all later segments that lie inside bucket b. One thread per first head of a bucket.
+__global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ bucket_start, uint32_t B, uint32_t K,
+                                               uint4* __restrict__ buckets, const uint4* __restrict__ heads,
+                                               const int32_t* __restrict__ head_bucket) {
+  const uint32_t M = bucket_start[B];
+  const uint64_t S = ((uint64_t)M + K - 1) / K;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0 || t >= S) return;
+  const int32_t hb = head_bucket[t];
+  if (hb < 0) return;
+  const uint32_t s = bucket_start[hb];
+  if ((t - 1) * (uint64_t)K > s) return;  // segment t-1 is a head of the same bucket: not the first head
+  const uint32_t e = bucket_start[hb + 1];
+  Xyzz acc, h;
+  load_xyzz(acc, buckets + 12 * (uint64_t)hb);
+  for (uint64_t u = t; u < S && u * K < e; u++) {
+    load_xyzz(h, heads + 12 * u);
+    xyzz_add_ni(&acc, &h);
+  }
+  store_xyzz(buckets + 12 * (uint64_t)hb, acc);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// bucket reduction: sum_k k * B_k per group by hierarchical running sums
+// ------------------------------------------------------------------------------------------------------------
+// Elements of a level are (S, W) pairs describing a span of `ell` original buckets: S = plain sum, W = sum with
+// local weights 1..ell. Combining L consecutive elements i = 0..L-1 into a span of L*ell buckets:
+//     S' = sum S_i,   W' = sum W_i + ell * sum_i i * S_i      (sum_i i*S_i by a descending running sum)
+// Level 0 reads raw buckets (S_i = W_i = B_i, ell = 1; empty buckets are identified by their zero count).
+__global__ void __launch_bounds__(128) k_reduce_pass(const uint4* __restrict__ inS, const uint4* __restrict__ inW,
+                                                     const uint32_t* __restrict__ bucket_start /* level 0 only */,
+                                                     uint4* __restrict__ outS, uint4* __restrict__ outW, uint32_t L,
+                                                     int log2_ell, uint64_t total_out) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_out) return;
+  Xyzz run, acc, wsum, x;
+  xyzz_set_inf(run);
+  xyzz_set_inf(acc);
+  xyzz_set_inf(wsum);
+  for (int i = (int)L - 1; i >= 0; i--) {
+    const uint64_t idx = t * L + i;
+    bool empty = false;
+    if (bucket_start) empty = bucket_start[idx + 1] == bucket_start[idx];
+    if (!empty) {
+      load_xyzz(x, inS + 12 * idx);
+      xyzz_add_ni(&run, &x);
+      if (inW) {
+        load_xyzz(x, inW + 12 * idx);
+        xyzz_add_ni(&wsum, &x);
+      }
+    }
+    if (i > 0) xyzz_add_ni(&acc, &run);
+  }
+  store_xyzz(outS + 12 * t, run);
+  for (int k = 0; k < log2_ell; k++) xyzz_dbl_ni(&acc);
+  if (inW) xyzz_add_ni(&acc, &wsum);
+  else xyzz_add_ni(&acc, &run);
+  store_xyzz(outW + 12 * t, acc);
+}
+
+// single MSM: result = sum_w 2^(c*w) * Wsum[w]  (Horner, high window first), then canonical affine
+__global__ void k_finalize_single(const uint4* __restrict__ group_w, int W, int c, uint4* __restrict__ out_affine) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Xyzz total, x;
+  xyzz_set_inf(total);
+  for (int w = W - 1; w >= 0; w--) {
+    load_xyzz(x, group_w + 12 * w);
+    xyzz_add_ni(&total, &x);
+    if (w > 0)
+      for (int k = 0; k < c; k++) xyzz_dbl_ni(&total);
+  }
+  Affine a;
+  xyzz_to_affine_ni(&a, &total);
+  store_affine(out_affine, a);
+}
+// batch: every group sum is a finished row commitment; normalise each to affine
+__global__ void __launch_bounds__(128) k_finalize_batch(const uint4* __restrict__ group_w, uint32_t groups,
+                                                        uint4* __restrict__ out_affine) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= groups) return;
+  Xyzz x;
+  load_xyzz(x, group_w + 12 * (uint64_t)t);
+  Affine a;
+  xyzz_to_affine_ni(&a, &x);
+  store_affine(out_affine + 6 * (uint64_t)t, a);
+}
+// n == 0 / all-zero scalars shortcut and generic "write identity"
+__global__ void k_write_identity(uint4* out_affine, uint32_t count) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count * 6) out_affine[t] = make_uint4(0, 0, 0, 0);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// SRS window tables: table[w * n + j] = 2^(c*w) * G_j  (affine), w < W
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_srs_tables(const uint4* __restrict__ bases, uint32_t n, int c, int W,
+                                                    uint4* __restrict__ table) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Affine g;
+  load_affine(g, bases + 6 * (uint64_t)j);
+  store_affine(table + 6 * (uint64_t)j, g);
+  Xyzz p;
+  xyzz_from_affine(p, g);
+  for (int w = 1; w < W; w++) {
+    for (int k = 0; k < c; k++) xyzz_dbl_ni(&p);
+    Affine a;
+    xyzz_to_affine_ni(&a, &p);
+    store_affine(table + 6 * ((uint64_t)w * n + j), a);
+    xyzz_from_affine(p, a);  // continue from the normalised point (ZZ = 1 keeps doublings cheap and exact)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// MIPP fold (src/mipp.rs:354-383): a_l[i] += c * a_r[i] (affine out), y_l[i] += c_inv * y_r[i]
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_compress_g1(uint4* __restrict__ a, uint32_t split,
+                                                     const uint32_t* __restrict__ scaler /* 8 limbs */, int mont) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= split) return;
+  uint32_t k[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) k[j] = scaler[j];
+  if (mont) {
+    uint32_t cnv[8];
+    mont_to_canonical<FrParams>(cnv, k);
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = cnv[j];
+  }
+  Affine l, r;
+  load_affine(l, a + 6 * (uint64_t)i);
+  load_affine(r, a + 6 * ((uint64_t)split + i));
+  Xyzz acc;
+  xyzz_set_inf(acc);
+  bool started = false;
+  for (int limb = 7; limb >= 0; limb--) {
+    for (int bit = 31; bit >= 0; bit--) {
+      if (started) xyzz_dbl_ni(&acc);
+      if ((k[limb] >> bit) & 1) {
+        xyzz_madd_ni(&acc, &r);
+        started = true;
+      }
+    }
+  }
+  xyzz_madd_ni(&acc, &l);
+  Affine o;
+  xyzz_to_affine_ni(&o, &acc);
+  store_affine(a + 6 * (uint64_t)i, o);
+}
+// y_l[i] += s * y_r[i] in Fr. Representation-agnostic for Montgomery inputs; for canonical inputs the scalar is
+// first lifted to Montgomery form (s * R) so that mont_mul(sR, y) = s*y stays canonical.
+__global__ void __launch_bounds__(128) k_compress_fr(uint32_t* __restrict__ y, uint32_t split,
+                                                     const uint32_t* __restrict__ scaler, int mont) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= split) return;
+  uint32_t s[8], l[8], r[8], t[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    s[j] = scaler[j];
+    l[j] = y[8 * (uint64_t)i + j];
+    r[j] = y[8 * ((uint64_t)split + i) + j];
+  }
+  if (!mont) {
+    uint32_t r2[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r2[j] = FrParams::r2(j);
+    mont_mul<FrParams>(t, s, r2);  // s * R
+#pragma unroll
+    for (int j = 0; j < 8; j++) s[j] = t[j];
+  }
+  mont_mul<FrParams>(t, s, r);
+  mod_add<FrParams>(l, l, t);
+#pragma unroll
+  for (int j = 0; j < 8; j++) y[8 * (uint64_t)i + j] = l[j];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// small utilities
+// ------------------------------------------------------------------------------------------------------------
+// out = sum of n affine points (n small: per-GPU partial results)
+__global__ void k_g1_sum(const uint4* __restrict__ pts, uint32_t n, uint4* __restrict__ out_affine) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Xyzz acc;
+  xyzz_set_inf(acc);
+  for (uint32_t i = 0; i < n; i++) {
+    Affine p;
+    load_affine(p, pts + 6 * (uint64_t)i);
+    xyzz_madd_ni(&acc, &p);
+  }
+  Affine a;
+  xyzz_to_affine_ni(&a, &acc);
+  store_affine(out_affine, a);
+}
+// out[i * nb + j] = A_i + B_j, affine
+__global__ void __launch_bounds__(128) k_g1_outer_sum(const uint4* __restrict__ A, uint32_t na,
+                                                      const uint4* __restrict__ Bp, uint32_t nb,
+                                                      uint4* __restrict__ out) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)na * nb) return;
+  Affine a, b;
+  load_affine(a, A + 6 * (t / nb));
+  load_affine(b, Bp + 6 * (t % nb));
+  Xyzz acc;
+  xyzz_from_affine(acc, a);
+  xyzz_madd_ni(&acc, &b);
+  Affine o;
+  xyzz_to_affine_ni(&o, &acc);
+  store_affine(out + 6 * t, o);
+}
+
+// unit-test kernels ------------------------------------------------------------------------------------------
+__global__ void k_test_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t n, uint32_t* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fq x, y, z;
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    x.l[j] = a[12 * (uint64_t)i + j];
+    y.l[j] = b[12 * (uint64_t)i + j];
+  }
+  fq_mul(z, x, y);
+#pragma unroll
+  for (int j = 0; j < 12; j++) out[12 * (uint64_t)i + j] = z.l[j];
+}
+__global__ void k_test_fq_addsub(const uint32_t* a, const uint32_t* b, uint32_t n, uint32_t* oadd, uint32_t* osub) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fq x, y, z, w;
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    x.l[j] = a[12 * (uint64_t)i + j];
+    y.l[j] = b[12 * (uint64_t)i + j];
+  }
+  fq_add(z, x, y);
+  fq_sub(w, x, y);
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    oadd[12 * (uint64_t)i + j] = z.l[j];
+    osub[12 * (uint64_t)i + j] = w.l[j];
+  }
+}
+__global__ void k_test_g1_add(const uint4* p, const uint4* q, uint32_t n, uint4* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine a, b, o;
+  load_affine(a, p + 6 * (uint64_t)i);
+  load_affine(b, q + 6 * (uint64_t)i);
+  Xyzz acc;
+  xyzz_from_affine(acc, a);
+  xyzz_madd(acc, b);  // the inlined hot-loop version
+  xyzz_to_affine_ni(&o, &acc);
+  store_affine(out + 6 * (uint64_t)i, o);
+}
+__global__ void k_test_g1_mul(const uint4* p, const uint32_t* k, uint32_t n, uint4* out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine a, o;
+  load_affine(a, p + 6 * (uint64_t)i);
+  Xyzz acc;
+  xyzz_set_inf(acc);
+  bool started = false;
+  for (int limb = 7; limb >= 0; limb--) {
+    const uint32_t kw = k[8 * (uint64_t)i + limb];
+    for (int bit = 31; bit >= 0; bit--) {
+      if (started) xyzz_dbl_ni(&acc);
+      if ((kw >> bit) & 1) {
+        xyzz_madd_ni(&acc, &a);
+        started = true;
+      }
+    }
+  }
+  xyzz_to_affine_ni(&o, &acc);
+  store_affine(out + 6 * (uint64_t)i, o);
+}
+
+// integer-pipe microbenchmarks (the roofline denominator is measured) --------------------------
+// kind 0: IMAD.WIDE.U32 with 64-bit accumulate, 8 independent chains per thread
+// kind 1: 32-bit IMAD (mad.lo), 8 independent chains
+__global__ void __launch_bounds__(256) k_int_pipe(int kind, int iters, uint32_t seed, uint64_t* sink) {
+  uint32_t a = seed ^ (threadIdx.x * 2654435761u), b = seed * 40503u + blockIdx.x;
+  if (kind == 0) {
+    uint64_t c0 = a, c1 = b, c2 = a + 1, c3 = b + 1, c4 = a + 2, c5 = b + 2, c6 = a + 3, c7 = b + 3;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c0) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c1) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c2) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c3) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c4) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c5) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c6) : "r"(a), "r"(b));
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c7) : "r"(a), "r"(b));
+      }
+    }
+    sink[(uint64_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+  } else {
+    uint32_t c0 = a, c1 = b, c2 = a + 1, c3 = b + 1, c4 = a + 2, c5 = b + 2, c6 = a + 3, c7 = b + 3;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c0) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c1) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c2) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c3) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c4) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c5) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c6) : "r"(a), "r"(b));
+        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c7) : "r"(a), "r"(b));
+      }
+    }
+    sink[(uint64_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+  }
+}
+// kind 2: dependent Fq Montgomery multiplications, 2 independent chains per thread
+__global__ void __launch_bounds__(128) k_fq_mul_peak(int iters, uint32_t seed, uint32_t* sink) {
+  Fq x, y, z = fq_one(), w = fq_one();
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    x.l[j] = (seed + j * 77u + threadIdx.x) & 0x00ffffffu;
+    y.l[j] = (seed * 3u + j * 1013u + blockIdx.x) & 0x00ffffffu;
+  }
+  for (int i = 0; i < iters; i++) {
+    fq_mul(z, z, x);
+    fq_mul(w, w, y);
+  }
+  uint32_t acc = 0;
+#pragma unroll
+  for (int j = 0; j < 12; j++) acc ^= z.l[j] ^ w.l[j];
+  sink[(uint64_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+}  // namespace tb

@@ -1,0 +1,65 @@
+"""Mirror of ark-ec 0.4 `VariableBaseMSM` for `ark_bls12_377::G1Projective`.
+
+The reference reaches it at src/sqrt_pst.rs:198, src/mipp.rs:385-394, src/commitments.rs:70-86,
+src/nizk/bullet.rs:93-118,237-257, src/dense_mlpoly.rs:553-555. Same names, argument meaning and error
+behaviour; values are numpy uint64 arrays in ark's in-memory layout:
+    bases   [n, 12]  x[6] || y[6] limbs, Montgomery; all-zero row == identity
+    scalars [n, 4]   Fr limbs -- Montgomery form for `msm` / `msm_unchecked` (they take `&[Fr]`),
+                     canonical for `msm_bigint` (it takes `&[BigInt<4>]`)
+Results are the canonical affine point (`.into_affine()` of what arkworks returns) as a [12] uint64 array.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Tuple, Union
+
+import numpy as np
+
+from . import _lib
+
+
+def _u64(a, cols: int) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a.reshape(-1, cols)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def msm_bigint(bases, bigints) -> np.ndarray:
+    """`VariableBaseMSM::msm_bigint(bases, bigints)`: canonical scalars; truncates to min(len)."""
+    b = _u64(bases, 12)
+    s = _u64(bigints, 4)
+    n = min(len(b), len(s))
+    out = np.zeros(12, dtype=np.uint64)
+    _lib.check(_lib.engine().tb200_msm_g1(_ptr(b), _ptr(s), n, 0, _ptr(out)))
+    return out
+
+
+def msm_unchecked(bases, scalars) -> np.ndarray:
+    """`VariableBaseMSM::msm_unchecked(bases, scalars)`: Montgomery-form `Fr` scalars; silently truncates to
+    min(len) like arkworks (the `into_bigint()` conversion runs on the GPU)."""
+    b = _u64(bases, 12)
+    s = _u64(scalars, 4)
+    n = min(len(b), len(s))
+    out = np.zeros(12, dtype=np.uint64)
+    _lib.check(_lib.engine().tb200_msm_g1(_ptr(b), _ptr(s), n, _lib.SCALARS_MONT, _ptr(out)))
+    return out
+
+
+def msm(bases, scalars) -> Tuple[str, Union[np.ndarray, int]]:
+    """`VariableBaseMSM::msm`: ("ok", point) iff lengths match, else ("err", min_len) -- Rust's Result<_, usize>."""
+    b = _u64(bases, 12)
+    s = _u64(scalars, 4)
+    if len(b) != len(s):
+        return ("err", min(len(b), len(s)))
+    return ("ok", msm_unchecked(b, s))
+
+
+def g1_sum(points) -> np.ndarray:
+    """Sum of a handful of affine points (combining per-GPU partial MSM results)."""
+    p = _u64(points, 12)
+    out = np.zeros(12, dtype=np.uint64)
+    _lib.check(_lib.engine().tb200_g1_sum(_ptr(p), len(p), _ptr(out)))
+    return out
