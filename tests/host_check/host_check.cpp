@@ -1,7 +1,7 @@
 // Test-only shim: compiles the product's __host__ __device__ field/group headers with g++ (carry chains
 // emulated) so the algorithm structure can be checked on a CPU-only box. Not part of the product library.
 #include <cstring>
-#include "../../testudo_b200/csrc/g1.cuh"
+#include "../../testudo_b200/csrc/g1_fast.cuh"
 #include "../../testudo_b200/csrc/digits.cuh"
 using namespace tb;
 extern "C" {
@@ -46,6 +46,23 @@ void hc_scalar_mul(const uint32_t* p_aff, const uint32_t* k, uint32_t* out_aff) 
   Xyzz a; xyzz_scalar_mul(a, p, k);
   xyzz_to_affine(r, a); memcpy(out_aff, &r, 96);
 }
+// hot-loop lazy madd: acc = sum of n affine points (with sign flags), then canonical affine out. Also reports the
+// largest limb-12 headroom seen (bound check): returns 1 if any coordinate ever reached 2^383.
+int hc_madd_fast_chain(const uint32_t* pts_aff, const uint32_t* neg, int n, uint32_t* out_aff) {
+  Xyzz acc; xyzz_set_inf(acc);
+  int overflow = 0;
+  for (int i = 0; i < n; i++) {
+    Affine q; memcpy(&q, pts_aff + 24 * i, 96);
+    if (neg[i]) fq_neg(q.y, q.y);
+    xyzz_madd_fast(acc, q);
+    if ((acc.x.l[11] | acc.y.l[11] | acc.zz.l[11] | acc.zzz.l[11]) >> 31) overflow = 1;
+  }
+  xyzz_canon(acc);
+  Affine r; xyzz_to_affine(r, acc); memcpy(out_aff, &r, 96);
+  return overflow;
+}
+void hc_fq_canon(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.l, a, 48); fq_canon(x); memcpy(r, x.l, 48); }
+void hc_fq_mul_lazy(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul_lazy<FqParams>(r, a, b); }
 // signed digits of one canonical scalar with window c: out[w] in [-2^(c-1), 2^(c-1)]
 int hc_digits(const uint32_t* s, int c, int32_t* out) {
   int W = num_windows(c);

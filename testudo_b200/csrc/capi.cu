@@ -258,7 +258,11 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   LAUNCH(k_accumulate, cdiv(p.S_max, ACC_THREADS), ACC_THREADS, st, entries, starts, (uint32_t)p.B, p.K, d_points,
          buckets, heads, head_bucket);
   if (mark(st, "accumulate")) return 1;
-  LAUNCH(k_fixup, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket);
+  // a bucket can span at most S_max segments: ceil(log2(S_max)) pointer-jumping rounds cover the worst case.
+  // Rounds beyond the largest bucket are empty launches (a few microseconds each).
+  for (uint32_t round = 0; (1ull << round) < p.S_max; round++)
+    LAUNCH(k_fixup_round, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, round, heads, head_bucket);
+  LAUNCH(k_fixup_final, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket);
   if (mark(st, "fixup")) return 1;
   // hierarchical bucket reduction
   const uint4 *inS = buckets, *inW = nullptr;

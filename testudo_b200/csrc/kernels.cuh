@@ -19,7 +19,7 @@
 // (8M+2S, 2750 IMAD.WIDE) per entry.
 #pragma once
 #include "digits.cuh"
-#include "g1.cuh"
+#include "g1_fast.cuh"
 
 namespace tb {
 
@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 3)
   xyzz_set_inf(acc);
   for (uint32_t pos = lo; pos < hi; pos++) {
     if (pos == end_b) {  // bucket b complete (or its part inside this segment)
+      xyzz_canon(acc);   // the loop keeps lazily reduced coordinates; everything downstream is canonical
       store_xyzz(is_head ? heads + 12 * t : buckets + 12 * (uint64_t)b, acc);
       is_head = false;
       xyzz_set_inf(acc);
@@ -268,30 +269,53 @@ __global__ void __launch_bounds__(ACC_THREADS, 3)
     Affine q;
     load_fq2_nc(q, points + 6 * (uint64_t)(e & 0x7fffffffu));
     if (e >> 31) fq_neg(q.y, q.y);
-    xyzz_madd(acc, q);
+    xyzz_madd_fast(acc, q);
   }
+  xyzz_canon(acc);
   store_xyzz(is_head ? heads + 12 * t : buckets + 12 * (uint64_t)b, acc);
 }
 
-// buckets[b] += heads of all later segments that lie inside bucket b. One thread per first head of a bucket.
-__global__ void __launch_bounds__(128) k_fixup(const uint32_t* __restrict__ bucket_start, uint32_t B, uint32_t K,
-                                               uint4* __restrict__ buckets, const uint4* __restrict__ heads,
-                                               const int32_t* __restrict__ head_bucket) {
+// Heads of one bucket occupy consecutive segments first..last (first = smallest t with t*K > bucket_start[b]).
+// They are summed by pointer jumping: in round r, head `first + i` with i % 2^(r+1) == 0 absorbs head
+// `first + i + 2^r` (if it belongs to the same bucket). After ceil(log2(#heads)) rounds heads[first] holds the sum;
+// k_fixup_final adds it to buckets[b]. Heavy buckets (skewed witnesses: most scalars 0/1; degenerate top
+// windows) therefore cost log-depth instead of a sequential walk over thousands of partial sums.
+__global__ void __launch_bounds__(128) k_fixup_round(const uint32_t* __restrict__ bucket_start, uint32_t B,
+                                                     uint32_t K, uint32_t round, uint4* __restrict__ heads,
+                                                     const int32_t* __restrict__ head_bucket) {
   const uint32_t M = bucket_start[B];
   const uint64_t S = ((uint64_t)M + K - 1) / K;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t == 0 || t >= S) return;
   const int32_t hb = head_bucket[t];
   if (hb < 0) return;
-  const uint32_t s = bucket_start[hb];
-  if ((t - 1) * (uint64_t)K > s) return;  // segment t-1 is a head of the same bucket: not the first head
-  const uint32_t e = bucket_start[hb + 1];
+  const uint64_t first = bucket_start[hb] / K + 1;
+  const uint64_t i = t - first;
+  const uint64_t stride = 1ull << round;
+  if (i & (2 * stride - 1)) return;
+  const uint64_t u = t + stride;
+  if (u >= S || u * K >= bucket_start[hb + 1]) return;  // partner is not a head of this bucket
+  Xyzz acc, h;
+  load_xyzz(acc, heads + 12 * t);
+  load_xyzz(h, heads + 12 * u);
+  xyzz_add_ni(&acc, &h);
+  store_xyzz(heads + 12 * t, acc);
+}
+__global__ void __launch_bounds__(128) k_fixup_final(const uint32_t* __restrict__ bucket_start, uint32_t B,
+                                                     uint32_t K, uint4* __restrict__ buckets,
+                                                     const uint4* __restrict__ heads,
+                                                     const int32_t* __restrict__ head_bucket) {
+  const uint32_t M = bucket_start[B];
+  const uint64_t S = ((uint64_t)M + K - 1) / K;
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0 || t >= S) return;
+  const int32_t hb = head_bucket[t];
+  if (hb < 0) return;
+  if (t != bucket_start[hb] / K + 1) return;  // only the first head of a bucket
   Xyzz acc, h;
   load_xyzz(acc, buckets + 12 * (uint64_t)hb);
-  for (uint64_t u = t; u < S && u * K < e; u++) {
-    load_xyzz(h, heads + 12 * u);
-    xyzz_add_ni(&acc, &h);
-  }
+  load_xyzz(h, heads + 12 * t);
+  xyzz_add_ni(&acc, &h);
   store_xyzz(buckets + 12 * (uint64_t)hb, acc);
 }
 

@@ -296,9 +296,10 @@ TB_HD bool mod_eq(const uint32_t* a, const uint32_t* b) {
   return d == 0;
 }
 
-// r = a * b * R^-1 mod p.  Even/odd accumulator CIOS described in the file header.
+// r = a * b * R^-1 (mod p), NOT fully reduced: r < p + a*b/R. Even/odd accumulator CIOS described in the
+// file header. Valid for any a < 2^(32N) and b < 2^(32N) - p (the running total stays below b + p + epsilon).
 template <class P>
-TB_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+TB_HD void mont_mul_lazy(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   constexpr int N = P::N;
   static_assert(N % 2 == 0, "even limb count");
   uint32_t e[N + 1], o[N], x = 0;
@@ -376,6 +377,12 @@ TB_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   r[0] = add_cc(e[0], x, c);
 #pragma unroll
   for (int j = 1; j < N; j++) r[j] = addc_cc(e[j], o[j - 1], c);
+}
+
+// canonical product: inputs < p, output < p
+template <class P>
+TB_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  mont_mul_lazy<P>(r, a, b);
   mod_reduce_once<P>(r);
 }
 
