@@ -1,0 +1,144 @@
+"""GPU parity: sqrt_pst commit (shared-SRS batched MSM) and the G1 work of open, vs golden rows and the oracles.
+Mirrors the reference's own tests check_sqrt_poly_eval / check_sqrt_poly_commit (src/sqrt_pst.rs:277-342) as far as
+the G1 scope goes (no pairings): eval identity, commit -> open with the debug_assert identity of src/sqrt_pst.rs:206."""
+import ctypes
+import hashlib
+
+import numpy as np
+import pytest
+
+import helpers as h
+from oracle import bls12_377 as o
+from testudo_b200 import _lib, commitments, fr, sqrt_pst
+
+pytestmark = pytest.mark.gpu
+GOLD = h.load_golden("msm_golden.json")
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def fake_transcript():
+    """Deterministic stand-in for the Poseidon transcript (out of scope): hashes what the prover appends."""
+    state = hashlib.sha256(b"testudo-b200-test")
+
+    def challenge(label, points):
+        state.update(label)
+        for p in points:
+            state.update(np.asarray(p, dtype=np.uint64).tobytes())
+        return int.from_bytes(state.digest(), "little") % o.R_ORDER or 1
+
+    return challenge
+
+
+@pytest.mark.parametrize("case", GOLD["sqrt_rows"], ids=lambda c: f"nv{c['num_vars']}")
+def test_commit_rows_golden(engine, case):
+    nv = case["num_vars"]
+    m_row = nv - nv // 2
+    srs, _ = o.rand_points(1 << m_row, case["srs_seed"])
+    z = o.rand_scalars(1 << nv, case["z_seed"])
+    ck = sqrt_pst.CommitterKey.from_points(h.pts_to_np(srs))
+    poly = sqrt_pst.Polynomial.from_evaluations(h.scalars_to_np(z, mont=True))
+    comm_list, t = poly.commit(ck)
+    assert t is None
+    assert [h.pt_from_np(r) for r in comm_list] == [h.pt_unhex(r) for r in case["rows"]]
+    ck.close()
+
+
+@pytest.mark.parametrize("nv,window", [(12, 0), (13, 0), (16, 0), (12, 5), (14, 11)])
+def test_commit_vs_c_oracle(engine, oracle_c, nv, window):
+    m_col = nv // 2
+    m_row = nv - m_col
+    srs = oracle_c.gen_points(h.pts_to_np([o.mul(31 + nv, o.G)])[0], h.pts_to_np([o.mul(977, o.G)])[0], 1 << m_row)
+    z = h.np_rand_scalars(1 << nv, nv)
+    z[5] = 0; z[6] = np.array(o.to_limbs64(o.R_ORDER - 1, 4), dtype=np.uint64); z[7] = np.array([1, 0, 0, 0], dtype=np.uint64)
+    if nv == 12:
+        z[3::64] = 0          # an all-zero row -> identity commitment (zero-padded witness)
+    ck = sqrt_pst.CommitterKey.from_points(srs, window_bits=window)
+    lib = _lib.engine()
+    out = np.zeros((1 << m_col, 12), dtype=np.uint64)
+    _lib.check(lib.tb200_msm_g1_batch(ck._h, P(z), 1 << m_col, 1 << m_row, 1, 1 << m_col, 0, P(out)))
+    exp = oracle_c.msm_g1_batch(srs, z, 1 << m_col, 1 << m_row, 1, 1 << m_col)
+    assert np.array_equal(out, exp)
+    if nv == 12:
+        assert not out[3].any()
+    # the same rows handed over as separate heap buffers (what Polynomial::commit holds, src/sqrt_pst.rs:48-62)
+    rows = [np.ascontiguousarray(z[i :: 1 << m_col]) for i in range(1 << m_col)]
+    ptrs = (ctypes.c_void_p * len(rows))(*[r.ctypes.data for r in rows])
+    out2 = np.zeros_like(out)
+    _lib.check(lib.tb200_msm_g1_batch_ptrs(ck._h, ptrs, len(rows), 1 << m_row, 0, P(out2)))
+    assert np.array_equal(out2, exp)
+    ck.close()
+
+
+def test_commit_closed_form_g_pow_poly_at_t(engine):
+    """SRS g^{eq(t,x)} (ark-poly-commit setup): every row commitment is g^{p_i(t)}."""
+    nv = 10
+    m_col = m_row = 5
+    t = o.rand_scalars(m_row, 555)
+    eq = []
+    for x in range(1 << m_row):   # little-endian variable order
+        v = 1
+        for k in range(m_row):
+            v = v * (t[k] if (x >> k) & 1 else (1 - t[k])) % o.R_ORDER
+        eq.append(v)
+    srs = [o.mul(e, o.G) for e in eq]
+    z = o.rand_scalars(1 << nv, 556)
+    ck = sqrt_pst.CommitterKey.from_points(h.pts_to_np(srs))
+    poly = sqrt_pst.Polynomial.from_evaluations(h.scalars_to_np(z, mont=True))
+    comm_list, _ = poly.commit(ck)
+    for i in range(1 << m_col):
+        pit = sum(z[(j << m_col) | i] * eq[j] for j in range(1 << m_row)) % o.R_ORDER
+        assert h.pt_from_np(comm_list[i]) == o.mul(pit, o.G)
+    ck.close()
+
+
+@pytest.mark.parametrize("nv", [5, 6])
+def test_sqrt_eval_and_open_identities(engine, nv):
+    """check_sqrt_poly_eval (src/sqrt_pst.rs:277-295) + the G1 chain of check_sqrt_poly_commit (:297-342)."""
+    m_col = nv // 2
+    m_row = nv - m_col
+    z = o.rand_scalars(1 << nv, 600 + nv)
+    r = o.rand_scalars(nv, 700 + nv)
+    srs, _ = o.rand_points(1 << m_row, 800 + nv)
+    poly = sqrt_pst.Polynomial.from_evaluations(h.scalars_to_np(z, mont=True))
+    # DensePolynomial::evaluate (MSB-first variable order, src/dense_mlpoly.rs) == sqrt-layout eval
+    direct = sum(zi * fr.get_chi_i(r, i) for i, zi in enumerate(z)) % o.R_ORDER
+    assert poly.eval(r) == direct
+    ck = sqrt_pst.CommitterKey.from_points(h.pts_to_np(srs))
+    comm_list, _ = poly.commit(ck)
+    opened = poly.open(fake_transcript(), comm_list, ck, r)          # asserts c_u == commit(q) inside
+    q = fr.from_mont_words(poly.q)
+    assert h.pt_from_np(opened.u) == o.msm_naive(srs, q)
+    chis = fr.from_mont_words(poly.chis_b)
+    assert h.pt_from_np(opened.u) == o.msm_naive([h.pt_from_np(c) for c in comm_list], chis)
+    assert len(opened.mipp.comms_u) == m_col
+    ck.close()
+
+
+def test_hyrax_commit_inner_contiguous_rows(engine, oracle_c):
+    """DensePolynomial::commit_inner (src/dense_mlpoly.rs:315-329): contiguous rows over shared gens, blinds 0 and != 0."""
+    L, R = 32, 64
+    G = oracle_c.gen_points(h.pts_to_np([o.mul(5, o.G)])[0], h.pts_to_np([o.mul(13, o.G)])[0], R)
+    hpt = h.pts_to_np([o.mul(424242, o.G)])[0]
+    z = h.np_rand_scalars(L * R, 9)
+    z[:R] = 0
+    z[R: 2 * R, 1:] = 0  # small scalars (addresses / timestamps)
+    zm = h.scalars_to_np(h.np_scalars_to_ints(z), mont=True)
+    gens = commitments.MultiCommitGens(G, hpt)
+    rows = commitments.commit_inner(zm, np.zeros((L, 4), dtype=np.uint64), gens)
+    exp = oracle_c.msm_g1_batch(G, z, L, R, R, 1)
+    assert np.array_equal(rows, exp)
+    assert not rows[0].any()
+    blinds = o.rand_scalars(L, 10)
+    rows_b = commitments.commit_inner(zm, h.scalars_to_np(blinds, mont=True), gens)
+    for i in (0, 1, 17):
+        assert h.pt_from_np(rows_b[i]) == o.add(h.pt_from_np(exp[i]), o.mul(blinds[i], h.pt_from_np(hpt)))
+    # commit_slice / commit_scalar (src/commitments.rs:70-86)
+    cs = commitments.PedersenCommit.commit_slice(zm[2 * R: 3 * R], h.scalars_to_np([blinds[2]], mont=True)[0], gens)
+    assert np.array_equal(cs, rows_b[2])
+    g1 = commitments.MultiCommitGens(G[:1], hpt)
+    sc = commitments.PedersenCommit.commit_scalar(h.scalars_to_np([77], mont=True)[0], h.scalars_to_np([88], mont=True)[0], g1)
+    assert h.pt_from_np(sc) == o.add(o.mul(77, h.pt_from_np(G[0])), o.mul(88, h.pt_from_np(hpt)))
+    gens.close()

@@ -90,6 +90,8 @@ struct Ctx {
   int device = -1;
   int sms = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // base upload of host-facing calls overlaps the digit/sort stages
+  cudaEvent_t ev_points = nullptr;
   Arena arena;
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -217,7 +219,8 @@ int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs,
 }
 
 // Runs the whole pipeline on `st`. d_points: affine points indexed by entry refs. d_out: groups*96 B (batch) or 96 B.
-int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points, uint4* d_out, cudaStream_t st) {
+int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points, uint4* d_out, cudaStream_t st,
+                 cudaEvent_t points_ready = nullptr) {
   const MsmGeom& q = p.geo;
   int rc = g.arena.reserve(p.bytes);
   if (rc) return fail(rc, "workspace allocation of %zu bytes failed: %s", p.bytes, cudaGetErrorString((cudaError_t)rc));
@@ -254,6 +257,7 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   if (mark(st, "scan")) return 1;
   LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, cursors, entries);
   if (mark(st, "scatter")) return 1;
+  if (points_ready) CU(cudaStreamWaitEvent(st, points_ready, 0));  // bases may still be in flight until here
   // M is only known on the device (starts[B]); launch for the upper bound, surplus threads exit immediately
   LAUNCH(k_accumulate, cdiv(p.S_max, ACC_THREADS), ACC_THREADS, st, entries, starts, (uint32_t)p.B, p.K, d_points,
          buckets, heads, head_bucket);
@@ -325,6 +329,8 @@ int tb200_init(int device) {
   g.device = device;
   g.sms = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&g.ev_points, cudaEventDisableTiming));
   CU(cudaMalloc((void**)&g.d_result, 16384));
   CU(cudaMallocHost((void**)&g.h_result, 16384));
   g.ready = true;
@@ -343,6 +349,8 @@ void tb200_shutdown(void) {
   cudaFree(g.d_result);
   cudaFreeHost(g.h_result);
   cudaStreamDestroy(g.stream);
+  cudaStreamDestroy(g.copy_stream);
+  cudaEventDestroy(g.ev_points);
   g.ready = false;
 }
 
@@ -366,7 +374,7 @@ void tb200_set_window_bits(int c) { g.forced_c = (c >= 3 && c <= 22) ? c : 0; }
 
 // ---- single MSM -------------------------------------------------------------------------------------------------
 static int msm_dev_locked(const void* d_bases, const void* d_scalars, size_t n, unsigned flags, void* d_out,
-                          cudaStream_t st) {
+                          cudaStream_t st, cudaEvent_t points_ready = nullptr) {
   if (n >= (1ull << 31)) return fail(TB200_E_LIMIT, "n = %zu exceeds 2^31 - 1 points per call", n);
   if (((uintptr_t)d_bases | (uintptr_t)d_scalars | (uintptr_t)d_out) & 15)
     return fail(TB200_E_ARG, "device pointers must be 16-byte aligned");
@@ -376,7 +384,7 @@ static int msm_dev_locked(const void* d_bases, const void* d_scalars, size_t n, 
   while (rc == TB200_E_LIMIT && c > 3) rc = make_plan(p, 1, (uint32_t)n, 0, 1, --c, 0, flags);
   if (rc) return rc;
   g.marks.clear();
-  rc = run_pipeline(p, (const uint32_t*)d_scalars, (const uint4*)d_bases, (uint4*)d_out, st);
+  rc = run_pipeline(p, (const uint32_t*)d_scalars, (const uint4*)d_bases, (uint4*)d_out, st, points_ready);
   if (rc) return rc;
   return finish_marks(st);
 }
@@ -399,11 +407,16 @@ int tb200_msm_g1(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, un
   if (n) {
     CU(cudaMallocAsync((void**)&d_b, n * 96, g.stream));
     CU(cudaMallocAsync((void**)&d_s, n * 32, g.stream));
-    // scalars first: the digit/sort stages only need them, the base upload overlaps on the copy engine
+    // the digit/sort stages only need the scalars; the 3x larger base upload runs on the copy stream and is
+    // awaited right before the accumulation kernel
+    CU(cudaEventRecord(g.ev_points, g.stream));  // allocations done
+    CU(cudaStreamWaitEvent(g.copy_stream, g.ev_points, 0));
     CU(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, g.stream));
-    CU(cudaMemcpyAsync(d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, g.copy_stream));
+    CU(cudaEventRecord(g.ev_points, g.copy_stream));
   }
-  int rc = msm_dev_locked(d_b ? d_b : g.d_result, d_s ? d_s : g.d_result, n, flags, g.d_result, g.stream);
+  int rc = msm_dev_locked(d_b ? d_b : g.d_result, d_s ? d_s : g.d_result, n, flags, g.d_result, g.stream,
+                          n ? g.ev_points : nullptr);
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(g.h_result, g.d_result, 96, cudaMemcpyDeviceToHost, g.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);

@@ -1,0 +1,145 @@
+"""Mirror of `sqrt_pst::Polynomial` (src/sqrt_pst.rs) for the G1 work of commit / open.
+
+Same names and argument meaning as the reference; values are numpy uint64 arrays in ark's memory layout
+(Fr: [.., 4] Montgomery limbs; G1Affine: [.., 12] Montgomery limbs, all-zero == identity).
+
+What runs where:
+  * `commit`  -- the row fan-out `polys.par_iter().map(|p| MultilinearPC::commit(ck, p))` (src/sqrt_pst.rs:121-125)
+    is ONE batched GPU call over the SRS `ck.powers_of_g[0]` resident on the device. Z is kept un-transposed:
+    row i of the reference's `polys` is the strided view Z[(j << m_col) | i] (src/sqrt_pst.rs:58), which the
+    kernel reads coalesced, so `from_evaluations` costs nothing.
+  * `open`    -- M2 `msm_unchecked(comms, chis)` (src/sqrt_pst.rs:198), M3 `MultilinearPC::commit(ck, q)` (:205)
+    and the G1 part of `MippProof::prove` (:212) run on the GPU.
+  * the pairing product `t` (src/sqrt_pst.rs:131-144), the G2 opening (src/sqrt_pst.rs:225) and the Poseidon
+    transcript are OUT OF SCOPE of this engine: `commit` returns t = None, `open` returns the G1
+    results and takes the Fiat-Shamir challenges from a callback.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+from . import _lib, fr, mipp, msm
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class CommitterKey:
+    """G1 side of ark-poly-commit `CommitterKey<E>`: nv and powers_of_g[0] (2^nv points), loaded on the GPU once
+    with its window tables (the `ck` argument of src/sqrt_pst.rs:117,168)."""
+
+    def __init__(self, powers_of_g0: np.ndarray, handle, nv: int):
+        self.powers_of_g0 = powers_of_g0
+        self.nv = nv
+        self._h = handle
+
+    @classmethod
+    def from_points(cls, powers_of_g0, window_bits: int = 0) -> "CommitterKey":
+        pts = np.ascontiguousarray(powers_of_g0, dtype=np.uint64).reshape(-1, 12)
+        n = len(pts)
+        assert n & (n - 1) == 0 and n > 0, "powers_of_g[0] has 2^nv points"
+        h = ctypes.c_void_p()
+        _lib.check(_lib.engine().tb200_srs_load(_ptr(pts), n, window_bits, ctypes.byref(h)))
+        return cls(pts, h, n.bit_length() - 1)
+
+    def close(self):
+        if self._h is not None:
+            _lib.check(_lib.engine().tb200_srs_free(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pc_commit(ck: CommitterKey, evals_mont: np.ndarray) -> np.ndarray:
+    """`MultilinearPC::commit(ck, poly).g_product` for one polynomial given by its evaluations (Montgomery Fr)."""
+    z = np.ascontiguousarray(evals_mont, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((1, 12), dtype=np.uint64)
+    _lib.check(_lib.engine().tb200_msm_g1_batch(ck._h, _ptr(z), 1, len(z), len(z), 1, _lib.SCALARS_MONT, _ptr(out)))
+    return out[0]
+
+
+@dataclass
+class OpenG1:
+    """G1 outputs of `Polynomial::open`: U.g_product, the commitment to q (debug cross-check) and the MIPP G1 data."""
+    u: np.ndarray
+    comm_q: np.ndarray
+    mipp: "mipp.MippProofG1"
+
+
+class Polynomial:
+    def __init__(self, z: np.ndarray, m: int, odd: int):
+        self.Z = z            # [2^n, 4] Montgomery Fr, un-transposed
+        self.m = m            # m_col
+        self.odd = odd
+        self.q: Optional[np.ndarray] = None
+        self.chis_b: Optional[np.ndarray] = None
+
+    @classmethod
+    def from_evaluations(cls, Z) -> "Polynomial":
+        """src/sqrt_pst.rs:32-75. len(Z) must be a power of two."""
+        z = np.ascontiguousarray(Z, dtype=np.uint64).reshape(-1, 4)
+        n = len(z)
+        assert n > 0 and n & (n - 1) == 0
+        num_vars = n.bit_length() - 1
+        return cls(z, num_vars // 2, num_vars % 2)
+
+    @property
+    def m_row(self) -> int:
+        return self.m + self.odd
+
+    def row(self, i: int) -> np.ndarray:
+        """polys[i].Z of the reference: Z[(j << m_col) | i] for j < 2^m_row."""
+        return self.Z[i :: 1 << self.m]
+
+    def commit(self, ck: CommitterKey) -> Tuple[np.ndarray, None]:
+        """src/sqrt_pst.rs:117-149 -> (comm_list as [2^m_col, 12] g_products, t). t (pairing product) is not computed."""
+        rows, cols = 1 << self.m, 1 << self.m_row
+        assert cols == len(ck.powers_of_g0), "ck.powers_of_g[0] must have 2^m_row points"
+        out = np.zeros((rows, 12), dtype=np.uint64)
+        _lib.check(_lib.engine().tb200_msm_g1_batch(ck._h, _ptr(self.Z), rows, cols, 1, rows, _lib.SCALARS_MONT,
+                                                    _ptr(out)))
+        return out, None
+
+    def get_q(self, point: List[int]) -> None:
+        """src/sqrt_pst.rs:81-101 (the reference's CPU code, unchanged by the engine). `point` as integers mod r."""
+        assert len(point) == 2 * self.m + self.odd
+        b = point[self.m + self.odd:]
+        pow_m = 1 << self.m
+        chis = [fr.get_chi_i(b, i) for i in range(pow_m)]
+        zi = fr.from_mont_words(self.Z)
+        zq = []
+        for j in range(pow_m << self.odd):
+            zq.append(sum(zi[(j << self.m) | i] * chis[i] for i in range(pow_m)) % fr.R)
+        self.q = fr.to_mont_words(zq)
+        self.chis_b = fr.to_mont_words(chis)
+
+    def eval(self, point: List[int]) -> int:
+        """src/sqrt_pst.rs:105-115."""
+        a = point[: len(point) // 2 + self.odd]
+        if self.q is None:
+            self.get_q(point)
+        q = fr.from_mont_words(self.q)
+        return sum(qj * fr.get_chi_i(a, j) for j, qj in enumerate(q)) % fr.R
+
+    def open(self, challenge: Callable[[bytes, List[np.ndarray]], int], comm_list: np.ndarray, ck: CommitterKey,
+             point: List[int]) -> OpenG1:
+        """G1 work of src/sqrt_pst.rs:168-230. `challenge(label, appended_points)` stands in for the Poseidon
+        transcript (out of scope): it receives what the reference appends and returns the squeezed scalar."""
+        if self.q is None:
+            self.get_q(point)
+        assert self.chis_b is not None, "chis(b) should have been computed for q"
+        assert len(self.chis_b) == len(comm_list)                      # src/sqrt_pst.rs:194
+        c_u = msm.msm_unchecked(comm_list, self.chis_b)                # M2, src/sqrt_pst.rs:198
+        comm_q = pc_commit(ck, self.q)                                 # M3, src/sqrt_pst.rs:205
+        assert np.array_equal(c_u, comm_q), "debug_assert!(c_u == comm.g_product) (src/sqrt_pst.rs:206)"
+        proof = mipp.MippProofG1.prove(challenge, comm_list, self.chis_b, c_u)   # src/sqrt_pst.rs:212-213
+        return OpenG1(u=c_u, comm_q=comm_q, mipp=proof)
