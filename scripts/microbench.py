@@ -21,6 +21,13 @@ for kind, name in ((0, "imad_wide_per_s"), (1, "imad_lo_per_s"), (2, "fq_mul_per
     res[name] = v.value
 print(json.dumps(res))
 
+# raw pinned H2D bandwidth of this box (ceiling of the e2e number)
+hb = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+db = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+for _ in range(2):
+    torch.cuda.synchronize(); t0 = time.time(); db.copy_(hb, non_blocking=True); torch.cuda.synchronize(); dt = time.time() - t0
+print(json.dumps({"h2d_pinned_GBps": round((1 << 30) / dt / 1e9, 2)}))
+del hb, db
 sizes = [int(a) for a in sys.argv[1:]] or [16, 20, 22]
 for logn in sizes:
     n = 1 << logn

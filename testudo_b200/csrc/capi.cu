@@ -328,6 +328,13 @@ int tb200_init(int device) {
   CU(cudaGetDeviceProperties(&prop, device));
   g.device = device;
   g.sms = prop.multiProcessorCount;
+  {  // keep freed staging buffers in the pool: with the default threshold (0) every synchronisation returns them
+     // to the OS and the next host-facing call pays hundreds of ms to map gigabytes again
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = ~0ull;
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&g.ev_points, cudaEventDisableTiming));

@@ -573,51 +573,55 @@ __global__ void k_test_g1_mul(const uint4* p, const uint32_t* k, uint32_t n, uin
 }
 
 // integer-pipe microbenchmarks (the roofline denominator is measured) --------------------------
-// kind 0: IMAD.WIDE.U32 with 64-bit accumulate, 8 independent chains per thread
-// kind 1: 32-bit IMAD (mad.lo), 8 independent chains
+// Eight chains per thread; every chain's multiplier is the low word another chain produced one step earlier, so
+// nothing is loop-invariant (ptxas strength-reduces an invariant product to adds) and nothing is warp-uniform
+// (ptxas moves uniform chains to the uniform datapath) -- both were observed with a naive version.
+// kind 0: IMAD.WIDE.U32 (32x32+64 -> 64);  kind 1: IMAD (32x32+32 -> 32)
 __global__ void __launch_bounds__(256) k_int_pipe(int kind, int iters, uint32_t seed, uint64_t* sink) {
-  uint32_t a = seed ^ (threadIdx.x * 2654435761u), b = seed * 40503u + blockIdx.x;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t b = (seed * 40503u + tid * 2654435761u) | 1u;
   if (kind == 0) {
-    uint64_t c0 = a, c1 = b, c2 = a + 1, c3 = b + 1, c4 = a + 2, c5 = b + 2, c6 = a + 3, c7 = b + 3;
+    uint64_t c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = ((uint64_t)(tid + k) << 32) | (seed + 77u * k);
     for (int i = 0; i < iters; i++) {
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c0) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c1) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c2) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c3) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c4) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c5) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c6) : "r"(a), "r"(b));
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c7) : "r"(a), "r"(b));
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          uint32_t a = (uint32_t)c[(k + 1) & 7];
+          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[k]) : "r"(a), "r"(b));
+        }
       }
     }
-    sink[(uint64_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+    sink[tid] = c[0] ^ c[1] ^ c[2] ^ c[3] ^ c[4] ^ c[5] ^ c[6] ^ c[7];
   } else {
-    uint32_t c0 = a, c1 = b, c2 = a + 1, c3 = b + 1, c4 = a + 2, c5 = b + 2, c6 = a + 3, c7 = b + 3;
+    uint32_t c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = seed + 77u * k + tid;
     for (int i = 0; i < iters; i++) {
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c0) : "r"(a), "r"(b));
-        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c1) : "r"(a), "r"(b));
-        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c2) : "r"(a), "r"(b));
-        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c3) : "r"(a), "r"(b));
-        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c4) : "r"(a), "r"(b));
-        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c5) : "r"(a), "r"(b));
-        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c6) : "r"(a), "r"(b));
-        asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c7) : "r"(a), "r"(b));
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          uint32_t a = c[(k + 1) & 7];
+          asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c[k]) : "r"(a), "r"(b));
+        }
       }
     }
-    sink[(uint64_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+    sink[tid] = c[0] ^ c[1] ^ c[2] ^ c[3] ^ c[4] ^ c[5] ^ c[6] ^ c[7];
   }
 }
-// kind 2: dependent Fq Montgomery multiplications, 2 independent chains per thread
+// kind 2: Fq Montgomery multiplications, 2 independent per-thread chains (lane-varying operands)
 __global__ void __launch_bounds__(128) k_fq_mul_peak(int iters, uint32_t seed, uint32_t* sink) {
-  Fq x, y, z = fq_one(), w = fq_one();
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  Fq x, y, z, w;
 #pragma unroll
   for (int j = 0; j < 12; j++) {
-    x.l[j] = (seed + j * 77u + threadIdx.x) & 0x00ffffffu;
-    y.l[j] = (seed * 3u + j * 1013u + blockIdx.x) & 0x00ffffffu;
+    x.l[j] = (seed + j * 77u + tid * 2654435761u) & 0x00ffffffu;
+    y.l[j] = (seed * 3u + j * 1013u + tid * 40503u) & 0x00ffffffu;
+    z.l[j] = (tid + j) & 0x00ffffffu;
+    w.l[j] = (tid * 7u + j) & 0x00ffffffu;
   }
   for (int i = 0; i < iters; i++) {
     fq_mul(z, z, x);
@@ -626,7 +630,7 @@ __global__ void __launch_bounds__(128) k_fq_mul_peak(int iters, uint32_t seed, u
   uint32_t acc = 0;
 #pragma unroll
   for (int j = 0; j < 12; j++) acc ^= z.l[j] ^ w.l[j];
-  sink[(uint64_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+  sink[tid] = acc;
 }
 
 }  // namespace tb
