@@ -61,6 +61,28 @@ int hc_madd_fast_chain(const uint32_t* pts_aff, const uint32_t* neg, int n, uint
   Affine r; xyzz_to_affine(r, acc); memcpy(out_aff, &r, 96);
   return overflow;
 }
+// lazy add / double chains: acc = sum_i (p_i), each p_i first pushed to a non-trivial XYZZ representation; then
+// `dbls` doublings; canonical affine out
+int hc_add_fast_chain(const uint32_t* pts_aff, int n, int dbls, const uint32_t* t_aff, uint32_t* out_aff) {
+  Affine t; memcpy(&t, t_aff, 96);
+  Affine nt = t; fq_neg(nt.y, nt.y);
+  Xyzz acc; xyzz_set_inf(acc);
+  int overflow = 0;
+  for (int i = 0; i < n; i++) {
+    Affine q; memcpy(&q, pts_aff + 24 * i, 96);
+    Xyzz x; xyzz_from_affine(x, q);
+    if (!xyzz_is_inf(x) && (i & 1)) { xyzz_madd_fast(x, t); xyzz_madd_fast(x, nt); }  // ZZ != 1, lazy coords
+    xyzz_add_fast(acc, x);
+    if ((acc.x.l[11] | acc.y.l[11] | acc.zz.l[11] | acc.zzz.l[11]) >> 31) overflow = 1;
+  }
+  for (int k = 0; k < dbls; k++) {
+    xyzz_dbl_fast(acc);
+    if ((acc.x.l[11] | acc.y.l[11] | acc.zz.l[11] | acc.zzz.l[11]) >> 31) overflow = 1;
+  }
+  xyzz_canon(acc);
+  Affine r; xyzz_to_affine(r, acc); memcpy(out_aff, &r, 96);
+  return overflow;
+}
 void hc_fq_canon(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.l, a, 48); fq_canon(x); memcpy(r, x.l, 48); }
 void hc_fq_mul_lazy(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul_lazy<FqParams>(r, a, b); }
 // signed digits of one canonical scalar with window c: out[w] in [-2^(c-1), 2^(c-1)]

@@ -142,6 +142,93 @@ TB_HD void xyzz_madd_fast(Xyzz& p, const Affine& q) {
   fq_sub_lazy<0>(p.y, qq, t);      // Y3 = .. + 2q - ..  < 3.5q  (invariant Y < 4q)
 }
 
+// exact XYZZ + XYZZ for the exceptional cases of the lazy add (by value: no addresses of caller registers)
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__
+#else
+inline
+#endif
+    Xyzz
+    xyzz_add_exact(Xyzz p, Xyzz q) {
+  fq_canon(p.x); fq_canon(p.y); fq_canon(p.zz); fq_canon(p.zzz);
+  fq_canon(q.x); fq_canon(q.y); fq_canon(q.zz); fq_canon(q.zzz);
+  xyzz_add(p, q);
+  return p;
+}
+
+// p += q, both XYZZ with the lazy invariant (X < 8q, Y < 4q, ZZ, ZZZ < 2q); result satisfies it again.
+// 12M + 2S through the out-of-line multiplier. Used by the bucket-reduction and fix-up kernels.
+TB_HD void xyzz_add_fast(Xyzz& p, const Xyzz& q) {
+  if (xyzz_is_inf(q)) return;
+  if (xyzz_is_inf(p)) {
+    p = q;
+    return;
+  }
+  Fq u1, u2, s1, s2;
+  u1 = fq_mul_call(p.x, q.zz);     // U1 < 1.2q
+  u2 = fq_mul_call(q.x, p.zz);     // U2 < 1.2q
+  s1 = fq_mul_call(p.y, q.zzz);    // S1 < 1.1q
+  s2 = fq_mul_call(q.y, p.zzz);    // S2 < 1.1q
+  fq_sub_lazy<0>(u2, u2, u1);      // P = U2 + 2q - U1 in (0, 3.2q)
+  fq_sub_lazy<0>(s2, s2, s1);      // R = S2 + 2q - S1 in (0, 3.1q)
+  if (u2.l[0] - 1u < 3u) {         // P = k q (k <= 3) possible: decide exactly
+    Fq chk = u2;
+    fq_canon(chk);
+    if (fq_is_zero(chk)) {
+      p = xyzz_add_exact(p, q);
+      return;
+    }
+  }
+  Fq pp, ppp, t;
+  pp = fq_mul_call(u2, u2);        // PP  < 1.1q
+  ppp = fq_mul_call(u2, pp);       // PPP < 1.1q
+  u1 = fq_mul_call(u1, pp);        // Q   < 1.1q
+  t = fq_mul_call(p.zz, q.zz);
+  p.zz = fq_mul_call(t, pp);       // ZZ3  < 2q
+  t = fq_mul_call(p.zzz, q.zzz);
+  p.zzz = fq_mul_call(t, ppp);     // ZZZ3 < 2q
+  t = fq_mul_call(s2, s2);         // RR < 1.1q
+  fq_sub_lazy<0>(t, t, ppp);
+  fq_sub_lazy<0>(t, t, u1);
+  fq_sub_lazy<0>(p.x, t, u1);      // X3 < 7.1q
+  fq_sub_lazy<2>(u1, u1, p.x);     // Q + 8q - X3 < 9.1q
+  u1 = fq_mul_call(s2, u1);        // < 1.3q
+  t = fq_mul_call(s1, ppp);        // < 1.1q
+  fq_sub_lazy<0>(p.y, u1, t);      // Y3 < 3.3q
+}
+
+// p = 2p with the lazy invariant in and out (6M + 3S)
+TB_HD void xyzz_dbl_fast(Xyzz& p) {
+  if (xyzz_is_inf(p)) return;
+  Fq u, v, w, s, m, t;
+  Carry c;
+  // U = 2Y < 8q (plain limb add: no reduction needed below 2^384)
+  u.l[0] = add_cc(p.y.l[0], p.y.l[0], c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) u.l[i] = addc_cc(p.y.l[i], p.y.l[i], c);
+  v = fq_mul_call(u, u);           // V < 1.5q
+  w = fq_mul_call(u, v);           // W < 1.1q
+  s = fq_mul_call(p.x, v);         // S < 1.1q
+  m = fq_mul_call(p.x, p.x);       // X^2 < 1.5q
+  Carry d;
+  t.l[0] = add_cc(m.l[0], m.l[0], d);
+#pragma unroll
+  for (int i = 1; i < 12; i++) t.l[i] = addc_cc(m.l[i], m.l[i], d);
+  Carry e;
+  m.l[0] = add_cc(t.l[0], m.l[0], e);
+#pragma unroll
+  for (int i = 1; i < 12; i++) m.l[i] = addc_cc(t.l[i], m.l[i], e);   // M = 3 X^2 < 4.5q
+  t = fq_mul_call(w, p.y);         // W * Y1 < 1.1q
+  Fq mm = fq_mul_call(m, m);       // < 1.2q
+  fq_sub_lazy<0>(mm, mm, s);
+  fq_sub_lazy<0>(p.x, mm, s);      // X3 = M^2 + 4q - 2S < 5.2q
+  fq_sub_lazy<2>(s, s, p.x);       // S + 8q - X3 < 9.1q
+  s = fq_mul_call(m, s);           // < 1.4q
+  fq_sub_lazy<0>(p.y, s, t);       // Y3 < 3.4q
+  p.zz = fq_mul_call(v, p.zz);     // < 2q
+  p.zzz = fq_mul_call(w, p.zzz);   // < 2q
+}
+
 TB_HD void xyzz_canon(Xyzz& p) {
   fq_canon(p.x);
   fq_canon(p.y);

@@ -77,6 +77,18 @@ __device__ __noinline__ void xyzz_add_ni(Xyzz* p, const Xyzz* q) { xyzz_add(*p, 
 __device__ __noinline__ void xyzz_dbl_ni(Xyzz* p) { xyzz_dbl(*p); }
 __device__ __noinline__ void xyzz_madd_ni(Xyzz* p, const Affine* q) { xyzz_madd(*p, *q); }
 __device__ __noinline__ void xyzz_to_affine_ni(Affine* r, const Xyzz* p) { xyzz_to_affine(*r, *p); }
+// lazy-reduction versions (g1_fast.cuh) behind one call site each: the few dozen local-memory words per call are
+// noise next to 9-14 multiplications, and the kernels that use them stay small and spill-free
+__device__ __noinline__ void xyzz_add_fast_ni(Xyzz* p, const Xyzz* q) {
+  Xyzz a = *p;
+  xyzz_add_fast(a, *q);
+  *p = a;
+}
+__device__ __noinline__ void xyzz_dbl_fast_ni(Xyzz* p) {
+  Xyzz a = *p;
+  xyzz_dbl_fast(a);
+  *p = a;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // geometry of one MSM call
@@ -298,7 +310,7 @@ __global__ void __launch_bounds__(128) k_fixup_round(const uint32_t* __restrict_
   Xyzz acc, h;
   load_xyzz(acc, heads + 12 * t);
   load_xyzz(h, heads + 12 * u);
-  xyzz_add_ni(&acc, &h);
+  xyzz_add_fast_ni(&acc, &h);
   store_xyzz(heads + 12 * t, acc);
 }
 __global__ void __launch_bounds__(128) k_fixup_final(const uint32_t* __restrict__ bucket_start, uint32_t B,
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(128) k_fixup_final(const uint32_t* __restrict_
   Xyzz acc, h;
   load_xyzz(acc, buckets + 12 * (uint64_t)hb);
   load_xyzz(h, heads + 12 * t);
-  xyzz_add_ni(&acc, &h);
+  xyzz_add_fast_ni(&acc, &h);
   store_xyzz(buckets + 12 * (uint64_t)hb, acc);
 }
 
@@ -332,28 +344,31 @@ __global__ void __launch_bounds__(128) k_reduce_pass(const uint4* __restrict__ i
                                                      int log2_ell, uint64_t total_out) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total_out) return;
-  Xyzz run, acc, wsum, x;
+  // lazily reduced coordinates throughout (g1_fast.cuh); the stored (S, W) pairs keep the lazy invariant.
+  // Two sweeps keep at most three XYZZ values live (the one-sweep form needed four and spilled).
+  Xyzz run, acc, x;
   xyzz_set_inf(run);
   xyzz_set_inf(acc);
-  xyzz_set_inf(wsum);
   for (int i = (int)L - 1; i >= 0; i--) {
     const uint64_t idx = t * L + i;
     bool empty = false;
     if (bucket_start) empty = bucket_start[idx + 1] == bucket_start[idx];
     if (!empty) {
       load_xyzz(x, inS + 12 * idx);
-      xyzz_add_ni(&run, &x);
-      if (inW) {
-        load_xyzz(x, inW + 12 * idx);
-        xyzz_add_ni(&wsum, &x);
-      }
+      xyzz_add_fast_ni(&run, &x);
     }
-    if (i > 0) xyzz_add_ni(&acc, &run);
+    if (i > 0) xyzz_add_fast_ni(&acc, &run);
   }
   store_xyzz(outS + 12 * t, run);
-  for (int k = 0; k < log2_ell; k++) xyzz_dbl_ni(&acc);
-  if (inW) xyzz_add_ni(&acc, &wsum);
-  else xyzz_add_ni(&acc, &run);
+  for (int k = 0; k < log2_ell; k++) xyzz_dbl_fast_ni(&acc);
+  if (inW) {
+    xyzz_set_inf(run);  // reused as sum of the W_i
+    for (int i = 0; i < (int)L; i++) {
+      load_xyzz(x, inW + 12 * (t * L + i));
+      xyzz_add_fast_ni(&run, &x);
+    }
+  }
+  xyzz_add_fast_ni(&acc, &run);
   store_xyzz(outW + 12 * t, acc);
 }
 
@@ -364,10 +379,11 @@ __global__ void k_finalize_single(const uint4* __restrict__ group_w, int W, int 
   xyzz_set_inf(total);
   for (int w = W - 1; w >= 0; w--) {
     load_xyzz(x, group_w + 12 * w);
-    xyzz_add_ni(&total, &x);
+    xyzz_add_fast_ni(&total, &x);
     if (w > 0)
-      for (int k = 0; k < c; k++) xyzz_dbl_ni(&total);
+      for (int k = 0; k < c; k++) xyzz_dbl_fast_ni(&total);
   }
+  xyzz_canon(total);
   Affine a;
   xyzz_to_affine_ni(&a, &total);
   store_affine(out_affine, a);
@@ -379,6 +395,7 @@ __global__ void __launch_bounds__(128) k_finalize_batch(const uint4* __restrict_
   if (t >= groups) return;
   Xyzz x;
   load_xyzz(x, group_w + 12 * (uint64_t)t);
+  xyzz_canon(x);  // group sums arrive lazily reduced
   Affine a;
   xyzz_to_affine_ni(&a, &x);
   store_affine(out_affine + 6 * (uint64_t)t, a);
