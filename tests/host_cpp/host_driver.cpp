@@ -1,0 +1,89 @@
+// Test driver for the C++ host mirror (testudo_b200/host/testudo_b200.hpp): reads a little-endian blob written by
+// tests/test_gpu_host_cpp.py, runs commit / open / MIPP / Pedersen through the mirror, writes the results back.
+// blob in : u64 nv | Z[2^nv] Fr | srs[2^m_row] G1 | point[nv] Fr | h G1 | blind Fr
+// blob out: comm_list[2^m_col] | u | comm_q | eval Fr | n_rounds u64 | (ul, ur)[rounds] | final_a | final_y | slice | err_len u64
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+
+#include "../../testudo_b200/host/testudo_b200.hpp"
+using namespace testudo_b200;
+
+template <class T>
+static std::vector<T> rd(std::ifstream& f, size_t n) {
+  std::vector<T> v(n);
+  f.read((char*)v.data(), n * sizeof(T));
+  return v;
+}
+template <class T>
+static void wr(std::ofstream& f, const T* p, size_t n) { f.write((const char*)p, n * sizeof(T)); }
+
+// deterministic stand-in for the Poseidon transcript: FNV-style mix of everything appended (same in the python test)
+struct FakeTranscript {
+  uint64_t st = 0xcbf29ce484222325ULL;
+  void absorb(const void* p, size_t n) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; i++) { st ^= b[i]; st *= 0x100000001b3ULL; }
+  }
+  Fr challenge(const char* label, const std::vector<G1Affine>& pts) {
+    absorb(label, strlen(label));
+    for (auto& p : pts) absorb(p.w, 96);
+    // small canonical value lifted to Montgomery form by multiplying with R^2
+    Fr v{{st | 1, st >> 7, 0, 0}};
+    Fr r2;
+    for (int i = 0; i < 8; i++) ((uint32_t*)r2.l)[i] = tb::FrParams::r2(i);
+    return fr::mul(v, r2);
+  }
+};
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  try {
+    init(-1);
+    std::ifstream in(argv[1], std::ios::binary);
+    uint64_t nv;
+    in.read((char*)&nv, 8);
+    size_t m_col = nv / 2, m_row = nv - m_col;
+    auto Z = rd<Fr>(in, size_t(1) << nv);
+    auto srs = rd<G1Affine>(in, size_t(1) << m_row);
+    auto point = rd<Fr>(in, nv);
+    auto hpt = rd<G1Affine>(in, 1);
+    auto blind = rd<Fr>(in, 1);
+    std::ofstream out(argv[2], std::ios::binary);
+
+    CommitterKey ck(srs);
+    Polynomial poly = Polynomial::from_evaluations(Z);
+    auto comm_list = poly.commit(ck);
+    wr(out, comm_list.data(), comm_list.size());
+    FakeTranscript tr;
+    auto opened = poly.open([&](const char* l, const std::vector<G1Affine>& p) { return tr.challenge(l, p); }, comm_list,
+                            ck, point);
+    wr(out, &opened.u, 1);
+    wr(out, &opened.comm_q, 1);
+    Fr ev = poly.eval(point);
+    wr(out, &ev, 1);
+    uint64_t rounds = opened.mipp.comms_u.size();
+    wr(out, &rounds, 1);
+    for (auto& pr : opened.mipp.comms_u) { wr(out, &pr.first, 1); wr(out, &pr.second, 1); }
+    wr(out, &opened.mipp.final_a, 1);
+    wr(out, &opened.mipp.final_y, 1);
+    // Pedersen commit_slice over gens = (srs, h) with the first row of Z and a blind
+    commitments::MultiCommitGens gens{srs, hpt[0]};
+    std::vector<Fr> row0(Z.begin(), Z.begin() + srs.size());
+    G1Affine sl = commitments::PedersenCommit::commit_slice(row0, blind[0], gens);
+    wr(out, &sl, 1);
+    // VariableBaseMSM::msm length rule
+    std::vector<Fr> shorter(Z.begin(), Z.begin() + srs.size() - 1);
+    auto r = msm::msm(srs, shorter);
+    uint64_t err = r.ok ? ~0ull : r.err_len;
+    wr(out, &err, 1);
+    // multiexponentiation error behaviour
+    uint64_t threw = 0;
+    try { mipp::multiexponentiation(srs, shorter); } catch (const mipp::InvalidIPVectorLength&) { threw = 1; }
+    wr(out, &threw, 1);
+    return 0;
+  } catch (const std::exception& e) {
+    std::cerr << "host_driver: " << e.what() << std::endl;
+    return 1;
+  }
+}

@@ -1,0 +1,111 @@
+"""GPU parity of the C++ host mirror (testudo_b200/host/testudo_b200.hpp): commit / open / MIPP / Pedersen driven
+from C++ through the C ABI, compared value by value with the big-integer oracle following src/sqrt_pst.rs and
+src/mipp.rs."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers as h
+from oracle import bls12_377 as o
+from testudo_b200 import build, fr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DRV_DIR = os.path.join(ROOT, "tests", "host_cpp")
+
+
+@pytest.fixture(scope="module")
+def driver():
+    build.build()
+    exe = os.path.join(DRV_DIR, "host_driver")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(DRV_DIR, "host_driver.cpp"),
+                           "-L" + build.LIB_DIR, "-ltestudo_b200", "-Wl,-rpath," + build.LIB_DIR])
+    return exe
+
+
+class FakeTranscript:
+    def __init__(self):
+        self.st = 0xCBF29CE484222325
+
+    def absorb(self, b: bytes):
+        for x in b:
+            self.st ^= x
+            self.st = (self.st * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+
+    def challenge(self, label: bytes, pts):
+        self.absorb(label)
+        for p in pts:
+            self.absorb(np.asarray(p, dtype=np.uint64).tobytes())
+        return ((self.st | 1) + ((self.st >> 7) << 64)) % o.R_ORDER
+
+
+@pytest.mark.parametrize("nv", [5, 8])
+def test_cpp_host_mirror_matches_reference_semantics(engine, driver, tmp_path, nv):
+    m_col = nv // 2
+    m_row = nv - m_col
+    z = o.rand_scalars(1 << nv, 900 + nv)
+    srs, _ = o.rand_points(1 << m_row, 910 + nv)
+    point = o.rand_scalars(nv, 920 + nv)
+    hpt = o.mul(424243, o.G)
+    blind = o.rand_scalars(1, 930 + nv)[0]
+    blob = struct.pack("<Q", nv) + h.scalars_to_np(z, mont=True).tobytes() + h.pts_to_np(srs).tobytes() + \
+        h.scalars_to_np(point, mont=True).tobytes() + h.pts_to_np([hpt]).tobytes() + h.scalars_to_np([blind], mont=True).tobytes()
+    fin, fout = tmp_path / "in.bin", tmp_path / "out.bin"
+    fin.write_bytes(blob)
+    subprocess.check_call([driver, str(fin), str(fout)])
+    data = np.frombuffer(fout.read_bytes(), dtype=np.uint64)
+    pos = 0
+
+    def take_pts(k):
+        nonlocal pos
+        v = data[pos: pos + 12 * k].reshape(k, 12)
+        pos += 12 * k
+        return v
+
+    def take_fr():
+        nonlocal pos
+        v = data[pos: pos + 4]
+        pos += 4
+        return h.scalars_from_np(v, mont=True)[0]
+
+    def take_u64():
+        nonlocal pos
+        v = int(data[pos])
+        pos += 1
+        return v
+
+    comm_list = take_pts(1 << m_col)
+    rows = [o.msm_naive(srs, [z[(j << m_col) | i] for j in range(1 << m_row)]) for i in range(1 << m_col)]
+    assert [h.pt_from_np(r) for r in comm_list] == rows                                    # src/sqrt_pst.rs:121-125
+    b = point[m_row:]
+    chis = [fr.get_chi_i(b, i) for i in range(1 << m_col)]
+    q = [sum(z[(j << m_col) | i] * chis[i] for i in range(1 << m_col)) % o.R_ORDER for j in range(1 << m_row)]
+    u = h.pt_from_np(take_pts(1)[0])
+    comm_q = h.pt_from_np(take_pts(1)[0])
+    assert u == o.msm_naive(rows, chis) == o.msm_naive(srs, q) == comm_q                    # :198, :205-206
+    a = point[:m_row]
+    assert take_fr() == sum(qj * fr.get_chi_i(a, j) for j, qj in enumerate(q)) % o.R_ORDER  # eval, :105-115
+    # MIPP loop, src/mipp.rs:58-120
+    tr = FakeTranscript()
+    tr.challenge(b"U", [h.pts_to_np([u])[0]])
+    m_a, m_y = list(rows), list(chis)
+    assert take_u64() == m_col
+    while len(m_a) > 1:
+        split = len(m_a) // 2
+        u_l = o.msm_naive(m_a[:split], m_y[split:])
+        u_r = o.msm_naive(m_a[split:], m_y[:split])
+        got = take_pts(2)
+        assert h.pt_from_np(got[0]) == u_l and h.pt_from_np(got[1]) == u_r
+        c_inv = tr.challenge(b"challenge_i", [got[0], got[1]])
+        c = pow(c_inv, -1, o.R_ORDER)
+        m_a = [o.add(m_a[i], o.mul(c, m_a[split + i])) for i in range(split)]
+        m_y = [(m_y[i] + c_inv * m_y[split + i]) % o.R_ORDER for i in range(split)]
+    assert h.pt_from_np(take_pts(1)[0]) == m_a[0]
+    assert take_fr() == m_y[0]
+    # PedersenCommit::commit_slice, src/commitments.rs:79-86
+    assert h.pt_from_np(take_pts(1)[0]) == o.add(o.msm_naive(srs, z[: 1 << m_row]), o.mul(blind, hpt))
+    assert take_u64() == (1 << m_row) - 1        # VariableBaseMSM::msm -> Err(min_len)
+    assert take_u64() == 1                       # multiexponentiation -> Err(InvalidIPVectorLength)

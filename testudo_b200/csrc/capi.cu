@@ -247,15 +247,34 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
     return 0;
   }
   if (mark(st, "begin")) return 1;
-  CU(cudaMemsetAsync(counts, 0, (p.B + 1) * 4, st));
   const uint32_t dig_grid = (uint32_t)std::min<uint64_t>(cdiv(items, 256), (uint64_t)g.sms * 16);
-  LAUNCH(k_digits<false>, dig_grid, 256, st, d_scalars, q, counts, (uint32_t*)nullptr);
+  // batches with enough rows to fill the GPU sort each row inside one CTA's shared memory
+  const size_t row_smem = (size_t)q.nb * 4;
+  const bool row_sort = q.batch && q.rows >= (uint32_t)g.sms && row_smem <= 160 * 1024;
+  if (row_sort) {
+    if (row_smem > 48 * 1024) {
+      CU(cudaFuncSetAttribute(k_batch_digits<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+      CU(cudaFuncSetAttribute(k_batch_digits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
+    }
+    k_batch_digits<false><<<q.rows, 256, row_smem, st>>>(d_scalars, q, counts, (uint32_t*)nullptr);
+    g_launches++;
+    CU(cudaGetLastError());
+  } else {
+    CU(cudaMemsetAsync(counts, 0, (p.B + 1) * 4, st));
+    LAUNCH(k_digits<false>, dig_grid, 256, st, d_scalars, q, counts, (uint32_t*)nullptr);
+  }
   if (mark(st, "digits")) return 1;
   LAUNCH(k_scan_tile_sums, p.ntiles, SCAN_THREADS, st, counts, (uint32_t)p.B, tile_sums);
   LAUNCH(k_scan_tile_offsets, 1, SCAN_THREADS, st, tile_sums, p.ntiles, tile_sums + p.ntiles);
   LAUNCH(k_scan_apply, p.ntiles, SCAN_THREADS, st, counts, (uint32_t)p.B, tile_sums, starts, cursors);
   if (mark(st, "scan")) return 1;
-  LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, cursors, entries);
+  if (row_sort) {
+    k_batch_digits<true><<<q.rows, 256, row_smem, st>>>(d_scalars, q, starts, entries);
+    g_launches++;
+    CU(cudaGetLastError());
+  } else {
+    LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, cursors, entries);
+  }
   if (mark(st, "scatter")) return 1;
   if (points_ready) CU(cudaStreamWaitEvent(st, points_ready, 0));  // bases may still be in flight until here
   // M is only known on the device (starts[B]); launch for the upper bound, surplus threads exit immediately

@@ -150,6 +150,54 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// shared-base batches: per-row counting sort in shared memory
+// ------------------------------------------------------------------------------------------------------------
+// In a batch every entry of row i falls into row i's own nb buckets, so one CTA per row keeps the row's histogram /
+// scatter cursors in shared memory (nb * 4 bytes: 16 KB at c = 13) instead of hammering L2 with 1.3e9 atomics, and
+// the scattered 4-byte writes of a row stay inside its 0.6 MB slice of entries[] while the CTA lives.
+//   SCATTER = false: smem histogram -> counts[row*nb ..] (plain coalesced stores, no global atomics)
+//   SCATTER = true : smem cursors loaded from the scanned bucket_start[], returning smem atomics give positions
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_batch_digits(const uint32_t* __restrict__ scalars, MsmGeom g,
+                                                      uint32_t* __restrict__ counters /* counts or bucket_start */,
+                                                      uint32_t* __restrict__ entries) {
+  extern __shared__ uint32_t s_cnt[];
+  const uint32_t row = blockIdx.x;
+  uint32_t* row_counters = counters + (uint64_t)row * g.nb;
+  for (uint32_t k = threadIdx.x; k < g.nb; k += blockDim.x) s_cnt[k] = SCATTER ? row_counters[k] : 0u;
+  __syncthreads();
+  for (uint32_t col = threadIdx.x; col < g.cols; col += blockDim.x) {
+    const uint4* sp = reinterpret_cast<const uint4*>(scalars + 8 * ((long long)row * g.row_stride +
+                                                                   (long long)col * g.col_stride));
+    uint4 lo = __ldg(sp), hi = __ldg(sp + 1);
+    uint32_t s[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    if (g.mont) {
+      uint32_t cnv[8];
+      mont_to_canonical<FrParams>(cnv, s);
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[i] = cnv[i];
+    }
+    if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) continue;
+    DigitIter it(s, g.c);
+    for (int w = 0; w < g.W; w++) {
+      int32_t d = it.next(w == g.W - 1);
+      if (d == 0) continue;
+      uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+      if (SCATTER) {
+        uint32_t pos = atomicAdd(&s_cnt[mag - 1], 1u);
+        entries[pos] = ((uint32_t)w * g.cols + col) | (d < 0 ? 0x80000000u : 0u);
+      } else {
+        atomicAdd(&s_cnt[mag - 1], 1u);
+      }
+    }
+  }
+  if (!SCATTER) {
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < g.nb; k += blockDim.x) row_counters[k] = s_cnt[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // exclusive scan of the bucket histogram (3 kernels; B <= 2^31). SCAN_TILE items per block.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 512;

@@ -338,10 +338,13 @@ TB_HD void mont_mul_lazy(uint32_t* r, const uint32_t* a, const uint32_t* b) {
       o[N - 1] = madc_hi(ai, b[N - 1], o[N - 1], c);  // O < 2^(32N-5): no carry out
     }
     // Montgomery digit: m = -(T mod 2^32); m * p_0 = m cancels limb 0 and carries k into limb 1
+    // k = carry(e0 + x) + (s != 0), both via the carry flag (s + 0xffffffff carries iff s != 0): four ALU-pipe
+    // adds. Written as `k += (s != 0)` ptxas emits select logic built from IMAD.MOVs, which occupy the FMA pipe.
     uint32_t s = add_cc(e[0], x, c);
     uint32_t k = addc(0, 0, c);
+    (void)add_cc(s, 0xffffffffu, c);
+    k = addc(k, 0, c);
     uint32_t m = neg32(s);
-    k += (s != 0);
     // E += m * (p_2, p_4, ...) from limb 1 up (p_0 handled above)
     e[1] = add_cc(e[1], k, c);
 #pragma unroll

@@ -1,0 +1,311 @@
+// C++ host side above the C ABI (include/testudo_b200.h): mirrors the reference's Rust interfaces for the MSM path
+// with the same names, argument meaning and error behaviour, so a maintainer can read it next to the Rust.
+//   msm::{msm, msm_unchecked, msm_bigint}        ark-ec VariableBaseMSM
+//   CommitterKey, Polynomial::{from_evaluations, commit, get_q, eval, open}   src/sqrt_pst.rs:14-230 (G1 work)
+//   mipp::{multiexponentiation, compress, prove_g1}                          src/mipp.rs:31-153,354-394 (G1 work)
+//   commitments::{MultiCommitGens, PedersenCommit, commit_inner}             src/commitments.rs, src/dense_mlpoly.rs:315-329
+// The reference is Rust and no Rust toolchain exists in the build image, hence C++ (INTEGRATION.md has the Rust stub).
+// Curve arithmetic never runs here: every group operation is a call into the CUDA library. The Fr scalar glue the
+// reference computes on the CPU (chi products, q = Z*chi, challenge inversion) uses the same Montgomery code as the
+// kernels through its host path (csrc/mont.cuh).
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/testudo_b200.h"
+#include "../csrc/mont.cuh"
+
+namespace testudo_b200 {
+
+struct Fr {  // ark-ff Fp256<MontBackend>: 4 x u64 Montgomery limbs
+  uint64_t l[4];
+  bool operator==(const Fr& o) const { return std::memcmp(l, o.l, 32) == 0; }
+};
+struct G1Affine {  // x[6] || y[6] Montgomery limbs; all-zero == identity
+  uint64_t w[12];
+  bool is_identity() const {
+    for (auto v : w)
+      if (v) return false;
+    return true;
+  }
+  bool operator==(const G1Affine& o) const { return std::memcmp(w, o.w, 96) == 0; }
+};
+static_assert(sizeof(Fr) == 32 && sizeof(G1Affine) == 96, "ABI layouts");
+
+struct EngineError : std::runtime_error {  // a CUDA failure has no error channel in commit/open: it unwinds
+  int code;
+  EngineError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+inline void check(int rc) {
+  if (rc != 0) throw EngineError(rc, tb200_last_error());
+}
+inline void init(int device = -1) { check(tb200_init(device)); }
+
+// ---- Fr glue (host path of the kernels' Montgomery code) ---------------------------------------------------------
+namespace fr {
+inline Fr mul(const Fr& a, const Fr& b) {
+  Fr r;
+  tb::mont_mul<tb::FrParams>((uint32_t*)r.l, (const uint32_t*)a.l, (const uint32_t*)b.l);
+  return r;
+}
+inline Fr add(const Fr& a, const Fr& b) {
+  Fr r;
+  tb::mod_add<tb::FrParams>((uint32_t*)r.l, (const uint32_t*)a.l, (const uint32_t*)b.l);
+  return r;
+}
+inline Fr sub(const Fr& a, const Fr& b) {
+  Fr r;
+  tb::mod_sub<tb::FrParams>((uint32_t*)r.l, (const uint32_t*)a.l, (const uint32_t*)b.l);
+  return r;
+}
+inline Fr one() {
+  Fr r;
+  for (int i = 0; i < 8; i++) ((uint32_t*)r.l)[i] = tb::FrParams::one(i);
+  return r;
+}
+inline Fr zero() { return Fr{{0, 0, 0, 0}}; }
+inline Fr inverse(const Fr& a) {  // a^(r-2)
+  static const uint64_t E[4] = {0x0a11800000000001ULL - 2, 0x59aa76fed0000001ULL, 0x60b44d1e5c37b001ULL,
+                                0x12ab655e9a2ca556ULL};
+  Fr acc = one(), base = a;
+  for (int i = 0; i < 256; i++) {
+    if ((E[i / 64] >> (i % 64)) & 1) acc = mul(acc, base);
+    base = mul(base, base);
+  }
+  return acc;
+}
+}  // namespace fr
+
+// ---- ark-ec VariableBaseMSM ------------------------------------------------------------------------------------------
+namespace msm {
+// msm_bigint(bases, bigints): canonical scalars; truncates to min(len)
+inline G1Affine msm_bigint(const std::vector<G1Affine>& bases, const std::vector<Fr>& bigints) {
+  size_t n = std::min(bases.size(), bigints.size());
+  G1Affine out;
+  check(tb200_msm_g1((const uint64_t*)bases.data(), (const uint64_t*)bigints.data(), n, 0, out.w));
+  return out;
+}
+// msm_unchecked(bases, scalars): Montgomery-form Fr; silently truncates to min(len) like arkworks
+inline G1Affine msm_unchecked(const G1Affine* bases, const Fr* scalars, size_t n) {
+  G1Affine out;
+  check(tb200_msm_g1((const uint64_t*)bases, (const uint64_t*)scalars, n, TB200_SCALARS_MONT, out.w));
+  return out;
+}
+inline G1Affine msm_unchecked(const std::vector<G1Affine>& bases, const std::vector<Fr>& scalars) {
+  return msm_unchecked(bases.data(), scalars.data(), std::min(bases.size(), scalars.size()));
+}
+// msm(bases, scalars) -> Result<G1, usize>: .second == true on Ok; on Err .first is unspecified and err_len = min(len)
+struct MsmResult {
+  bool ok;
+  G1Affine value;
+  size_t err_len;
+};
+inline MsmResult msm(const std::vector<G1Affine>& bases, const std::vector<Fr>& scalars) {
+  if (bases.size() != scalars.size()) return {false, {}, std::min(bases.size(), scalars.size())};
+  return {true, msm_unchecked(bases, scalars), 0};
+}
+}  // namespace msm
+
+// ---- sqrt_pst -----------------------------------------------------------------------------------------------------------
+class CommitterKey {  // G1 side of ark-poly-commit CommitterKey: powers_of_g[0], resident on the GPU with window tables
+ public:
+  explicit CommitterKey(const std::vector<G1Affine>& powers_of_g0, int window_bits = 0) : n_(powers_of_g0.size()) {
+    check(tb200_srs_load((const uint64_t*)powers_of_g0.data(), n_, window_bits, &h_));
+  }
+  ~CommitterKey() {
+    if (h_) tb200_srs_free(h_);
+  }
+  CommitterKey(const CommitterKey&) = delete;
+  CommitterKey& operator=(const CommitterKey&) = delete;
+  tb200_srs_t handle() const { return h_; }
+  size_t size() const { return n_; }
+
+ private:
+  tb200_srs_t h_ = nullptr;
+  size_t n_;
+};
+
+// MultilinearPC::commit(ck, poly).g_product for one polynomial
+inline G1Affine pc_commit(const CommitterKey& ck, const std::vector<Fr>& evals) {
+  G1Affine out;
+  check(tb200_msm_g1_batch(ck.handle(), (const uint64_t*)evals.data(), 1, evals.size(), (ptrdiff_t)evals.size(), 1,
+                           TB200_SCALARS_MONT, out.w));
+  return out;
+}
+
+namespace mipp {
+struct InvalidIPVectorLength : std::runtime_error {  // Error::InvalidIPVectorLength, src/mipp.rs:400-421
+  InvalidIPVectorLength() : std::runtime_error("InvalidIPVectorLength") {}
+};
+// src/mipp.rs:385-394
+inline G1Affine multiexponentiation(const std::vector<G1Affine>& left, const std::vector<Fr>& right) {
+  if (left.size() != right.size()) throw InvalidIPVectorLength();
+  return msm::msm_unchecked(left, right);
+}
+// src/mipp.rs:354-367 (G1): vec[i] += vec[i + split]^scaler; vec is truncated to split
+inline void compress(std::vector<G1Affine>& vec, size_t split, const Fr& scaler) {
+  if (vec.size() < 2 * split) throw std::invalid_argument("compress: split too large");
+  check(tb200_compress_g1((uint64_t*)vec.data(), split, scaler.l, TB200_SCALARS_MONT));
+  vec.resize(split);
+}
+// src/mipp.rs:370-383
+inline void compress_field(std::vector<Fr>& vec, size_t split, const Fr& scaler) {
+  for (size_t i = 0; i < split; i++) vec[i] = fr::add(vec[i], fr::mul(vec[split + i], scaler));
+  vec.resize(split);
+}
+struct MippProofG1 {  // G1 fields of MippProof<E> (src/mipp.rs:22-28)
+  std::vector<std::pair<G1Affine, G1Affine>> comms_u;
+  G1Affine final_a;
+  Fr final_y;
+  std::vector<Fr> xs, xs_inv;
+};
+// challenge(label, points appended by the reference) -> c_inv (the Poseidon transcript itself is out of scope)
+using Challenge = std::function<Fr(const char* label, const std::vector<G1Affine>& appended)>;
+// G1 part of MippProof::prove (src/mipp.rs:31-153); vectors stay on the GPU across rounds
+inline MippProofG1 prove_g1(const Challenge& challenge, const std::vector<G1Affine>& a, const std::vector<Fr>& y,
+                            const G1Affine& U) {
+  if (a.size() != y.size()) throw InvalidIPVectorLength();
+  MippProofG1 out;
+  challenge("U", {U});  // src/mipp.rs:56
+  tb200_mipp_t h = nullptr;
+  check(tb200_mipp_g1_begin((const uint64_t*)a.data(), (const uint64_t*)y.data(), a.size(), TB200_SCALARS_MONT, &h));
+  try {
+    while (tb200_mipp_g1_len(h) > 1) {  // src/mipp.rs:58
+      G1Affine ul, ur;
+      check(tb200_mipp_g1_cross(h, ul.w, ur.w));                // :77-85
+      Fr c_inv = challenge("challenge_i", {ul, ur});             // :97-101
+      Fr c = fr::inverse(c_inv);                                 // :106
+      check(tb200_mipp_g1_fold(h, c.l, c_inv.l));                // :110-112
+      out.comms_u.push_back({ul, ur});                           // :117
+      out.xs.push_back(c);
+      out.xs_inv.push_back(c_inv);
+    }
+    check(tb200_mipp_g1_read(h, out.final_a.w, out.final_y.l));  // :122
+  } catch (...) {
+    tb200_mipp_g1_end(h);
+    throw;
+  }
+  check(tb200_mipp_g1_end(h));
+  return out;
+}
+}  // namespace mipp
+
+class Polynomial {  // src/sqrt_pst.rs:14-20
+ public:
+  // src/sqrt_pst.rs:32-75. Z is kept un-transposed: row i is the strided view Z[(j << m_col) | i]
+  static Polynomial from_evaluations(std::vector<Fr> Z) {
+    size_t n = Z.size();
+    if (n == 0 || (n & (n - 1))) throw std::invalid_argument("evaluation list must be a power of two");
+    size_t nv = 0;
+    while ((size_t(1) << nv) < n) nv++;
+    Polynomial p;
+    p.Z_ = std::move(Z);
+    p.m_ = nv / 2;
+    p.odd_ = nv % 2;
+    return p;
+  }
+  size_t m() const { return m_; }
+  size_t odd() const { return odd_; }
+  // src/sqrt_pst.rs:117-149 -> comm_list (g_products). The pairing product t is out of scope.
+  std::vector<G1Affine> commit(const CommitterKey& ck) const {
+    size_t rows = size_t(1) << m_, cols = size_t(1) << (m_ + odd_);
+    if (cols != ck.size()) throw std::invalid_argument("ck.powers_of_g[0] must have 2^m_row points");
+    std::vector<G1Affine> out(rows);
+    check(tb200_msm_g1_batch(ck.handle(), (const uint64_t*)Z_.data(), rows, cols, 1, (ptrdiff_t)rows, TB200_SCALARS_MONT,
+                             (uint64_t*)out.data()));
+    return out;
+  }
+  // src/sqrt_pst.rs:152-166 (bits of i MSB first)
+  static Fr get_chi_i(const std::vector<Fr>& b, size_t i) {
+    size_t m = b.size();
+    Fr prod = fr::one();
+    for (size_t j = 0; j < m; j++) {
+      if ((i >> (m - j - 1)) & 1) prod = fr::mul(prod, b[j]);
+      else prod = fr::mul(prod, fr::sub(fr::one(), b[j]));
+    }
+    return prod;
+  }
+  // src/sqrt_pst.rs:81-101 (the reference's CPU code, unchanged)
+  void get_q(const std::vector<Fr>& point) {
+    std::vector<Fr> b(point.begin() + m_ + odd_, point.end());
+    size_t pow_m = size_t(1) << m_;
+    chis_b_.resize(pow_m);
+    for (size_t i = 0; i < pow_m; i++) chis_b_[i] = get_chi_i(b, i);
+    q_.assign(pow_m << odd_, fr::zero());
+    for (size_t j = 0; j < q_.size(); j++)
+      for (size_t i = 0; i < pow_m; i++) q_[j] = fr::add(q_[j], fr::mul(Z_[(j << m_) | i], chis_b_[i]));
+  }
+  // src/sqrt_pst.rs:105-115
+  Fr eval(const std::vector<Fr>& point) {
+    std::vector<Fr> a(point.begin(), point.begin() + point.size() / 2 + odd_);
+    if (q_.empty()) get_q(point);
+    Fr acc = fr::zero();
+    for (size_t j = 0; j < q_.size(); j++) acc = fr::add(acc, fr::mul(q_[j], get_chi_i(a, j)));
+    return acc;
+  }
+  struct OpenG1 {
+    G1Affine u, comm_q;
+    mipp::MippProofG1 mipp;
+  };
+  // G1 work of src/sqrt_pst.rs:168-230
+  OpenG1 open(const mipp::Challenge& challenge, const std::vector<G1Affine>& comm_list, const CommitterKey& ck,
+              const std::vector<Fr>& point) {
+    if (q_.empty()) get_q(point);
+    if (chis_b_.size() != comm_list.size()) throw std::logic_error("chis.len() == comm_list.len()");  // :194
+    OpenG1 o;
+    o.u = msm::msm_unchecked(comm_list, chis_b_);  // :198
+    o.comm_q = pc_commit(ck, q_);                   // :205
+    if (!(o.u == o.comm_q)) throw std::logic_error("debug_assert!(c_u == comm.g_product) failed");  // :206
+    o.mipp = mipp::prove_g1(challenge, comm_list, chis_b_, o.u);  // :212-213
+    return o;
+  }
+  const std::vector<Fr>& q() const { return q_; }
+  const std::vector<Fr>& chis_b() const { return chis_b_; }
+
+ private:
+  std::vector<Fr> Z_, q_, chis_b_;
+  size_t m_ = 0, odd_ = 0;
+};
+
+// ---- commitments ---------------------------------------------------------------------------------------------------------
+namespace commitments {
+struct MultiCommitGens {  // src/commitments.rs:10-15 (generator derivation :17-39 is out of scope)
+  std::vector<G1Affine> G;
+  G1Affine h;
+  size_t n() const { return G.size(); }
+};
+struct PedersenCommit {
+  // src/commitments.rs:70-77
+  static G1Affine commit_scalar(const Fr& scalar, const Fr& blind, const MultiCommitGens& gens_n) {
+    if (gens_n.n() != 1) throw std::invalid_argument("assert_eq!(gens_n.n, 1)");
+    std::vector<G1Affine> b{gens_n.G[0], gens_n.h};
+    std::vector<Fr> s{scalar, blind};
+    return msm::msm_unchecked(b, s);
+  }
+  // src/commitments.rs:79-86: msm_unchecked(G, scalars) + h * blind as one MSM over G || h
+  static G1Affine commit_slice(const std::vector<Fr>& scalars, const Fr& blind, const MultiCommitGens& gens_n) {
+    if (scalars.size() != gens_n.n()) throw std::invalid_argument("assert_eq!(scalars.len(), gens_n.n)");
+    std::vector<G1Affine> b = gens_n.G;
+    b.push_back(gens_n.h);
+    std::vector<Fr> s = scalars;
+    s.push_back(blind);
+    return msm::msm_unchecked(b, s);
+  }
+};
+// DensePolynomial::commit_inner (src/dense_mlpoly.rs:315-329) with all-zero blinds (every `commit(gens, false)` site)
+inline std::vector<G1Affine> commit_inner(const std::vector<Fr>& Z, size_t L_size, const CommitterKey& gens_srs) {
+  size_t R = Z.size() / L_size;
+  if (L_size * R != Z.size() || R != gens_srs.size()) throw std::invalid_argument("L_size * R_size == Z.len()");
+  std::vector<G1Affine> out(L_size);
+  check(tb200_msm_g1_batch(gens_srs.handle(), (const uint64_t*)Z.data(), L_size, R, (ptrdiff_t)R, 1, TB200_SCALARS_MONT,
+                           (uint64_t*)out.data()));
+  return out;
+}
+}  // namespace commitments
+
+}  // namespace testudo_b200
