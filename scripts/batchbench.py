@@ -29,6 +29,7 @@ for nv in [int(a) for a in sys.argv[1:]] or [20, 26]:
     z = make_scalars_dev(rows * cols, seed=nv + 1)
     out = torch.zeros((rows, 12), dtype=torch.int64, device="cuda")
     lib.tb200_set_profiling(1)
+    lib.tb200_set_accumulate_mode(int(os.environ.get("TB_MODE", "0")))
     for rep in range(2):
         torch.cuda.synchronize()
         t0 = time.time()

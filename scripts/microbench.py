@@ -39,6 +39,7 @@ for logn in sizes:
     scal = make_scalars_dev(n, seed=logn)
     out = torch.zeros(12, dtype=torch.int64, device="cuda")
     lib.tb200_set_profiling(1)
+    lib.tb200_set_accumulate_mode(int(os.environ.get("TB_MODE", "0")))
     for c in ([0] if logn < 20 else [int(x) for x in os.environ.get("TB_CS", "0,16").split(",")]):
         lib.tb200_set_window_bits(c)
         for rep in range(2):

@@ -99,3 +99,61 @@ def test_msm_linearity_property(engine, oracle_c):
     r1, r2, r3 = msm.msm_bigint(bases, s1), msm.msm_bigint(bases, s2), msm.msm_bigint(bases, s3)
     assert np.array_equal(msm.g1_sum(np.stack([r1, r2])), r3)
     assert h.pt_from_np(r3) == o.mul(sum((x + y) * (7 + 11 * k) for k, (x, y) in enumerate(zip(i1, i2))) % o.R_ORDER, o.G)
+
+
+# ---- batched-affine accumulation (mode 2) must give the same points as the XYZZ path and the oracles --------------
+@pytest.fixture
+def affine_mode(engine):
+    engine.tb200_set_accumulate_mode(2)
+    yield engine
+    engine.tb200_set_accumulate_mode(0)
+
+
+@pytest.mark.parametrize("case", GOLD["explicit"] + GOLD["edge"], ids=lambda c: c.get("name", "explicit"))
+def test_affine_mode_edge_golden(affine_mode, case):
+    pts = [h.pt_unhex(p) for p in case["points"]]
+    sc = [int(s, 16) for s in case["scalars"]]
+    assert h.pt_from_np(msm.msm_bigint(h.pts_to_np(pts), h.scalars_to_np(sc))) == h.pt_unhex(case["result"])
+
+
+@pytest.mark.parametrize("case", GOLD["seeded"], ids=lambda c: f"n{c['n']}")
+def test_affine_mode_seeded_golden(affine_mode, case):
+    pts, _ = o.rand_points(case["n"], case["points_seed"])
+    sc = o.rand_scalars(case["n"], case["scalars_seed"])
+    assert h.pt_from_np(msm.msm_bigint(h.pts_to_np(pts), h.scalars_to_np(sc))) == h.pt_unhex(case["result"])
+
+
+@pytest.mark.parametrize("c", [3, 6, 11, 16])
+def test_affine_mode_skewed_duplicates_identities(affine_mode, oracle_c, c):
+    """Heavy buckets, repeated bases (P + P inside a round), P + (-P), identity bases, zero scalars."""
+    n = 1 << 14
+    bases = oracle_c.gen_points(h.pts_to_np([o.mul(99, o.G)])[0], h.pts_to_np([o.mul(31337, o.G)])[0], n)
+    bases[1000:1200] = bases[1000]
+    bases[3000:3100:2] = h.pts_to_np([o.neg(h.pt_from_np(bases[1000]))])[0]   # negations of a repeated base
+    bases[5000:5010] = 0
+    sc = h.np_rand_scalars(n, 50 + c)
+    kind = np.random.default_rng(60 + c).integers(0, 4, size=n)
+    sc[kind < 2] = 0
+    sc[kind == 2] = np.array([1, 0, 0, 0], dtype=np.uint64)
+    sc[1000:1200] = np.array([7, 0, 0, 0], dtype=np.uint64)
+    sc[3000:3100:2] = np.array([7, 0, 0, 0], dtype=np.uint64)
+    affine_mode.tb200_set_window_bits(c)
+    try:
+        got = msm.msm_bigint(bases, sc)
+    finally:
+        affine_mode.tb200_set_window_bits(0)
+    assert np.array_equal(got, oracle_c.msm_g1(bases, sc))
+
+
+def test_affine_mode_equals_xyzz_mode_large(engine, oracle_c):
+    n = 1 << 18
+    bases = oracle_c.gen_points(h.pts_to_np([o.mul(3, o.G)])[0], h.pts_to_np([o.mul(5, o.G)])[0], n)
+    sc = h.np_rand_scalars(n, 77)
+    engine.tb200_set_accumulate_mode(1)
+    a = msm.msm_bigint(bases, sc)
+    engine.tb200_set_accumulate_mode(2)
+    b = msm.msm_bigint(bases, sc)
+    engine.tb200_set_accumulate_mode(0)
+    assert np.array_equal(a, b)
+    ints = h.np_scalars_to_ints(sc)
+    assert h.pt_from_np(a) == o.mul(sum(s * (3 + 5 * k) for k, s in enumerate(ints)) % o.R_ORDER, o.G)

@@ -46,8 +46,17 @@ def test_commit_rows_golden(engine, case):
     ck.close()
 
 
-@pytest.mark.parametrize("nv,window", [(12, 0), (13, 0), (16, 0), (12, 5), (14, 11)])
-def test_commit_vs_c_oracle(engine, oracle_c, nv, window):
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("nv,window", [(12, 0), (13, 0), (16, 0), (17, 0), (12, 5), (14, 11)])
+def test_commit_vs_c_oracle(engine, oracle_c, nv, window, mode):
+    engine.tb200_set_accumulate_mode(mode)
+    try:
+        _commit_vs_c_oracle(engine, oracle_c, nv, window)
+    finally:
+        engine.tb200_set_accumulate_mode(0)
+
+
+def _commit_vs_c_oracle(engine, oracle_c, nv, window):
     m_col = nv // 2
     m_row = nv - m_col
     srs = oracle_c.gen_points(h.pts_to_np([o.mul(31 + nv, o.G)])[0], h.pts_to_np([o.mul(977, o.G)])[0], 1 << m_row)

@@ -52,6 +52,7 @@ SIGNATURES = {
     "tb200_last_geometry": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_uint64),
                                     ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(c_int)]),
     "tb200_set_window_bits": (None, [c_int]),
+    "tb200_set_accumulate_mode": (None, [c_int]),
     "tb200_int_pipe_peak": (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_double)]),
     "tb200_test_fq_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "tb200_test_fq_addsub": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),

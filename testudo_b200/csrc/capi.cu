@@ -13,7 +13,7 @@
 #include <vector>
 
 #include "../../include/testudo_b200.h"
-#include "kernels.cuh"
+#include "kernels_affine.cuh"
 
 using namespace tb;
 
@@ -98,6 +98,7 @@ struct Ctx {
   std::vector<Stage> marks;
   std::map<std::string, double> stage_ms;
   int forced_c = 0;
+  int acc_mode = 0;  // 0 = automatic, 1 = XYZZ segments (k_accumulate), 2 = batched-affine rounds
   // geometry of the last call
   int last_c = 0, last_W = 0, last_K = 0;
   uint64_t last_entries = 0, last_buckets = 0;
@@ -170,6 +171,8 @@ struct Plan {
   uint32_t K, S_max, ntiles;
   std::vector<uint32_t> Ls;  // reduction fan-in per level
   size_t bytes;
+  bool affine;               // batched-affine rounds instead of k_accumulate
+  uint64_t N1, N2;           // upper bounds of the round-0 / round-1 output counts
 };
 
 int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs, int c, int batch, unsigned flags) {
@@ -200,14 +203,24 @@ int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs,
     p.Ls.push_back(L);
     n /= L;
   }
+  // batched-affine accumulation pays off once the GPU is saturated and buckets hold several points
+  p.N1 = (p.M_max + p.B) / 2 + 1;
+  p.N2 = (p.N1 + p.B) / 2 + 1;
+  p.affine = g.acc_mode == 2 || (g.acc_mode == 0 && p.M_max >= (1ull << 23) && p.M_max >= 6 * p.B);
   // arena size
   size_t b = 0;
   b += Arena::pad((p.B + 1) * 4) * 2;  // counts, starts
   b += Arena::pad(p.B * 4);            // cursors
   b += Arena::pad((size_t)p.ntiles * 4 + 4);
   b += Arena::pad(std::max<uint64_t>(p.M_max, 1) * 4);  // entries
-  b += Arena::pad(p.B * 192);                           // buckets
-  b += Arena::pad((size_t)p.S_max * 192) + Arena::pad((size_t)p.S_max * 4);
+  if (p.affine) {
+    b += Arena::pad((p.B + 1) * 4) * 3;                 // sizes, two offset arrays
+    b += Arena::pad(p.N1 * 4) + Arena::pad(p.N1 * 48);  // pair index, prefix-product scratch
+    b += Arena::pad(p.N1 * 96) + Arena::pad(p.N2 * 96); // ping-pong point arrays
+  } else {
+    b += Arena::pad(p.B * 192);                         // buckets
+    b += Arena::pad((size_t)p.S_max * 192) + Arena::pad((size_t)p.S_max * 4);
+  }
   uint64_t n = p.B;
   for (uint32_t L : p.Ls) {
     n /= L;
@@ -230,9 +243,23 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   uint32_t* cursors = g.arena.take<uint32_t>(p.B);
   uint32_t* tile_sums = g.arena.take<uint32_t>(p.ntiles + 1);
   uint32_t* entries = g.arena.take<uint32_t>(std::max<uint64_t>(p.M_max, 1));
-  uint4* buckets = g.arena.take<uint4>(p.B * 12);
-  uint4* heads = g.arena.take<uint4>((size_t)p.S_max * 12);
-  int32_t* head_bucket = g.arena.take<int32_t>(p.S_max);
+  uint4 *buckets = nullptr, *heads = nullptr;
+  int32_t* head_bucket = nullptr;
+  uint32_t *sizes = nullptr, *offA = nullptr, *offB = nullptr, *pidx = nullptr;
+  uint4 *scratch = nullptr, *ptsA = nullptr, *ptsB = nullptr;
+  if (p.affine) {
+    sizes = g.arena.take<uint32_t>(p.B + 1);
+    offA = g.arena.take<uint32_t>(p.B + 1);
+    offB = g.arena.take<uint32_t>(p.B + 1);
+    pidx = g.arena.take<uint32_t>(p.N1);
+    scratch = g.arena.take<uint4>(p.N1 * 3);
+    ptsA = g.arena.take<uint4>(p.N1 * 6);
+    ptsB = g.arena.take<uint4>(p.N2 * 6);
+  } else {
+    buckets = g.arena.take<uint4>(p.B * 12);
+    heads = g.arena.take<uint4>((size_t)p.S_max * 12);
+    head_bucket = g.arena.take<int32_t>(p.S_max);
+  }
 
   g.last_c = q.c;
   g.last_W = q.W;
@@ -261,7 +288,7 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
     CU(cudaGetLastError());
   } else {
     CU(cudaMemsetAsync(counts, 0, (p.B + 1) * 4, st));
-    LAUNCH(k_digits<false>, dig_grid, 256, st, d_scalars, q, counts, (uint32_t*)nullptr);
+    LAUNCH(k_digits<false>, dig_grid, 256, st, d_scalars, q, counts, (uint32_t*)nullptr, -1);
   }
   if (mark(st, "digits")) return 1;
   LAUNCH(k_scan_tile_sums, p.ntiles, SCAN_THREADS, st, counts, (uint32_t)p.B, tile_sums);
@@ -273,10 +300,84 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
     g_launches++;
     CU(cudaGetLastError());
   } else {
-    LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, cursors, entries);
+    // large single MSMs: one pass per window keeps the writes of a pass inside an L2-sized slice of entries[]
+    const bool per_window = !q.batch && q.c >= 19 && (uint64_t)q.cols * 4 * q.W > (64ull << 20);
+    if (per_window) {
+      for (int w = 0; w < q.W; w++) LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, cursors, entries, w);
+    } else {
+      LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, cursors, entries, -1);
+    }
   }
   if (mark(st, "scatter")) return 1;
   if (points_ready) CU(cudaStreamWaitEvent(st, points_ready, 0));  // bases may still be in flight until here
+  const uint4 *inS = nullptr, *inW = nullptr;
+  uint64_t n = p.B;
+  int log2_ell = 0;
+  size_t first_level = 0;
+  if (p.affine) {
+    // ---- batched-affine rounds: every bucket shrinks from n to ceil(n/2) points per round ------------------------
+    uint32_t* d_max = tile_sums + p.ntiles;  // one spare word next to the scan scratch
+    CU(cudaMemsetAsync(d_max, 0, 4, st));
+    LAUNCH(k_max_size, (uint32_t)std::min<uint64_t>(cdiv(p.B, 256), (uint64_t)g.sms * 8), 256, st, starts,
+           (uint32_t)p.B, d_max);
+    uint32_t maxn = 0;
+    CU(cudaMemcpyAsync(&maxn, d_max, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));  // the only host round trip of the pipeline: the number of rounds
+    const uint32_t* off_in = starts;
+    uint32_t* off_bufs[2] = {offA, offB};
+    uint4* pt_bufs[2] = {ptsA, ptsB};
+    const uint4* cur = nullptr;
+    uint64_t n_in_bound = p.M_max;
+    int round = 0;
+    for (; maxn > 1; maxn = (maxn + 1) / 2, round++) {
+      uint32_t* off_out = off_bufs[round & 1];
+      uint4* nxt = pt_bufs[round & 1];
+      const uint64_t n_out_bound = (n_in_bound + p.B) / 2 + 1;
+      LAUNCH(k_half_sizes, cdiv(p.B, 256), 256, st, off_in, (uint32_t)p.B, sizes);
+      LAUNCH(k_scan_tile_sums, p.ntiles, SCAN_THREADS, st, sizes, (uint32_t)p.B, tile_sums);
+      LAUNCH(k_scan_tile_offsets, 1, SCAN_THREADS, st, tile_sums, p.ntiles, tile_sums + p.ntiles);
+      LAUNCH(k_scan_apply, p.ntiles, SCAN_THREADS, st, sizes, (uint32_t)p.B, tile_sums, off_out, cursors);
+      LAUNCH(k_pair_index, cdiv(cdiv(n_out_bound, 8), 256), 256, st, off_in, off_out, (uint32_t)p.B, pidx);
+      // outputs per thread: enough threads for ~2 waves, at least 64 outputs to amortise the inversion
+      uint64_t threads_target = (uint64_t)g.sms * 3 * 128 * 2;
+      uint32_t T = (uint32_t)std::min<uint64_t>(512, std::max<uint64_t>(64, n_out_bound / threads_target));
+      uint32_t warps = cdiv(n_out_bound, 32ull * T);
+      if (round == 0)
+        LAUNCH(k_affine_round<true>, cdiv((uint64_t)warps * 32, 128), 128, st, pidx, off_out, (uint32_t)p.B, T, entries,
+               d_points, cur, nxt, scratch);
+      else
+        LAUNCH(k_affine_round<false>, cdiv((uint64_t)warps * 32, 128), 128, st, pidx, off_out, (uint32_t)p.B, T,
+               entries, d_points, cur, nxt, scratch);
+      off_in = off_out;
+      cur = nxt;
+      n_in_bound = n_out_bound;
+    }
+    if (mark(st, "accumulate")) return 1;
+    if (mark(st, "fixup")) return 1;
+    // level 0 of the reduction reads the (at most one) affine point of every bucket
+    const uint32_t L0 = p.Ls.empty() ? 1 : p.Ls[0];
+    if (round == 0) {
+      // every bucket already has <= 1 entry: materialise the points once through a copy round
+      uint32_t* off_out = off_bufs[0];
+      LAUNCH(k_half_sizes, cdiv(p.B, 256), 256, st, off_in, (uint32_t)p.B, sizes);
+      LAUNCH(k_scan_tile_sums, p.ntiles, SCAN_THREADS, st, sizes, (uint32_t)p.B, tile_sums);
+      LAUNCH(k_scan_tile_offsets, 1, SCAN_THREADS, st, tile_sums, p.ntiles, tile_sums + p.ntiles);
+      LAUNCH(k_scan_apply, p.ntiles, SCAN_THREADS, st, sizes, (uint32_t)p.B, tile_sums, off_out, cursors);
+      LAUNCH(k_pair_index, cdiv(cdiv(p.N1, 8), 256), 256, st, off_in, off_out, (uint32_t)p.B, pidx);
+      LAUNCH(k_affine_round<true>, cdiv(cdiv(p.N1, 32ull * 64) * 32ull, 128), 128, st, pidx, off_out, (uint32_t)p.B,
+             64u, entries, d_points, cur, ptsA, scratch);
+      off_in = off_out;
+      cur = ptsA;
+    }
+    n /= L0;
+    uint4* outS = g.arena.take<uint4>(n * 12);
+    uint4* outW = g.arena.take<uint4>(n * 12);
+    LAUNCH(k_reduce_pass0_affine, cdiv(n, 128), 128, st, cur, off_in, outS, outW, L0, n);
+    inS = outS;
+    inW = outW;
+    for (uint32_t v = L0; v > 1; v >>= 1) log2_ell++;
+    first_level = 1;
+  } else {
   // M is only known on the device (starts[B]); launch for the upper bound, surplus threads exit immediately
   LAUNCH(k_accumulate, cdiv(p.S_max, ACC_THREADS), ACC_THREADS, st, entries, starts, (uint32_t)p.B, p.K, d_points,
          buckets, heads, head_bucket);
@@ -287,12 +388,12 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
     LAUNCH(k_fixup_round, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, round, heads, head_bucket);
   LAUNCH(k_fixup_final, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket);
   if (mark(st, "fixup")) return 1;
+  inS = buckets;
+  }
   // hierarchical bucket reduction
-  const uint4 *inS = buckets, *inW = nullptr;
-  const uint32_t* level0 = starts;
-  uint64_t n = p.B;
-  int log2_ell = 0;
-  for (uint32_t L : p.Ls) {
+  const uint32_t* level0 = p.affine ? nullptr : starts;
+  for (size_t li = first_level; li < p.Ls.size(); li++) {
+    const uint32_t L = p.Ls[li];
     n /= L;
     uint4* outS = g.arena.take<uint4>(n * 12);
     uint4* outW = g.arena.take<uint4>(n * 12);
@@ -302,7 +403,7 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
     level0 = nullptr;
     for (uint32_t v = L; v > 1; v >>= 1) log2_ell++;
   }
-  const uint4* group_w = inW ? inW : buckets;  // nb == 1 (c == 1) never happens: c >= 3
+  const uint4* group_w = inW;  // nb >= 4 (c >= 3): at least one reduction level has run
   if (mark(st, "reduce")) return 1;
   if (q.batch) LAUNCH(k_finalize_batch, cdiv(q.groups, 128), 128, st, group_w, q.groups, d_out);
   else LAUNCH(k_finalize_single, 1, 32, st, group_w, q.W, q.c, d_out);
@@ -397,6 +498,7 @@ int tb200_last_geometry(int* c, int* windows, uint64_t* entries, uint64_t* bucke
   return 0;
 }
 void tb200_set_window_bits(int c) { g.forced_c = (c >= 3 && c <= 22) ? c : 0; }
+void tb200_set_accumulate_mode(int mode) { g.acc_mode = (mode >= 0 && mode <= 2) ? mode : 0; }
 
 // ---- single MSM -------------------------------------------------------------------------------------------------
 static int msm_dev_locked(const void* d_bases, const void* d_scalars, size_t n, unsigned flags, void* d_out,
@@ -509,6 +611,8 @@ static int batch_dev_locked(tb200_srs_t srs, const uint32_t* d_scalars, size_t r
   const uint64_t per_row = (uint64_t)std::max<size_t>(cols, 1) * srs->W;
   const uint64_t nb = 1ull << (srs->c - 1);
   uint64_t chunk = std::min<uint64_t>({(uint64_t)rows, ((1ull << 31) - 1) / per_row, ((1ull << 30)) / nb});
+  // batched-affine rounds keep ~100 B of scratch per sorted entry: bound a chunk to ~2.7e8 entries (~30 GB)
+  if (g.acc_mode != 1) chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(1, (1ull << 28) / per_row));
   if (chunk == 0) return fail(TB200_E_LIMIT, "a single row exceeds the per-pass limits");
   g.marks.clear();
   for (size_t r0 = 0; r0 < rows; r0 += chunk) {
