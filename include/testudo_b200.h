@@ -97,6 +97,14 @@ int tb200_mipp_g1_end(tb200_mipp_t h);
 /* stand-alone `compress` for G1 (src/mipp.rs:354-367): vec[i] = vec[i] + scaler * vec[split + i], i < split */
 int tb200_compress_g1(uint64_t* vec_xy, size_t split, const uint64_t scaler[4], unsigned flags);
 
+/* ---- sqrt_pst scalar work on the device (Fr values in ark Montgomery form) ---------------
+ * chis_out[i] = prod_j (bit(i, m-1-j) ? b[j] : 1 - b[j]), i < 2^m  -- `Polynomial::get_chi_i`, src/sqrt_pst.rs:152-166 */
+int tb200_fr_chis(const uint64_t* b, size_t m, uint64_t* chis_out);
+/* out[j] = sum_i Z[j*cols + i] * v[i], j < rows -- `get_q` (src/sqrt_pst.rs:81-101) with Z[(j << m_col) | i], v = chis,
+ * and `eval` (src/sqrt_pst.rs:105-115) with rows = 1. HBM-bound: 32 B per multiply-add. */
+int tb200_fr_matvec(const uint64_t* Z, size_t rows, size_t cols, const uint64_t* v, uint64_t* out);
+int tb200_fr_matvec_dev(const void* d_Z, size_t rows, size_t cols, const void* d_v, void* d_out, void* stream);
+
 /* ---- group utilities ------------------------------------------------------------------------------------ */
 /* out = sum of n affine points (combining per-GPU partial results after the NCCL all-gather) */
 int tb200_g1_sum(const uint64_t* pts_xy, size_t n, uint64_t out_xy[12]);

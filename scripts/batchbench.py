@@ -59,6 +59,20 @@ for nv in [int(a) for a in sys.argv[1:]] or [20, 26]:
     print(json.dumps({"num_vars": nv, "rows": rows, "cols": cols, "verified_rows": ok, "c": cc.value, "W": W.value,
                       "K": K.value, "entries": M.value, "buckets": B.value, "srs_load_s": round(t_srs, 3),
                       "commit_ms": round(dt * 1e3, 2), "Mpairs_per_s": round(rows * cols / dt / 1e6, 2), "stages": stages}))
+    # get_q on the device: q = Z * chis over the resident matrix, HBM-bound (32 B per element)
+    chis = make_scalars_dev(rows, seed=nv + 2)
+    qv = torch.zeros((cols, 4), dtype=torch.int64, device="cuda")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for rep in range(3):
+        e0.record(st)
+        _lib.check(lib.tb200_fr_matvec_dev(ctypes.c_void_p(z.data_ptr()), cols, rows, ctypes.c_void_p(chis.data_ptr()),
+                                           ctypes.c_void_p(qv.data_ptr()), ctypes.c_void_p(st.cuda_stream)))
+        e1.record(st)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"get_q_num_vars": nv, "ms": round(ms, 3), "GBps": round(rows * cols * 32 / ms / 1e6, 1)}))
     _lib.check(lib.tb200_srs_free(h))
     del z, out
     torch.cuda.empty_cache()

@@ -151,3 +151,19 @@ def test_hyrax_commit_inner_contiguous_rows(engine, oracle_c):
     sc = commitments.PedersenCommit.commit_scalar(h.scalars_to_np([77], mont=True)[0], h.scalars_to_np([88], mont=True)[0], g1)
     assert h.pt_from_np(sc) == o.add(o.mul(77, h.pt_from_np(G[0])), o.mul(88, h.pt_from_np(hpt)))
     gens.close()
+
+
+@pytest.mark.parametrize("nv", [1, 2, 7, 10, 13])
+def test_get_q_chis_eval_on_device(engine, nv):
+    """k_fr_chis / k_fr_matvec vs the reference's CPU loops (src/sqrt_pst.rs:81-115) in integers."""
+    z = o.rand_scalars(1 << nv, 1000 + nv)
+    z[0] = 0
+    z[-1] = o.R_ORDER - 1
+    r = o.rand_scalars(nv, 1100 + nv)
+    poly = sqrt_pst.Polynomial.from_evaluations(h.scalars_to_np(z, mont=True))
+    poly.get_q(r)
+    q_host, chis_host = poly.get_q_host(r)
+    assert np.array_equal(poly.q, q_host)
+    assert np.array_equal(poly.chis_b, chis_host)
+    direct = sum(zi * fr.get_chi_i(r, i) for i, zi in enumerate(z)) % o.R_ORDER      # check_sqrt_poly_eval
+    assert poly.eval(r) == direct

@@ -44,6 +44,9 @@ SIGNATURES = {
     "tb200_mipp_g1_read": (c_int, [c_void_p, c_void_p, c_void_p]),
     "tb200_mipp_g1_end": (c_int, [c_void_p]),
     "tb200_compress_g1": (c_int, [c_void_p, c_size_t, c_void_p, c_uint]),
+    "tb200_fr_chis": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "tb200_fr_matvec": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
+    "tb200_fr_matvec_dev": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
     "tb200_g1_sum": (c_int, [c_void_p, c_size_t, c_void_p]),
     "tb200_g1_sum_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "tb200_g1_outer_sum_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -143,6 +143,8 @@ int pick_c_single(uint64_t n) {
   for (int c = 3; c <= 20; c++) {
     int W = num_windows(c);
     double cost = (double)W * ((double)n + 4.0 * (double)(1u << (c - 1)));
+    int top_bits = SCALAR_BITS - (W - 1) * c;  // payload bits of the top window
+    if (top_bits < 4) cost += 0.5 * (double)n;  // degenerate top window: contended atomics, one giant bucket
     if (cost < bestc) {
       bestc = cost;
       best = c;
@@ -206,7 +208,10 @@ int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs,
   // batched-affine accumulation pays off once the GPU is saturated and buckets hold several points
   p.N1 = (p.M_max + p.B) / 2 + 1;
   p.N2 = (p.N1 + p.B) / 2 + 1;
-  p.affine = g.acc_mode == 2 || (g.acc_mode == 0 && p.M_max >= (1ull << 23) && p.M_max >= 6 * p.B);
+  // Opt-in only. Measured on B200 at 2^24 (profiles/r01_summary.md): the rounds move ~105 GB through HBM and pay
+  // one Fermat inversion per thread per round, which outweighs the 30% fewer multiplications; the XYZZ segment
+  // kernel (85% of the integer pipe) stays the automatic choice.
+  p.affine = g.acc_mode == 2;
   // arena size
   size_t b = 0;
   b += Arena::pad((p.B + 1) * 4) * 2;  // counts, starts
@@ -612,7 +617,7 @@ static int batch_dev_locked(tb200_srs_t srs, const uint32_t* d_scalars, size_t r
   const uint64_t nb = 1ull << (srs->c - 1);
   uint64_t chunk = std::min<uint64_t>({(uint64_t)rows, ((1ull << 31) - 1) / per_row, ((1ull << 30)) / nb});
   // batched-affine rounds keep ~100 B of scratch per sorted entry: bound a chunk to ~2.7e8 entries (~30 GB)
-  if (g.acc_mode != 1) chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(1, (1ull << 28) / per_row));
+  if (g.acc_mode == 2) chunk = std::min<uint64_t>(chunk, std::max<uint64_t>(1, (1ull << 28) / per_row));
   if (chunk == 0) return fail(TB200_E_LIMIT, "a single row exceeds the per-pass limits");
   g.marks.clear();
   for (size_t r0 = 0; r0 < rows; r0 += chunk) {
@@ -814,6 +819,63 @@ int tb200_compress_g1(uint64_t* vec_xy, size_t split, const uint64_t scaler[4], 
   cudaFreeAsync(d_v, g.stream);
   cudaFreeAsync(d_k, g.stream);
   return 0;
+}
+
+// ---- sqrt_pst scalar work on the device -------------------------------------------------------------------------------
+int tb200_fr_chis(const uint64_t* b, size_t m, uint64_t* chis_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!chis_out || (m && !b) || m > 28) return fail(TB200_E_ARG, "bad arguments (m = %zu)", m);
+  CU(cudaSetDevice(g.device));
+  const size_t n = size_t(1) << m;
+  uint32_t *d_b = nullptr, *d_o = nullptr;
+  CU(cudaMallocAsync((void**)&d_b, std::max<size_t>(m, 1) * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_o, n * 32, g.stream));
+  if (m) CU(cudaMemcpyAsync(d_b, b, m * 32, cudaMemcpyHostToDevice, g.stream));
+  LAUNCH(k_fr_chis, cdiv(n, 128), 128, g.stream, d_b, (uint32_t)m, d_o);
+  CU(cudaMemcpyAsync(chis_out, d_o, n * 32, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  cudaFreeAsync(d_b, g.stream);
+  cudaFreeAsync(d_o, g.stream);
+  return 0;
+}
+int tb200_fr_matvec_dev(const void* d_Z, size_t rows, size_t cols, const void* d_v, void* d_out, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_out || ((rows && cols) && (!d_Z || !d_v))) return fail(TB200_E_ARG, "null pointer");
+  if (rows >= (1ull << 31) || cols >= (1ull << 31)) return fail(TB200_E_LIMIT, "matrix too large");
+  if (((uintptr_t)d_Z | (uintptr_t)d_v | (uintptr_t)d_out) & 15) return fail(TB200_E_ARG, "device pointers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  CU(cudaSetDevice(g.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+  LAUNCH(k_fr_matvec, cdiv(rows * 32, 256), 256, st, (const uint32_t*)d_Z, (uint32_t)rows, (uint32_t)cols,
+         (const uint32_t*)d_v, (uint32_t*)d_out);
+  return 0;
+}
+int tb200_fr_matvec(const uint64_t* Z, size_t rows, size_t cols, const uint64_t* v, uint64_t* out) {
+  uint32_t *d_z = nullptr, *d_v = nullptr, *d_o = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (need_ready()) return TB200_E_STATE;
+    if (!out || !Z || !v || rows == 0 || cols == 0) return fail(TB200_E_ARG, "bad arguments");
+    CU(cudaSetDevice(g.device));
+    CU(cudaMallocAsync((void**)&d_z, rows * cols * 32, g.stream));
+    CU(cudaMallocAsync((void**)&d_v, cols * 32, g.stream));
+    CU(cudaMallocAsync((void**)&d_o, rows * 32, g.stream));
+    CU(cudaMemcpyAsync(d_z, Z, rows * cols * 32, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(d_v, v, cols * 32, cudaMemcpyHostToDevice, g.stream));
+  }
+  int rc = tb200_fr_matvec_dev(d_z, rows, cols, d_v, d_o, nullptr);
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out, d_o, rows * 32, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d_z, g.stream);
+  cudaFreeAsync(d_v, g.stream);
+  cudaFreeAsync(d_o, g.stream);
+  return rc;
 }
 
 // ---- group utilities ---------------------------------------------------------------------------------------------

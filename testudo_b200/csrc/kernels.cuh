@@ -548,6 +548,61 @@ __global__ void __launch_bounds__(128) k_compress_fr(uint32_t* __restrict__ y, u
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// sqrt_pst scalar work: chi products, q = Z * chi, dot product -- Fr, Montgomery form
+// ------------------------------------------------------------------------------------------------------------
+// chis[i] = prod_j (bit_{m-1-j}(i) ? b[j] : 1 - b[j])   (Polynomial::get_chi_i, src/sqrt_pst.rs:152-166)
+__global__ void __launch_bounds__(128) k_fr_chis(const uint32_t* __restrict__ b, uint32_t m, uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (1u << m)) return;
+  uint32_t prod[8], one[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) prod[k] = one[k] = FrParams::one(k);
+  for (uint32_t j = 0; j < m; j++) {
+    uint32_t f[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) f[k] = b[8 * j + k];
+    if (!((i >> (m - j - 1)) & 1)) mod_sub<FrParams>(f, one, f);
+    mont_mul<FrParams>(prod, prod, f);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) out[8 * (uint64_t)i + k] = prod[k];
+}
+__device__ __forceinline__ void fr_warp_sum(uint32_t* acc) {  // butterfly sum over the 32 lanes
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    uint32_t other[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) other[k] = __shfl_xor_sync(0xffffffffu, acc[k], o);
+    mod_add<FrParams>(acc, acc, other);
+  }
+}
+// q[j] = sum_i Z[j * cols + i] * v[i]  (get_q, src/sqrt_pst.rs:81-101: Z[(j << m_col) | i] * chis[i]); one warp per j,
+// lanes read 32 consecutive scalars (1 KiB) per step. HBM-bound: 32 B per multiply-add.
+__global__ void __launch_bounds__(256) k_fr_matvec(const uint32_t* __restrict__ Z, uint32_t rows, uint32_t cols,
+                                                   const uint32_t* __restrict__ v, uint32_t* __restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (j >= rows) return;
+  uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (uint32_t i = lane; i < cols; i += 32) {
+    const uint4* zp = reinterpret_cast<const uint4*>(Z + 8 * (j * cols + i));
+    const uint4* vp = reinterpret_cast<const uint4*>(v + 8 * (uint64_t)i);
+    uint4 z0 = __ldg(zp), z1 = __ldg(zp + 1), v0 = __ldg(vp), v1 = __ldg(vp + 1);
+    uint32_t a[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+    uint32_t c[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t t[8];
+    mont_mul<FrParams>(t, a, c);
+    mod_add<FrParams>(acc, acc, t);
+  }
+  fr_warp_sum(acc);
+  if (lane == 0) {
+    uint4* op = reinterpret_cast<uint4*>(out + 8 * j);
+    op[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+    op[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------------------------
 // out = sum of n affine points (n small: per-GPU partial results)

@@ -110,25 +110,38 @@ class Polynomial:
         return out, None
 
     def get_q(self, point: List[int]) -> None:
-        """src/sqrt_pst.rs:81-101 (the reference's CPU code, unchanged by the engine). `point` as integers mod r."""
+        """src/sqrt_pst.rs:81-101 on the GPU: chis by k_fr_chis, q = Z * chis by k_fr_matvec.
+        `point` as integers mod r."""
         assert len(point) == 2 * self.m + self.odd
+        lib = _lib.engine()
+        b = fr.to_mont_words(point[self.m + self.odd:]) if self.m else np.zeros((0, 4), dtype=np.uint64)
+        pow_m = 1 << self.m
+        chis = np.zeros((pow_m, 4), dtype=np.uint64)
+        _lib.check(lib.tb200_fr_chis(_ptr(b), self.m, _ptr(chis)))
+        q = np.zeros((pow_m << self.odd, 4), dtype=np.uint64)
+        _lib.check(lib.tb200_fr_matvec(_ptr(self.Z), len(q), pow_m, _ptr(chis), _ptr(q)))
+        self.q, self.chis_b = q, chis
+
+    def get_q_host(self, point: List[int]) -> Tuple[np.ndarray, np.ndarray]:
+        """The same with Python integers (the reference's CPU loop); cross-check for tests, small sizes only."""
         b = point[self.m + self.odd:]
         pow_m = 1 << self.m
         chis = [fr.get_chi_i(b, i) for i in range(pow_m)]
         zi = fr.from_mont_words(self.Z)
-        zq = []
-        for j in range(pow_m << self.odd):
-            zq.append(sum(zi[(j << self.m) | i] * chis[i] for i in range(pow_m)) % fr.R)
-        self.q = fr.to_mont_words(zq)
-        self.chis_b = fr.to_mont_words(chis)
+        zq = [sum(zi[(j << self.m) | i] * chis[i] for i in range(pow_m)) % fr.R for j in range(pow_m << self.odd)]
+        return fr.to_mont_words(zq), fr.to_mont_words(chis)
 
     def eval(self, point: List[int]) -> int:
-        """src/sqrt_pst.rs:105-115."""
+        """src/sqrt_pst.rs:105-115: q(a) = sum_j q[j] * chi_j(a), on the GPU."""
         a = point[: len(point) // 2 + self.odd]
         if self.q is None:
             self.get_q(point)
-        q = fr.from_mont_words(self.q)
-        return sum(qj * fr.get_chi_i(a, j) for j, qj in enumerate(q)) % fr.R
+        lib = _lib.engine()
+        chis_a = np.zeros((len(self.q), 4), dtype=np.uint64)
+        _lib.check(lib.tb200_fr_chis(_ptr(fr.to_mont_words(a)), len(a), _ptr(chis_a)))
+        out = np.zeros((1, 4), dtype=np.uint64)
+        _lib.check(lib.tb200_fr_matvec(_ptr(self.q), 1, len(self.q), _ptr(chis_a), _ptr(out)))
+        return fr.from_mont_words(out)[0]
 
     def open(self, challenge: Callable[[bytes, List[np.ndarray]], int], comm_list: np.ndarray, ck: CommitterKey,
              point: List[int]) -> OpenG1:
