@@ -123,8 +123,9 @@ double tb200_stage_ms(const char* stage);
 int tb200_last_geometry(int* c, int* windows, uint64_t* entries, uint64_t* buckets, int* segment);
 /* override the automatic window choice for single MSMs (0 = automatic) */
 void tb200_set_window_bits(int c);
-/* bucket-accumulation method: 0 = automatic, 1 = XYZZ mixed additions over balanced segments (k_accumulate),
- * 2 = batched-affine pairwise rounds (Montgomery's trick; large inputs). Both give identical results. */
+/* bucket-accumulation method: 0 = automatic (currently 3); 1 = XYZZ mixed additions over balanced segments with
+ * register operands (k_accumulate); 2 = batched-affine pairwise rounds (Montgomery's trick; experimental, slower
+ * on B200 -- DESIGN.md); 3 = XYZZ segments with shared-memory operand slots (k_accumulate_s). Identical results. */
 void tb200_set_accumulate_mode(int mode);
 /* integer-pipe microbenchmark: runs `iters` dependent-chain iterations of wide MACs on every SM and returns the
  * achieved 32x32->64 multiply-accumulates per second in *out_macs_per_s (kind: 0 = IMAD.WIDE.U32 reg-reg,

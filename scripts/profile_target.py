@@ -18,6 +18,7 @@ bases = make_bases_dev(n, seed=3)
 scal = make_scalars_dev(n, seed=4)
 out = torch.zeros(12, dtype=torch.int64, device="cuda")
 lib.tb200_set_window_bits(c)
+lib.tb200_set_accumulate_mode(int(os.environ.get("TB_MODE", "0")))
 for _ in range(2):
     _lib.check(lib.tb200_msm_g1_dev(bases.data_ptr(), scal.data_ptr(), n, 0, out.data_ptr(), None))
     torch.cuda.synchronize()

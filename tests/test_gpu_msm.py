@@ -25,11 +25,17 @@ def test_msm_seeded_golden(engine, case):
     assert h.pt_from_np(msm.msm_unchecked(h.pts_to_np(pts), h.scalars_to_np(sc, mont=True))) == exp
 
 
+@pytest.mark.parametrize("mode", [1, 3])
 @pytest.mark.parametrize("case", GOLD["explicit"] + GOLD["edge"], ids=lambda c: c.get("name", "explicit"))
-def test_msm_explicit_and_edge_golden(engine, case):
+def test_msm_explicit_and_edge_golden(engine, case, mode):
     pts = [h.pt_unhex(p) for p in case["points"]]
     sc = [int(s, 16) for s in case["scalars"]]
-    assert h.pt_from_np(msm.msm_bigint(h.pts_to_np(pts), h.scalars_to_np(sc))) == h.pt_unhex(case["result"])
+    engine.tb200_set_accumulate_mode(mode)
+    try:
+        got = msm.msm_bigint(h.pts_to_np(pts), h.scalars_to_np(sc))
+    finally:
+        engine.tb200_set_accumulate_mode(0)
+    assert h.pt_from_np(got) == h.pt_unhex(case["result"])
 
 
 def test_msm_empty_and_length_rules(engine):
@@ -43,8 +49,17 @@ def test_msm_empty_and_length_rules(engine):
     assert h.pt_from_np(msm.msm_bigint(B[:0], S[:0])) is None            # n == 0 -> identity
 
 
+@pytest.mark.parametrize("mode", [1, 3])
 @pytest.mark.parametrize("c", [3, 5, 8, 11, 13, 16])
-def test_msm_every_window_width(engine, oracle_c, c):
+def test_msm_every_window_width(engine, oracle_c, c, mode):
+    engine.tb200_set_accumulate_mode(mode)
+    try:
+        _every_window_width(engine, c)
+    finally:
+        engine.tb200_set_accumulate_mode(0)
+
+
+def _every_window_width(engine, c):
     n = 700
     pts, dl = o.rand_points(n, 300 + c)
     sc = o.rand_scalars(n, 400 + c)
@@ -72,7 +87,16 @@ def test_msm_vs_c_oracle_and_dlog(engine, oracle_c, logn):
     assert h.pt_from_np(got) == o.mul(sum(s * (a + step * k) for k, s in enumerate(ints)) % o.R_ORDER, o.G)
 
 
-def test_msm_skewed_scalars_heavy_buckets(engine, oracle_c):
+@pytest.mark.parametrize("mode", [1, 3])
+def test_msm_skewed_scalars_heavy_buckets(engine, oracle_c, mode):
+    engine.tb200_set_accumulate_mode(mode)
+    try:
+        _skewed_heavy_buckets(oracle_c)
+    finally:
+        engine.tb200_set_accumulate_mode(0)
+
+
+def _skewed_heavy_buckets(oracle_c):
     """R1CS-like witness: 50% zeros, 25% ones, 25% uniform, repeated bases -> a few huge
     buckets that span many accumulation segments and exercise the head/fix-up path and the doubling branch."""
     n = 1 << 15
@@ -153,7 +177,9 @@ def test_affine_mode_equals_xyzz_mode_large(engine, oracle_c):
     a = msm.msm_bigint(bases, sc)
     engine.tb200_set_accumulate_mode(2)
     b = msm.msm_bigint(bases, sc)
+    engine.tb200_set_accumulate_mode(3)
+    c3 = msm.msm_bigint(bases, sc)
     engine.tb200_set_accumulate_mode(0)
-    assert np.array_equal(a, b)
+    assert np.array_equal(a, b) and np.array_equal(a, c3)
     ints = h.np_scalars_to_ints(sc)
     assert h.pt_from_np(a) == o.mul(sum(s * (3 + 5 * k) for k, s in enumerate(ints)) % o.R_ORDER, o.G)

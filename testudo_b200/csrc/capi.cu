@@ -14,6 +14,7 @@
 
 #include "../../include/testudo_b200.h"
 #include "kernels_affine.cuh"
+#include "kernels_smem.cuh"
 
 using namespace tb;
 
@@ -98,7 +99,8 @@ struct Ctx {
   std::vector<Stage> marks;
   std::map<std::string, double> stage_ms;
   int forced_c = 0;
-  int acc_mode = 0;  // 0 = automatic, 1 = XYZZ segments (k_accumulate), 2 = batched-affine rounds
+  int acc_mode = 0;  // 0 = automatic (= 3), 1 = XYZZ segments, register operands (k_accumulate), 2 = batched-affine
+                     // rounds, 3 = XYZZ segments, shared-memory operand slots (k_accumulate_s)
   // geometry of the last call
   int last_c = 0, last_W = 0, last_K = 0;
   uint64_t last_entries = 0, last_buckets = 0;
@@ -384,8 +386,16 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
     first_level = 1;
   } else {
   // M is only known on the device (starts[B]); launch for the upper bound, surplus threads exit immediately
-  LAUNCH(k_accumulate, cdiv(p.S_max, ACC_THREADS), ACC_THREADS, st, entries, starts, (uint32_t)p.B, p.K, d_points,
-         buckets, heads, head_bucket);
+  if (g.acc_mode == 3 || g.acc_mode == 0) {  // default: operands in shared-memory slots (kernels_smem.cuh)
+    CU(cudaFuncSetAttribute(k_accumulate_s, cudaFuncAttributeMaxDynamicSharedMemorySize, ACCS_SMEM));
+    k_accumulate_s<<<cdiv(p.S_max, ACCS_THREADS), ACCS_THREADS, ACCS_SMEM, st>>>(entries, starts, (uint32_t)p.B, p.K,
+                                                                                d_points, buckets, heads, head_bucket);
+    g_launches++;
+    CU(cudaGetLastError());
+  } else {
+    LAUNCH(k_accumulate, cdiv(p.S_max, ACC_THREADS), ACC_THREADS, st, entries, starts, (uint32_t)p.B, p.K, d_points,
+           buckets, heads, head_bucket);
+  }
   if (mark(st, "accumulate")) return 1;
   // a bucket can span at most S_max segments: ceil(log2(S_max)) pointer-jumping rounds cover the worst case.
   // Rounds beyond the largest bucket are empty launches (a few microseconds each).
@@ -503,7 +513,7 @@ int tb200_last_geometry(int* c, int* windows, uint64_t* entries, uint64_t* bucke
   return 0;
 }
 void tb200_set_window_bits(int c) { g.forced_c = (c >= 3 && c <= 22) ? c : 0; }
-void tb200_set_accumulate_mode(int mode) { g.acc_mode = (mode >= 0 && mode <= 2) ? mode : 0; }
+void tb200_set_accumulate_mode(int mode) { g.acc_mode = (mode >= 0 && mode <= 3) ? mode : 0; }
 
 // ---- single MSM -------------------------------------------------------------------------------------------------
 static int msm_dev_locked(const void* d_bases, const void* d_scalars, size_t n, unsigned flags, void* d_out,
