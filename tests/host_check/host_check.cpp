@@ -84,6 +84,8 @@ int hc_add_fast_chain(const uint32_t* pts_aff, int n, int dbls, const uint32_t* 
   return overflow;
 }
 void hc_fq_canon(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.l, a, 48); fq_canon(x); memcpy(r, x.l, 48); }
+void hc_fq_sqr_lazy(const uint32_t* a, uint32_t* r) { mont_sqr_lazy<FqParams>(r, a); }
+void hc_fr_sqr_lazy(const uint32_t* a, uint32_t* r) { mont_sqr_lazy<FrParams>(r, a); }
 void hc_fq_mul_lazy(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul_lazy<FqParams>(r, a, b); }
 // signed digits of one canonical scalar with window c: out[w] in [-2^(c-1), 2^(c-1)]
 int hc_digits(const uint32_t* s, int c, int32_t* out) {

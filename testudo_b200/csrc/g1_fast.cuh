@@ -87,6 +87,21 @@ inline Fq fq_mul_call(Fq a, Fq b) {
 }
 #endif
 
+// dedicated squaring (78 + 132 wide MACs instead of 144 + 132), same calling convention
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ Fq fq_sqr_call(Fq a) {
+  Fq r;
+  mont_sqr_lazy<FqParams>(r.l, a.l);
+  return r;
+}
+#else
+inline Fq fq_sqr_call(Fq a) {
+  Fq r;
+  mont_sqr_lazy<FqParams>(r.l, a.l);
+  return r;
+}
+#endif
+
 // exact path for the exceptional cases; operands by value so the caller's registers never get an address
 #if defined(__CUDA_ARCH__)
 __device__ __noinline__
@@ -127,12 +142,12 @@ TB_HD void xyzz_madd_fast(Xyzz& p, const Affine& q) {
     }
   }
   Fq t, ppp, qq;
-  t = fq_mul_call(pp, pp);         // PP  < 1.8q
+  t = fq_sqr_call(pp);             // PP  < 1.8q
   ppp = fq_mul_call(pp, t);        // PPP < 1.2q
   qq = fq_mul_call(p.x, t);        // Q   < 1.2q
   p.zz = fq_mul_call(p.zz, t);     // ZZ3  < 2q
   p.zzz = fq_mul_call(p.zzz, ppp); // ZZZ3 < 2q
-  t = fq_mul_call(rr, rr);         // RR  < 1.3q
+  t = fq_sqr_call(rr);             // RR  < 1.3q
   fq_sub_lazy<0>(t, t, ppp);       // RR + 2q - PPP
   fq_sub_lazy<0>(t, t, qq);        //    + 2q - Q
   fq_sub_lazy<0>(p.x, t, qq);      // X3 = ... + 2q - Q  < 7.3q  (invariant X < 8q)
@@ -180,14 +195,14 @@ TB_HD void xyzz_add_fast(Xyzz& p, const Xyzz& q) {
     }
   }
   Fq pp, ppp, t;
-  pp = fq_mul_call(u2, u2);        // PP  < 1.1q
+  pp = fq_sqr_call(u2);            // PP  < 1.1q
   ppp = fq_mul_call(u2, pp);       // PPP < 1.1q
   u1 = fq_mul_call(u1, pp);        // Q   < 1.1q
   t = fq_mul_call(p.zz, q.zz);
   p.zz = fq_mul_call(t, pp);       // ZZ3  < 2q
   t = fq_mul_call(p.zzz, q.zzz);
   p.zzz = fq_mul_call(t, ppp);     // ZZZ3 < 2q
-  t = fq_mul_call(s2, s2);         // RR < 1.1q
+  t = fq_sqr_call(s2);             // RR < 1.1q
   fq_sub_lazy<0>(t, t, ppp);
   fq_sub_lazy<0>(t, t, u1);
   fq_sub_lazy<0>(p.x, t, u1);      // X3 < 7.1q
@@ -206,10 +221,10 @@ TB_HD void xyzz_dbl_fast(Xyzz& p) {
   u.l[0] = add_cc(p.y.l[0], p.y.l[0], c);
 #pragma unroll
   for (int i = 1; i < 12; i++) u.l[i] = addc_cc(p.y.l[i], p.y.l[i], c);
-  v = fq_mul_call(u, u);           // V < 1.5q
+  v = fq_sqr_call(u);              // V < 1.5q
   w = fq_mul_call(u, v);           // W < 1.1q
   s = fq_mul_call(p.x, v);         // S < 1.1q
-  m = fq_mul_call(p.x, p.x);       // X^2 < 1.5q
+  m = fq_sqr_call(p.x);            // X^2 < 1.5q
   Carry d;
   t.l[0] = add_cc(m.l[0], m.l[0], d);
 #pragma unroll
@@ -219,7 +234,7 @@ TB_HD void xyzz_dbl_fast(Xyzz& p) {
 #pragma unroll
   for (int i = 1; i < 12; i++) m.l[i] = addc_cc(t.l[i], m.l[i], e);   // M = 3 X^2 < 4.5q
   t = fq_mul_call(w, p.y);         // W * Y1 < 1.1q
-  Fq mm = fq_mul_call(m, m);       // < 1.2q
+  Fq mm = fq_sqr_call(m);          // < 1.2q
   fq_sub_lazy<0>(mm, mm, s);
   fq_sub_lazy<0>(p.x, mm, s);      // X3 = M^2 + 4q - 2S < 5.2q
   fq_sub_lazy<2>(s, s, p.x);       // S + 8q - X3 < 9.1q

@@ -39,6 +39,13 @@ __device__ __noinline__ void slot_mul(uint4* sm, int d, int a, int b) {
   mont_mul_lazy<FqParams>(r.l, x.l, y.l);
   slot_store(sm, d, r);
 }
+// d = a * a (dedicated squaring)
+__device__ __noinline__ void slot_sqr(uint4* sm, int d, int a) {
+  Fq x, r;
+  slot_load(x, sm, a);
+  mont_sqr_lazy<FqParams>(r.l, x.l);
+  slot_store(sm, d, r);
+}
 // d = a + k*q - b; returns the low limb of the result (for the P = 0 mod q filter)
 template <int SEL>
 __device__ __forceinline__ uint32_t slot_sub(uint4* sm, int d, int a, int b) {
@@ -87,12 +94,12 @@ __device__ __forceinline__ void madd_slots(uint4* sm, const Affine& q, bool& inf
       return;
     }
   }
-  slot_mul(sm, SA, SPP, SPP);                     // PP   (slot A)
+  slot_sqr(sm, SA, SPP);                          // PP   (slot A)
   slot_mul(sm, SB, SPP, SA);                      // PPP  (slot B)
   slot_mul(sm, SQQ, SX, SA);                      // Q
   slot_mul(sm, SZZ, SZZ, SA);                     // ZZ3
   slot_mul(sm, SZZZ, SZZZ, SB);                   // ZZZ3
-  slot_mul(sm, SA, SRR, SRR);                     // RR   (slot A)
+  slot_sqr(sm, SA, SRR);                          // RR   (slot A)
   slot_sub<0>(sm, SA, SA, SB);                    // RR + 2q - PPP
   slot_sub<0>(sm, SA, SA, SQQ);                   //    + 2q - Q
   slot_sub<0>(sm, SX, SA, SQQ);                   // X3

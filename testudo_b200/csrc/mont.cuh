@@ -382,6 +382,112 @@ TB_HD void mont_mul_lazy(uint32_t* r, const uint32_t* a, const uint32_t* b) {
   for (int j = 1; j < N; j++) r[j] = addc_cc(e[j], o[j - 1], c);
 }
 
+// r = a * a * R^-1 (mod p), lazily reduced like mont_mul_lazy, with 78 instead of 144 product MACs (N = 12):
+// row i takes a_i * a_i (weight 2^(64 i)) and a_i * 2 a_j for j > i only. The doubled operand is prepared once:
+// d[j] = limb j of 2a, dc[j] = (a_j << 1) without the bit shifted in from a_{j-1} (the lowest doubled limb of a row
+// must not contain a_i's top bit). Relative to the row's base the products land on the same limb positions as in
+// mont_mul_lazy, so the even/odd accumulators, the Montgomery step and all bounds are unchanged (the row sums only
+// regroup the same total). Requires a < 2^(32N-1) (true for every lazily reduced Fq value: < 16 q < 2^381).
+template <class P>
+TB_HD void mont_sqr_lazy(uint32_t* r, const uint32_t* a) {
+  constexpr int N = P::N;
+  uint32_t d[N], dc[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    dc[j] = a[j] << 1;
+    d[j] = j ? (dc[j] | (a[j - 1] >> 31)) : dc[j];
+  }
+  uint32_t e[N + 1], o[N], x = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    const uint32_t ai = a[i];
+    Carry c;
+    // v(j): the row's operand at relative limb j (j >= i)
+#define TB_SQR_V(j) ((j) == i ? ai : ((j) == i + 1 ? dc[(j)] : d[(j)]))
+    if (i == 0) {
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        e[j] = mul_lo(ai, TB_SQR_V(j));
+        e[j + 1] = mul_hi(ai, TB_SQR_V(j));
+        o[j] = mul_lo(ai, TB_SQR_V(j + 1));
+        o[j + 1] = mul_hi(ai, TB_SQR_V(j + 1));
+      }
+      e[N] = 0;
+    } else {
+      // E: even relative limbs j >= i
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int je = (i & 1) ? i + 1 : i;  // first even j >= i
+      const int jo = (i & 1) ? i : i + 1;  // first odd  j >= i
+      if (je < N) {
+        e[je] = mad_lo_cc(ai, TB_SQR_V(je), e[je], c);
+        e[je + 1] = madc_hi_cc(ai, TB_SQR_V(je), e[je + 1], c);
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+          if (j > je) {
+            e[j] = madc_lo_cc(ai, TB_SQR_V(j), e[j], c);
+            e[j + 1] = madc_hi_cc(ai, TB_SQR_V(j), e[j + 1], c);
+          }
+        }
+        e[N] = addc(e[N], 0, c);
+      }
+      if (jo < N) {
+        o[jo - 1] = mad_lo_cc(ai, TB_SQR_V(jo), o[jo - 1], c);
+        if (jo == N - 1) {
+          o[jo] = madc_hi(ai, TB_SQR_V(jo), o[jo], c);
+        } else {
+          o[jo] = madc_hi_cc(ai, TB_SQR_V(jo), o[jo], c);
+#pragma unroll
+          for (int j = 1; j < N; j += 2) {
+            if (j > jo && j < N - 1) {
+              o[j - 1] = madc_lo_cc(ai, TB_SQR_V(j), o[j - 1], c);
+              o[j] = madc_hi_cc(ai, TB_SQR_V(j), o[j], c);
+            }
+          }
+          o[N - 2] = madc_lo_cc(ai, TB_SQR_V(N - 1), o[N - 2], c);
+          o[N - 1] = madc_hi(ai, TB_SQR_V(N - 1), o[N - 1], c);
+        }
+      }
+    }
+#undef TB_SQR_V
+    uint32_t s = add_cc(e[0], x, c);
+    uint32_t k = addc(0, 0, c);
+    (void)add_cc(s, 0xffffffffu, c);
+    k = addc(k, 0, c);
+    uint32_t m = neg32(s);
+    e[1] = add_cc(e[1], k, c);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      e[j] = madc_lo_cc(m, P::p(j), e[j], c);
+      e[j + 1] = madc_hi_cc(m, P::p(j), e[j + 1], c);
+    }
+    e[N] = addc(e[N], 0, c);
+    o[0] = mad_lo_cc(m, P::p(1), o[0], c);
+    o[1] = madc_hi_cc(m, P::p(1), o[1], c);
+#pragma unroll
+    for (int j = 2; j < N - 2; j += 2) {
+      o[j] = madc_lo_cc(m, P::p(j + 1), o[j], c);
+      o[j + 1] = madc_hi_cc(m, P::p(j + 1), o[j + 1], c);
+    }
+    o[N - 2] = madc_lo_cc(m, P::p(N - 1), o[N - 2], c);
+    o[N - 1] = madc_hi(m, P::p(N - 1), o[N - 1], c);
+    x = e[1];
+    uint32_t t[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) t[j] = o[j];
+#pragma unroll
+    for (int j = 0; j < N - 1; j++) o[j] = e[j + 2];
+    o[N - 1] = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) e[j] = t[j];
+    e[N] = 0;
+  }
+  Carry c;
+  r[0] = add_cc(e[0], x, c);
+#pragma unroll
+  for (int j = 1; j < N; j++) r[j] = addc_cc(e[j], o[j - 1], c);
+}
+
 // canonical product: inputs < p, output < p
 template <class P>
 TB_HD void mont_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
