@@ -285,12 +285,12 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   // batches with enough rows to fill the GPU sort each row inside one CTA's shared memory
   const size_t row_smem = (size_t)q.nb * 4;
   const bool row_sort = q.batch && q.rows >= (uint32_t)g.sms && row_smem <= 160 * 1024;
+  // >= 116 KB of dynamic shared memory => one CTA per SM (see k_batch_digits)
+  const size_t row_smem_launch = std::max<size_t>(row_smem, 116 * 1024);
   if (row_sort) {
-    if (row_smem > 48 * 1024) {
-      CU(cudaFuncSetAttribute(k_batch_digits<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
-      CU(cudaFuncSetAttribute(k_batch_digits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem));
-    }
-    k_batch_digits<false><<<q.rows, 256, row_smem, st>>>(d_scalars, q, counts, (uint32_t*)nullptr);
+    CU(cudaFuncSetAttribute(k_batch_digits<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_launch));
+    CU(cudaFuncSetAttribute(k_batch_digits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_launch));
+    k_batch_digits<false><<<q.rows, 1024, row_smem_launch, st>>>(d_scalars, q, counts, (uint32_t*)nullptr);
     g_launches++;
     CU(cudaGetLastError());
   } else {
@@ -303,7 +303,7 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   LAUNCH(k_scan_apply, p.ntiles, SCAN_THREADS, st, counts, (uint32_t)p.B, tile_sums, starts, cursors);
   if (mark(st, "scan")) return 1;
   if (row_sort) {
-    k_batch_digits<true><<<q.rows, 256, row_smem, st>>>(d_scalars, q, starts, entries);
+    k_batch_digits<true><<<q.rows, 1024, row_smem_launch, st>>>(d_scalars, q, starts, entries);
     g_launches++;
     CU(cudaGetLastError());
   } else {
@@ -397,9 +397,11 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
            buckets, heads, head_bucket);
   }
   if (mark(st, "accumulate")) return 1;
-  // a bucket can span at most S_max segments: ceil(log2(S_max)) pointer-jumping rounds cover the worst case.
-  // Rounds beyond the largest bucket are empty launches (a few microseconds each).
-  for (uint32_t round = 0; (1ull << round) < p.S_max; round++)
+  // A bucket holds at most one entry per (column, window) of its group: cols entries (single MSM: one window per
+  // group) or cols * W (batch row), i.e. it spans at most that many / K + 1 segments.
+  const uint64_t max_bucket = q.batch ? (uint64_t)q.cols * q.W : (uint64_t)q.cols;
+  const uint64_t max_span = std::min<uint64_t>(p.S_max, max_bucket / p.K + 2);
+  for (uint32_t round = 0; (1ull << round) < max_span; round++)
     LAUNCH(k_fixup_round, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, round, heads, head_bucket);
   LAUNCH(k_fixup_final, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket);
   if (mark(st, "fixup")) return 1;

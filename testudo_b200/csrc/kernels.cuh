@@ -166,8 +166,11 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
 // the scattered 4-byte writes of a row stay inside its 0.6 MB slice of entries[] while the CTA lives.
 //   SCATTER = false: smem histogram -> counts[row*nb ..] (plain coalesced stores, no global atomics)
 //   SCATTER = true : smem cursors loaded from the scanned bucket_start[], returning smem atomics give positions
+// Launch shape: ONE 1024-thread CTA per SM (the host pads the dynamic shared memory to enforce it). With many
+// small CTAs ~1200 rows were in flight and their 0.6 MB output slices (~760 MB) overflowed L2: the scattered 4-byte
+// writes then became partial-sector read-modify-writes in DRAM (47 ms at 2^26); 148 rows in flight stay L2-resident.
 template <bool SCATTER>
-__global__ void __launch_bounds__(256) k_batch_digits(const uint32_t* __restrict__ scalars, MsmGeom g,
+__global__ void __launch_bounds__(1024) k_batch_digits(const uint32_t* __restrict__ scalars, MsmGeom g,
                                                       uint32_t* __restrict__ counters /* counts or bucket_start */,
                                                       uint32_t* __restrict__ entries) {
   extern __shared__ uint32_t s_cnt[];
