@@ -93,7 +93,10 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // base upload of host-facing calls overlaps the digit/sort stages
   cudaEvent_t ev_points = nullptr;
+  cudaStream_t stream2 = nullptr;      // second pipeline for independent small MSMs (MIPP cross commitments)
+  cudaEvent_t ev_join = nullptr;
   Arena arena;
+  Arena arena2;
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<Stage> marks;
@@ -240,32 +243,33 @@ int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs,
 
 // Runs the whole pipeline on `st`. d_points: affine points indexed by entry refs. d_out: groups*96 B (batch) or 96 B.
 int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points, uint4* d_out, cudaStream_t st,
-                 cudaEvent_t points_ready = nullptr) {
+                 cudaEvent_t points_ready = nullptr, Arena* arena_p = nullptr) {
   const MsmGeom& q = p.geo;
-  int rc = g.arena.reserve(p.bytes);
+  Arena& arena = arena_p ? *arena_p : g.arena;
+  int rc = arena.reserve(p.bytes);
   if (rc) return fail(rc, "workspace allocation of %zu bytes failed: %s", p.bytes, cudaGetErrorString((cudaError_t)rc));
-  g.arena.reset();
-  uint32_t* counts = g.arena.take<uint32_t>(p.B + 1);
-  uint32_t* starts = g.arena.take<uint32_t>(p.B + 1);
-  uint32_t* cursors = g.arena.take<uint32_t>(p.B);
-  uint32_t* tile_sums = g.arena.take<uint32_t>(p.ntiles + 1);
-  uint32_t* entries = g.arena.take<uint32_t>(std::max<uint64_t>(p.M_max, 1));
+  arena.reset();
+  uint32_t* counts = arena.take<uint32_t>(p.B + 1);
+  uint32_t* starts = arena.take<uint32_t>(p.B + 1);
+  uint32_t* cursors = arena.take<uint32_t>(p.B);
+  uint32_t* tile_sums = arena.take<uint32_t>(p.ntiles + 1);
+  uint32_t* entries = arena.take<uint32_t>(std::max<uint64_t>(p.M_max, 1));
   uint4 *buckets = nullptr, *heads = nullptr;
   int32_t* head_bucket = nullptr;
   uint32_t *sizes = nullptr, *offA = nullptr, *offB = nullptr, *pidx = nullptr;
   uint4 *scratch = nullptr, *ptsA = nullptr, *ptsB = nullptr;
   if (p.affine) {
-    sizes = g.arena.take<uint32_t>(p.B + 1);
-    offA = g.arena.take<uint32_t>(p.B + 1);
-    offB = g.arena.take<uint32_t>(p.B + 1);
-    pidx = g.arena.take<uint32_t>(p.N1);
-    scratch = g.arena.take<uint4>(p.N1 * 3);
-    ptsA = g.arena.take<uint4>(p.N1 * 6);
-    ptsB = g.arena.take<uint4>(p.N2 * 6);
+    sizes = arena.take<uint32_t>(p.B + 1);
+    offA = arena.take<uint32_t>(p.B + 1);
+    offB = arena.take<uint32_t>(p.B + 1);
+    pidx = arena.take<uint32_t>(p.N1);
+    scratch = arena.take<uint4>(p.N1 * 3);
+    ptsA = arena.take<uint4>(p.N1 * 6);
+    ptsB = arena.take<uint4>(p.N2 * 6);
   } else {
-    buckets = g.arena.take<uint4>(p.B * 12);
-    heads = g.arena.take<uint4>((size_t)p.S_max * 12);
-    head_bucket = g.arena.take<int32_t>(p.S_max);
+    buckets = arena.take<uint4>(p.B * 12);
+    heads = arena.take<uint4>((size_t)p.S_max * 12);
+    head_bucket = arena.take<int32_t>(p.S_max);
   }
 
   g.last_c = q.c;
@@ -377,8 +381,8 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
       cur = ptsA;
     }
     n /= L0;
-    uint4* outS = g.arena.take<uint4>(n * 12);
-    uint4* outW = g.arena.take<uint4>(n * 12);
+    uint4* outS = arena.take<uint4>(n * 12);
+    uint4* outW = arena.take<uint4>(n * 12);
     LAUNCH(k_reduce_pass0_affine, cdiv(n, 128), 128, st, cur, off_in, outS, outW, L0, n);
     inS = outS;
     inW = outW;
@@ -412,8 +416,8 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   for (size_t li = first_level; li < p.Ls.size(); li++) {
     const uint32_t L = p.Ls[li];
     n /= L;
-    uint4* outS = g.arena.take<uint4>(n * 12);
-    uint4* outW = g.arena.take<uint4>(n * 12);
+    uint4* outS = arena.take<uint4>(n * 12);
+    uint4* outW = arena.take<uint4>(n * 12);
     LAUNCH(k_reduce_pass, cdiv(n, 128), 128, st, inS, inW, level0, outS, outW, L, log2_ell, n);
     inS = outS;
     inW = outW;
@@ -475,6 +479,8 @@ int tb200_init(int device) {
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&g.ev_points, cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
   CU(cudaMalloc((void**)&g.d_result, 16384));
   CU(cudaMallocHost((void**)&g.h_result, 16384));
   g.ready = true;
@@ -486,8 +492,13 @@ void tb200_shutdown(void) {
   if (!g.ready) return;
   cudaSetDevice(g.device);
   cudaStreamSynchronize(g.stream);
+  cudaStreamSynchronize(g.stream2);
   if (g.arena.base) cudaFree(g.arena.base);
+  if (g.arena2.base) cudaFree(g.arena2.base);
   g.arena = Arena();
+  g.arena2 = Arena();
+  cudaStreamDestroy(g.stream2);
+  cudaEventDestroy(g.ev_join);
   for (auto e : g.ev_pool) cudaEventDestroy(e);
   g.ev_pool.clear();
   cudaFree(g.d_result);
@@ -519,7 +530,8 @@ void tb200_set_accumulate_mode(int mode) { g.acc_mode = (mode >= 0 && mode <= 3)
 
 // ---- single MSM -------------------------------------------------------------------------------------------------
 static int msm_dev_locked(const void* d_bases, const void* d_scalars, size_t n, unsigned flags, void* d_out,
-                          cudaStream_t st, cudaEvent_t points_ready = nullptr) {
+                          cudaStream_t st, cudaEvent_t points_ready = nullptr, Arena* arena = nullptr,
+                          bool finish = true) {
   if (n >= (1ull << 31)) return fail(TB200_E_LIMIT, "n = %zu exceeds 2^31 - 1 points per call", n);
   if (((uintptr_t)d_bases | (uintptr_t)d_scalars | (uintptr_t)d_out) & 15)
     return fail(TB200_E_ARG, "device pointers must be 16-byte aligned");
@@ -529,9 +541,9 @@ static int msm_dev_locked(const void* d_bases, const void* d_scalars, size_t n, 
   while (rc == TB200_E_LIMIT && c > 3) rc = make_plan(p, 1, (uint32_t)n, 0, 1, --c, 0, flags);
   if (rc) return rc;
   g.marks.clear();
-  rc = run_pipeline(p, (const uint32_t*)d_scalars, (const uint4*)d_bases, (uint4*)d_out, st, points_ready);
+  rc = run_pipeline(p, (const uint32_t*)d_scalars, (const uint4*)d_bases, (uint4*)d_out, st, points_ready, arena);
   if (rc) return rc;
-  return finish_marks(st);
+  return finish ? finish_marks(st) : 0;
 }
 
 int tb200_msm_g1_dev(const void* d_bases_xy, const void* d_scalars, size_t n, unsigned flags, void* d_out_xy,
@@ -758,10 +770,18 @@ int tb200_mipp_g1_cross(tb200_mipp_t h, uint64_t comm_u_l[12], uint64_t comm_u_r
   CU(cudaSetDevice(g.device));
   const uint32_t split = h->n / 2;
   // comm_u_l = MSM(a[:split], y[split:]), comm_u_r = MSM(a[split:], y[:split])   (src/mipp.rs:82-84)
-  int rc = msm_dev_locked(h->a, h->y + 8 * (size_t)split, split, h->flags, g.d_result, g.stream);
+  // the two MSMs are independent and latency-bound (sequential Horner + inversion tail): run them concurrently on
+  // two streams with separate workspaces (the reference runs them as two rayon tasks, src/mipp.rs:77-85)
+  const bool prof = g.profiling;
+  g.profiling = false;
+  int rc = msm_dev_locked(h->a, h->y + 8 * (size_t)split, split, h->flags, g.d_result, g.stream, nullptr, nullptr, false);
+  if (rc == 0)
+    rc = msm_dev_locked(h->a + 6 * (size_t)split, h->y, split, h->flags, g.d_result + 6, g.stream2, nullptr, &g.arena2,
+                        false);
+  g.profiling = prof;
   if (rc) return rc;
-  rc = msm_dev_locked(h->a + 6 * (size_t)split, h->y, split, h->flags, g.d_result + 6, g.stream);
-  if (rc) return rc;
+  CU(cudaEventRecord(g.ev_join, g.stream2));
+  CU(cudaStreamWaitEvent(g.stream, g.ev_join, 0));
   CU(cudaMemcpyAsync(g.h_result, g.d_result, 192, cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
   memcpy(comm_u_l, g.h_result, 96);
