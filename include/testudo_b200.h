@@ -97,6 +97,14 @@ int tb200_mipp_g1_end(tb200_mipp_t h);
 /* stand-alone `compress` for G1 (src/mipp.rs:354-367): vec[i] = vec[i] + scaler * vec[split + i], i < split */
 int tb200_compress_g1(uint64_t* vec_xy, size_t split, const uint64_t scaler[4], unsigned flags);
 
+/* ---- device buffers (for hosts that keep data resident across calls, e.g. Z between commit and open) -------------
+ * Plain cudaMalloc / blocking copies on the library's device; pointers are valid for every *_dev entry point. */
+int tb200_dev_alloc(size_t bytes, void** out);
+int tb200_dev_free(void* d_ptr);
+int tb200_dev_upload(void* d_dst, const void* h_src, size_t bytes);
+int tb200_dev_download(void* h_dst, const void* d_src, size_t bytes);
+int tb200_stream_sync(void); /* wait for work enqueued on the library's stream by *_dev calls with stream == NULL */
+
 /* ---- sqrt_pst scalar work on the device (Fr values in ark Montgomery form) ---------------
  * chis_out[i] = prod_j (bit(i, m-1-j) ? b[j] : 1 - b[j]), i < 2^m  -- `Polynomial::get_chi_i`, src/sqrt_pst.rs:152-166 */
 int tb200_fr_chis(const uint64_t* b, size_t m, uint64_t* chis_out);

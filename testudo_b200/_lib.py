@@ -44,6 +44,11 @@ SIGNATURES = {
     "tb200_mipp_g1_read": (c_int, [c_void_p, c_void_p, c_void_p]),
     "tb200_mipp_g1_end": (c_int, [c_void_p]),
     "tb200_compress_g1": (c_int, [c_void_p, c_size_t, c_void_p, c_uint]),
+    "tb200_dev_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
+    "tb200_dev_free": (c_int, [c_void_p]),
+    "tb200_dev_upload": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "tb200_dev_download": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "tb200_stream_sync": (c_int, []),
     "tb200_fr_chis": (c_int, [c_void_p, c_size_t, c_void_p]),
     "tb200_fr_matvec": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "tb200_fr_matvec_dev": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),

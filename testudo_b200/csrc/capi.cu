@@ -853,6 +853,49 @@ int tb200_compress_g1(uint64_t* vec_xy, size_t split, const uint64_t scaler[4], 
   return 0;
 }
 
+// ---- device buffers for hosts without a CUDA runtime of their own (the Rust/C++ side keeps Z resident) -----------------
+int tb200_dev_alloc(size_t bytes, void** out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || bytes == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(g.device));
+  CU(cudaMalloc(out, bytes));
+  return 0;
+}
+int tb200_dev_free(void* p) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  CU(cudaSetDevice(g.device));
+  CU(cudaStreamSynchronize(g.stream));
+  CU(cudaFree(p));
+  return 0;
+}
+int tb200_dev_upload(void* d_dst, const void* h_src, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_dst || !h_src) return fail(TB200_E_ARG, "null pointer");
+  CU(cudaSetDevice(g.device));
+  CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+int tb200_dev_download(void* h_dst, const void* d_src, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!h_dst || !d_src) return fail(TB200_E_ARG, "null pointer");
+  CU(cudaSetDevice(g.device));
+  CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+int tb200_stream_sync(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  CU(cudaSetDevice(g.device));
+  CU(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
 // ---- sqrt_pst scalar work on the device -------------------------------------------------------------------------------
 int tb200_fr_chis(const uint64_t* b, size_t m, uint64_t* chis_out) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -75,13 +75,44 @@ class OpenG1:
     mipp: "mipp.MippProofG1"
 
 
+class _DeviceBuffer:
+    """cudaMalloc'ed copy of a numpy array (tb200_dev_*), freed with the owner."""
+
+    def __init__(self, arr: np.ndarray):
+        lib = _lib.engine()
+        self.ptr = ctypes.c_void_p()
+        self.nbytes = arr.nbytes
+        _lib.check(lib.tb200_dev_alloc(max(arr.nbytes, 16), ctypes.byref(self.ptr)))
+        if arr.nbytes:
+            _lib.check(lib.tb200_dev_upload(self.ptr, _ptr(arr), arr.nbytes))
+
+    def download(self, shape, dtype=np.uint64) -> np.ndarray:
+        out = np.zeros(shape, dtype=dtype)
+        _lib.check(_lib.engine().tb200_dev_download(_ptr(out), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr is not None:
+            _lib.check(_lib.engine().tb200_dev_free(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 class Polynomial:
     def __init__(self, z: np.ndarray, m: int, odd: int):
-        self.Z = z            # [2^n, 4] Montgomery Fr, un-transposed
+        self.Z = z            # [2^n, 4] Montgomery Fr, un-transposed (host copy)
         self.m = m            # m_col
         self.odd = odd
         self.q: Optional[np.ndarray] = None
         self.chis_b: Optional[np.ndarray] = None
+        # the reference transposes Z here (src/sqrt_pst.rs:48-62); we upload it instead, once: commit and get_q
+        # then work on the resident matrix
+        self._dZ = _DeviceBuffer(z)
 
     @classmethod
     def from_evaluations(cls, Z) -> "Polynomial":
@@ -104,9 +135,12 @@ class Polynomial:
         """src/sqrt_pst.rs:117-149 -> (comm_list as [2^m_col, 12] g_products, t). t (pairing product) is not computed."""
         rows, cols = 1 << self.m, 1 << self.m_row
         assert cols == len(ck.powers_of_g0), "ck.powers_of_g[0] must have 2^m_row points"
-        out = np.zeros((rows, 12), dtype=np.uint64)
-        _lib.check(_lib.engine().tb200_msm_g1_batch(ck._h, _ptr(self.Z), rows, cols, 1, rows, _lib.SCALARS_MONT,
-                                                    _ptr(out)))
+        lib = _lib.engine()
+        d_out = _DeviceBuffer(np.zeros((rows, 12), dtype=np.uint64))
+        _lib.check(lib.tb200_msm_g1_batch_dev(ck._h, self._dZ.ptr, rows, cols, 1, rows, _lib.SCALARS_MONT, d_out.ptr, None))
+        _lib.check(lib.tb200_stream_sync())
+        out = d_out.download((rows, 12))
+        d_out.free()
         return out, None
 
     def get_q(self, point: List[int]) -> None:
@@ -118,8 +152,14 @@ class Polynomial:
         pow_m = 1 << self.m
         chis = np.zeros((pow_m, 4), dtype=np.uint64)
         _lib.check(lib.tb200_fr_chis(_ptr(b), self.m, _ptr(chis)))
-        q = np.zeros((pow_m << self.odd, 4), dtype=np.uint64)
-        _lib.check(lib.tb200_fr_matvec(_ptr(self.Z), len(q), pow_m, _ptr(chis), _ptr(q)))
+        nq = pow_m << self.odd
+        d_chis = _DeviceBuffer(chis)
+        d_q = _DeviceBuffer(np.zeros((nq, 4), dtype=np.uint64))
+        _lib.check(lib.tb200_fr_matvec_dev(self._dZ.ptr, nq, pow_m, d_chis.ptr, d_q.ptr, None))   # Z stays resident
+        _lib.check(lib.tb200_stream_sync())
+        q = d_q.download((nq, 4))
+        d_chis.free()
+        d_q.free()
         self.q, self.chis_b = q, chis
 
     def get_q_host(self, point: List[int]) -> Tuple[np.ndarray, np.ndarray]:
