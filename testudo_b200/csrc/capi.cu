@@ -225,7 +225,7 @@ int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs,
   b += Arena::pad(std::max<uint64_t>(p.M_max, 1) * 4);  // entries
   if (p.affine) {
     b += Arena::pad((p.B + 1) * 4) * 3;                 // sizes, two offset arrays
-    b += Arena::pad(p.N1 * 4) + Arena::pad(p.N1 * 48);  // pair index, prefix-product scratch
+    b += Arena::pad(p.N1 * 4) + Arena::pad(p.N1 * 48) + Arena::pad(p.N1);  // pair index, prefix scratch, kinds
     b += Arena::pad(p.N1 * 96) + Arena::pad(p.N2 * 96); // ping-pong point arrays
   } else {
     b += Arena::pad(p.B * 192);                         // buckets
@@ -258,12 +258,14 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   int32_t* head_bucket = nullptr;
   uint32_t *sizes = nullptr, *offA = nullptr, *offB = nullptr, *pidx = nullptr;
   uint4 *scratch = nullptr, *ptsA = nullptr, *ptsB = nullptr;
+  uint8_t* kinds = nullptr;
   if (p.affine) {
     sizes = arena.take<uint32_t>(p.B + 1);
     offA = arena.take<uint32_t>(p.B + 1);
     offB = arena.take<uint32_t>(p.B + 1);
     pidx = arena.take<uint32_t>(p.N1);
     scratch = arena.take<uint4>(p.N1 * 3);
+    kinds = arena.take<uint8_t>(p.N1);
     ptsA = arena.take<uint4>(p.N1 * 6);
     ptsB = arena.take<uint4>(p.N2 * 6);
   } else {
@@ -355,10 +357,10 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
       uint32_t warps = cdiv(n_out_bound, 32ull * T);
       if (round == 0)
         LAUNCH(k_affine_round<true>, cdiv((uint64_t)warps * 32, 128), 128, st, pidx, off_out, (uint32_t)p.B, T, entries,
-               d_points, cur, nxt, scratch);
+               d_points, cur, nxt, scratch, kinds);
       else
         LAUNCH(k_affine_round<false>, cdiv((uint64_t)warps * 32, 128), 128, st, pidx, off_out, (uint32_t)p.B, T,
-               entries, d_points, cur, nxt, scratch);
+               entries, d_points, cur, nxt, scratch, kinds);
       off_in = off_out;
       cur = nxt;
       n_in_bound = n_out_bound;
@@ -376,7 +378,7 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
       LAUNCH(k_scan_apply, p.ntiles, SCAN_THREADS, st, sizes, (uint32_t)p.B, tile_sums, off_out, cursors);
       LAUNCH(k_pair_index, cdiv(cdiv(p.N1, 8), 256), 256, st, off_in, off_out, (uint32_t)p.B, pidx);
       LAUNCH(k_affine_round<true>, cdiv(cdiv(p.N1, 32ull * 64) * 32ull, 128), 128, st, pidx, off_out, (uint32_t)p.B,
-             64u, entries, d_points, cur, ptsA, scratch);
+             64u, entries, d_points, cur, ptsA, scratch, kinds);
       off_in = off_out;
       cur = ptsA;
     }

@@ -106,82 +106,141 @@ __global__ void __launch_bounds__(256) k_pair_index(const uint32_t* __restrict__
   }
 }
 
-// load input i of the current round: round 0 gathers +-points[entries[i]], later rounds read cur[i]
+// ---- round kernel, second generation --------------------------------------------------------------------------
+// What ncu showed about the first version (profiles/r01_summary.md 3): both sweeps gathered both full points
+// (105 GB of DRAM traffic at 2^24) behind three dependent loads (pidx -> entries -> point) with one multiplication
+// of work per forward iteration, so `long_scoreboard` dominated. Now
+//   * the forward sweep reads x-coordinates only (y is touched only when x0 == x1) and stores the classification,
+//     so the backward sweep neither re-tests nor re-derives anything;
+//   * the dependent load chain is software-pipelined three deep (index, entry, coordinates of the NEXT outputs are
+//     in flight while the current product is multiplied);
+//   * field work is lazily reduced with the out-of-line multiplier / squarer of the XYZZ loop; only the stored
+//     output coordinates are made canonical (exact equality tests in the next round stay trivial).
+__device__ __forceinline__ void load_fq_nc(Fq& v, const uint4* __restrict__ src) {
+  uint4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+  v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w;
+  v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
+  v.l[8] = c.x; v.l[9] = c.y; v.l[10] = c.z; v.l[11] = c.w;
+}
+__device__ __forceinline__ void load_fq(Fq& v, const uint4* src) {
+  uint4 a = src[0], b = src[1], c = src[2];
+  v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w;
+  v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w;
+  v.l[8] = c.x; v.l[9] = c.y; v.l[10] = c.z; v.l[11] = c.w;
+}
+__device__ __forceinline__ void store_fq(uint4* dst, const Fq& v) {
+  dst[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+  dst[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+  dst[2] = make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]);
+}
+enum : uint32_t { PAIR_COPY0 = 0, PAIR_COPY1 = 1, PAIR_INF = 2, PAIR_ADD = 3, PAIR_DBL = 4 };
+
+// address of point `i` of the round's input (round 0: through entries[]); *neg = sign bit of the entry
 template <bool FIRST>
-__device__ __forceinline__ void load_input(Affine& a, uint32_t i, const uint32_t* __restrict__ entries,
-                                           const uint4* __restrict__ points, const uint4* __restrict__ cur) {
+__device__ __forceinline__ const uint4* input_ptr(uint32_t i, const uint32_t* __restrict__ entries,
+                                                  const uint4* __restrict__ points, const uint4* __restrict__ cur,
+                                                  uint32_t* neg) {
   if (FIRST) {
     const uint32_t e = __ldg(entries + i);
-    load_fq2_nc(a, points + 6 * (uint64_t)(e & 0x7fffffffu));
-    if (e >> 31) fq_neg(a.y, a.y);
-  } else {
-    load_affine(a, cur + 6 * (uint64_t)i);
+    *neg = e >> 31;
+    return points + 6 * (uint64_t)(e & 0x7fffffffu);
   }
+  *neg = 0;
+  return cur + 6 * (uint64_t)i;
 }
-
-// classification of one output: what the batch inversion has to invert and which formula applies
-enum : uint32_t { PAIR_COPY0 = 0, PAIR_COPY1 = 1, PAIR_INF = 2, PAIR_ADD = 3, PAIR_DBL = 4 };
-__device__ __forceinline__ uint32_t classify(const Affine& a, const Affine& b, bool has_partner, Fq& denom) {
-  if (!has_partner || affine_is_inf(b)) return PAIR_COPY0;
+// rare path of the forward sweep: x0 == x1 (or an identity input): look at y and decide
+template <bool FIRST>
+__device__ __noinline__ uint32_t classify_slow(uint32_t i0, const uint32_t* __restrict__ entries,
+                                               const uint4* __restrict__ points, const uint4* __restrict__ cur,
+                                               Fq* denom) {
+  uint32_t n0, n1;
+  Affine a, b;
+  load_affine(a, input_ptr<FIRST>(i0, entries, points, cur, &n0));
+  load_affine(b, input_ptr<FIRST>(i0 + 1, entries, points, cur, &n1));
+  if (n0) fq_neg(a.y, a.y);
+  if (n1) fq_neg(b.y, b.y);
+  if (affine_is_inf(b)) return PAIR_COPY0;
   if (affine_is_inf(a)) return PAIR_COPY1;
-  fq_sub(denom, b.x, a.x);
-  if (!fq_is_zero(denom)) return PAIR_ADD;
+  if (!fq_eq(a.x, b.x)) {  // one of them had x == 0 without being the identity
+    fq_sub(*denom, b.x, a.x);
+    return PAIR_ADD;
+  }
   if (fq_eq(a.y, b.y) && !fq_is_zero(a.y)) {
-    fq_dbl(denom, a.y);
+    fq_dbl(*denom, a.y);
     return PAIR_DBL;
   }
-  return PAIR_INF;  // P + (-P) (or a 2-torsion point doubled, which cannot occur in the prime-order subgroup)
+  return PAIR_INF;
 }
 
-// One round. Outputs are dealt to the lanes of a warp round-robin (output = base + i*32 + lane) so that the lanes'
-// accesses to cur[]/nxt[]/scratch stay adjacent; every thread handles T outputs.
 template <bool FIRST>
 __global__ void __launch_bounds__(128, 3)
     k_affine_round(const uint32_t* __restrict__ pidx, const uint32_t* __restrict__ off_out, uint32_t B, uint32_t T,
                    const uint32_t* __restrict__ entries, const uint4* __restrict__ points,
-                   const uint4* __restrict__ cur, uint4* __restrict__ nxt, uint4* __restrict__ scratch) {
+                   const uint4* __restrict__ cur, uint4* __restrict__ nxt, uint4* __restrict__ scratch,
+                   uint8_t* __restrict__ kinds) {
   const uint32_t n_out = off_out[B];
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t base = warp * 32ull * T;
-  if (base >= n_out) return;
-  // forward: prefix products of the denominators
-  Fq run = fq_one();
-  for (uint32_t i = 0; i < T; i++) {
-    const uint64_t p = base + (uint64_t)i * 32 + lane;
-    if (p >= n_out) break;
-    const uint32_t pi = __ldg(pidx + p);
-    const uint32_t i0 = pi & 0x7fffffffu;
-    const bool partner = pi >> 31;
-    Affine a, b;
-    load_input<FIRST>(a, i0, entries, points, cur);
-    if (partner) load_input<FIRST>(b, i0 + 1, entries, points, cur);
-    Fq d;
-    const uint32_t kind = classify(a, b, partner, d);
-    // prefix BEFORE this output (what the backward sweep multiplies the running inverse with)
-    uint4* sp = scratch + 3 * p;
-    sp[0] = make_uint4(run.l[0], run.l[1], run.l[2], run.l[3]);
-    sp[1] = make_uint4(run.l[4], run.l[5], run.l[6], run.l[7]);
-    sp[2] = make_uint4(run.l[8], run.l[9], run.l[10], run.l[11]);
-    if (kind >= PAIR_ADD) run = fq_mulc_call(run, d);
-  }
-  Fq inv = fq_inv_call(run);
-  // backward
-  uint32_t cnt = 0;
+  if (base + lane >= n_out) return;
+  const uint32_t cnt = (uint32_t)min((uint64_t)T, (n_out - (base + lane) + 31) / 32);
+  // ---- forward sweep: prefix products of the denominators, three-stage software pipeline -------------------
+  // stage A (2 ahead): pair index; stage B (1 ahead): addresses (round 0: entries) and the two x loads
+  uint32_t pi_next2 = cnt > 1 ? __ldg(pidx + base + 32 + lane) : 0;
+  uint32_t pi_next = __ldg(pidx + base + lane);
+  Fq x0n, x1n;
   {
-    const uint64_t first = base + lane;
-    if (first < n_out) cnt = (uint32_t)min((uint64_t)T, (n_out - first + 31) / 32);
+    uint32_t ng;
+    const uint32_t i0 = pi_next & 0x7fffffffu;
+    load_fq_nc(x0n, input_ptr<FIRST>(i0, entries, points, cur, &ng));
+    if (pi_next >> 31) load_fq_nc(x1n, input_ptr<FIRST>(i0 + 1, entries, points, cur, &ng));
+    else x1n = x0n;
   }
+  Fq run = fq_one();
+  for (uint32_t i = 0; i < cnt; i++) {
+    const uint64_t p = base + (uint64_t)i * 32 + lane;
+    const uint32_t pi = pi_next;
+    Fq x0 = x0n, x1 = x1n;
+    pi_next = pi_next2;
+    if (i + 2 < cnt) pi_next2 = __ldg(pidx + p + 64);
+    if (i + 1 < cnt) {  // issue the coordinate loads of the next output before working on this one
+      uint32_t ng;
+      const uint32_t j0 = pi_next & 0x7fffffffu;
+      load_fq_nc(x0n, input_ptr<FIRST>(j0, entries, points, cur, &ng));
+      if (pi_next >> 31) load_fq_nc(x1n, input_ptr<FIRST>(j0 + 1, entries, points, cur, &ng));
+      else x1n = x0n;
+    }
+    uint32_t kind;
+    Fq d;
+    if (!(pi >> 31)) {
+      kind = PAIR_COPY0;
+    } else {
+      fq_sub(d, x1, x0);  // inputs are canonical
+      kind = PAIR_ADD;
+      if (fq_is_zero(d) || fq_is_zero(x0) || fq_is_zero(x1)) kind = classify_slow<FIRST>(pi & 0x7fffffffu, entries, points, cur, &d);
+    }
+    store_fq(scratch + 3 * p, run);  // prefix BEFORE this output
+    kinds[p] = (uint8_t)kind;
+    if (kind >= PAIR_ADD) run = fq_mul_call(run, d);
+  }
+  fq_canon(run);
+  Fq inv = fq_inv_call(run);
+  // ---- backward sweep ----------------------------------------------------------------------------------------------
   for (uint32_t i = cnt; i-- > 0;) {
     const uint64_t p = base + (uint64_t)i * 32 + lane;
     const uint32_t pi = __ldg(pidx + p);
     const uint32_t i0 = pi & 0x7fffffffu;
-    const bool partner = pi >> 31;
+    const uint32_t kind = kinds[p];
     Affine a, b, o;
-    load_input<FIRST>(a, i0, entries, points, cur);
-    if (partner) load_input<FIRST>(b, i0 + 1, entries, points, cur);
-    Fq d;
-    const uint32_t kind = classify(a, b, partner, d);
+    uint32_t n0 = 0, n1 = 0;
+    if (kind != PAIR_COPY1 && kind != PAIR_INF) {
+      load_fq2_nc(a, input_ptr<FIRST>(i0, entries, points, cur, &n0));
+      if (n0) fq_neg(a.y, a.y);
+    }
+    if (kind == PAIR_COPY1 || kind == PAIR_ADD) {
+      load_fq2_nc(b, input_ptr<FIRST>(i0 + 1, entries, points, cur, &n1));
+      if (n1) fq_neg(b.y, b.y);
+    }
     if (kind == PAIR_COPY0) {
       o = a;
     } else if (kind == PAIR_COPY1) {
@@ -190,30 +249,35 @@ __global__ void __launch_bounds__(128, 3)
       o.x = fq_zero();
       o.y = fq_zero();
     } else {
-      Fq pre;
-      const uint4* sp = scratch + 3 * p;
-      uint4 v0 = sp[0], v1 = sp[1], v2 = sp[2];
-      pre.l[0] = v0.x; pre.l[1] = v0.y; pre.l[2] = v0.z; pre.l[3] = v0.w;
-      pre.l[4] = v1.x; pre.l[5] = v1.y; pre.l[6] = v1.z; pre.l[7] = v1.w;
-      pre.l[8] = v2.x; pre.l[9] = v2.y; pre.l[10] = v2.z; pre.l[11] = v2.w;
-      Fq dinv = fq_mulc_call(inv, pre);  // 1 / d
-      inv = fq_mulc_call(inv, d);        // running inverse without this d
-      Fq num, lam, t;
+      Fq pre, d, num, lam, t;
+      load_fq(pre, scratch + 3 * p);
       if (kind == PAIR_ADD) {
-        fq_sub(num, b.y, a.y);
-      } else {  // doubling: 3 x^2
-        t = fq_mulc_call(a.x, a.x);
-        fq_dbl(num, t);
-        fq_add(num, num, t);
+        fq_sub(d, b.x, a.x);
+        fq_sub_lazy<0>(num, b.y, a.y);   // y1 + 2q - y0 < 3q
+      } else {                           // doubling: d = 2 y0, num = 3 x0^2
+        fq_dbl(d, a.y);
+        t = fq_sqr_call(a.x);            // < 2q
+        Carry c;
+        num.l[0] = add_cc(t.l[0], t.l[0], c);
+#pragma unroll
+        for (int k = 1; k < 12; k++) num.l[k] = addc_cc(t.l[k], t.l[k], c);
+        Carry c2;
+        num.l[0] = add_cc(num.l[0], t.l[0], c2);
+#pragma unroll
+        for (int k = 1; k < 12; k++) num.l[k] = addc_cc(num.l[k], t.l[k], c2);   // < 6q
         b.x = a.x;
       }
-      lam = fq_mulc_call(num, dinv);
-      t = fq_mulc_call(lam, lam);
-      fq_sub(t, t, a.x);
-      fq_sub(o.x, t, b.x);     // x3 = lambda^2 - x1 - x2
-      fq_sub(t, a.x, o.x);
-      t = fq_mulc_call(lam, t);
-      fq_sub(o.y, t, a.y);     // y3 = lambda (x1 - x3) - y1
+      Fq dinv = fq_mul_call(inv, pre);   // 1 / d                 < 2q
+      inv = fq_mul_call(inv, d);         // running inverse        < 2q
+      lam = fq_mul_call(num, dinv);      //                        < 2q
+      t = fq_sqr_call(lam);              //                        < 2q
+      fq_sub_lazy<0>(t, t, a.x);         // + 2q - x0              < 4q
+      fq_sub_lazy<0>(o.x, t, b.x);       // x3 = .. + 2q - x1      < 6q
+      fq_sub_lazy<2>(t, a.x, o.x);       // x0 + 8q - x3           < 9q
+      t = fq_mul_call(lam, t);           //                        < 2q
+      fq_sub_lazy<0>(o.y, t, a.y);       // y3 = .. + 2q - y0      < 4q
+      fq_canon(o.x);
+      fq_canon(o.y);
     }
     store_affine(nxt + 6 * p, o);
   }
