@@ -133,7 +133,8 @@ int tb200_last_geometry(int* c, int* windows, uint64_t* entries, uint64_t* bucke
 void tb200_set_window_bits(int c);
 /* bucket-accumulation method: 0 = automatic (currently 3); 1 = XYZZ mixed additions over balanced segments with
  * register operands (k_accumulate); 2 = batched-affine pairwise rounds (Montgomery's trick; experimental, slower
- * on B200 -- DESIGN.md); 3 = XYZZ segments with shared-memory operand slots (k_accumulate_s). Identical results. */
+ * on B200 -- DESIGN.md); 3 = XYZZ segments with shared-memory operand slots (k_accumulate_s); 4 = as 3 with the
+ * Karatsuba multiplier and the fused Y3 reduction (mont_kara.cuh). Identical results. */
 void tb200_set_accumulate_mode(int mode);
 /* integer-pipe microbenchmark: runs `iters` dependent-chain iterations of wide MACs on every SM and returns the
  * achieved 32x32->64 multiply-accumulates per second in *out_macs_per_s (kind: 0 = IMAD.WIDE.U32 reg-reg,

@@ -3,6 +3,7 @@
 #include <cstring>
 #include "../../testudo_b200/csrc/g1_fast.cuh"
 #include "../../testudo_b200/csrc/digits.cuh"
+#include "../../testudo_b200/csrc/mont_kara.cuh"
 using namespace tb;
 extern "C" {
 void hc_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul<FqParams>(r, a, b); }
@@ -86,6 +87,14 @@ int hc_add_fast_chain(const uint32_t* pts_aff, int n, int dbls, const uint32_t* 
 void hc_fq_canon(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.l, a, 48); fq_canon(x); memcpy(r, x.l, 48); }
 void hc_fq_sqr_lazy(const uint32_t* a, uint32_t* r) { mont_sqr_lazy<FqParams>(r, a); }
 void hc_fr_sqr_lazy(const uint32_t* a, uint32_t* r) { mont_sqr_lazy<FrParams>(r, a); }
+void hc_kara_mul12(const uint32_t* a, const uint32_t* b, uint32_t* T) { kara_mul12(T, a, b); }
+void hc_fq_mul_kara(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul_kara(r, a, b); }
+void hc_fq_mul2_kara(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* r) {
+  mont_mul2_kara(r, a, b, c, d);
+}
+void hc_fq_mul2_lazy(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* r) {
+  mont_mul2_lazy<FqParams>(r, a, b, c, d);
+}
 void hc_fq_mul_lazy(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul_lazy<FqParams>(r, a, b); }
 // signed digits of one canonical scalar with window c: out[w] in [-2^(c-1), 2^(c-1)]
 int hc_digits(const uint32_t* s, int c, int32_t* out) {

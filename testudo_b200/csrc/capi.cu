@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -102,6 +103,7 @@ struct Ctx {
   std::vector<Stage> marks;
   std::map<std::string, double> stage_ms;
   int forced_c = 0;
+  size_t host_chunk_min = size_t(1) << 21;  // tb200_msm_g1 with host buffers: chunked upload/compute overlap from here
   int acc_mode = 0;  // 0 = automatic (= 3), 1 = XYZZ segments, register operands (k_accumulate), 2 = batched-affine
                      // rounds, 3 = XYZZ segments, shared-memory operand slots (k_accumulate_s)
   // geometry of the last call
@@ -182,8 +184,16 @@ struct Plan {
   uint64_t N1, N2;           // upper bounds of the round-0 / round-1 output counts
 };
 
+// a single MSM processed as point-range chunks that accumulate into ONE persistent bucket array
+struct ChunkCtl {
+  uint32_t ref_base;  // global index of the chunk's first point
+  uint4* buckets;     // B * 192 B, all zero (= identity) before the first chunk
+  bool last;          // run the reduction / finalisation after this chunk
+};
+
 int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs, int c, int batch, unsigned flags) {
   MsmGeom& q = p.geo;
+  q.ref_base = 0;
   q.rows = rows;
   q.cols = cols;
   q.row_stride = rs;
@@ -243,8 +253,9 @@ int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs,
 
 // Runs the whole pipeline on `st`. d_points: affine points indexed by entry refs. d_out: groups*96 B (batch) or 96 B.
 int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points, uint4* d_out, cudaStream_t st,
-                 cudaEvent_t points_ready = nullptr, Arena* arena_p = nullptr) {
-  const MsmGeom& q = p.geo;
+                 cudaEvent_t points_ready = nullptr, Arena* arena_p = nullptr, const ChunkCtl* chunk = nullptr) {
+  MsmGeom q = p.geo;
+  if (chunk) q.ref_base = chunk->ref_base;
   Arena& arena = arena_p ? *arena_p : g.arena;
   int rc = arena.reserve(p.bytes);
   if (rc) return fail(rc, "workspace allocation of %zu bytes failed: %s", p.bytes, cudaGetErrorString((cudaError_t)rc));
@@ -269,7 +280,7 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
     ptsA = arena.take<uint4>(p.N1 * 6);
     ptsB = arena.take<uint4>(p.N2 * 6);
   } else {
-    buckets = arena.take<uint4>(p.B * 12);
+    buckets = chunk ? chunk->buckets : arena.take<uint4>(p.B * 12);
     heads = arena.take<uint4>((size_t)p.S_max * 12);
     head_bucket = arena.take<int32_t>(p.S_max);
   }
@@ -392,10 +403,19 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
     first_level = 1;
   } else {
   // M is only known on the device (starts[B]); launch for the upper bound, surplus threads exit immediately
-  if (g.acc_mode == 3 || g.acc_mode == 0) {  // default: operands in shared-memory slots (kernels_smem.cuh)
-    CU(cudaFuncSetAttribute(k_accumulate_s, cudaFuncAttributeMaxDynamicSharedMemorySize, ACCS_SMEM));
-    k_accumulate_s<<<cdiv(p.S_max, ACCS_THREADS), ACCS_THREADS, ACCS_SMEM, st>>>(entries, starts, (uint32_t)p.B, p.K,
-                                                                                d_points, buckets, heads, head_bucket);
+  if (g.acc_mode == 0 || g.acc_mode >= 3 || chunk) {  // operands in shared-memory slots (kernels_smem.cuh)
+    const dim3 grid(cdiv(p.S_max, ACCS_THREADS));
+    // mode 3: plain CIOS products; 0 / 4: Y3 as one fused sum of two products (default); 5: + Karatsuba singles
+#define TB_ACCS(V)                                                                                                   \
+  do {                                                                                                               \
+    CU(cudaFuncSetAttribute(k_accumulate_s<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACCS_SMEM));             \
+    k_accumulate_s<V><<<grid, ACCS_THREADS, ACCS_SMEM, st>>>(entries, starts, (uint32_t)p.B, p.K, d_points, buckets, \
+                                                             heads, head_bucket, chunk ? 1 : 0);                    \
+  } while (0)
+    if (g.acc_mode == 3) TB_ACCS(0);
+    else if (g.acc_mode == 5) TB_ACCS(3);
+    else TB_ACCS(2);
+#undef TB_ACCS
     g_launches++;
     CU(cudaGetLastError());
   } else {
@@ -411,10 +431,12 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
     LAUNCH(k_fixup_round, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, round, heads, head_bucket);
   LAUNCH(k_fixup_final, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket);
   if (mark(st, "fixup")) return 1;
+  if (chunk && !chunk->last) return 0;  // later point-range chunks continue in the same buckets
   inS = buckets;
   }
   // hierarchical bucket reduction
-  const uint32_t* level0 = p.affine ? nullptr : starts;
+  // chunked runs: emptiness is per chunk; the persistent buckets carry the identity (all zero) instead
+  const uint32_t* level0 = (p.affine || chunk) ? nullptr : starts;
   for (size_t li = first_level; li < p.Ls.size(); li++) {
     const uint32_t L = p.Ls[li];
     n /= L;
@@ -485,6 +507,11 @@ int tb200_init(int device) {
   CU(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
   CU(cudaMalloc((void**)&g.d_result, 16384));
   CU(cudaMallocHost((void**)&g.h_result, 16384));
+  if (const char* m = getenv("TB200_HOST_CHUNK_MIN")) g.host_chunk_min = (size_t)atoll(m);  // tuning aid
+  if (const char* m = getenv("TB200_ACC_MODE")) {  // tuning aid: same effect as tb200_set_accumulate_mode
+    int v = atoi(m);
+    g.acc_mode = (v >= 0 && v <= 5) ? v : 0;
+  }
   g.ready = true;
   return 0;
 }
@@ -528,7 +555,7 @@ int tb200_last_geometry(int* c, int* windows, uint64_t* entries, uint64_t* bucke
   return 0;
 }
 void tb200_set_window_bits(int c) { g.forced_c = (c >= 3 && c <= 22) ? c : 0; }
-void tb200_set_accumulate_mode(int mode) { g.acc_mode = (mode >= 0 && mode <= 3) ? mode : 0; }
+void tb200_set_accumulate_mode(int mode) { g.acc_mode = (mode >= 0 && mode <= 5) ? mode : 0; }
 
 // ---- single MSM -------------------------------------------------------------------------------------------------
 static int msm_dev_locked(const void* d_bases, const void* d_scalars, size_t n, unsigned flags, void* d_out,
@@ -557,11 +584,78 @@ int tb200_msm_g1_dev(const void* d_bases_xy, const void* d_scalars, size_t n, un
   return msm_dev_locked(d_bases_xy, d_scalars, n, flags, d_out_xy, stream ? (cudaStream_t)stream : g.stream);
 }
 
+// Host-facing single MSM for large n: point-range chunks of growing size (1/8, 1/4, 1/4, 3/8 of the points). Chunk
+// k+1 is uploaded on the copy stream while chunk k is sorted and accumulated; every chunk accumulates into the SAME
+// persistent bucket array (k_accumulate_s continues from the stored bucket, no extra group operations), and the
+// reduction / finalisation run once after the last chunk. Without it the accumulation waits for the whole 96 n byte
+// base upload (~37 ms at 2^24 over PCIe Gen5) with the GPU idle.
+static int msm_host_chunked(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, unsigned flags,
+                            uint64_t out_xy[12]) {
+  constexpr int C = 4;
+  const size_t unit = ((n + 7) / 8 + 31) & ~size_t(31);
+  const size_t cut[C + 1] = {0, std::min(n, unit), std::min(n, 3 * unit), std::min(n, 5 * unit), n};
+  const int c = pick_c_single(n);
+  Plan plans[C];
+  size_t B = 0;
+  for (int k = 0; k < C; k++) {
+    int rc = make_plan(plans[k], 1, (uint32_t)(cut[k + 1] - cut[k]), 0, 1, c, 0, flags);
+    if (rc) return rc;
+    B = plans[k].B;
+  }
+  uint4 *d_b = nullptr, *d_s = nullptr, *d_buckets = nullptr;
+  CU(cudaMallocAsync((void**)&d_b, n * 96, g.stream));
+  CU(cudaMallocAsync((void**)&d_s, n * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_buckets, B * 192, g.stream));
+  CU(cudaMemsetAsync(d_buckets, 0, B * 192, g.stream));
+  CU(cudaEventRecord(g.ev_points, g.stream));  // allocations exist
+  CU(cudaStreamWaitEvent(g.copy_stream, g.ev_points, 0));
+  cudaEvent_t ev_s[C], ev_b[C];
+  for (int k = 0; k < C; k++) {
+    const size_t lo = cut[k], cnt = cut[k + 1] - cut[k];
+    CU(cudaEventCreateWithFlags(&ev_s[k], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ev_b[k], cudaEventDisableTiming));
+    CU(cudaMemcpyAsync((char*)d_s + lo * 32, (const char*)scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice,
+                       g.copy_stream));
+    CU(cudaEventRecord(ev_s[k], g.copy_stream));
+    CU(cudaMemcpyAsync((char*)d_b + lo * 96, (const char*)bases_xy + lo * 96, cnt * 96, cudaMemcpyHostToDevice,
+                       g.copy_stream));
+    CU(cudaEventRecord(ev_b[k], g.copy_stream));
+  }
+  g.marks.clear();
+  int rc = 0;
+  for (int k = 0; k < C && rc == 0; k++) {
+    CU(cudaStreamWaitEvent(g.stream, ev_s[k], 0));
+    ChunkCtl ctl{(uint32_t)cut[k], d_buckets, k == C - 1};
+    rc = run_pipeline(plans[k], (const uint32_t*)d_s + 8 * cut[k], d_b, g.d_result, g.stream, ev_b[k], nullptr, &ctl);
+  }
+  if (rc == 0) rc = finish_marks(g.stream);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(g.h_result, g.d_result, 96, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
+    else memcpy(out_xy, g.h_result, 96);
+  } else {
+    cudaStreamSynchronize(g.stream);
+    cudaStreamSynchronize(g.copy_stream);
+  }
+  for (int k = 0; k < C; k++) {
+    cudaEventDestroy(ev_s[k]);
+    cudaEventDestroy(ev_b[k]);
+  }
+  cudaFreeAsync(d_b, g.stream);
+  cudaFreeAsync(d_s, g.stream);
+  cudaFreeAsync(d_buckets, g.stream);
+  return rc;
+}
+
 int tb200_msm_g1(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, unsigned flags, uint64_t out_xy[12]) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (need_ready()) return TB200_E_STATE;
   if (!out_xy || (n && (!bases_xy || !scalars))) return fail(TB200_E_ARG, "null pointer");
   CU(cudaSetDevice(g.device));
+  // large inputs: overlap the upload with the accumulation (every chunk is non-empty and keeps the GPU busy)
+  if (n >= g.host_chunk_min && n < (size_t(1) << 31) && g.acc_mode != 1 && g.acc_mode != 2)
+    return msm_host_chunked(bases_xy, scalars, n, flags, out_xy);
   uint4 *d_b = nullptr, *d_s = nullptr;
   if (n) {
     CU(cudaMallocAsync((void**)&d_b, n * 96, g.stream));

@@ -106,6 +106,7 @@ struct MsmGeom {
   uint32_t groups;              // single: W; batch: rows
   int batch;                    // 1: shared-base batch (group = row, ref = w*cols + j); 0: single (group = w, ref = j)
   int mont;                     // scalars are Montgomery-form Fr
+  uint32_t ref_base;            // single MSM processed in point-range chunks: entry ref = ref_base + col
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
       uint32_t group = g.batch ? row : (uint32_t)w;
       uint32_t bucket = group * g.nb + (mag - 1);
       if (SCATTER) {
-        uint32_t ref = g.batch ? (uint32_t)w * g.cols + col : col;
+        uint32_t ref = g.batch ? (uint32_t)w * g.cols + col : g.ref_base + col;
         uint32_t pos = atomicAdd(&counters[bucket], 1u);
         entries[pos] = ref | (d < 0 ? 0x80000000u : 0u);
       } else {

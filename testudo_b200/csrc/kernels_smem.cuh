@@ -9,6 +9,7 @@
 // integer-pipe time), nothing spills, and the freed registers hold the prefetched next point.
 #pragma once
 #include "kernels.cuh"
+#include "mont_kara.cuh"
 
 namespace tb {
 
@@ -39,6 +40,31 @@ __device__ __noinline__ void slot_mul(uint4* sm, int d, int a, int b) {
   mont_mul_lazy<FqParams>(r.l, x.l, y.l);
   slot_store(sm, d, r);
 }
+// Karatsuba variant (mont_kara.cuh): 240 instead of 276 wide MACs but ~170 more ALU-pipe instructions
+__device__ __noinline__ void slot_mul_k(uint4* sm, int d, int a, int b) {
+  Fq x, y, r;
+  slot_load(x, sm, a);
+  slot_load(y, sm, b);
+  mont_mul_kara(r.l, x.l, y.l);
+  slot_store(sm, d, r);
+}
+// d = a * b + c * e, even/odd CIOS with one reduction (mont_mul2_lazy: 420 wide MACs)
+__device__ __noinline__ void slot_mul2_c(uint4* sm, int d, int a, int b, int c, int e) {
+  Fq x, y, z, w, r;
+  slot_load(x, sm, a);
+  slot_load(y, sm, b);
+  slot_load(z, sm, c);
+  slot_load(w, sm, e);
+  mont_mul2_lazy<FqParams>(r.l, x.l, y.l, z.l, w.l);
+  slot_store(sm, d, r);
+}
+// V: bit 0 = Karatsuba for the single products (measured: no gain -- on sm_100a ALU-pipe instructions do not issue for
+// free next to IMAD.WIDE, benches/pipes.cu); bit 1 = Y3 as ONE fused sum of two products (-132 wide MACs, default)
+template <int V>
+__device__ __forceinline__ void slot_mulv(uint4* sm, int d, int a, int b) {
+  if ((V & 1) == 0) slot_mul(sm, d, a, b);
+  else slot_mul_k(sm, d, a, b);
+}
 // d = a * a (dedicated squaring)
 __device__ __noinline__ void slot_sqr(uint4* sm, int d, int a) {
   Fq x, r;
@@ -58,6 +84,18 @@ __device__ __forceinline__ uint32_t slot_sub(uint4* sm, int d, int a, int b) {
 }
 
 // acc (slots SX..SZZZ) += q; `inf` tracks whether the accumulator is the identity. Bounds as in xyzz_madd_fast.
+// d = 4q - a  (a <= 4q)
+__device__ __forceinline__ void slot_negy(uint4* sm, int d, int a) {
+  Fq x, r;
+  slot_load(x, sm, a);
+  Carry c;
+  r.l[0] = sub_cc(fq_kq(1, 0), x.l[0], c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) r.l[i] = subc_cc(fq_kq(1, i), x.l[i], c);
+  slot_store(sm, d, r);
+}
+
+template <int V>
 __device__ __forceinline__ void madd_slots(uint4* sm, const Affine& q, bool& inf) {
   if (affine_is_inf(q)) return;
   if (inf) {
@@ -71,8 +109,8 @@ __device__ __forceinline__ void madd_slots(uint4* sm, const Affine& q, bool& inf
   }
   slot_store(sm, SA, q.x);
   slot_store(sm, SB, q.y);
-  slot_mul(sm, SPP, SA, SZZ);                     // U2
-  slot_mul(sm, SRR, SB, SZZZ);                    // S2
+  slot_mulv<V>(sm, SPP, SA, SZZ);                 // U2
+  slot_mulv<V>(sm, SRR, SB, SZZZ);                // S2
   const uint32_t plo = slot_sub<2>(sm, SPP, SPP, SX);   // P = U2 + 8q - X1
   slot_sub<1>(sm, SRR, SRR, SY);                  // R = S2 + 4q - Y1
   if (plo - 1u < 9u) {                            // P = k q possible: decide exactly, out of line
@@ -95,18 +133,25 @@ __device__ __forceinline__ void madd_slots(uint4* sm, const Affine& q, bool& inf
     }
   }
   slot_sqr(sm, SA, SPP);                          // PP   (slot A)
-  slot_mul(sm, SB, SPP, SA);                      // PPP  (slot B)
-  slot_mul(sm, SQQ, SX, SA);                      // Q
-  slot_mul(sm, SZZ, SZZ, SA);                     // ZZ3
-  slot_mul(sm, SZZZ, SZZZ, SB);                   // ZZZ3
+  slot_mulv<V>(sm, SB, SPP, SA);                  // PPP  (slot B)
+  slot_mulv<V>(sm, SQQ, SX, SA);                  // Q
+  slot_mulv<V>(sm, SZZ, SZZ, SA);                 // ZZ3
+  slot_mulv<V>(sm, SZZZ, SZZZ, SB);               // ZZZ3
   slot_sqr(sm, SA, SRR);                          // RR   (slot A)
   slot_sub<0>(sm, SA, SA, SB);                    // RR + 2q - PPP
   slot_sub<0>(sm, SA, SA, SQQ);                   //    + 2q - Q
-  slot_sub<0>(sm, SX, SA, SQQ);                   // X3
-  slot_sub<2>(sm, SQQ, SQQ, SX);                  // Q + 8q - X3
-  slot_mul(sm, SQQ, SRR, SQQ);                    // R (Q - X3)
-  slot_mul(sm, SA, SY, SB);                       // Y1 PPP
-  slot_sub<0>(sm, SY, SQQ, SA);                   // Y3
+  slot_sub<0>(sm, SX, SA, SQQ);                   // X3 < 7.3q
+  slot_sub<2>(sm, SQQ, SQQ, SX);                  // Q + 8q - X3 < 9.2q
+  if ((V & 2) == 0) {
+    slot_mulv<V>(sm, SQQ, SRR, SQQ);              // R (Q - X3)
+    slot_mulv<V>(sm, SA, SY, SB);                 // Y1 PPP
+    slot_sub<0>(sm, SY, SQQ, SA);                 // Y3
+  } else {
+    // Y3 = R (Q - X3) + (4q - Y1) PPP with ONE Montgomery reduction: R < 6q, Q - X3 < 9.2q, 4q - Y1 <= 4q,
+    // PPP < 1.2q  =>  Y3 < q + (55.2 + 4.8) q^2 / 2^384 < 1.5q   (invariant Y < 4q)
+    slot_negy(sm, SA, SY);                        // 4q - Y1
+    slot_mul2_c(sm, SY, SA, SB, SRR, SQQ);        // b + d = PPP + (Q - X3) < 10.4q (mont_mul2_lazy's bound)
+  }
 }
 
 __device__ __forceinline__ void flush_slots(uint4* sm, uint4* dst, bool inf) {
@@ -118,15 +163,27 @@ __device__ __forceinline__ void flush_slots(uint4* sm, uint4* dst, bool inf) {
     slot_load(acc.y, sm, SY);
     slot_load(acc.zz, sm, SZZ);
     slot_load(acc.zzz, sm, SZZZ);
-    xyzz_canon(acc);
+    // stored lazily reduced (X < 8q, Y < 4q, ZZ, ZZZ < 2q): every consumer (k_fixup_*, k_reduce_pass) takes the
+    // lazy invariant, and a flush is a divergent branch of the hot loop, so it should be as short as possible
   }
   store_xyzz(dst, acc);
 }
 
+// accumulator slots <- stored XYZZ bucket; returns true if it is the identity
+__device__ __forceinline__ bool load_bucket_slots(uint4* sm, const uint4* src) {
+  uint4 v[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) v[i] = src[i];
+#pragma unroll
+  for (int i = 0; i < 12; i++) sm[(i / 3) * 3 * ACCS_THREADS + (i % 3) * ACCS_THREADS] = v[i];  // slots SX..SZZZ = 0..3
+  return (v[6].x | v[6].y | v[6].z | v[6].w | v[7].x | v[7].y | v[7].z | v[7].w | v[8].x | v[8].y | v[8].z | v[8].w) == 0;
+}
+
+template <int V>
 __global__ void __launch_bounds__(ACCS_THREADS, 4)
     k_accumulate_s(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ bucket_start, uint32_t B,
                    uint32_t K, const uint4* __restrict__ points, uint4* __restrict__ buckets,
-                   uint4* __restrict__ heads, int32_t* __restrict__ head_bucket) {
+                   uint4* __restrict__ heads, int32_t* __restrict__ head_bucket, int merge) {
   extern __shared__ uint4 s_slots[];
   uint4* sm = s_slots + threadIdx.x;
   const uint32_t M = __ldg(bucket_start + B);
@@ -146,6 +203,9 @@ __global__ void __launch_bounds__(ACCS_THREADS, 4)
   head_bucket[t] = is_head ? (int32_t)b : -1;
   uint32_t end_b = __ldg(bucket_start + b + 1);
   bool inf = true;
+  // `merge`: buckets[] already holds the sums of earlier point-range chunks of the same MSM (identity = all zero):
+  // the thread that owns the first entry of a bucket continues from the stored value -- no extra group operation
+  if (merge && !is_head) inf = load_bucket_slots(sm, buckets + 12 * (uint64_t)b);
   // software pipeline: the point of entry pos+1 is gathered into registers while entry pos is being added
   Affine nxt;
   uint32_t e = __ldg(entries + lo);
@@ -159,6 +219,7 @@ __global__ void __launch_bounds__(ACCS_THREADS, 4)
         b++;
         end_b = __ldg(bucket_start + b + 1);
       } while (end_b == pos);
+      if (merge) inf = load_bucket_slots(sm, buckets + 12 * (uint64_t)b);
     }
     Affine q = nxt;
     const uint32_t neg = e >> 31;
@@ -167,7 +228,7 @@ __global__ void __launch_bounds__(ACCS_THREADS, 4)
       load_fq2_nc(nxt, points + 6 * (uint64_t)(e & 0x7fffffffu));
     }
     if (neg) fq_neg(q.y, q.y);
-    madd_slots(sm, q, inf);
+    madd_slots<V>(sm, q, inf);
   }
   flush_slots(sm, is_head ? heads + 12 * t : buckets + 12 * (uint64_t)b, inf);
 }

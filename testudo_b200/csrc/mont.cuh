@@ -123,6 +123,17 @@ TB_HD uint32_t mul_hi(uint32_t a, uint32_t b) {
   return (uint32_t)(((uint64_t)a * b) >> 32);
 #endif
 }
+// lo/hi of a 32x32 product through ONE PTX mul.wide: ptxas emits IMAD.WIDE.U32 and cannot peephole the high half
+// into a later addition (which splits the product into IMAD + IMAD.HI.U32 plus two moves)
+TB_HD void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  asm volatile("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+#else
+  uint64_t t = (uint64_t)a * b;
+  lo = (uint32_t)t;
+  hi = (uint32_t)(t >> 32);
+#endif
+}
 TB_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t d, Carry& c) {
 #ifdef __CUDA_ARCH__
   uint32_t r;
@@ -376,6 +387,86 @@ TB_HD void mont_mul_lazy(uint32_t* r, const uint32_t* a, const uint32_t* b) {
     e[N] = 0;
   }
   // r = x + E + O * 2^32  (< 2p), then one conditional subtraction
+  Carry c;
+  r[0] = add_cc(e[0], x, c);
+#pragma unroll
+  for (int j = 1; j < N; j++) r[j] = addc_cc(e[j], o[j - 1], c);
+}
+
+// r = (a * b + c * d) * R^-1 (mod p) with ONE Montgomery reduction (2 N^2 + N (N - 1) wide MACs instead of
+// 2 N (2N - 1)): every row adds a_i * B and c_i * D to the even/odd accumulators before the quotient digit is taken.
+// NOT fully reduced: r < p + (a b + c d) / R; requires b + d + p < 2^(32N) - the running total stays below
+// b + d + p + epsilon, so the top-limb arguments of mont_mul_lazy carry over when b + d < 2^(32N - 4).
+template <class P>
+TB_HD void mont_mul2_lazy(uint32_t* r, const uint32_t* a, const uint32_t* b, const uint32_t* cc, const uint32_t* d) {
+  constexpr int N = P::N;
+  uint32_t e[N + 1], o[N], x = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    Carry c;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const uint32_t ai = half ? cc[i] : a[i];
+      const uint32_t* bb = half ? d : b;
+      if (i == 0 && half == 0) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+          mul_wide(e[j], e[j + 1], ai, bb[j]);
+          mul_wide(o[j], o[j + 1], ai, bb[j + 1]);
+        }
+        e[N] = 0;
+      } else {
+        e[0] = mad_lo_cc(ai, bb[0], e[0], c);
+        e[1] = madc_hi_cc(ai, bb[0], e[1], c);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) {
+          e[j] = madc_lo_cc(ai, bb[j], e[j], c);
+          e[j + 1] = madc_hi_cc(ai, bb[j], e[j + 1], c);
+        }
+        e[N] = addc(e[N], 0, c);
+        o[0] = mad_lo_cc(ai, bb[1], o[0], c);
+        o[1] = madc_hi_cc(ai, bb[1], o[1], c);
+#pragma unroll
+        for (int j = 2; j < N - 2; j += 2) {
+          o[j] = madc_lo_cc(ai, bb[j + 1], o[j], c);
+          o[j + 1] = madc_hi_cc(ai, bb[j + 1], o[j + 1], c);
+        }
+        o[N - 2] = madc_lo_cc(ai, bb[N - 1], o[N - 2], c);
+        o[N - 1] = madc_hi(ai, bb[N - 1], o[N - 1], c);
+      }
+    }
+    uint32_t s = add_cc(e[0], x, c);
+    uint32_t k = addc(0, 0, c);
+    (void)add_cc(s, 0xffffffffu, c);
+    k = addc(k, 0, c);
+    uint32_t m = neg32(s);
+    e[1] = add_cc(e[1], k, c);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+      e[j] = madc_lo_cc(m, P::p(j), e[j], c);
+      e[j + 1] = madc_hi_cc(m, P::p(j), e[j + 1], c);
+    }
+    e[N] = addc(e[N], 0, c);
+    o[0] = mad_lo_cc(m, P::p(1), o[0], c);
+    o[1] = madc_hi_cc(m, P::p(1), o[1], c);
+#pragma unroll
+    for (int j = 2; j < N - 2; j += 2) {
+      o[j] = madc_lo_cc(m, P::p(j + 1), o[j], c);
+      o[j + 1] = madc_hi_cc(m, P::p(j + 1), o[j + 1], c);
+    }
+    o[N - 2] = madc_lo_cc(m, P::p(N - 1), o[N - 2], c);
+    o[N - 1] = madc_hi(m, P::p(N - 1), o[N - 1], c);
+    x = e[1];
+    uint32_t t[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) t[j] = o[j];
+#pragma unroll
+    for (int j = 0; j < N - 1; j++) o[j] = e[j + 2];
+    o[N - 1] = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) e[j] = t[j];
+    e[N] = 0;
+  }
   Carry c;
   r[0] = add_cc(e[0], x, c);
 #pragma unroll
