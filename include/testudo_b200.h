@@ -131,10 +131,11 @@ double tb200_stage_ms(const char* stage);
 int tb200_last_geometry(int* c, int* windows, uint64_t* entries, uint64_t* buckets, int* segment);
 /* override the automatic window choice for single MSMs (0 = automatic) */
 void tb200_set_window_bits(int c);
-/* bucket-accumulation method: 0 = automatic (currently 3); 1 = XYZZ mixed additions over balanced segments with
+/* bucket-accumulation method: 0 = automatic (currently 4); 1 = XYZZ mixed additions over balanced segments with
  * register operands (k_accumulate); 2 = batched-affine pairwise rounds (Montgomery's trick; experimental, slower
  * on B200 -- DESIGN.md); 3 = XYZZ segments with shared-memory operand slots (k_accumulate_s); 4 = as 3 with the
- * Karatsuba multiplier and the fused Y3 reduction (mont_kara.cuh). Identical results. */
+ * sum-of-two-products reduction for Y3 (mont_mul2_lazy; what 0 selects); 5 = as 4 with the Karatsuba multiplier for the
+ * single products (mont_kara.cuh; measured no faster). Identical results. */
 void tb200_set_accumulate_mode(int mode);
 /* integer-pipe microbenchmark: runs `iters` dependent-chain iterations of wide MACs on every SM and returns the
  * achieved 32x32->64 multiply-accumulates per second in *out_macs_per_s (kind: 0 = IMAD.WIDE.U32 reg-reg,

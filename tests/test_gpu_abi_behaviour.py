@@ -81,3 +81,24 @@ def test_single_msm_2p22_closed_form_and_skew(engine):
                                            ctypes.c_void_p(out.data_ptr()), None))
         _lib.check(engine.tb200_stream_sync())
         assert np.array_equal(out.cpu().numpy().view(np.uint64), synthetic.expected_msm(sc, n, seed=11)), skew
+
+
+def test_host_facing_msm_chunked_path(engine):
+    """tb200_msm_g1 with host buffers splits n >= 2^21 into point-range chunks that accumulate into one persistent
+    bucket array (the upload of chunk k+1 overlaps the compute of chunk k). Ragged size, uniform and skewed scalars,
+    closed-form check; the device-resident call on the same inputs must give the identical point."""
+    import torch
+
+    n = (1 << 21) + 12345
+    bases = synthetic.make_bases_dev(n, seed=21)
+    for skew in (False, True):
+        sc = synthetic.make_scalars_dev(n, seed=22, skew=skew)
+        B = bases.cpu().numpy().view(np.uint64)
+        S = sc.cpu().numpy().view(np.uint64)
+        got = msm.msm_bigint(B, S)
+        assert np.array_equal(got, synthetic.expected_msm(sc, n, seed=21)), skew
+        out = torch.zeros(12, dtype=torch.int64, device="cuda")
+        _lib.check(engine.tb200_msm_g1_dev(ctypes.c_void_p(bases.data_ptr()), ctypes.c_void_p(sc.data_ptr()), n, 0,
+                                           ctypes.c_void_p(out.data_ptr()), None))
+        _lib.check(engine.tb200_stream_sync())
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), got), skew

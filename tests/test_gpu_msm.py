@@ -25,7 +25,7 @@ def test_msm_seeded_golden(engine, case):
     assert h.pt_from_np(msm.msm_unchecked(h.pts_to_np(pts), h.scalars_to_np(sc, mont=True))) == exp
 
 
-@pytest.mark.parametrize("mode", [1, 3, 4])
+@pytest.mark.parametrize("mode", [1, 3, 5])
 @pytest.mark.parametrize("case", GOLD["explicit"] + GOLD["edge"], ids=lambda c: c.get("name", "explicit"))
 def test_msm_explicit_and_edge_golden(engine, case, mode):
     pts = [h.pt_unhex(p) for p in case["points"]]
@@ -49,7 +49,7 @@ def test_msm_empty_and_length_rules(engine):
     assert h.pt_from_np(msm.msm_bigint(B[:0], S[:0])) is None            # n == 0 -> identity
 
 
-@pytest.mark.parametrize("mode", [1, 3, 4])
+@pytest.mark.parametrize("mode", [1, 3, 5])
 @pytest.mark.parametrize("c", [3, 5, 8, 11, 13, 16])
 def test_msm_every_window_width(engine, oracle_c, c, mode):
     engine.tb200_set_accumulate_mode(mode)
@@ -87,7 +87,7 @@ def test_msm_vs_c_oracle_and_dlog(engine, oracle_c, logn):
     assert h.pt_from_np(got) == o.mul(sum(s * (a + step * k) for k, s in enumerate(ints)) % o.R_ORDER, o.G)
 
 
-@pytest.mark.parametrize("mode", [1, 3, 4])
+@pytest.mark.parametrize("mode", [1, 3, 5])
 def test_msm_skewed_scalars_heavy_buckets(engine, oracle_c, mode):
     engine.tb200_set_accumulate_mode(mode)
     try:
