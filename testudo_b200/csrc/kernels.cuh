@@ -433,21 +433,116 @@ __global__ void __launch_bounds__(128) k_reduce_pass(const uint4* __restrict__ i
   store_xyzz(outW + 12 * t, acc);
 }
 
-// single MSM: result = sum_w 2^(c*w) * Wsum[w]  (Horner, high window first), then canonical affine
-__global__ void k_finalize_single(const uint4* __restrict__ group_w, int W, int c, uint4* __restrict__ out_affine) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  Xyzz total, x;
-  xyzz_set_inf(total);
-  for (int w = W - 1; w >= 0; w--) {
-    load_xyzz(x, group_w + 12 * w);
-    xyzz_add_fast_ni(&total, &x);
-    if (w > 0)
-      for (int k = 0; k < c; k++) xyzz_dbl_fast_ni(&total);
+// single MSM: result = sum_w 2^(c*w) * Wsum[w]  (Horner, high window first), then canonical affine.
+// The ~(W-1)*c = 240 doublings are a strictly sequential chain; one thread needs 9 dependent multiplications per
+// doubling (2.7 ms at c = 20). Four lanes of one warp share a doubling instead: its products form three levels of
+// mutually independent multiplications (V, X^2 | W, S, M^2 | M(S-X3), W Y, V ZZ, W ZZZ), exchanged through shared
+// memory, so the chain costs three multiplication latencies per doubling. Same formulas and lazy bounds as
+// xyzz_dbl_fast (g1_fast.cuh).
+__device__ __forceinline__ void fq_lazy_double(Fq& r, const Fq& a) {  // r = 2a, plain limb add (a < 2^383)
+  Carry c;
+  r.l[0] = add_cc(a.l[0], a.l[0], c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) r.l[i] = addc_cc(a.l[i], a.l[i], c);
+}
+__device__ __forceinline__ void fq_lazy_add(Fq& r, const Fq& a, const Fq& b) {
+  Carry c;
+  r.l[0] = add_cc(a.l[0], b.l[0], c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) r.l[i] = addc_cc(a.l[i], b.l[i], c);
+}
+__global__ void __launch_bounds__(32) k_finalize_single(const uint4* __restrict__ group_w, int W, int c,
+                                                        uint4* __restrict__ out_affine) {
+  // shared operand file of the cooperative doubling; all lanes run the SAME multiplier call on different operands
+  enum { PX = 0, PY, PZZ, PZZZ, U, V, WW, S, M, T0, T1, D, NV };
+  __shared__ Fq sv[NV];
+  __shared__ int s_inf;
+  const int lane = threadIdx.x;
+  if (blockIdx.x != 0) return;
+  if (lane == 0) {
+    Xyzz t;
+    xyzz_set_inf(t);
+    sv[PX] = t.x; sv[PY] = t.y; sv[PZZ] = t.zz; sv[PZZZ] = t.zzz;
   }
-  xyzz_canon(total);
-  Affine a;
-  xyzz_to_affine_ni(&a, &total);
-  store_affine(out_affine, a);
+  __syncwarp();
+  for (int w = W - 1; w >= 0; w--) {
+    if (lane == 0) {
+      Xyzz total, x;
+      total.x = sv[PX]; total.y = sv[PY]; total.zz = sv[PZZ]; total.zzz = sv[PZZZ];
+      load_xyzz(x, group_w + 12 * w);
+      xyzz_add_fast_ni(&total, &x);
+      sv[PX] = total.x; sv[PY] = total.y; sv[PZZ] = total.zz; sv[PZZZ] = total.zzz;
+      s_inf = xyzz_is_inf(total) ? 1 : 0;
+    }
+    __syncwarp();
+    if (w == 0 || s_inf) continue;         // 2 * identity = identity (uniform branch: s_inf is shared)
+    for (int k = 0; k < c; k++) {
+      if (lane == 0) {                     // U = 2Y < 8q
+        Fq u;
+        fq_lazy_double(u, sv[PY]);
+        sv[U] = u;
+      }
+      __syncwarp();
+      // level 1: V = U^2 (lane 0) | X^2 (lane 1)
+      {
+        const int ia = lane == 0 ? U : PX;
+        Fq r = fq_mul_call(sv[ia], sv[ia]);
+        if (lane == 0) sv[V] = r;                            // V < 1.5q
+        if (lane == 1) {
+          Fq t;
+          fq_lazy_double(t, r);
+          fq_lazy_add(r, t, r);                              // M = 3 X^2 < 4.5q
+          sv[M] = r;
+        }
+      }
+      __syncwarp();
+      // level 2: W = U V (lane 0) | S = X V (lane 1) | M^2 (lane 2)
+      {
+        const int ia = lane == 0 ? U : (lane == 1 ? PX : M);
+        const int ib = lane == 2 ? M : V;
+        Fq r = fq_mul_call(sv[ia], sv[ib]);
+        if (lane == 0) sv[WW] = r;                           // W < 1.1q
+        if (lane == 1) sv[S] = r;                            // S < 1.1q
+        if (lane == 2) sv[T0] = r;                           // M^2 < 1.2q
+      }
+      __syncwarp();
+      if (lane == 0) {                     // X3 = M^2 + 4q - 2S < 5.2q;  D = S + 8q - X3 < 9.1q
+        Fq x3, d;
+        fq_sub_lazy<0>(x3, sv[T0], sv[S]);
+        fq_sub_lazy<0>(x3, x3, sv[S]);
+        fq_sub_lazy<2>(d, sv[S], x3);
+        sv[PX] = x3;
+        sv[D] = d;
+      }
+      __syncwarp();
+      // level 3: M D (lane 0) | W Y (lane 1) | V ZZ (lane 2) | W ZZZ (lane 3)
+      {
+        const int ia = lane == 0 ? M : (lane == 2 ? V : WW);
+        const int ib = lane == 0 ? D : (lane == 1 ? PY : (lane == 2 ? PZZ : PZZZ));
+        Fq r = fq_mul_call(sv[ia], sv[ib]);
+        __syncwarp();                                        // every operand has been read
+        if (lane == 0) sv[T0] = r;                           // < 1.4q
+        if (lane == 1) sv[T1] = r;                           // < 1.1q
+        if (lane == 2) sv[PZZ] = r;                          // < 2q
+        if (lane == 3) sv[PZZZ] = r;                         // < 2q
+      }
+      __syncwarp();
+      if (lane == 0) {                     // Y3 = M D + 2q - W Y < 3.4q
+        Fq y3;
+        fq_sub_lazy<0>(y3, sv[T0], sv[T1]);
+        sv[PY] = y3;
+      }
+      __syncwarp();
+    }
+  }
+  if (lane == 0) {
+    Xyzz total;
+    total.x = sv[PX]; total.y = sv[PY]; total.zz = sv[PZZ]; total.zzz = sv[PZZZ];
+    xyzz_canon(total);
+    Affine a;
+    xyzz_to_affine_ni(&a, &total);
+    store_affine(out_affine, a);
+  }
 }
 // batch: every group sum is a finished row commitment; normalise each to affine
 __global__ void __launch_bounds__(128) k_finalize_batch(const uint4* __restrict__ group_w, uint32_t groups,
