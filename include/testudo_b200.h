@@ -58,6 +58,19 @@ int tb200_msm_g1(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, un
 int tb200_msm_g1_dev(const void* d_bases_xy, const void* d_scalars, size_t n, unsigned flags,
                      void* d_out_xy, void* stream);
 
+/* ---- G2 multi-scalar multiplication ------------------------------------------------
+ * Replaces `<E::G2 as VariableBaseMSM>::msm_unchecked / msm_bigint` + `.into_affine()` for
+ * `ark_bls12_377::G2Projective`: the G2 openings of `MultilinearPC::open` (src/sqrt_pst.rs:225) and MIPP's
+ * `commit_g2` (src/mipp.rs:114). A G2 affine point is 24 u64 = x.c0[6] || x.c1[6] || y.c0[6] || y.c1[6]
+ * (Fq2 = Fq[u]/(u^2+5), coordinates in Montgomery form, little-endian limbs); all-zero == identity.
+ * Scalars and `flags` as for tb200_msm_g1. The result is the canonical affine point. */
+int tb200_msm_g2(const uint64_t* bases, const uint64_t* scalars, size_t n, unsigned flags, uint64_t out[24]);
+/* Same with DEVICE pointers (16-byte aligned); result (192 bytes) written to d_out; returns after enqueueing. */
+int tb200_msm_g2_dev(const void* d_bases, const void* d_scalars, size_t n, unsigned flags, void* d_out,
+                     void* stream);
+/* `compress` on a G2 vector (src/mipp.rs:133, 354-367): vec[i] = vec[i] + scaler * vec[split + i], i < split */
+int tb200_compress_g2(uint64_t* vec, size_t split, const uint64_t scaler[4], unsigned flags);
+
 /* ---- shared-base (SRS) batched MSM -------------------------------------------------------------------
  * Replaces the row fan-out `self.polys.par_iter().map(|p| MultilinearPC::commit(ck, p))`
  * (src/sqrt_pst.rs:121-125: 2^m_col MSMs over ck.powers_of_g[0]) and the Hyrax fan-out
@@ -147,6 +160,8 @@ int tb200_test_fq_mul(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* 
 int tb200_test_fq_addsub(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_add, uint64_t* out_sub);
 int tb200_test_g1_add(const uint64_t* p_xy, const uint64_t* q_xy, size_t n, uint64_t* out_xy); /* via XYZZ madd */
 int tb200_test_g1_mul(const uint64_t* p_xy, const uint64_t* k, size_t n, uint64_t* out_xy);    /* k canonical */
+int tb200_test_g2_add(const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out);           /* 24 u64 each */
+int tb200_test_g2_mul(const uint64_t* p, const uint64_t* k, size_t n, uint64_t* out);           /* k canonical */
 
 #ifdef __cplusplus
 }

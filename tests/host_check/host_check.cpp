@@ -4,6 +4,7 @@
 #include "../../testudo_b200/csrc/g1_fast.cuh"
 #include "../../testudo_b200/csrc/digits.cuh"
 #include "../../testudo_b200/csrc/mont_kara.cuh"
+#include "../../testudo_b200/csrc/g2.cuh"
 using namespace tb;
 extern "C" {
 void hc_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul<FqParams>(r, a, b); }
@@ -94,6 +95,37 @@ void hc_fq_mul2_kara(const uint32_t* a, const uint32_t* b, const uint32_t* c, co
 }
 void hc_fq_mul2_lazy(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* r) {
   mont_mul2_lazy<FqParams>(r, a, b, c, d);
+}
+// G2 (g2.cuh): Fq2 arithmetic and the XYZZ group law over the twist
+void hc_fq2_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fq2 x, y, z; memcpy(&x, a, 96); memcpy(&y, b, 96); fq2_mul(z, x, y); memcpy(r, &z, 96); }
+void hc_fq2_sqr(const uint32_t* a, uint32_t* r) { Fq2 x, z; memcpy(&x, a, 96); fq2_sqr(z, x); memcpy(r, &z, 96); }
+void hc_fq2_inv(const uint32_t* a, uint32_t* r) { Fq2 x, z; memcpy(&x, a, 96); fq2_inv(z, x); memcpy(r, &z, 96); }
+static void g2_scale(Xyzz2& a, const Affine2& t) {  // same point, ZZ != 1
+  xyzz2_madd(a, t); Affine2 nt = t; fq2_neg(nt.y, nt.y); xyzz2_madd(a, nt);
+}
+void hc_g2_madd(const uint32_t* p_aff, const uint32_t* q_aff, uint32_t* out_aff) {
+  Affine2 p, q, r; memcpy(&p, p_aff, 192); memcpy(&q, q_aff, 192);
+  Xyzz2 acc; xyzz2_set_inf(acc); xyzz2_madd(acc, p);
+  xyzz2_madd(acc, q);
+  xyzz2_to_affine(r, acc); memcpy(out_aff, &r, 192);
+}
+void hc_g2_add(const uint32_t* p_aff, const uint32_t* q_aff, const uint32_t* t_aff, uint32_t* out_aff) {
+  Affine2 p, q, t, r; memcpy(&p, p_aff, 192); memcpy(&q, q_aff, 192); memcpy(&t, t_aff, 192);
+  Xyzz2 a, b; xyzz2_set_inf(a); xyzz2_madd(a, p); xyzz2_set_inf(b); xyzz2_madd(b, q);
+  g2_scale(a, t); g2_scale(b, t);
+  xyzz2_add(a, b);
+  xyzz2_to_affine(r, a); memcpy(out_aff, &r, 192);
+}
+void hc_g2_dbl(const uint32_t* p_aff, const uint32_t* t_aff, uint32_t* out_aff) {
+  Affine2 p, t, r; memcpy(&p, p_aff, 192); memcpy(&t, t_aff, 192);
+  Xyzz2 a; xyzz2_set_inf(a); xyzz2_madd(a, p); g2_scale(a, t);
+  xyzz2_dbl(a);
+  xyzz2_to_affine(r, a); memcpy(out_aff, &r, 192);
+}
+void hc_g2_scalar_mul(const uint32_t* p_aff, const uint32_t* k, uint32_t* out_aff) {
+  Affine2 p, r; memcpy(&p, p_aff, 192);
+  Xyzz2 a; xyzz2_scalar_mul(a, p, k);
+  xyzz2_to_affine(r, a); memcpy(out_aff, &r, 192);
 }
 void hc_fq_mul_lazy(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul_lazy<FqParams>(r, a, b); }
 // signed digits of one canonical scalar with window c: out[w] in [-2^(c-1), 2^(c-1)]

@@ -44,6 +44,9 @@ SIGNATURES = {
     "tb200_mipp_g1_read": (c_int, [c_void_p, c_void_p, c_void_p]),
     "tb200_mipp_g1_end": (c_int, [c_void_p]),
     "tb200_compress_g1": (c_int, [c_void_p, c_size_t, c_void_p, c_uint]),
+    "tb200_msm_g2": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
+    "tb200_msm_g2_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p, c_void_p]),
+    "tb200_compress_g2": (c_int, [c_void_p, c_size_t, c_void_p, c_uint]),
     "tb200_dev_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
     "tb200_dev_free": (c_int, [c_void_p]),
     "tb200_dev_upload": (c_int, [c_void_p, c_void_p, c_size_t]),
@@ -66,6 +69,8 @@ SIGNATURES = {
     "tb200_test_fq_addsub": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "tb200_test_g1_add": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "tb200_test_g1_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tb200_test_g2_add": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tb200_test_g2_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 

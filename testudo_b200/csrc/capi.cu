@@ -15,6 +15,7 @@
 
 #include "../../include/testudo_b200.h"
 #include "kernels_affine.cuh"
+#include "kernels_g2.cuh"
 #include "kernels_smem.cuh"
 
 using namespace tb;
@@ -180,6 +181,7 @@ struct Plan {
   uint32_t K, S_max, ntiles;
   std::vector<uint32_t> Ls;  // reduction fan-in per level
   size_t bytes;
+  bool g2 = false;           // points are G2 (Fq2 coordinates: 192-byte affine, 384-byte XYZZ); single MSMs only
   bool affine;               // batched-affine rounds instead of k_accumulate
   uint64_t N1, N2;           // upper bounds of the round-0 / round-1 output counts
 };
@@ -191,8 +193,11 @@ struct ChunkCtl {
   bool last;          // run the reduction / finalisation after this chunk
 };
 
-int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs, int c, int batch, unsigned flags) {
+int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs, int c, int batch, unsigned flags,
+              bool g2 = false) {
   MsmGeom& q = p.geo;
+  p.g2 = g2;
+  const size_t pw = g2 ? 2 : 1;  // point width relative to G1
   q.ref_base = 0;
   q.rows = rows;
   q.cols = cols;
@@ -226,7 +231,7 @@ int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs,
   // Opt-in only. Measured on B200 at 2^24 (profiles/r01_summary.md): the rounds move ~105 GB through HBM and pay
   // one Fermat inversion per thread per round, which outweighs the 30% fewer multiplications; the XYZZ segment
   // kernel (85% of the integer pipe) stays the automatic choice.
-  p.affine = g.acc_mode == 2;
+  p.affine = g.acc_mode == 2 && !g2;
   // arena size
   size_t b = 0;
   b += Arena::pad((p.B + 1) * 4) * 2;  // counts, starts
@@ -238,15 +243,15 @@ int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs,
     b += Arena::pad(p.N1 * 4) + Arena::pad(p.N1 * 48) + Arena::pad(p.N1);  // pair index, prefix scratch, kinds
     b += Arena::pad(p.N1 * 96) + Arena::pad(p.N2 * 96); // ping-pong point arrays
   } else {
-    b += Arena::pad(p.B * 192);                         // buckets
-    b += Arena::pad((size_t)p.S_max * 192) + Arena::pad((size_t)p.S_max * 4);
+    b += Arena::pad(p.B * 192 * pw);                    // buckets
+    b += Arena::pad((size_t)p.S_max * 192 * pw) + Arena::pad((size_t)p.S_max * 4);
   }
   uint64_t n = p.B;
   for (uint32_t L : p.Ls) {
     n /= L;
-    b += Arena::pad(n * 192) * 2;
+    b += Arena::pad(n * 192 * pw) * 2;
   }
-  b += Arena::pad((size_t)q.groups * 192) * 2 + 4096;
+  b += Arena::pad((size_t)q.groups * 192 * pw) * 2 + 4096;
   p.bytes = b;
   return 0;
 }
@@ -256,6 +261,7 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
                  cudaEvent_t points_ready = nullptr, Arena* arena_p = nullptr, const ChunkCtl* chunk = nullptr) {
   MsmGeom q = p.geo;
   if (chunk) q.ref_base = chunk->ref_base;
+  const size_t pw = p.g2 ? 2 : 1;
   Arena& arena = arena_p ? *arena_p : g.arena;
   int rc = arena.reserve(p.bytes);
   if (rc) return fail(rc, "workspace allocation of %zu bytes failed: %s", p.bytes, cudaGetErrorString((cudaError_t)rc));
@@ -280,8 +286,8 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
     ptsA = arena.take<uint4>(p.N1 * 6);
     ptsB = arena.take<uint4>(p.N2 * 6);
   } else {
-    buckets = chunk ? chunk->buckets : arena.take<uint4>(p.B * 12);
-    heads = arena.take<uint4>((size_t)p.S_max * 12);
+    buckets = chunk ? chunk->buckets : arena.take<uint4>(p.B * 12 * pw);
+    heads = arena.take<uint4>((size_t)p.S_max * 12 * pw);
     head_bucket = arena.take<int32_t>(p.S_max);
   }
 
@@ -294,7 +300,7 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   const uint64_t items = (uint64_t)q.rows * q.cols;
   if (items == 0) {
     uint32_t cnt = q.batch ? q.rows : 1;
-    if (cnt) LAUNCH(k_write_identity, cdiv(cnt * 6, 128), 128, st, d_out, cnt);
+    if (cnt) LAUNCH(k_write_identity, cdiv(cnt * 6 * pw, 128), 128, st, d_out, (uint32_t)(cnt * pw));
     return 0;
   }
   if (mark(st, "begin")) return 1;
@@ -403,7 +409,10 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
     first_level = 1;
   } else {
   // M is only known on the device (starts[B]); launch for the upper bound, surplus threads exit immediately
-  if (g.acc_mode == 0 || g.acc_mode >= 3 || chunk) {  // operands in shared-memory slots (kernels_smem.cuh)
+  if (p.g2) {
+    LAUNCH(k_accumulate_g2, cdiv(p.S_max, 64), 64, st, entries, starts, (uint32_t)p.B, p.K, d_points, buckets, heads,
+           head_bucket);
+  } else if (g.acc_mode == 0 || g.acc_mode >= 3 || chunk) {  // operands in shared-memory slots (kernels_smem.cuh)
     const dim3 grid(cdiv(p.S_max, ACCS_THREADS));
     // mode 3: plain CIOS products; 0 / 4: Y3 as one fused sum of two products (default); 5: + Karatsuba singles
 #define TB_ACCS(V)                                                                                                   \
@@ -427,9 +436,15 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   // group) or cols * W (batch row), i.e. it spans at most that many / K + 1 segments.
   const uint64_t max_bucket = q.batch ? (uint64_t)q.cols * q.W : (uint64_t)q.cols;
   const uint64_t max_span = std::min<uint64_t>(p.S_max, max_bucket / p.K + 2);
-  for (uint32_t round = 0; (1ull << round) < max_span; round++)
-    LAUNCH(k_fixup_round, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, round, heads, head_bucket);
-  LAUNCH(k_fixup_final, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket);
+  if (p.g2) {
+    for (uint32_t round = 0; (1ull << round) < max_span; round++)
+      LAUNCH(k_fixup_round_g2, cdiv(p.S_max, 64), 64, st, starts, (uint32_t)p.B, p.K, round, heads, head_bucket);
+    LAUNCH(k_fixup_final_g2, cdiv(p.S_max, 64), 64, st, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket);
+  } else {
+    for (uint32_t round = 0; (1ull << round) < max_span; round++)
+      LAUNCH(k_fixup_round, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, round, heads, head_bucket);
+    LAUNCH(k_fixup_final, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket);
+  }
   if (mark(st, "fixup")) return 1;
   if (chunk && !chunk->last) return 0;  // later point-range chunks continue in the same buckets
   inS = buckets;
@@ -440,9 +455,10 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   for (size_t li = first_level; li < p.Ls.size(); li++) {
     const uint32_t L = p.Ls[li];
     n /= L;
-    uint4* outS = arena.take<uint4>(n * 12);
-    uint4* outW = arena.take<uint4>(n * 12);
-    LAUNCH(k_reduce_pass, cdiv(n, 128), 128, st, inS, inW, level0, outS, outW, L, log2_ell, n);
+    uint4* outS = arena.take<uint4>(n * 12 * pw);
+    uint4* outW = arena.take<uint4>(n * 12 * pw);
+    if (p.g2) LAUNCH(k_reduce_pass_g2, cdiv(n, 64), 64, st, inS, inW, level0, outS, outW, L, log2_ell, n);
+    else LAUNCH(k_reduce_pass, cdiv(n, 128), 128, st, inS, inW, level0, outS, outW, L, log2_ell, n);
     inS = outS;
     inW = outW;
     level0 = nullptr;
@@ -450,7 +466,8 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   }
   const uint4* group_w = inW;  // nb >= 4 (c >= 3): at least one reduction level has run
   if (mark(st, "reduce")) return 1;
-  if (q.batch) LAUNCH(k_finalize_batch, cdiv(q.groups, 128), 128, st, group_w, q.groups, d_out);
+  if (p.g2) LAUNCH(k_finalize_single_g2, 1, 32, st, group_w, q.W, q.c, d_out);
+  else if (q.batch) LAUNCH(k_finalize_batch, cdiv(q.groups, 128), 128, st, group_w, q.groups, d_out);
   else LAUNCH(k_finalize_single, 1, 32, st, group_w, q.W, q.c, d_out);
   if (mark(st, "finalize")) return 1;
   return 0;
@@ -560,14 +577,14 @@ void tb200_set_accumulate_mode(int mode) { g.acc_mode = (mode >= 0 && mode <= 5)
 // ---- single MSM -------------------------------------------------------------------------------------------------
 static int msm_dev_locked(const void* d_bases, const void* d_scalars, size_t n, unsigned flags, void* d_out,
                           cudaStream_t st, cudaEvent_t points_ready = nullptr, Arena* arena = nullptr,
-                          bool finish = true) {
+                          bool finish = true, bool g2 = false) {
   if (n >= (1ull << 31)) return fail(TB200_E_LIMIT, "n = %zu exceeds 2^31 - 1 points per call", n);
   if (((uintptr_t)d_bases | (uintptr_t)d_scalars | (uintptr_t)d_out) & 15)
     return fail(TB200_E_ARG, "device pointers must be 16-byte aligned");
   Plan p;
   int c = pick_c_single(std::max<size_t>(n, 1));
-  int rc = make_plan(p, 1, (uint32_t)n, 0, 1, c, 0, flags);
-  while (rc == TB200_E_LIMIT && c > 3) rc = make_plan(p, 1, (uint32_t)n, 0, 1, --c, 0, flags);
+  int rc = make_plan(p, 1, (uint32_t)n, 0, 1, c, 0, flags, g2);
+  while (rc == TB200_E_LIMIT && c > 3) rc = make_plan(p, 1, (uint32_t)n, 0, 1, --c, 0, flags, g2);
   if (rc) return rc;
   g.marks.clear();
   rc = run_pipeline(p, (const uint32_t*)d_scalars, (const uint4*)d_bases, (uint4*)d_out, st, points_ready, arena);
@@ -679,6 +696,63 @@ int tb200_msm_g1(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, un
   if (d_b) cudaFreeAsync(d_b, g.stream);
   if (d_s) cudaFreeAsync(d_s, g.stream);
   return rc;
+}
+
+// ---- G2 (MultilinearPC::open, commit_g2, G2 compress) -------------------------------------------
+int tb200_msm_g2_dev(const void* d_bases, const void* d_scalars, size_t n, unsigned flags, void* d_out, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_out || (n && (!d_bases || !d_scalars))) return fail(TB200_E_ARG, "null pointer");
+  CU(cudaSetDevice(g.device));
+  return msm_dev_locked(d_bases, d_scalars, n, flags, d_out, stream ? (cudaStream_t)stream : g.stream, nullptr, nullptr,
+                        true, true);
+}
+
+int tb200_msm_g2(const uint64_t* bases, const uint64_t* scalars, size_t n, unsigned flags, uint64_t out[24]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || (n && (!bases || !scalars))) return fail(TB200_E_ARG, "null pointer");
+  CU(cudaSetDevice(g.device));
+  uint4 *d_b = nullptr, *d_s = nullptr;
+  if (n) {
+    CU(cudaMallocAsync((void**)&d_b, n * 192, g.stream));
+    CU(cudaMallocAsync((void**)&d_s, n * 32, g.stream));
+    CU(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(d_b, bases, n * 192, cudaMemcpyHostToDevice, g.stream));
+  }
+  int rc = msm_dev_locked(d_b ? d_b : g.d_result, d_s ? d_s : g.d_result, n, flags, g.d_result, g.stream, nullptr,
+                          nullptr, true, true);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(g.h_result, g.d_result, 192, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
+    else memcpy(out, g.h_result, 192);
+  }
+  if (d_b) cudaFreeAsync(d_b, g.stream);
+  if (d_s) cudaFreeAsync(d_s, g.stream);
+  return rc;
+}
+
+int tb200_compress_g2(uint64_t* vec, size_t split, const uint64_t scaler[4], unsigned flags) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!vec || !scaler) return fail(TB200_E_ARG, "null pointer");
+  if (split == 0) return 0;
+  if (split >= (1u << 26)) return fail(TB200_E_LIMIT, "split too large");
+  CU(cudaSetDevice(g.device));
+  uint4* d_v = nullptr;
+  uint32_t* d_k = nullptr;
+  CU(cudaMallocAsync((void**)&d_v, 2 * split * 192, g.stream));
+  CU(cudaMallocAsync((void**)&d_k, 32, g.stream));
+  CU(cudaMemcpyAsync(d_v, vec, 2 * split * 192, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(d_k, scaler, 32, cudaMemcpyHostToDevice, g.stream));
+  LAUNCH(k_compress_g2, cdiv(split, 64), 64, g.stream, d_v, (uint32_t)split, d_k,
+         (flags & TB200_SCALARS_MONT) ? 1 : 0);
+  CU(cudaMemcpyAsync(vec, d_v, split * 192, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  cudaFreeAsync(d_v, g.stream);
+  cudaFreeAsync(d_k, g.stream);
+  return 0;
 }
 
 // ---- SRS / batch ----------------------------------------------------------------------------------------------------
@@ -1179,6 +1253,26 @@ int tb200_test_g1_add(const uint64_t* p_xy, const uint64_t* q_xy, size_t n, uint
                                (uint32_t)n, (uint4*)d1);
                         return 0;
                       });
+}
+int tb200_test_g2_add(const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!p || !q || !out || n == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(g.device));
+  return with_buffers(p, n * 192, q, n * 192, out, n * 192, nullptr, 0, [&](char* da, char* db, char* d1, char*) {
+    LAUNCH(k_test_g2_add, cdiv(n, 64), 64, g.stream, (const uint4*)da, (const uint4*)db, (uint32_t)n, (uint4*)d1);
+    return 0;
+  });
+}
+int tb200_test_g2_mul(const uint64_t* p, const uint64_t* k, size_t n, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!p || !k || !out || n == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(g.device));
+  return with_buffers(p, n * 192, k, n * 32, out, n * 192, nullptr, 0, [&](char* da, char* db, char* d1, char*) {
+    LAUNCH(k_test_g2_mul, cdiv(n, 64), 64, g.stream, (const uint4*)da, (const uint32_t*)db, (uint32_t)n, (uint4*)d1);
+    return 0;
+  });
 }
 int tb200_test_g1_mul(const uint64_t* p_xy, const uint64_t* k, size_t n, uint64_t* out_xy) {
   std::lock_guard<std::mutex> lk(g_mu);
