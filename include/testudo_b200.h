@@ -71,6 +71,20 @@ int tb200_msm_g2_dev(const void* d_bases, const void* d_scalars, size_t n, unsig
 /* `compress` on a G2 vector (src/mipp.rs:133, 354-367): vec[i] = vec[i] + scaler * vec[split + i], i < split */
 int tb200_compress_g2(uint64_t* vec, size_t split, const uint64_t scaler[4], unsigned flags);
 
+/* ---- PST openings: `MultilinearPC::open` (G2 proofs, src/sqrt_pst.rs:225) and the fork's `open_g1` (G1 proofs,
+ * src/mipp.rs:144) of ark-poly-commit 0.4 multilinear_pc (call sites M6 and X1) ------------
+ * evals: the 2^nv evaluations of the polynomial (`to_evaluations()` order); point: nv field elements; both in the
+ * representation selected by `flags` (TB200_SCALARS_MONT = ark's in-memory Fr). level_bases[i] = the CRS level used
+ * for variable i: 2^(nv - i) affine points (`ck.powers_of_h[off + i]` resp. `ck.powers_of_g[off + i]`, off =
+ * ck.nv - nv for the variable-CRS fork). For i in 0..nv, k = nv - i:
+ *     q_k[b] = r_k[2b+1] - r_k[2b],  r_{k-1}[b] = r_k[2b] (1 - point[i]) + r_k[2b+1] point[i],
+ *     proofs[i] = MSM(level_bases[i], q_k duplicated to length 2^k).into_affine()
+ * The quotient loop runs on the device (no host pass over the evaluations). proofs: nv x 12 (G1) / nv x 24 (G2). */
+int tb200_pst_open_g1(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                      unsigned flags, uint64_t* proofs);
+int tb200_pst_open_g2(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                      unsigned flags, uint64_t* proofs);
+
 /* ---- shared-base (SRS) batched MSM -------------------------------------------------------------------
  * Replaces the row fan-out `self.polys.par_iter().map(|p| MultilinearPC::commit(ck, p))`
  * (src/sqrt_pst.rs:121-125: 2^m_col MSMs over ck.powers_of_g[0]) and the Hyrax fan-out

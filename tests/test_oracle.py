@@ -96,3 +96,22 @@ def test_c_oracle_large_by_dlog(oracle_c):
     ints = h.np_scalars_to_ints(sc)
     exp = o.mul(sum(s * (a + step * k) for k, s in enumerate(ints)) % o.R_ORDER, o.G)
     assert h.pt_from_np(oracle_c.msm_g1(bases, sc)) == exp
+
+
+def test_pst_open_restatement_satisfies_the_pst_identity():
+    """oracle/pst.py (ark-poly-commit `MultilinearPC::open` restated): with a known trapdoor t the proofs' exponents
+    satisfy f(t) - f(point) = sum_i (t_i - point_i) q_i(t_{i+1..}) -- the relation `check` verifies with pairings --
+    and the MSM over the synthetic CRS level equals q_i(t_{i+1..}) * G."""
+    from oracle import pst
+
+    nv = 5
+    t = o.rand_scalars(nv, 1)
+    evals = o.rand_scalars(1 << nv, 2)
+    point = o.rand_scalars(nv, 3)
+    qs = pst.quotients(evals, point)
+    dl = [pst.mle_eval(q, t[i + 1:]) for i, q in enumerate(qs)]
+    lhs = (pst.mle_eval(evals, t) - pst.mle_eval(evals, point)) % o.R_ORDER
+    assert lhs == sum((t[i] - point[i]) * dl[i] for i in range(nv)) % o.R_ORDER
+    levels = [[o.mul(e, o.G) for e in pst.eq_exponents(t[k:])] for k in range(nv)]
+    proofs = pst.open_proofs(evals, point, levels, o.msm_naive)
+    assert proofs == [o.mul(d, o.G) for d in dl]

@@ -755,6 +755,72 @@ int tb200_compress_g2(uint64_t* vec, size_t split, const uint64_t scaler[4], uns
   return 0;
 }
 
+// ---- MultilinearPC::open (G2 proofs) / open_g1 (G1 proofs): quotient loop on the device, one MSM per variable ---------
+static int pst_open_locked(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                           unsigned flags, uint64_t* proofs, bool g2) {
+  if (!evals || !point || !level_bases || !proofs) return fail(TB200_E_ARG, "null pointer");
+  if (nv == 0) return 0;
+  if (nv > 28) return fail(TB200_E_LIMIT, "nv = %zu: at most 2^28 evaluations", nv);
+  for (size_t i = 0; i < nv; i++)
+    if (!level_bases[i]) return fail(TB200_E_ARG, "level_bases[%zu] is null", i);
+  const size_t n = size_t(1) << nv, pt = g2 ? 192 : 96;
+  uint32_t *d_r0 = nullptr, *d_r1 = nullptr, *d_q = nullptr, *d_p = nullptr;
+  uint4 *d_bases = nullptr, *d_proofs = nullptr;
+  CU(cudaMallocAsync((void**)&d_r0, n * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_r1, std::max<size_t>(n / 2, 1) * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_q, n * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_p, nv * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_bases, n * pt, g.stream));
+  CU(cudaMallocAsync((void**)&d_proofs, nv * pt, g.stream));
+  CU(cudaMemcpyAsync(d_r0, evals, n * 32, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(d_p, point, nv * 32, cudaMemcpyHostToDevice, g.stream));
+  if (!(flags & TB200_SCALARS_MONT)) {
+    LAUNCH(k_fr_to_mont, cdiv(n, 128), 128, g.stream, d_r0, (uint32_t)n);
+    LAUNCH(k_fr_to_mont, cdiv(nv, 128), 128, g.stream, d_p, (uint32_t)nv);
+  }
+  int rc = 0;
+  uint32_t *r_in = d_r0, *r_out = d_r1;
+  for (size_t i = 0; i < nv && rc == 0; i++) {
+    const size_t k = nv - i, half = size_t(1) << (k - 1);
+    // the level's bases travel while the quotient kernel runs (same stream order keeps d_bases safe: the previous
+    // level's MSM has been enqueued before this copy)
+    CU(cudaMemcpyAsync(d_bases, level_bases[i], 2 * half * pt, cudaMemcpyHostToDevice, g.stream));
+    LAUNCH(k_pst_level, cdiv(half, 128), 128, g.stream, r_in, (uint32_t)half, d_p + 8 * i, r_out, d_q);
+    rc = msm_dev_locked(d_bases, d_q, 2 * half, TB200_SCALARS_MONT, (char*)d_proofs + i * pt, g.stream, nullptr,
+                        nullptr, false, g2);
+    std::swap(r_in, r_out);
+  }
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(proofs, d_proofs, nv * pt, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "proof copy failed: %s", cudaGetErrorString(e));
+  } else {
+    cudaStreamSynchronize(g.stream);
+  }
+  g.marks.clear();
+  cudaFreeAsync(d_r0, g.stream);
+  cudaFreeAsync(d_r1, g.stream);
+  cudaFreeAsync(d_q, g.stream);
+  cudaFreeAsync(d_p, g.stream);
+  cudaFreeAsync(d_bases, g.stream);
+  cudaFreeAsync(d_proofs, g.stream);
+  return rc;
+}
+int tb200_pst_open_g1(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                      unsigned flags, uint64_t* proofs) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  CU(cudaSetDevice(g.device));
+  return pst_open_locked(evals, nv, point, level_bases, flags, proofs, false);
+}
+int tb200_pst_open_g2(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                      unsigned flags, uint64_t* proofs) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  CU(cudaSetDevice(g.device));
+  return pst_open_locked(evals, nv, point, level_bases, flags, proofs, true);
+}
+
 // ---- SRS / batch ----------------------------------------------------------------------------------------------------
 int tb200_srs_load(const uint64_t* bases_xy, size_t n, int window_bits, tb200_srs_t* out) {
   std::lock_guard<std::mutex> lk(g_mu);

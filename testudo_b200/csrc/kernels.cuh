@@ -701,6 +701,48 @@ __global__ void __launch_bounds__(256) k_fr_matvec(const uint32_t* __restrict__ 
   }
 }
 
+// One level of `MultilinearPC::open` / `open_g1` (ark-poly-commit 0.4 multilinear_pc; call sites
+// src/sqrt_pst.rs:225, src/mipp.rs:144): for b < half
+//     q[b] = r[2b+1] - r[2b],      r'[b] = r[2b] (1 - p) + r[2b+1] p = r[2b] + p q[b]
+// and the MSM scalars of the level are q duplicated to length 2 half (`cur_q[x >> 1]`). Everything in Montgomery form;
+// canonical callers convert with k_fr_to_mont first.
+__global__ void __launch_bounds__(128) k_pst_level(const uint32_t* __restrict__ r_in, uint32_t half,
+                                                   const uint32_t* __restrict__ p, uint32_t* __restrict__ r_out,
+                                                   uint32_t* __restrict__ q_dup) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= half) return;
+  const uint4* src = reinterpret_cast<const uint4*>(r_in + 16 * (uint64_t)b);
+  const uint4 l0 = src[0], l1 = src[1], h0 = src[2], h1 = src[3];
+  uint32_t lo[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+  uint32_t hi[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  uint32_t pt[8], q[8], t[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) pt[k] = p[k];
+  mod_sub<FrParams>(q, hi, lo);
+  mont_mul<FrParams>(t, pt, q);
+  mod_add<FrParams>(t, t, lo);
+  uint4* ro = reinterpret_cast<uint4*>(r_out + 8 * (uint64_t)b);
+  ro[0] = make_uint4(t[0], t[1], t[2], t[3]);
+  ro[1] = make_uint4(t[4], t[5], t[6], t[7]);
+  uint4* qo = reinterpret_cast<uint4*>(q_dup + 16 * (uint64_t)b);
+  qo[0] = qo[2] = make_uint4(q[0], q[1], q[2], q[3]);
+  qo[1] = qo[3] = make_uint4(q[4], q[5], q[6], q[7]);
+}
+// canonical -> Montgomery in place (a * R^2 * R^-1)
+__global__ void __launch_bounds__(128) k_fr_to_mont(uint32_t* __restrict__ v, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t a[8], r2[8], t[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    a[k] = v[8 * (uint64_t)i + k];
+    r2[k] = FrParams::r2(k);
+  }
+  mont_mul<FrParams>(t, a, r2);
+#pragma unroll
+  for (int k = 0; k < 8; k++) v[8 * (uint64_t)i + k] = t[k];
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // small utilities
 // ------------------------------------------------------------------------------------------------------------
