@@ -9,7 +9,7 @@ import pytest
 
 import helpers as h
 from oracle import bls12_377 as o
-from testudo_b200 import _lib, commitments, fr, sqrt_pst
+from testudo_b200 import _lib, commitments, fr, mipp, sqrt_pst
 
 pytestmark = pytest.mark.gpu
 GOLD = h.load_golden("msm_golden.json")
@@ -167,3 +167,57 @@ def test_get_q_chis_eval_on_device(engine, nv):
     assert np.array_equal(poly.chis_b, chis_host)
     direct = sum(zi * fr.get_chi_i(r, i) for i, zi in enumerate(z)) % o.R_ORDER      # check_sqrt_poly_eval
     assert poly.eval(r) == direct
+
+
+def _crs_levels(engine, t, g2):
+    """Synthetic CRS with known trapdoor: powers[k][x] = eq((t_k..), x) * generator."""
+    from oracle import bls12_377_g2 as o2
+    from oracle import pst
+
+    levels = []
+    for k in range(len(t)):
+        e = pst.eq_exponents(t[k:])
+        out = np.zeros((len(e), 24 if g2 else 12), np.uint64)
+        gen = np.array([o2.affine_to_words(o2.G2)], dtype=np.uint64) if g2 else h.pts_to_np([o.G])
+        gen = np.ascontiguousarray(np.tile(gen, (len(e), 1)))
+        fn = engine.tb200_test_g2_mul if g2 else engine.tb200_test_g1_mul
+        _lib.check(fn(P(gen), P(h.scalars_to_np(e)), len(e), P(out)))
+        levels.append(out)
+    return levels
+
+
+@pytest.mark.parametrize("nv", [4, 7])
+def test_open_with_full_crs_g2_proof_and_mipp_open_g1(engine, nv):
+    """`Polynomial::open` with the whole CommitterKey (src/sqrt_pst.rs:168-230): the PST proof of q at a_rev (G2 MSMs,
+    :225) and MIPP's final_h / pst_proof_h (src/mipp.rs:114-144) against the closed forms a known trapdoor gives."""
+    from oracle import bls12_377_g2 as o2
+    from oracle import pst
+
+    m_col = nv // 2
+    m_row = nv - m_col
+    odd = nv % 2
+    t = o.rand_scalars(m_row, 900 + nv)
+    g_levels = _crs_levels(engine, t, False)
+    h_levels = _crs_levels(engine, t, True)
+    z = o.rand_scalars(1 << nv, 910 + nv)
+    r = o.rand_scalars(nv, 920 + nv)
+    poly = sqrt_pst.Polynomial.from_evaluations(h.scalars_to_np(z, mont=True))
+    ck = sqrt_pst.CommitterKey.from_points(g_levels[0]).with_levels(g_levels, h_levels)
+    comm_list, _ = poly.commit(ck)
+    opened = poly.open(fake_transcript(), comm_list, ck, r)
+    # PST proof of q at a_rev: proof_i = q_i(t_{i+1..}) * G2
+    q = fr.from_mont_words(poly.q)
+    a_rev = list(r[: m_col + odd])[::-1]
+    dl = [pst.mle_eval(qi, t[i + 1:]) for i, qi in enumerate(pst.quotients(q, a_rev))]
+    assert [o2.affine_from_words(p) for p in opened.pst_proof] == [o2.mul(d, o2.G2) for d in dl]
+    # and U = q(t) * G closes the PST identity against the claimed evaluation q(a_rev)
+    assert h.pt_from_np(opened.u) == o.mul(pst.mle_eval(q, t), o.G)
+    assert (pst.mle_eval(q, t) - pst.mle_eval(q, a_rev)) % o.R_ORDER == \
+        sum((t[i] - a_rev[i]) * dl[i] for i in range(m_row)) % o.R_ORDER
+    # MIPP: final_h = p_h(t_odd..) * G2 and the open_g1 proof of p_h at rs over powers_of_g[odd + i]
+    mp = opened.mipp
+    ph = mipp.polynomial_evaluations_from_transcript(mp.xs_inv)
+    assert o2.affine_from_words(mp.final_h) == o2.mul(pst.mle_eval(ph, t[odd:]), o2.G2)
+    dlh = [pst.mle_eval(qi, t[odd + i + 1:]) for i, qi in enumerate(pst.quotients(ph, mp.rs))]
+    assert [h.pt_from_np(p) for p in mp.pst_proof_h] == [o.mul(d, o.G) for d in dlh]
+    ck.close()

@@ -1,8 +1,10 @@
-"""Mirror of the G1 work in `mipp.rs`: `multiexponentiation`, `compress`, and the prover loop of
-`MippProof::prove` (src/mipp.rs:31-153, 354-394). G2 / GT work (compress of h, pairing products, commit_g2) and the
-Poseidon transcript are out of scope -- challenges come from a callback.
+"""Mirror of the group work in `mipp.rs`: `multiexponentiation`, `compress`, and the prover loop of
+`MippProof::prove` (src/mipp.rs:31-153, 354-394), including -- when the G2 key `h` and the CRS levels are passed --
+the G2 `compress` of the commitment key (:114), the structured polynomial (:128-131, 159-180), `commit_g2` (:133) and
+the `open_g1` proof (:144). The GT work (pairing products `comms_t`) and the Poseidon transcript are out of scope
+ -- challenges come from a callback.
 
-The vectors stay on the GPU across rounds (tb200_mipp_g1_*): upload once, two points back per round.
+The G1 vectors stay on the GPU across rounds (tb200_mipp_g1_*): upload once, two points back per round.
 """
 from __future__ import annotations
 
@@ -12,7 +14,7 @@ from typing import Callable, List, Tuple
 
 import numpy as np
 
-from . import _lib, curve, fr, msm
+from . import _lib, curve, fr, msm, msm_g2, multilinear_pc
 
 
 def _ptr(a: np.ndarray):
@@ -49,19 +51,29 @@ class MippProofG1:
     final_y: np.ndarray = None
     xs: List[int] = field(default_factory=list)
     xs_inv: List[int] = field(default_factory=list)
+    final_h: np.ndarray = None          # [24] G2 affine, when the key `h` was passed
+    pst_proof_h: np.ndarray = None      # [m, 12] `ProofG1.proofs`, when the CRS levels were passed
+    rs: List[int] = field(default_factory=list)
 
     @classmethod
-    def prove(cls, challenge: Callable[[bytes, List[np.ndarray]], int], a, y_mont, U) -> "MippProofG1":
-        """G1 part of src/mipp.rs:31-153. `challenge(label, points)` returns c_inv as an integer mod r after the
-        reference would have appended `points` (comm_u_l, comm_u_r; comm_t_l/r are GT and out of scope)."""
+    def prove(cls, challenge: Callable[[bytes, List[np.ndarray]], int], a, y_mont, U, h=None,
+              powers_of_g_levels=None) -> "MippProofG1":
+        """src/mipp.rs:31-153 without the GT work. `challenge(label, points)` returns the squeezed scalar as an integer
+        mod r after the reference would have appended `points` (comm_u_l, comm_u_r; comm_t_l/r are GT and out of scope).
+        `h` = `ck.powers_of_h[odd]` ([n, 24]); `powers_of_g_levels[i]` = `ck.powers_of_g[off + i]` for `open_g1`."""
         lib = _lib.engine()
         a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 12)
         y = np.ascontiguousarray(y_mont, dtype=np.uint64).reshape(-1, 4)
         if len(a) != len(y):
             raise InvalidIPVectorLength()
         out = cls()
+        m_h = None
+        if h is not None:
+            m_h = np.ascontiguousarray(h, dtype=np.uint64).reshape(-1, 24)
+            if len(m_h) != len(a):
+                raise InvalidIPVectorLength()
         challenge(b"U", [np.asarray(U)])                                 # transcript.append(b"U", U), :56
-        h = ctypes.c_void_p()
+        h_key, h = h, ctypes.c_void_p()
         _lib.check(lib.tb200_mipp_g1_begin(_ptr(a), _ptr(y), len(a), _lib.SCALARS_MONT, ctypes.byref(h)))
         try:
             while lib.tb200_mipp_g1_len(h) > 1:                          # :58
@@ -73,6 +85,8 @@ class MippProofG1:
                 cw = curve.scalars_to_words([c], mont=True)[0]
                 ciw = curve.scalars_to_words([c_inv], mont=True)[0]
                 _lib.check(lib.tb200_mipp_g1_fold(h, _ptr(cw), _ptr(ciw)))   # compress(m_a, c), compress_field(m_y, c_inv)
+                if m_h is not None:
+                    m_h = msm_g2.compress(m_h, len(m_h) // 2, ciw, mont=True)   # compress(&mut m_h, split, &c_inv), :114
                 out.comms_u.append((ul, ur))                             # :117
                 out.xs.append(c)
                 out.xs_inv.append(c_inv)
@@ -82,4 +96,29 @@ class MippProofG1:
             out.final_a, out.final_y = fa[0], fy[0]                      # :122
         finally:
             _lib.check(lib.tb200_mipp_g1_end(h))
+        if m_h is not None:
+            assert len(m_h) == 1                                         # :121
+            out.final_h = m_h[0]
+            # structured polynomial p_h with final_h = h^{p_h(t)} (:128-131); commit_g2 is the reference's
+            # debug_assert cross-check (:133-134) -- executed, like there
+            evals = polynomial_evaluations_from_transcript(out.xs_inv)
+            ev_w = curve.scalars_to_words(evals, mont=True)
+            c_h = msm_g2.msm_unchecked(h_key, ev_w)
+            assert np.array_equal(c_h, out.final_h), "debug_assert!(c.h_product == final_h) (src/mipp.rs:134)"
+            if powers_of_g_levels is not None:
+                m = len(out.xs_inv)
+                out.rs = [challenge(b"random_point", []) % fr.R for _ in range(m)]          # :138-141
+                rs_w = curve.scalars_to_words(out.rs, mont=True) if m else np.zeros((0, 4), dtype=np.uint64)
+                out.pst_proof_h = multilinear_pc.open_g1(powers_of_g_levels, ev_w, rs_w)   # :144
         return out
+
+
+def polynomial_evaluations_from_transcript(cs_inv: List[int]) -> List[int]:
+    """src/mipp.rs:159-180: evaluations over {0,1}^m of prod_i (1 - z_i + cs_inv[m - i - 1] z_i); bit j of the index
+    (from the lsb) selects cs_inv[m - j - 1]."""
+    m = len(cs_inv)
+    evals = [1]
+    for j in range(m):
+        f = cs_inv[m - j - 1] % fr.R
+        evals = evals + [e * f % fr.R for e in evals]
+    return evals

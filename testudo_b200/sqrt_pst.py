@@ -10,9 +10,10 @@ What runs where:
     kernel reads coalesced, so `from_evaluations` costs nothing.
   * `open`    -- M2 `msm_unchecked(comms, chis)` (src/sqrt_pst.rs:198), M3 `MultilinearPC::commit(ck, q)` (:205)
     and the G1 part of `MippProof::prove` (:212) run on the GPU.
-  * the pairing product `t` (src/sqrt_pst.rs:131-144), the G2 opening (src/sqrt_pst.rs:225) and the Poseidon
-    transcript are OUT OF SCOPE of this engine: `commit` returns t = None, `open` returns the G1
-    results and takes the Fiat-Shamir challenges from a callback.
+  * with the G2 side of the key (`powers_of_h`, `powers_of_g` levels) `open` also produces the PST proof
+    `MultilinearPC::open(ck, &q, &a_rev)` (:218-225, G2 MSMs) and MIPP's `final_h` / `pst_proof_h` (SURVEY.md 8f rank 1).
+  * the pairing product `t` (src/sqrt_pst.rs:131-144) and the Poseidon transcript are OUT OF SCOPE of this engine
+    (SURVEY.md 8f): `commit` returns t = None, `open` takes the Fiat-Shamir challenges from a callback.
 """
 from __future__ import annotations
 
@@ -22,7 +23,7 @@ from typing import Callable, List, Optional, Tuple
 
 import numpy as np
 
-from . import _lib, fr, mipp, msm
+from . import _lib, curve, fr, mipp, msm, multilinear_pc
 
 
 def _ptr(a: np.ndarray):
@@ -37,6 +38,16 @@ class CommitterKey:
         self.powers_of_g0 = powers_of_g0
         self.nv = nv
         self._h = handle
+        # optional rest of `CommitterKey<E>`: powers_of_g[k] / powers_of_h[k] with 2^(nv - k) points each
+        self.powers_of_g: Optional[List[np.ndarray]] = None     # [*, 12] per level
+        self.powers_of_h: Optional[List[np.ndarray]] = None     # [*, 24] per level
+
+    def with_levels(self, powers_of_g: List[np.ndarray], powers_of_h: List[np.ndarray]) -> "CommitterKey":
+        assert len(powers_of_g) == self.nv and len(powers_of_h) == self.nv
+        assert all(len(l) == 1 << (self.nv - k) for k, l in enumerate(powers_of_g))
+        assert all(len(l) == 1 << (self.nv - k) for k, l in enumerate(powers_of_h))
+        self.powers_of_g, self.powers_of_h = list(powers_of_g), list(powers_of_h)
+        return self
 
     @classmethod
     def from_points(cls, powers_of_g0, window_bits: int = 0) -> "CommitterKey":
@@ -73,6 +84,7 @@ class OpenG1:
     u: np.ndarray
     comm_q: np.ndarray
     mipp: "mipp.MippProofG1"
+    pst_proof: Optional[np.ndarray] = None   # `Proof{proofs: Vec<G2Affine>}` as [m_row, 24] when ck carries powers_of_h
 
 
 class _DeviceBuffer:
@@ -194,5 +206,11 @@ class Polynomial:
         c_u = msm.msm_unchecked(comm_list, self.chis_b)                # M2, src/sqrt_pst.rs:198
         comm_q = pc_commit(ck, self.q)                                 # M3, src/sqrt_pst.rs:205
         assert np.array_equal(c_u, comm_q), "debug_assert!(c_u == comm.g_product) (src/sqrt_pst.rs:206)"
-        proof = mipp.MippProofG1.prove(challenge, comm_list, self.chis_b, c_u)   # src/sqrt_pst.rs:212-213
-        return OpenG1(u=c_u, comm_q=comm_q, mipp=proof)
+        h_vec = ck.powers_of_h[self.odd] if ck.powers_of_h is not None else None     # src/sqrt_pst.rs:207
+        g_levels = ck.powers_of_g[self.odd:] if ck.powers_of_g is not None else None  # variable CRS: off = ck.nv - m
+        proof = mipp.MippProofG1.prove(challenge, comm_list, self.chis_b, c_u, h_vec, g_levels)   # :212-213
+        pst_proof = None
+        if ck.powers_of_h is not None:
+            a_rev = list(point[: self.m + self.odd])[::-1]                        # :218-222
+            pst_proof = multilinear_pc.open(ck.powers_of_h, self.q, curve.scalars_to_words(a_rev, mont=True))  # :225
+        return OpenG1(u=c_u, comm_q=comm_q, mipp=proof, pst_proof=pst_proof)
