@@ -20,11 +20,13 @@ struct Fq2 {
   Fq c0, c1;
 };
 
-// out-of-line Fq multiplier for the G2 paths (3 calls per Fq2 product): keeps the G2 kernels' code small
+// The three (two) Fq products of an Fq2 product (square) are independent: they are inlined into ONE out-of-line
+// function per Fq2 operation so that ptxas interleaves their carry chains. The G2 paths are latency-bound
+// (sqrt(n)-sized MSMs, 253-step doubling chains), and a lone Montgomery product is a ~600-cycle dependent chain.
 #if defined(__CUDA_ARCH__)
-__device__ __noinline__ void fq_mul_ol(Fq* r, const Fq* a, const Fq* b) { fq_mul(*r, *a, *b); }
+#define TB_G2_OL __device__ __noinline__
 #else
-inline void fq_mul_ol(Fq* r, const Fq* a, const Fq* b) { fq_mul(*r, *a, *b); }
+#define TB_G2_OL inline
 #endif
 
 TB_HD void fq2_add(Fq2& r, const Fq2& a, const Fq2& b) {
@@ -64,31 +66,44 @@ TB_HD void fq_mul5(Fq& r, const Fq& a) {
   fq_add(r, t, a);
 }
 // (a0 + a1 u)(b0 + b1 u) = (a0 b0 - 5 a1 b1) + ((a0 + a1)(b0 + b1) - a0 b0 - a1 b1) u     (Karatsuba: 3 Fq products)
-TB_HD void fq2_mul(Fq2& r, const Fq2& a, const Fq2& b) {
+TB_G2_OL void fq2_mul_ol(Fq2* rp, const Fq2* ap, const Fq2* bp) {
+  const Fq2 a = *ap, b = *bp;
   Fq v0, v1, s, t, m;
-  fq_mul_ol(&v0, &a.c0, &b.c0);
-  fq_mul_ol(&v1, &a.c1, &b.c1);
   fq_add(s, a.c0, a.c1);
   fq_add(t, b.c0, b.c1);
-  fq_mul_ol(&m, &s, &t);
+  mont_mul_lazy<FqParams>(v0.l, a.c0.l, b.c0.l);   // three independent chains
+  mont_mul_lazy<FqParams>(v1.l, a.c1.l, b.c1.l);
+  mont_mul_lazy<FqParams>(m.l, s.l, t.l);
+  mod_reduce_once<FqParams>(v0.l);
+  mod_reduce_once<FqParams>(v1.l);
+  mod_reduce_once<FqParams>(m.l);
   fq_sub(m, m, v0);
+  Fq2 r;
   fq_sub(r.c1, m, v1);
   fq_mul5(t, v1);
   fq_sub(r.c0, v0, t);
+  *rp = r;
 }
+TB_HD void fq2_mul(Fq2& r, const Fq2& a, const Fq2& b) { fq2_mul_ol(&r, &a, &b); }
 // (a0 + a1 u)^2 = ((a0 + a1)(a0 - 5 a1) + 4 a0 a1) + 2 a0 a1 u                            (2 Fq products)
-TB_HD void fq2_sqr(Fq2& r, const Fq2& a) {
+TB_G2_OL void fq2_sqr_ol(Fq2* rp, const Fq2* ap) {
+  const Fq2 a = *ap;
   Fq v, s, t, m;
-  fq_mul_ol(&v, &a.c0, &a.c1);
   fq_add(s, a.c0, a.c1);
   fq_mul5(t, a.c1);
   fq_sub(t, a.c0, t);
-  fq_mul_ol(&m, &s, &t);
+  mont_mul_lazy<FqParams>(v.l, a.c0.l, a.c1.l);    // two independent chains
+  mont_mul_lazy<FqParams>(m.l, s.l, t.l);
+  mod_reduce_once<FqParams>(v.l);
+  mod_reduce_once<FqParams>(m.l);
+  Fq2 r;
   fq_dbl(t, v);          // 2 a0 a1
   fq_dbl(s, t);          // 4 a0 a1
   fq_add(r.c0, m, s);
   r.c1 = t;
+  *rp = r;
 }
+TB_HD void fq2_sqr(Fq2& r, const Fq2& a) { fq2_sqr_ol(&r, &a); }
 // 1 / (a0 + a1 u) = (a0 - a1 u) / (a0^2 + 5 a1^2)
 TB_HD void fq2_inv(Fq2& r, const Fq2& a) {
   Fq n, t, ni;
