@@ -220,8 +220,11 @@ int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs,
   p.S_max = cdiv(std::max<uint64_t>(p.M_max, 1), p.K);
   p.ntiles = (uint32_t)(p.B / SCAN_TILE + 1);
   p.Ls.clear();
+  // Fan-in 32 at level 0 (throughput-bound: millions of buckets). The levels above it of a SINGLE MSM hold few
+  // elements and are latency-bound (2L - 1 sequential additions + log2(ell) doublings per thread): fan-in 8 there
+  // (measured at 2^24, c = 20: 3.5 -> 1.9 ms for the upper levels). Batches keep 32: thousands of rows fill the GPU.
   for (uint32_t n = q.nb; n > 1;) {
-    uint32_t L = std::min<uint32_t>(n, 32);
+    uint32_t L = std::min<uint32_t>(n, (batch || p.Ls.empty()) ? 32 : 8);
     p.Ls.push_back(L);
     n /= L;
   }

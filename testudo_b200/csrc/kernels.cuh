@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(128) k_fixup_final(const uint32_t* __restrict_
 // local weights 1..ell. Combining L consecutive elements i = 0..L-1 into a span of L*ell buckets:
 //     S' = sum S_i,   W' = sum W_i + ell * sum_i i * S_i      (sum_i i*S_i by a descending running sum)
 // Level 0 reads raw buckets (S_i = W_i = B_i, ell = 1; empty buckets are identified by their zero count).
-__global__ void __launch_bounds__(128) k_reduce_pass(const uint4* __restrict__ inS, const uint4* __restrict__ inW,
+__global__ void __launch_bounds__(128, 4) k_reduce_pass(const uint4* __restrict__ inS, const uint4* __restrict__ inW,
                                                      const uint32_t* __restrict__ bucket_start /* level 0 only */,
                                                      uint4* __restrict__ outS, uint4* __restrict__ outW, uint32_t L,
                                                      int log2_ell, uint64_t total_out) {
