@@ -71,6 +71,17 @@ int tb200_msm_g2_dev(const void* d_bases, const void* d_scalars, size_t n, unsig
 /* `compress` on a G2 vector (src/mipp.rs:133, 354-367): vec[i] = vec[i] + scaler * vec[split + i], i < split */
 int tb200_compress_g2(uint64_t* vec, size_t split, const uint64_t scaler[4], unsigned flags);
 
+/* MIPP's G2 commitment key m_h (src/mipp.rs:43,114) kept on the device and folded on a stream of its own, so
+ * the G2 folds overlap the G1 rounds: begin uploads `h` (n x 24 u64, n a power of two), fold(c_inv) ENQUEUES
+ * h[i] <- h[i] + c_inv * h[n/2 + i] and halves the length, read waits and downloads the current vector (len() points;
+ * final_h after the last round), end frees. `flags` selects the representation of c_inv. */
+typedef struct tb200_mipp_g2* tb200_mipp_g2_t;
+int tb200_mipp_g2_begin(const uint64_t* h_vec, size_t n, unsigned flags, tb200_mipp_g2_t* out);
+size_t tb200_mipp_g2_len(tb200_mipp_g2_t h);
+int tb200_mipp_g2_fold(tb200_mipp_g2_t h, const uint64_t c_inv[4]);
+int tb200_mipp_g2_read(tb200_mipp_g2_t h, uint64_t* out);
+int tb200_mipp_g2_end(tb200_mipp_g2_t h);
+
 /* ---- PST openings: `MultilinearPC::open` (G2 proofs, src/sqrt_pst.rs:225) and the fork's `open_g1` (G1 proofs,
  * src/mipp.rs:144) of ark-poly-commit 0.4 multilinear_pc (call sites M6 and X1) ------------
  * evals: the 2^nv evaluations of the polynomial (`to_evaluations()` order); point: nv field elements; both in the

@@ -47,6 +47,11 @@ SIGNATURES = {
     "tb200_msm_g2": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
     "tb200_msm_g2_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p, c_void_p]),
     "tb200_compress_g2": (c_int, [c_void_p, c_size_t, c_void_p, c_uint]),
+    "tb200_mipp_g2_begin": (c_int, [c_void_p, c_size_t, c_uint, c_void_p]),
+    "tb200_mipp_g2_len": (c_size_t, [c_void_p]),
+    "tb200_mipp_g2_fold": (c_int, [c_void_p, c_void_p]),
+    "tb200_mipp_g2_read": (c_int, [c_void_p, c_void_p]),
+    "tb200_mipp_g2_end": (c_int, [c_void_p]),
     "tb200_pst_open_g1": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_uint, c_void_p]),
     "tb200_pst_open_g2": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_uint, c_void_p]),
     "tb200_dev_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),

@@ -99,6 +99,11 @@ struct Ctx {
   cudaEvent_t ev_join = nullptr;
   Arena arena;
   Arena arena2;
+  // side pipelines for batches of independent small MSMs (the per-variable MSMs of a PST opening)
+  static constexpr int SIDE = 8;
+  cudaStream_t side_stream[SIDE] = {};
+  cudaEvent_t side_done[SIDE] = {};
+  Arena side_arena[SIDE];
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
   std::vector<Stage> marks;
@@ -496,6 +501,17 @@ struct tb200_mipp {
   uint32_t* scal = nullptr;  // 16 limbs staging for c, c_inv
 };
 
+// the G2 commitment key of MIPP (m_h, src/mipp.rs:43,114): folded on its own stream, overlapping the G1 rounds
+struct tb200_mipp_g2 {
+  uint32_t n = 0;
+  unsigned flags = 0;
+  uint4* h = nullptr;          // n0 G2 affine points (12 uint4 each)
+  uint32_t* scal = nullptr;    // device staging: one 8-limb scalar per round
+  uint32_t* scal_host = nullptr;  // pinned, same shape (every round has its own slot: the copies are asynchronous)
+  cudaStream_t st = nullptr;      // own stream: the folds overlap the G1 rounds on the library's streams
+  int round = 0;
+};
+
 extern "C" {
 
 int tb200_init(int device) {
@@ -544,6 +560,16 @@ void tb200_shutdown(void) {
   cudaStreamSynchronize(g.stream2);
   if (g.arena.base) cudaFree(g.arena.base);
   if (g.arena2.base) cudaFree(g.arena2.base);
+  for (int i = 0; i < g.SIDE; i++) {
+    if (g.side_stream[i]) {
+      cudaStreamSynchronize(g.side_stream[i]);
+      cudaStreamDestroy(g.side_stream[i]);
+      cudaEventDestroy(g.side_done[i]);
+      g.side_stream[i] = nullptr;
+    }
+    if (g.side_arena[i].base) cudaFree(g.side_arena[i].base);
+    g.side_arena[i] = Arena();
+  }
   g.arena = Arena();
   g.arena2 = Arena();
   cudaStreamDestroy(g.stream2);
@@ -769,11 +795,12 @@ static int pst_open_locked(const uint64_t* evals, size_t nv, const uint64_t* poi
   const size_t n = size_t(1) << nv, pt = g2 ? 192 : 96;
   uint32_t *d_r0 = nullptr, *d_r1 = nullptr, *d_q = nullptr, *d_p = nullptr;
   uint4 *d_bases = nullptr, *d_proofs = nullptr;
+  // level i occupies [off_i, off_i + 2^(nv-i)) of d_q / d_bases, off_i = 2^(nv+1) - 2^(nv-i+1)
   CU(cudaMallocAsync((void**)&d_r0, n * 32, g.stream));
   CU(cudaMallocAsync((void**)&d_r1, std::max<size_t>(n / 2, 1) * 32, g.stream));
-  CU(cudaMallocAsync((void**)&d_q, n * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_q, 2 * n * 32, g.stream));
   CU(cudaMallocAsync((void**)&d_p, nv * 32, g.stream));
-  CU(cudaMallocAsync((void**)&d_bases, n * pt, g.stream));
+  CU(cudaMallocAsync((void**)&d_bases, 2 * n * pt, g.stream));
   CU(cudaMallocAsync((void**)&d_proofs, nv * pt, g.stream));
   CU(cudaMemcpyAsync(d_r0, evals, n * 32, cudaMemcpyHostToDevice, g.stream));
   CU(cudaMemcpyAsync(d_p, point, nv * 32, cudaMemcpyHostToDevice, g.stream));
@@ -781,17 +808,38 @@ static int pst_open_locked(const uint64_t* evals, size_t nv, const uint64_t* poi
     LAUNCH(k_fr_to_mont, cdiv(n, 128), 128, g.stream, d_r0, (uint32_t)n);
     LAUNCH(k_fr_to_mont, cdiv(nv, 128), 128, g.stream, d_p, (uint32_t)nv);
   }
-  int rc = 0;
+  // the quotient loop is a cheap sequential chain; the nv MSMs that consume it are independent of each other and
+  // latency-bound (Horner chain + inversion), so they run concurrently on side streams with their own workspaces
+  std::vector<size_t> off(nv);
   uint32_t *r_in = d_r0, *r_out = d_r1;
-  for (size_t i = 0; i < nv && rc == 0; i++) {
-    const size_t k = nv - i, half = size_t(1) << (k - 1);
-    // the level's bases travel while the quotient kernel runs (same stream order keeps d_bases safe: the previous
-    // level's MSM has been enqueued before this copy)
-    CU(cudaMemcpyAsync(d_bases, level_bases[i], 2 * half * pt, cudaMemcpyHostToDevice, g.stream));
-    LAUNCH(k_pst_level, cdiv(half, 128), 128, g.stream, r_in, (uint32_t)half, d_p + 8 * i, r_out, d_q);
-    rc = msm_dev_locked(d_bases, d_q, 2 * half, TB200_SCALARS_MONT, (char*)d_proofs + i * pt, g.stream, nullptr,
-                        nullptr, false, g2);
+  size_t o = 0;
+  for (size_t i = 0; i < nv; i++) {
+    const size_t half = size_t(1) << (nv - i - 1);
+    off[i] = o;
+    CU(cudaMemcpyAsync((char*)d_bases + o * pt, level_bases[i], 2 * half * pt, cudaMemcpyHostToDevice, g.stream));
+    LAUNCH(k_pst_level, cdiv(half, 128), 128, g.stream, r_in, (uint32_t)half, d_p + 8 * i, r_out, d_q + 8 * o);
     std::swap(r_in, r_out);
+    o += 2 * half;
+  }
+  CU(cudaEventRecord(g.ev_join, g.stream));
+  const bool prof = g.profiling;
+  g.profiling = false;
+  int rc = 0;
+  for (size_t i = 0; i < nv && rc == 0; i++) {
+    const int sl = (int)(i % g.SIDE);
+    if (!g.side_stream[sl]) {
+      CU(cudaStreamCreateWithFlags(&g.side_stream[sl], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&g.side_done[sl], cudaEventDisableTiming));
+    }
+    if (i < (size_t)g.SIDE) CU(cudaStreamWaitEvent(g.side_stream[sl], g.ev_join, 0));
+    rc = msm_dev_locked((char*)d_bases + off[i] * pt, d_q + 8 * off[i], size_t(1) << (nv - i), TB200_SCALARS_MONT,
+                        (char*)d_proofs + i * pt, g.side_stream[sl], nullptr, &g.side_arena[sl], false, g2);
+  }
+  g.profiling = prof;
+  for (int sl = 0; sl < g.SIDE && sl < (int)nv; sl++) {
+    if (!g.side_stream[sl]) continue;
+    cudaEventRecord(g.side_done[sl], g.side_stream[sl]);
+    cudaStreamWaitEvent(g.stream, g.side_done[sl], 0);
   }
   if (rc == 0) {
     cudaError_t e = cudaMemcpyAsync(proofs, d_proofs, nv * pt, cudaMemcpyDeviceToHost, g.stream);
@@ -1065,6 +1113,79 @@ int tb200_mipp_g1_end(tb200_mipp_t h) {
     cudaFree(h->a);
     cudaFree(h->y);
     cudaFree(h->scal);
+  }
+  delete h;
+  return 0;
+}
+
+int tb200_mipp_g2_begin(const uint64_t* h_vec, size_t n, unsigned flags, tb200_mipp_g2_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!h_vec || !out || n == 0) return fail(TB200_E_ARG, "bad arguments");
+  if (n & (n - 1)) return fail(TB200_E_ARG, "MIPP vectors must have a power-of-two length (n = %zu)", n);
+  if (n >= (1u << 26)) return fail(TB200_E_LIMIT, "vector too long");
+  CU(cudaSetDevice(g.device));
+  tb200_mipp_g2* m = new tb200_mipp_g2();
+  m->n = (uint32_t)n;
+  m->flags = flags;
+  cudaError_t e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
+  cudaStream_t m_st = m->st;
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->h, n * 192);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->scal, 64 * 32);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&m->scal_host, 64 * 32);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->h, h_vec, n * 192, cudaMemcpyHostToDevice, m_st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(m_st);   // h_vec is only borrowed for the duration of the call
+  if (e != cudaSuccess) {
+    cudaFree(m->h);
+    cudaFree(m->scal);
+    cudaFreeHost(m->scal_host);
+    if (m->st) cudaStreamDestroy(m->st);
+    delete m;
+    return fail((int)e, "mipp_g2_begin failed: %s", cudaGetErrorString(e));
+  }
+  *out = m;
+  return 0;
+}
+size_t tb200_mipp_g2_len(tb200_mipp_g2_t h) { return h ? h->n : 0; }
+/* h[i] <- h[i] + c_inv * h[split + i]; returns after ENQUEUEING on the handle's own stream */
+int tb200_mipp_g2_fold(tb200_mipp_g2_t h, const uint64_t c_inv[4]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!h || !c_inv) return fail(TB200_E_ARG, "null pointer");
+  if (h->n < 2) return fail(TB200_E_STATE, "MIPP vector is already folded to length 1");
+  if (h->round >= 64) return fail(TB200_E_LIMIT, "too many rounds");
+  CU(cudaSetDevice(g.device));
+  const uint32_t split = h->n / 2;
+  cudaStream_t m_st = h->st;
+  memcpy(h->scal_host + 8 * h->round, c_inv, 32);
+  CU(cudaMemcpyAsync(h->scal + 8 * h->round, h->scal_host + 8 * h->round, 32, cudaMemcpyHostToDevice, m_st));
+  LAUNCH(k_compress_g2, cdiv(split, 64), 64, m_st, h->h, split, h->scal + 8 * h->round,
+         (h->flags & TB200_SCALARS_MONT) ? 1 : 0);
+  h->round++;
+  h->n = split;
+  return 0;
+}
+/* the current vector (len() points); waits for the enqueued folds */
+int tb200_mipp_g2_read(tb200_mipp_g2_t h, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!h || !out) return fail(TB200_E_ARG, "null pointer");
+  CU(cudaSetDevice(g.device));
+  cudaStream_t m_st = h->st;
+  CU(cudaMemcpyAsync(out, h->h, (size_t)h->n * 192, cudaMemcpyDeviceToHost, m_st));
+  CU(cudaStreamSynchronize(m_st));
+  return 0;
+}
+int tb200_mipp_g2_end(tb200_mipp_g2_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!h) return fail(TB200_E_ARG, "null handle");
+  if (g.ready) {
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(h->st);
+    cudaFree(h->h);
+    cudaFree(h->scal);
+    cudaFreeHost(h->scal_host);
+    cudaStreamDestroy(h->st);
   }
   delete h;
   return 0;

@@ -67,11 +67,13 @@ class MippProofG1:
         if len(a) != len(y):
             raise InvalidIPVectorLength()
         out = cls()
-        m_h = None
+        m_h = None                                                        # device handle of the folded G2 key
         if h is not None:
-            m_h = np.ascontiguousarray(h, dtype=np.uint64).reshape(-1, 24)
-            if len(m_h) != len(a):
+            hk = np.ascontiguousarray(h, dtype=np.uint64).reshape(-1, 24)
+            if len(hk) != len(a):
                 raise InvalidIPVectorLength()
+            m_h = ctypes.c_void_p()
+            _lib.check(lib.tb200_mipp_g2_begin(_ptr(hk), len(hk), _lib.SCALARS_MONT, ctypes.byref(m_h)))
         challenge(b"U", [np.asarray(U)])                                 # transcript.append(b"U", U), :56
         h_key, h = h, ctypes.c_void_p()
         _lib.check(lib.tb200_mipp_g1_begin(_ptr(a), _ptr(y), len(a), _lib.SCALARS_MONT, ctypes.byref(h)))
@@ -85,8 +87,8 @@ class MippProofG1:
                 cw = curve.scalars_to_words([c], mont=True)[0]
                 ciw = curve.scalars_to_words([c_inv], mont=True)[0]
                 _lib.check(lib.tb200_mipp_g1_fold(h, _ptr(cw), _ptr(ciw)))   # compress(m_a, c), compress_field(m_y, c_inv)
-                if m_h is not None:
-                    m_h = msm_g2.compress(m_h, len(m_h) // 2, ciw, mont=True)   # compress(&mut m_h, split, &c_inv), :114
+                if m_h is not None:                                      # compress(&mut m_h, split, &c_inv), :114
+                    _lib.check(lib.tb200_mipp_g2_fold(m_h, _ptr(ciw)))     # enqueued: overlaps the next G1 round
                 out.comms_u.append((ul, ur))                             # :117
                 out.xs.append(c)
                 out.xs_inv.append(c_inv)
@@ -94,11 +96,20 @@ class MippProofG1:
             fy = np.zeros((1, 4), dtype=np.uint64)
             _lib.check(lib.tb200_mipp_g1_read(h, _ptr(fa), _ptr(fy)))
             out.final_a, out.final_y = fa[0], fy[0]                      # :122
+        except BaseException:
+            if m_h is not None:
+                lib.tb200_mipp_g2_end(m_h)
+            raise
         finally:
             _lib.check(lib.tb200_mipp_g1_end(h))
         if m_h is not None:
-            assert len(m_h) == 1                                         # :121
-            out.final_h = m_h[0]
+            assert lib.tb200_mipp_g2_len(m_h) == 1                       # :121
+            fh = np.zeros((1, 24), dtype=np.uint64)
+            try:
+                _lib.check(lib.tb200_mipp_g2_read(m_h, _ptr(fh)))
+            finally:
+                _lib.check(lib.tb200_mipp_g2_end(m_h))
+            out.final_h = fh[0]
             # structured polynomial p_h with final_h = h^{p_h(t)} (:128-131); commit_g2 is the reference's
             # debug_assert cross-check (:133-134) -- executed, like there
             evals = polynomial_evaluations_from_transcript(out.xs_inv)
