@@ -36,10 +36,36 @@ struct FakeTranscript {
   }
 };
 
+// mode "g2": blob in : u64 nv | evals[2^nv] Fr | point[nv] Fr | G2 levels (2^nv, 2^(nv-1), .., 2 points) | G1 levels
+//            blob out: G2 proofs[nv] | G1 proofs[nv] | msm_g2(level 0, evals) | compress(level 0, split, point[0])[split]
+static int run_g2(const char* fin, const char* fout) {
+  std::ifstream in(fin, std::ios::binary);
+  uint64_t nv;
+  in.read((char*)&nv, 8);
+  auto evals = rd<Fr>(in, size_t(1) << nv);
+  auto point = rd<Fr>(in, nv);
+  std::vector<std::vector<G2Affine>> h_levels;
+  std::vector<std::vector<G1Affine>> g_levels;
+  for (size_t i = 0; i < nv; i++) h_levels.push_back(rd<G2Affine>(in, size_t(1) << (nv - i)));
+  for (size_t i = 0; i < nv; i++) g_levels.push_back(rd<G1Affine>(in, size_t(1) << (nv - i)));
+  std::ofstream out(fout, std::ios::binary);
+  auto p2 = multilinear_pc::open(h_levels, evals, point);
+  wr(out, p2.data(), p2.size());
+  auto p1 = multilinear_pc::open_g1(g_levels, evals, point);
+  wr(out, p1.data(), p1.size());
+  G2Affine c = msm_g2::msm_unchecked(h_levels[0], evals);
+  wr(out, &c, 1);
+  auto v = h_levels[0];
+  msm_g2::compress(v, v.size() / 2, point[0]);
+  wr(out, v.data(), v.size());
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 3) return 2;
   try {
     init(-1);
+    if (argc > 3 && std::string(argv[3]) == "g2") return run_g2(argv[1], argv[2]);
     std::ifstream in(argv[1], std::ios::binary);
     uint64_t nv;
     in.read((char*)&nv, 8);

@@ -109,3 +109,34 @@ def test_cpp_host_mirror_matches_reference_semantics(engine, driver, tmp_path, n
     assert h.pt_from_np(take_pts(1)[0]) == o.add(o.msm_naive(srs, z[: 1 << m_row]), o.mul(blind, hpt))
     assert take_u64() == (1 << m_row) - 1        # VariableBaseMSM::msm -> Err(min_len)
     assert take_u64() == 1                       # multiexponentiation -> Err(InvalidIPVectorLength)
+
+
+def test_cpp_host_mirror_g2_and_pst_openings(engine, driver, tmp_path):
+    """The C++ mirror's G2 MSM / compress and MultilinearPC::open / open_g1 wrappers against the big-integer oracles."""
+    from oracle import bls12_377_g2 as o2
+    from oracle import pst
+
+    nv = 4
+    t = o.rand_scalars(nv, 940)
+    evals = o.rand_scalars(1 << nv, 941)
+    point = o.rand_scalars(nv, 942)
+    exps = [pst.eq_exponents(t[k:]) for k in range(nv)]
+    h_lv = [[o2.mul(e, o2.G2) for e in lv] for lv in exps]
+    g_lv = [[o.mul(e, o.G) for e in lv] for lv in exps]
+    g2np = lambda pts: np.array([o2.affine_to_words(p) for p in pts], dtype=np.uint64)
+    blob = struct.pack("<Q", nv) + h.scalars_to_np(evals, mont=True).tobytes() + h.scalars_to_np(point, mont=True).tobytes()
+    blob += b"".join(g2np(lv).tobytes() for lv in h_lv) + b"".join(h.pts_to_np(lv).tobytes() for lv in g_lv)
+    fin, fout = tmp_path / "in2.bin", tmp_path / "out2.bin"
+    fin.write_bytes(blob)
+    subprocess.check_call([driver, str(fin), str(fout), "g2"])
+    data = np.frombuffer(fout.read_bytes(), dtype=np.uint64)
+    p2 = data[: 24 * nv].reshape(nv, 24)
+    p1 = data[24 * nv: 36 * nv].reshape(nv, 12)
+    rest = data[36 * nv:]
+    assert [o2.affine_from_words(r) for r in p2] == pst.open_proofs(evals, point, h_lv, o2.msm_naive)
+    assert [h.pt_from_np(r) for r in p1] == pst.open_proofs(evals, point, g_lv, o.msm_naive)
+    assert o2.affine_from_words(rest[:24]) == o2.msm_naive(h_lv[0], evals)
+    split = (1 << nv) // 2
+    comp = rest[24:].reshape(split, 24)
+    assert [o2.affine_from_words(r) for r in comp] == [o2.add(h_lv[0][i], o2.mul(point[0], h_lv[0][split + i]))
+                                                       for i in range(split)]

@@ -35,7 +35,11 @@ struct G1Affine {  // x[6] || y[6] Montgomery limbs; all-zero == identity
   }
   bool operator==(const G1Affine& o) const { return std::memcmp(w, o.w, 96) == 0; }
 };
-static_assert(sizeof(Fr) == 32 && sizeof(G1Affine) == 96, "ABI layouts");
+struct G2Affine {  // x.c0[6] || x.c1[6] || y.c0[6] || y.c1[6] Montgomery limbs (Fq2 = Fq[u]/(u^2+5)); all-zero == identity
+  uint64_t w[24];
+  bool operator==(const G2Affine& o) const { return std::memcmp(w, o.w, 192) == 0; }
+};
+static_assert(sizeof(Fr) == 32 && sizeof(G1Affine) == 96 && sizeof(G2Affine) == 192, "ABI layouts");
 
 struct EngineError : std::runtime_error {  // a CUDA failure has no error channel in commit/open: it unwinds
   int code;
@@ -307,5 +311,54 @@ inline std::vector<G1Affine> commit_inner(const std::vector<Fr>& Z, size_t L_siz
   return out;
 }
 }  // namespace commitments
+
+// ---- ark-ec VariableBaseMSM for G2Projective (commit_g2, src/mipp.rs:133) ----------------------------------------------
+namespace msm_g2 {
+inline G2Affine msm_unchecked(const std::vector<G2Affine>& bases, const std::vector<Fr>& scalars) {
+  G2Affine out;
+  check(tb200_msm_g2((const uint64_t*)bases.data(), (const uint64_t*)scalars.data(),
+                     std::min(bases.size(), scalars.size()), TB200_SCALARS_MONT, out.w));
+  return out;
+}
+// MIPP `compress` on the G2 key (src/mipp.rs:114, 354-367): vec[i] += scaler * vec[split + i], truncated to split
+inline void compress(std::vector<G2Affine>& vec, size_t split, const Fr& scaler) {
+  if (vec.size() < 2 * split) throw std::invalid_argument("compress: vector shorter than 2 * split");
+  check(tb200_compress_g2((uint64_t*)vec.data(), split, scaler.l, TB200_SCALARS_MONT));
+  vec.resize(split);
+}
+}  // namespace msm_g2
+
+// ---- ark-poly-commit multilinear_pc::MultilinearPC::{open, open_g1} (src/sqrt_pst.rs:225, src/mipp.rs:144) -----------
+namespace multilinear_pc {
+// level_bases[i] = ck.powers_of_h[off + i] (2^(nv - i) points); evals = poly.to_evaluations(); point has nv entries
+inline std::vector<G2Affine> open(const std::vector<std::vector<G2Affine>>& level_bases, const std::vector<Fr>& evals,
+                                  const std::vector<Fr>& point) {
+  const size_t nv = point.size();
+  if (evals.size() != (size_t(1) << nv) || level_bases.size() < nv) throw std::invalid_argument("open: sizes");
+  std::vector<const uint64_t*> ptrs(nv);
+  for (size_t i = 0; i < nv; i++) {
+    if (level_bases[i].size() != (size_t(1) << (nv - i))) throw std::invalid_argument("open: CRS level size");
+    ptrs[i] = (const uint64_t*)level_bases[i].data();
+  }
+  std::vector<G2Affine> proofs(nv);
+  check(tb200_pst_open_g2((const uint64_t*)evals.data(), nv, (const uint64_t*)point.data(), ptrs.data(),
+                          TB200_SCALARS_MONT, (uint64_t*)proofs.data()));
+  return proofs;
+}
+inline std::vector<G1Affine> open_g1(const std::vector<std::vector<G1Affine>>& level_bases, const std::vector<Fr>& evals,
+                                     const std::vector<Fr>& point) {
+  const size_t nv = point.size();
+  if (evals.size() != (size_t(1) << nv) || level_bases.size() < nv) throw std::invalid_argument("open_g1: sizes");
+  std::vector<const uint64_t*> ptrs(nv);
+  for (size_t i = 0; i < nv; i++) {
+    if (level_bases[i].size() != (size_t(1) << (nv - i))) throw std::invalid_argument("open_g1: CRS level size");
+    ptrs[i] = (const uint64_t*)level_bases[i].data();
+  }
+  std::vector<G1Affine> proofs(nv);
+  check(tb200_pst_open_g1((const uint64_t*)evals.data(), nv, (const uint64_t*)point.data(), ptrs.data(),
+                          TB200_SCALARS_MONT, (uint64_t*)proofs.data()));
+  return proofs;
+}
+}  // namespace multilinear_pc
 
 }  // namespace testudo_b200
