@@ -5,6 +5,7 @@
 #include "../../testudo_b200/csrc/digits.cuh"
 #include "../../testudo_b200/csrc/mont_kara.cuh"
 #include "../../testudo_b200/csrc/g2.cuh"
+#include "../../testudo_b200/csrc/fq12.cuh"
 using namespace tb;
 extern "C" {
 void hc_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul<FqParams>(r, a, b); }
@@ -135,4 +136,26 @@ int hc_digits(const uint32_t* s, int c, int32_t* out) {
   for (int w = 0; w < W; w++) out[w] = it.next(w == W - 1);
   return W;
 }
+// ---- Fq12 tower / pairing (fq12.cuh): 144 u32 per Fq12 in ark's in-memory order -------------------------------------
+void hc_fq12_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) {
+  Fq12 x, y; memcpy(&x, a, 576); memcpy(&y, b, 576); fq12_mul(x, x, y); memcpy(r, &x, 576);
+}
+void hc_fq12_sqr(const uint32_t* a, uint32_t* r) { Fq12 x; memcpy(&x, a, 576); fq12_sqr(x, x); memcpy(r, &x, 576); }
+void hc_fq12_inv(const uint32_t* a, uint32_t* r) { Fq12 x; memcpy(&x, a, 576); fq12_inv(x, x); memcpy(r, &x, 576); }
+void hc_fq12_frobenius(const uint32_t* a, int k, uint32_t* r) {
+  Fq12 x; memcpy(&x, a, 576); fq12_frobenius(x, x, k); memcpy(r, &x, 576);
+}
+void hc_fq12_cyclotomic_sqr(const uint32_t* a, uint32_t* r) {
+  Fq12 x; memcpy(&x, a, 576); fq12_cyclotomic_sqr_ol(&x, &x); memcpy(r, &x, 576);
+}
+void hc_fq12_mul_by_034(const uint32_t* a, const uint32_t* l0, const uint32_t* l3, const uint32_t* l4, uint32_t* r) {
+  Fq12 x; Fq2 c0, c3, c4; memcpy(&x, a, 576); memcpy(&c0, l0, 96); memcpy(&c3, l3, 96); memcpy(&c4, l4, 96);
+  fq12_mul_by_034_ol(&x, &c0, &c3, &c4); memcpy(r, &x, 576);
+}
+void hc_fq12_exp_by_x(const uint32_t* a, uint32_t* r) { Fq12 x; memcpy(&x, a, 576); fq12_exp_by_x(x, x); memcpy(r, &x, 576); }
+void hc_miller_loop(const uint32_t* p_aff, const uint32_t* q_aff, uint32_t* r) {
+  Affine p; Affine2 q; Fq12 f; memcpy(&p, p_aff, 96); memcpy(&q, q_aff, 192);
+  miller_loop(f, p, q); memcpy(r, &f, 576);
+}
+void hc_final_exp(const uint32_t* a, uint32_t* r) { Fq12 x, y; memcpy(&x, a, 576); fq12_final_exp(y, x); memcpy(r, &y, 576); }
 }
