@@ -187,6 +187,26 @@ int tb200_test_g1_add(const uint64_t* p_xy, const uint64_t* q_xy, size_t n, uint
 int tb200_test_g1_mul(const uint64_t* p_xy, const uint64_t* k, size_t n, uint64_t* out_xy);    /* k canonical */
 int tb200_test_g2_add(const uint64_t* p, const uint64_t* q, size_t n, uint64_t* out);           /* 24 u64 each */
 int tb200_test_g2_mul(const uint64_t* p, const uint64_t* k, size_t n, uint64_t* out);           /* k canonical */
+/* one Fq12 operation per element (see kernels_pairing.cuh k_test_fq12_op for the op codes); a, b, out: n x 72 u64 */
+int tb200_test_fq12_op(int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
+
+/* ---- pairing products ---------------------------------------------------------------
+ * GT element = Fq12 = 72 x u64: twelve Fq (6 LE limbs, Montgomery form) in ark's in-memory tower order
+ * c0.c0.c0, c0.c0.c1, c0.c1.c0, ... c1.c2.c1 (Fq12 = Fq6[w]/(w^2 - v), Fq6 = Fq2[v]/(v^3 - u), Fq2 = Fq[u]/(u^2 + 5)).
+ * tb200_multi_pairing replaces `E::multi_pairing(g1s, g2s).0` (ark-ec 0.4 `Bls12`: Miller loops, product, one final
+ * exponentiation with ark's exponent 3 (q^12 - 1)/r-equivalent chain) at src/sqrt_pst.rs:131-144 (`t`) and
+ * `pairings_product`, src/mipp.rs:396-398. Pairs with an identity on either side contribute 1, as in ark; n == 0
+ * yields 1. */
+int tb200_multi_pairing(const uint64_t* g1_xy, const uint64_t* g2, size_t n, uint64_t out[72]);
+/* Same with DEVICE pointers; d_out receives 576 bytes; returns after enqueueing on `stream` (NULL = library stream). */
+int tb200_multi_pairing_dev(const void* d_g1_xy, const void* d_g2, size_t n, void* d_out, void* stream);
+/* The two cross pairing products of a MIPP round over the device-resident vectors (src/mipp.rs:87-94):
+ * comm_t_l = prod_i e(a[i], h[split + i]), comm_t_r = prod_i e(a[split + i], h[i]), split = len / 2.
+ * Both handles must have the same current length (>= 2). Waits for the G2 folds enqueued so far. */
+int tb200_mipp_pairing_cross(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_t_l[72], uint64_t comm_t_r[72]);
+/* out[i] = base[i] ^ exps[i] in GT (the verifier's `tx.pow(c)`, src/mipp.rs:252-255); exponents are Fr values
+ * (canonical, or Montgomery with TB200_SCALARS_MONT). */
+int tb200_gt_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned flags, uint64_t* out);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,93 @@
+#include <cstdio>
+#include <cstring>
+#include "../../testudo_b200/csrc/kernels_pairing.cuh"
+using namespace tb;
+__global__ void __launch_bounds__(32) k_a(const uint4* a, uint4* out, int stop) {
+  Fq12 x, r;
+  load_fq12(x, a);
+  fq12_final_exp(r, x, stop);
+  store_fq12(out, r);
+}
+__global__ void k_b(const uint4* a, uint4* out, int stop) {
+  if (threadIdx.x != 0) return;
+  Fq12 x, r;
+  load_fq12(x, a);
+  fq12_final_exp(r, x, stop);
+  store_fq12(out, r);
+}
+__global__ void k_c(const uint4* __restrict__ a, uint4* __restrict__ out, int stop) {
+  Fq12 x, r;
+  load_fq12(x, a);
+  fq12_final_exp(r, x, stop);
+  store_fq12(out, r);
+}
+__global__ void k_d(const uint4* a, uint4* out, int stop) {
+  Fq12 x, r;
+  load_fq12(x, a + 36 * (size_t)blockIdx.x);
+  fq12_final_exp(r, x, stop);
+  store_fq12(out + 36 * (size_t)blockIdx.x, r);
+}
+__global__ void k_e(const uint4* a, uint4* out) {
+  Fq12 x, r;
+  load_fq12(x, a);
+  fq12_final_exp(r, x);
+  store_fq12(out, r);
+}
+__global__ void k_f(const uint4* a, uint4* out) {
+  Fq12 x, r;
+  load_fq12(x, a);
+  fq12_final_exp(r, x, 13);
+  store_fq12(out, r);
+}
+__global__ void k_g(const uint4* a, uint4* out) {
+  Fq12 x, r;
+  load_fq12(x, a);
+  fq12_final_exp(r, x, 9);
+  store_fq12(out, r);
+}
+__global__ void k_h(const uint4* a, uint4* out) {
+  Fq12 x, r;
+  load_fq12(x, a);
+  fq12_final_exp(r, x, 5);
+  store_fq12(out, r);
+}
+int cmp(const char* name, const uint32_t* o, const uint32_t* ho) {
+  int bad = 0, first = -1;
+  for (int i = 0; i < 144; i++) if (o[i] != ho[i]) { bad++; if (first < 0) first = i; }
+  printf("%s mismatches=%d first=%d err=%s\n", name, bad, first, cudaGetErrorString(cudaGetLastError()));
+  return bad;
+}
+template <class K> void attr(const char* n, K k) {
+  cudaFuncAttributes a; cudaFuncGetAttributes(&a, k);
+  printf("%s: local=%zu regs=%d\n", n, a.localSizeBytes, a.numRegs);
+}
+int main() {
+  uint32_t h[144], o[144], ho[144];
+  for (int i = 0; i < 144; i++) h[i] = (i % 12 == 11) ? 0x00123456u : 0x9e3779b9u * (i + 1);
+  uint4 *da, *dr;
+  cudaMalloc(&da, 576); cudaMalloc(&dr, 576);
+  cudaMemcpy(da, h, 576, cudaMemcpyHostToDevice);
+  Fq12 x, y; memcpy(&x, h, 576);
+  fq12_final_exp(y, x, 1000); memcpy(ho, &y, 576);
+  attr("k_a", k_a); attr("k_b", k_b); attr("k_c", k_c); attr("k_d", k_d); attr("k_final_exp", k_final_exp);
+  size_t lim; cudaDeviceGetLimit(&lim, cudaLimitStackSize); printf("stack limit %zu\n", lim);
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) { cudaDeviceSetLimit(cudaLimitStackSize, 65536); printf("-- stack limit raised\n"); }
+    cudaMemset(dr, 0, 576); k_a<<<1, 1>>>(da, dr, 1000); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_a<<<1,1>>>", o, ho);
+    cudaMemset(dr, 0, 576); k_b<<<1, 32>>>(da, dr, 1000); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_b<<<1,32>>>", o, ho);
+    cudaMemset(dr, 0, 576); k_b<<<1, 1>>>(da, dr, 1000); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_b<<<1,1>>>", o, ho);
+    cudaMemset(dr, 0, 576); k_c<<<1, 1>>>(da, dr, 1000); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_c<<<1,1>>>", o, ho);
+    cudaMemset(dr, 0, 576); k_d<<<1, 1>>>(da, dr, 1000); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_d<<<1,1>>>", o, ho);
+    cudaMemset(dr, 0, 576); k_final_exp<<<1, 32>>>(da, dr); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_final_exp<<<1,32>>>", o, ho);
+    cudaMemset(dr, 0, 576); k_final_exp<<<1, 1>>>(da, dr); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_final_exp<<<1,1>>>", o, ho);
+  }
+  k_e<<<1, 1>>>(da, dr); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_e const stop", o, ho);
+  int st[3] = {13, 9, 5};
+  for (int q = 0; q < 3; q++) {
+    fq12_final_exp(y, x, st[q]); memcpy(ho, &y, 576);
+    if (q == 0) k_f<<<1, 1>>>(da, dr); else if (q == 1) k_g<<<1, 1>>>(da, dr); else k_h<<<1, 1>>>(da, dr);
+    cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost);
+    char nm[32]; snprintf(nm, 32, "const stop=%d", st[q]); cmp(nm, o, ho);
+  }
+  return 0;
+}

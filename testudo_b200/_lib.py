@@ -52,6 +52,10 @@ SIGNATURES = {
     "tb200_mipp_g2_fold": (c_int, [c_void_p, c_void_p]),
     "tb200_mipp_g2_read": (c_int, [c_void_p, c_void_p]),
     "tb200_mipp_g2_end": (c_int, [c_void_p]),
+    "tb200_multi_pairing": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tb200_multi_pairing_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "tb200_mipp_pairing_cross": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "tb200_gt_pow": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
     "tb200_pst_open_g1": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_uint, c_void_p]),
     "tb200_pst_open_g2": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_uint, c_void_p]),
     "tb200_dev_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
@@ -77,6 +81,7 @@ SIGNATURES = {
     "tb200_test_g1_add": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "tb200_test_g1_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "tb200_test_g2_add": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tb200_test_fq12_op": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tb200_test_g2_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libtestudo_b200.so")
 SOURCES = ["capi.cu"]
-HEADERS = ["mont.cuh", "g1.cuh", "g1_fast.cuh", "digits.cuh", "kernels.cuh", "kernels_affine.cuh", "kernels_smem.cuh", "mont_kara.cuh", "g2.cuh", "kernels_g2.cuh", os.path.join("..", "..", "include", "testudo_b200.h")]
+HEADERS = ["mont.cuh", "g1.cuh", "g1_fast.cuh", "digits.cuh", "kernels.cuh", "kernels_affine.cuh", "kernels_smem.cuh", "mont_kara.cuh", "g2.cuh", "kernels_g2.cuh", "fq12.cuh", "fq12_consts.inc", "kernels_pairing.cuh", os.path.join("..", "..", "include", "testudo_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -16,6 +16,7 @@
 #include "../../include/testudo_b200.h"
 #include "kernels_affine.cuh"
 #include "kernels_g2.cuh"
+#include "kernels_pairing.cuh"
 #include "kernels_smem.cuh"
 
 using namespace tb;
@@ -1191,6 +1192,120 @@ int tb200_mipp_g2_end(tb200_mipp_g2_t h) {
   return 0;
 }
 
+// ---- pairing products -----------------------------------------------------------------------------------------------
+// Miller values of `n` pairs (g2 index = j ^ xor_mask) -> `segs` products (segment s = pairs [s n/segs, (s+1) n/segs))
+// -> final exponentiation of each, written to d_out (segs x 576 B). Everything is enqueued on `st`; the scratch is
+// stream-ordered. `after_miller`, if given, is recorded once the Miller kernel (the only reader of g1 / g2) is enqueued.
+static int pairing_products_locked(const uint4* d_g1, const uint4* d_g2, uint32_t n, uint32_t xor_mask, uint32_t segs,
+                                   uint4* d_out, cudaStream_t st, cudaEvent_t after_miller) {
+  if (n == 0) {
+    LAUNCH(k_fq12_set_one, 1, 32, st, d_out, segs);
+    return 0;
+  }
+  uint32_t len = n / segs;
+  uint4 *buf_a = nullptr, *buf_b = nullptr;
+  CU(cudaMallocAsync((void**)&buf_a, (size_t)n * 576, st));
+  CU(cudaMallocAsync((void**)&buf_b, (size_t)segs * cdiv(len, FQ12_FAN) * 576 + 576, st));
+  LAUNCH(k_miller, cdiv(n, 32), 32, st, d_g1, d_g2, n, xor_mask, buf_a);
+  if (after_miller) CU(cudaEventRecord(after_miller, st));
+  uint4 *cur = buf_a, *nxt = buf_b;
+  while (len > 1) {
+    const uint32_t m = cdiv(len, FQ12_FAN);
+    LAUNCH(k_fq12_prod_level, dim3(cdiv(m, 32), segs), 32, st, cur, len, m, nxt);
+    std::swap(cur, nxt);
+    len = m;
+  }
+  LAUNCH(k_final_exp, segs, 32, st, cur, d_out);
+  CU(cudaFreeAsync(buf_a, st));
+  CU(cudaFreeAsync(buf_b, st));
+  return 0;
+}
+
+int tb200_multi_pairing_dev(const void* d_g1_xy, const void* d_g2, size_t n, void* d_out, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_out || (n && (!d_g1_xy || !d_g2))) return fail(TB200_E_ARG, "null pointer");
+  if (n >= (1u << 26)) return fail(TB200_E_LIMIT, "too many pairs");
+  CU(cudaSetDevice(g.device));
+  return pairing_products_locked((const uint4*)d_g1_xy, (const uint4*)d_g2, (uint32_t)n, 0, 1, (uint4*)d_out,
+                                 stream ? (cudaStream_t)stream : g.stream, nullptr);
+}
+
+int tb200_multi_pairing(const uint64_t* g1_xy, const uint64_t* g2, size_t n, uint64_t out[72]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || (n && (!g1_xy || !g2))) return fail(TB200_E_ARG, "null pointer");
+  if (n >= (1u << 26)) return fail(TB200_E_LIMIT, "too many pairs");
+  CU(cudaSetDevice(g.device));
+  uint4 *d_p = nullptr, *d_q = nullptr, *d_o = nullptr;
+  CU(cudaMallocAsync((void**)&d_o, 576, g.stream));
+  if (n) {
+    CU(cudaMallocAsync((void**)&d_p, n * 96, g.stream));
+    CU(cudaMallocAsync((void**)&d_q, n * 192, g.stream));
+    CU(cudaMemcpyAsync(d_p, g1_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(d_q, g2, n * 192, cudaMemcpyHostToDevice, g.stream));
+  }
+  int rc = pairing_products_locked(d_p, d_q, (uint32_t)n, 0, 1, d_o, g.stream, nullptr);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out, d_o, 576, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "pairing result copy failed: %s", cudaGetErrorString(e));
+  }
+  if (d_p) cudaFreeAsync(d_p, g.stream);
+  if (d_q) cudaFreeAsync(d_q, g.stream);
+  cudaFreeAsync(d_o, g.stream);
+  return rc;
+}
+
+int tb200_mipp_pairing_cross(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_t_l[72], uint64_t comm_t_r[72]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!a || !h || !comm_t_l || !comm_t_r) return fail(TB200_E_ARG, "null pointer");
+  if (a->n != h->n) return fail(TB200_E_ARG, "MIPP vectors differ in length (%u vs %u)", a->n, h->n);
+  if (a->n < 2) return fail(TB200_E_STATE, "MIPP vectors are already folded to length 1");
+  CU(cudaSetDevice(g.device));
+  const uint32_t n = a->n, split = n / 2;
+  // the G2 key is folded on its own stream: wait for the folds enqueued so far, and make later folds (which rewrite h
+  // in place) wait for this round's Miller kernel
+  CU(cudaEventRecord(g.ev_join, h->st));
+  CU(cudaStreamWaitEvent(g.stream, g.ev_join, 0));
+  uint4* d_o = nullptr;
+  CU(cudaMallocAsync((void**)&d_o, 2 * 576, g.stream));
+  int rc = pairing_products_locked(a->a, h->h, n, split, 2, d_o, g.stream, g.ev_join);
+  if (rc == 0) {
+    cudaError_t e = cudaStreamWaitEvent(h->st, g.ev_join, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(comm_t_l, d_o, 576, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(comm_t_r, d_o + 36, 576, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "pairing result copy failed: %s", cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d_o, g.stream);
+  return rc;
+}
+
+int tb200_gt_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned flags, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (n == 0) return 0;
+  if (!bases || !exps || !out) return fail(TB200_E_ARG, "null pointer");
+  if (n >= (1u << 22)) return fail(TB200_E_LIMIT, "too many elements");
+  CU(cudaSetDevice(g.device));
+  uint4 *d_b = nullptr, *d_o = nullptr;
+  uint32_t* d_e = nullptr;
+  CU(cudaMallocAsync((void**)&d_b, n * 576, g.stream));
+  CU(cudaMallocAsync((void**)&d_o, n * 576, g.stream));
+  CU(cudaMallocAsync((void**)&d_e, n * 32, g.stream));
+  CU(cudaMemcpyAsync(d_b, bases, n * 576, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(d_e, exps, n * 32, cudaMemcpyHostToDevice, g.stream));
+  LAUNCH(k_fq12_pow, cdiv(n, 32), 32, g.stream, d_b, d_e, (uint32_t)n, (flags & TB200_SCALARS_MONT) ? 1 : 0, d_o);
+  CU(cudaMemcpyAsync(out, d_o, n * 576, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  cudaFreeAsync(d_b, g.stream);
+  cudaFreeAsync(d_o, g.stream);
+  cudaFreeAsync(d_e, g.stream);
+  return 0;
+}
+
 int tb200_compress_g1(uint64_t* vec_xy, size_t split, const uint64_t scaler[4], unsigned flags) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (need_ready()) return TB200_E_STATE;
@@ -1475,6 +1590,17 @@ int tb200_test_g1_mul(const uint64_t* p_xy, const uint64_t* k, size_t n, uint64_
                                (uint32_t)n, (uint4*)d1);
                         return 0;
                       });
+}
+
+int tb200_test_fq12_op(int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!a || !b || !out || n == 0 || op < 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(g.device));
+  return with_buffers(a, n * 576, b, n * 576, out, n * 576, nullptr, 0, [&](char* da, char* db, char* d1, char*) {
+    LAUNCH(k_test_fq12_op, cdiv(n, 32), 32, g.stream, op, (const uint4*)da, (const uint4*)db, (uint32_t)n, (uint4*)d1);
+    return 0;
+  });
 }
 
 }  // extern "C"

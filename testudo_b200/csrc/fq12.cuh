@@ -224,7 +224,9 @@ TB_HD void fq12_conj(Fq12& r, const Fq12& a) {
   r.c0 = a.c0;
   fq6_neg(r.c1, a.c1);
 }
-TB_HD void fq12_inv(Fq12& r, const Fq12& a) {
+TB_G2_OL void fq12_inv_ol(Fq12* rp, const Fq12* ap) {
+  Fq12& r = *rp;
+  const Fq12& a = *ap;
   Fq6 t, s;
   fq6_mul(t, a.c0, a.c0);
   fq6_mul(s, a.c1, a.c1);
@@ -235,6 +237,7 @@ TB_HD void fq12_inv(Fq12& r, const Fq12& a) {
   fq6_mul(s, a.c1, t);
   fq6_neg(r.c1, s);
 }
+TB_HD void fq12_inv(Fq12& r, const Fq12& a) { fq12_inv_ol(&r, &a); }
 // coefficient of w^i (i = 0..5) inside the tower layout
 TB_HD Fq2& fq12_coeff(Fq12& a, int i) {
   Fq6& h = (i & 1) ? a.c1 : a.c0;
@@ -242,8 +245,8 @@ TB_HD Fq2& fq12_coeff(Fq12& a, int i) {
   return j == 0 ? h.c0 : (j == 1 ? h.c1 : h.c2);
 }
 // a^(q^k), k = 1 or 2: coefficient of w^i -> conj^k(.) * u^(i (q^k - 1)/6)
-TB_HD void fq12_frobenius(Fq12& r, const Fq12& a, int k) {
-  r = a;
+TB_G2_OL void fq12_frobenius_ol(Fq12* rp, const Fq12* ap, int k) {
+  Fq12 r = *ap;
   for (int i = 0; i < 6; i++) {
     Fq2& c = fq12_coeff(r, i);
     if (k == 1) fq2_conj(c, c);
@@ -258,7 +261,9 @@ TB_HD void fq12_frobenius(Fq12& r, const Fq12& a, int k) {
       fq2_scale(c, c, g);
     }
   }
+  *rp = r;
 }
+TB_HD void fq12_frobenius(Fq12& r, const Fq12& a, int k) { fq12_frobenius_ol(&r, &a, k); }
 // a * ((l0, 0, 0) + (l3, l4, 0) w): the line of a D-type twist (ark `mul_by_034`), 13 Fq2 products
 TB_G2_OL void fq12_mul_by_034_ol(Fq12* ap, const Fq2* l0p, const Fq2* l3p, const Fq2* l4p) {
   Fq12& a = *ap;
@@ -342,33 +347,51 @@ TB_G2_OL void fq12_cyclotomic_sqr_ol(Fq12* rp, const Fq12* ap) {
 constexpr uint64_t BLS_X = 0x8508c00000000001ull;  // ark-bls12-377 Config::X (positive)
 
 // a^x for a unitary a (ark `exp_by_x` = cyclotomic_exp, X_IS_NEGATIVE = false)
-TB_HD void fq12_exp_by_x(Fq12& r, const Fq12& a) {
+TB_G2_OL void fq12_exp_by_x_ol(Fq12* rp, const Fq12* ap) {
+  const Fq12 a = *ap;
   Fq12 acc = a;
   for (int bit = 62; bit >= 0; bit--) {
     fq12_cyclotomic_sqr_ol(&acc, &acc);
-    if ((BLS_X >> bit) & 1) fq12_mul(acc, acc, a);
+    if ((BLS_X >> bit) & 1) fq12_mul_ol(&acc, &acc, &a);
   }
-  r = acc;
+  *rp = acc;
 }
+TB_HD void fq12_exp_by_x(Fq12& r, const Fq12& a) { fq12_exp_by_x_ol(&r, &a); }
 
 // ark `Bls12::final_exponentiation`, step for step
-TB_HD void fq12_final_exp(Fq12& out, const Fq12& f) {
+TB_G2_OL void fq12_final_exp_ol(Fq12* outp, const Fq12* fp, int stop) {
+  Fq12& out = *outp;
+  const Fq12 f = *fp;
   Fq12 r, f2, y0, y1, y2;
+  int step = 0;
+#define TB_FE_STEP(x) if (++step == stop) { out = x; return; }
   fq12_conj(r, f);
+  TB_FE_STEP(r)                // 1
   fq12_inv(f2, f);
+  TB_FE_STEP(f2)               // 2
   fq12_mul(r, r, f2);          // f^(q^6 - 1)
+  TB_FE_STEP(r)                // 3
   f2 = r;
   fq12_frobenius(r, r, 2);
+  TB_FE_STEP(r)                // 4
   fq12_mul(r, r, f2);          // f^((q^6 - 1)(q^2 + 1))
+  TB_FE_STEP(r)                // 5
   fq12_cyclotomic_sqr_ol(&y0, &r);
+  TB_FE_STEP(y0)               // 6
   fq12_exp_by_x(y1, r);
+  TB_FE_STEP(y1)               // 7
   fq12_conj(y2, r);
   fq12_mul(y1, y1, y2);
+  TB_FE_STEP(y1)               // 8
   fq12_exp_by_x(y2, y1);
+  TB_FE_STEP(y2)               // 9
   fq12_conj(y1, y1);
+  TB_FE_STEP(y1)               // 10
   fq12_mul(y1, y1, y2);
+  TB_FE_STEP(y1)               // 11
   fq12_exp_by_x(y2, y1);
   fq12_frobenius(y1, y1, 1);
+  TB_FE_STEP(y1)               // 12
   fq12_mul(y1, y1, y2);
   fq12_mul(r, r, y0);
   fq12_exp_by_x(y0, y1);
@@ -378,7 +401,10 @@ TB_HD void fq12_final_exp(Fq12& out, const Fq12& f) {
   fq12_mul(y1, y1, y2);
   fq12_mul(y1, y1, y0);
   fq12_mul(out, r, y1);
+#undef TB_FE_STEP
 }
+// `stop` < 1000 returns the value after that many steps of the chain (test hook: tests/test_gpu_pairing.py)
+TB_HD void fq12_final_exp(Fq12& out, const Fq12& f, int stop = 1000) { fq12_final_exp_ol(&out, &f, stop); }
 
 // ---- Miller loop ---------------------------------------------------------------------------------------------
 struct G2Hom {  // homogeneous projective point on the twist (ark `G2HomProjective`)
@@ -467,9 +493,14 @@ TB_HD void miller_add_step(Fq12& f, G2Hom& r, const Affine2& q, const Fq& px, co
 
 // f_{x,Q}(P) (up to factors the final exponentiation removes); 1 if either point is the identity, as
 // ark's multi_miller_loop skips such pairs
-TB_HD void miller_loop(Fq12& f, const Affine& p, const Affine2& q) {
-  f = fq12_one();
-  if (affine_is_inf(p) || affine2_is_inf(q)) return;
+TB_G2_OL void miller_loop_ol(Fq12* fp, const Affine* pp, const Affine2* qp) {
+  const Affine p = *pp;
+  const Affine2 q = *qp;
+  Fq12 f = fq12_one();
+  if (affine_is_inf(p) || affine2_is_inf(q)) {
+    *fp = f;
+    return;
+  }
   G2Hom r;
   r.x = q.x;
   r.y = q.y;
@@ -479,6 +510,8 @@ TB_HD void miller_loop(Fq12& f, const Affine& p, const Affine2& q) {
     miller_double_step(f, r, p.x, p.y);
     if ((BLS_X >> bit) & 1) miller_add_step(f, r, q, p.x, p.y);
   }
+  *fp = f;
 }
+TB_HD void miller_loop(Fq12& f, const Affine& p, const Affine2& q) { miller_loop_ol(&f, &p, &q); }
 
 }  // namespace tb

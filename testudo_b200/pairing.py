@@ -1,0 +1,56 @@
+"""Mirror of the pairing calls on the reference's commitment path, ark-ec 0.4 `Pairing` for
+`ark_bls12_377::Bls12_377`:
+
+    E::multi_pairing(g1s, g2s).0      src/sqrt_pst.rs:143 (the IPP commitment t), src/mipp.rs:396-398 (pairings_product)
+    E::pairing(p, q).0                src/mipp.rs:320 (verifier)
+    TargetField::pow(bigint)          src/mipp.rs:252-255 (verifier)
+
+Values are numpy uint64 arrays in ark's in-memory layout: G1 affine [12], G2 affine [24], GT = Fq12 [72] (tower order
+c0.c0.c0 ... c1.c2.c1, Montgomery limbs). Everything runs on the GPU (tb200_multi_pairing / tb200_gt_pow); there is no
+CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+GT_WORDS = 72
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def multi_pairing(g1s, g2s) -> np.ndarray:
+    """`E::multi_pairing(a, b).0`. ark zips the two iterators (the shorter one bounds the product) and skips pairs with
+    an identity on either side."""
+    p = np.ascontiguousarray(g1s, dtype=np.uint64).reshape(-1, 12)
+    q = np.ascontiguousarray(g2s, dtype=np.uint64).reshape(-1, 24)
+    n = min(len(p), len(q))
+    out = np.zeros(GT_WORDS, dtype=np.uint64)
+    _lib.check(_lib.engine().tb200_multi_pairing(_ptr(p), _ptr(q), n, _ptr(out)))
+    return out
+
+
+def pairings_product(gs, hs) -> np.ndarray:
+    """src/mipp.rs:396-398."""
+    return multi_pairing(gs, hs)
+
+
+def pairing(p, q) -> np.ndarray:
+    """`E::pairing(p, q).0`."""
+    return multi_pairing(np.asarray(p).reshape(1, 12), np.asarray(q).reshape(1, 24))
+
+
+def gt_pow(bases, exps, mont: bool = False) -> np.ndarray:
+    """Element-wise `base.pow(exp)` in GT; exponents are Fr limbs (canonical `BigInt<4>` by default)."""
+    b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, GT_WORDS)
+    e = np.ascontiguousarray(exps, dtype=np.uint64).reshape(-1, 4)
+    if len(b) != len(e):
+        raise ValueError("bases and exponents differ in length")
+    out = np.zeros_like(b)
+    _lib.check(_lib.engine().tb200_gt_pow(_ptr(b), _ptr(e), len(b), _lib.SCALARS_MONT if mont else 0, _ptr(out)))
+    return out
