@@ -221,3 +221,80 @@ def test_open_with_full_crs_g2_proof_and_mipp_open_g1(engine, nv):
     dlh = [pst.mle_eval(qi, t[odd + i + 1:]) for i, qi in enumerate(pst.quotients(ph, mp.rs))]
     assert [h.pt_from_np(p) for p in mp.pst_proof_h] == [o.mul(d, o.G) for d in dlh]
     ck.close()
+
+
+def _neutral(values):
+    """Encodes what is appended to the transcript as the C-ABI word arrays, for prover (numpy) and verifier (oracle)."""
+    from oracle import bls12_377_g2 as o2
+    from oracle import pairing as pr
+
+    out = []
+    for v in values:
+        if isinstance(v, tuple) and v and v[0] in ("g1", "g2", "gt"):
+            kind, val = v
+            words = o.affine_to_words(val) if kind == "g1" else (o2.affine_to_words(val) if kind == "g2" else pr.to_words(val))
+            out.append(np.array(words, dtype=np.uint64))
+        else:
+            out.append(np.asarray(v, dtype=np.uint64))
+    return out
+
+
+def shared_transcript():
+    inner = fake_transcript()
+    return lambda label, values: inner(label, _neutral(values))
+
+
+@pytest.mark.parametrize("nv", [5, 6])
+def test_check_sqrt_poly_commit_roundtrip_with_oracle_verifier(engine, nv):
+    """The reference's own test for this path, `check_sqrt_poly_commit(5)` / `(6)` (src/sqrt_pst.rs:297-342): setup,
+    commit (comm_list AND the pairing product t), open (U, PST proof, MIPP proof with comms_t), verify == true -- with
+    every prover value produced by the GPU path and the verifier being the independent big-integer restatement
+    (oracle/verifier.py). Tampered proofs must be rejected."""
+    from oracle import bls12_377_g2 as o2
+    from oracle import pairing as pr
+    from oracle import verifier as ver
+
+    m_col = nv // 2
+    m_row = nv - m_col
+    odd = nv % 2
+    t = o.rand_scalars(m_row, 1900 + nv)
+    g_levels = _crs_levels(engine, t, False)
+    h_levels = _crs_levels(engine, t, True)
+    vk = ver.setup_vk(t)
+    z = o.rand_scalars(1 << nv, 1910 + nv)
+    r = o.rand_scalars(nv, 1920 + nv)
+    poly = sqrt_pst.Polynomial.from_evaluations(h.scalars_to_np(z, mont=True))
+    v = poly.eval(r)
+    ck = sqrt_pst.CommitterKey.from_points(g_levels[0]).with_levels(g_levels, h_levels)
+    comm_list, t_gt = poly.commit(ck)
+    assert t_gt is not None
+    # t = prod e(C_i, h_i) against the oracle's pairing
+    h_vec = [o2.affine_from_words(w) for w in h_levels[odd]]
+    T = pr.from_words(t_gt)
+    assert T == pr.multi_pairing([h.pt_from_np(c) for c in comm_list], h_vec)
+    opened = poly.open(shared_transcript(), comm_list, ck, r, t_gt)
+    mp = opened.mipp
+    assert len(mp.comms_t) == m_col and len(mp.comms_u) == m_col
+
+    def proof_dict():
+        return {
+            "comms_u": [(h.pt_from_np(l), h.pt_from_np(rr)) for l, rr in mp.comms_u],
+            "comms_t": [(pr.from_words(l), pr.from_words(rr)) for l, rr in mp.comms_t],
+            "final_a": h.pt_from_np(mp.final_a),
+            "final_h": o2.affine_from_words(mp.final_h),
+            "pst_proof_h": [h.pt_from_np(p) for p in mp.pst_proof_h],
+        }
+
+    U = h.pt_from_np(opened.u)
+    pst_proof = [o2.affine_from_words(p) for p in opened.pst_proof]
+    assert ver.sqrt_pst_verify(vk, shared_transcript(), U, r, v, pst_proof, proof_dict(), T) is True
+    # negative cases: wrong value, tampered PST proof, tampered cross pairing product, wrong T
+    assert ver.sqrt_pst_verify(vk, shared_transcript(), U, r, (v + 1) % o.R_ORDER, pst_proof, proof_dict(), T) is False
+    bad = list(pst_proof)
+    bad[0] = o2.add(bad[0], o2.G2)
+    assert ver.sqrt_pst_verify(vk, shared_transcript(), U, r, v, bad, proof_dict(), T) is False
+    pd = proof_dict()
+    pd["comms_t"][0] = (pr.f12_mul(pd["comms_t"][0][0], T), pd["comms_t"][0][1])
+    assert ver.sqrt_pst_verify(vk, shared_transcript(), U, r, v, pst_proof, pd, T) is False
+    assert ver.sqrt_pst_verify(vk, shared_transcript(), U, r, v, pst_proof, proof_dict(), pr.f12_sqr(T)) is False
+    ck.close()

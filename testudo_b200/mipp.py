@@ -1,8 +1,9 @@
 """Mirror of the group work in `mipp.rs`: `multiexponentiation`, `compress`, and the prover loop of
 `MippProof::prove` (src/mipp.rs:31-153, 354-394), including -- when the G2 key `h` and the CRS levels are passed --
-the G2 `compress` of the commitment key (:114), the structured polynomial (:128-131, 159-180), `commit_g2` (:133) and
-the `open_g1` proof (:144). The GT work (pairing products `comms_t`) and the Poseidon transcript are out of scope
- -- challenges come from a callback.
+the G2 `compress` of the commitment key (:114), the cross pairing products `comms_t` (:87-94, SURVEY.md 8f rank 3:
+tb200_mipp_pairing_cross over the device-resident a and h), the structured polynomial (:128-131, 159-180), `commit_g2`
+(:133) and the `open_g1` proof (:144). The Poseidon transcript is out of scope -- challenges come
+from a callback that receives what the reference appends.
 
 The G1 vectors stay on the GPU across rounds (tb200_mipp_g1_*): upload once, two points back per round.
 """
@@ -47,6 +48,7 @@ def compress(vec, split: int, scaler_mont) -> np.ndarray:
 class MippProofG1:
     """G1 fields of `MippProof<E>` (src/mipp.rs:22-28): comms_u and final_a (+ the folded y for cross-checks)."""
     comms_u: List[Tuple[np.ndarray, np.ndarray]] = field(default_factory=list)
+    comms_t: List[Tuple[np.ndarray, np.ndarray]] = field(default_factory=list)   # GT pairs ([72] each), when `h` was passed
     final_a: np.ndarray = None
     final_y: np.ndarray = None
     xs: List[int] = field(default_factory=list)
@@ -58,8 +60,8 @@ class MippProofG1:
     @classmethod
     def prove(cls, challenge: Callable[[bytes, List[np.ndarray]], int], a, y_mont, U, h=None,
               powers_of_g_levels=None) -> "MippProofG1":
-        """src/mipp.rs:31-153 without the GT work. `challenge(label, points)` returns the squeezed scalar as an integer
-        mod r after the reference would have appended `points` (comm_u_l, comm_u_r; comm_t_l/r are GT and out of scope).
+        """src/mipp.rs:31-153. `challenge(label, values)` returns the squeezed scalar as an integer mod r after the
+        reference would have appended `values` (comm_u_l, comm_u_r, and -- when the G2 key is passed -- comm_t_l, comm_t_r).
         `h` = `ck.powers_of_h[odd]` ([n, 24]); `powers_of_g_levels[i]` = `ck.powers_of_g[off + i]` for `open_g1`."""
         lib = _lib.engine()
         a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 12)
@@ -82,7 +84,14 @@ class MippProofG1:
                 ul = np.zeros(12, dtype=np.uint64)
                 ur = np.zeros(12, dtype=np.uint64)
                 _lib.check(lib.tb200_mipp_g1_cross(h, _ptr(ul), _ptr(ur)))   # :77-85
-                c_inv = challenge(b"challenge_i", [ul, ur]) % fr.R       # :97-101
+                appended = [ul, ur]
+                if m_h is not None:                                      # pairings_product(a_l, h_r), (a_r, h_l), :87-94
+                    tl = np.zeros(72, dtype=np.uint64)
+                    tr = np.zeros(72, dtype=np.uint64)
+                    _lib.check(lib.tb200_mipp_pairing_cross(h, m_h, _ptr(tl), _ptr(tr)))
+                    out.comms_t.append((tl, tr))                         # :116
+                    appended += [tl, tr]
+                c_inv = challenge(b"challenge_i", appended) % fr.R       # :97-101
                 c = fr.inverse(c_inv)                                    # :106
                 cw = curve.scalars_to_words([c], mont=True)[0]
                 ciw = curve.scalars_to_words([c_inv], mont=True)[0]

@@ -12,8 +12,11 @@ What runs where:
     and the G1 part of `MippProof::prove` (:212) run on the GPU.
   * with the G2 side of the key (`powers_of_h`, `powers_of_g` levels) `open` also produces the PST proof
     `MultilinearPC::open(ck, &q, &a_rev)` (:218-225, G2 MSMs) and MIPP's `final_h` / `pst_proof_h` (SURVEY.md 8f rank 1).
-  * the pairing product `t` (src/sqrt_pst.rs:131-144) and the Poseidon transcript are OUT OF SCOPE of this engine
-    (SURVEY.md 8f): `commit` returns t = None, `open` takes the Fiat-Shamir challenges from a callback.
+  * the pairing product `t = multi_pairing(comm_list, powers_of_h[odd])` (src/sqrt_pst.rs:131-144) and MIPP's
+    `comms_t` run on the GPU too when ck carries the G2 side; with a G1-only key `commit`
+    returns t = None.
+  * the Poseidon transcript is OUT OF SCOPE of this engine: `open` takes the Fiat-Shamir
+    challenges from a callback that receives what the reference appends.
 """
 from __future__ import annotations
 
@@ -23,7 +26,7 @@ from typing import Callable, List, Optional, Tuple
 
 import numpy as np
 
-from . import _lib, curve, fr, mipp, msm, multilinear_pc
+from . import _lib, curve, fr, mipp, msm, multilinear_pc, pairing
 
 
 def _ptr(a: np.ndarray):
@@ -143,17 +146,30 @@ class Polynomial:
         """polys[i].Z of the reference: Z[(j << m_col) | i] for j < 2^m_row."""
         return self.Z[i :: 1 << self.m]
 
-    def commit(self, ck: CommitterKey) -> Tuple[np.ndarray, None]:
-        """src/sqrt_pst.rs:117-149 -> (comm_list as [2^m_col, 12] g_products, t). t (pairing product) is not computed."""
+    def commit(self, ck: CommitterKey) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+        """src/sqrt_pst.rs:117-149 -> (comm_list as [2^m_col, 12] g_products, t). t = multi_pairing(comm_list,
+        ck.powers_of_h[odd]) as a [72] GT element (computed from the device-resident commitments) when ck carries
+        powers_of_h, else None."""
         rows, cols = 1 << self.m, 1 << self.m_row
         assert cols == len(ck.powers_of_g0), "ck.powers_of_g[0] must have 2^m_row points"
         lib = _lib.engine()
         d_out = _DeviceBuffer(np.zeros((rows, 12), dtype=np.uint64))
         _lib.check(lib.tb200_msm_g1_batch_dev(ck._h, self._dZ.ptr, rows, cols, 1, rows, _lib.SCALARS_MONT, d_out.ptr, None))
+        t = None
+        if ck.powers_of_h is not None:                                  # src/sqrt_pst.rs:128-143
+            h_vec = np.ascontiguousarray(ck.powers_of_h[self.odd], dtype=np.uint64).reshape(-1, 24)
+            assert len(h_vec) == rows, "comm_list.len() == h_vec.len() (src/sqrt_pst.rs:129)"
+            d_h = _DeviceBuffer(h_vec)
+            d_t = _DeviceBuffer(np.zeros(pairing.GT_WORDS, dtype=np.uint64))
+            _lib.check(lib.tb200_multi_pairing_dev(d_out.ptr, d_h.ptr, rows, d_t.ptr, None))
+            _lib.check(lib.tb200_stream_sync())
+            t = d_t.download((pairing.GT_WORDS,))
+            d_h.free()
+            d_t.free()
         _lib.check(lib.tb200_stream_sync())
         out = d_out.download((rows, 12))
         d_out.free()
-        return out, None
+        return out, t
 
     def get_q(self, point: List[int]) -> None:
         """src/sqrt_pst.rs:81-101 on the GPU: chis by k_fr_chis, q = Z * chis by k_fr_matvec.
@@ -196,9 +212,10 @@ class Polynomial:
         return fr.from_mont_words(out)[0]
 
     def open(self, challenge: Callable[[bytes, List[np.ndarray]], int], comm_list: np.ndarray, ck: CommitterKey,
-             point: List[int]) -> OpenG1:
-        """G1 work of src/sqrt_pst.rs:168-230. `challenge(label, appended_points)` stands in for the Poseidon
-        transcript (out of scope): it receives what the reference appends and returns the squeezed scalar."""
+             point: List[int], t: Optional[np.ndarray] = None) -> OpenG1:
+        """src/sqrt_pst.rs:168-230 (`t` is accepted and unused, as `_T` in MippProof::prove, src/mipp.rs:38).
+        `challenge(label, appended_values)` stands in for the Poseidon transcript (out of scope): it receives what the
+        reference appends and returns the squeezed scalar."""
         if self.q is None:
             self.get_q(point)
         assert self.chis_b is not None, "chis(b) should have been computed for q"
