@@ -26,4 +26,9 @@ for n in (1, 2, 64, 1024, 8192):
         t0 = time.perf_counter()
         pairing.multi_pairing(a, b)
         ts.append(time.perf_counter() - t0)
-    print(f"multi_pairing n={n}: {min(ts) * 1e3:.2f} ms", flush=True)
+    lib = _lib.engine()
+    lib.tb200_set_profiling(1)
+    pairing.multi_pairing(a, b)
+    st = {k: round(lib.tb200_stage_ms(k.encode()), 3) for k in ("miller", "gt_product", "final_exp")}
+    lib.tb200_set_profiling(0)
+    print(f"multi_pairing n={n}: {min(ts) * 1e3:.2f} ms  stages {st}", flush=True)

@@ -70,6 +70,28 @@ def test_fq12_ops_on_device(engine):
     assert run_op(engine, 7, A[:4]) == [pr.final_exponentiation(x) for x in xs[:4]]
 
 
+def test_warp_cooperative_fq12_ops(engine):
+    """The warp-cooperative engine behind k_final_exp (one warp per Fq12 operation, operands in shared memory)."""
+    import random
+
+    rng = random.Random(5)
+    n = 6
+    xs = [tuple((rng.randrange(o.Q), rng.randrange(o.Q)) for _ in range(6)) for _ in range(n)]
+    ys = [tuple((rng.randrange(o.Q), rng.randrange(o.Q)) for _ in range(6)) for _ in range(n)]
+    xs[0] = pr.F12_ONE
+    A, B = f12_np(xs), f12_np(ys)
+    assert run_op(engine, 20, A, B) == [pr.f12_mul(x, y) for x, y in zip(xs, ys)]
+    assert run_op(engine, 21, A) == [pr.f12_sqr(x) for x in xs]
+    assert run_op(engine, 24, A) == [pr.f12_frobenius(x, 1) for x in xs]
+    assert run_op(engine, 25, A) == [pr.f12_frobenius(x, 2) for x in xs]
+    assert run_op(engine, 26, A) == [pr.f12_sqr(x) for x in xs]
+    us = [pr.f12_pow(E_GEN, rng.randrange(1, o.R_ORDER)) for _ in range(3)]
+    U = f12_np(us)
+    assert run_op(engine, 22, U) == [pr.f12_sqr(u) for u in us]
+    assert run_op(engine, 27, U) == [pr.f12_conj(pr.f12_sqr(u)) for u in us]
+    assert run_op(engine, 23, A[:3]) == [pr.final_exponentiation(x) for x in xs[:3]]
+
+
 def test_miller_loop_on_device(engine):
     ps, _ = o.rand_points(3, 9)
     qs, _ = o2.rand_points(3, 10)

@@ -1206,8 +1206,11 @@ static int pairing_products_locked(const uint4* d_g1, const uint4* d_g2, uint32_
   uint4 *buf_a = nullptr, *buf_b = nullptr;
   CU(cudaMallocAsync((void**)&buf_a, (size_t)n * 576, st));
   CU(cudaMallocAsync((void**)&buf_b, (size_t)segs * cdiv(len, FQ12_FAN) * 576 + 576, st));
+  g.marks.clear();
+  if (mark(st, "begin")) return 1;
   LAUNCH(k_miller, cdiv(n, 32), 32, st, d_g1, d_g2, n, xor_mask, buf_a);
   if (after_miller) CU(cudaEventRecord(after_miller, st));
+  if (mark(st, "miller")) return 1;
   uint4 *cur = buf_a, *nxt = buf_b;
   while (len > 1) {
     const uint32_t m = cdiv(len, FQ12_FAN);
@@ -1215,10 +1218,12 @@ static int pairing_products_locked(const uint4* d_g1, const uint4* d_g2, uint32_
     std::swap(cur, nxt);
     len = m;
   }
+  if (mark(st, "gt_product")) return 1;
   LAUNCH(k_final_exp, segs, 32, st, cur, d_out);
+  if (mark(st, "final_exp")) return 1;
   CU(cudaFreeAsync(buf_a, st));
   CU(cudaFreeAsync(buf_b, st));
-  return 0;
+  return finish_marks(st);
 }
 
 int tb200_multi_pairing_dev(const void* d_g1_xy, const void* d_g2, size_t n, void* d_out, void* stream) {
@@ -1598,7 +1603,10 @@ int tb200_test_fq12_op(int op, const uint64_t* a, const uint64_t* b, size_t n, u
   if (!a || !b || !out || n == 0 || op < 0) return fail(TB200_E_ARG, "bad arguments");
   CU(cudaSetDevice(g.device));
   return with_buffers(a, n * 576, b, n * 576, out, n * 576, nullptr, 0, [&](char* da, char* db, char* d1, char*) {
-    LAUNCH(k_test_fq12_op, cdiv(n, 32), 32, g.stream, op, (const uint4*)da, (const uint4*)db, (uint32_t)n, (uint4*)d1);
+    if (op >= 20 && op < 100)
+      LAUNCH(k_test_w12_op, (uint32_t)n, 32, g.stream, op, (const uint4*)da, (const uint4*)db, (uint4*)d1);
+    else
+      LAUNCH(k_test_fq12_op, cdiv(n, 32), 32, g.stream, op, (const uint4*)da, (const uint4*)db, (uint32_t)n, (uint4*)d1);
     return 0;
   });
 }

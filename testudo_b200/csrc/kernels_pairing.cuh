@@ -71,13 +71,267 @@ __global__ void __launch_bounds__(32) k_fq12_prod_level(const uint4* __restrict_
   store_fq12(out + 36 * ((size_t)blockIdx.y * m + t), acc);
 }
 
-// out[b] = final_exponentiation(in[b]); one thread per product
+// ---- warp-cooperative Fq12 arithmetic --------------------------------------------------------------------------------
+// A final exponentiation is ONE dependent chain of ~315 cyclotomic squarings and ~45 Fq12 products; run by a single
+// thread it took 20 ms (31 idle lanes, every Fq2 product in sequence). Here one WARP owns the chain: the Fq12 values live
+// in shared memory and the 18 (12, 6) independent Fq2 products inside every Fq12 product (squaring, cyclotomic squaring)
+// run on 18 lanes at once; the cheap linear recombinations are spread over lanes the same way. Phases are separated by
+// __syncwarp(). All pointers are shared-memory objects of the calling warp; dst may alias the inputs.
+struct WScratch {
+  Fq2 xy[2][3][3];   // materialised Fq6 operands X_i, Y_i (i < 3) of up to three Fq6 products
+  Fq2 prod[18];      // Karatsuba products: [i][j], j = 0..5 -> a0b0, a1b1, a2b2, (a1+a2)(b1+b2), (a0+a1)(b0+b1), (a0+a2)(b0+b2)
+  Fq2 r6[3][3];      // the three Fq6 results
+};
+__device__ __forceinline__ Fq2* w12_c(Fq12* a, int idx) { return reinterpret_cast<Fq2*>(a) + idx; }
+__device__ __forceinline__ const Fq2* w12_c(const Fq12* a, int idx) { return reinterpret_cast<const Fq2*>(a) + idx; }
+
+// phases 1-2 of every product: lane (i, j) multiplies the Karatsuba operands of Fq6 product i; lane (i, t) then
+// assembles coefficient t of result i. `count` = number of Fq6 products (1..3).
+__device__ __noinline__ void w_fq6_products(WScratch* w, int count) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (lane < 6 * count) {
+    const int i = lane / 6, j = lane % 6;
+    const int t0 = (j < 3) ? j : (j == 3 ? 1 : 0);
+    const int t1 = (j == 4) ? 1 : 2;
+    Fq2 a = w->xy[0][i][t0], b = w->xy[1][i][t0];
+    if (j >= 3) {
+      fq2_add(a, a, w->xy[0][i][t1]);
+      fq2_add(b, b, w->xy[1][i][t1]);
+    }
+    fq2_mul_ol(&w->prod[lane], &a, &b);
+  }
+  __syncwarp();
+  if (lane < 3 * count) {
+    const int i = lane / 3, t = lane % 3;
+    const Fq2* p = &w->prod[6 * i];
+    Fq2 r, m;
+    if (t == 0) {          // v0 + xi (m12 - v1 - v2)
+      fq2_sub(m, p[3], p[1]);
+      fq2_sub(m, m, p[2]);
+      fq2_mul_xi(m, m);
+      fq2_add(r, p[0], m);
+    } else if (t == 1) {   // m01 - v0 - v1 + xi v2
+      fq2_sub(r, p[4], p[0]);
+      fq2_sub(r, r, p[1]);
+      fq2_mul_xi(m, p[2]);
+      fq2_add(r, r, m);
+    } else {               // m02 - v0 - v2 + v1
+      fq2_sub(r, p[5], p[0]);
+      fq2_sub(r, r, p[2]);
+      fq2_add(r, r, p[1]);
+    }
+    w->r6[i][t] = r;
+  }
+  __syncwarp();
+}
+
+// dst = a * b: X = {a0, a1, a0 + a1}, Y = {b0, b1, b0 + b1}; C0 = R0 + v R1, C1 = R2 - R0 - R1
+__device__ __noinline__ void w12_mul(Fq12* dst, const Fq12* a, const Fq12* b, WScratch* w) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (lane < 18) {
+    const int which = lane / 9, i = (lane % 9) / 3, t = lane % 3;
+    const Fq12* src = which ? b : a;
+    Fq2 v;
+    if (i < 2) v = *w12_c(src, 3 * i + t);
+    else fq2_add(v, *w12_c(src, t), *w12_c(src, 3 + t));
+    w->xy[which][i][t] = v;
+  }
+  w_fq6_products(w, 3);
+  if (lane < 6) {
+    Fq2 r;
+    if (lane < 3) {        // C0.c[t] = R0[t] + (v R1)[t], v (x0, x1, x2) = (xi x2, x0, x1)
+      Fq2 m = w->r6[1][(lane + 2) % 3];
+      if (lane == 0) fq2_mul_xi(m, m);
+      fq2_add(r, w->r6[0][lane], m);
+    } else {
+      const int t = lane - 3;
+      fq2_sub(r, w->r6[2][t], w->r6[0][t]);
+      fq2_sub(r, r, w->r6[1][t]);
+    }
+    *w12_c(dst, lane) = r;
+  }
+  __syncwarp();
+}
+
+// dst = a^2 (complex squaring): R0 = a0 a1, R1 = (a0 + a1)(a0 + v a1); C0 = R1 - R0 - v R0, C1 = 2 R0
+__device__ __noinline__ void w12_sqr(Fq12* dst, const Fq12* a, WScratch* w) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (lane < 12) {
+    const int which = lane / 6, i = (lane % 6) / 3, t = lane % 3;
+    Fq2 v;
+    if (i == 0) v = *w12_c(a, 3 * which + t);                   // X0 = a0, Y0 = a1
+    else if (which == 0) fq2_add(v, *w12_c(a, t), *w12_c(a, 3 + t));   // X1 = a0 + a1
+    else {                                                      // Y1 = a0 + v a1
+      Fq2 m = *w12_c(a, 3 + (t + 2) % 3);
+      if (t == 0) fq2_mul_xi(m, m);
+      fq2_add(v, *w12_c(a, t), m);
+    }
+    w->xy[which][i][t] = v;
+  }
+  w_fq6_products(w, 2);
+  if (lane < 6) {
+    Fq2 r;
+    if (lane < 3) {
+      Fq2 m = w->r6[0][(lane + 2) % 3];
+      if (lane == 0) fq2_mul_xi(m, m);
+      fq2_sub(r, w->r6[1][lane], w->r6[0][lane]);
+      fq2_sub(r, r, m);
+    } else {
+      fq2_dbl(r, w->r6[0][lane - 3]);
+    }
+    *w12_c(dst, lane) = r;
+  }
+  __syncwarp();
+}
+
+// dst = a^2 for a unitary a (Granger-Scott, as fq12_cyclotomic_sqr_ol): six Fq2 products on six lanes.
+// tower slot of z_k: z0 = c[0], z1 = c[4], z2 = c[3], z3 = c[2], z4 = c[1], z5 = c[5]
+__device__ __noinline__ void w12_cyclotomic_sqr(Fq12* dst, const Fq12* a, WScratch* w) {
+  const int lane = threadIdx.x & 31;
+  constexpr int slot[6] = {0, 4, 3, 2, 1, 5};
+  __syncwarp();
+  if (lane < 6) {
+    const int p = lane >> 1;
+    const Fq2 za = *w12_c(a, slot[2 * p]), zb = *w12_c(a, slot[2 * p + 1]);
+    if ((lane & 1) == 0) fq2_mul_ol(&w->prod[lane], &za, &zb);          // tmp = za zb
+    else {
+      Fq2 s, m;
+      fq2_add(s, za, zb);
+      fq2_mul_xi(m, zb);
+      fq2_add(m, m, za);
+      fq2_mul_ol(&w->prod[lane], &s, &m);                               // (za + zb)(za + xi zb)
+    }
+  }
+  __syncwarp();
+  if (lane < 6) {
+    // z_k' = 3 t - 2 z_k (k = 0, 3, 4) or 3 t + 2 z_k (k = 1, 2, 5), with t = t0, t1, xi t5, t4, t2, t3 for k = 0..5 where
+    // t_{2p} = prod[2p+1] - tmp - xi tmp and t_{2p+1} = 2 tmp (tmp = prod[2p])
+    constexpr int tsel[6] = {0, 1, 5, 4, 2, 3};
+    const int ti = tsel[lane], p = ti >> 1;
+    Fq2 t, m;
+    if ((ti & 1) == 0) {
+      fq2_sub(t, w->prod[2 * p + 1], w->prod[2 * p]);
+      fq2_mul_xi(m, w->prod[2 * p]);
+      fq2_sub(t, t, m);
+    } else {
+      fq2_dbl(t, w->prod[2 * p]);
+    }
+    if (lane == 2) fq2_mul_xi(t, t);
+    const Fq2 z = *w12_c(a, slot[lane]);
+    Fq2 o;
+    if (lane == 0 || lane == 3 || lane == 4) fq2_sub(o, t, z);
+    else fq2_add(o, t, z);
+    fq2_dbl(o, o);
+    fq2_add(o, o, t);
+    *w12_c(dst, slot[lane]) = o;   // each lane rewrites only the slot it read in this phase: dst may alias a
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void w12_copy(Fq12* dst, const Fq12* a) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  Fq2 v;
+  if (lane < 6) v = *w12_c(a, lane);
+  __syncwarp();
+  if (lane < 6) *w12_c(dst, lane) = v;
+  __syncwarp();
+}
+__device__ __forceinline__ void w12_conj(Fq12* dst, const Fq12* a) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  Fq2 v;
+  if (lane < 6) {
+    v = *w12_c(a, lane);
+    if (lane >= 3) fq2_neg(v, v);
+  }
+  __syncwarp();
+  if (lane < 6) *w12_c(dst, lane) = v;
+  __syncwarp();
+}
+// a^(q^k), k = 1, 2: tower slot idx holds the coefficient of w^e, e = 2 idx (idx < 3) or 2 (idx - 3) + 1
+__device__ __noinline__ void w12_frobenius(Fq12* dst, const Fq12* a, int k) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  Fq2 c;
+  if (lane < 6) {
+    const int e = lane < 3 ? 2 * lane : 2 * (lane - 3) + 1;
+    c = *w12_c(a, lane);
+    if (k == 1) fq2_conj(c, c);
+    if (e > 0) {
+      if (k == 1) {
+        Fq2 g;
+        g.c0 = fq_from_table(FQ12_C(FROB1)[e - 1][0]);
+        g.c1 = fq_from_table(FQ12_C(FROB1)[e - 1][1]);
+        fq2_mul_ol(&c, &c, &g);
+      } else {
+        const Fq g = fq_from_table(FQ12_C(FROB2)[e - 1]);
+        fq2_scale(c, c, g);
+      }
+    }
+  }
+  __syncwarp();
+  if (lane < 6) *w12_c(dst, lane) = c;
+  __syncwarp();
+}
+__device__ __noinline__ void w12_exp_by_x(Fq12* dst, const Fq12* a, Fq12* acc, WScratch* w) {
+  w12_copy(acc, a);
+  for (int bit = 62; bit >= 0; bit--) {
+    w12_cyclotomic_sqr(acc, acc, w);
+    if ((BLS_X >> bit) & 1) w12_mul(acc, acc, a, w);
+  }
+  w12_copy(dst, acc);
+}
+
+struct WFinalExp {
+  Fq12 f, r, f2, y0, y1, y2, acc;
+  WScratch w;
+};
+
+// the chain of fq12_final_exp_ol (ark `final_exponentiation`), one warp; s->f holds the input, the result lands in s->r
+__device__ __noinline__ void w12_final_exp(WFinalExp* s) {
+  const int lane = threadIdx.x & 31;
+  WScratch* w = &s->w;
+  w12_conj(&s->r, &s->f);
+  if (lane == 0) fq12_inv_ol(&s->f2, &s->f);      // one inversion per product: a lone Fq inversion dominates it
+  __syncwarp();
+  w12_mul(&s->r, &s->r, &s->f2, w);
+  w12_copy(&s->f2, &s->r);
+  w12_frobenius(&s->r, &s->r, 2);
+  w12_mul(&s->r, &s->r, &s->f2, w);
+  w12_cyclotomic_sqr(&s->y0, &s->r, w);
+  w12_exp_by_x(&s->y1, &s->r, &s->acc, w);
+  w12_conj(&s->y2, &s->r);
+  w12_mul(&s->y1, &s->y1, &s->y2, w);
+  w12_exp_by_x(&s->y2, &s->y1, &s->acc, w);
+  w12_conj(&s->y1, &s->y1);
+  w12_mul(&s->y1, &s->y1, &s->y2, w);
+  w12_exp_by_x(&s->y2, &s->y1, &s->acc, w);
+  w12_frobenius(&s->y1, &s->y1, 1);
+  w12_mul(&s->y1, &s->y1, &s->y2, w);
+  w12_mul(&s->r, &s->r, &s->y0, w);
+  w12_exp_by_x(&s->y0, &s->y1, &s->acc, w);
+  w12_exp_by_x(&s->y2, &s->y0, &s->acc, w);
+  w12_frobenius(&s->y0, &s->y1, 2);
+  w12_conj(&s->y1, &s->y1);
+  w12_mul(&s->y1, &s->y1, &s->y2, w);
+  w12_mul(&s->y1, &s->y1, &s->y0, w);
+  w12_mul(&s->r, &s->r, &s->y1, w);
+}
+
+// out[b] = final_exponentiation(in[b]); one warp per product
 __global__ void __launch_bounds__(32) k_final_exp(const uint4* __restrict__ in, uint4* __restrict__ out) {
-  if (threadIdx.x != 0) return;
-  Fq12 f, e;
-  load_fq12(f, in + 36 * (size_t)blockIdx.x);
-  fq12_final_exp(e, f);
-  store_fq12(out + 36 * (size_t)blockIdx.x, e);
+  __shared__ WFinalExp s;
+  const int lane = threadIdx.x;
+  uint4* f4 = reinterpret_cast<uint4*>(&s.f);
+  for (int i = lane; i < 36; i += 32) f4[i] = in[36 * (size_t)blockIdx.x + i];
+  __syncwarp();
+  w12_final_exp(&s);
+  const uint4* r4 = reinterpret_cast<const uint4*>(&s.r);
+  for (int i = lane; i < 36; i += 32) out[36 * (size_t)blockIdx.x + i] = r4[i];
 }
 
 // out[b] = in[b] with no pairs at all (n == 0): the empty product
@@ -118,6 +372,34 @@ __global__ void __launch_bounds__(32) k_fq12_pow(const uint4* __restrict__ in, c
 // test hook: one Fq12 operation per thread (tests/test_gpu_pairing.py drives every op against the oracle)
 //   0 mul(a,b)  1 sqr(a)  2 inv(a)  3 frobenius(a,1)  4 frobenius(a,2)  5 cyclotomic_sqr(a)  6 exp_by_x(a)
 //   7 final_exp(a)  8 mul_by_034(a; b = l0 || l3 || l4)  9 miller(a = G1 affine || G2 affine)
+//   20 w12_mul  21 w12_sqr  22 w12_cyclotomic_sqr  23 w12_final_exp  24 w12_frobenius(1)  25 w12_frobenius(2)
+//   (warp-cooperative versions: element i is processed by the whole warp of block i / launched with n blocks)
+__global__ void __launch_bounds__(32) k_test_w12_op(int op, const uint4* a, const uint4* b, uint4* out) {
+  __shared__ WFinalExp s;
+  const int lane = threadIdx.x;
+  uint4* f4 = reinterpret_cast<uint4*>(&s.f);
+  uint4* g4 = reinterpret_cast<uint4*>(&s.f2);
+  for (int i = lane; i < 36; i += 32) {
+    f4[i] = a[36 * (size_t)blockIdx.x + i];
+    g4[i] = b[36 * (size_t)blockIdx.x + i];
+  }
+  __syncwarp();
+  switch (op) {
+    case 20: w12_mul(&s.r, &s.f, &s.f2, &s.w); break;
+    case 21: w12_sqr(&s.r, &s.f, &s.w); break;
+    case 22: w12_cyclotomic_sqr(&s.r, &s.f, &s.w); break;
+    case 23: w12_final_exp(&s); break;
+    case 24: w12_frobenius(&s.r, &s.f, 1); break;
+    case 25: w12_frobenius(&s.r, &s.f, 2); break;
+    case 26: w12_mul(&s.f, &s.f, &s.f, &s.w); w12_copy(&s.r, &s.f); break;     // aliasing
+    case 27: w12_cyclotomic_sqr(&s.f, &s.f, &s.w); w12_conj(&s.r, &s.f); break;
+    default: break;
+  }
+  __syncwarp();
+  const uint4* r4 = reinterpret_cast<const uint4*>(&s.r);
+  for (int i = lane; i < 36; i += 32) out[36 * (size_t)blockIdx.x + i] = r4[i];
+}
+
 __global__ void __launch_bounds__(32) k_test_fq12_op(int op, const uint4* a, const uint4* b, uint32_t n, uint4* out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
