@@ -298,3 +298,47 @@ def test_check_sqrt_poly_commit_roundtrip_with_oracle_verifier(engine, nv):
     assert ver.sqrt_pst_verify(vk, shared_transcript(), U, r, v, pst_proof, pd, T) is False
     assert ver.sqrt_pst_verify(vk, shared_transcript(), U, r, v, pst_proof, proof_dict(), pr.f12_sqr(T)) is False
     ck.close()
+
+
+@pytest.mark.parametrize("nv", [4, 5])
+def test_commit_open_bit_exact_vs_oracle_prover(engine, nv):
+    """Every value `Polynomial::commit` and `Polynomial::open` produce (comm_list, t, U, the G2 PST proof, comms_u,
+    comms_t, final_a, final_h, pst_proof_h) from the GPU path, compared limb for limb with the big-integer restatement of
+    the reference's prover (oracle/sqrt_pst.py) on the same CRS, polynomial, point and transcript."""
+    from oracle import bls12_377_g2 as o2
+    from oracle import pairing as pr
+    from oracle import sqrt_pst as osp
+
+    m_col = nv // 2
+    m_row = nv - m_col
+    t = o.rand_scalars(m_row, 3900 + nv)
+    ock = osp.setup_ck(t)
+    g_levels = [h.pts_to_np(l) for l in ock["powers_of_g"]]
+    h_levels = [np.array([o2.affine_to_words(p) for p in l], dtype=np.uint64).reshape(-1, 24) for l in ock["powers_of_h"]]
+    z = o.rand_scalars(1 << nv, 3910 + nv)
+    r = o.rand_scalars(nv, 3920 + nv)
+    # oracle
+    opoly = osp.Polynomial(z)
+    o_comm, o_T = opoly.commit(ock)
+    o_U, o_pst, o_mipp = opoly.open(shared_transcript(), o_comm, ock, r, o_T)
+    # GPU
+    poly = sqrt_pst.Polynomial.from_evaluations(h.scalars_to_np(z, mont=True))
+    ck = sqrt_pst.CommitterKey.from_points(g_levels[0]).with_levels(g_levels, h_levels)
+    comm_list, t_gt = poly.commit(ck)
+    opened = poly.open(shared_transcript(), comm_list, ck, r, t_gt)
+    assert np.array_equal(comm_list, h.pts_to_np(o_comm))
+    assert np.array_equal(t_gt, np.array(pr.to_words(o_T), dtype=np.uint64))
+    assert np.array_equal(opened.u, h.pts_to_np([o_U])[0])
+    assert np.array_equal(opened.pst_proof, np.array([o2.affine_to_words(p) for p in o_pst], dtype=np.uint64))
+    mp = opened.mipp
+    assert mp.xs_inv == o_mipp["xs_inv"] and mp.rs == o_mipp["rs"]
+    for (gl, gr), (ol, orr) in zip(mp.comms_u, o_mipp["comms_u"]):
+        assert np.array_equal(gl, h.pts_to_np([ol])[0]) and np.array_equal(gr, h.pts_to_np([orr])[0])
+    for (gl, gr), (ol, orr) in zip(mp.comms_t, o_mipp["comms_t"]):
+        assert np.array_equal(gl, np.array(pr.to_words(ol), dtype=np.uint64))
+        assert np.array_equal(gr, np.array(pr.to_words(orr), dtype=np.uint64))
+    assert len(mp.comms_t) == len(o_mipp["comms_t"]) == m_col
+    assert np.array_equal(mp.final_a, h.pts_to_np([o_mipp["final_a"]])[0])
+    assert np.array_equal(mp.final_h, np.array(o2.affine_to_words(o_mipp["final_h"]), dtype=np.uint64))
+    assert np.array_equal(mp.pst_proof_h, h.pts_to_np(o_mipp["pst_proof_h"]))
+    ck.close()
