@@ -206,6 +206,8 @@ int tb200_multi_pairing_dev(const void* d_g1_xy, const void* d_g2, size_t n, voi
 int tb200_mipp_pairing_cross(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_t_l[72], uint64_t comm_t_r[72]);
 /* out[i] = base[i] ^ exps[i] in GT (the verifier's `tx.pow(c)`, src/mipp.rs:252-255); exponents are Fr values
  * (canonical, or Montgomery with TB200_SCALARS_MONT). */
+/* tuning/test hook: pairing products of up to `n` pairs run one WARP per Miller loop, larger ones one THREAD (default 2048) */
+void tb200_set_pairing_coop_max(int n);
 int tb200_gt_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned flags, uint64_t* out);
 
 #ifdef __cplusplus

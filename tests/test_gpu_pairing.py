@@ -92,6 +92,33 @@ def test_warp_cooperative_fq12_ops(engine):
     assert run_op(engine, 23, A[:3]) == [pr.final_exponentiation(x) for x in xs[:3]]
 
 
+def test_cooperative_miller_loop_and_both_launch_modes(engine):
+    """Warp-per-pair Miller loop (op 28) against the oracle, and tb200_multi_pairing under both launch modes
+    (thread-per-pair / warp-per-pair) on the same inputs, identities included."""
+    ps, _ = o.rand_points(5, 19)
+    qs, _ = o2.rand_points(5, 20)
+    ps[3], qs[4] = None, None
+    a = np.zeros((5, 72), dtype=np.uint64)
+    a[:, :12] = h.pts_to_np(ps)
+    a[:, 12:36] = g2_np(qs)
+    got = run_op(engine, 28, a)
+    assert [pr.final_exponentiation(f) for f in got] == [pr.pairing(p, q) for p, q in zip(ps, qs)]
+    assert got[3] == pr.F12_ONE and got[4] == pr.F12_ONE
+    ps, _ = o.rand_points(33, 21)
+    qs, _ = o2.rand_points(33, 22)
+    ps[7], qs[9] = None, None
+    A, B = h.pts_to_np(ps), g2_np(qs)
+    try:
+        engine.tb200_set_pairing_coop_max(0)
+        thread_mode = pairing.multi_pairing(A, B)
+        engine.tb200_set_pairing_coop_max(1 << 20)
+        warp_mode = pairing.multi_pairing(A, B)
+    finally:
+        engine.tb200_set_pairing_coop_max(2048)
+    assert np.array_equal(thread_mode, warp_mode)
+    assert pr.from_words(warp_mode) == pr.multi_pairing(ps, qs)
+
+
 def test_miller_loop_on_device(engine):
     ps, _ = o.rand_points(3, 9)
     qs, _ = o2.rand_points(3, 10)

@@ -111,6 +111,7 @@ struct Ctx {
   std::map<std::string, double> stage_ms;
   int forced_c = 0;
   size_t host_chunk_min = size_t(1) << 21;  // tb200_msm_g1 with host buffers: chunked upload/compute overlap from here
+  int pairing_coop_max = 2048;  // Miller loops: warp-per-pair up to this many pairs, thread-per-pair above
   int acc_mode = 0;  // 0 = automatic (= 3), 1 = XYZZ segments, register operands (k_accumulate), 2 = batched-affine
                      // rounds, 3 = XYZZ segments, shared-memory operand slots (k_accumulate_s)
   // geometry of the last call
@@ -601,6 +602,7 @@ int tb200_last_geometry(int* c, int* windows, uint64_t* entries, uint64_t* bucke
   if (segment) *segment = g.last_K;
   return 0;
 }
+void tb200_set_pairing_coop_max(int n) { g.pairing_coop_max = n < 0 ? 0 : n; }
 void tb200_set_window_bits(int c) { g.forced_c = (c >= 3 && c <= 22) ? c : 0; }
 void tb200_set_accumulate_mode(int mode) { g.acc_mode = (mode >= 0 && mode <= 5) ? mode : 0; }
 
@@ -1208,13 +1210,17 @@ static int pairing_products_locked(const uint4* d_g1, const uint4* d_g2, uint32_
   CU(cudaMallocAsync((void**)&buf_b, (size_t)segs * cdiv(len, FQ12_FAN) * 576 + 576, st));
   g.marks.clear();
   if (mark(st, "begin")) return 1;
-  LAUNCH(k_miller, cdiv(n, 32), 32, st, d_g1, d_g2, n, xor_mask, buf_a);
+  // below ~2 waves of resident warps one WARP per pair (latency 10 -> ~3 ms); above, one thread per pair
+  const bool coop = n <= (uint32_t)g.pairing_coop_max;
+  if (coop) LAUNCH(k_miller_coop, n, 32, st, d_g1, d_g2, xor_mask, buf_a);
+  else LAUNCH(k_miller, cdiv(n, 32), 32, st, d_g1, d_g2, n, xor_mask, buf_a);
   if (after_miller) CU(cudaEventRecord(after_miller, st));
   if (mark(st, "miller")) return 1;
   uint4 *cur = buf_a, *nxt = buf_b;
   while (len > 1) {
     const uint32_t m = cdiv(len, FQ12_FAN);
-    LAUNCH(k_fq12_prod_level, dim3(cdiv(m, 32), segs), 32, st, cur, len, m, nxt);
+    if ((uint64_t)m * segs <= 4096) LAUNCH(k_fq12_prod_level_coop, dim3(m, segs), 32, st, cur, len, m, nxt);
+    else LAUNCH(k_fq12_prod_level, dim3(cdiv(m, 32), segs), 32, st, cur, len, m, nxt);
     std::swap(cur, nxt);
     len = m;
   }

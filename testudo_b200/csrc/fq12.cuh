@@ -411,30 +411,46 @@ struct G2Hom {  // homogeneous projective point on the twist (ark `G2HomProjecti
   Fq2 x, y, z;
 };
 
-// ark `G2HomProjective::double_in_place` fused with `ell` (TwistType::D): r = 2 r, f *= line_{r,r}(P)
-TB_HD void miller_double_step(Fq12& f, G2Hom& r, const Fq& px, const Fq& py) {
-  const Fq two_inv = fq_from_table(FQ12_C(TWO_INV));
+// r = a / 2 (mod q): (a + (a odd ? q : 0)) >> 1; the same map in Montgomery form
+TB_HD void fq_halve(Fq& r, const Fq& a) {
+  const uint32_t mask = 0u - (a.l[0] & 1u);
+  uint32_t t[12];
+  Carry c;
+  t[0] = add_cc(a.l[0], FqParams::p(0) & mask, c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) t[i] = addc_cc(a.l[i], FqParams::p(i) & mask, c);
+#pragma unroll
+  for (int i = 0; i < 11; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
+  r.l[11] = t[11] >> 1;
+}
+// (0 + b1 u) * t with B' = (0, b1) the twist coefficient: -5 b1 t1 + b1 t0 u
+TB_HD void fq2_mul_twist_b(Fq2& e, const Fq2& t) {
   const Fq b1 = fq_from_table(FQ12_C(TWIST_B1));
+  Fq m0, m1;
+  fq_mul(m0, t.c1, b1);
+  fq_mul(m1, t.c0, b1);
+  fq_mul5(m0, m0);
+  fq_neg(e.c0, m0);
+  e.c1 = m1;
+}
+
+// ark `G2HomProjective::double_in_place` (TwistType::D): r = 2 r; the line through r, r evaluated at P as the three
+// non-zero coefficients of ark's `ell` / `mul_by_034`: (l0, l3, l4) = (-h py, 3 j px, i)
+TB_HD void g2_double_line(G2Hom& r, Fq2& l0, Fq2& l3, Fq2& l4, const Fq& px, const Fq& py) {
   Fq2 a, b, c, e, ff, g, h, i, j, e2, t;
   fq2_mul(a, r.x, r.y);
-  fq2_scale(a, a, two_inv);
+  fq_halve(a.c0, a.c0);
+  fq_halve(a.c1, a.c1);
   fq2_sqr(b, r.y);
   fq2_sqr(c, r.z);
   fq2_dbl(t, c);
   fq2_add(t, t, c);            // 3 z^2
-  // e = B' * t with B' = (0, b1): (0 + b1 u)(t0 + t1 u) = -5 b1 t1 + b1 t0 u
-  {
-    Fq m0, m1;
-    fq_mul(m0, t.c1, b1);
-    fq_mul(m1, t.c0, b1);
-    fq_mul5(m0, m0);
-    fq_neg(e.c0, m0);
-    e.c1 = m1;
-  }
+  fq2_mul_twist_b(e, t);       // e = B' 3 z^2
   fq2_dbl(ff, e);
   fq2_add(ff, ff, e);          // 3 e
   fq2_add(g, b, ff);
-  fq2_scale(g, g, two_inv);
+  fq_halve(g.c0, g.c0);
+  fq_halve(g.c1, g.c1);
   fq2_add(t, r.y, r.z);
   fq2_sqr(h, t);
   fq2_add(t, b, c);
@@ -449,18 +465,21 @@ TB_HD void miller_double_step(Fq12& f, G2Hom& r, const Fq& px, const Fq& py) {
   fq2_add(t, t, e2);
   fq2_sub(r.y, g, t);
   fq2_mul(r.z, b, h);
-  // coefficients (-h, 3 j, i); line = (-h py) + (3 j px) w + i w^3-ish slot: mul_by_034(c0 py, c1 px, c2)
-  Fq2 l0, l3;
   fq2_neg(l0, h);
   fq2_scale(l0, l0, py);
   fq2_dbl(t, j);
   fq2_add(t, t, j);
   fq2_scale(l3, t, px);
-  fq12_mul_by_034_ol(&f, &l0, &l3, &i);
+  l4 = i;
+}
+TB_HD void miller_double_step(Fq12& f, G2Hom& r, const Fq& px, const Fq& py) {
+  Fq2 l0, l3, l4;
+  g2_double_line(r, l0, l3, l4, px, py);
+  fq12_mul_by_034_ol(&f, &l0, &l3, &l4);
 }
 
-// ark `G2HomProjective::add_in_place` fused with `ell`: r = r + q, f *= line_{r,q}(P)
-TB_HD void miller_add_step(Fq12& f, G2Hom& r, const Affine2& q, const Fq& px, const Fq& py) {
+// ark `G2HomProjective::add_in_place`: r = r + q; line coefficients (l0, l3, l4) = (lambda py, -theta px, j)
+TB_HD void g2_add_line(G2Hom& r, Fq2& l0, Fq2& l3, Fq2& l4, const Affine2& q, const Fq& px, const Fq& py) {
   Fq2 theta, lambda, c, d, e, ff, g, h, j, t;
   fq2_mul(t, q.y, r.z);
   fq2_sub(theta, r.y, t);
@@ -483,12 +502,15 @@ TB_HD void miller_add_step(Fq12& f, G2Hom& r, const Affine2& q, const Fq& px, co
   fq2_mul(j, theta, q.x);
   fq2_mul(t, lambda, q.y);
   fq2_sub(j, j, t);
-  // coefficients (lambda, -theta, j)
-  Fq2 l0, l3;
   fq2_scale(l0, lambda, py);
   fq2_neg(l3, theta);
   fq2_scale(l3, l3, px);
-  fq12_mul_by_034_ol(&f, &l0, &l3, &j);
+  l4 = j;
+}
+TB_HD void miller_add_step(Fq12& f, G2Hom& r, const Affine2& q, const Fq& px, const Fq& py) {
+  Fq2 l0, l3, l4;
+  g2_add_line(r, l0, l3, l4, q, px, py);
+  fq12_mul_by_034_ol(&f, &l0, &l3, &l4);
 }
 
 // f_{x,Q}(P) (up to factors the final exponentiation removes); 1 if either point is the identity, as

@@ -322,6 +322,177 @@ __device__ __noinline__ void w12_final_exp(WFinalExp* s) {
   w12_mul(&s->r, &s->r, &s->y1, w);
 }
 
+// ---- warp-cooperative Miller loop (one warp per pair) --------------------------------------------------------------
+// Thread-per-pair keeps the integer pipe fed only when there are thousands of pairs; the MIPP rounds of the reference
+// issue products of 2^12 ... 1 pairs and every one of them waits for a full 10 ms single-thread Miller loop. Below ~2^11
+// pairs one warp owns a pair: f^2 and f * line are the cooperative Fq12 operations above, the doubling step runs its
+// five + six independent Fq2 products on parallel lanes, and only the six addition steps of the loop are serial.
+struct WMiller {
+  Fq12 f, line;      // line = (l0, 0, 0) + (l3, l4, 0) w in tower slots 0, 3, 4; slots 1, 2, 5 stay zero
+  G2Hom r;
+  Affine2 q;
+  Affine p;
+  Fq2 t[6];
+  WScratch w;
+};
+
+// ark `double_in_place` (see g2_double_line) on parallel lanes; updates s->r and the line slots of s->line
+__device__ __noinline__ void w_double_step(WMiller* s) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (lane < 5) {
+    Fq2 o;
+    if (lane == 0) {                       // a = x y / 2
+      fq2_mul_ol(&o, &s->r.x, &s->r.y);
+      fq_halve(o.c0, o.c0);
+      fq_halve(o.c1, o.c1);
+      s->t[0] = o;
+    } else if (lane == 1) {                // b = y^2
+      fq2_sqr_ol(&o, &s->r.y);
+      s->t[1] = o;
+    } else if (lane == 2) {                // c = z^2, e = B' 3 c
+      Fq2 c, t3;
+      fq2_sqr_ol(&c, &s->r.z);
+      fq2_dbl(t3, c);
+      fq2_add(t3, t3, c);
+      fq2_mul_twist_b(o, t3);
+      s->t[2] = c;
+      s->t[3] = o;
+    } else if (lane == 3) {                // (y + z)^2
+      Fq2 yz;
+      fq2_add(yz, s->r.y, s->r.z);
+      fq2_sqr_ol(&o, &yz);
+      s->t[4] = o;
+    } else {                               // j = x^2
+      fq2_sqr_ol(&o, &s->r.x);
+      s->t[5] = o;
+    }
+  }
+  __syncwarp();
+  Fq2 out;
+  if (lane < 6) {
+    const Fq2 b = s->t[1], e = s->t[3];
+    if (lane == 0) {                       // x' = a (b - 3 e)
+      Fq2 f3, d;
+      fq2_dbl(f3, e);
+      fq2_add(f3, f3, e);
+      fq2_sub(d, b, f3);
+      fq2_mul_ol(&out, &s->t[0], &d);
+    } else if (lane == 1) {                // y' = ((b + 3 e) / 2)^2 - 3 e^2
+      Fq2 f3, g, e2, t3;
+      fq2_dbl(f3, e);
+      fq2_add(f3, f3, e);
+      fq2_add(g, b, f3);
+      fq_halve(g.c0, g.c0);
+      fq_halve(g.c1, g.c1);
+      fq2_sqr_ol(&g, &g);
+      fq2_sqr_ol(&e2, &e);
+      fq2_dbl(t3, e2);
+      fq2_add(t3, t3, e2);
+      fq2_sub(out, g, t3);
+    } else if (lane == 2 || lane == 3) {   // h = (y + z)^2 - (b + c);  z' = b h;  l0 = -h py
+      Fq2 h, bc;
+      fq2_add(bc, b, s->t[2]);
+      fq2_sub(h, s->t[4], bc);
+      if (lane == 2) fq2_mul_ol(&out, &b, &h);
+      else {
+        fq2_neg(h, h);
+        fq2_scale(out, h, s->p.y);
+      }
+    } else if (lane == 4) {                // l3 = 3 j px
+      Fq2 j3;
+      fq2_dbl(j3, s->t[5]);
+      fq2_add(j3, j3, s->t[5]);
+      fq2_scale(out, j3, s->p.x);
+    } else {                               // l4 = i = e - b
+      fq2_sub(out, e, b);
+    }
+  }
+  __syncwarp();
+  if (lane == 0) s->r.x = out;
+  else if (lane == 1) s->r.y = out;
+  else if (lane == 2) s->r.z = out;
+  else if (lane == 3) *w12_c(&s->line, 0) = out;
+  else if (lane == 4) *w12_c(&s->line, 3) = out;
+  else if (lane == 5) *w12_c(&s->line, 4) = out;
+  __syncwarp();
+}
+
+// s->p, s->q loaded; result in s->f
+__device__ __noinline__ void w_miller_loop(WMiller* s) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (lane < 6) {
+    *w12_c(&s->f, lane) = lane == 0 ? fq2_one() : fq2_zero();
+    *w12_c(&s->line, lane) = fq2_zero();
+  }
+  if (lane == 6) {
+    s->r.x = s->q.x;
+    s->r.y = s->q.y;
+    s->r.z = fq2_one();
+  }
+  __syncwarp();
+  if (affine_is_inf(s->p) || affine2_is_inf(s->q)) return;   // uniform across the warp
+  for (int bit = 62; bit >= 0; bit--) {
+    if (bit != 62) w12_sqr(&s->f, &s->f, &s->w);
+    w_double_step(s);
+    w12_mul(&s->f, &s->f, &s->line, &s->w);
+    if ((BLS_X >> bit) & 1) {
+      if (lane == 0) {
+        Fq2 l0, l3, l4;
+        G2Hom r = s->r;
+        g2_add_line(r, l0, l3, l4, s->q, s->p.x, s->p.y);
+        s->r = r;
+        *w12_c(&s->line, 0) = l0;
+        *w12_c(&s->line, 3) = l3;
+        *w12_c(&s->line, 4) = l4;
+      }
+      __syncwarp();
+      w12_mul(&s->f, &s->f, &s->line, &s->w);
+    }
+  }
+}
+
+// f[j] = Miller(g1[j], g2[j ^ xor_mask]), one warp (= one block) per pair
+__global__ void __launch_bounds__(32) k_miller_coop(const uint4* __restrict__ g1, const uint4* __restrict__ g2,
+                                                    uint32_t xor_mask, uint4* __restrict__ f_out) {
+  __shared__ WMiller s;
+  const int lane = threadIdx.x;
+  const uint32_t j = blockIdx.x;
+  uint4* p4 = reinterpret_cast<uint4*>(&s.p);
+  uint4* q4 = reinterpret_cast<uint4*>(&s.q);
+  if (lane < 6) p4[lane] = g1[6 * (size_t)j + lane];
+  if (lane >= 8 && lane < 20) q4[lane - 8] = g2[12 * (size_t)(j ^ xor_mask) + (lane - 8)];
+  __syncwarp();
+  w_miller_loop(&s);
+  __syncwarp();
+  const uint4* f4 = reinterpret_cast<const uint4*>(&s.f);
+  for (int i = lane; i < 36; i += 32) f_out[36 * (size_t)j + i] = f4[i];
+}
+
+// product tree level, one warp per output: out[s][t] = prod_k in[s][t + k m]
+__global__ void __launch_bounds__(32) k_fq12_prod_level_coop(const uint4* __restrict__ in, uint32_t len, uint32_t m,
+                                                             uint4* __restrict__ out) {
+  __shared__ Fq12 acc, x;
+  __shared__ WScratch w;
+  const int lane = threadIdx.x;
+  const uint32_t t = blockIdx.x;
+  const uint4* src = in + 36 * (size_t)blockIdx.y * len;
+  uint4* a4 = reinterpret_cast<uint4*>(&acc);
+  uint4* x4 = reinterpret_cast<uint4*>(&x);
+  for (int i = lane; i < 36; i += 32) a4[i] = src[36 * (size_t)t + i];
+  for (int k = 1; k < FQ12_FAN; k++) {
+    const uint64_t idx = (uint64_t)t + (uint64_t)k * m;
+    if (idx >= len) break;
+    __syncwarp();
+    for (int i = lane; i < 36; i += 32) x4[i] = src[36 * idx + i];
+    __syncwarp();
+    w12_mul(&acc, &acc, &x, &w);
+  }
+  __syncwarp();
+  for (int i = lane; i < 36; i += 32) out[36 * ((size_t)blockIdx.y * m + t) + i] = a4[i];
+}
+
 // out[b] = final_exponentiation(in[b]); one warp per product
 __global__ void __launch_bounds__(32) k_final_exp(const uint4* __restrict__ in, uint4* __restrict__ out) {
   __shared__ WFinalExp s;
@@ -392,6 +563,17 @@ __global__ void __launch_bounds__(32) k_test_w12_op(int op, const uint4* a, cons
     case 24: w12_frobenius(&s.r, &s.f, 1); break;
     case 25: w12_frobenius(&s.r, &s.f, 2); break;
     case 26: w12_mul(&s.f, &s.f, &s.f, &s.w); w12_copy(&s.r, &s.f); break;     // aliasing
+    case 28: {                                                                  // cooperative Miller loop: a = G1 || G2
+      __shared__ WMiller ms;
+      uint4* p4 = reinterpret_cast<uint4*>(&ms.p);
+      uint4* q4 = reinterpret_cast<uint4*>(&ms.q);
+      if (lane < 6) p4[lane] = a[36 * (size_t)blockIdx.x + lane];
+      if (lane >= 8 && lane < 20) q4[lane - 8] = a[36 * (size_t)blockIdx.x + 6 + (lane - 8)];
+      __syncwarp();
+      w_miller_loop(&ms);
+      w12_copy(&s.r, &ms.f);
+      break;
+    }
     case 27: w12_cyclotomic_sqr(&s.f, &s.f, &s.w); w12_conj(&s.r, &s.f); break;
     default: break;
   }
