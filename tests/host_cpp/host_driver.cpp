@@ -61,11 +61,37 @@ static int run_g2(const char* fin, const char* fout) {
   return 0;
 }
 
+// in: n, n G1 points, n G2 points, one Fr exponent -> out: multi_pairing, pairing of the first pair, its power, and
+// multi_pairing with the G2 side one element shorter (zip semantics)
+static int run_pairing(const char* fin, const char* fout) {
+  std::ifstream in(fin, std::ios::binary);
+  uint64_t n;
+  in.read((char*)&n, 8);
+  auto a = rd<G1Affine>(in, n);
+  auto b = rd<G2Affine>(in, n);
+  auto e = rd<Fr>(in, 1);
+  std::ofstream out(fout, std::ios::binary);
+  Gt t = pairing::ipp_commitment(a, b);
+  wr(out, &t, 1);
+  Gt one = pairing::pairing(a[0], b[0]);
+  wr(out, &one, 1);
+  Gt pw = pairing::pow(one, e[0]);
+  wr(out, &pw, 1);
+  std::vector<G2Affine> shorter(b.begin(), b.end() - 1);
+  Gt z = pairing::pairings_product(a, shorter);
+  wr(out, &z, 1);
+  uint64_t threw = 0;
+  try { pairing::ipp_commitment(a, shorter); } catch (const std::invalid_argument&) { threw = 1; }
+  wr(out, &threw, 1);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 3) return 2;
   try {
     init(-1);
     if (argc > 3 && std::string(argv[3]) == "g2") return run_g2(argv[1], argv[2]);
+    if (argc > 3 && std::string(argv[3]) == "pairing") return run_pairing(argv[1], argv[2]);
     std::ifstream in(argv[1], std::ios::binary);
     uint64_t nv;
     in.read((char*)&nv, 8);

@@ -140,3 +140,28 @@ def test_cpp_host_mirror_g2_and_pst_openings(engine, driver, tmp_path):
     comp = rest[24:].reshape(split, 24)
     assert [o2.affine_from_words(r) for r in comp] == [o2.add(h_lv[0][i], o2.mul(point[0], h_lv[0][split + i]))
                                                        for i in range(split)]
+
+
+def test_cpp_host_mirror_pairing(engine, driver, tmp_path):
+    """The C++ mirror's pairing wrappers (E::multi_pairing, pairings_product, GT pow) against the big-integer oracle."""
+    from oracle import bls12_377_g2 as o2
+    from oracle import pairing as pr
+
+    n = 5
+    ps, _ = o.rand_points(n, 951)
+    qs, _ = o2.rand_points(n, 952)
+    ps[2] = None
+    e = o.rand_scalars(1, 953)[0]
+    g2np = np.array([o2.affine_to_words(p) for p in qs], dtype=np.uint64)
+    blob = struct.pack("<Q", n) + h.pts_to_np(ps).tobytes() + g2np.tobytes() + h.scalars_to_np([e], mont=True).tobytes()
+    fin, fout = tmp_path / "in3.bin", tmp_path / "out3.bin"
+    fin.write_bytes(blob)
+    subprocess.check_call([driver, str(fin), str(fout), "pairing"])
+    data = np.frombuffer(fout.read_bytes(), dtype=np.uint64)
+    gts = [pr.from_words(data[72 * i: 72 * i + 72]) for i in range(4)]
+    first = pr.pairing(ps[0], qs[0])
+    assert gts[0] == pr.multi_pairing(ps, qs)
+    assert gts[1] == first
+    assert gts[2] == pr.f12_pow(first, e)
+    assert gts[3] == pr.multi_pairing(ps[:-1], qs[:-1])
+    assert int(data[288]) == 1

@@ -39,7 +39,11 @@ struct G2Affine {  // x.c0[6] || x.c1[6] || y.c0[6] || y.c1[6] Montgomery limbs 
   uint64_t w[24];
   bool operator==(const G2Affine& o) const { return std::memcmp(w, o.w, 192) == 0; }
 };
-static_assert(sizeof(Fr) == 32 && sizeof(G1Affine) == 96 && sizeof(G2Affine) == 192, "ABI layouts");
+struct Gt {  // ark Fq12 in memory: c0.c0.c0, c0.c0.c1, ..., c1.c2.c1, each 6 Montgomery limbs
+  uint64_t w[72];
+  bool operator==(const Gt& o) const { return std::memcmp(w, o.w, sizeof w) == 0; }
+};
+static_assert(sizeof(Fr) == 32 && sizeof(G1Affine) == 96 && sizeof(G2Affine) == 192 && sizeof(Gt) == 576, "ABI layouts");
 
 struct EngineError : std::runtime_error {  // a CUDA failure has no error channel in commit/open: it unwinds
   int code;
@@ -360,5 +364,30 @@ inline std::vector<G1Affine> open_g1(const std::vector<std::vector<G1Affine>>& l
   return proofs;
 }
 }  // namespace multilinear_pc
+
+// ---- ark-ec Pairing for Bls12_377: E::multi_pairing / pairings_product (src/sqrt_pst.rs:131-144, src/mipp.rs:396-398) ---
+namespace pairing {
+// `E::multi_pairing(a, b).0`: zips (the shorter side bounds the product), pairs with an identity contribute 1
+inline Gt multi_pairing(const std::vector<G1Affine>& a, const std::vector<G2Affine>& b) {
+  Gt out;
+  check(tb200_multi_pairing((const uint64_t*)a.data(), (const uint64_t*)b.data(), std::min(a.size(), b.size()), out.w));
+  return out;
+}
+inline Gt pairings_product(const std::vector<G1Affine>& gs, const std::vector<G2Affine>& hs) {  // src/mipp.rs:396-398
+  return multi_pairing(gs, hs);
+}
+inline Gt pairing(const G1Affine& p, const G2Affine& q) { return multi_pairing({p}, {q}); }
+// `TargetField::pow(c.into_bigint())` on Montgomery-form exponents (the verifier's tx.pow(c), src/mipp.rs:252-255)
+inline Gt pow(const Gt& base, const Fr& exp) {
+  Gt out;
+  check(tb200_gt_pow(base.w, exp.l, 1, TB200_SCALARS_MONT, out.w));
+  return out;
+}
+// the IPP commitment of Polynomial::commit: t = multi_pairing(comm_list, ck.powers_of_h[odd])  (src/sqrt_pst.rs:128-143)
+inline Gt ipp_commitment(const std::vector<G1Affine>& comm_list, const std::vector<G2Affine>& h_vec) {
+  if (comm_list.size() != h_vec.size()) throw std::invalid_argument("assert!(comm_list.len() == h_vec.len())");
+  return multi_pairing(comm_list, h_vec);
+}
+}  // namespace pairing
 
 }  // namespace testudo_b200
