@@ -204,6 +204,10 @@ int tb200_multi_pairing_dev(const void* d_g1_xy, const void* d_g2, size_t n, voi
  * comm_t_l = prod_i e(a[i], h[split + i]), comm_t_r = prod_i e(a[split + i], h[i]), split = len / 2.
  * Both handles must have the same current length (>= 2). Waits for the G2 folds enqueued so far. */
 int tb200_mipp_pairing_cross(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_t_l[72], uint64_t comm_t_r[72]);
+/* A whole MIPP round's prover values in one call (src/mipp.rs:77-94): the cross MSMs comm_u_l / comm_u_r and the cross
+ * pairing products comm_t_l / comm_t_r are enqueued on separate streams and awaited together. */
+int tb200_mipp_cross_all(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_u_l[12], uint64_t comm_u_r[12],
+                         uint64_t comm_t_l[72], uint64_t comm_t_r[72]);
 /* out[i] = base[i] ^ exps[i] in GT (the verifier's `tx.pow(c)`, src/mipp.rs:252-255); exponents are Fr values
  * (canonical, or Montgomery with TB200_SCALARS_MONT). */
 /* tuning/test hook: pairing products of up to `n` pairs run one WARP per Miller loop, larger ones one THREAD (default 2048) */

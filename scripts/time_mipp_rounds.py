@@ -33,8 +33,8 @@ for rep in range(2):
         ul, ur = np.zeros(12, np.uint64), np.zeros(12, np.uint64)
         tl, tr = np.zeros(72, np.uint64), np.zeros(72, np.uint64)
         c = rand_sc(1)[0]; ci = rand_sc(1)[0]
-        t0 = time.perf_counter(); _lib.check(lib.tb200_mipp_g1_cross(ha, P(ul), P(ur)))
-        t1 = time.perf_counter(); _lib.check(lib.tb200_mipp_pairing_cross(ha, hh, P(tl), P(tr)))
+        t0 = time.perf_counter()
+        t1 = time.perf_counter(); _lib.check(lib.tb200_mipp_cross_all(ha, hh, P(ul), P(ur), P(tl), P(tr)))
         t2 = time.perf_counter(); _lib.check(lib.tb200_mipp_g1_fold(ha, P(c), P(ci)))
         t3 = time.perf_counter(); _lib.check(lib.tb200_mipp_g2_fold(hh, P(ci)))
         t4 = time.perf_counter()
@@ -44,6 +44,6 @@ for rep in range(2):
     total = time.perf_counter() - t_all
     lib.tb200_mipp_g1_end(ha); lib.tb200_mipp_g2_end(hh)
     print(f"pass {rep}: total {total * 1e3:.1f} ms (final g2 read {(t1 - t0) * 1e3:.2f} ms)")
-    print("   len   g1_cross  pairing_cross  g1_fold  g2_fold(enqueue)   [ms]")
+    print("   len      -      cross_all  g1_fold(enq) g2_fold(enq)   [ms]")
     for r in rows:
         print(f"{r[0]:6d} {r[1] * 1e3:9.2f} {r[2] * 1e3:13.2f} {r[3] * 1e3:9.2f} {r[4] * 1e3:9.2f}")

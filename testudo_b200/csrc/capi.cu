@@ -98,6 +98,8 @@ struct Ctx {
   cudaEvent_t ev_points = nullptr;
   cudaStream_t stream2 = nullptr;      // second pipeline for independent small MSMs (MIPP cross commitments)
   cudaEvent_t ev_join = nullptr;
+  cudaStream_t pair_stream = nullptr;  // pairing products of a MIPP round, next to its cross MSMs (created on first use)
+  cudaEvent_t ev_pair = nullptr, ev_pair2 = nullptr;
   Arena arena;
   Arena arena2;
   // side pipelines for batches of independent small MSMs (the per-variable MSMs of a PST opening)
@@ -500,7 +502,9 @@ struct tb200_mipp {
   unsigned flags = 0;
   uint4* a = nullptr;   // n0 affine points
   uint32_t* y = nullptr;  // n0 scalars (8 limbs)
-  uint32_t* scal = nullptr;  // 16 limbs staging for c, c_inv
+  uint32_t* scal = nullptr;  // 16 limbs staging for c, c_inv, one slot per round (the folds are only enqueued)
+  uint32_t* scal_host = nullptr;  // pinned, same shape
+  int round = 0;
 };
 
 // the G2 commitment key of MIPP (m_h, src/mipp.rs:43,114): folded on its own stream, overlapping the G1 rounds
@@ -576,6 +580,13 @@ void tb200_shutdown(void) {
   g.arena2 = Arena();
   cudaStreamDestroy(g.stream2);
   cudaEventDestroy(g.ev_join);
+  if (g.pair_stream) {
+    cudaStreamSynchronize(g.pair_stream);
+    cudaStreamDestroy(g.pair_stream);
+    cudaEventDestroy(g.ev_pair);
+    cudaEventDestroy(g.ev_pair2);
+    g.pair_stream = nullptr;
+  }
   for (auto e : g.ev_pool) cudaEventDestroy(e);
   g.ev_pool.clear();
   cudaFree(g.d_result);
@@ -1036,7 +1047,8 @@ int tb200_mipp_g1_begin(const uint64_t* a_xy, const uint64_t* y, size_t n, unsig
   h->flags = flags;
   cudaError_t e = cudaMalloc((void**)&h->a, n * 96);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->y, n * 32);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&h->scal, 64);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->scal, 64 * 64);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->scal_host, 64 * 64);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->a, a_xy, n * 96, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->y, y, n * 32, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
@@ -1044,6 +1056,7 @@ int tb200_mipp_g1_begin(const uint64_t* a_xy, const uint64_t* y, size_t n, unsig
     cudaFree(h->a);
     cudaFree(h->y);
     cudaFree(h->scal);
+    cudaFreeHost(h->scal_host);
     delete h;
     return fail((int)e, "MIPP upload failed: %s", cudaGetErrorString(e));
   }
@@ -1064,6 +1077,8 @@ int tb200_mipp_g1_cross(tb200_mipp_t h, uint64_t comm_u_l[12], uint64_t comm_u_r
   // two streams with separate workspaces (the reference runs them as two rayon tasks, src/mipp.rs:77-85)
   const bool prof = g.profiling;
   g.profiling = false;
+  CU(cudaEventRecord(g.ev_join, g.stream));                     // the folds are only enqueued: stream2 must follow them
+  CU(cudaStreamWaitEvent(g.stream2, g.ev_join, 0));
   int rc = msm_dev_locked(h->a, h->y + 8 * (size_t)split, split, h->flags, g.d_result, g.stream, nullptr, nullptr, false);
   if (rc == 0)
     rc = msm_dev_locked(h->a + 6 * (size_t)split, h->y, split, h->flags, g.d_result + 6, g.stream2, nullptr, &g.arena2,
@@ -1085,14 +1100,18 @@ int tb200_mipp_g1_fold(tb200_mipp_t h, const uint64_t c[4], const uint64_t c_inv
   if (!h || !c || !c_inv) return fail(TB200_E_ARG, "null pointer");
   if (h->n < 2) return fail(TB200_E_STATE, "MIPP vectors are already folded to length 1");
   CU(cudaSetDevice(g.device));
+  if (h->round >= 64) return fail(TB200_E_LIMIT, "too many rounds");
   const uint32_t split = h->n / 2;
-  memcpy(g.h_result, c, 32);
-  memcpy((char*)g.h_result + 32, c_inv, 32);
-  CU(cudaMemcpyAsync(h->scal, g.h_result, 64, cudaMemcpyHostToDevice, g.stream));
+  // enqueue only: every later use of a / y is ordered behind the folds on the library's stream
+  uint32_t* hs = h->scal_host + 16 * h->round;
+  uint32_t* ds = h->scal + 16 * h->round;
+  memcpy(hs, c, 32);
+  memcpy(hs + 8, c_inv, 32);
+  CU(cudaMemcpyAsync(ds, hs, 64, cudaMemcpyHostToDevice, g.stream));
   const int mont = (h->flags & TB200_SCALARS_MONT) ? 1 : 0;
-  LAUNCH(k_compress_g1, cdiv(split, 128), 128, g.stream, h->a, split, h->scal, mont);
-  LAUNCH(k_compress_fr, cdiv(split, 128), 128, g.stream, h->y, split, h->scal + 8, mont);
-  CU(cudaStreamSynchronize(g.stream));
+  LAUNCH(k_compress_g1, cdiv(split, 128), 128, g.stream, h->a, split, ds, mont);
+  LAUNCH(k_compress_fr, cdiv(split, 128), 128, g.stream, h->y, split, ds + 8, mont);
+  h->round++;
   h->n = split;
   return 0;
 }
@@ -1116,6 +1135,7 @@ int tb200_mipp_g1_end(tb200_mipp_t h) {
     cudaFree(h->a);
     cudaFree(h->y);
     cudaFree(h->scal);
+    cudaFreeHost(h->scal_host);
   }
   delete h;
   return 0;
@@ -1291,6 +1311,66 @@ int tb200_mipp_pairing_cross(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_t_
     if (e != cudaSuccess) rc = fail((int)e, "pairing result copy failed: %s", cudaGetErrorString(e));
   }
   cudaFreeAsync(d_o, g.stream);
+  return rc;
+}
+
+// One MIPP round's four values in one call: the two cross MSMs (library streams) and the two cross pairing products
+// (their own stream) run side by side; a single host synchronisation at the end.
+int tb200_mipp_cross_all(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_u_l[12], uint64_t comm_u_r[12],
+                         uint64_t comm_t_l[72], uint64_t comm_t_r[72]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!a || !h || !comm_u_l || !comm_u_r || !comm_t_l || !comm_t_r) return fail(TB200_E_ARG, "null pointer");
+  if (a->n != h->n) return fail(TB200_E_ARG, "MIPP vectors differ in length (%u vs %u)", a->n, h->n);
+  if (a->n < 2) return fail(TB200_E_STATE, "MIPP vectors are already folded to length 1");
+  CU(cudaSetDevice(g.device));
+  if (!g.pair_stream) {
+    CU(cudaStreamCreateWithFlags(&g.pair_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&g.ev_pair, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&g.ev_pair2, cudaEventDisableTiming));
+  }
+  const uint32_t n = a->n, split = n / 2;
+  const bool prof = g.profiling;
+  g.profiling = false;
+  // pairing stream: behind the G1 folds (library stream) and the G2 folds (the key's stream)
+  CU(cudaEventRecord(g.ev_pair, g.stream));
+  CU(cudaStreamWaitEvent(g.pair_stream, g.ev_pair, 0));
+  CU(cudaStreamWaitEvent(g.stream2, g.ev_pair, 0));             // the second cross MSM reads the folded a, y too
+  CU(cudaEventRecord(g.ev_pair2, h->st));
+  CU(cudaStreamWaitEvent(g.pair_stream, g.ev_pair2, 0));
+  uint4* d_o = nullptr;
+  CU(cudaMallocAsync((void**)&d_o, 2 * 576, g.pair_stream));
+  int rc = pairing_products_locked(a->a, h->h, n, split, 2, d_o, g.pair_stream, g.ev_pair);
+  if (rc == 0) {
+    cudaError_t e = cudaStreamWaitEvent(h->st, g.ev_pair, 0);   // later G2 folds rewrite h: behind this round's Miller kernel
+    if (e != cudaSuccess) rc = fail((int)e, "event wait failed: %s", cudaGetErrorString(e));
+  }
+  // cross MSMs as in tb200_mipp_g1_cross
+  if (rc == 0)
+    rc = msm_dev_locked(a->a, a->y + 8 * (size_t)split, split, a->flags, g.d_result, g.stream, nullptr, nullptr, false);
+  if (rc == 0)
+    rc = msm_dev_locked(a->a + 6 * (size_t)split, a->y, split, a->flags, g.d_result + 6, g.stream2, nullptr, &g.arena2,
+                        false);
+  g.profiling = prof;
+  if (rc == 0) {
+    cudaError_t e = cudaEventRecord(g.ev_join, g.stream2);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(g.stream, g.ev_join, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(g.h_result, g.d_result, 192, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(comm_t_l, d_o, 576, cudaMemcpyDeviceToHost, g.pair_stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(comm_t_r, d_o + 36, 576, cudaMemcpyDeviceToHost, g.pair_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.pair_stream);
+    if (e != cudaSuccess) rc = fail((int)e, "MIPP round failed: %s", cudaGetErrorString(e));
+    else {
+      memcpy(comm_u_l, g.h_result, 96);
+      memcpy(comm_u_r, (char*)g.h_result + 96, 96);
+    }
+  } else {
+    cudaStreamSynchronize(g.stream);
+    cudaStreamSynchronize(g.stream2);
+    cudaStreamSynchronize(g.pair_stream);
+  }
+  cudaFreeAsync(d_o, g.pair_stream);
   return rc;
 }
 

@@ -83,14 +83,15 @@ class MippProofG1:
             while lib.tb200_mipp_g1_len(h) > 1:                          # :58
                 ul = np.zeros(12, dtype=np.uint64)
                 ur = np.zeros(12, dtype=np.uint64)
-                _lib.check(lib.tb200_mipp_g1_cross(h, _ptr(ul), _ptr(ur)))   # :77-85
                 appended = [ul, ur]
-                if m_h is not None:                                      # pairings_product(a_l, h_r), (a_r, h_l), :87-94
-                    tl = np.zeros(72, dtype=np.uint64)
+                if m_h is not None:        # :77-94 in one call: the cross MSMs and pairings_product(a_l, h_r), (a_r, h_l)
+                    tl = np.zeros(72, dtype=np.uint64)                   # run side by side on separate streams
                     tr = np.zeros(72, dtype=np.uint64)
-                    _lib.check(lib.tb200_mipp_pairing_cross(h, m_h, _ptr(tl), _ptr(tr)))
+                    _lib.check(lib.tb200_mipp_cross_all(h, m_h, _ptr(ul), _ptr(ur), _ptr(tl), _ptr(tr)))
                     out.comms_t.append((tl, tr))                         # :116
                     appended += [tl, tr]
+                else:
+                    _lib.check(lib.tb200_mipp_g1_cross(h, _ptr(ul), _ptr(ur)))   # :77-85
                 c_inv = challenge(b"challenge_i", appended) % fr.R       # :97-101
                 c = fr.inverse(c_inv)                                    # :106
                 cw = curve.scalars_to_words([c], mont=True)[0]
