@@ -513,6 +513,7 @@ struct tb200_mipp_g2 {
   unsigned flags = 0;
   uint4* h = nullptr;          // n0 G2 affine points (12 uint4 each)
   uint32_t* scal = nullptr;    // device staging: one 8-limb scalar per round
+  uint32_t* digits = nullptr;  // its four base-x digits (k_glv4_digits), same shape
   uint32_t* scal_host = nullptr;  // pinned, same shape (every round has its own slot: the copies are asynchronous)
   cudaStream_t st = nullptr;      // own stream: the folds overlap the G1 rounds on the library's streams
   int round = 0;
@@ -1155,12 +1156,14 @@ int tb200_mipp_g2_begin(const uint64_t* h_vec, size_t n, unsigned flags, tb200_m
   cudaStream_t m_st = m->st;
   if (e == cudaSuccess) e = cudaMalloc((void**)&m->h, n * 192);
   if (e == cudaSuccess) e = cudaMalloc((void**)&m->scal, 64 * 32);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&m->digits, 64 * 32);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&m->scal_host, 64 * 32);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->h, h_vec, n * 192, cudaMemcpyHostToDevice, m_st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(m_st);   // h_vec is only borrowed for the duration of the call
   if (e != cudaSuccess) {
     cudaFree(m->h);
     cudaFree(m->scal);
+    cudaFree(m->digits);
     cudaFreeHost(m->scal_host);
     if (m->st) cudaStreamDestroy(m->st);
     delete m;
@@ -1182,8 +1185,9 @@ int tb200_mipp_g2_fold(tb200_mipp_g2_t h, const uint64_t c_inv[4]) {
   cudaStream_t m_st = h->st;
   memcpy(h->scal_host + 8 * h->round, c_inv, 32);
   CU(cudaMemcpyAsync(h->scal + 8 * h->round, h->scal_host + 8 * h->round, 32, cudaMemcpyHostToDevice, m_st));
-  LAUNCH(k_compress_g2, cdiv(split, 64), 64, m_st, h->h, split, h->scal + 8 * h->round,
-         (h->flags & TB200_SCALARS_MONT) ? 1 : 0);
+  // 4-dimensional decomposition over the twisted Frobenius (kernels_pairing.cuh): 64 doublings instead of 253
+  LAUNCH(k_glv4_digits, 1, 32, m_st, h->scal + 8 * h->round, (h->flags & TB200_SCALARS_MONT) ? 1 : 0, h->digits + 8 * h->round);
+  LAUNCH(k_compress_g2_glv, cdiv(split, 64), 64, m_st, h->h, split, h->digits + 8 * h->round);
   h->round++;
   h->n = split;
   return 0;
@@ -1207,6 +1211,7 @@ int tb200_mipp_g2_end(tb200_mipp_g2_t h) {
     cudaStreamSynchronize(h->st);
     cudaFree(h->h);
     cudaFree(h->scal);
+    cudaFree(h->digits);
     cudaFreeHost(h->scal_host);
     cudaStreamDestroy(h->st);
   }

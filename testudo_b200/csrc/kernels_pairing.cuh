@@ -540,6 +540,85 @@ __global__ void __launch_bounds__(32) k_fq12_pow(const uint4* __restrict__ in, c
   store_fq12(out + 36 * (size_t)t, acc);
 }
 
+// ---- MIPP `compress` with the curve endomorphisms ---------------------------------------------------------------------
+// h_l + c_inv * h_r over 253-bit c_inv is a 253-step doubling chain per element and was the longest stage of a MIPP round
+// (12 ms for ONE element). On the order-r subgroup the twisted Frobenius psi(x, y) = (conj(x) g_2, conj(y) g_3),
+// g_i = u^(i (q-1)/6), acts as multiplication by x (the curve parameter; q = x mod r), and r < x^4: writing
+// k = k0 + k1 x + k2 x^2 + k3 x^3 with 0 <= k_i < x < 2^64 turns k P into a 4-way simultaneous multiplication with 64
+// doublings. PRECONDITION: the points lie in G2 (true for every CRS / folded-CRS vector the reference passes,
+// src/mipp.rs:43,114) -- outside the subgroup psi(P) != [x] P.
+// G1: phi(x, y) = (beta x, y) is multiplication by lambda = x^2 - 1 (127-bit halves, 127 doublings).
+
+// digits[0..3] = base-x digits of the canonical scalar (u64 each, as 8 u32 words); one thread
+__global__ void k_glv4_digits(const uint32_t* __restrict__ scaler, int mont, uint32_t* __restrict__ digits) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint32_t k[8];
+  for (int j = 0; j < 8; j++) k[j] = scaler[j];
+  if (mont) mont_to_canonical<FrParams>(k, k);
+  uint64_t q[4];
+  for (int j = 0; j < 4; j++) q[j] = (uint64_t)k[2 * j] | ((uint64_t)k[2 * j + 1] << 32);
+  for (int d = 0; d < 4; d++) {
+    uint64_t rem = 0, nq[4] = {0, 0, 0, 0};
+    for (int bit = 255; bit >= 0; bit--) {
+      const uint64_t top = rem >> 63;
+      rem = (rem << 1) | ((q[bit >> 6] >> (bit & 63)) & 1);
+      if (top || rem >= BLS_X) {
+        rem -= BLS_X;
+        nq[bit >> 6] |= 1ull << (bit & 63);
+      }
+    }
+    digits[2 * d] = (uint32_t)rem;
+    digits[2 * d + 1] = (uint32_t)(rem >> 32);
+    for (int j = 0; j < 4; j++) q[j] = nq[j];
+  }
+}
+
+__device__ __forceinline__ void g2_psi(Affine2& r, const Affine2& p) {
+  const Fq g2c = fq_from_table(FQ12_C(FROB1)[1][0]);   // u^(2 (q-1)/6), in Fq
+  const Fq g3c = fq_from_table(FQ12_C(FROB1)[2][0]);   // u^(3 (q-1)/6), in Fq
+  fq2_conj(r.x, p.x);
+  fq2_scale(r.x, r.x, g2c);
+  fq2_conj(r.y, p.y);
+  fq2_scale(r.y, r.y, g3c);
+}
+
+// a[i] <- a[i] + k * a[split + i], k given by its four base-x digits
+__global__ void __launch_bounds__(64) k_compress_g2_glv(uint4* __restrict__ a, uint32_t split,
+                                                        const uint32_t* __restrict__ digits) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= split) return;
+  uint64_t kd[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) kd[j] = (uint64_t)digits[2 * j] | ((uint64_t)digits[2 * j + 1] << 32);
+  Affine2 l, b[4];
+  load_affine2(l, a + 12 * (uint64_t)i);
+  load_affine2(b[0], a + 12 * ((uint64_t)split + i));
+  for (int j = 1; j < 4; j++) g2_psi(b[j], b[j - 1]);
+  Xyzz2 T[16];                       // T[m] = sum over the set bits j of m of psi^j(r)
+  xyzz2_set_inf(T[0]);
+  for (int m = 1; m < 16; m++) {
+    const int low = __ffs(m) - 1;
+    T[m] = T[m & (m - 1)];
+    xyzz2_madd_ni(&T[m], &b[low]);
+  }
+  Xyzz2 acc;
+  xyzz2_set_inf(acc);
+  bool started = false;
+  for (int bit = 63; bit >= 0; bit--) {
+    if (started) xyzz2_dbl_ni(&acc);
+    const int m = (int)((kd[0] >> bit) & 1) | ((int)((kd[1] >> bit) & 1) << 1) | ((int)((kd[2] >> bit) & 1) << 2) |
+                  ((int)((kd[3] >> bit) & 1) << 3);
+    if (m) {
+      xyzz2_add_ni(&acc, &T[m]);
+      started = true;
+    }
+  }
+  xyzz2_madd_ni(&acc, &l);
+  Affine2 o;
+  xyzz2_to_affine_ni(&o, &acc);
+  store_affine2(a + 12 * (uint64_t)i, o);
+}
+
 // test hook: one Fq12 operation per thread (tests/test_gpu_pairing.py drives every op against the oracle)
 //   0 mul(a,b)  1 sqr(a)  2 inv(a)  3 frobenius(a,1)  4 frobenius(a,2)  5 cyclotomic_sqr(a)  6 exp_by_x(a)
 //   7 final_exp(a)  8 mul_by_034(a; b = l0 || l3 || l4)  9 miller(a = G1 affine || G2 affine)
