@@ -14,6 +14,7 @@ void hc_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { mod_add<FqPa
 void hc_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { mod_sub<FqParams>(r, a, b); }
 void hc_fq_neg(const uint32_t* a, uint32_t* r) { mod_neg<FqParams>(r, a); }
 void hc_fq_inv(const uint32_t* a, uint32_t* r) { Fq x, y; memcpy(x.l, a, 48); fq_inv(y, x); memcpy(r, y.l, 48); }
+void hc_fq_inv_fermat(const uint32_t* a, uint32_t* r) { Fq x, y; memcpy(x.l, a, 48); fq_inv_fermat(y, x); memcpy(r, y.l, 48); }
 void hc_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul<FrParams>(r, a, b); }
 void hc_fr_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { mod_add<FrParams>(r, a, b); }
 void hc_fr_to_canonical(const uint32_t* a, uint32_t* r) { mont_to_canonical<FrParams>(r, a); }

@@ -59,8 +59,12 @@ def test_fq_arithmetic(hc):
         hc.hc_fq_add(P(w32(a, 12)), P(w32(b, 12)), P(out)); assert i32(out) == (a + b) % o.Q
         hc.hc_fq_sub(P(w32(a, 12)), P(w32(b, 12)), P(out)); assert i32(out) == (a - b) % o.Q
         hc.hc_fq_neg(P(w32(a, 12)), P(out)); assert i32(out) == (-a) % o.Q
-    for a in edge[1:] + vals[20:30]:
+    out2 = np.zeros(12, np.uint32)
+    for a in edge[1:] + vals[20:60] + [1, 2, o.Q - 1, o.FQ_R, (o.Q + 1) // 2]:
+        # binary extended Euclid (fq_inv) against its definition and against the Fermat ladder it replaced
         hc.hc_fq_inv(P(w32(a, 12)), P(out)); assert i32(out) * a % o.Q == o.FQ_R * o.FQ_R % o.Q
+        hc.hc_fq_inv_fermat(P(w32(a, 12)), P(out2)); assert np.array_equal(out, out2)
+    hc.hc_fq_inv(P(w32(0, 12)), P(out)); assert i32(out) == 0
 
 
 def test_fr_arithmetic(hc):

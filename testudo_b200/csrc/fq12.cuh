@@ -411,18 +411,6 @@ struct G2Hom {  // homogeneous projective point on the twist (ark `G2HomProjecti
   Fq2 x, y, z;
 };
 
-// r = a / 2 (mod q): (a + (a odd ? q : 0)) >> 1; the same map in Montgomery form
-TB_HD void fq_halve(Fq& r, const Fq& a) {
-  const uint32_t mask = 0u - (a.l[0] & 1u);
-  uint32_t t[12];
-  Carry c;
-  t[0] = add_cc(a.l[0], FqParams::p(0) & mask, c);
-#pragma unroll
-  for (int i = 1; i < 12; i++) t[i] = addc_cc(a.l[i], FqParams::p(i) & mask, c);
-#pragma unroll
-  for (int i = 0; i < 11; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
-  r.l[11] = t[11] >> 1;
-}
 // (0 + b1 u) * t with B' = (0, b1) the twist coefficient: -5 b1 t1 + b1 t0 u
 TB_HD void fq2_mul_twist_b(Fq2& e, const Fq2& t) {
   const Fq b1 = fq_from_table(FQ12_C(TWIST_B1));

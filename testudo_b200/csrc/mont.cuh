@@ -629,8 +629,9 @@ TB_HD Fq fq_one() {
   return r;
 }
 
-// a^(q-2) by square-and-multiply over the fixed exponent (to-affine conversions only; not on the hot loop)
-TB_HD void fq_inv(Fq& r, const Fq& a) {
+// a^(q-2) by square-and-multiply over the fixed exponent: 377 squarings + ~190 products, a ~400 000-instruction
+// dependent chain. Kept as the cross-check of fq_inv (tests/test_host_logic.py, tb200_test_fq_inv).
+TB_HD void fq_inv_fermat(Fq& r, const Fq& a) {
   // q - 2: limb 0 of q is 1 -> 0xffffffff with a borrow into limb 1
   Fq acc = fq_one();
   bool started = false;
@@ -650,6 +651,83 @@ TB_HD void fq_inv(Fq& r, const Fq& a) {
     }
   }
   r = acc;
+}
+
+// r = a / 2 (mod q): (a + (a odd ? q : 0)) >> 1
+TB_HD void fq_halve(Fq& r, const Fq& a) {
+  const uint32_t mask = 0u - (a.l[0] & 1u);
+  uint32_t t[12];
+  Carry c;
+  t[0] = add_cc(a.l[0], FqParams::p(0) & mask, c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) t[i] = addc_cc(a.l[i], FqParams::p(i) & mask, c);
+#pragma unroll
+  for (int i = 0; i < 11; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
+  r.l[11] = t[11] >> 1;
+}
+TB_HD void fq_shr1(Fq& a) {
+#pragma unroll
+  for (int i = 0; i < 11; i++) a.l[i] = (a.l[i] >> 1) | (a.l[i + 1] << 31);
+  a.l[11] >>= 1;
+}
+TB_HD bool fq_is_one_int(const Fq& a) {  // the INTEGER 1 (not the Montgomery one)
+  uint32_t nz = a.l[0] ^ 1u;
+#pragma unroll
+  for (int i = 1; i < 12; i++) nz |= a.l[i];
+  return nz == 0;
+}
+// plain 12-limb a >= b
+TB_HD bool fq_geq(const Fq& a, const Fq& b) {
+  Carry c;
+  (void)sub_cc(a.l[0], b.l[0], c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) (void)subc_cc(a.l[i], b.l[i], c);
+  return subc_mask(c) == 0;
+}
+TB_HD void fq_sub_plain(Fq& r, const Fq& a, const Fq& b) {  // a - b for a >= b, no modular wrap
+  Carry c;
+  r.l[0] = sub_cc(a.l[0], b.l[0], c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) r.l[i] = subc_cc(a.l[i], b.l[i], c);
+}
+
+// Inversion by the binary extended Euclidean algorithm (~2 x 377 iterations of 12-limb shifts / subtractions, ~10x fewer
+// instructions than the Fermat ladder above): every latency-bound tail of the engine ends in one of these (to-affine of
+// an MSM result, of every folded MIPP element, the final exponentiation's Fq12 inverse). Input and output in Montgomery
+// form: for X = a R the loop yields X^-1 = a^-1 R^-1 as an integer; one Montgomery product with R^3 restores a^-1 R.
+// 0 -> 0 (as the ladder).
+TB_HD void fq_inv(Fq& r, const Fq& a) {
+  if (fq_is_zero(a)) {
+    r = fq_zero();
+    return;
+  }
+  Fq u = a, v, x1 = fq_zero(), x2 = fq_zero();
+#pragma unroll
+  for (int i = 0; i < 12; i++) v.l[i] = FqParams::p(i);
+  x1.l[0] = 1;
+  while (!fq_is_one_int(u) && !fq_is_one_int(v)) {
+    while ((u.l[0] & 1u) == 0) {
+      fq_shr1(u);
+      fq_halve(x1, x1);
+    }
+    while ((v.l[0] & 1u) == 0) {
+      fq_shr1(v);
+      fq_halve(x2, x2);
+    }
+    if (fq_geq(u, v)) {
+      fq_sub_plain(u, u, v);
+      fq_sub(x1, x1, x2);
+    } else {
+      fq_sub_plain(v, v, u);
+      fq_sub(x2, x2, x1);
+    }
+  }
+  const Fq res = fq_is_one_int(u) ? x1 : x2;
+  Fq r2, r3;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r2.l[i] = FqParams::r2(i);
+  fq_mul(r3, r2, r2);       // R^2 R^2 R^-1 = R^3
+  fq_mul(r, res, r3);       // a^-1 R^-1 R^3 R^-1 = a^-1 R
 }
 
 }  // namespace tb
