@@ -1237,20 +1237,20 @@ static int pairing_products_locked(const uint4* d_g1, const uint4* d_g2, uint32_
   if (mark(st, "begin")) return 1;
   // below ~2 waves of resident warps one WARP per pair (latency 10 -> ~3 ms); above, one thread per pair
   const bool coop = n <= (uint32_t)g.pairing_coop_max;
-  if (coop) LAUNCH(k_miller_coop, n, 32, st, d_g1, d_g2, xor_mask, buf_a);
+  if (coop) LAUNCH(k_miller_coop, n, W12_THREADS, st, d_g1, d_g2, xor_mask, buf_a);
   else LAUNCH(k_miller, cdiv(n, 32), 32, st, d_g1, d_g2, n, xor_mask, buf_a);
   if (after_miller) CU(cudaEventRecord(after_miller, st));
   if (mark(st, "miller")) return 1;
   uint4 *cur = buf_a, *nxt = buf_b;
   while (len > 1) {
     const uint32_t m = cdiv(len, FQ12_FAN);
-    if ((uint64_t)m * segs <= 4096) LAUNCH(k_fq12_prod_level_coop, dim3(m, segs), 32, st, cur, len, m, nxt);
+    if ((uint64_t)m * segs <= 4096) LAUNCH(k_fq12_prod_level_coop, dim3(m, segs), W12_THREADS, st, cur, len, m, nxt);
     else LAUNCH(k_fq12_prod_level, dim3(cdiv(m, 32), segs), 32, st, cur, len, m, nxt);
     std::swap(cur, nxt);
     len = m;
   }
   if (mark(st, "gt_product")) return 1;
-  LAUNCH(k_final_exp, segs, 32, st, cur, d_out);
+  LAUNCH(k_final_exp, segs, W12_THREADS, st, cur, d_out);
   if (mark(st, "final_exp")) return 1;
   CU(cudaFreeAsync(buf_a, st));
   CU(cudaFreeAsync(buf_b, st));
@@ -1695,7 +1695,7 @@ int tb200_test_fq12_op(int op, const uint64_t* a, const uint64_t* b, size_t n, u
   CU(cudaSetDevice(g.device));
   return with_buffers(a, n * 576, b, n * 576, out, n * 576, nullptr, 0, [&](char* da, char* db, char* d1, char*) {
     if (op >= 20 && op < 100)
-      LAUNCH(k_test_w12_op, (uint32_t)n, 32, g.stream, op, (const uint4*)da, (const uint4*)db, (uint4*)d1);
+      LAUNCH(k_test_w12_op, (uint32_t)n, W12_THREADS, g.stream, op, (const uint4*)da, (const uint4*)db, (uint4*)d1);
     else
       LAUNCH(k_test_fq12_op, cdiv(n, 32), 32, g.stream, op, (const uint4*)da, (const uint4*)db, (uint32_t)n, (uint4*)d1);
     return 0;

@@ -71,211 +71,279 @@ __global__ void __launch_bounds__(32) k_fq12_prod_level(const uint4* __restrict_
   store_fq12(out + 36 * ((size_t)blockIdx.y * m + t), acc);
 }
 
-// ---- warp-cooperative Fq12 arithmetic --------------------------------------------------------------------------------
+// ---- block-cooperative Fq12 arithmetic (two warps, one Fq product per lane) ------------------------------------------------
 // A final exponentiation is ONE dependent chain of ~315 cyclotomic squarings and ~45 Fq12 products; run by a single
-// thread it took 20 ms (31 idle lanes, every Fq2 product in sequence). Here one WARP owns the chain: the Fq12 values live
-// in shared memory and the 18 (12, 6) independent Fq2 products inside every Fq12 product (squaring, cyclotomic squaring)
-// run on 18 lanes at once; the cheap linear recombinations are spread over lanes the same way. Phases are separated by
-// __syncwarp(). All pointers are shared-memory objects of the calling warp; dst may alias the inputs.
+// thread it took 20 ms (31 idle lanes, every product in sequence). Here a 64-thread CTA owns the chain: the Fq12 values
+// live in shared memory and the 54 (36, 18) independent Fq products inside every Karatsuba Fq12 product (complex squaring,
+// Granger-Scott squaring) run on 54 lanes at once -- one 276-MAC Montgomery product per lane; the linear recombinations
+// are spread the same way, one Fq coefficient per lane. (First version: one Fq2 product = three interleaved Fq products
+// per lane, 18 lanes of one warp: ncu showed one instruction per 3.9 cycles, `wait` the only stall, ~5 200 instructions on
+// the critical lane per Fq12 product; per-Fq lanes cut that to ~1 700.) Phases are separated by __syncthreads(); every
+// function must be called by all 64 threads of the CTA. Pointers are shared-memory objects; dst may alias the inputs.
+constexpr int W12_THREADS = 64;
+#define W12_SYNC() __syncthreads()
 struct WScratch {
-  Fq2 xy[2][3][3];   // materialised Fq6 operands X_i, Y_i (i < 3) of up to three Fq6 products
-  Fq2 prod[18];      // Karatsuba products: [i][j], j = 0..5 -> a0b0, a1b1, a2b2, (a1+a2)(b1+b2), (a0+a1)(b0+b1), (a0+a2)(b0+b2)
-  Fq2 r6[3][3];      // the three Fq6 results
+  Fq xy[2][3][3][2];   // materialised Fq6 operands X_i, Y_i (i < 3) of up to three Fq6 products, [t][c] = Fq2 coefficient t, part c
+  Fq kar[54];          // [product 0..17][a0 b0, a1 b1, (a0 + a1)(b0 + b1)]
+  Fq prod[18][2];      // Fq2 products: [i][j], j = 0..5 -> x0y0, x1y1, x2y2, (x1+x2)(y1+y2), (x0+x1)(y0+y1), (x0+x2)(y0+y2)
+  Fq r6[3][3][2];      // the three Fq6 results
 };
+__device__ __forceinline__ Fq* w12_q(Fq12* a) { return reinterpret_cast<Fq*>(a); }              // [2 * slot + c]
+__device__ __forceinline__ const Fq* w12_q(const Fq12* a) { return reinterpret_cast<const Fq*>(a); }
 __device__ __forceinline__ Fq2* w12_c(Fq12* a, int idx) { return reinterpret_cast<Fq2*>(a) + idx; }
 __device__ __forceinline__ const Fq2* w12_c(const Fq12* a, int idx) { return reinterpret_cast<const Fq2*>(a) + idx; }
+__device__ __forceinline__ void fq_mul5_neg(Fq& r, const Fq& a) {   // -5 a
+  Fq t;
+  fq_mul5(t, a);
+  fq_neg(r, t);
+}
+// lane `part` of the Karatsuba split of the Fq2 value v: c0, c1 or c0 + c1
+__device__ __forceinline__ void w_kar_operand(Fq& o, const Fq* v0, const Fq* v1, bool two, int part) {
+  if (part < 2) {
+    o = v0[part];
+    if (two) fq_add(o, o, v1[part]);
+  } else {
+    fq_add(o, v0[0], v0[1]);
+    if (two) {
+      fq_add(o, o, v1[0]);
+      fq_add(o, o, v1[1]);
+    }
+  }
+}
+// kar[3 pr + 0..2] -> the Fq2 product pr, coefficient c:  c0 = v0 - 5 v1,  c1 = m - v0 - v1
+__device__ __forceinline__ void w_fq2_from_kar(Fq& o, const Fq* kar, int c) {
+  if (c == 0) {
+    Fq t;
+    fq_mul5(t, kar[1]);
+    fq_sub(o, kar[0], t);
+  } else {
+    fq_sub(o, kar[2], kar[0]);
+    fq_sub(o, o, kar[1]);
+  }
+}
 
-// phases 1-2 of every product: lane (i, j) multiplies the Karatsuba operands of Fq6 product i; lane (i, t) then
-// assembles coefficient t of result i. `count` = number of Fq6 products (1..3).
+// phases 1-3 of every product: 18 * count lanes multiply, 12 * count lanes assemble the Fq2 products, 6 * count lanes
+// assemble coefficient (t, c) of Fq6 result i. `count` = number of Fq6 products (1..3).
 __device__ __noinline__ void w_fq6_products(WScratch* w, int count) {
-  const int lane = threadIdx.x & 31;
-  __syncwarp();
-  if (lane < 6 * count) {
-    const int i = lane / 6, j = lane % 6;
+  const int tid = threadIdx.x;
+  W12_SYNC();
+  if (tid < 18 * count) {
+    const int pr = tid / 3, part = tid % 3, i = pr / 6, j = pr % 6;
     const int t0 = (j < 3) ? j : (j == 3 ? 1 : 0);
     const int t1 = (j == 4) ? 1 : 2;
-    Fq2 a = w->xy[0][i][t0], b = w->xy[1][i][t0];
-    if (j >= 3) {
-      fq2_add(a, a, w->xy[0][i][t1]);
-      fq2_add(b, b, w->xy[1][i][t1]);
-    }
-    fq2_mul_ol(&w->prod[lane], &a, &b);
+    Fq a, b;
+    w_kar_operand(a, w->xy[0][i][t0], w->xy[0][i][t1], j >= 3, part);
+    w_kar_operand(b, w->xy[1][i][t0], w->xy[1][i][t1], j >= 3, part);
+    fq_mul_ol(&w->kar[tid], &a, &b);
   }
-  __syncwarp();
-  if (lane < 3 * count) {
-    const int i = lane / 3, t = lane % 3;
-    const Fq2* p = &w->prod[6 * i];
-    Fq2 r, m;
-    if (t == 0) {          // v0 + xi (m12 - v1 - v2)
-      fq2_sub(m, p[3], p[1]);
-      fq2_sub(m, m, p[2]);
-      fq2_mul_xi(m, m);
-      fq2_add(r, p[0], m);
+  W12_SYNC();
+  if (tid < 12 * count) {
+    Fq o;
+    w_fq2_from_kar(o, &w->kar[3 * (tid / 2)], tid & 1);
+    w->prod[tid / 2][tid & 1] = o;
+  }
+  W12_SYNC();
+  if (tid < 6 * count) {
+    const int i = tid / 6, t = (tid % 6) / 2, c = tid & 1;
+    const Fq(*p)[2] = &w->prod[6 * i];
+    Fq r, m;
+    if (t == 0) {          // v0 + xi (m12 - v1 - v2);  (xi z).c0 = -5 z.c1, (xi z).c1 = z.c0
+      fq_sub(m, p[3][1 - c], p[1][1 - c]);
+      fq_sub(m, m, p[2][1 - c]);
+      if (c == 0) fq_mul5_neg(m, m);
+      fq_add(r, p[0][c], m);
     } else if (t == 1) {   // m01 - v0 - v1 + xi v2
-      fq2_sub(r, p[4], p[0]);
-      fq2_sub(r, r, p[1]);
-      fq2_mul_xi(m, p[2]);
-      fq2_add(r, r, m);
+      fq_sub(r, p[4][c], p[0][c]);
+      fq_sub(r, r, p[1][c]);
+      if (c == 0) fq_mul5_neg(m, p[2][1]);
+      else m = p[2][0];
+      fq_add(r, r, m);
     } else {               // m02 - v0 - v2 + v1
-      fq2_sub(r, p[5], p[0]);
-      fq2_sub(r, r, p[2]);
-      fq2_add(r, r, p[1]);
+      fq_sub(r, p[5][c], p[0][c]);
+      fq_sub(r, r, p[2][c]);
+      fq_add(r, r, p[1][c]);
     }
-    w->r6[i][t] = r;
+    w->r6[i][t][c] = r;
   }
-  __syncwarp();
+  W12_SYNC();
+}
+// coefficient (t, c) of v * R for an Fq6 value R[3][2]: v (x0, x1, x2) = (xi x2, x0, x1)
+__device__ __forceinline__ void w_mul_v_coeff(Fq& o, const Fq (*R)[2], int t, int c) {
+  if (t > 0) o = R[t - 1][c];
+  else if (c == 0) fq_mul5_neg(o, R[2][1]);
+  else o = R[2][0];
 }
 
 // dst = a * b: X = {a0, a1, a0 + a1}, Y = {b0, b1, b0 + b1}; C0 = R0 + v R1, C1 = R2 - R0 - R1
 __device__ __noinline__ void w12_mul(Fq12* dst, const Fq12* a, const Fq12* b, WScratch* w) {
-  const int lane = threadIdx.x & 31;
-  __syncwarp();
-  if (lane < 18) {
-    const int which = lane / 9, i = (lane % 9) / 3, t = lane % 3;
-    const Fq12* src = which ? b : a;
-    Fq2 v;
-    if (i < 2) v = *w12_c(src, 3 * i + t);
-    else fq2_add(v, *w12_c(src, t), *w12_c(src, 3 + t));
-    w->xy[which][i][t] = v;
+  const int tid = threadIdx.x;
+  W12_SYNC();
+  if (tid < 36) {
+    const int which = tid / 18, rem = tid % 18, i = rem / 6, t = (rem % 6) / 2, c = rem & 1;
+    const Fq* src = w12_q(which ? b : a);
+    Fq v;
+    if (i < 2) v = src[2 * (3 * i + t) + c];
+    else fq_add(v, src[2 * t + c], src[2 * (3 + t) + c]);
+    w->xy[which][i][t][c] = v;
   }
   w_fq6_products(w, 3);
-  if (lane < 6) {
-    Fq2 r;
-    if (lane < 3) {        // C0.c[t] = R0[t] + (v R1)[t], v (x0, x1, x2) = (xi x2, x0, x1)
-      Fq2 m = w->r6[1][(lane + 2) % 3];
-      if (lane == 0) fq2_mul_xi(m, m);
-      fq2_add(r, w->r6[0][lane], m);
+  if (tid < 12) {
+    const int slot = tid / 2, c = tid & 1;
+    Fq r, m;
+    if (slot < 3) {
+      w_mul_v_coeff(m, w->r6[1], slot, c);
+      fq_add(r, w->r6[0][slot][c], m);
     } else {
-      const int t = lane - 3;
-      fq2_sub(r, w->r6[2][t], w->r6[0][t]);
-      fq2_sub(r, r, w->r6[1][t]);
+      fq_sub(r, w->r6[2][slot - 3][c], w->r6[0][slot - 3][c]);
+      fq_sub(r, r, w->r6[1][slot - 3][c]);
     }
-    *w12_c(dst, lane) = r;
+    w12_q(dst)[tid] = r;
   }
-  __syncwarp();
+  W12_SYNC();
 }
 
 // dst = a^2 (complex squaring): R0 = a0 a1, R1 = (a0 + a1)(a0 + v a1); C0 = R1 - R0 - v R0, C1 = 2 R0
 __device__ __noinline__ void w12_sqr(Fq12* dst, const Fq12* a, WScratch* w) {
-  const int lane = threadIdx.x & 31;
-  __syncwarp();
-  if (lane < 12) {
-    const int which = lane / 6, i = (lane % 6) / 3, t = lane % 3;
-    Fq2 v;
-    if (i == 0) v = *w12_c(a, 3 * which + t);                   // X0 = a0, Y0 = a1
-    else if (which == 0) fq2_add(v, *w12_c(a, t), *w12_c(a, 3 + t));   // X1 = a0 + a1
-    else {                                                      // Y1 = a0 + v a1
-      Fq2 m = *w12_c(a, 3 + (t + 2) % 3);
-      if (t == 0) fq2_mul_xi(m, m);
-      fq2_add(v, *w12_c(a, t), m);
+  const int tid = threadIdx.x;
+  W12_SYNC();
+  if (tid < 24) {
+    const int which = tid / 12, rem = tid % 12, i = rem / 6, t = (rem % 6) / 2, c = rem & 1;
+    const Fq* src = w12_q(a);
+    Fq v;
+    if (i == 0) v = src[2 * (3 * which + t) + c];                            // X0 = a0, Y0 = a1
+    else if (which == 0) fq_add(v, src[2 * t + c], src[2 * (3 + t) + c]);    // X1 = a0 + a1
+    else {                                                                   // Y1 = a0 + v a1
+      Fq m;
+      w_mul_v_coeff(m, reinterpret_cast<const Fq(*)[2]>(src + 6), t, c);
+      fq_add(v, src[2 * t + c], m);
     }
-    w->xy[which][i][t] = v;
+    w->xy[which][i][t][c] = v;
   }
   w_fq6_products(w, 2);
-  if (lane < 6) {
-    Fq2 r;
-    if (lane < 3) {
-      Fq2 m = w->r6[0][(lane + 2) % 3];
-      if (lane == 0) fq2_mul_xi(m, m);
-      fq2_sub(r, w->r6[1][lane], w->r6[0][lane]);
-      fq2_sub(r, r, m);
+  if (tid < 12) {
+    const int slot = tid / 2, c = tid & 1;
+    Fq r, m;
+    if (slot < 3) {
+      w_mul_v_coeff(m, w->r6[0], slot, c);
+      fq_sub(r, w->r6[1][slot][c], w->r6[0][slot][c]);
+      fq_sub(r, r, m);
     } else {
-      fq2_dbl(r, w->r6[0][lane - 3]);
+      fq_dbl(r, w->r6[0][slot - 3][c]);
     }
-    *w12_c(dst, lane) = r;
+    w12_q(dst)[tid] = r;
   }
-  __syncwarp();
+  W12_SYNC();
 }
 
-// dst = a^2 for a unitary a (Granger-Scott, as fq12_cyclotomic_sqr_ol): six Fq2 products on six lanes.
+// dst = a^2 for a unitary a (Granger-Scott, as fq12_cyclotomic_sqr_ol): six Fq2 products = 18 Fq products on 18 lanes.
 // tower slot of z_k: z0 = c[0], z1 = c[4], z2 = c[3], z3 = c[2], z4 = c[1], z5 = c[5]
 __device__ __noinline__ void w12_cyclotomic_sqr(Fq12* dst, const Fq12* a, WScratch* w) {
-  const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
   constexpr int slot[6] = {0, 4, 3, 2, 1, 5};
-  __syncwarp();
-  if (lane < 6) {
-    const int p = lane >> 1;
-    const Fq2 za = *w12_c(a, slot[2 * p]), zb = *w12_c(a, slot[2 * p + 1]);
-    if ((lane & 1) == 0) fq2_mul_ol(&w->prod[lane], &za, &zb);          // tmp = za zb
-    else {
-      Fq2 s, m;
-      fq2_add(s, za, zb);
-      fq2_mul_xi(m, zb);
-      fq2_add(m, m, za);
-      fq2_mul_ol(&w->prod[lane], &s, &m);                               // (za + zb)(za + xi zb)
+  W12_SYNC();
+  if (tid < 18) {
+    const int l = tid / 3, part = tid % 3, p = l >> 1;
+    const Fq* za = w12_q(a) + 2 * slot[2 * p];
+    const Fq* zb = w12_q(a) + 2 * slot[2 * p + 1];
+    Fq x, y;
+    if ((l & 1) == 0) {                         // tmp = za zb
+      w_kar_operand(x, za, za, false, part);
+      w_kar_operand(y, zb, zb, false, part);
+    } else {                                    // (za + zb)(za + xi zb)
+      w_kar_operand(x, za, zb, true, part);
+      Fq B[2], m;
+      fq_mul5_neg(m, zb[1]);
+      fq_add(B[0], za[0], m);
+      fq_add(B[1], za[1], zb[0]);
+      w_kar_operand(y, B, B, false, part);
     }
+    fq_mul_ol(&w->kar[tid], &x, &y);
   }
-  __syncwarp();
-  if (lane < 6) {
+  W12_SYNC();
+  if (tid < 12) {
+    Fq o;
+    w_fq2_from_kar(o, &w->kar[3 * (tid / 2)], tid & 1);
+    w->prod[tid / 2][tid & 1] = o;
+  }
+  W12_SYNC();
+  if (tid < 12) {
     // z_k' = 3 t - 2 z_k (k = 0, 3, 4) or 3 t + 2 z_k (k = 1, 2, 5), with t = t0, t1, xi t5, t4, t2, t3 for k = 0..5 where
     // t_{2p} = prod[2p+1] - tmp - xi tmp and t_{2p+1} = 2 tmp (tmp = prod[2p])
     constexpr int tsel[6] = {0, 1, 5, 4, 2, 3};
-    const int ti = tsel[lane], p = ti >> 1;
-    Fq2 t, m;
-    if ((ti & 1) == 0) {
-      fq2_sub(t, w->prod[2 * p + 1], w->prod[2 * p]);
-      fq2_mul_xi(m, w->prod[2 * p]);
-      fq2_sub(t, t, m);
+    const int k = tid / 2, c = tid & 1;
+    const int ti = tsel[k], p = ti >> 1;
+    // coefficient cc of t_{ti}
+    auto tcoef = [&](Fq& o, int cc) {
+      if ((ti & 1) == 0) {
+        Fq m;
+        fq_sub(o, w->prod[2 * p + 1][cc], w->prod[2 * p][cc]);
+        if (cc == 0) fq_mul5_neg(m, w->prod[2 * p][1]);
+        else m = w->prod[2 * p][0];
+        fq_sub(o, o, m);
+      } else {
+        fq_dbl(o, w->prod[2 * p][cc]);
+      }
+    };
+    Fq t;
+    if (k == 2) {                               // xi t5
+      Fq u;
+      tcoef(u, 1 - c);
+      if (c == 0) fq_mul5_neg(t, u);
+      else t = u;
     } else {
-      fq2_dbl(t, w->prod[2 * p]);
+      tcoef(t, c);
     }
-    if (lane == 2) fq2_mul_xi(t, t);
-    const Fq2 z = *w12_c(a, slot[lane]);
-    Fq2 o;
-    if (lane == 0 || lane == 3 || lane == 4) fq2_sub(o, t, z);
-    else fq2_add(o, t, z);
-    fq2_dbl(o, o);
-    fq2_add(o, o, t);
-    *w12_c(dst, slot[lane]) = o;   // each lane rewrites only the slot it read in this phase: dst may alias a
+    const Fq z = w12_q(a)[2 * slot[k] + c];
+    Fq o;
+    if (k == 0 || k == 3 || k == 4) fq_sub(o, t, z);
+    else fq_add(o, t, z);
+    fq_dbl(o, o);
+    fq_add(o, o, t);
+    w12_q(dst)[2 * slot[k] + c] = o;            // each lane rewrites only the coefficient it read: dst may alias a
   }
-  __syncwarp();
+  W12_SYNC();
 }
 
 __device__ __forceinline__ void w12_copy(Fq12* dst, const Fq12* a) {
-  const int lane = threadIdx.x & 31;
-  __syncwarp();
-  Fq2 v;
-  if (lane < 6) v = *w12_c(a, lane);
-  __syncwarp();
-  if (lane < 6) *w12_c(dst, lane) = v;
-  __syncwarp();
+  const int tid = threadIdx.x;
+  W12_SYNC();
+  Fq v;
+  if (tid < 12) v = w12_q(a)[tid];
+  W12_SYNC();
+  if (tid < 12) w12_q(dst)[tid] = v;
+  W12_SYNC();
 }
 __device__ __forceinline__ void w12_conj(Fq12* dst, const Fq12* a) {
-  const int lane = threadIdx.x & 31;
-  __syncwarp();
-  Fq2 v;
-  if (lane < 6) {
-    v = *w12_c(a, lane);
-    if (lane >= 3) fq2_neg(v, v);
+  const int tid = threadIdx.x;
+  W12_SYNC();
+  Fq v;
+  if (tid < 12) {
+    v = w12_q(a)[tid];
+    if (tid >= 6) fq_neg(v, v);
   }
-  __syncwarp();
-  if (lane < 6) *w12_c(dst, lane) = v;
-  __syncwarp();
+  W12_SYNC();
+  if (tid < 12) w12_q(dst)[tid] = v;
+  W12_SYNC();
 }
-// a^(q^k), k = 1, 2: tower slot idx holds the coefficient of w^e, e = 2 idx (idx < 3) or 2 (idx - 3) + 1
+// a^(q^k), k = 1, 2: tower slot idx holds the coefficient of w^e, e = 2 idx (idx < 3) or 2 (idx - 3) + 1; every
+// Frobenius coefficient u^(e (q^k - 1)/6) lies in Fq (tests/test_oracle_pairing.py), so this is 12 independent Fq products
 __device__ __noinline__ void w12_frobenius(Fq12* dst, const Fq12* a, int k) {
-  const int lane = threadIdx.x & 31;
-  __syncwarp();
-  Fq2 c;
-  if (lane < 6) {
-    const int e = lane < 3 ? 2 * lane : 2 * (lane - 3) + 1;
-    c = *w12_c(a, lane);
-    if (k == 1) fq2_conj(c, c);
+  const int tid = threadIdx.x;
+  W12_SYNC();
+  Fq c;
+  if (tid < 12) {
+    const int sl = tid / 2;
+    const int e = sl < 3 ? 2 * sl : 2 * (sl - 3) + 1;
+    c = w12_q(a)[tid];
+    if (k == 1 && (tid & 1)) fq_neg(c, c);
     if (e > 0) {
-      if (k == 1) {
-        Fq2 g;
-        g.c0 = fq_from_table(FQ12_C(FROB1)[e - 1][0]);
-        g.c1 = fq_from_table(FQ12_C(FROB1)[e - 1][1]);
-        fq2_mul_ol(&c, &c, &g);
-      } else {
-        const Fq g = fq_from_table(FQ12_C(FROB2)[e - 1]);
-        fq2_scale(c, c, g);
-      }
+      const Fq g = fq_from_table(k == 1 ? FQ12_C(FROB1)[e - 1][0] : FQ12_C(FROB2)[e - 1]);
+      fq_mul_ol(&c, &c, &g);
     }
   }
-  __syncwarp();
-  if (lane < 6) *w12_c(dst, lane) = c;
-  __syncwarp();
+  W12_SYNC();
+  if (tid < 12) w12_q(dst)[tid] = c;
+  W12_SYNC();
 }
 __device__ __noinline__ void w12_exp_by_x(Fq12* dst, const Fq12* a, Fq12* acc, WScratch* w) {
   w12_copy(acc, a);
@@ -291,13 +359,12 @@ struct WFinalExp {
   WScratch w;
 };
 
-// the chain of fq12_final_exp_ol (ark `final_exponentiation`), one warp; s->f holds the input, the result lands in s->r
+// the chain of fq12_final_exp_ol (ark `final_exponentiation`), one CTA; s->f holds the input, the result lands in s->r
 __device__ __noinline__ void w12_final_exp(WFinalExp* s) {
-  const int lane = threadIdx.x & 31;
   WScratch* w = &s->w;
   w12_conj(&s->r, &s->f);
-  if (lane == 0) fq12_inv_ol(&s->f2, &s->f);      // one inversion per product: a lone Fq inversion dominates it
-  __syncwarp();
+  if (threadIdx.x == 0) fq12_inv_ol(&s->f2, &s->f);      // one inversion per product
+  W12_SYNC();
   w12_mul(&s->r, &s->r, &s->f2, w);
   w12_copy(&s->f2, &s->r);
   w12_frobenius(&s->r, &s->r, 2);
@@ -332,96 +399,167 @@ struct WMiller {
   G2Hom r;
   Affine2 q;
   Affine p;
-  Fq2 t[6];
+  Fq kar[16];        // Fq products of the doubling step
+  Fq v[11][2];       // its Fq2 intermediates (a, b, c, (y+z)^2, j, e, d, g, h, -h, 3j)
   WScratch w;
 };
 
-// ark `double_in_place` (see g2_double_line) on parallel lanes; updates s->r and the line slots of s->line
+// ark `double_in_place` (see g2_double_line) on parallel lanes; updates s->r and the line coefficients in s->line.
+// SIMT rule that shaped it: lanes of a warp that take DIFFERENT branches run one after the other, so a first version with
+// one Fq2 product per lane in lane-specific branches took 44 us per step. Here every expensive operation (the Montgomery
+// products) is ONE uniform call whose operands were selected per lane beforehand; only cheap additions sit in
+// lane-specific branches. Three rounds of products: {x y, y^2, z^2, (y+z)^2, x^2} (11 Fq products), the twist
+// coefficient, {a (b-3e), g^2, e^2, b h, -h py, 3j px} (14 Fq products). Squarings use (v0 + v1)(v0 - 5 v1), v0 v1.
+__device__ __forceinline__ void w_sqr_asm(Fq& o, const Fq& s0, const Fq& s1, int c) {   // (s0 + 4 s1, 2 s1)
+  Fq t;
+  fq_dbl(t, s1);
+  if (c == 0) {
+    fq_dbl(t, t);
+    fq_add(o, s0, t);
+  } else {
+    o = t;
+  }
+}
+__device__ __forceinline__ void w_sqr_operands(Fq& a, Fq& b, const Fq* v, int which) {   // which: 0 -> s0, 1 -> s1
+  if (which == 0) {
+    Fq t;
+    fq_add(a, v[0], v[1]);
+    fq_mul5(t, v[1]);
+    fq_sub(b, v[0], t);
+  } else {
+    a = v[0];
+    b = v[1];
+  }
+}
 __device__ __noinline__ void w_double_step(WMiller* s) {
-  const int lane = threadIdx.x & 31;
-  __syncwarp();
-  if (lane < 5) {
-    Fq2 o;
-    if (lane == 0) {                       // a = x y / 2
-      fq2_mul_ol(&o, &s->r.x, &s->r.y);
-      fq_halve(o.c0, o.c0);
-      fq_halve(o.c1, o.c1);
-      s->t[0] = o;
-    } else if (lane == 1) {                // b = y^2
-      fq2_sqr_ol(&o, &s->r.y);
-      s->t[1] = o;
-    } else if (lane == 2) {                // c = z^2, e = B' 3 c
-      Fq2 c, t3;
-      fq2_sqr_ol(&c, &s->r.z);
-      fq2_dbl(t3, c);
-      fq2_add(t3, t3, c);
-      fq2_mul_twist_b(o, t3);
-      s->t[2] = c;
-      s->t[3] = o;
-    } else if (lane == 3) {                // (y + z)^2
-      Fq2 yz;
-      fq2_add(yz, s->r.y, s->r.z);
-      fq2_sqr_ol(&o, &yz);
-      s->t[4] = o;
-    } else {                               // j = x^2
-      fq2_sqr_ol(&o, &s->r.x);
-      s->t[5] = o;
-    }
-  }
-  __syncwarp();
-  Fq2 out;
-  if (lane < 6) {
-    const Fq2 b = s->t[1], e = s->t[3];
-    if (lane == 0) {                       // x' = a (b - 3 e)
-      Fq2 f3, d;
-      fq2_dbl(f3, e);
-      fq2_add(f3, f3, e);
-      fq2_sub(d, b, f3);
-      fq2_mul_ol(&out, &s->t[0], &d);
-    } else if (lane == 1) {                // y' = ((b + 3 e) / 2)^2 - 3 e^2
-      Fq2 f3, g, e2, t3;
-      fq2_dbl(f3, e);
-      fq2_add(f3, f3, e);
-      fq2_add(g, b, f3);
-      fq_halve(g.c0, g.c0);
-      fq_halve(g.c1, g.c1);
-      fq2_sqr_ol(&g, &g);
-      fq2_sqr_ol(&e2, &e);
-      fq2_dbl(t3, e2);
-      fq2_add(t3, t3, e2);
-      fq2_sub(out, g, t3);
-    } else if (lane == 2 || lane == 3) {   // h = (y + z)^2 - (b + c);  z' = b h;  l0 = -h py
-      Fq2 h, bc;
-      fq2_add(bc, b, s->t[2]);
-      fq2_sub(h, s->t[4], bc);
-      if (lane == 2) fq2_mul_ol(&out, &b, &h);
-      else {
-        fq2_neg(h, h);
-        fq2_scale(out, h, s->p.y);
+  const int lane = threadIdx.x;
+  enum { VA = 0, VB, VC, VYZ, VJ, VE, VD, VG, VH, VNH, VJ3 };
+  Fq(*v)[2] = s->v;
+  const Fq* rx = reinterpret_cast<const Fq*>(&s->r.x);
+  const Fq* ry = reinterpret_cast<const Fq*>(&s->r.y);
+  const Fq* rz = reinterpret_cast<const Fq*>(&s->r.z);
+  W12_SYNC();
+  // round 1: 0-2 x y (Karatsuba), 3-4 y^2, 5-6 z^2, 7-8 (y+z)^2, 9-10 x^2
+  if (lane < 11) {
+    Fq a, b;
+    if (lane < 3) {
+      w_kar_operand(a, rx, rx, false, lane);
+      w_kar_operand(b, ry, ry, false, lane);
+    } else {
+      const int q = (lane - 3) >> 1;
+      Fq w[2];
+      const Fq* src = q == 0 ? ry : (q == 1 ? rz : (q == 3 ? rx : ry));
+      w[0] = src[0];
+      w[1] = src[1];
+      if (q == 2) {
+        fq_add(w[0], w[0], rz[0]);
+        fq_add(w[1], w[1], rz[1]);
       }
-    } else if (lane == 4) {                // l3 = 3 j px
-      Fq2 j3;
-      fq2_dbl(j3, s->t[5]);
-      fq2_add(j3, j3, s->t[5]);
-      fq2_scale(out, j3, s->p.x);
-    } else {                               // l4 = i = e - b
-      fq2_sub(out, e, b);
+      w_sqr_operands(a, b, w, (lane - 3) & 1);
+    }
+    fq_mul_ol(&s->kar[lane], &a, &b);
+  }
+  W12_SYNC();
+  if (lane < 12) {
+    const int c = lane & 1;
+    Fq o;
+    if (lane < 2) {                 // a = x y / 2
+      w_fq2_from_kar(o, &s->kar[0], c);
+      fq_halve(o, o);
+      v[VA][c] = o;
+    } else if (lane < 10) {         // b, c, (y+z)^2, j
+      const int q = (lane - 2) >> 1;
+      w_sqr_asm(o, s->kar[3 + 2 * q], s->kar[4 + 2 * q], c);
+      v[VB + q][c] = o;
+    } else {                        // e = B' 3 c with B' = (0, -1/5): e.c0 = 3 c.c1, e.c1 = b1 * 3 c.c0
+      Fq cc, t;
+      w_sqr_asm(cc, s->kar[5], s->kar[6], 1 - c);
+      fq_dbl(t, cc);
+      fq_add(t, t, cc);
+      if (c == 0) o = t;
+      else {
+        const Fq b1 = fq_from_table(FQ12_C(TWIST_B1));
+        fq_mul_ol(&o, &t, &b1);
+      }
+      v[VE][c] = o;
     }
   }
-  __syncwarp();
-  if (lane == 0) s->r.x = out;
-  else if (lane == 1) s->r.y = out;
-  else if (lane == 2) s->r.z = out;
-  else if (lane == 3) *w12_c(&s->line, 0) = out;
-  else if (lane == 4) *w12_c(&s->line, 3) = out;
-  else if (lane == 5) *w12_c(&s->line, 4) = out;
-  __syncwarp();
+  W12_SYNC();
+  if (lane < 10) {                  // d = b - 3e, g = (b + 3e)/2, h = (y+z)^2 - b - c, -h, 3j
+    const int c = lane & 1, q = lane >> 1;
+    Fq o, t;
+    if (q < 2) {
+      fq_dbl(t, v[VE][c]);
+      fq_add(t, t, v[VE][c]);
+      if (q == 0) fq_sub(o, v[VB][c], t);
+      else {
+        fq_add(o, v[VB][c], t);
+        fq_halve(o, o);
+      }
+      v[VD + q][c] = o;
+    } else if (q < 4) {
+      fq_sub(o, v[VYZ][c], v[VB][c]);
+      fq_sub(o, o, v[VC][c]);
+      if (q == 3) fq_neg(o, o);
+      v[VH + (q - 2)][c] = o;
+    } else {
+      fq_dbl(t, v[VJ][c]);
+      fq_add(o, t, v[VJ][c]);
+      v[VJ3][c] = o;
+    }
+  }
+  W12_SYNC();
+  // round 2: 0-2 a d, 3-4 g^2, 5-6 e^2, 7-9 b h, 10-11 (-h) py, 12-13 (3 j) px
+  if (lane < 14) {
+    Fq a, b;
+    if (lane < 3) {
+      w_kar_operand(a, v[VA], v[VA], false, lane);
+      w_kar_operand(b, v[VD], v[VD], false, lane);
+    } else if (lane < 7) {
+      w_sqr_operands(a, b, lane < 5 ? v[VG] : v[VE], (lane - 3) & 1);
+    } else if (lane < 10) {
+      w_kar_operand(a, v[VB], v[VB], false, lane - 7);
+      w_kar_operand(b, v[VH], v[VH], false, lane - 7);
+    } else if (lane < 12) {
+      a = v[VNH][lane - 10];
+      b = s->p.y;
+    } else {
+      a = v[VJ3][lane - 12];
+      b = s->p.x;
+    }
+    fq_mul_ol(&s->kar[lane], &a, &b);
+  }
+  W12_SYNC();
+  if (lane < 12) {
+    const int c = lane & 1, q = lane >> 1;
+    Fq o;
+    if (q == 0) w_fq2_from_kar(o, &s->kar[0], c);            // x' = a (b - 3 e)
+    else if (q == 1) {                                       // y' = g^2 - 3 e^2
+      Fq g2v, e2v, t;
+      w_sqr_asm(g2v, s->kar[3], s->kar[4], c);
+      w_sqr_asm(e2v, s->kar[5], s->kar[6], c);
+      fq_dbl(t, e2v);
+      fq_add(t, t, e2v);
+      fq_sub(o, g2v, t);
+    } else if (q == 2) w_fq2_from_kar(o, &s->kar[7], c);     // z' = b h
+    else if (q == 3) o = s->kar[10 + c];                     // l0 = -h py
+    else if (q == 4) o = s->kar[12 + c];                     // l3 = 3 j px
+    else fq_sub(o, v[VE][c], v[VB][c]);                      // l4 = e - b
+    Fq* dst = q == 0 ? reinterpret_cast<Fq*>(&s->r.x)
+            : q == 1 ? reinterpret_cast<Fq*>(&s->r.y)
+            : q == 2 ? reinterpret_cast<Fq*>(&s->r.z)
+            : q == 3 ? w12_q(&s->line) + 0
+            : q == 4 ? w12_q(&s->line) + 6
+                     : w12_q(&s->line) + 8;
+    dst[c] = o;                                              // r was last read in round 1
+  }
+  W12_SYNC();
 }
 
 // s->p, s->q loaded; result in s->f
 __device__ __noinline__ void w_miller_loop(WMiller* s) {
-  const int lane = threadIdx.x & 31;
-  __syncwarp();
+  const int lane = threadIdx.x;
+  W12_SYNC();
   if (lane < 6) {
     *w12_c(&s->f, lane) = lane == 0 ? fq2_one() : fq2_zero();
     *w12_c(&s->line, lane) = fq2_zero();
@@ -431,7 +569,7 @@ __device__ __noinline__ void w_miller_loop(WMiller* s) {
     s->r.y = s->q.y;
     s->r.z = fq2_one();
   }
-  __syncwarp();
+  W12_SYNC();
   if (affine_is_inf(s->p) || affine2_is_inf(s->q)) return;   // uniform across the warp
   for (int bit = 62; bit >= 0; bit--) {
     if (bit != 62) w12_sqr(&s->f, &s->f, &s->w);
@@ -447,14 +585,14 @@ __device__ __noinline__ void w_miller_loop(WMiller* s) {
         *w12_c(&s->line, 3) = l3;
         *w12_c(&s->line, 4) = l4;
       }
-      __syncwarp();
+      W12_SYNC();
       w12_mul(&s->f, &s->f, &s->line, &s->w);
     }
   }
 }
 
-// f[j] = Miller(g1[j], g2[j ^ xor_mask]), one warp (= one block) per pair
-__global__ void __launch_bounds__(32) k_miller_coop(const uint4* __restrict__ g1, const uint4* __restrict__ g2,
+// f[j] = Miller(g1[j], g2[j ^ xor_mask]), one 64-thread CTA per pair
+__global__ void __launch_bounds__(W12_THREADS) k_miller_coop(const uint4* __restrict__ g1, const uint4* __restrict__ g2,
                                                     uint32_t xor_mask, uint4* __restrict__ f_out) {
   __shared__ WMiller s;
   const int lane = threadIdx.x;
@@ -463,15 +601,15 @@ __global__ void __launch_bounds__(32) k_miller_coop(const uint4* __restrict__ g1
   uint4* q4 = reinterpret_cast<uint4*>(&s.q);
   if (lane < 6) p4[lane] = g1[6 * (size_t)j + lane];
   if (lane >= 8 && lane < 20) q4[lane - 8] = g2[12 * (size_t)(j ^ xor_mask) + (lane - 8)];
-  __syncwarp();
+  W12_SYNC();
   w_miller_loop(&s);
-  __syncwarp();
+  W12_SYNC();
   const uint4* f4 = reinterpret_cast<const uint4*>(&s.f);
-  for (int i = lane; i < 36; i += 32) f_out[36 * (size_t)j + i] = f4[i];
+  for (int i = lane; i < 36; i += W12_THREADS) f_out[36 * (size_t)j + i] = f4[i];
 }
 
-// product tree level, one warp per output: out[s][t] = prod_k in[s][t + k m]
-__global__ void __launch_bounds__(32) k_fq12_prod_level_coop(const uint4* __restrict__ in, uint32_t len, uint32_t m,
+// product tree level, one CTA per output: out[s][t] = prod_k in[s][t + k m]
+__global__ void __launch_bounds__(W12_THREADS) k_fq12_prod_level_coop(const uint4* __restrict__ in, uint32_t len, uint32_t m,
                                                              uint4* __restrict__ out) {
   __shared__ Fq12 acc, x;
   __shared__ WScratch w;
@@ -480,29 +618,29 @@ __global__ void __launch_bounds__(32) k_fq12_prod_level_coop(const uint4* __rest
   const uint4* src = in + 36 * (size_t)blockIdx.y * len;
   uint4* a4 = reinterpret_cast<uint4*>(&acc);
   uint4* x4 = reinterpret_cast<uint4*>(&x);
-  for (int i = lane; i < 36; i += 32) a4[i] = src[36 * (size_t)t + i];
+  for (int i = lane; i < 36; i += W12_THREADS) a4[i] = src[36 * (size_t)t + i];
   for (int k = 1; k < FQ12_FAN; k++) {
     const uint64_t idx = (uint64_t)t + (uint64_t)k * m;
     if (idx >= len) break;
-    __syncwarp();
-    for (int i = lane; i < 36; i += 32) x4[i] = src[36 * idx + i];
-    __syncwarp();
+    W12_SYNC();
+    for (int i = lane; i < 36; i += W12_THREADS) x4[i] = src[36 * idx + i];
+    W12_SYNC();
     w12_mul(&acc, &acc, &x, &w);
   }
-  __syncwarp();
-  for (int i = lane; i < 36; i += 32) out[36 * ((size_t)blockIdx.y * m + t) + i] = a4[i];
+  W12_SYNC();
+  for (int i = lane; i < 36; i += W12_THREADS) out[36 * ((size_t)blockIdx.y * m + t) + i] = a4[i];
 }
 
-// out[b] = final_exponentiation(in[b]); one warp per product
-__global__ void __launch_bounds__(32) k_final_exp(const uint4* __restrict__ in, uint4* __restrict__ out) {
+// out[b] = final_exponentiation(in[b]); one CTA per product
+__global__ void __launch_bounds__(W12_THREADS) k_final_exp(const uint4* __restrict__ in, uint4* __restrict__ out) {
   __shared__ WFinalExp s;
   const int lane = threadIdx.x;
   uint4* f4 = reinterpret_cast<uint4*>(&s.f);
-  for (int i = lane; i < 36; i += 32) f4[i] = in[36 * (size_t)blockIdx.x + i];
-  __syncwarp();
+  for (int i = lane; i < 36; i += W12_THREADS) f4[i] = in[36 * (size_t)blockIdx.x + i];
+  W12_SYNC();
   w12_final_exp(&s);
   const uint4* r4 = reinterpret_cast<const uint4*>(&s.r);
-  for (int i = lane; i < 36; i += 32) out[36 * (size_t)blockIdx.x + i] = r4[i];
+  for (int i = lane; i < 36; i += W12_THREADS) out[36 * (size_t)blockIdx.x + i] = r4[i];
 }
 
 // out[b] = in[b] with no pairs at all (n == 0): the empty product
@@ -624,16 +762,16 @@ __global__ void __launch_bounds__(64) k_compress_g2_glv(uint4* __restrict__ a, u
 //   7 final_exp(a)  8 mul_by_034(a; b = l0 || l3 || l4)  9 miller(a = G1 affine || G2 affine)
 //   20 w12_mul  21 w12_sqr  22 w12_cyclotomic_sqr  23 w12_final_exp  24 w12_frobenius(1)  25 w12_frobenius(2)
 //   (warp-cooperative versions: element i is processed by the whole warp of block i / launched with n blocks)
-__global__ void __launch_bounds__(32) k_test_w12_op(int op, const uint4* a, const uint4* b, uint4* out) {
+__global__ void __launch_bounds__(W12_THREADS) k_test_w12_op(int op, const uint4* a, const uint4* b, uint4* out) {
   __shared__ WFinalExp s;
   const int lane = threadIdx.x;
   uint4* f4 = reinterpret_cast<uint4*>(&s.f);
   uint4* g4 = reinterpret_cast<uint4*>(&s.f2);
-  for (int i = lane; i < 36; i += 32) {
+  for (int i = lane; i < 36; i += W12_THREADS) {
     f4[i] = a[36 * (size_t)blockIdx.x + i];
     g4[i] = b[36 * (size_t)blockIdx.x + i];
   }
-  __syncwarp();
+  W12_SYNC();
   switch (op) {
     case 20: w12_mul(&s.r, &s.f, &s.f2, &s.w); break;
     case 21: w12_sqr(&s.r, &s.f, &s.w); break;
@@ -648,7 +786,7 @@ __global__ void __launch_bounds__(32) k_test_w12_op(int op, const uint4* a, cons
       uint4* q4 = reinterpret_cast<uint4*>(&ms.q);
       if (lane < 6) p4[lane] = a[36 * (size_t)blockIdx.x + lane];
       if (lane >= 8 && lane < 20) q4[lane - 8] = a[36 * (size_t)blockIdx.x + 6 + (lane - 8)];
-      __syncwarp();
+      W12_SYNC();
       w_miller_loop(&ms);
       w12_copy(&s.r, &ms.f);
       break;
@@ -656,9 +794,9 @@ __global__ void __launch_bounds__(32) k_test_w12_op(int op, const uint4* a, cons
     case 27: w12_cyclotomic_sqr(&s.f, &s.f, &s.w); w12_conj(&s.r, &s.f); break;
     default: break;
   }
-  __syncwarp();
+  W12_SYNC();
   const uint4* r4 = reinterpret_cast<const uint4*>(&s.r);
-  for (int i = lane; i < 36; i += 32) out[36 * (size_t)blockIdx.x + i] = r4[i];
+  for (int i = lane; i < 36; i += W12_THREADS) out[36 * (size_t)blockIdx.x + i] = r4[i];
 }
 
 __global__ void __launch_bounds__(32) k_test_fq12_op(int op, const uint4* a, const uint4* b, uint32_t n, uint4* out) {
