@@ -592,7 +592,7 @@ __device__ __noinline__ void w_miller_loop(WMiller* s) {
 }
 
 // f[j] = Miller(g1[j], g2[j ^ xor_mask]), one 64-thread CTA per pair
-__global__ void __launch_bounds__(W12_THREADS) k_miller_coop(const uint4* __restrict__ g1, const uint4* __restrict__ g2,
+__global__ void __launch_bounds__(W12_THREADS, 8) k_miller_coop(const uint4* __restrict__ g1, const uint4* __restrict__ g2,
                                                     uint32_t xor_mask, uint4* __restrict__ f_out) {
   __shared__ WMiller s;
   const int lane = threadIdx.x;
