@@ -7,7 +7,7 @@ import pytest
 
 import helpers as h
 from oracle import bls12_377 as o
-from testudo_b200 import mipp
+from testudo_b200 import _lib, mipp
 
 pytestmark = pytest.mark.gpu
 
@@ -76,3 +76,57 @@ def test_mipp_prover_loop_matches_reference_semantics(engine, n):
     assert rounds == n.bit_length() - 1
     assert h.pt_from_np(proof.final_a) == m_a[0]
     assert h.scalars_from_np(proof.final_y, mont=True)[0] == m_y[0]
+
+
+def test_mipp_round_entry_points_agree(engine):
+    """One MIPP round through the fused call (tb200_mipp_cross_all) and through the separate calls
+    (tb200_mipp_g1_cross + tb200_mipp_pairing_cross), before and after a fold, against the oracle's cross
+    commitments and pairing products (src/mipp.rs:77-94)."""
+    import ctypes
+
+    from oracle import bls12_377_g2 as o2
+    from oracle import pairing as pr
+
+    def P(a):
+        return a.ctypes.data_as(ctypes.c_void_p)
+
+    n = 8
+    a, _ = o.rand_points(n, 61)
+    hk, _ = o2.rand_points(n, 62)
+    y = o.rand_scalars(n, 63)
+    A = h.pts_to_np(a)
+    H = np.array([o2.affine_to_words(q) for q in hk], dtype=np.uint64)
+    Y = h.scalars_to_np(y, mont=True)
+    ha, hh = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(engine.tb200_mipp_g1_begin(P(A), P(Y), n, _lib.SCALARS_MONT, ctypes.byref(ha)))
+    _lib.check(engine.tb200_mipp_g2_begin(P(H), n, _lib.SCALARS_MONT, ctypes.byref(hh)))
+    try:
+        m_a, m_h, m_y = list(a), list(hk), list(y)
+        for rnd in range(2):
+            split = len(m_a) // 2
+            ul, ur = np.zeros(12, np.uint64), np.zeros(12, np.uint64)
+            tl, tr = np.zeros(72, np.uint64), np.zeros(72, np.uint64)
+            _lib.check(engine.tb200_mipp_cross_all(ha, hh, P(ul), P(ur), P(tl), P(tr)))
+            ul2, ur2 = np.zeros(12, np.uint64), np.zeros(12, np.uint64)
+            tl2, tr2 = np.zeros(72, np.uint64), np.zeros(72, np.uint64)
+            _lib.check(engine.tb200_mipp_g1_cross(ha, P(ul2), P(ur2)))
+            _lib.check(engine.tb200_mipp_pairing_cross(ha, hh, P(tl2), P(tr2)))
+            assert np.array_equal(ul, ul2) and np.array_equal(ur, ur2)
+            assert np.array_equal(tl, tl2) and np.array_equal(tr, tr2)
+            assert h.pt_from_np(ul) == o.msm_naive(m_a[:split], m_y[split:])
+            assert h.pt_from_np(ur) == o.msm_naive(m_a[split:], m_y[:split])
+            assert pr.from_words(tl) == pr.multi_pairing(m_a[:split], m_h[split:])
+            assert pr.from_words(tr) == pr.multi_pairing(m_a[split:], m_h[:split])
+            c_inv = o.rand_scalars(1, 64 + rnd)[0]
+            c = pow(c_inv, -1, o.R_ORDER)
+            _lib.check(engine.tb200_mipp_g1_fold(ha, P(h.scalars_to_np([c], mont=True)), P(h.scalars_to_np([c_inv], mont=True))))
+            _lib.check(engine.tb200_mipp_g2_fold(hh, P(h.scalars_to_np([c_inv], mont=True))))
+            m_a = [o.add(m_a[i], o.mul(c, m_a[split + i])) for i in range(split)]
+            m_y = [(m_y[i] + c_inv * m_y[split + i]) % o.R_ORDER for i in range(split)]
+            m_h = [o2.add(m_h[i], o2.mul(c_inv, m_h[split + i])) for i in range(split)]
+        fh = np.zeros((2, 24), np.uint64)
+        _lib.check(engine.tb200_mipp_g2_read(hh, P(fh)))
+        assert [o2.affine_from_words(r) for r in fh] == m_h          # the twisted-Frobenius fold, bit-exact
+    finally:
+        engine.tb200_mipp_g1_end(ha)
+        engine.tb200_mipp_g2_end(hh)
