@@ -76,7 +76,16 @@ def test_tower_constants_match_generated_header():
         assert fc[2][i][1] == 0
         exp.append(fc[2][i][0])
     exp += [o2.B2[1], pow(2, -1, o.Q)]
-    assert o2.B2[0] == 0 and vals == exp
+    assert o2.B2[0] == 0 and vals[:-1] == exp
+    # every Frobenius coefficient lies in Fq (the cooperative kernels rely on it)
+    assert all(fc[1][i][1] == 0 for i in range(1, 6))
+    # G1_BETA: phi(x, y) = (beta x, y) is multiplication by lambda = x^2 - 1 on G1; psi on G2 is multiplication by x
+    beta, lam = vals[-1], pr.X * pr.X - 1
+    pt = o.mul(0xC0FFEE123456789, o.G)
+    assert (pt[0] * beta % o.Q, pt[1]) == o.mul(lam, pt) and (lam * lam + lam + 1) % o.R_ORDER == 0
+    q2 = o2.mul(0xBADC0DE987654321, o2.G2)
+    psi = (o2.f2_mul(pr.f2_conj(q2[0]), fc[1][2]), o2.f2_mul(pr.f2_conj(q2[1]), fc[1][3]))
+    assert psi == o2.mul(pr.X, q2) and pr.X ** 4 > o.R_ORDER
 
 
 def test_host_fq12_arithmetic(hc):

@@ -504,6 +504,7 @@ struct tb200_mipp {
   uint32_t* y = nullptr;  // n0 scalars (8 limbs)
   uint32_t* scal = nullptr;  // 16 limbs staging for c, c_inv, one slot per round (the folds are only enqueued)
   uint32_t* scal_host = nullptr;  // pinned, same shape
+  uint32_t* digits = nullptr;     // the two 128-bit halves of c over the G1 endomorphism (k_glv2_digits), 8 words per round
   int round = 0;
 };
 
@@ -1049,6 +1050,7 @@ int tb200_mipp_g1_begin(const uint64_t* a_xy, const uint64_t* y, size_t n, unsig
   cudaError_t e = cudaMalloc((void**)&h->a, n * 96);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->y, n * 32);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->scal, 64 * 64);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->digits, 64 * 32);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->scal_host, 64 * 64);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->a, a_xy, n * 96, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->y, y, n * 32, cudaMemcpyHostToDevice, g.stream);
@@ -1057,6 +1059,7 @@ int tb200_mipp_g1_begin(const uint64_t* a_xy, const uint64_t* y, size_t n, unsig
     cudaFree(h->a);
     cudaFree(h->y);
     cudaFree(h->scal);
+    cudaFree(h->digits);
     cudaFreeHost(h->scal_host);
     delete h;
     return fail((int)e, "MIPP upload failed: %s", cudaGetErrorString(e));
@@ -1110,7 +1113,9 @@ int tb200_mipp_g1_fold(tb200_mipp_t h, const uint64_t c[4], const uint64_t c_inv
   memcpy(hs + 8, c_inv, 32);
   CU(cudaMemcpyAsync(ds, hs, 64, cudaMemcpyHostToDevice, g.stream));
   const int mont = (h->flags & TB200_SCALARS_MONT) ? 1 : 0;
-  LAUNCH(k_compress_g1, cdiv(split, 128), 128, g.stream, h->a, split, ds, mont);
+  // a_l + c a_r over the G1 endomorphism (kernels_pairing.cuh): 127 doublings instead of 253
+  LAUNCH(k_glv2_digits, 1, 32, g.stream, ds, mont, h->digits + 8 * h->round);
+  LAUNCH(k_compress_g1_glv, cdiv(split, 128), 128, g.stream, h->a, split, h->digits + 8 * h->round);
   LAUNCH(k_compress_fr, cdiv(split, 128), 128, g.stream, h->y, split, ds + 8, mont);
   h->round++;
   h->n = split;
@@ -1136,6 +1141,7 @@ int tb200_mipp_g1_end(tb200_mipp_t h) {
     cudaFree(h->a);
     cudaFree(h->y);
     cudaFree(h->scal);
+    cudaFree(h->digits);
     cudaFreeHost(h->scal_host);
   }
   delete h;

@@ -757,6 +757,83 @@ __global__ void __launch_bounds__(64) k_compress_g2_glv(uint4* __restrict__ a, u
   store_affine2(a + 12 * (uint64_t)i, o);
 }
 
+// G1 fold over phi(x, y) = (beta x, y) = [lambda](x, y), lambda = x^2 - 1 < 2^127: k = k1 lambda + k0 with k0 < lambda and
+// k1 = floor(k / lambda) < 2^127 (r < lambda^2 + lambda + 1), then a 2-way simultaneous multiplication, 127 doublings.
+// digits[0..3] = k0, digits[4..7] = k1 (128 bits each). Same precondition: the points lie in G1's order-r subgroup.
+__global__ void k_glv2_digits(const uint32_t* __restrict__ scaler, int mont, uint32_t* __restrict__ digits) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint32_t k[8];
+  for (int j = 0; j < 8; j++) k[j] = scaler[j];
+  if (mont) mont_to_canonical<FrParams>(k, k);
+  // lambda = BLS_X^2 - 1 as two 64-bit halves
+  const uint64_t xl = BLS_X & 0xffffffffull, xh = BLS_X >> 32;
+  const uint64_t ll = xl * xl, lh = xl * xh, hh = xh * xh;     // x^2 = hh 2^64 + 2 lh 2^32 + ll
+  uint64_t lo = ll + (lh << 33);
+  uint64_t hi = hh + (lh >> 31) + (lo < ll ? 1 : 0);
+  hi -= (lo == 0);
+  lo -= 1;
+  uint64_t q[4], nq[4] = {0, 0, 0, 0}, r0 = 0, r1 = 0;         // remainder r1:r0 < lambda < 2^127
+  for (int j = 0; j < 4; j++) q[j] = (uint64_t)k[2 * j] | ((uint64_t)k[2 * j + 1] << 32);
+  for (int bit = 255; bit >= 0; bit--) {
+    r1 = (r1 << 1) | (r0 >> 63);
+    r0 = (r0 << 1) | ((q[bit >> 6] >> (bit & 63)) & 1);
+    if (r1 > hi || (r1 == hi && r0 >= lo)) {
+      const uint64_t b = r0 < lo;
+      r0 -= lo;
+      r1 -= hi + b;
+      nq[bit >> 6] |= 1ull << (bit & 63);
+    }
+  }
+  digits[0] = (uint32_t)r0;
+  digits[1] = (uint32_t)(r0 >> 32);
+  digits[2] = (uint32_t)r1;
+  digits[3] = (uint32_t)(r1 >> 32);
+  digits[4] = (uint32_t)nq[0];
+  digits[5] = (uint32_t)(nq[0] >> 32);
+  digits[6] = (uint32_t)nq[1];
+  digits[7] = (uint32_t)(nq[1] >> 32);     // nq[2], nq[3] are zero for k < r
+}
+
+// a[i] <- a[i] + k * a[split + i], k = k0 + k1 lambda
+__global__ void __launch_bounds__(128) k_compress_g1_glv(uint4* __restrict__ a, uint32_t split,
+                                                         const uint32_t* __restrict__ digits) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= split) return;
+  uint32_t k0[4], k1[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    k0[j] = digits[j];
+    k1[j] = digits[4 + j];
+  }
+  Affine l, r, pr;
+  load_affine(l, a + 6 * (uint64_t)i);
+  load_affine(r, a + 6 * ((uint64_t)split + i));
+  const Fq beta = fq_from_table(FQ12_C(G1_BETA));
+  fq_mul_ol(&pr.x, &r.x, &beta);           // phi(r); the identity (0, 0) stays (0, 0)
+  pr.y = r.y;
+  Xyzz t3;                                 // r + phi(r)
+  xyzz_set_inf(t3);
+  xyzz_madd_ni(&t3, &r);
+  xyzz_madd_ni(&t3, &pr);
+  Xyzz acc;
+  xyzz_set_inf(acc);
+  bool started = false;
+  for (int limb = 3; limb >= 0; limb--) {
+    for (int bit = 31; bit >= 0; bit--) {
+      if (started) xyzz_dbl_ni(&acc);
+      const int m = (int)((k0[limb] >> bit) & 1) | ((int)((k1[limb] >> bit) & 1) << 1);
+      if (m == 1) xyzz_madd_ni(&acc, &r);
+      else if (m == 2) xyzz_madd_ni(&acc, &pr);
+      else if (m == 3) xyzz_add_ni(&acc, &t3);
+      started = started || m != 0;
+    }
+  }
+  xyzz_madd_ni(&acc, &l);
+  Affine o;
+  xyzz_to_affine_ni(&o, &acc);
+  store_affine(a + 6 * (uint64_t)i, o);
+}
+
 // test hook: one Fq12 operation per thread (tests/test_gpu_pairing.py drives every op against the oracle)
 //   0 mul(a,b)  1 sqr(a)  2 inv(a)  3 frobenius(a,1)  4 frobenius(a,2)  5 cyclotomic_sqr(a)  6 exp_by_x(a)
 //   7 final_exp(a)  8 mul_by_034(a; b = l0 || l3 || l4)  9 miller(a = G1 affine || G2 affine)
