@@ -1193,7 +1193,7 @@ int tb200_mipp_g2_fold(tb200_mipp_g2_t h, const uint64_t c_inv[4]) {
   CU(cudaMemcpyAsync(h->scal + 8 * h->round, h->scal_host + 8 * h->round, 32, cudaMemcpyHostToDevice, m_st));
   // 4-dimensional decomposition over the twisted Frobenius (kernels_pairing.cuh): 64 doublings instead of 253
   LAUNCH(k_glv4_digits, 1, 32, m_st, h->scal + 8 * h->round, (h->flags & TB200_SCALARS_MONT) ? 1 : 0, h->digits + 8 * h->round);
-  LAUNCH(k_compress_g2_glv, cdiv(split, 64), 64, m_st, h->h, split, h->digits + 8 * h->round);
+  LAUNCH(k_compress_g2_glv4w, cdiv(split, 32), 128, m_st, h->h, split, h->digits + 8 * h->round);
   h->round++;
   h->n = split;
   return 0;

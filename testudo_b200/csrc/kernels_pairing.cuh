@@ -757,6 +757,44 @@ __global__ void __launch_bounds__(64) k_compress_g2_glv(uint4* __restrict__ a, u
   store_affine2(a + 12 * (uint64_t)i, o);
 }
 
+// The same fold with the four dimensions on four WARPS of a CTA (32 elements per CTA): warp j multiplies psi^j(r) by the
+// 64-bit digit k_j (the digit is warp-uniform, so its double-and-add does not diverge), the three partial sums travel
+// through shared memory to warp 0, which adds them, adds a[i] and normalises. Per thread 64 doublings + ~32 mixed
+// additions instead of 64 doublings + 60 full additions + an 11-addition table: the latency of a fold is what a MIPP round
+// waits for.
+__global__ void __launch_bounds__(128) k_compress_g2_glv4w(uint4* __restrict__ a, uint32_t split,
+                                                           const uint32_t* __restrict__ digits) {
+  __shared__ Xyzz2 part[3][32];
+  const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const uint32_t i = blockIdx.x * 32 + lane;
+  const bool live = i < split;
+  Xyzz2 acc;
+  xyzz2_set_inf(acc);
+  if (live) {
+    const uint64_t kd = (uint64_t)digits[2 * j] | ((uint64_t)digits[2 * j + 1] << 32);
+    Affine2 b;
+    load_affine2(b, a + 12 * ((uint64_t)split + i));
+    for (int t = 0; t < j; t++) g2_psi(b, b);
+    bool started = false;
+    for (int bit = 63; bit >= 0; bit--) {
+      if (started) xyzz2_dbl_ni(&acc);
+      if ((kd >> bit) & 1) {
+        xyzz2_madd_ni(&acc, &b);
+        started = true;
+      }
+    }
+    if (j > 0) part[j - 1][lane] = acc;
+  }
+  __syncthreads();
+  if (j != 0 || !live) return;
+  for (int t = 0; t < 3; t++) xyzz2_add_ni(&acc, &part[t][lane]);
+  Affine2 l, o;
+  load_affine2(l, a + 12 * (uint64_t)i);
+  xyzz2_madd_ni(&acc, &l);
+  xyzz2_to_affine_ni(&o, &acc);
+  store_affine2(a + 12 * (uint64_t)i, o);
+}
+
 // G1 fold over phi(x, y) = (beta x, y) = [lambda](x, y), lambda = x^2 - 1 < 2^127: k = k1 lambda + k0 with k0 < lambda and
 // k1 = floor(k / lambda) < 2^127 (r < lambda^2 + lambda + 1), then a 2-way simultaneous multiplication, 127 doublings.
 // digits[0..3] = k0, digits[4..7] = k1 (128 bits each). Same precondition: the points lie in G1's order-r subgroup.
