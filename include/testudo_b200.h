@@ -200,6 +200,15 @@ int tb200_test_fq12_op(int op, const uint64_t* a, const uint64_t* b, size_t n, u
 int tb200_multi_pairing(const uint64_t* g1_xy, const uint64_t* g2, size_t n, uint64_t out[72]);
 /* Same with DEVICE pointers; d_out receives 576 bytes; returns after enqueueing on `stream` (NULL = library stream). */
 int tb200_multi_pairing_dev(const void* d_g1_xy, const void* d_g2, size_t n, void* d_out, void* stream);
+/* Sharded pairing product (one process per GPU): each rank reduces ITS slice of the pairs to one partial
+ * value -- the product of the Miller-loop values, NO final exponentiation (576 bytes) --, the partials are all-gathered,
+ * and tb200_gt_product_final_exp multiplies them and applies the single final exponentiation:
+ *   multi_pairing(a, b) == gt_product_final_exp([miller_product(slice_r) for every rank r]).
+ * The partial value is only meaningful as input of the combination (it depends on the Miller-loop formulas). */
+int tb200_miller_product(const uint64_t* g1_xy, const uint64_t* g2, size_t n, uint64_t out[72]);
+int tb200_miller_product_dev(const void* d_g1_xy, const void* d_g2, size_t n, void* d_out, void* stream);
+int tb200_gt_product_final_exp(const uint64_t* parts, size_t n, uint64_t out[72]);
+int tb200_gt_product_final_exp_dev(const void* d_parts, size_t n, void* d_out, void* stream);
 /* The two cross pairing products of a MIPP round over the device-resident vectors (src/mipp.rs:87-94):
  * comm_t_l = prod_i e(a[i], h[split + i]), comm_t_r = prod_i e(a[split + i], h[i]), split = len / 2.
  * Both handles must have the same current length (>= 2). Waits for the G2 folds enqueued so far. */

@@ -207,3 +207,23 @@ def test_multi_pairing_device_pointers(engine):
             engine.tb200_dev_free(ptr)
     assert np.array_equal(out, pairing.multi_pairing(A, B))
     assert pr.from_words(out) == pr.multi_pairing(ps, qs)
+
+
+def test_sharded_pairing_product_entry_points(engine):
+    """multi_pairing(a, b) == final_exponentiation_of_product([miller_product(slice) ...]) for uneven slices (one of
+    them empty, one beyond the warp-per-pair limit), and through parallel.multi_pairing_sharded at world size 1."""
+    from testudo_b200 import parallel
+
+    n = 2100
+    ps, dl1 = o.rand_points(n, 51)
+    qs, dl2 = o2.rand_points(n, 52)
+    A, B = h.pts_to_np(ps), g2_np(qs)
+    whole = pairing.multi_pairing(A, B)
+    cuts = [0, 0, 3, 40, n]
+    parts = [pairing.miller_product(A[lo:hi], B[lo:hi]) for lo, hi in zip(cuts[:-1], cuts[1:])]
+    assert pr.from_words(parts[0]) == pr.F12_ONE
+    assert np.array_equal(pairing.final_exponentiation_of_product(np.array(parts)), whole)
+    assert np.array_equal(parallel.multi_pairing_sharded(A, B), whole)
+    assert pr.from_words(whole) == pr.f12_pow(E_GEN, sum(a * b for a, b in zip(dl1, dl2)) % o.R_ORDER)
+    # a partial value followed by the oracle's final exponentiation is the oracle's pairing product of that slice
+    assert pr.final_exponentiation(pr.from_words(parts[2])) == pr.multi_pairing(ps[3:40], qs[3:40])

@@ -87,3 +87,58 @@ def test_sharded_msm_and_rows_world2(n, rows):
         assert p.exitcode == 0
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(r[1] and r[2] for r in results), results
+
+
+def _oracle_miller_product(g1s, g2s):
+    from oracle import bls12_377_g2 as o2
+    from oracle import pairing as pr
+
+    ps = [h.pt_from_np(r) for r in np.asarray(g1s, dtype=np.uint64).reshape(-1, 12)]
+    qs = [o2.affine_from_words(r) for r in np.asarray(g2s, dtype=np.uint64).reshape(-1, 24)]
+    return np.array(pr.to_words(pr.multi_miller_loop(ps, qs)), dtype=np.uint64)
+
+
+def _oracle_combine(parts):
+    from oracle import pairing as pr
+
+    f = pr.F12_ONE
+    for row in np.asarray(parts, dtype=np.uint64).reshape(-1, 72):
+        f = pr.f12_mul(f, pr.from_words(row))
+    return np.array(pr.to_words(pr.final_exponentiation(f)), dtype=np.uint64)
+
+
+def _pairing_worker(rank, world, port, n, q):
+    from oracle import bls12_377_g2 as o2
+    from oracle import pairing as pr
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ps, _ = o.rand_points(n, 21)
+        qs, _ = o2.rand_points(n, 22)
+        A = h.pts_to_np(ps)
+        B = np.array([o2.affine_to_words(p) for p in qs], dtype=np.uint64).reshape(-1, 24)
+        lo, hi = parallel.shard_range(n, rank, world)
+        got = parallel.multi_pairing_sharded(A[lo:hi], B[lo:hi], local_miller_product=_oracle_miller_product,
+                                             combine=_oracle_combine)
+        q.put((rank, pr.from_words(got) == pr.multi_pairing(ps, qs)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_pairing_product_world2():
+    """t = multi_pairing(comm_list, h_vec) with the pairs sharded across ranks: one partial Miller product per rank, one
+    all-gather of 576 B, one final exponentiation -- the host logic of parallel.multi_pairing_sharded under gloo."""
+    world, n = 2, 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pairing_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r[0] for r in results) == [0, 1] and all(r[1] for r in results), results

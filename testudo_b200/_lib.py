@@ -54,6 +54,10 @@ SIGNATURES = {
     "tb200_mipp_g2_end": (c_int, [c_void_p]),
     "tb200_multi_pairing": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "tb200_multi_pairing_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "tb200_miller_product": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tb200_miller_product_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "tb200_gt_product_final_exp": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "tb200_gt_product_final_exp_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "tb200_mipp_pairing_cross": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "tb200_set_pairing_coop_max": (None, [c_int]),
     "tb200_mipp_cross_all": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

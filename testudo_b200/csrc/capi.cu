@@ -1229,8 +1229,11 @@ int tb200_mipp_g2_end(tb200_mipp_g2_t h) {
 // Miller values of `n` pairs (g2 index = j ^ xor_mask) -> `segs` products (segment s = pairs [s n/segs, (s+1) n/segs))
 // -> final exponentiation of each, written to d_out (segs x 576 B). Everything is enqueued on `st`; the scratch is
 // stream-ordered. `after_miller`, if given, is recorded once the Miller kernel (the only reader of g1 / g2) is enqueued.
+// `d_gt_in` != nullptr: skip the Miller stage, the n inputs are Fq12 values (per-rank Miller products to be combined).
+// `final_exp` = false: stop after the product tree (a partial Miller product for a sharded pairing product).
 static int pairing_products_locked(const uint4* d_g1, const uint4* d_g2, uint32_t n, uint32_t xor_mask, uint32_t segs,
-                                   uint4* d_out, cudaStream_t st, cudaEvent_t after_miller) {
+                                   uint4* d_out, cudaStream_t st, cudaEvent_t after_miller,
+                                   const uint4* d_gt_in = nullptr, bool final_exp = true) {
   if (n == 0) {
     LAUNCH(k_fq12_set_one, 1, 32, st, d_out, segs);
     return 0;
@@ -1243,7 +1246,8 @@ static int pairing_products_locked(const uint4* d_g1, const uint4* d_g2, uint32_
   if (mark(st, "begin")) return 1;
   // below ~2 waves of resident warps one WARP per pair (latency 10 -> ~3 ms); above, one thread per pair
   const bool coop = n <= (uint32_t)g.pairing_coop_max;
-  if (coop) LAUNCH(k_miller_coop, n, W12_THREADS, st, d_g1, d_g2, xor_mask, buf_a);
+  if (d_gt_in) CU(cudaMemcpyAsync(buf_a, d_gt_in, (size_t)n * 576, cudaMemcpyDeviceToDevice, st));
+  else if (coop) LAUNCH(k_miller_coop, n, W12_THREADS, st, d_g1, d_g2, xor_mask, buf_a);
   else LAUNCH(k_miller, cdiv(n, 32), 32, st, d_g1, d_g2, n, xor_mask, buf_a);
   if (after_miller) CU(cudaEventRecord(after_miller, st));
   if (mark(st, "miller")) return 1;
@@ -1256,7 +1260,8 @@ static int pairing_products_locked(const uint4* d_g1, const uint4* d_g2, uint32_
     len = m;
   }
   if (mark(st, "gt_product")) return 1;
-  LAUNCH(k_final_exp, segs, W12_THREADS, st, cur, d_out);
+  if (final_exp) LAUNCH(k_final_exp, segs, W12_THREADS, st, cur, d_out);
+  else CU(cudaMemcpyAsync(d_out, cur, (size_t)segs * 576, cudaMemcpyDeviceToDevice, st));
   if (mark(st, "final_exp")) return 1;
   CU(cudaFreeAsync(buf_a, st));
   CU(cudaFreeAsync(buf_b, st));
@@ -1297,6 +1302,75 @@ int tb200_multi_pairing(const uint64_t* g1_xy, const uint64_t* g2, size_t n, uin
   if (d_q) cudaFreeAsync(d_q, g.stream);
   cudaFreeAsync(d_o, g.stream);
   return rc;
+}
+
+// Sharded pairing product (SURVEY.md 8e pattern: per-GPU partial, one all-gather, combine): the Miller product of a
+// slice of the pairs WITHOUT the final exponentiation ...
+int tb200_miller_product(const uint64_t* g1_xy, const uint64_t* g2, size_t n, uint64_t out[72]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || (n && (!g1_xy || !g2))) return fail(TB200_E_ARG, "null pointer");
+  if (n >= (1u << 26)) return fail(TB200_E_LIMIT, "too many pairs");
+  CU(cudaSetDevice(g.device));
+  uint4 *d_p = nullptr, *d_q = nullptr, *d_o = nullptr;
+  CU(cudaMallocAsync((void**)&d_o, 576, g.stream));
+  if (n) {
+    CU(cudaMallocAsync((void**)&d_p, n * 96, g.stream));
+    CU(cudaMallocAsync((void**)&d_q, n * 192, g.stream));
+    CU(cudaMemcpyAsync(d_p, g1_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(d_q, g2, n * 192, cudaMemcpyHostToDevice, g.stream));
+  }
+  int rc = pairing_products_locked(d_p, d_q, (uint32_t)n, 0, 1, d_o, g.stream, nullptr, nullptr, false);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out, d_o, 576, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
+  }
+  if (d_p) cudaFreeAsync(d_p, g.stream);
+  if (d_q) cudaFreeAsync(d_q, g.stream);
+  cudaFreeAsync(d_o, g.stream);
+  return rc;
+}
+int tb200_miller_product_dev(const void* d_g1_xy, const void* d_g2, size_t n, void* d_out, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_out || (n && (!d_g1_xy || !d_g2))) return fail(TB200_E_ARG, "null pointer");
+  if (n >= (1u << 26)) return fail(TB200_E_LIMIT, "too many pairs");
+  CU(cudaSetDevice(g.device));
+  return pairing_products_locked((const uint4*)d_g1_xy, (const uint4*)d_g2, (uint32_t)n, 0, 1, (uint4*)d_out,
+                                 stream ? (cudaStream_t)stream : g.stream, nullptr, nullptr, false);
+}
+// ... and the combination: the product of `n` such partial values, then ONE final exponentiation
+int tb200_gt_product_final_exp(const uint64_t* parts, size_t n, uint64_t out[72]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || (n && !parts)) return fail(TB200_E_ARG, "null pointer");
+  if (n >= (1u << 20)) return fail(TB200_E_LIMIT, "too many partial products");
+  CU(cudaSetDevice(g.device));
+  uint4 *d_in = nullptr, *d_o = nullptr;
+  CU(cudaMallocAsync((void**)&d_o, 576, g.stream));
+  if (n) {
+    CU(cudaMallocAsync((void**)&d_in, n * 576, g.stream));
+    CU(cudaMemcpyAsync(d_in, parts, n * 576, cudaMemcpyHostToDevice, g.stream));
+  }
+  int rc = pairing_products_locked(nullptr, nullptr, (uint32_t)n, 0, 1, d_o, g.stream, nullptr, d_in, true);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out, d_o, 576, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
+  }
+  if (d_in) cudaFreeAsync(d_in, g.stream);
+  cudaFreeAsync(d_o, g.stream);
+  return rc;
+}
+int tb200_gt_product_final_exp_dev(const void* d_parts, size_t n, void* d_out, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_out || (n && !d_parts)) return fail(TB200_E_ARG, "null pointer");
+  if (n >= (1u << 20)) return fail(TB200_E_LIMIT, "too many partial products");
+  CU(cudaSetDevice(g.device));
+  return pairing_products_locked(nullptr, nullptr, (uint32_t)n, 0, 1, (uint4*)d_out,
+                                 stream ? (cudaStream_t)stream : g.stream, nullptr, (const uint4*)d_parts, true);
 }
 
 int tb200_mipp_pairing_cross(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_t_l[72], uint64_t comm_t_r[72]) {

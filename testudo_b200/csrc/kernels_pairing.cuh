@@ -720,48 +720,12 @@ __device__ __forceinline__ void g2_psi(Affine2& r, const Affine2& p) {
   fq2_scale(r.y, r.y, g3c);
 }
 
-// a[i] <- a[i] + k * a[split + i], k given by its four base-x digits
-__global__ void __launch_bounds__(64) k_compress_g2_glv(uint4* __restrict__ a, uint32_t split,
-                                                        const uint32_t* __restrict__ digits) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= split) return;
-  uint64_t kd[4];
-#pragma unroll
-  for (int j = 0; j < 4; j++) kd[j] = (uint64_t)digits[2 * j] | ((uint64_t)digits[2 * j + 1] << 32);
-  Affine2 l, b[4];
-  load_affine2(l, a + 12 * (uint64_t)i);
-  load_affine2(b[0], a + 12 * ((uint64_t)split + i));
-  for (int j = 1; j < 4; j++) g2_psi(b[j], b[j - 1]);
-  Xyzz2 T[16];                       // T[m] = sum over the set bits j of m of psi^j(r)
-  xyzz2_set_inf(T[0]);
-  for (int m = 1; m < 16; m++) {
-    const int low = __ffs(m) - 1;
-    T[m] = T[m & (m - 1)];
-    xyzz2_madd_ni(&T[m], &b[low]);
-  }
-  Xyzz2 acc;
-  xyzz2_set_inf(acc);
-  bool started = false;
-  for (int bit = 63; bit >= 0; bit--) {
-    if (started) xyzz2_dbl_ni(&acc);
-    const int m = (int)((kd[0] >> bit) & 1) | ((int)((kd[1] >> bit) & 1) << 1) | ((int)((kd[2] >> bit) & 1) << 2) |
-                  ((int)((kd[3] >> bit) & 1) << 3);
-    if (m) {
-      xyzz2_add_ni(&acc, &T[m]);
-      started = true;
-    }
-  }
-  xyzz2_madd_ni(&acc, &l);
-  Affine2 o;
-  xyzz2_to_affine_ni(&o, &acc);
-  store_affine2(a + 12 * (uint64_t)i, o);
-}
-
-// The same fold with the four dimensions on four WARPS of a CTA (32 elements per CTA): warp j multiplies psi^j(r) by the
-// 64-bit digit k_j (the digit is warp-uniform, so its double-and-add does not diverge), the three partial sums travel
-// through shared memory to warp 0, which adds them, adds a[i] and normalises. Per thread 64 doublings + ~32 mixed
-// additions instead of 64 doublings + 60 full additions + an 11-addition table: the latency of a fold is what a MIPP round
-// waits for.
+// a[i] <- a[i] + k * a[split + i], k given by its four base-x digits, with the four dimensions on four WARPS of a CTA
+// (32 elements per CTA): warp j multiplies psi^j(r) by the 64-bit digit k_j (the digit is warp-uniform, so its
+// double-and-add does not diverge), the three partial sums travel through shared memory to warp 0, which adds them, adds
+// a[i] and normalises. Per thread 64 doublings + ~32 mixed additions (a first version did all four dimensions in one
+// thread with a 15-entry table: 64 doublings + 60 full additions + 11 for the table, 5.3 ms instead of 3.6): the latency of
+// a fold is what a MIPP round waits for.
 __global__ void __launch_bounds__(128) k_compress_g2_glv4w(uint4* __restrict__ a, uint32_t split,
                                                            const uint32_t* __restrict__ digits) {
   __shared__ Xyzz2 part[3][32];

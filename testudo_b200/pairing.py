@@ -54,3 +54,22 @@ def gt_pow(bases, exps, mont: bool = False) -> np.ndarray:
     out = np.zeros_like(b)
     _lib.check(_lib.engine().tb200_gt_pow(_ptr(b), _ptr(e), len(b), _lib.SCALARS_MONT if mont else 0, _ptr(out)))
     return out
+
+
+def miller_product(g1s, g2s) -> np.ndarray:
+    """This process's share of a sharded pairing product: the product of the Miller-loop values of the given pairs,
+    WITHOUT the final exponentiation ([72] words; only meaningful as input of `final_exponentiation_of_product`)."""
+    p = np.ascontiguousarray(g1s, dtype=np.uint64).reshape(-1, 12)
+    q = np.ascontiguousarray(g2s, dtype=np.uint64).reshape(-1, 24)
+    n = min(len(p), len(q))
+    out = np.zeros(GT_WORDS, dtype=np.uint64)
+    _lib.check(_lib.engine().tb200_miller_product(_ptr(p), _ptr(q), n, _ptr(out)))
+    return out
+
+
+def final_exponentiation_of_product(parts) -> np.ndarray:
+    """Multiplies partial Miller products (one per rank) and applies the single final exponentiation."""
+    f = np.ascontiguousarray(parts, dtype=np.uint64).reshape(-1, GT_WORDS)
+    out = np.zeros(GT_WORDS, dtype=np.uint64)
+    _lib.check(_lib.engine().tb200_gt_product_final_exp(_ptr(f), len(f), _ptr(out)))
+    return out

@@ -3,6 +3,9 @@
   * single large MSM   -> contiguous POINT RANGES per rank; each rank reduces its slice to one affine partial;
                           one all-gather of 96 B per rank; every rank sums the partials (tb200_g1_sum).
   * row commitments    -> ROWS per rank over the replicated SRS; one all-gather of rows/G x 96 B; no reduction.
+  * pairing product t  -> PAIRS per rank (the row commitments a rank computed, with its slice of h_vec): each rank reduces
+                          its pairs to one partial Miller product (576 B, no final exponentiation); one all-gather;
+                          every rank multiplies the partials and applies the single final exponentiation.
   * MIPP rounds        -> replicas only (log-depth serial chain over <= 2^13 points; not worth sharding).
 
 The data path has no other communication. `local_msm`, `local_rows` and `sum_points` default to the CUDA engine; the
@@ -83,3 +86,42 @@ def commit_rows_sharded(local_rows_fn: Callable[[int, int], np.ndarray], total_r
         rlo, rhi = shard_range(total_rows, r, world)
         out[rlo:rhi] = allp[r, : rhi - rlo]
     return out
+
+
+def all_gather_words(local: np.ndarray, group=None) -> np.ndarray:
+    """All-gather of one equally sized uint64 vector per rank -> [world, len]."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    local = np.ascontiguousarray(local, dtype=np.uint64).reshape(-1)
+    if world == 1:
+        return local.reshape(1, -1).copy()
+    dev = _device()
+    mine = torch.from_numpy(local.view(np.int64)).to(dev)
+    out = torch.empty((world * local.shape[0],), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return out.cpu().numpy().view(np.uint64).reshape(world, -1)
+
+
+def _engine_miller_product(g1s: np.ndarray, g2s: np.ndarray) -> np.ndarray:
+    from . import pairing
+
+    return pairing.miller_product(g1s, g2s)
+
+
+def _engine_combine(parts: np.ndarray) -> np.ndarray:
+    from . import pairing
+
+    return pairing.final_exponentiation_of_product(parts)
+
+
+def multi_pairing_sharded(g1_local: np.ndarray, g2_local: np.ndarray, group=None,
+                          local_miller_product: Optional[Callable] = None,
+                          combine: Optional[Callable] = None) -> np.ndarray:
+    """`E::multi_pairing` over the union of every rank's pairs (e.g. `t = multi_pairing(comm_list, h_vec)` of
+    `Polynomial::commit`, src/sqrt_pst.rs:131-144, with the rows sharded as in commit_rows_sharded): one partial Miller
+    product per rank, one all-gather of 576 B per rank, one final exponentiation on every rank. All ranks return the same
+    GT element."""
+    local_miller_product = local_miller_product or _engine_miller_product
+    combine = combine or _engine_combine
+    partial = np.asarray(local_miller_product(g1_local, g2_local), dtype=np.uint64).reshape(72)
+    parts = all_gather_words(partial, group)
+    return np.asarray(combine(parts), dtype=np.uint64).reshape(72)
