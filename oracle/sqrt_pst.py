@@ -8,6 +8,9 @@ Follows, line by line:
 The transcript is a callback `challenge(label, [(kind, value), ...]) -> int`, kind in {"g1", "g2", "gt"} -- the values
 the reference appends at that point (src/mipp.rs:56,97-101,138-141).
 
+PARITY UNPINNED against the arkworks binary: the reference holds no fixtures for these values and cannot be
+built here; prover and verifier restatements are pinned against each other (tests/test_oracle_sqrt_pst.py).
+
 ck = dict(nv, powers_of_g[k], powers_of_h[k]) with level k holding the 2^(nv-k) points eq((t_k..), x) * generator.
 """
 from __future__ import annotations

@@ -11,6 +11,9 @@ Restates:
   * `Polynomial::verify`     src/sqrt_pst.rs:232-267
 The transcript is the same callback the prover mirror takes: `challenge(label, appended_values) -> int`.
 
+PARITY UNPINNED against the arkworks binary: the reference holds no fixtures for these values and cannot be
+built here; prover and verifier restatements are pinned against each other (tests/test_oracle_sqrt_pst.py).
+
 vk = dict(nv, g, h, g_mask[nv], h_mask[nv]) over the oracle's point types (oracle/bls12_377.py, bls12_377_g2.py);
 GT values are flat Fq12 tuples (oracle/pairing.py).
 """
