@@ -264,6 +264,7 @@ int make_plan(Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs,
     b += Arena::pad(n * 192 * pw) * 2;
   }
   b += Arena::pad((size_t)q.groups * 192 * pw) * 2 + 4096;
+  if (g2) b += Arena::pad((size_t)4 * 96 * 384);        // window-combine partial sums (k_finalize_single_g2_glv)
   p.bytes = b;
   return 0;
 }
@@ -478,7 +479,11 @@ int run_pipeline(const Plan& p, const uint32_t* d_scalars, const uint4* d_points
   }
   const uint4* group_w = inW;  // nb >= 4 (c >= 3): at least one reduction level has run
   if (mark(st, "reduce")) return 1;
-  if (p.g2) LAUNCH(k_finalize_single_g2, 1, 32, st, group_w, q.W, q.c, d_out);
+  if (p.g2 && q.W <= 96) {
+    // window combine over the twisted Frobenius: 4 W parallel 64-doubling chains + a tree instead of ~250 serial doublings
+    uint4* fin = arena.take<uint4>((size_t)4 * q.W * 24);
+    LAUNCH(k_finalize_single_g2_glv, 1, 384, st, group_w, q.W, q.c, fin, d_out);
+  } else if (p.g2) LAUNCH(k_finalize_single_g2, 1, 32, st, group_w, q.W, q.c, d_out);
   else if (q.batch) LAUNCH(k_finalize_batch, cdiv(q.groups, 128), 128, st, group_w, q.groups, d_out);
   else LAUNCH(k_finalize_single, 1, 32, st, group_w, q.W, q.c, d_out);
   if (mark(st, "finalize")) return 1;

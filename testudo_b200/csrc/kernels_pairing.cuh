@@ -759,6 +759,98 @@ __global__ void __launch_bounds__(128) k_compress_g2_glv4w(uint4* __restrict__ a
   store_affine2(a + 12 * (uint64_t)i, o);
 }
 
+// Window combine of a single G2 MSM over the endomorphism. The Horner form sum_w 2^(c w) S_w is a chain of ~250
+// doublings on ONE thread (11 ms: the latency floor of every G2 MSM the reference issues -- commit_g2, the PST opening
+// proofs). Here thread (w, j) multiplies psi^j(S_w) by the j-th base-x digit of 2^(c w) mod r (64 doublings), and a
+// shared-memory tree adds the 4 W partial sums. psi on XYZZ coordinates: (conj X g_2, conj Y g_3, conj ZZ, conj ZZZ).
+// One CTA of 4 W threads (W <= 96); the partial sums live in global scratch (4 W x 384 B).
+__device__ __forceinline__ void xyzz2_psi(Xyzz2& r, const Xyzz2& p) {
+  const Fq g2c = fq_from_table(FQ12_C(FROB1)[1][0]);
+  const Fq g3c = fq_from_table(FQ12_C(FROB1)[2][0]);
+  fq2_conj(r.x, p.x);
+  fq2_scale(r.x, r.x, g2c);
+  fq2_conj(r.y, p.y);
+  fq2_scale(r.y, r.y, g3c);
+  fq2_conj(r.zz, p.zz);
+  fq2_conj(r.zzz, p.zzz);
+}
+__global__ void __launch_bounds__(384) k_finalize_single_g2_glv(const uint4* __restrict__ group_w, int W, int c,
+                                                                uint4* __restrict__ scratch, uint4* __restrict__ out_affine) {
+  const int t = threadIdx.x, w = t >> 2, j = t & 3;
+  const int total = 4 * W;
+  if (t < total) {
+    // base-x digit j of 2^(c w) mod r  (c w <= 253 < 2 * 253: at most one subtraction of r)
+    uint64_t q[4] = {0, 0, 0, 0};
+    const int e = c * w;
+    q[e >> 6] = 1ull << (e & 63);
+    if (e >= 252) {   // r has 253 bits: 2^252 < r < 2^253
+      uint64_t rr[4];
+      for (int i = 0; i < 4; i++) rr[i] = (uint64_t)FrParams::p(2 * i) | ((uint64_t)FrParams::p(2 * i + 1) << 32);
+      bool ge = true;
+      for (int i = 3; i >= 0; i--) {
+        if (q[i] != rr[i]) {
+          ge = q[i] > rr[i];
+          break;
+        }
+      }
+      if (ge) {
+        uint64_t borrow = 0;
+        for (int i = 0; i < 4; i++) {
+          const uint64_t d = q[i] - rr[i] - borrow;
+          borrow = (q[i] < rr[i] + borrow) || (rr[i] + borrow < borrow) ? 1 : 0;
+          q[i] = d;
+        }
+      }
+    }
+    uint64_t digit = 0;
+    for (int d = 0; d <= j; d++) {
+      uint64_t rem = 0, nq[4] = {0, 0, 0, 0};
+      for (int bit = 255; bit >= 0; bit--) {
+        const uint64_t top = rem >> 63;
+        rem = (rem << 1) | ((q[bit >> 6] >> (bit & 63)) & 1);
+        if (top || rem >= BLS_X) {
+          rem -= BLS_X;
+          nq[bit >> 6] |= 1ull << (bit & 63);
+        }
+      }
+      digit = rem;
+      for (int i = 0; i < 4; i++) q[i] = nq[i];
+    }
+    Xyzz2 b, acc;
+    load_xyzz2(b, group_w + 24 * w);
+    for (int i = 0; i < j; i++) xyzz2_psi(b, b);
+    xyzz2_set_inf(acc);
+    bool started = false;
+    for (int bit = 63; bit >= 0; bit--) {
+      if (started) xyzz2_dbl_ni(&acc);
+      if ((digit >> bit) & 1) {
+        xyzz2_add_ni(&acc, &b);
+        started = true;
+      }
+    }
+    store_xyzz2(scratch + 24 * t, acc);
+  }
+  // tree sum over the 4 W partial values
+  for (int stride = 256; stride >= 1; stride >>= 1) {
+    __syncthreads();
+    if (t < stride && t + stride < total) {
+      Xyzz2 x, y;
+      load_xyzz2(x, scratch + 24 * t);
+      load_xyzz2(y, scratch + 24 * (t + stride));
+      xyzz2_add_ni(&x, &y);
+      store_xyzz2(scratch + 24 * t, x);
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    Xyzz2 x;
+    load_xyzz2(x, scratch);
+    Affine2 a;
+    xyzz2_to_affine_ni(&a, &x);
+    store_affine2(out_affine, a);
+  }
+}
+
 // G1 fold over phi(x, y) = (beta x, y) = [lambda](x, y), lambda = x^2 - 1 < 2^127: k = k1 lambda + k0 with k0 < lambda and
 // k1 = floor(k / lambda) < 2^127 (r < lambda^2 + lambda + 1), then a 2-way simultaneous multiplication, 127 doublings.
 // digits[0..3] = k0, digits[4..7] = k1 (128 bits each). Same precondition: the points lie in G1's order-r subgroup.
