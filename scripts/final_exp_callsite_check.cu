@@ -1,6 +1,9 @@
+// Reproducer / regression harness for the call-site-dependent NVVM miscompiles described in DESIGN.md (pairing products):
+// the same final exponentiation through differently shaped kernels, device vs the host build of the same header.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -o /tmp/fe_check scripts/final_exp_callsite_check.cu
 #include <cstdio>
 #include <cstring>
-#include "../../testudo_b200/csrc/kernels_pairing.cuh"
+#include "../testudo_b200/csrc/kernels_pairing.cuh"
 using namespace tb;
 __global__ void __launch_bounds__(32) k_a(const uint4* a, uint4* out, int stop) {
   Fq12 x, r;
@@ -78,8 +81,8 @@ int main() {
     cudaMemset(dr, 0, 576); k_b<<<1, 1>>>(da, dr, 1000); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_b<<<1,1>>>", o, ho);
     cudaMemset(dr, 0, 576); k_c<<<1, 1>>>(da, dr, 1000); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_c<<<1,1>>>", o, ho);
     cudaMemset(dr, 0, 576); k_d<<<1, 1>>>(da, dr, 1000); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_d<<<1,1>>>", o, ho);
-    cudaMemset(dr, 0, 576); k_final_exp<<<1, 32>>>(da, dr); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_final_exp<<<1,32>>>", o, ho);
-    cudaMemset(dr, 0, 576); k_final_exp<<<1, 1>>>(da, dr); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_final_exp<<<1,1>>>", o, ho);
+    cudaMemset(dr, 0, 576); k_final_exp<<<1, W12_THREADS>>>(da, dr); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_final_exp<<<1,32>>>", o, ho);
+    cudaMemset(dr, 0, 576); k_final_exp<<<1, W12_THREADS>>>(da, dr); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_final_exp<<<1,1>>>", o, ho);
   }
   k_e<<<1, 1>>>(da, dr); cudaDeviceSynchronize(); cudaMemcpy(o, dr, 576, cudaMemcpyDeviceToHost); cmp("k_e const stop", o, ho);
   int st[3] = {13, 9, 5};
