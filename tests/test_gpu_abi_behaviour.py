@@ -102,3 +102,49 @@ def test_host_facing_msm_chunked_path(engine):
                                            ctypes.c_void_p(out.data_ptr()), None))
         _lib.check(engine.tb200_stream_sync())
         assert np.array_equal(out.cpu().numpy().view(np.uint64), got), skew
+
+
+def test_pairing_argument_errors_and_concurrent_callers(engine):
+    """Error returns of the pairing entry points and thread-safety: pairing products issued from
+    several host threads at once (the reference runs its two pairings_product calls as rayon tasks, src/mipp.rs:87-94)."""
+    from oracle import bls12_377_g2 as o2
+    from oracle import pairing as pr
+    from testudo_b200 import pairing
+
+    gt = np.zeros(72, np.uint64)
+    assert engine.tb200_multi_pairing(None, None, 3, P(gt)) == -1
+    assert engine.tb200_multi_pairing(None, None, 0, None) == -1
+    assert engine.tb200_miller_product(None, None, 2, P(gt)) == -1
+    assert engine.tb200_gt_product_final_exp(None, 2, P(gt)) == -1
+    assert engine.tb200_gt_pow(None, None, 0, 0, None) == 0                                  # empty batch is a no-op
+    assert engine.tb200_gt_pow(None, None, 1, 0, P(gt)) == -1
+    pts, _ = o.rand_points(4, 81)
+    qs, _ = o2.rand_points(4, 82)
+    A = h.pts_to_np(pts)
+    B = np.array([o2.affine_to_words(q) for q in qs], dtype=np.uint64)
+    y = h.scalars_to_np([1, 2, 3, 4], mont=True)
+    ha, hh = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(engine.tb200_mipp_g1_begin(P(A), P(y), 4, 1, ctypes.byref(ha)))
+    _lib.check(engine.tb200_mipp_g2_begin(P(B[:2].copy()), 2, 1, ctypes.byref(hh)))
+    u = np.zeros(12, np.uint64)
+    assert engine.tb200_mipp_cross_all(ha, hh, P(u), P(u), P(gt), P(gt)) == -1               # lengths differ
+    assert b"differ" in engine.tb200_last_error()
+    assert engine.tb200_mipp_pairing_cross(ha, hh, P(gt), P(gt)) == -1
+    assert engine.tb200_mipp_cross_all(ha, None, P(u), P(u), P(gt), P(gt)) == -1
+    engine.tb200_mipp_g1_end(ha)
+    engine.tb200_mipp_g2_end(hh)
+    exp = np.array(pr.to_words(pr.multi_pairing(pts, qs)), dtype=np.uint64)
+    results, errors = [None] * 6, []
+
+    def worker(k):
+        try:
+            results[k] = pairing.multi_pairing(A, B)
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors and all(np.array_equal(r, exp) for r in results)
