@@ -63,7 +63,9 @@ int tb200_msm_g1_dev(const void* d_bases_xy, const void* d_scalars, size_t n, un
  * `ark_bls12_377::G2Projective`: the G2 openings of `MultilinearPC::open` (src/sqrt_pst.rs:225) and MIPP's
  * `commit_g2` (src/mipp.rs:114). A G2 affine point is 24 u64 = x.c0[6] || x.c1[6] || y.c0[6] || y.c1[6]
  * (Fq2 = Fq[u]/(u^2+5), coordinates in Montgomery form, little-endian limbs); all-zero == identity.
- * Scalars and `flags` as for tb200_msm_g1. The result is the canonical affine point. */
+ * Scalars and `flags` as for tb200_msm_g1. The result is the canonical affine point.
+ * PRECONDITION: the bases lie in G2, the order-r subgroup of the twist (always true for a CRS): the window combine
+ * uses the twisted Frobenius, which is multiplication by the curve parameter only there. */
 int tb200_msm_g2(const uint64_t* bases, const uint64_t* scalars, size_t n, unsigned flags, uint64_t out[24]);
 /* Same with DEVICE pointers (16-byte aligned); result (192 bytes) written to d_out; returns after enqueueing. */
 int tb200_msm_g2_dev(const void* d_bases, const void* d_scalars, size_t n, unsigned flags, void* d_out,
