@@ -129,7 +129,9 @@ typedef struct tb200_mipp* tb200_mipp_t;
 int tb200_mipp_g1_begin(const uint64_t* a_xy, const uint64_t* y, size_t n, unsigned flags, tb200_mipp_t* out);
 size_t tb200_mipp_g1_len(tb200_mipp_t h);
 int tb200_mipp_g1_cross(tb200_mipp_t h, uint64_t comm_u_l[12], uint64_t comm_u_r[12]);
-/* c and c_inv are Fr scalars in the representation selected by `flags` at begin() */
+/* c and c_inv are Fr scalars in the representation selected by `flags` at begin(). The fold is only ENQUEUED (the
+ * scalars are copied before the call returns); every later call on the handle is ordered behind it. It runs over the
+ * G1 endomorphism (127 doublings), so the vector must lie in the order-r subgroup -- true for commitments. */
 int tb200_mipp_g1_fold(tb200_mipp_t h, const uint64_t c[4], const uint64_t c_inv[4]);
 /* current vectors (len() entries): a as affine points, y as scalars in the begin() representation */
 int tb200_mipp_g1_read(tb200_mipp_t h, uint64_t* a_xy, uint64_t* y);
