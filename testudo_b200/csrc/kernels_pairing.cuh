@@ -905,24 +905,28 @@ __global__ void __launch_bounds__(128) k_compress_g1_glv(uint4* __restrict__ a, 
   const Fq beta = fq_from_table(FQ12_C(G1_BETA));
   fq_mul_ol(&pr.x, &r.x, &beta);           // phi(r); the identity (0, 0) stays (0, 0)
   pr.y = r.y;
+  // the lazily reduced group law of the MSM hot loop (g1_fast.cuh: one out-of-line multiplier): with the canonical
+  // operations the three inlined group routines are ~350 KB of SASS and the kernel stalled on instruction fetch
+  // (ncu: `no_instruction` 2.06 per issue)
   Xyzz t3;                                 // r + phi(r)
   xyzz_set_inf(t3);
-  xyzz_madd_ni(&t3, &r);
-  xyzz_madd_ni(&t3, &pr);
+  xyzz_madd_fast_ni(&t3, &r);
+  xyzz_madd_fast_ni(&t3, &pr);
   Xyzz acc;
   xyzz_set_inf(acc);
   bool started = false;
   for (int limb = 3; limb >= 0; limb--) {
     for (int bit = 31; bit >= 0; bit--) {
-      if (started) xyzz_dbl_ni(&acc);
+      if (started) xyzz_dbl_fast_ni(&acc);
       const int m = (int)((k0[limb] >> bit) & 1) | ((int)((k1[limb] >> bit) & 1) << 1);
-      if (m == 1) xyzz_madd_ni(&acc, &r);
-      else if (m == 2) xyzz_madd_ni(&acc, &pr);
-      else if (m == 3) xyzz_add_ni(&acc, &t3);
+      if (m == 1) xyzz_madd_fast_ni(&acc, &r);
+      else if (m == 2) xyzz_madd_fast_ni(&acc, &pr);
+      else if (m == 3) xyzz_add_fast_ni(&acc, &t3);
       started = started || m != 0;
     }
   }
-  xyzz_madd_ni(&acc, &l);
+  xyzz_madd_fast_ni(&acc, &l);
+  xyzz_canon(acc);
   Affine o;
   xyzz_to_affine_ni(&o, &acc);
   store_affine(a + 6 * (uint64_t)i, o);
