@@ -14,9 +14,14 @@
  * Return value: 0 on success; negative = argument error (TB200_E_*); positive = cudaError_t.
  * `tb200_last_error()` gives a thread-local message. All calls are blocking and thread-safe (they are issued
  * concurrently by rayon workers in the reference: src/sqrt_pst.rs:121-125, src/mipp.rs:77-85 via
- * src/macros.rs:1-17); the library serialises them on one device context per process.
- * One process drives one GPU (tb200_init(device)); multi-GPU runs use one process per GPU and combine the
- * per-GPU partial results with tb200_g1_sum (see testudo_b200/parallel.py for the NCCL all-gather).
+ * src/macros.rs:1-17); the library serialises them.
+ * Multi-GPU: ONE process drives all the GPUs it names in tb200_init_devices -- the reference is one
+ * process that fans rows out internally (src/sqrt_pst.rs:121-125). The host-facing entry points then shard by
+ * themselves: a large single MSM by point range, row commitments by row range over the replicated SRS, a pairing
+ * product by pair range; each GPU's share is uploaded and computed by its own worker thread, and the per-GPU partial
+ * results are combined by one ncclAllGather (single-process NCCL clique over NVLink) inside the call. The *_dev
+ * entry points, MIPP and the PST openings run on the primary device (devices[0]). One process per GPU (torchrun,
+ * testudo_b200/parallel.py) remains possible: every process then initialises its own single device.
  */
 #ifndef TESTUDO_B200_H
 #define TESTUDO_B200_H
@@ -39,6 +44,12 @@ extern "C" {
 /* Select `device` (-1 = current) and create the context; idempotent. Fails loudly without a CUDA device:
  * there is no CPU fallback anywhere in this library. */
 int tb200_init(int device);
+/* One context per listed CUDA ordinal, devices[0] = primary; builds the NCCL clique when ndevices > 1 (libnccl is
+ * dlopen'ed then, not before). Idempotent; a later call may append devices behind the same primary (SRS handles loaded
+ * before must be reloaded). Replaces nothing in the reference (it has no device notion) -- called once by the -sys
+ * crate's initialiser, INTEGRATION.md. */
+int tb200_init_devices(const int* devices, int ndevices);
+int tb200_device_count(void); /* contexts created so far (0 before init) */
 void tb200_shutdown(void);
 const char* tb200_last_error(void);
 /* number of kernels this library has launched since init / reset (bench.py reports it as gpu_launches) */
@@ -57,6 +68,11 @@ int tb200_msm_g1(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, un
  * `stream` is a cudaStream_t (NULL = the library's stream); the call returns after enqueueing. */
 int tb200_msm_g1_dev(const void* d_bases_xy, const void* d_scalars, size_t n, unsigned flags,
                      void* d_out_xy, void* stream);
+/* One MSM whose inputs are RESIDENT on the GPUs: device slot i (order of tb200_init_devices) holds n[i] points and
+ * scalars at d_bases_xy[i] / d_scalars[i] (n[i] may be 0). Per-GPU partial points, one all-gather of 96 bytes per GPU,
+ * sum on the primary, result to the host ("single large MSM"). Blocking. */
+int tb200_msm_g1_sharded_dev(const void* const* d_bases_xy, const void* const* d_scalars, const size_t* n,
+                             unsigned flags, uint64_t out_xy[12]);
 
 /* ---- G2 multi-scalar multiplication ------------------------------------------------
  * Replaces `<E::G2 as VariableBaseMSM>::msm_unchecked / msm_bigint` + `.into_affine()` for
@@ -119,6 +135,24 @@ int tb200_msm_g1_batch_ptrs(tb200_srs_t srs, const uint64_t* const* row_ptrs, si
                             unsigned flags, uint64_t* out_xy);
 int tb200_msm_g1_batch_dev(tb200_srs_t srs, const void* d_scalars, size_t rows, size_t cols, ptrdiff_t row_stride,
                            ptrdiff_t col_stride, unsigned flags, void* d_out_xy, void* stream);
+/* Hyrax rows WITH blinds: out[i] = MSM(gens_n.G, row_i) + blinds[i] * h -- `PedersenCommit::commit_slice`
+ * (src/commitments.rs:80-86) under `DensePolynomial::commit_inner` (src/dense_mlpoly.rs:315-329) with
+ * `commit(gens, random_tape)` (src/dense_mlpoly.rs:349-377). The blinding base h is loaded as one extra column of the
+ * SRS (tb200_srs_load_blinded) and the blind rides along as the row's extra scalar: still ONE batched call.
+ * scalars: rows x cols contiguous; cols == tb200_srs_size(srs) (the size WITHOUT h). */
+int tb200_srs_load_blinded(const uint64_t* bases_xy, size_t n, const uint64_t h_xy[12], int window_bits, tb200_srs_t* out);
+int tb200_msm_g1_batch_blinded(tb200_srs_t srs, const uint64_t* scalars, size_t rows, size_t cols, const uint64_t* blinds,
+                               unsigned flags, uint64_t* out_xy);
+/* `Polynomial::commit` in one call (src/sqrt_pst.rs:117-149): the row commitments (-> out_rows_xy, rows x 12) AND the IPP
+ * commitment t = prod_i e(C_i, h_vec[i]) (-> out_t; h_vec = ck.powers_of_h[odd], rows x 24 u64, src/sqrt_pst.rs:128-144).
+ * With several GPUs every GPU commits its row range, pairs ITS rows with its slice of h_vec (the rows never leave the GPU
+ * between the two stages) and contributes one partial Miller product; one all-gather of 576 bytes per GPU and ONE final
+ * exponentiation on the primary. Rows as separate heap buffers (self.polys) or as a strided view of Z. */
+int tb200_sqrt_pst_commit(tb200_srs_t srs, const uint64_t* const* row_ptrs, size_t rows, size_t cols, unsigned flags,
+                          const uint64_t* h_vec, uint64_t* out_rows_xy, uint64_t out_t[72]);
+int tb200_sqrt_pst_commit_strided(tb200_srs_t srs, const uint64_t* scalars, size_t rows, size_t cols,
+                                  ptrdiff_t row_stride, ptrdiff_t col_stride, unsigned flags, const uint64_t* h_vec,
+                                  uint64_t* out_rows_xy, uint64_t out_t[72]);
 
 /* ---- MIPP G1 steps, device-resident across rounds --------------------------------------------------------
  * Replaces the G1 work of `MippProof::prove` (src/mipp.rs:58-120): per round
@@ -146,6 +180,12 @@ int tb200_dev_free(void* d_ptr);
 int tb200_dev_upload(void* d_dst, const void* h_src, size_t bytes);
 int tb200_dev_download(void* h_dst, const void* d_src, size_t bytes);
 int tb200_stream_sync(void); /* wait for work enqueued on the library's stream by *_dev calls with stream == NULL */
+/* Page-locked host memory usable from every device of the library (cudaHostAlloc portable / cudaHostRegister): uploads
+ * from such buffers are asynchronous and run at full PCIe rate; pageable buffers work too but are staged by the driver. */
+int tb200_host_alloc(size_t bytes, void** out);
+int tb200_host_free(void* h_ptr);
+int tb200_host_register(void* h_ptr, size_t bytes);
+int tb200_host_unregister(void* h_ptr);
 
 /* ---- sqrt_pst scalar work on the device (Fr values in ark Montgomery form) ---------------
  * chis_out[i] = prod_j (bit(i, m-1-j) ? b[j] : 1 - b[j]), i < 2^m  -- `Polynomial::get_chi_i`, src/sqrt_pst.rs:152-166 */
@@ -173,12 +213,17 @@ double tb200_stage_ms(const char* stage);
 int tb200_last_geometry(int* c, int* windows, uint64_t* entries, uint64_t* buckets, int* segment);
 /* override the automatic window choice for single MSMs (0 = automatic) */
 void tb200_set_window_bits(int c);
-/* bucket-accumulation method: 0 = automatic (currently 4); 1 = XYZZ mixed additions over balanced segments with
- * register operands (k_accumulate); 2 = batched-affine pairwise rounds (Montgomery's trick; experimental, slower
- * on B200 -- DESIGN.md); 3 = XYZZ segments with shared-memory operand slots (k_accumulate_s); 4 = as 3 with the
- * sum-of-two-products reduction for Y3 (mont_mul2_lazy; what 0 selects); 5 = as 4 with the Karatsuba multiplier for the
- * single products (mont_kara.cuh; measured no faster). Identical results. */
+/* bucket-accumulation method (XYZZ mixed additions over balanced segments, operands in shared-memory slots,
+ * k_accumulate_s): 0 = automatic (= 4); 3 = plain CIOS products; 4 = Y3 as one fused sum of two products
+ * (mont_mul2_lazy). Identical results. The measured dead ends (register operands, batched-affine rounds, Karatsuba)
+ * live in csrc/experimental/ and are not part of the library. */
 void tb200_set_accumulate_mode(int mode);
+/* test / tuning hooks: the number of sorted entries one pipeline pass may index (default 2^32 - 1024; a single MSM
+ * with more entries, n * windows, runs as point-range passes over one persistent bucket array; 0 restores the default),
+ * and the work per GPU (points of a single MSM, scalars of a batch) below which a host-facing call is NOT sharded
+ * (default 2^18; 0 restores it). */
+void tb200_set_pass_entries_max(uint64_t entries);
+void tb200_set_shard_min(size_t units);
 /* integer-pipe microbenchmark: runs `iters` dependent-chain iterations of wide MACs on every SM and returns the
  * achieved 32x32->64 multiply-accumulates per second in *out_macs_per_s (kind: 0 = IMAD.WIDE.U32 reg-reg,
  * 1 = IMAD (32-bit lo), 2 = full Fq Montgomery multiplications per second). */

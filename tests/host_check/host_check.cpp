@@ -3,7 +3,7 @@
 #include <cstring>
 #include "../../testudo_b200/csrc/g1_fast.cuh"
 #include "../../testudo_b200/csrc/digits.cuh"
-#include "../../testudo_b200/csrc/mont_kara.cuh"
+#include "../../testudo_b200/csrc/experimental/mont_kara.cuh"
 #include "../../testudo_b200/csrc/g2.cuh"
 #include "../../testudo_b200/csrc/fq12.cuh"
 using namespace tb;

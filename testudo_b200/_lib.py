@@ -2,6 +2,7 @@
 present, loading / initialising raises."""
 from __future__ import annotations
 
+import atexit
 import ctypes
 import os
 import threading
@@ -24,12 +25,24 @@ c_int = ctypes.c_int
 # every symbol include/testudo_b200.h declares: (restype, argtypes)
 SIGNATURES = {
     "tb200_init": (c_int, [c_int]),
+    "tb200_init_devices": (c_int, [ctypes.POINTER(c_int), c_int]),
+    "tb200_device_count": (c_int, []),
     "tb200_shutdown": (None, []),
     "tb200_last_error": (ctypes.c_char_p, []),
     "tb200_launch_count": (ctypes.c_uint64, []),
     "tb200_reset_launch_count": (None, []),
     "tb200_msm_g1": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
     "tb200_msm_g1_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p, c_void_p]),
+    "tb200_msm_g1_sharded_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_uint, c_void_p]),
+    "tb200_srs_load_blinded": (c_int, [c_void_p, c_size_t, c_void_p, c_int, ctypes.POINTER(c_void_p)]),
+    "tb200_msm_g1_batch_blinded": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p, c_uint, c_void_p]),
+    "tb200_sqrt_pst_commit": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint, c_void_p, c_void_p, c_void_p]),
+    "tb200_sqrt_pst_commit_strided": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_ssize_t, c_ssize_t, c_uint,
+                                              c_void_p, c_void_p, c_void_p]),
+    "tb200_host_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
+    "tb200_host_free": (c_int, [c_void_p]),
+    "tb200_host_register": (c_int, [c_void_p, c_size_t]),
+    "tb200_host_unregister": (c_int, [c_void_p]),
     "tb200_srs_load": (c_int, [c_void_p, c_size_t, c_int, ctypes.POINTER(c_void_p)]),
     "tb200_srs_free": (c_int, [c_void_p]),
     "tb200_srs_size": (c_size_t, [c_void_p]),
@@ -81,6 +94,8 @@ SIGNATURES = {
                                     ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(c_int)]),
     "tb200_set_window_bits": (None, [c_int]),
     "tb200_set_accumulate_mode": (None, [c_int]),
+    "tb200_set_pass_entries_max": (None, [ctypes.c_uint64]),
+    "tb200_set_shard_min": (None, [c_size_t]),
     "tb200_int_pipe_peak": (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_double)]),
     "tb200_test_fq_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "tb200_test_fq_addsub": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
@@ -113,6 +128,7 @@ def load() -> ctypes.CDLL:
                 fn.restype = res
                 fn.argtypes = args
             _lib = lib
+            atexit.register(lib.tb200_shutdown)  # joins the per-GPU worker threads, destroys the NCCL clique
     return _lib
 
 
@@ -122,13 +138,32 @@ def check(rc: int) -> None:
 
 
 def init(device: int = -1) -> ctypes.CDLL:
-    """Create the CUDA context on `device` (raises without a GPU)."""
+    """Create the CUDA context on `device` (raises without a GPU). TB200_DEVICES="0,1,..." in the environment makes the
+    first initialisation a multi-device one (tb200_init_devices)."""
     global _inited
     lib = load()
     if not _inited:
-        check(lib.tb200_init(device))
+        env = os.environ.get("TB200_DEVICES", "").strip()
+        if env and device < 0:
+            init_devices([int(x) for x in env.split(",") if x.strip()])
+        else:
+            check(lib.tb200_init(device))
         _inited = True
     return lib
+
+
+def init_devices(devices) -> ctypes.CDLL:
+    """One process, several GPUs: `devices[0]` is the primary (tb200_init_devices)."""
+    global _inited
+    lib = load()
+    arr = (c_int * len(devices))(*devices)
+    check(lib.tb200_init_devices(arr, len(devices)))
+    _inited = True
+    return lib
+
+
+def device_count() -> int:
+    return load().tb200_device_count()
 
 
 def engine() -> ctypes.CDLL:

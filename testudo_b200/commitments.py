@@ -23,6 +23,7 @@ class MultiCommitGens:
         self.h = np.ascontiguousarray(h, dtype=np.uint64).reshape(12)
         self.n = len(self.G)
         self._srs: Optional[ctypes.c_void_p] = None
+        self._srs_blinded: Optional[ctypes.c_void_p] = None
 
     def srs(self):
         if self._srs is None:
@@ -31,10 +32,19 @@ class MultiCommitGens:
             self._srs = hnd
         return self._srs
 
+    def srs_blinded(self):
+        """G with h appended as one extra column (tb200_srs_load_blinded): the blind rides along as a row's last scalar."""
+        if self._srs_blinded is None:
+            hnd = ctypes.c_void_p()
+            _lib.check(_lib.engine().tb200_srs_load_blinded(_ptr(self.G), self.n, _ptr(self.h), 0, ctypes.byref(hnd)))
+            self._srs_blinded = hnd
+        return self._srs_blinded
+
     def close(self):
-        if self._srs is not None:
-            _lib.check(_lib.engine().tb200_srs_free(self._srs))
-            self._srs = None
+        for name in ("_srs", "_srs_blinded"):
+            if getattr(self, name) is not None:
+                _lib.check(_lib.engine().tb200_srs_free(getattr(self, name)))
+                setattr(self, name, None)
 
 
 class PedersenCommit:
@@ -59,8 +69,9 @@ class PedersenCommit:
 
 def commit_inner(Z_mont, blinds_mont, gens: MultiCommitGens) -> np.ndarray:
     """`DensePolynomial::commit_inner` (src/dense_mlpoly.rs:315-329): C[i] = commit_slice(Z[R*i .. R*(i+1)], blinds[i]).
-    The L_size row MSMs over the shared gens.G are one batched call; the `h * blind` terms (zero at every call site
-    that passes `commit(gens, false)`) are added by a second, tiny batched step."""
+    The L_size row MSMs over the shared gens.G are ONE batched call, with or without blinds: `commit(gens, false)` passes
+    zero blinds and takes the plain SRS; with blinds (src/dense_mlpoly.rs:349-377) h is the extra column
+    of the SRS and blinds[i] the extra scalar of row i."""
     z = np.ascontiguousarray(Z_mont, dtype=np.uint64).reshape(-1, 4)
     blinds = np.ascontiguousarray(blinds_mont, dtype=np.uint64).reshape(-1, 4)
     L = len(blinds)
@@ -68,11 +79,9 @@ def commit_inner(Z_mont, blinds_mont, gens: MultiCommitGens) -> np.ndarray:
     assert L * R == len(z) and R == gens.n
     lib = _lib.engine()
     rows = np.zeros((L, 12), dtype=np.uint64)
-    _lib.check(lib.tb200_msm_g1_batch(gens.srs(), _ptr(z), L, R, R, 1, _lib.SCALARS_MONT, _ptr(rows)))
     if not blinds.any():
-        return rows
-    out = np.zeros_like(rows)
-    for i in range(L):  # blinded rows: C_i + blind_i * h
-        hb = msm.msm_unchecked(gens.h.reshape(1, 12), blinds[i].reshape(1, 4))
-        out[i] = msm.g1_sum(np.stack([rows[i], hb]))
-    return out
+        _lib.check(lib.tb200_msm_g1_batch(gens.srs(), _ptr(z), L, R, R, 1, _lib.SCALARS_MONT, _ptr(rows)))
+    else:
+        _lib.check(lib.tb200_msm_g1_batch_blinded(gens.srs_blinded(), _ptr(z), L, R, _ptr(blinds), _lib.SCALARS_MONT,
+                                                  _ptr(rows)))
+    return rows

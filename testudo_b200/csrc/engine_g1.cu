@@ -1,0 +1,886 @@
+// G1 unit of the engine: the kernels of kernels.cuh / kernels_smem.cuh and everything that launches
+// them -- the MSM pipeline (digits -> scan -> scatter -> accumulate -> fix-up -> reduce -> finalize), the shared-base
+// batch, the SRS window tables, the device-resident MIPP G1 loop, the PST quotient loop and the Fr helpers of sqrt_pst.
+// There is no CPU arithmetic path in this file (nor anywhere in the library).
+#include <algorithm>
+
+#include "engine.h"
+#include "kernels_smem.cuh"
+
+using namespace tb;
+
+namespace tbe {
+
+// ---- window selection ---------------------------------------------------------------------------------------
+// cost in mixed-addition units: accumulation entries + ~4 adds per bucket for the hierarchical reduction
+static int pick_c_single(uint64_t n) {
+  if (E.forced_c) return E.forced_c;
+  int best = 3;
+  double bestc = 1e300;
+  for (int c = 3; c <= 20; c++) {
+    int W = num_windows(c);
+    double cost = (double)W * ((double)n + 4.0 * (double)(1u << (c - 1)));
+    int top_bits = SCALAR_BITS - (W - 1) * c;  // payload bits of the top window
+    if (top_bits < 4) cost += 0.5 * (double)n;  // degenerate top window: contended atomics, one giant bucket
+    if (cost < bestc) {
+      bestc = cost;
+      best = c;
+    }
+  }
+  return best;
+}
+int pick_c_batch(uint64_t cols) {
+  int best = 3;
+  double bestc = 1e300;
+  for (int c = 3; c <= 16; c++) {
+    int W = num_windows(c);
+    double cost = (double)W * (double)cols + 4.0 * (double)(1u << (c - 1));
+    if (cost < bestc) {
+      bestc = cost;
+      best = c;
+    }
+  }
+  return best;
+}
+
+// ---- the pipeline --------------------------------------------------------------------------------------------
+struct Plan {
+  MsmGeom geo;
+  uint64_t M_max, B;
+  uint32_t K, S_max, ntiles;
+  std::vector<uint32_t> Ls;  // reduction fan-in per level
+  size_t bytes;
+  bool g2 = false;           // points are G2 (Fq2 coordinates: 192-byte affine, 384-byte XYZZ); single MSMs only
+};
+
+// a single MSM processed as point-range chunks that accumulate into ONE persistent bucket array
+struct ChunkCtl {
+  uint32_t ref_base;  // global index of the chunk's first point
+  uint4* buckets;     // B * 192 B, all zero (= identity) before the first chunk
+  bool last;          // run the reduction / finalisation after this chunk
+};
+
+static int make_plan(const Ctx& g, Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs, int c, int batch,
+                     unsigned flags, bool g2 = false) {
+  MsmGeom& q = p.geo;
+  p.g2 = g2;
+  const size_t pw = g2 ? 2 : 1;  // point width relative to G1
+  q.ref_base = 0;
+  q.rows = rows;
+  q.cols = cols;
+  q.row_stride = rs;
+  q.col_stride = cs;
+  q.c = c;
+  q.W = num_windows(c);
+  q.nb = 1u << (c - 1);
+  q.batch = batch;
+  q.groups = batch ? rows : (uint32_t)q.W;
+  q.mont = (flags & TB200_SCALARS_MONT) ? 1 : 0;
+  p.M_max = (uint64_t)rows * cols * q.W;
+  p.B = (uint64_t)q.groups * q.nb;
+  if (p.M_max > E.pass_entries_max || p.B >= (1ull << 31))
+    return fail(TB200_E_LIMIT, "MSM too large for one pass: %llu entries, %llu buckets", (unsigned long long)p.M_max,
+                (unsigned long long)p.B);
+  uint64_t target_threads = (uint64_t)g.sms * 3 * ACCS_THREADS * 4;
+  uint64_t K = (p.M_max + target_threads - 1) / target_threads;
+  p.K = (uint32_t)std::min<uint64_t>(256, std::max<uint64_t>(4, K));
+  p.S_max = cdiv(std::max<uint64_t>(p.M_max, 1), p.K);
+  p.ntiles = (uint32_t)(p.B / SCAN_TILE + 1);
+  p.Ls.clear();
+  // Fan-in 32 at level 0 (throughput-bound: millions of buckets). The levels above it of a SINGLE MSM hold few
+  // elements and are latency-bound (2L - 1 sequential additions + log2(ell) doublings per thread): fan-in 8 there
+  // (measured at 2^24, c = 20: 3.5 -> 1.9 ms for the upper levels). Batches keep 32: thousands of rows fill the GPU.
+  for (uint32_t n = q.nb; n > 1;) {
+    uint32_t L = std::min<uint32_t>(n, (batch || p.Ls.empty()) ? 32 : 8);
+    p.Ls.push_back(L);
+    n /= L;
+  }
+  size_t b = 0;
+  b += Arena::pad((p.B + 1) * 4) * 2;  // counts, starts
+  b += Arena::pad(p.B * 4);            // cursors
+  b += Arena::pad((size_t)p.ntiles * 4 + 4);
+  b += Arena::pad(std::max<uint64_t>(p.M_max, 1) * 4);  // entries
+  b += Arena::pad(p.B * 192 * pw);                      // buckets
+  b += Arena::pad((size_t)p.S_max * 192 * pw) + Arena::pad((size_t)p.S_max * 4);
+  uint64_t n = p.B;
+  for (uint32_t L : p.Ls) {
+    n /= L;
+    b += Arena::pad(n * 192 * pw) * 2;
+  }
+  b += Arena::pad((size_t)q.groups * 192 * pw) * 2 + 4096;
+  if (g2) b += Arena::pad((size_t)4 * 96 * 384);  // window-combine partial sums (k_finalize_single_g2_glv)
+  p.bytes = b;
+  return 0;
+}
+
+// Runs the whole pipeline on `st`. d_points: affine points indexed by entry refs. d_out: groups*96 B (batch) or 96 B.
+// The caller has acquired `arena` for `st` (Arena::acquire) and releases it afterwards.
+static int run_pipeline(Ctx& g, const Plan& p, const uint32_t* d_scalars, const uint4* d_points, uint4* d_out,
+                        cudaStream_t st, cudaEvent_t points_ready, Arena& arena, const ChunkCtl* chunk = nullptr) {
+  MsmGeom q = p.geo;
+  if (chunk) q.ref_base = chunk->ref_base;
+  const size_t pw = p.g2 ? 2 : 1;
+  int rc = arena.reserve(p.bytes);
+  if (rc) return fail(rc, "workspace allocation of %zu bytes failed: %s", p.bytes, cudaGetErrorString((cudaError_t)rc));
+  arena.reset();
+  uint32_t* counts = arena.take<uint32_t>(p.B + 1);
+  uint32_t* starts = arena.take<uint32_t>(p.B + 1);
+  uint32_t* cursors = arena.take<uint32_t>(p.B);
+  uint32_t* tile_sums = arena.take<uint32_t>(p.ntiles + 1);
+  uint32_t* entries = arena.take<uint32_t>(std::max<uint64_t>(p.M_max, 1));
+  uint4* buckets = chunk ? chunk->buckets : arena.take<uint4>(p.B * 12 * pw);
+  uint4* heads = arena.take<uint4>((size_t)p.S_max * 12 * pw);
+  int32_t* head_bucket = arena.take<int32_t>(p.S_max);
+
+  g.last_c = q.c;
+  g.last_W = q.W;
+  g.last_K = (int)p.K;
+  g.last_entries = p.M_max;
+  g.last_buckets = p.B;
+
+  const uint64_t items = (uint64_t)q.rows * q.cols;
+  if (items == 0) {
+    uint32_t cnt = q.batch ? q.rows : 1;
+    if (cnt) LAUNCH(k_write_identity, cdiv(cnt * 6 * pw, 128), 128, st, d_out, (uint32_t)(cnt * pw));
+    return 0;
+  }
+  if (mark(g, st, "begin")) return 1;
+  const uint32_t dig_grid = (uint32_t)std::min<uint64_t>(cdiv(items, 256), (uint64_t)g.sms * 16);
+  // batches with enough rows to fill the GPU sort each row inside one CTA's shared memory
+  const size_t row_smem = (size_t)q.nb * 4;
+  const bool row_sort = q.batch && q.rows >= (uint32_t)g.sms && row_smem <= 160 * 1024;
+  // >= 116 KB of dynamic shared memory => one CTA per SM (see k_batch_digits)
+  const size_t row_smem_launch = std::max<size_t>(row_smem, 116 * 1024);
+  if (row_sort) {
+    CU(cudaFuncSetAttribute(k_batch_digits<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_launch));
+    CU(cudaFuncSetAttribute(k_batch_digits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_launch));
+    LAUNCH_SMEM(k_batch_digits<false>, q.rows, 1024, row_smem_launch, st, d_scalars, q, counts, (uint32_t*)nullptr);
+  } else {
+    CU(cudaMemsetAsync(counts, 0, (p.B + 1) * 4, st));
+    LAUNCH(k_digits<false>, dig_grid, 256, st, d_scalars, q, counts, (uint32_t*)nullptr, -1);
+  }
+  if (mark(g, st, "digits")) return 1;
+  LAUNCH(k_scan_tile_sums, p.ntiles, SCAN_THREADS, st, counts, (uint32_t)p.B, tile_sums);
+  LAUNCH(k_scan_tile_offsets, 1, SCAN_THREADS, st, tile_sums, p.ntiles, tile_sums + p.ntiles);
+  LAUNCH(k_scan_apply, p.ntiles, SCAN_THREADS, st, counts, (uint32_t)p.B, tile_sums, starts, cursors);
+  if (mark(g, st, "scan")) return 1;
+  if (row_sort) {
+    LAUNCH_SMEM(k_batch_digits<true>, q.rows, 1024, row_smem_launch, st, d_scalars, q, starts, entries);
+  } else {
+    // large single MSMs: one pass per window keeps the writes of a pass inside an L2-sized slice of entries[]
+    const bool per_window = !q.batch && q.c >= 19 && (uint64_t)q.cols * 4 * q.W > (64ull << 20);
+    if (per_window) {
+      for (int w = 0; w < q.W; w++) LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, cursors, entries, w);
+    } else {
+      LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, cursors, entries, -1);
+    }
+  }
+  if (mark(g, st, "scatter")) return 1;
+  if (points_ready) CU(cudaStreamWaitEvent(st, points_ready, 0));  // bases may still be in flight until here
+  // M is only known on the device (starts[B]); launch for the upper bound, surplus threads exit immediately
+  if (p.g2) {
+    if (int r = g2_accumulate(st, p.S_max, entries, starts, (uint32_t)p.B, p.K, d_points, buckets, heads, head_bucket))
+      return r;
+  } else {
+    // operands in shared-memory slots (kernels_smem.cuh). acc_mode 3: plain CIOS products; 0 / 4: Y3 as one fused sum
+    // of two products (default)
+    const dim3 grid(cdiv(p.S_max, ACCS_THREADS));
+    if (E.acc_mode == 3) {
+      CU(cudaFuncSetAttribute(k_accumulate_s<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACCS_SMEM));
+      LAUNCH_SMEM(k_accumulate_s<0>, grid, ACCS_THREADS, ACCS_SMEM, st, entries, starts, (uint32_t)p.B, p.K, d_points,
+                  buckets, heads, head_bucket, chunk ? 1 : 0);
+    } else {
+      CU(cudaFuncSetAttribute(k_accumulate_s<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACCS_SMEM));
+      LAUNCH_SMEM(k_accumulate_s<2>, grid, ACCS_THREADS, ACCS_SMEM, st, entries, starts, (uint32_t)p.B, p.K, d_points,
+                  buckets, heads, head_bucket, chunk ? 1 : 0);
+    }
+  }
+  if (mark(g, st, "accumulate")) return 1;
+  // A bucket holds at most one entry per (column, window) of its group: cols entries (single MSM: one window per
+  // group) or cols * W (batch row), i.e. it spans at most that many / K + 1 segments.
+  const uint64_t max_bucket = q.batch ? (uint64_t)q.cols * q.W : (uint64_t)q.cols;
+  const uint64_t max_span = std::min<uint64_t>(p.S_max, max_bucket / p.K + 2);
+  if (p.g2) {
+    for (uint32_t round = 0; (1ull << round) < max_span; round++)
+      if (int r = g2_fixup_round(st, p.S_max, starts, (uint32_t)p.B, p.K, round, heads, head_bucket)) return r;
+    if (int r = g2_fixup_final(st, p.S_max, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket)) return r;
+  } else {
+    for (uint32_t round = 0; (1ull << round) < max_span; round++)
+      LAUNCH(k_fixup_round, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, round, heads, head_bucket);
+    LAUNCH(k_fixup_final, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket);
+  }
+  if (mark(g, st, "fixup")) return 1;
+  if (chunk && !chunk->last) return 0;  // later point-range chunks continue in the same buckets
+  // hierarchical bucket reduction
+  // chunked runs: emptiness is per chunk; the persistent buckets carry the identity (all zero) instead
+  const uint4 *inS = buckets, *inW = nullptr;
+  uint64_t n = p.B;
+  int log2_ell = 0;
+  const uint32_t* level0 = chunk ? nullptr : starts;
+  for (size_t li = 0; li < p.Ls.size(); li++) {
+    const uint32_t L = p.Ls[li];
+    n /= L;
+    uint4* outS = arena.take<uint4>(n * 12 * pw);
+    uint4* outW = arena.take<uint4>(n * 12 * pw);
+    if (p.g2) {
+      if (int r = g2_reduce_pass(st, inS, inW, level0, outS, outW, L, log2_ell, n)) return r;
+    } else {
+      LAUNCH(k_reduce_pass, cdiv(n, 128), 128, st, inS, inW, level0, outS, outW, L, log2_ell, n);
+    }
+    inS = outS;
+    inW = outW;
+    level0 = nullptr;
+    for (uint32_t v = L; v > 1; v >>= 1) log2_ell++;
+  }
+  const uint4* group_w = inW;  // nb >= 4 (c >= 3): at least one reduction level has run
+  if (mark(g, st, "reduce")) return 1;
+  if (p.g2 && q.W <= 96) {
+    // window combine over the twisted Frobenius: 4 W parallel 64-doubling chains + a tree instead of ~250 serial doublings
+    uint4* fin = arena.take<uint4>((size_t)4 * q.W * 24);
+    if (int r = g2_finalize_single_glv(st, group_w, q.W, q.c, fin, d_out)) return r;
+  } else if (p.g2) {
+    if (int r = g2_finalize_single(st, group_w, q.W, q.c, d_out)) return r;
+  } else if (q.batch) {
+    LAUNCH(k_finalize_batch, cdiv(q.groups, 128), 128, st, group_w, q.groups, d_out);
+  } else {
+    LAUNCH(k_finalize_single, 1, 32, st, group_w, q.W, q.c, d_out);
+  }
+  if (mark(g, st, "finalize")) return 1;
+  return 0;
+}
+
+// ---- single MSM over device pointers ------------------------------------------------------------------------------
+int msm_dev(Ctx& g, const void* d_bases, const void* d_scalars, size_t n, unsigned flags, void* d_out, cudaStream_t st,
+            cudaEvent_t points_ready, Arena* arena_p, bool finish, bool g2) {
+  if (n >= (1ull << 31)) return fail(TB200_E_LIMIT, "n = %zu exceeds 2^31 - 1 points per call", n);
+  if (((uintptr_t)d_bases | (uintptr_t)d_scalars | (uintptr_t)d_out) & 15)
+    return fail(TB200_E_ARG, "device pointers must be 16-byte aligned");
+  g.marks.clear();
+  Arena& arena = arena_p ? *arena_p : g.arena;
+  const int c = pick_c_single(std::max<size_t>(n, 1));
+  const uint64_t W = (uint64_t)num_windows(c);
+  const uint64_t pass_pts = std::max<uint64_t>(E.pass_entries_max / W, 1);
+  int rc = arena.acquire(st);
+  if (rc) return rc;
+  if (n <= pass_pts) {
+    Plan p;
+    rc = make_plan(g, p, 1, (uint32_t)n, 0, 1, c, 0, flags, g2);
+    if (rc) return rc;
+    rc = run_pipeline(g, p, (const uint32_t*)d_scalars, (const uint4*)d_bases, (uint4*)d_out, st, points_ready, arena);
+  } else {
+    // more sorted entries than one pass can index (n W > 2^32): point-range passes over ONE persistent bucket array
+    // (the accumulate kernel continues from the stored bucket), reduction / finalisation once after the last pass
+    if (g2) return fail(TB200_E_LIMIT, "G2 MSM of %zu points exceeds the per-pass entry limit", n);
+    const uint64_t cap = pass_pts >= 32 ? (pass_pts & ~31ull) : pass_pts;  // 32-aligned pass boundaries
+    const uint64_t npass = (n + cap - 1) / cap;
+    const uint64_t per = std::min<uint64_t>(cap, (((n + npass - 1) / npass) + 31) & ~31ull);
+    const uint64_t B = W << (c - 1);
+    uint4* d_buckets = nullptr;
+    CU(cudaMallocAsync((void**)&d_buckets, B * 192, st));
+    CU(cudaMemsetAsync(d_buckets, 0, B * 192, st));
+    for (uint64_t lo = 0; lo < n && rc == 0; lo += per) {
+      const uint64_t cnt = std::min<uint64_t>(per, n - lo);
+      Plan p;
+      rc = make_plan(g, p, 1, (uint32_t)cnt, 0, 1, c, 0, flags, false);
+      if (rc) break;
+      ChunkCtl ctl{(uint32_t)lo, d_buckets, lo + cnt >= n};
+      rc = run_pipeline(g, p, (const uint32_t*)d_scalars + 8 * lo, (const uint4*)d_bases, (uint4*)d_out, st,
+                        lo == 0 ? points_ready : nullptr, arena, &ctl);
+    }
+    cudaFreeAsync(d_buckets, st);
+  }
+  if (rc) return rc;
+  rc = arena.release(st);
+  if (rc) return rc;
+  return finish ? finish_marks(g, st) : 0;
+}
+
+// Host-facing single MSM of one device's share. Large n: point-range chunks of growing size (1/8, 1/4, 1/4, 3/8 of the
+// points); chunk k+1 is uploaded on the copy stream while chunk k is sorted and accumulated; every chunk accumulates into
+// the SAME persistent bucket array (k_accumulate_s continues from the stored bucket, no extra group operations), and the
+// reduction / finalisation run once after the last chunk. Without it the accumulation waits for the whole 96 n byte
+// base upload (~37 ms at 2^24 over PCIe Gen5) with the GPU idle.
+int msm_host_enqueue(Ctx& g, const uint64_t* bases_xy, const uint64_t* scalars, size_t n, unsigned flags,
+                     std::vector<void*>& to_free) {
+  CU(cudaSetDevice(g.device));
+  if (n >= (size_t(1) << 31)) return fail(TB200_E_LIMIT, "n = %zu exceeds 2^31 - 1 points per call", n);
+  if (n == 0) return msm_dev(g, g.d_result, g.d_result, 0, flags, g.d_result, g.stream, nullptr, nullptr, false);
+  uint4 *d_b = nullptr, *d_s = nullptr;
+  CU(cudaMallocAsync((void**)&d_b, n * 96, g.stream));
+  to_free.push_back(d_b);
+  CU(cudaMallocAsync((void**)&d_s, n * 32, g.stream));
+  to_free.push_back(d_s);
+  const int c = pick_c_single(n);
+  const uint64_t W = (uint64_t)num_windows(c);
+  const bool chunked = n >= E.host_chunk_min && (uint64_t)n * W <= E.pass_entries_max;
+  if (!chunked) {
+    // the digit / sort stages only need the scalars; the 3x larger base upload runs on the copy stream and is awaited
+    // right before the accumulation kernel
+    CU(cudaEventRecord(g.ev_points, g.stream));  // allocations done
+    CU(cudaStreamWaitEvent(g.copy_stream, g.ev_points, 0));
+    CU(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, g.copy_stream));
+    CU(cudaEventRecord(g.ev_points, g.copy_stream));
+    return msm_dev(g, d_b, d_s, n, flags, g.d_result, g.stream, g.ev_points, nullptr, false);
+  }
+  constexpr int C = 4;
+  const size_t unit = ((n + 7) / 8 + 31) & ~size_t(31);
+  const size_t cut[C + 1] = {0, std::min(n, unit), std::min(n, 3 * unit), std::min(n, 5 * unit), n};
+  Plan plans[C];
+  size_t B = 0;
+  for (int k = 0; k < C; k++) {
+    int rc = make_plan(g, plans[k], 1, (uint32_t)(cut[k + 1] - cut[k]), 0, 1, c, 0, flags);
+    if (rc) return rc;
+    B = plans[k].B;
+  }
+  uint4* d_buckets = nullptr;
+  CU(cudaMallocAsync((void**)&d_buckets, B * 192, g.stream));
+  to_free.push_back(d_buckets);
+  CU(cudaMemsetAsync(d_buckets, 0, B * 192, g.stream));
+  CU(cudaEventRecord(g.ev_points, g.stream));  // allocations exist
+  CU(cudaStreamWaitEvent(g.copy_stream, g.ev_points, 0));
+  while (g.chunk_ev.size() < 2 * C) {
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g.chunk_ev.push_back(e);
+  }
+  for (int k = 0; k < C; k++) {
+    const size_t lo = cut[k], cnt = cut[k + 1] - cut[k];
+    CU(cudaMemcpyAsync((char*)d_s + lo * 32, (const char*)scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice,
+                       g.copy_stream));
+    CU(cudaEventRecord(g.chunk_ev[2 * k], g.copy_stream));
+    CU(cudaMemcpyAsync((char*)d_b + lo * 96, (const char*)bases_xy + lo * 96, cnt * 96, cudaMemcpyHostToDevice,
+                       g.copy_stream));
+    CU(cudaEventRecord(g.chunk_ev[2 * k + 1], g.copy_stream));
+  }
+  g.marks.clear();
+  if (int rc = g.arena.acquire(g.stream)) return rc;
+  for (int k = 0; k < C; k++) {
+    CU(cudaStreamWaitEvent(g.stream, g.chunk_ev[2 * k], 0));
+    ChunkCtl ctl{(uint32_t)cut[k], d_buckets, k == C - 1};
+    int rc = run_pipeline(g, plans[k], (const uint32_t*)d_s + 8 * cut[k], d_b, g.d_result, g.stream, g.chunk_ev[2 * k + 1],
+                          g.arena, &ctl);
+    if (rc) return rc;
+  }
+  return g.arena.release(g.stream);
+}
+
+// ---- shared-base batch ------------------------------------------------------------------------------------------------
+// rows are processed in chunks that respect the per-pass limits of the pipeline
+int batch_dev(Ctx& g, const uint4* table, int c, int W, uint32_t srs_n, const uint32_t* d_scalars, size_t rows, size_t cols,
+              long long rs, long long cs, unsigned flags, uint4* d_out, cudaStream_t st) {
+  if (cols > srs_n) return fail(TB200_E_ARG, "cols = %zu exceeds the SRS size %u", cols, srs_n);
+  if (((uintptr_t)d_scalars | (uintptr_t)d_out) & 15) return fail(TB200_E_ARG, "device pointers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  const uint64_t per_row = (uint64_t)std::max<size_t>(cols, 1) * W;
+  const uint64_t nb = 1ull << (c - 1);
+  const uint64_t chunk = std::min<uint64_t>(
+      {(uint64_t)rows, std::min<uint64_t>(E.pass_entries_max, (1ull << 31) - 1) / per_row, (1ull << 30) / nb});
+  if (chunk == 0) return fail(TB200_E_LIMIT, "a single row exceeds the per-pass limits");
+  if (int rc = g.arena.acquire(st)) return rc;
+  for (size_t r0 = 0; r0 < rows; r0 += chunk) {
+    uint32_t nr = (uint32_t)std::min<uint64_t>(chunk, rows - r0);
+    Plan p;
+    int rc = make_plan(g, p, nr, (uint32_t)cols, rs, cs, c, 1, flags);
+    if (rc) return rc;
+    // entry refs are w * cols + j and the callers guarantee cols == srs_n, the stride of the window tables
+    rc = run_pipeline(g, p, d_scalars + 8 * (long long)r0 * rs, table, d_out + 6 * r0, st, nullptr, g.arena);
+    if (rc) return rc;
+  }
+  return g.arena.release(st);
+}
+
+int srs_build_table(Ctx& g, const uint64_t* bases_xy, size_t n, int c, int W, uint4** out_table) {
+  CU(cudaSetDevice(g.device));
+  uint4 *table = nullptr, *d_b = nullptr;
+  cudaError_t e = cudaMalloc((void**)&table, (size_t)W * n * 96);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_b, n * 96);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, g.stream);
+  if (e == cudaSuccess) {
+    k_srs_tables<<<cdiv(n, 128), 128, 0, g.stream>>>(d_b, (uint32_t)n, c, W, table);
+    g_launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  if (d_b) cudaFree(d_b);
+  if (e != cudaSuccess) {
+    if (table) cudaFree(table);
+    return fail((int)e, "SRS table build failed on device %d: %s", g.device, cudaGetErrorString(e));
+  }
+  *out_table = table;
+  return 0;
+}
+
+int g1_sum_dev(Ctx& g, const void* d_pts, size_t n, void* d_out, cudaStream_t st) {
+  (void)g;
+  LAUNCH(k_g1_sum, 1, 32, st, (const uint4*)d_pts, (uint32_t)n, (uint4*)d_out);
+  return 0;
+}
+
+static int fr_fold(cudaStream_t st, uint32_t* y, uint32_t split, const uint32_t* d_c_inv, int mont) {
+  LAUNCH(k_compress_fr, cdiv(split, 128), 128, st, y, split, d_c_inv, mont);
+  return 0;
+}
+
+}  // namespace tbe
+
+using namespace tbe;
+
+extern "C" {
+
+int tb200_msm_g1_dev(const void* d_bases_xy, const void* d_scalars, size_t n, unsigned flags, void* d_out_xy,
+                     void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_out_xy || (n && (!d_bases_xy || !d_scalars))) return fail(TB200_E_ARG, "null pointer");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  return msm_dev(g, d_bases_xy, d_scalars, n, flags, d_out_xy, stream ? (cudaStream_t)stream : g.stream);
+}
+
+int tb200_msm_g1_batch_dev(tb200_srs_t srs, const void* d_scalars, size_t rows, size_t cols, ptrdiff_t row_stride,
+                           ptrdiff_t col_stride, unsigned flags, void* d_out_xy, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!srs || (rows && (!d_out_xy || (cols && !d_scalars)))) return fail(TB200_E_ARG, "null pointer");
+  if (cols != srs->n && cols != 0)
+    return fail(TB200_E_ARG, "cols (%zu) must equal the SRS size (%u): window tables are laid out per SRS", cols, srs->n);
+  if (row_stride < 0 || col_stride < 0) return fail(TB200_E_ARG, "negative strides are not supported");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+  g.marks.clear();
+  int rc = batch_dev(g, srs->table[0], srs->c, srs->W, srs->n, (const uint32_t*)d_scalars, rows, cols, row_stride,
+                     col_stride, flags, (uint4*)d_out_xy, st);
+  return rc ? rc : finish_marks(g, st);
+}
+
+// ---- MultilinearPC::open (G2 proofs) / open_g1 (G1 proofs): quotient loop on the device, one MSM per variable ---------
+static int pst_open_locked(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                           unsigned flags, uint64_t* proofs, bool g2) {
+  if (!evals || !point || !level_bases || !proofs) return fail(TB200_E_ARG, "null pointer");
+  if (nv == 0) return 0;
+  if (nv > 28) return fail(TB200_E_LIMIT, "nv = %zu: at most 2^28 evaluations", nv);
+  for (size_t i = 0; i < nv; i++)
+    if (!level_bases[i]) return fail(TB200_E_ARG, "level_bases[%zu] is null", i);
+  Ctx& g = primary();
+  const size_t n = size_t(1) << nv, pt = g2 ? 192 : 96;
+  uint32_t *d_r0 = nullptr, *d_r1 = nullptr, *d_q = nullptr, *d_p = nullptr;
+  uint4 *d_bases = nullptr, *d_proofs = nullptr;
+  // level i occupies [off_i, off_i + 2^(nv-i)) of d_q / d_bases, off_i = 2^(nv+1) - 2^(nv-i+1)
+  CU(cudaMallocAsync((void**)&d_r0, n * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_r1, std::max<size_t>(n / 2, 1) * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_q, 2 * n * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_p, nv * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_bases, 2 * n * pt, g.stream));
+  CU(cudaMallocAsync((void**)&d_proofs, nv * pt, g.stream));
+  CU(cudaMemcpyAsync(d_r0, evals, n * 32, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(d_p, point, nv * 32, cudaMemcpyHostToDevice, g.stream));
+  if (!(flags & TB200_SCALARS_MONT)) {
+    LAUNCH(k_fr_to_mont, cdiv(n, 128), 128, g.stream, d_r0, (uint32_t)n);
+    LAUNCH(k_fr_to_mont, cdiv(nv, 128), 128, g.stream, d_p, (uint32_t)nv);
+  }
+  // the quotient loop is a cheap sequential chain; the nv MSMs that consume it are independent of each other and
+  // latency-bound (Horner chain + inversion), so they run concurrently on side streams with their own workspaces
+  std::vector<size_t> off(nv);
+  uint32_t *r_in = d_r0, *r_out = d_r1;
+  size_t o = 0;
+  for (size_t i = 0; i < nv; i++) {
+    const size_t half = size_t(1) << (nv - i - 1);
+    off[i] = o;
+    CU(cudaMemcpyAsync((char*)d_bases + o * pt, level_bases[i], 2 * half * pt, cudaMemcpyHostToDevice, g.stream));
+    LAUNCH(k_pst_level, cdiv(half, 128), 128, g.stream, r_in, (uint32_t)half, d_p + 8 * i, r_out, d_q + 8 * o);
+    std::swap(r_in, r_out);
+    o += 2 * half;
+  }
+  CU(cudaEventRecord(g.ev_join, g.stream));
+  const bool prof = g.profiling;
+  g.profiling = false;
+  int rc = 0;
+  for (size_t i = 0; i < nv && rc == 0; i++) {
+    const int sl = (int)(i % Ctx::SIDE);
+    if (!g.side_stream[sl]) {
+      CU(cudaStreamCreateWithFlags(&g.side_stream[sl], cudaStreamNonBlocking));
+      CU(cudaEventCreateWithFlags(&g.side_done[sl], cudaEventDisableTiming));
+    }
+    if (i < (size_t)Ctx::SIDE) CU(cudaStreamWaitEvent(g.side_stream[sl], g.ev_join, 0));
+    rc = msm_dev(g, (char*)d_bases + off[i] * pt, d_q + 8 * off[i], size_t(1) << (nv - i), TB200_SCALARS_MONT,
+                 (char*)d_proofs + i * pt, g.side_stream[sl], nullptr, &g.side_arena[sl], false, g2);
+  }
+  g.profiling = prof;
+  for (int sl = 0; sl < Ctx::SIDE && sl < (int)nv; sl++) {
+    if (!g.side_stream[sl]) continue;
+    cudaEventRecord(g.side_done[sl], g.side_stream[sl]);
+    cudaStreamWaitEvent(g.stream, g.side_done[sl], 0);
+  }
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(proofs, d_proofs, nv * pt, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "proof copy failed: %s", cudaGetErrorString(e));
+  } else {
+    cudaStreamSynchronize(g.stream);
+  }
+  g.marks.clear();
+  cudaFreeAsync(d_r0, g.stream);
+  cudaFreeAsync(d_r1, g.stream);
+  cudaFreeAsync(d_q, g.stream);
+  cudaFreeAsync(d_p, g.stream);
+  cudaFreeAsync(d_bases, g.stream);
+  cudaFreeAsync(d_proofs, g.stream);
+  return rc;
+}
+int tb200_pst_open_g1(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                      unsigned flags, uint64_t* proofs) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  CU(cudaSetDevice(primary().device));
+  return pst_open_locked(evals, nv, point, level_bases, flags, proofs, false);
+}
+int tb200_pst_open_g2(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                      unsigned flags, uint64_t* proofs) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  CU(cudaSetDevice(primary().device));
+  return pst_open_locked(evals, nv, point, level_bases, flags, proofs, true);
+}
+
+// ---- MIPP (G1 side) ---------------------------------------------------------------------------------------------------
+int tb200_mipp_g1_begin(const uint64_t* a_xy, const uint64_t* y, size_t n, unsigned flags, tb200_mipp_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || !a_xy || !y || n == 0 || (n & (n - 1)) || n >= (1u << 28))
+    return fail(TB200_E_ARG, "MIPP vectors must have a power-of-two length (got %zu)", n);
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  tb200_mipp* h = new tb200_mipp();
+  h->n = (uint32_t)n;
+  h->flags = flags;
+  cudaError_t e = cudaMalloc((void**)&h->a, n * 96);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->y, n * 32);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->scal, 64 * 64);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->digits, 64 * 32);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&h->scal_host, 64 * 64);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->a, a_xy, n * 96, cudaMemcpyHostToDevice, g.stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h->y, y, n * 32, cudaMemcpyHostToDevice, g.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  if (e != cudaSuccess) {
+    cudaFree(h->a);
+    cudaFree(h->y);
+    cudaFree(h->scal);
+    cudaFree(h->digits);
+    cudaFreeHost(h->scal_host);
+    delete h;
+    return fail((int)e, "MIPP upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return 0;
+}
+size_t tb200_mipp_g1_len(tb200_mipp_t h) { return h ? h->n : 0; }
+
+int tb200_mipp_g1_cross(tb200_mipp_t h, uint64_t comm_u_l[12], uint64_t comm_u_r[12]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!h || !comm_u_l || !comm_u_r) return fail(TB200_E_ARG, "null pointer");
+  if (h->n < 2) return fail(TB200_E_STATE, "MIPP vectors are already folded to length 1");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  const uint32_t split = h->n / 2;
+  // comm_u_l = MSM(a[:split], y[split:]), comm_u_r = MSM(a[split:], y[:split])   (src/mipp.rs:82-84)
+  // the two MSMs are independent and latency-bound (sequential Horner + inversion tail): run them concurrently on
+  // two streams with separate workspaces (the reference runs them as two rayon tasks, src/mipp.rs:77-85)
+  const bool prof = g.profiling;
+  g.profiling = false;
+  CU(cudaEventRecord(g.ev_join, g.stream));  // the folds are only enqueued: stream2 must follow them
+  CU(cudaStreamWaitEvent(g.stream2, g.ev_join, 0));
+  int rc = msm_dev(g, h->a, h->y + 8 * (size_t)split, split, h->flags, g.d_result, g.stream, nullptr, nullptr, false);
+  if (rc == 0)
+    rc = msm_dev(g, h->a + 6 * (size_t)split, h->y, split, h->flags, g.d_result + 6, g.stream2, nullptr, &g.arena2, false);
+  g.profiling = prof;
+  if (rc) return rc;
+  CU(cudaEventRecord(g.ev_join, g.stream2));
+  CU(cudaStreamWaitEvent(g.stream, g.ev_join, 0));
+  CU(cudaMemcpyAsync(g.h_result, g.d_result, 192, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  memcpy(comm_u_l, g.h_result, 96);
+  memcpy(comm_u_r, (char*)g.h_result + 96, 96);
+  return 0;
+}
+
+int tb200_mipp_g1_fold(tb200_mipp_t h, const uint64_t c[4], const uint64_t c_inv[4]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!h || !c || !c_inv) return fail(TB200_E_ARG, "null pointer");
+  if (h->n < 2) return fail(TB200_E_STATE, "MIPP vectors are already folded to length 1");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  if (h->round >= 64) return fail(TB200_E_LIMIT, "too many rounds");
+  const uint32_t split = h->n / 2;
+  // enqueue only: every later use of a / y is ordered behind the folds on the library's stream
+  uint32_t* hs = h->scal_host + 16 * h->round;
+  uint32_t* ds = h->scal + 16 * h->round;
+  memcpy(hs, c, 32);
+  memcpy(hs + 8, c_inv, 32);
+  CU(cudaMemcpyAsync(ds, hs, 64, cudaMemcpyHostToDevice, g.stream));
+  const int mont = (h->flags & TB200_SCALARS_MONT) ? 1 : 0;
+  // a_l + c a_r over the G1 endomorphism (engine_pairing.cu): 127 doublings instead of 253
+  if (int rc = g1_fold_glv(g.stream, ds, mont, h->digits + 8 * h->round, h->a, split)) return rc;
+  if (int rc = fr_fold(g.stream, h->y, split, ds + 8, mont)) return rc;
+  h->round++;
+  h->n = split;
+  return 0;
+}
+
+int tb200_mipp_g1_read(tb200_mipp_t h, uint64_t* a_xy, uint64_t* y) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!h) return fail(TB200_E_ARG, "null handle");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  if (a_xy) CU(cudaMemcpyAsync(a_xy, h->a, (size_t)h->n * 96, cudaMemcpyDeviceToHost, g.stream));
+  if (y) CU(cudaMemcpyAsync(y, h->y, (size_t)h->n * 32, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+int tb200_mipp_g1_end(tb200_mipp_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!h) return fail(TB200_E_ARG, "null handle");
+  if (E.ready) {
+    Ctx& g = primary();
+    cudaSetDevice(g.device);
+    cudaStreamSynchronize(g.stream);
+    cudaFree(h->a);
+    cudaFree(h->y);
+    cudaFree(h->scal);
+    cudaFree(h->digits);
+    cudaFreeHost(h->scal_host);
+  }
+  delete h;
+  return 0;
+}
+
+int tb200_compress_g1(uint64_t* vec_xy, size_t split, const uint64_t scaler[4], unsigned flags) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!vec_xy || !scaler) return fail(TB200_E_ARG, "null pointer");
+  if (split == 0) return 0;
+  if (split >= (1u << 27)) return fail(TB200_E_LIMIT, "split too large");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  uint4* d_v = nullptr;
+  uint32_t* d_k = nullptr;
+  CU(cudaMallocAsync((void**)&d_v, 2 * split * 96, g.stream));
+  CU(cudaMallocAsync((void**)&d_k, 32, g.stream));
+  CU(cudaMemcpyAsync(d_v, vec_xy, 2 * split * 96, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(d_k, scaler, 32, cudaMemcpyHostToDevice, g.stream));
+  LAUNCH(k_compress_g1, cdiv(split, 128), 128, g.stream, d_v, (uint32_t)split, d_k, (flags & TB200_SCALARS_MONT) ? 1 : 0);
+  CU(cudaMemcpyAsync(vec_xy, d_v, split * 96, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  cudaFreeAsync(d_v, g.stream);
+  cudaFreeAsync(d_k, g.stream);
+  return 0;
+}
+
+// ---- sqrt_pst scalar work on the device -------------------------------------------------------------------------------
+int tb200_fr_chis(const uint64_t* b, size_t m, uint64_t* chis_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!chis_out || (m && !b) || m > 28) return fail(TB200_E_ARG, "bad arguments (m = %zu)", m);
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  const size_t n = size_t(1) << m;
+  uint32_t *d_b = nullptr, *d_o = nullptr;
+  CU(cudaMallocAsync((void**)&d_b, std::max<size_t>(m, 1) * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_o, n * 32, g.stream));
+  if (m) CU(cudaMemcpyAsync(d_b, b, m * 32, cudaMemcpyHostToDevice, g.stream));
+  LAUNCH(k_fr_chis, cdiv(n, 128), 128, g.stream, d_b, (uint32_t)m, d_o);
+  CU(cudaMemcpyAsync(chis_out, d_o, n * 32, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  cudaFreeAsync(d_b, g.stream);
+  cudaFreeAsync(d_o, g.stream);
+  return 0;
+}
+static int fr_matvec_enqueue(Ctx& g, const void* d_Z, size_t rows, size_t cols, const void* d_v, void* d_out, cudaStream_t st) {
+  if (rows >= (1ull << 31) || cols >= (1ull << 31)) return fail(TB200_E_LIMIT, "matrix too large");
+  if (((uintptr_t)d_Z | (uintptr_t)d_v | (uintptr_t)d_out) & 15) return fail(TB200_E_ARG, "device pointers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  (void)g;
+  LAUNCH(k_fr_matvec, cdiv(rows * 32, 256), 256, st, (const uint32_t*)d_Z, (uint32_t)rows, (uint32_t)cols,
+         (const uint32_t*)d_v, (uint32_t*)d_out);
+  return 0;
+}
+int tb200_fr_matvec_dev(const void* d_Z, size_t rows, size_t cols, const void* d_v, void* d_out, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_out || ((rows && cols) && (!d_Z || !d_v))) return fail(TB200_E_ARG, "null pointer");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  return fr_matvec_enqueue(g, d_Z, rows, cols, d_v, d_out, stream ? (cudaStream_t)stream : g.stream);
+}
+int tb200_fr_matvec(const uint64_t* Z, size_t rows, size_t cols, const uint64_t* v, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || !Z || !v || rows == 0 || cols == 0) return fail(TB200_E_ARG, "bad arguments");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  uint32_t *d_z = nullptr, *d_v = nullptr, *d_o = nullptr;
+  CU(cudaMallocAsync((void**)&d_z, rows * cols * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_v, cols * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_o, rows * 32, g.stream));
+  CU(cudaMemcpyAsync(d_z, Z, rows * cols * 32, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(d_v, v, cols * 32, cudaMemcpyHostToDevice, g.stream));
+  int rc = fr_matvec_enqueue(g, d_z, rows, cols, d_v, d_o, g.stream);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out, d_o, rows * 32, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
+  }
+  cudaFreeAsync(d_z, g.stream);
+  cudaFreeAsync(d_v, g.stream);
+  cudaFreeAsync(d_o, g.stream);
+  return rc;
+}
+
+// ---- group utilities ---------------------------------------------------------------------------------------------
+int tb200_g1_sum_dev(const void* d_pts_xy, size_t n, void* d_out_xy, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_out_xy || (n && !d_pts_xy)) return fail(TB200_E_ARG, "null pointer");
+  if (n >= (1u << 20)) return fail(TB200_E_LIMIT, "tb200_g1_sum is meant for a handful of partial results");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  return g1_sum_dev(g, d_pts_xy, n, d_out_xy, stream ? (cudaStream_t)stream : g.stream);
+}
+int tb200_g1_sum(const uint64_t* pts_xy, size_t n, uint64_t out_xy[12]) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out_xy || (n && !pts_xy)) return fail(TB200_E_ARG, "null pointer");
+  if (n > 128) return fail(TB200_E_LIMIT, "tb200_g1_sum (host form) takes at most 128 points");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  if (n) CU(cudaMemcpyAsync(g.d_result + 6, pts_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
+  LAUNCH(k_g1_sum, 1, 32, g.stream, g.d_result + 6, (uint32_t)n, g.d_result);
+  CU(cudaMemcpyAsync(g.h_result, g.d_result, 96, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  memcpy(out_xy, g.h_result, 96);
+  return 0;
+}
+int tb200_g1_outer_sum_dev(const void* d_a_xy, size_t na, const void* d_b_xy, size_t nb, void* d_out_xy, void* stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!d_a_xy || !d_b_xy || !d_out_xy || na == 0 || nb == 0) return fail(TB200_E_ARG, "bad arguments");
+  if ((uint64_t)na * nb >= (1ull << 31)) return fail(TB200_E_LIMIT, "outer sum too large");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : g.stream;
+  LAUNCH(k_g1_outer_sum, cdiv((uint64_t)na * nb, 128), 128, st, (const uint4*)d_a_xy, (uint32_t)na, (const uint4*)d_b_xy,
+         (uint32_t)nb, (uint4*)d_out_xy);
+  return 0;
+}
+
+// ---- microbenchmarks / unit-test hooks ------------------------------------------------------------------------------
+int tb200_int_pipe_peak(int kind, int iters, double* out_per_s) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out_per_s || iters <= 0 || kind < 0 || kind > 2) return fail(TB200_E_ARG, "bad arguments");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  const int threads = kind == 2 ? 128 : 256;
+  const int blocks = g.sms * (kind == 2 ? 3 : 8);
+  void* sink = nullptr;
+  CU(cudaMalloc(&sink, (size_t)blocks * threads * 8));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  for (int rep = 0; rep < 2; rep++) {  // first repetition warms up
+    CU(cudaEventRecord(e0, g.stream));
+    if (kind == 2) LAUNCH(k_fq_mul_peak, blocks, threads, g.stream, iters, 12345u, (uint32_t*)sink);
+    else LAUNCH(k_int_pipe, blocks, threads, g.stream, kind, iters, 12345u, (uint64_t*)sink);
+    CU(cudaEventRecord(e1, g.stream));
+    CU(cudaStreamSynchronize(g.stream));
+  }
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  double ops = (double)blocks * threads * (double)iters * (kind == 2 ? 2.0 : 64.0);
+  *out_per_s = ops / (ms * 1e-3);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return 0;
+}
+
+}  // extern "C"
+
+namespace tbe {
+// unit-test scaffolding shared with the other units: blocking copies around one launch on the primary's stream
+int with_buffers(const void* a, size_t abytes, const void* b, size_t bbytes, void* o1, size_t o1bytes, void* o2,
+                 size_t o2bytes, const std::function<int(char*, char*, char*, char*)>& launch) {
+  char *d_a = nullptr, *d_b = nullptr, *d_o1 = nullptr, *d_o2 = nullptr;
+  CU(cudaMalloc((void**)&d_a, std::max<size_t>(abytes, 16)));
+  CU(cudaMalloc((void**)&d_b, std::max<size_t>(bbytes, 16)));
+  CU(cudaMalloc((void**)&d_o1, std::max<size_t>(o1bytes, 16)));
+  CU(cudaMalloc((void**)&d_o2, std::max<size_t>(o2bytes, 16)));
+  CU(cudaMemcpy(d_a, a, abytes, cudaMemcpyHostToDevice));
+  if (b) CU(cudaMemcpy(d_b, b, bbytes, cudaMemcpyHostToDevice));
+  int rc = launch(d_a, d_b, d_o1, d_o2);
+  if (rc == 0) {
+    CU(cudaStreamSynchronize(primary().stream));
+    CU(cudaMemcpy(o1, d_o1, o1bytes, cudaMemcpyDeviceToHost));
+    if (o2) CU(cudaMemcpy(o2, d_o2, o2bytes, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_a);
+  cudaFree(d_b);
+  cudaFree(d_o1);
+  cudaFree(d_o2);
+  return rc;
+}
+}  // namespace tbe
+
+extern "C" {
+
+int tb200_test_fq_mul(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!a || !b || !out || n == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(primary().device));
+  cudaStream_t st = primary().stream;
+  return with_buffers(a, n * 48, b, n * 48, out, n * 48, nullptr, 0, [&](char* da, char* db, char* d1, char*) {
+    LAUNCH(k_test_fq_mul, cdiv(n, 128), 128, st, (const uint32_t*)da, (const uint32_t*)db, (uint32_t)n, (uint32_t*)d1);
+    return 0;
+  });
+}
+int tb200_test_fq_addsub(const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out_add, uint64_t* out_sub) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!a || !b || !out_add || !out_sub || n == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(primary().device));
+  cudaStream_t st = primary().stream;
+  return with_buffers(a, n * 48, b, n * 48, out_add, n * 48, out_sub, n * 48, [&](char* da, char* db, char* d1, char* d2) {
+    LAUNCH(k_test_fq_addsub, cdiv(n, 128), 128, st, (const uint32_t*)da, (const uint32_t*)db, (uint32_t)n, (uint32_t*)d1,
+           (uint32_t*)d2);
+    return 0;
+  });
+}
+int tb200_test_g1_add(const uint64_t* p_xy, const uint64_t* q_xy, size_t n, uint64_t* out_xy) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!p_xy || !q_xy || !out_xy || n == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(primary().device));
+  cudaStream_t st = primary().stream;
+  return with_buffers(p_xy, n * 96, q_xy, n * 96, out_xy, n * 96, nullptr, 0, [&](char* da, char* db, char* d1, char*) {
+    LAUNCH(k_test_g1_add, cdiv(n, 64), 64, st, (const uint4*)da, (const uint4*)db, (uint32_t)n, (uint4*)d1);
+    return 0;
+  });
+}
+int tb200_test_g1_mul(const uint64_t* p_xy, const uint64_t* k, size_t n, uint64_t* out_xy) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!p_xy || !k || !out_xy || n == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(primary().device));
+  cudaStream_t st = primary().stream;
+  return with_buffers(p_xy, n * 96, k, n * 32, out_xy, n * 96, nullptr, 0, [&](char* da, char* db, char* d1, char*) {
+    LAUNCH(k_test_g1_mul, cdiv(n, 64), 64, st, (const uint4*)da, (const uint32_t*)db, (uint32_t)n, (uint4*)d1);
+    return 0;
+  });
+}
+
+}  // extern "C"

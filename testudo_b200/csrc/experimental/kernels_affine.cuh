@@ -17,7 +17,7 @@
 //     either input identity / no partner: result = the other input, d := 1
 // All coordinates here are canonical (equality tests are exact); identity = (0, 0).
 #pragma once
-#include "kernels.cuh"
+#include "../kernels.cuh"
 
 namespace tb {
 

@@ -15,7 +15,7 @@
 // must stay below 2^384 (callers track the bounds; g1_fast.cuh). Host build emulates the carry chains
 // (tests/host_check).
 #pragma once
-#include "mont.cuh"
+#include "../mont.cuh"
 
 namespace tb {
 

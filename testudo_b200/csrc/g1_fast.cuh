@@ -74,7 +74,7 @@ TB_HD void fq_canon(Fq& a) {
 
 // the one out-of-line multiplier of the hot loop (register-passed on the device)
 #if defined(__CUDA_ARCH__)
-__device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) {
+static __device__ __noinline__ Fq fq_mul_call(Fq a, Fq b) {
   Fq r;
   mont_mul_lazy<FqParams>(r.l, a.l, b.l);
   return r;
@@ -89,7 +89,7 @@ inline Fq fq_mul_call(Fq a, Fq b) {
 
 // dedicated squaring (78 + 132 wide MACs instead of 144 + 132), same calling convention
 #if defined(__CUDA_ARCH__)
-__device__ __noinline__ Fq fq_sqr_call(Fq a) {
+static __device__ __noinline__ Fq fq_sqr_call(Fq a) {
   Fq r;
   mont_sqr_lazy<FqParams>(r.l, a.l);
   return r;

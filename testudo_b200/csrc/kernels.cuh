@@ -27,7 +27,7 @@ namespace tb {
 // vectorised global <-> register moves (16-byte accesses; all buffers are 16-byte aligned)
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_fq2_nc(Affine& p, const uint4* __restrict__ src) {
-  uint32_t* d = p.x.l;  // x and y are contiguous: 24 words
+  uint32_t* d = reinterpret_cast<uint32_t*>(&p);  // the whole packed object (x, y: 24 words)
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     uint4 v = __ldg(src + i);
@@ -38,7 +38,7 @@ __device__ __forceinline__ void load_fq2_nc(Affine& p, const uint4* __restrict__
   }
 }
 __device__ __forceinline__ void load_affine(Affine& p, const uint4* src) {
-  uint32_t* d = p.x.l;
+  uint32_t* d = reinterpret_cast<uint32_t*>(&p);
 #pragma unroll
   for (int i = 0; i < 6; i++) {
     uint4 v = src[i];
@@ -49,12 +49,12 @@ __device__ __forceinline__ void load_affine(Affine& p, const uint4* src) {
   }
 }
 __device__ __forceinline__ void store_affine(uint4* dst, const Affine& p) {
-  const uint32_t* s = p.x.l;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
 #pragma unroll
   for (int i = 0; i < 6; i++) dst[i] = make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
 }
 __device__ __forceinline__ void load_xyzz(Xyzz& p, const uint4* src) {
-  uint32_t* d = p.x.l;  // x, y, zz, zzz contiguous: 48 words
+  uint32_t* d = reinterpret_cast<uint32_t*>(&p);  // the whole packed object (x, y, zz, zzz: 48 words)
 #pragma unroll
   for (int i = 0; i < 12; i++) {
     uint4 v = src[i];
@@ -65,7 +65,7 @@ __device__ __forceinline__ void load_xyzz(Xyzz& p, const uint4* src) {
   }
 }
 __device__ __forceinline__ void store_xyzz(uint4* dst, const Xyzz& p) {
-  const uint32_t* s = p.x.l;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
 #pragma unroll
   for (int i = 0; i < 12; i++) dst[i] = make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
 }
@@ -73,23 +73,23 @@ static_assert(sizeof(Affine) == 96 && sizeof(Xyzz) == 192, "packed layouts");
 
 // out-of-line group operations for the non-hot kernels (keeps their code small; they are latency-, not
 // throughput-bound)
-__device__ __noinline__ void xyzz_add_ni(Xyzz* p, const Xyzz* q) { xyzz_add(*p, *q); }
-__device__ __noinline__ void xyzz_dbl_ni(Xyzz* p) { xyzz_dbl(*p); }
-__device__ __noinline__ void xyzz_madd_ni(Xyzz* p, const Affine* q) { xyzz_madd(*p, *q); }
-__device__ __noinline__ void xyzz_to_affine_ni(Affine* r, const Xyzz* p) { xyzz_to_affine(*r, *p); }
+static __device__ __noinline__ void xyzz_add_ni(Xyzz* p, const Xyzz* q) { xyzz_add(*p, *q); }
+static __device__ __noinline__ void xyzz_dbl_ni(Xyzz* p) { xyzz_dbl(*p); }
+static __device__ __noinline__ void xyzz_madd_ni(Xyzz* p, const Affine* q) { xyzz_madd(*p, *q); }
+static __device__ __noinline__ void xyzz_to_affine_ni(Affine* r, const Xyzz* p) { xyzz_to_affine(*r, *p); }
 // lazy-reduction versions (g1_fast.cuh) behind one call site each: the few dozen local-memory words per call are
 // noise next to 9-14 multiplications, and the kernels that use them stay small and spill-free
-__device__ __noinline__ void xyzz_add_fast_ni(Xyzz* p, const Xyzz* q) {
+static __device__ __noinline__ void xyzz_add_fast_ni(Xyzz* p, const Xyzz* q) {
   Xyzz a = *p;
   xyzz_add_fast(a, *q);
   *p = a;
 }
-__device__ __noinline__ void xyzz_madd_fast_ni(Xyzz* p, const Affine* q) {
+static __device__ __noinline__ void xyzz_madd_fast_ni(Xyzz* p, const Affine* q) {
   Xyzz a = *p;
   xyzz_madd_fast(a, *q);
   *p = a;
 }
-__device__ __noinline__ void xyzz_dbl_fast_ni(Xyzz* p) {
+static __device__ __noinline__ void xyzz_dbl_fast_ni(Xyzz* p) {
   Xyzz a = *p;
   xyzz_dbl_fast(a);
   *p = a;
@@ -109,6 +109,9 @@ struct MsmGeom {
   uint32_t ref_base;            // single MSM processed in point-range chunks: entry ref = ref_base + col
 };
 
+// Translation units that only need the device functions of this header (engine_g2.cu, engine_pairing.cu) define
+// TB_NO_G1_KERNELS: a __global__ function must live in exactly one unit of the library.
+#ifndef TB_NO_G1_KERNELS
 // ------------------------------------------------------------------------------------------------------------
 // digits: histogram and scatter share one body
 // ------------------------------------------------------------------------------------------------------------
@@ -302,8 +305,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t* __r
 // mixed additions. A run that begins at its bucket's first entry is written to buckets[b] (each non-empty
 // bucket has exactly one such writer); a run that continues a bucket begun in an earlier segment is the
 // thread's "head" and goes to heads[t] / head_bucket[t] for k_fixup.
+// The register-operand form below is kept for reference only (TB_EXPERIMENTAL_REG_ACCUMULATE): the shared-memory operand
+// slots of k_accumulate_s (kernels_smem.cuh) are 30 % faster and the only accumulate kernel in the default build.
 constexpr int ACC_THREADS = 128;
 
+#ifdef TB_EXPERIMENTAL_REG_ACCUMULATE
 __global__ void __launch_bounds__(ACC_THREADS, 3)
     k_accumulate(const uint32_t* __restrict__ entries, const uint32_t* __restrict__ bucket_start, uint32_t B,
                  uint32_t K, const uint4* __restrict__ points, uint4* __restrict__ buckets,
@@ -347,6 +353,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 3)
   xyzz_canon(acc);
   store_xyzz(is_head ? heads + 12 * t : buckets + 12 * (uint64_t)b, acc);
 }
+#endif  // TB_EXPERIMENTAL_REG_ACCUMULATE
 
 // Heads of one bucket occupy consecutive segments first..last (first = smallest t with t*K > bucket_start[b]).
 // They are summed by pointer jumping: in round r, head `first + i` with i % 2^(r+1) == 0 absorbs head
@@ -439,6 +446,7 @@ __global__ void __launch_bounds__(128, 4) k_reduce_pass(const uint4* __restrict_
 // mutually independent multiplications (V, X^2 | W, S, M^2 | M(S-X3), W Y, V ZZ, W ZZZ), exchanged through shared
 // memory, so the chain costs three multiplication latencies per doubling. Same formulas and lazy bounds as
 // xyzz_dbl_fast (g1_fast.cuh).
+#endif  // TB_NO_G1_KERNELS
 __device__ __forceinline__ void fq_lazy_double(Fq& r, const Fq& a) {  // r = 2a, plain limb add (a < 2^383)
   Carry c;
   r.l[0] = add_cc(a.l[0], a.l[0], c);
@@ -451,6 +459,7 @@ __device__ __forceinline__ void fq_lazy_add(Fq& r, const Fq& a, const Fq& b) {
 #pragma unroll
   for (int i = 1; i < 12; i++) r.l[i] = addc_cc(a.l[i], b.l[i], c);
 }
+#ifndef TB_NO_G1_KERNELS
 __global__ void __launch_bounds__(32) k_finalize_single(const uint4* __restrict__ group_w, int W, int c,
                                                         uint4* __restrict__ out_affine) {
   // shared operand file of the cooperative doubling; all lanes run the SAME multiplier call on different operands
@@ -903,4 +912,5 @@ __global__ void __launch_bounds__(128) k_fq_mul_peak(int iters, uint32_t seed, u
   sink[tid] = acc;
 }
 
+#endif  // TB_NO_G1_KERNELS
 }  // namespace tb

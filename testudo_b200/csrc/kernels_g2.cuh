@@ -13,7 +13,7 @@
 namespace tb {
 
 __device__ __forceinline__ void load_affine2(Affine2& p, const uint4* src) {
-  uint32_t* d = p.x.c0.l;  // x.c0, x.c1, y.c0, y.c1 contiguous: 48 words
+  uint32_t* d = reinterpret_cast<uint32_t*>(&p);  // the whole packed object: 48 words
 #pragma unroll
   for (int i = 0; i < 12; i++) {
     uint4 v = src[i];
@@ -24,12 +24,12 @@ __device__ __forceinline__ void load_affine2(Affine2& p, const uint4* src) {
   }
 }
 __device__ __forceinline__ void store_affine2(uint4* dst, const Affine2& p) {
-  const uint32_t* s = p.x.c0.l;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
 #pragma unroll
   for (int i = 0; i < 12; i++) dst[i] = make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
 }
 __device__ __forceinline__ void load_xyzz2(Xyzz2& p, const uint4* src) {
-  uint32_t* d = p.x.c0.l;  // 96 words
+  uint32_t* d = reinterpret_cast<uint32_t*>(&p);  // the whole packed object: 96 words
 #pragma unroll
   for (int i = 0; i < 24; i++) {
     uint4 v = src[i];
@@ -40,17 +40,18 @@ __device__ __forceinline__ void load_xyzz2(Xyzz2& p, const uint4* src) {
   }
 }
 __device__ __forceinline__ void store_xyzz2(uint4* dst, const Xyzz2& p) {
-  const uint32_t* s = p.x.c0.l;
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
 #pragma unroll
   for (int i = 0; i < 24; i++) dst[i] = make_uint4(s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]);
 }
 static_assert(sizeof(Affine2) == 192 && sizeof(Xyzz2) == 384, "packed layouts");
 
-__device__ __noinline__ void xyzz2_add_ni(Xyzz2* p, const Xyzz2* q) { xyzz2_add(*p, *q); }
-__device__ __noinline__ void xyzz2_dbl_ni(Xyzz2* p) { xyzz2_dbl(*p); }
-__device__ __noinline__ void xyzz2_madd_ni(Xyzz2* p, const Affine2* q) { xyzz2_madd(*p, *q); }
-__device__ __noinline__ void xyzz2_to_affine_ni(Affine2* r, const Xyzz2* p) { xyzz2_to_affine(*r, *p); }
+static __device__ __noinline__ void xyzz2_add_ni(Xyzz2* p, const Xyzz2* q) { xyzz2_add(*p, *q); }
+static __device__ __noinline__ void xyzz2_dbl_ni(Xyzz2* p) { xyzz2_dbl(*p); }
+static __device__ __noinline__ void xyzz2_madd_ni(Xyzz2* p, const Affine2* q) { xyzz2_madd(*p, *q); }
+static __device__ __noinline__ void xyzz2_to_affine_ni(Affine2* r, const Xyzz2* p) { xyzz2_to_affine(*r, *p); }
 
+#ifndef TB_NO_G2_KERNELS  // see kernels.cuh: a __global__ function lives in exactly one unit
 // same segment scheme as k_accumulate (kernels.cuh): thread t owns sorted entries [t K, (t+1) K)
 __global__ void __launch_bounds__(64) k_accumulate_g2(const uint32_t* __restrict__ entries,
                                                       const uint32_t* __restrict__ bucket_start, uint32_t B, uint32_t K,
@@ -250,4 +251,5 @@ __global__ void k_test_g2_mul(const uint4* p, const uint32_t* k, uint32_t n, uin
   store_affine2(out + 12 * (uint64_t)i, o);
 }
 
+#endif  // TB_NO_G2_KERNELS
 }  // namespace tb

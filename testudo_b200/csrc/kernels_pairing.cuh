@@ -124,7 +124,7 @@ __device__ __forceinline__ void w_fq2_from_kar(Fq& o, const Fq* kar, int c) {
 
 // phases 1-3 of every product: 18 * count lanes multiply, 12 * count lanes assemble the Fq2 products, 6 * count lanes
 // assemble coefficient (t, c) of Fq6 result i. `count` = number of Fq6 products (1..3).
-__device__ __noinline__ void w_fq6_products(WScratch* w, int count) {
+static __device__ __noinline__ void w_fq6_products(WScratch* w, int count) {
   const int tid = threadIdx.x;
   W12_SYNC();
   if (tid < 18 * count) {
@@ -175,7 +175,7 @@ __device__ __forceinline__ void w_mul_v_coeff(Fq& o, const Fq (*R)[2], int t, in
 }
 
 // dst = a * b: X = {a0, a1, a0 + a1}, Y = {b0, b1, b0 + b1}; C0 = R0 + v R1, C1 = R2 - R0 - R1
-__device__ __noinline__ void w12_mul(Fq12* dst, const Fq12* a, const Fq12* b, WScratch* w) {
+static __device__ __noinline__ void w12_mul(Fq12* dst, const Fq12* a, const Fq12* b, WScratch* w) {
   const int tid = threadIdx.x;
   W12_SYNC();
   if (tid < 36) {
@@ -203,7 +203,7 @@ __device__ __noinline__ void w12_mul(Fq12* dst, const Fq12* a, const Fq12* b, WS
 }
 
 // dst = a^2 (complex squaring): R0 = a0 a1, R1 = (a0 + a1)(a0 + v a1); C0 = R1 - R0 - v R0, C1 = 2 R0
-__device__ __noinline__ void w12_sqr(Fq12* dst, const Fq12* a, WScratch* w) {
+static __device__ __noinline__ void w12_sqr(Fq12* dst, const Fq12* a, WScratch* w) {
   const int tid = threadIdx.x;
   W12_SYNC();
   if (tid < 24) {
@@ -237,7 +237,7 @@ __device__ __noinline__ void w12_sqr(Fq12* dst, const Fq12* a, WScratch* w) {
 
 // dst = a^2 for a unitary a (Granger-Scott, as fq12_cyclotomic_sqr_ol): six Fq2 products = 18 Fq products on 18 lanes.
 // tower slot of z_k: z0 = c[0], z1 = c[4], z2 = c[3], z3 = c[2], z4 = c[1], z5 = c[5]
-__device__ __noinline__ void w12_cyclotomic_sqr(Fq12* dst, const Fq12* a, WScratch* w) {
+static __device__ __noinline__ void w12_cyclotomic_sqr(Fq12* dst, const Fq12* a, WScratch* w) {
   const int tid = threadIdx.x;
   constexpr int slot[6] = {0, 4, 3, 2, 1, 5};
   W12_SYNC();
@@ -327,7 +327,7 @@ __device__ __forceinline__ void w12_conj(Fq12* dst, const Fq12* a) {
 }
 // a^(q^k), k = 1, 2: tower slot idx holds the coefficient of w^e, e = 2 idx (idx < 3) or 2 (idx - 3) + 1; every
 // Frobenius coefficient u^(e (q^k - 1)/6) lies in Fq (tests/test_oracle_pairing.py), so this is 12 independent Fq products
-__device__ __noinline__ void w12_frobenius(Fq12* dst, const Fq12* a, int k) {
+static __device__ __noinline__ void w12_frobenius(Fq12* dst, const Fq12* a, int k) {
   const int tid = threadIdx.x;
   W12_SYNC();
   Fq c;
@@ -345,7 +345,7 @@ __device__ __noinline__ void w12_frobenius(Fq12* dst, const Fq12* a, int k) {
   if (tid < 12) w12_q(dst)[tid] = c;
   W12_SYNC();
 }
-__device__ __noinline__ void w12_exp_by_x(Fq12* dst, const Fq12* a, Fq12* acc, WScratch* w) {
+static __device__ __noinline__ void w12_exp_by_x(Fq12* dst, const Fq12* a, Fq12* acc, WScratch* w) {
   w12_copy(acc, a);
   for (int bit = 62; bit >= 0; bit--) {
     w12_cyclotomic_sqr(acc, acc, w);
@@ -360,7 +360,7 @@ struct WFinalExp {
 };
 
 // the chain of fq12_final_exp_ol (ark `final_exponentiation`), one CTA; s->f holds the input, the result lands in s->r
-__device__ __noinline__ void w12_final_exp(WFinalExp* s) {
+static __device__ __noinline__ void w12_final_exp(WFinalExp* s) {
   WScratch* w = &s->w;
   w12_conj(&s->r, &s->f);
   if (threadIdx.x == 0) fq12_inv_ol(&s->f2, &s->f);      // one inversion per product
@@ -431,7 +431,7 @@ __device__ __forceinline__ void w_sqr_operands(Fq& a, Fq& b, const Fq* v, int wh
     b = v[1];
   }
 }
-__device__ __noinline__ void w_double_step(WMiller* s) {
+static __device__ __noinline__ void w_double_step(WMiller* s) {
   const int lane = threadIdx.x;
   enum { VA = 0, VB, VC, VYZ, VJ, VE, VD, VG, VH, VNH, VJ3 };
   Fq(*v)[2] = s->v;
@@ -557,7 +557,7 @@ __device__ __noinline__ void w_double_step(WMiller* s) {
 }
 
 // s->p, s->q loaded; result in s->f
-__device__ __noinline__ void w_miller_loop(WMiller* s) {
+static __device__ __noinline__ void w_miller_loop(WMiller* s) {
   const int lane = threadIdx.x;
   W12_SYNC();
   if (lane < 6) {

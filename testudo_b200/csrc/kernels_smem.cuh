@@ -9,7 +9,9 @@
 // integer-pipe time), nothing spills, and the freed registers hold the prefetched next point.
 #pragma once
 #include "kernels.cuh"
-#include "mont_kara.cuh"
+#ifdef TB_EXPERIMENTAL_KARATSUBA  // measured 3 % slower on sm_100a; not part of the default build
+#include "experimental/mont_kara.cuh"
+#endif
 
 namespace tb {
 
@@ -33,23 +35,25 @@ __device__ __forceinline__ void slot_store(uint4* sm, int slot, const Fq& v) {
   p[2 * ACCS_THREADS] = make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]);
 }
 // d = a * b (lazy Montgomery product); `sm` already points at this thread's lane of slot 0
-__device__ __noinline__ void slot_mul(uint4* sm, int d, int a, int b) {
+static __device__ __noinline__ void slot_mul(uint4* sm, int d, int a, int b) {
   Fq x, y, r;
   slot_load(x, sm, a);
   slot_load(y, sm, b);
   mont_mul_lazy<FqParams>(r.l, x.l, y.l);
   slot_store(sm, d, r);
 }
-// Karatsuba variant (mont_kara.cuh): 240 instead of 276 wide MACs but ~170 more ALU-pipe instructions
-__device__ __noinline__ void slot_mul_k(uint4* sm, int d, int a, int b) {
+#ifdef TB_EXPERIMENTAL_KARATSUBA
+// Karatsuba variant (experimental/mont_kara.cuh): 240 instead of 276 wide MACs but ~170 more ALU-pipe instructions
+static __device__ __noinline__ void slot_mul_k(uint4* sm, int d, int a, int b) {
   Fq x, y, r;
   slot_load(x, sm, a);
   slot_load(y, sm, b);
   mont_mul_kara(r.l, x.l, y.l);
   slot_store(sm, d, r);
 }
+#endif
 // d = a * b + c * e, even/odd CIOS with one reduction (mont_mul2_lazy: 420 wide MACs)
-__device__ __noinline__ void slot_mul2_c(uint4* sm, int d, int a, int b, int c, int e) {
+static __device__ __noinline__ void slot_mul2_c(uint4* sm, int d, int a, int b, int c, int e) {
   Fq x, y, z, w, r;
   slot_load(x, sm, a);
   slot_load(y, sm, b);
@@ -62,11 +66,16 @@ __device__ __noinline__ void slot_mul2_c(uint4* sm, int d, int a, int b, int c, 
 // free next to IMAD.WIDE, benches/pipes.cu); bit 1 = Y3 as ONE fused sum of two products (-132 wide MACs, default)
 template <int V>
 __device__ __forceinline__ void slot_mulv(uint4* sm, int d, int a, int b) {
-  if ((V & 1) == 0) slot_mul(sm, d, a, b);
-  else slot_mul_k(sm, d, a, b);
+#ifdef TB_EXPERIMENTAL_KARATSUBA
+  if ((V & 1) != 0) {
+    slot_mul_k(sm, d, a, b);
+    return;
+  }
+#endif
+  slot_mul(sm, d, a, b);
 }
 // d = a * a (dedicated squaring)
-__device__ __noinline__ void slot_sqr(uint4* sm, int d, int a) {
+static __device__ __noinline__ void slot_sqr(uint4* sm, int d, int a) {
   Fq x, r;
   slot_load(x, sm, a);
   mont_sqr_lazy<FqParams>(r.l, x.l);

@@ -119,24 +119,34 @@ class _DeviceBuffer:
 
 
 class Polynomial:
-    def __init__(self, z: np.ndarray, m: int, odd: int):
+    def __init__(self, z: np.ndarray, m: int, odd: int, resident: Optional[bool] = None):
         self.Z = z            # [2^n, 4] Montgomery Fr, un-transposed (host copy)
         self.m = m            # m_col
         self.odd = odd
         self.q: Optional[np.ndarray] = None
         self.chis_b: Optional[np.ndarray] = None
-        # the reference transposes Z here (src/sqrt_pst.rs:48-62); we upload it instead, once: commit and get_q
-        # then work on the resident matrix
-        self._dZ = _DeviceBuffer(z)
+        # The reference transposes Z here (src/sqrt_pst.rs:48-62). One GPU: we upload it instead, once, and commit and
+        # get_q work on the resident matrix. Several GPUs (tb200_init_devices): commit hands the HOST matrix to the
+        # library, which ships every GPU its row range (chunked, overlapped with the compute); the primary's copy for
+        # get_q is uploaded when `open` first needs it.
+        self.resident = (_lib.device_count() <= 1) if resident is None else resident
+        self._dZ_buf: Optional[_DeviceBuffer] = _DeviceBuffer(z) if self.resident else None
+
+    @property
+    def _dZ(self) -> "_DeviceBuffer":
+        if self._dZ_buf is None:
+            self._dZ_buf = _DeviceBuffer(self.Z)
+        return self._dZ_buf
 
     @classmethod
-    def from_evaluations(cls, Z) -> "Polynomial":
+    def from_evaluations(cls, Z, resident: Optional[bool] = None) -> "Polynomial":
         """src/sqrt_pst.rs:32-75. len(Z) must be a power of two."""
         z = np.ascontiguousarray(Z, dtype=np.uint64).reshape(-1, 4)
         n = len(z)
         assert n > 0 and n & (n - 1) == 0
         num_vars = n.bit_length() - 1
-        return cls(z, num_vars // 2, num_vars % 2)
+        _lib.engine()
+        return cls(z, num_vars // 2, num_vars % 2, resident)
 
     @property
     def m_row(self) -> int:
@@ -153,6 +163,8 @@ class Polynomial:
         rows, cols = 1 << self.m, 1 << self.m_row
         assert cols == len(ck.powers_of_g0), "ck.powers_of_g[0] must have 2^m_row points"
         lib = _lib.engine()
+        if not self.resident:
+            return self._commit_host(ck)
         d_out = _DeviceBuffer(np.zeros((rows, 12), dtype=np.uint64))
         _lib.check(lib.tb200_msm_g1_batch_dev(ck._h, self._dZ.ptr, rows, cols, 1, rows, _lib.SCALARS_MONT, d_out.ptr, None))
         t = None
@@ -169,6 +181,21 @@ class Polynomial:
         _lib.check(lib.tb200_stream_sync())
         out = d_out.download((rows, 12))
         d_out.free()
+        return out, t
+
+    def _commit_host(self, ck: CommitterKey) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+        """commit from the HOST matrix through the sharding entry points: rows (and t) in one library call."""
+        rows, cols = 1 << self.m, 1 << self.m_row
+        lib = _lib.engine()
+        out = np.zeros((rows, 12), dtype=np.uint64)
+        if ck.powers_of_h is None:
+            _lib.check(lib.tb200_msm_g1_batch(ck._h, _ptr(self.Z), rows, cols, 1, rows, _lib.SCALARS_MONT, _ptr(out)))
+            return out, None
+        h_vec = np.ascontiguousarray(ck.powers_of_h[self.odd], dtype=np.uint64).reshape(-1, 24)
+        assert len(h_vec) == rows, "comm_list.len() == h_vec.len() (src/sqrt_pst.rs:129)"
+        t = np.zeros(pairing.GT_WORDS, dtype=np.uint64)
+        _lib.check(lib.tb200_sqrt_pst_commit_strided(ck._h, _ptr(self.Z), rows, cols, 1, rows, _lib.SCALARS_MONT,
+                                                     _ptr(h_vec), _ptr(out), _ptr(t)))
         return out, t
 
     def get_q(self, point: List[int]) -> None:

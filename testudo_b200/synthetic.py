@@ -44,13 +44,15 @@ def split(n: int) -> Tuple[int, int]:
     return na, nb
 
 
-def make_bases_dev(n: int, seed: int = 1) -> torch.Tensor:
-    """[n, 12] int64 CUDA tensor of affine points with known dlogs."""
+def make_bases_dev(n: int, seed: int = 1, multiples_of_g=None) -> torch.Tensor:
+    """[n, 12] int64 CUDA tensor of affine points with known dlogs. `multiples_of_g(start, step, count)` -> [count, 12]
+    words lets a checker supply the 2 sqrt(n) generator multiples from outside the engine (tests pass the oracle's)."""
     lib = _lib.init()
     a0, sa, b0, sb = dlog_params(seed)
     na, nb = split(n)
-    A = torch.from_numpy(_multiples_of_g(lib, a0, sa, na).view(np.int64)).cuda()
-    B = torch.from_numpy(_multiples_of_g(lib, b0, sb, nb).view(np.int64)).cuda()
+    gen = multiples_of_g or (lambda start, step, count: _multiples_of_g(lib, start, step, count))
+    A = torch.from_numpy(np.ascontiguousarray(gen(a0, sa, na), dtype=np.uint64).view(np.int64)).cuda()
+    B = torch.from_numpy(np.ascontiguousarray(gen(b0, sb, nb), dtype=np.uint64).view(np.int64)).cuda()
     out = torch.empty((na * nb, 12), dtype=torch.int64, device="cuda")
     _lib.check(lib.tb200_g1_outer_sum_dev(_p(A), na, _p(B), nb, _p(out), None))
     torch.cuda.synchronize()
@@ -71,12 +73,12 @@ def make_scalars_dev(n: int, seed: int = 1, skew: bool = False) -> torch.Tensor:
     return s
 
 
-def expected_msm(scalars: torch.Tensor, n: int, seed: int = 1) -> np.ndarray:
-    """Closed-form result of MSM(make_bases_dev(n, seed), scalars) as C-ABI words (one GPU scalar-mul)."""
-    lib = _lib.init()
+def expected_dlog(scalars, n: int, seed: int = 1) -> int:
+    """sum_k s_k * dlog_k mod r for MSM(make_bases_dev(n, seed), scalars): the discrete log of the result. Host integer
+    work only; a checker turns it into the expected point with ITS OWN scalar multiplication (tests: the oracle's)."""
     a0, sa, b0, sb = dlog_params(seed)
     na, nb = split(n)
-    s = scalars[:n].cpu().numpy().view(np.uint64)
+    s = scalars[:n].cpu().numpy().view(np.uint64) if isinstance(scalars, torch.Tensor) else np.asarray(scalars[:n]).view(np.uint64)
     pad = na * nb - n
     if pad:
         s = np.concatenate([s, np.zeros((pad, 4), dtype=np.uint64)])
@@ -95,7 +97,14 @@ def expected_msm(scalars: torch.Tensor, n: int, seed: int = 1) -> np.ndarray:
         total += to_int(row_sums[i]) * (a0 + i * sa + b0)
     for j in range(nb):
         total += to_int(col_sums[j]) * (j * sb)
-    k = curve.scalars_to_words([total % curve.R_ORDER])
+    return total % curve.R_ORDER
+
+
+def expected_msm(scalars, n: int, seed: int = 1) -> np.ndarray:
+    """Closed-form result of MSM(make_bases_dev(n, seed), scalars) as C-ABI words, with the one scalar multiplication on
+    the GPU (self-check only: three engine paths agreeing; the parity tests use expected_dlog + the oracle)."""
+    lib = _lib.init()
+    k = curve.scalars_to_words([expected_dlog(scalars, n, seed)])
     out = np.zeros((1, 12), dtype=np.uint64)
     g = curve.generator_words().reshape(1, 12)
     _lib.check(lib.tb200_test_g1_mul(_np_p(g), _np_p(k), 1, _np_p(out)))
