@@ -121,3 +121,8 @@ def ark_window_bits(n: int) -> int:
 
 def num_threads() -> int:
     return lib().oracle_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    """omp_set_num_threads: torchrun exports OMP_NUM_THREADS=1, which would make the CPU arm a 1-core figure."""
+    lib().oracle_set_num_threads(ctypes.c_int(int(n)))

@@ -402,6 +402,13 @@ static void load_scalars(uint64_t *dst, const uint64_t *src, size_t n, int mont)
   for (size_t i = 0; i < n; i++) fr_from_mont(dst + 4 * i, src + 4 * i);
 }
 
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

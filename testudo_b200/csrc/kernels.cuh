@@ -855,7 +855,7 @@ __global__ void k_test_g1_mul(const uint4* p, const uint32_t* k, uint32_t n, uin
 // Eight chains per thread; every chain's multiplier is the low word another chain produced one step earlier, so
 // nothing is loop-invariant (ptxas strength-reduces an invariant product to adds) and nothing is warp-uniform
 // (ptxas moves uniform chains to the uniform datapath) -- both were observed with a naive version.
-// kind 0: IMAD.WIDE.U32 (32x32+64 -> 64);  kind 1: IMAD (32x32+32 -> 32)
+// kind 0: IMAD.WIDE.U32.X (32x32+64 -> 64 with carry in / out);  kind 1: IMAD (32x32+32 -> 32)
 __global__ void __launch_bounds__(256) k_int_pipe(int kind, int iters, uint32_t seed, uint64_t* sink) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t b = (seed * 40503u + tid * 2654435761u) | 1u;
@@ -868,8 +868,14 @@ __global__ void __launch_bounds__(256) k_int_pipe(int kind, int iters, uint32_t 
       for (int u = 0; u < 8; u++) {
 #pragma unroll
         for (int k = 0; k < 8; k++) {
+          // the carry-chained pair the Montgomery products issue (SASS: IMAD.WIDE.U32.X); the plain
+          // `mad.wide.u32 c, a, b, c` with a 64-bit addend issues 25 % slower (benches/pipes.cu) and under-states the peak
           uint32_t a = (uint32_t)c[(k + 1) & 7];
-          asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[k]) : "r"(a), "r"(b));
+          uint32_t lo = (uint32_t)c[k], hi = (uint32_t)(c[k] >> 32);
+          if (k == 0) asm volatile("mad.lo.cc.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(a), "r"(b));
+          else asm volatile("madc.lo.cc.u32 %0, %1, %2, %0;" : "+r"(lo) : "r"(a), "r"(b));
+          asm volatile("madc.hi.cc.u32 %0, %1, %2, %0;" : "+r"(hi) : "r"(a), "r"(b));
+          c[k] = ((uint64_t)hi << 32) | lo;
         }
       }
     }
