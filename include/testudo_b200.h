@@ -183,6 +183,15 @@ int tb200_stream_sync(void); /* wait for work enqueued on the library's stream b
 /* Page-locked host memory usable from every device of the library (cudaHostAlloc portable / cudaHostRegister): uploads
  * from such buffers are asynchronous and run at full PCIe rate; pageable buffers work too but are staged by the driver. */
 int tb200_host_alloc(size_t bytes, void** out);
+/* NUMA-placed pinned buffers. Page-locked pages live where they were first touched; eight GPUs reading 2 GiB each from
+ * one socket's memory are bound by that socket, not by PCIe (round 1: 0.72 end-to-end efficiency at 8 GPUs). _near places
+ * the buffer on the NUMA node of device slot `device_slot`; _sharded splits `units` elements of `unit_bytes` into the
+ * SAME contiguous per-device ranges the sharded entry points use (point ranges of tb200_msm_g1, row ranges of a row-major
+ * batch) and places every range next to the GPU that will read it. Without topology in sysfs both are plain pinned
+ * allocations. Free with tb200_host_free. tb200_device_numa_node: the node of a device slot, -1 if unknown. */
+int tb200_host_alloc_near(size_t bytes, int device_slot, void** out);
+int tb200_host_alloc_sharded(size_t units, size_t unit_bytes, void** out);
+int tb200_device_numa_node(int device_slot);
 int tb200_host_free(void* h_ptr);
 int tb200_host_register(void* h_ptr, size_t bytes);
 int tb200_host_unregister(void* h_ptr);

@@ -40,6 +40,9 @@ SIGNATURES = {
     "tb200_sqrt_pst_commit_strided": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_ssize_t, c_ssize_t, c_uint,
                                               c_void_p, c_void_p, c_void_p]),
     "tb200_host_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
+    "tb200_host_alloc_near": (c_int, [c_size_t, c_int, ctypes.POINTER(c_void_p)]),
+    "tb200_host_alloc_sharded": (c_int, [c_size_t, c_size_t, ctypes.POINTER(c_void_p)]),
+    "tb200_device_numa_node": (c_int, [c_int]),
     "tb200_host_free": (c_int, [c_void_p]),
     "tb200_host_register": (c_int, [c_void_p, c_size_t]),
     "tb200_host_unregister": (c_int, [c_void_p]),

@@ -14,6 +14,8 @@
 //     collective: every GPU writes its rows straight into the caller's output buffer.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <sched.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 
@@ -121,9 +123,59 @@ int finish_marks(Ctx& g, cudaStream_t st) {
   return 0;
 }
 
+// ---- NUMA topology from sysfs (placement of pinned buffers and of the worker threads; see tb200_host_alloc_sharded) ------
+int numa_node_of(int device) {
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return -1;
+  for (char* c = bus; *c; c++) *c = (char)tolower(*c);
+  std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return -1;
+  int node = -1;
+  if (fscanf(f, "%d", &node) != 1) node = -1;
+  fclose(f);
+  return node;
+}
+// CPUs of a node ("0-31,64-95") intersected with the CPUs this process may run on; empty when unknown
+std::vector<int> cpus_of_node(int node) {
+  std::vector<int> out;
+  if (node < 0) return out;
+  char path[96];
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  FILE* f = fopen(path, "r");
+  if (!f) return out;
+  char buf[4096] = {0};
+  if (!fgets(buf, sizeof buf, f)) buf[0] = 0;
+  fclose(f);
+  cpu_set_t allowed;
+  CPU_ZERO(&allowed);
+  if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return out;
+  for (char* p = buf; *p && *p != '\n';) {
+    char* end;
+    long a = strtol(p, &end, 10), b = a;
+    if (end == p) break;
+    p = end;
+    if (*p == '-') {
+      b = strtol(p + 1, &end, 10);
+      p = end;
+    }
+    for (long c = a; c <= b && c < CPU_SETSIZE; c++)
+      if (CPU_ISSET((int)c, &allowed)) out.push_back((int)c);
+    if (*p == ',') p++;
+  }
+  return out;
+}
+bool bind_this_thread(const std::vector<int>& cpus) {
+  if (cpus.empty()) return false;
+  cpu_set_t set;
+  CPU_ZERO(&set);
+  for (int c : cpus) CPU_SET(c, &set);
+  return sched_setaffinity(0, sizeof set, &set) == 0;
+}
 // ---- worker threads ------------------------------------------------------------------------------------------------------
 static void worker_main(Ctx* c) {
   cudaSetDevice(c->device);
+  bind_this_thread(cpus_of_node(numa_node_of(c->device)));  // copies are issued from the GPU's own socket
   std::unique_lock<std::mutex> lk(c->wmu);
   for (;;) {
     c->wcv.wait(lk, [c] { return c->job_ready || c->quit; });
@@ -488,6 +540,55 @@ int tb200_stream_sync(void) {
   CU(cudaStreamSynchronize(primary().stream));
   return 0;
 }
+// ---- NUMA placement of pinned host buffers ----------------------------------------------------------------------------
+// Eight GPUs pulling 2 GiB each from pinned pages that all sit on one socket are limited by that socket's memory
+// controllers and the inter-socket link, not by PCIe (round 1: end-to-end efficiency 0.72 at 8 GPUs). Pinned pages are
+// physically placed when they are first touched, so the shard a GPU will read is touched by a thread bound to the CPUs
+// of that GPU's NUMA node and only then page-locked. Everything degrades to a plain pinned allocation when sysfs
+// exposes no topology (numa_node = -1, single node, restricted cpuset).
+namespace {
+std::map<void*, size_t> g_mapped;  // buffers handed out by tb200_host_alloc_sharded / _near: base -> mapped bytes
+
+// first touch of [p, p + bytes) from threads bound to `node` (unbound if the node is unknown)
+void touch_on_node(char* p, size_t bytes, int node) {
+  const std::vector<int> cpus = cpus_of_node(node);
+  const int nt = (int)std::max<size_t>(1, std::min<size_t>(8, bytes >> 26));
+  std::vector<std::thread> ts;
+  for (int t = 0; t < nt; t++)
+    ts.emplace_back([=, &cpus] {
+      bind_this_thread(cpus);
+      const size_t a = bytes * t / nt, b = bytes * (t + 1) / nt;
+      for (size_t o = a; o < b; o += 4096) p[o] = 0;
+    });
+  for (auto& t : ts) t.join();
+}
+// shares[i] bytes placed next to device slot dev_slot[i], one contiguous page-locked mapping
+int host_alloc_placed(const std::vector<size_t>& shares, const std::vector<int>& dev_slot, void** out) {
+  size_t bytes = 0;
+  for (size_t s : shares) bytes += s;
+  const size_t mapped = (bytes + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1);
+  void* p = mmap(nullptr, mapped, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) return fail(TB200_E_LIMIT, "mmap of %zu bytes failed", mapped);
+  madvise(p, mapped, MADV_HUGEPAGE);
+  size_t off = 0;
+  for (size_t i = 0; i < shares.size(); i++) {
+    // page-granular boundaries: the page that straddles two shares goes with the first
+    const size_t end = (i + 1 == shares.size()) ? mapped : std::min(mapped, (off + shares[i] + 4095) & ~size_t(4095));
+    const size_t start = (off + 4095) & ~size_t(4095);
+    if (end > start) touch_on_node((char*)p + start, end - start, numa_node_of(E.devs[dev_slot[i]]->device));
+    off += shares[i];
+  }
+  cudaError_t e = cudaHostRegister(p, mapped, cudaHostRegisterPortable);
+  if (e != cudaSuccess) {
+    munmap(p, mapped);
+    return fail((int)e, "cudaHostRegister of %zu bytes failed: %s", mapped, cudaGetErrorString(e));
+  }
+  g_mapped[p] = mapped;
+  *out = p;
+  return 0;
+}
+}  // namespace
+
 int tb200_host_alloc(size_t bytes, void** out) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (need_ready()) return TB200_E_STATE;
@@ -496,9 +597,43 @@ int tb200_host_alloc(size_t bytes, void** out) {
   CU(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
   return 0;
 }
+int tb200_host_alloc_near(size_t bytes, int device_slot, void** out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || bytes == 0 || device_slot < 0 || device_slot >= ndev()) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(primary().device));
+  return host_alloc_placed({bytes}, {device_slot}, out);
+}
+int tb200_host_alloc_sharded(size_t units, size_t unit_bytes, void** out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || units == 0 || unit_bytes == 0) return fail(TB200_E_ARG, "bad arguments");
+  CU(cudaSetDevice(primary().device));
+  std::vector<size_t> shares;
+  std::vector<int> slots;
+  for (int i = 0; i < ndev(); i++) {  // the same split the sharded entry points use
+    size_t lo, hi;
+    shard_range(units, ndev(), i, &lo, &hi);
+    shares.push_back((hi - lo) * unit_bytes);
+    slots.push_back(i);
+  }
+  return host_alloc_placed(shares, slots, out);
+}
+int tb200_device_numa_node(int device_slot) {
+  if (!E.ready || device_slot < 0 || device_slot >= ndev()) return -1;
+  return numa_node_of(E.devs[device_slot]->device);
+}
 int tb200_host_free(void* p) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (need_ready()) return TB200_E_STATE;
+  auto it = g_mapped.find(p);
+  if (it != g_mapped.end()) {
+    cudaError_t e = cudaHostUnregister(p);
+    munmap(p, it->second);
+    g_mapped.erase(it);
+    if (e != cudaSuccess) return fail((int)e, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+    return 0;
+  }
   CU(cudaFreeHost(p));
   return 0;
 }
