@@ -233,6 +233,10 @@ void tb200_set_accumulate_mode(int mode);
  * (default 2^18; 0 restores it). */
 void tb200_set_pass_entries_max(uint64_t entries);
 void tb200_set_shard_min(size_t units);
+/* tb200_sqrt_pst_commit: 1 = run the Miller loops of every row chunk on a side stream next to the row MSMs of the
+ * following chunk (one partial product per chunk); 0 (default) = all Miller loops behind the row stage. See DESIGN.md
+ * (multi-GPU) for the measurements behind the default. */
+void tb200_set_commit_pipeline(int enabled);
 /* integer-pipe microbenchmark: runs `iters` dependent-chain iterations of wide MACs on every SM and returns the
  * achieved 32x32->64 multiply-accumulates per second in *out_macs_per_s (kind: 0 = IMAD.WIDE.U32 reg-reg,
  * 1 = IMAD (32-bit lo), 2 = full Fq Montgomery multiplications per second). */

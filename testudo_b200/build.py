@@ -24,7 +24,7 @@ UNITS = {
     "engine_g2.cu": _G2,
     "engine_pairing.cu": _G2 + ["fq12.cuh", "fq12_consts.inc", "kernels_pairing.cuh"],
 }
-COMMON = ["engine.h", API_HEADER]
+COMMON = ["engine.h", "glv_host.h", API_HEADER]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

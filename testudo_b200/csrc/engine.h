@@ -133,6 +133,7 @@ struct Engine {
   size_t host_chunk_min = size_t(1) << 21;  // host-facing single MSMs: chunked upload/compute overlap from here
   size_t shard_min = size_t(1) << 18;       // host-facing single MSMs are sharded over the GPUs from ndev * this
   int pairing_coop_max = 2048;              // Miller loops: CTA-per-pair up to this many pairs, lanes-per-pair above
+  int commit_pipeline = 0;                  // tb200_sqrt_pst_commit: Miller loops of a row chunk next to the next chunk's MSMs
   int acc_mode = 0;                         // 0 / 4: fused-Y3 XYZZ segments (default); 3: plain CIOS products
   uint64_t pass_entries_max = (1ull << 32) - 1024;  // sorted entries one pipeline pass can index (tests lower it)
   bool profiling = false;
@@ -172,6 +173,13 @@ struct tb200_mipp {
   uint32_t* scal_host = nullptr;  // pinned, same shape
   uint32_t* digits = nullptr;     // the two 128-bit halves of c over the G1 endomorphism, 8 words per round
   int round = 0;
+  // two-phase fold (kernels_pairing.cuh): the multiples 2^j a_r[i] of the NEXT fold are computed on `pre_st` while the
+  // round's cross values are; nullptr = one-phase fold (vector too long for the table)
+  uint4* mult = nullptr;
+  cudaStream_t pre_st = nullptr;
+  cudaEvent_t ev_pre = nullptr, ev_fold = nullptr;
+  uint16_t* sel = nullptr;        // per round: the selection list of the fold scalar (glv_host.h), device / pinned host
+  uint16_t* sel_host = nullptr;
 };
 // the G2 commitment key of MIPP (m_h, src/mipp.rs:43,114): folded on its own stream, overlapping the G1 rounds
 struct tb200_mipp_g2 {
@@ -183,6 +191,11 @@ struct tb200_mipp_g2 {
   uint32_t* scal_host = nullptr;  // pinned, same shape
   cudaStream_t st = nullptr;      // own stream: the folds overlap the G1 rounds on the library's streams
   int round = 0;
+  uint4* mult = nullptr;          // two-phase fold, as in tb200_mipp
+  cudaStream_t pre_st = nullptr;
+  cudaEvent_t ev_pre = nullptr, ev_fold = nullptr;
+  uint16_t* sel = nullptr;
+  uint16_t* sel_host = nullptr;
 };
 
 namespace tbe {
@@ -221,6 +234,12 @@ int g2_finalize_single(cudaStream_t st, const uint4* group_w, int W, int c, uint
 int g2_finalize_single_glv(cudaStream_t st, const uint4* group_w, int W, int c, uint4* fin_scratch, uint4* d_out);
 // a_l + c a_r over the G1 endomorphism: digits of c (8 words at d_digits) then the fold of `split` elements
 int g1_fold_glv(cudaStream_t st, const uint32_t* d_scaler, int mont, uint32_t* d_digits, uint4* a, uint32_t split);
+// the same fold in two phases: multiples of a[first .. first + count) (independent of the scalar) / the fold itself
+constexpr size_t FOLD_MULT_BYTES_MAX = size_t(3) << 30;      // per handle; longer vectors use the one-phase fold
+inline size_t g1_fold_mult_bytes(size_t n) { return (n / 2) * 127 * 192; }
+inline size_t g2_fold_mult_bytes(size_t n) { return (n / 2) * 64 * 384; }
+int g1_fold_pre(cudaStream_t st, const uint4* a, uint32_t first, uint32_t count, uint4* mult);
+int g1_fold_apply(cudaStream_t st, const uint16_t* d_sel, uint4* a, uint32_t split, const uint4* mult);
 // Miller loops of n pairs -> product tree -> (optionally) final exponentiation; see engine_pairing.cu
 int pairing_products(Ctx& g, const uint4* d_g1, const uint4* d_g2, uint32_t n, uint32_t xor_mask, uint32_t segs,
                      uint4* d_out, cudaStream_t st, cudaEvent_t after_miller, const uint4* d_gt_in = nullptr,

@@ -497,6 +497,7 @@ void tb200_set_pass_entries_max(uint64_t entries) {
   E.pass_entries_max = entries ? std::min<uint64_t>(std::max<uint64_t>(entries, 1024), (1ull << 32) - 1024) : (1ull << 32) - 1024;
 }
 void tb200_set_shard_min(size_t units) { E.shard_min = units ? units : (size_t(1) << 18); }
+void tb200_set_commit_pipeline(int enabled) { E.commit_pipeline = enabled ? 1 : 0; }
 
 // ---- device / pinned host buffers for hosts without a CUDA runtime of their own ------------------------------------------
 int tb200_dev_alloc(size_t bytes, void** out) {
@@ -831,29 +832,71 @@ struct RowChunk {
 
 // chunks of growing size: the first upload is the only one the GPU waits for, every later one hides behind the
 // previous chunk's compute (57 us of integer work vs 5-25 us of transfer per 8192-column row)
-std::vector<RowChunk> row_chunks(size_t rows, int sms) {
+std::vector<RowChunk> row_chunks(size_t rows, int sms, bool small_tail) {
   std::vector<RowChunk> v;
   const size_t min_chunk = (size_t)std::max(sms, 1);  // >= one CTA per SM for the per-row sort kernel
   if (rows < 4 * min_chunk) {
     v.push_back({0, rows});
     return v;
   }
+  // The LAST chunks are small as well: whatever follows the row MSMs of a chunk (its Miller loops in
+  // tb200_sqrt_pst_commit, the download of its rows) overlaps the compute of the chunks behind it -- except for the last
+  // one. Miller kernels that share the SMs with the accumulation run ~3x slower than alone (their dependent IMAD chains
+  // queue behind a saturated integer pipe), so the chunk BEFORE the last is small too: a 4460-pair Miller kernel behind
+  // a 148-row tail left 10+ ms exposed (measured: t cost 22 ms instead of 12).
+  // Measured (profiles/r02_summary.md): the pipelined pairing LOSES 9-12 ms at 4096-8192 rows per GPU -- every Miller
+  // CTA that becomes resident displaces an accumulation CTA (4 x 128 threads x 128 registers fill the register file) --
+  // so it is opt-in (tb200_set_commit_pipeline) and the small tail chunks exist only then.
+  const size_t tail = small_tail ? min_chunk : 0;
+  size_t pre = small_tail ? std::max(min_chunk, rows / 16) : 0;
+  if (rows < tail + pre + 2 * min_chunk) pre = 0;
+  const size_t body = rows - tail - pre;
   size_t len = std::max(min_chunk, rows / 16), a = 0;
-  while (a < rows) {
-    size_t b = std::min(rows, a + len);
-    if (rows - b < min_chunk) b = rows;
+  while (a < body) {
+    size_t b = std::min(body, a + len);
+    if (body - b < min_chunk) b = body;
     v.push_back({a, b});
     a = b;
     len *= 2;
   }
+  if (pre) v.push_back({body, body + pre});
+  if (tail) v.push_back({body + pre, rows});
   return v;
 }
 
-// One device's share (rows [r0, r1) of the batch): chunked upload on the copy stream, pipeline per chunk on the main
-// stream, results left in d_out (my_rows x 96 B, device). Device layout of the scalars: [cols_total][chunk rows] for a
-// column-major source (row stride 1: the un-transposed sqrt_pst matrix), else [chunk rows][cols_total].
+// Pairing stage of tb200_sqrt_pst_commit, pipelined: once the rows of a chunk exist, their Miller loops against the
+// matching slice of the G2 key run on the context's pair stream NEXT TO the row MSMs of the following chunk (the Miller
+// kernels are latency-bound and leave the integer pipe to the accumulation); one partial Miller product per chunk.
+struct PairPipe {
+  const uint4* d_h = nullptr;    // this share's slice of h_vec on the device (rows [r0, r1)), nullptr: no pairing stage
+  cudaEvent_t h_ready = nullptr; // recorded on the copy stream once d_h has arrived
+  uint4* d_parts = nullptr;      // one 576-byte partial product per chunk
+  int nparts = 0;
+};
+int pair_stream_ready(Ctx& g) {
+  if (g.pair_stream) return 0;
+  CU(cudaStreamCreateWithFlags(&g.pair_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&g.ev_pair, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&g.ev_pair2, cudaEventDisableTiming));
+  return 0;
+}
+int pair_chunk(Ctx& g, PairPipe* pp, const uint4* d_rows, size_t a, size_t nr) {
+  if (!pp || !pp->d_h || nr == 0) return 0;
+  if (int rc = pair_stream_ready(g)) return rc;
+  CU(cudaEventRecord(g.ev_pair, g.stream));               // the rows of this chunk exist
+  CU(cudaStreamWaitEvent(g.pair_stream, g.ev_pair, 0));
+  if (pp->nparts == 0) CU(cudaStreamWaitEvent(g.pair_stream, pp->h_ready, 0));
+  const bool prof = g.profiling;
+  g.profiling = false;                                    // stage marks belong to the main stream
+  int rc = pairing_products(g, d_rows + 6 * a, pp->d_h + 12 * a, (uint32_t)nr, 0, 1, pp->d_parts + 36 * (size_t)pp->nparts,
+                            g.pair_stream, nullptr, nullptr, false);
+  g.profiling = prof;
+  pp->nparts++;
+  return rc;
+}
+
 int batch_share_enqueue(Ctx& g, const tb200_srs* srs, const RowSource& src, size_t r0, size_t r1, unsigned flags,
-                        uint4** d_out_p, std::vector<void*>& to_free) {
+                        uint4** d_out_p, std::vector<void*>& to_free, PairPipe* pp = nullptr) {
   CU(cudaSetDevice(g.device));
   const size_t my_rows = r1 - r0, cols = src.cols, colsT = cols + (src.blinds ? 1 : 0);
   uint4* d_o = nullptr;
@@ -861,8 +904,15 @@ int batch_share_enqueue(Ctx& g, const tb200_srs* srs, const RowSource& src, size
   to_free.push_back(d_o);
   *d_out_p = d_o;
   if (my_rows == 0) return 0;
-  if (colsT == 0) return batch_dev(g, srs->table[g.slot], srs->c, srs->W, srs->n, (const uint32_t*)d_o, my_rows, 0, 0, 1,
-                                   flags, d_o, g.stream);
+  if (pp && pp->d_h) {
+    CU(cudaMallocAsync((void**)&pp->d_parts, (row_chunks(my_rows, g.sms, true).size() + 1) * 576, g.stream));
+    to_free.push_back(pp->d_parts);
+  }
+  if (colsT == 0) {
+    int rc = batch_dev(g, srs->table[g.slot], srs->c, srs->W, srs->n, (const uint32_t*)d_o, my_rows, 0, 0, 1, flags, d_o,
+                       g.stream);
+    return rc ? rc : pair_chunk(g, pp, d_o, 0, my_rows);
+  }
   const bool col_major = !src.ptrs && src.rs == 1 && src.rows > 1;  // rows are the unit-stride dimension
   const bool simple = src.ptrs || col_major || (src.cs == 1);
   if (!simple) {
@@ -873,15 +923,16 @@ int batch_share_enqueue(Ctx& g, const tb200_srs* srs, const RowSource& src, size
     CU(cudaMallocAsync((void**)&d_s, extent * 32, g.stream));
     to_free.push_back(d_s);
     CU(cudaMemcpyAsync(d_s, src.base + 4 * (long long)r0 * src.rs, extent * 32, cudaMemcpyHostToDevice, g.stream));
-    return batch_dev(g, srs->table[g.slot], srs->c, srs->W, srs->n, (const uint32_t*)d_s, my_rows, cols, src.rs, src.cs,
-                     flags, d_o, g.stream);
+    int rc = batch_dev(g, srs->table[g.slot], srs->c, srs->W, srs->n, (const uint32_t*)d_s, my_rows, cols, src.rs, src.cs,
+                       flags, d_o, g.stream);
+    return rc ? rc : pair_chunk(g, pp, d_o, 0, my_rows);
   }
   uint4* d_s = nullptr;
   CU(cudaMallocAsync((void**)&d_s, my_rows * colsT * 32, g.stream));
   to_free.push_back(d_s);
   CU(cudaEventRecord(g.ev_points, g.stream));  // the allocation exists
   CU(cudaStreamWaitEvent(g.copy_stream, g.ev_points, 0));
-  const std::vector<RowChunk> chunks = row_chunks(my_rows, g.sms);
+  const std::vector<RowChunk> chunks = row_chunks(my_rows, g.sms, pp && pp->d_h);
   std::vector<cudaEvent_t>& evs = g.chunk_ev;
   while (evs.size() < chunks.size()) {
     cudaEvent_t e;
@@ -933,6 +984,8 @@ int batch_share_enqueue(Ctx& g, const tb200_srs* srs, const RowSource& src, size
     int rc = batch_dev(g, srs->table[g.slot], srs->c, srs->W, srs->n, (const uint32_t*)dst, nr, colsT, rs, cs, flags,
                        d_o + 6 * a, g.stream);
     if (rc) return rc;
+    rc = pair_chunk(g, pp, d_o, a, nr);
+    if (rc) return rc;
   }
   return 0;
 }
@@ -975,15 +1028,29 @@ int commit_rows_locked(tb200_srs_t srs, const RowSource& src, unsigned flags, ui
           CU(cudaMemcpyAsync(d_h, h_vec + 24 * lo, (hi - lo) * 192, cudaMemcpyHostToDevice, g.copy_stream));
           CU(cudaEventRecord(g.ev_join, g.copy_stream));
         }
-        int r = batch_share_enqueue(g, srs, src, lo, hi, flags, &d_out[g.slot], to_free[g.slot]);
+        PairPipe pipe;
+        pipe.d_h = d_h;
+        pipe.h_ready = g.ev_join;
+        const bool pipelined = h_vec && E.commit_pipeline != 0;
+        int r = batch_share_enqueue(g, srs, src, lo, hi, flags, &d_out[g.slot], to_free[g.slot], pipelined ? &pipe : nullptr);
         if (r) return r;
         if (hi > lo)
           CU(cudaMemcpyAsync(out_xy + 12 * lo, d_out[g.slot], (hi - lo) * 96, cudaMemcpyDeviceToHost, g.stream));
         if (h_vec) {
-          // partial Miller product of this share (no final exponentiation), 576 B at d_result + 128
-          if (d_h) CU(cudaStreamWaitEvent(g.stream, g.ev_join, 0));
-          r = pairing_products(g, d_out[g.slot], d_h, (uint32_t)(hi - lo), 0, 1, g.d_result + Ctx::RES_PART, g.stream, nullptr, nullptr,
-                               nd == 1);
+          // this share's partial Miller product = the product of its chunks' partials (no final exponentiation unless
+          // this is the only GPU), 576 B at d_result + RES_PART
+          if (!pipelined) {  // all Miller loops of the share behind its row MSMs
+            if (d_h) CU(cudaStreamWaitEvent(g.stream, g.ev_join, 0));
+            r = pairing_products(g, d_out[g.slot], d_h, (uint32_t)(hi - lo), 0, 1, g.d_result + Ctx::RES_PART, g.stream, nullptr,
+                                 nullptr, nd == 1);
+          } else {
+            if (pipe.nparts) {
+              CU(cudaEventRecord(g.ev_pair2, g.pair_stream));
+              CU(cudaStreamWaitEvent(g.stream, g.ev_pair2, 0));
+            }
+            r = pairing_products(g, nullptr, nullptr, (uint32_t)pipe.nparts, 0, 1, g.d_result + Ctx::RES_PART, g.stream,
+                                 nullptr, pipe.d_parts, nd == 1);
+          }
           if (r) return r;
         }
         return 0;

@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "engine.h"
+#include "glv_host.h"
 #include "kernels_smem.cuh"
 
 using namespace tb;
@@ -323,10 +324,23 @@ int msm_host_enqueue(Ctx& g, const uint64_t* bases_xy, const uint64_t* scalars, 
     CU(cudaEventRecord(g.ev_points, g.copy_stream));
     return msm_dev(g, d_b, d_s, n, flags, g.d_result, g.stream, g.ev_points, nullptr, false);
   }
-  constexpr int C = 4;
-  const size_t unit = ((n + 7) / 8 + 31) & ~size_t(31);
-  const size_t cut[C + 1] = {0, std::min(n, unit), std::min(n, 3 * unit), std::min(n, 5 * unit), n};
-  Plan plans[C];
+  // Chunk sizes in sixteenths of the points. The first chunk is small (its upload is the only one the GPU waits for),
+  // the LAST chunks are small too: when several GPUs share the host link the call is upload-bound (8 GPUs of this box
+  // pull 23-35 GB/s each instead of 55, profiles/r02_h2d_probe_8gpu.txt) and everything after the last byte has
+  // arrived -- the last chunk's sort and accumulation -- is exposed. Below 2^23 points four chunks keep the number of
+  // pipeline passes (fix-up rounds, launch gaps) down.
+  static const int big[] = {1, 2, 4, 4, 3, 1, 1}, small[] = {2, 4, 4, 6};
+  const bool many = n >= (size_t(1) << 23);
+  const int C = many ? 7 : 4;
+  const int* frac = many ? big : small;
+  constexpr int CMAX = 7;
+  const size_t unit = ((n + 15) / 16 + 31) & ~size_t(31);
+  size_t cut[CMAX + 1] = {0};
+  for (int k = 0, acc = 0; k < C; k++) {
+    acc += frac[k];
+    cut[k + 1] = (k == C - 1) ? n : std::min(n, (size_t)acc * unit);
+  }
+  Plan plans[CMAX];
   size_t B = 0;
   for (int k = 0; k < C; k++) {
     int rc = make_plan(g, plans[k], 1, (uint32_t)(cut[k + 1] - cut[k]), 0, 1, c, 0, flags);
@@ -339,7 +353,7 @@ int msm_host_enqueue(Ctx& g, const uint64_t* bases_xy, const uint64_t* scalars, 
   CU(cudaMemsetAsync(d_buckets, 0, B * 192, g.stream));
   CU(cudaEventRecord(g.ev_points, g.stream));  // allocations exist
   CU(cudaStreamWaitEvent(g.copy_stream, g.ev_points, 0));
-  while (g.chunk_ev.size() < 2 * C) {
+  while (g.chunk_ev.size() < 2 * (size_t)C) {
     cudaEvent_t e;
     CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     g.chunk_ev.push_back(e);
@@ -563,7 +577,24 @@ int tb200_mipp_g1_begin(const uint64_t* a_xy, const uint64_t* y, size_t n, unsig
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->a, a_xy, n * 96, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->y, y, n * 32, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  if (e == cudaSuccess && n >= 2 && g1_fold_mult_bytes(n) <= FOLD_MULT_BYTES_MAX) {
+    // two-phase fold (kernels_pairing.cuh): the multiples of the first round's right half start right away
+    e = cudaMalloc((void**)&h->mult, g1_fold_mult_bytes(n));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->pre_st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fold, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->sel, 64 * glv::SEL_MAX * 2);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&h->sel_host, 64 * glv::SEL_MAX * 2);
+    if (e == cudaSuccess && g1_fold_pre(h->pre_st, h->a, (uint32_t)(n / 2), (uint32_t)(n / 2), h->mult)) e = cudaErrorUnknown;
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev_pre, h->pre_st);
+  }
   if (e != cudaSuccess) {
+    cudaFree(h->mult);
+    cudaFree(h->sel);
+    cudaFreeHost(h->sel_host);
+    if (h->pre_st) cudaStreamDestroy(h->pre_st);
+    if (h->ev_pre) cudaEventDestroy(h->ev_pre);
+    if (h->ev_fold) cudaEventDestroy(h->ev_fold);
     cudaFree(h->a);
     cudaFree(h->y);
     cudaFree(h->scal);
@@ -623,7 +654,23 @@ int tb200_mipp_g1_fold(tb200_mipp_t h, const uint64_t c[4], const uint64_t c_inv
   CU(cudaMemcpyAsync(ds, hs, 64, cudaMemcpyHostToDevice, g.stream));
   const int mont = (h->flags & TB200_SCALARS_MONT) ? 1 : 0;
   // a_l + c a_r over the G1 endomorphism (engine_pairing.cu): 127 doublings instead of 253
-  if (int rc = g1_fold_glv(g.stream, ds, mont, h->digits + 8 * h->round, h->a, split)) return rc;
+  if (h->mult) {
+    // the scalar is decomposed on the host (one value per round): the device gets the list of stored multiples to add
+    uint16_t* hsel = h->sel_host + (size_t)glv::SEL_MAX * h->round;
+    uint16_t* dsel = h->sel + (size_t)glv::SEL_MAX * h->round;
+    glv::select_g1(c, mont != 0, hsel);
+    CU(cudaMemcpyAsync(dsel, hsel, (size_t)(hsel[0] + 1) * 2, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaStreamWaitEvent(g.stream, h->ev_pre, 0));         // the multiples of this round's right half
+    if (int rc = g1_fold_apply(g.stream, dsel, h->a, split, h->mult)) return rc;
+    if (split >= 2) {                                        // phase A of the next round, off the critical path
+      CU(cudaEventRecord(h->ev_fold, g.stream));
+      CU(cudaStreamWaitEvent(h->pre_st, h->ev_fold, 0));
+      if (int rc = g1_fold_pre(h->pre_st, h->a, split / 2, split / 2, h->mult)) return rc;
+      CU(cudaEventRecord(h->ev_pre, h->pre_st));
+    }
+  } else if (int rc = g1_fold_glv(g.stream, ds, mont, h->digits + 8 * h->round, h->a, split)) {
+    return rc;
+  }
   if (int rc = fr_fold(g.stream, h->y, split, ds + 8, mont)) return rc;
   h->round++;
   h->n = split;
@@ -648,6 +695,15 @@ int tb200_mipp_g1_end(tb200_mipp_t h) {
     Ctx& g = primary();
     cudaSetDevice(g.device);
     cudaStreamSynchronize(g.stream);
+    if (h->pre_st) {
+      cudaStreamSynchronize(h->pre_st);
+      cudaStreamDestroy(h->pre_st);
+      cudaEventDestroy(h->ev_pre);
+      cudaEventDestroy(h->ev_fold);
+    }
+    cudaFree(h->mult);
+    cudaFree(h->sel);
+    cudaFreeHost(h->sel_host);
     cudaFree(h->a);
     cudaFree(h->y);
     cudaFree(h->scal);

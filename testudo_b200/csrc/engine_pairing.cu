@@ -6,6 +6,7 @@
 #include <algorithm>
 
 #include "engine.h"
+#include "glv_host.h"
 #include "kernels_pairing.cuh"
 
 using namespace tb;
@@ -17,6 +18,18 @@ int g2_finalize_single_glv(cudaStream_t st, const uint4* group_w, int W, int c, 
   return 0;
 }
 
+int g1_fold_pre(cudaStream_t st, const uint4* a, uint32_t first, uint32_t count, uint4* mult) {
+  LAUNCH(k_fold_pre_g1, cdiv(count, 128), 128, st, a, first, count, mult);
+  return 0;
+}
+// lanes per element of the two-phase folds: a warp per element while the vector is short (latency), 8 lanes when it is
+// long (four elements per warp: throughput)
+static inline int fold_lanes(uint32_t split) { return split >= 1024 ? 8 : 32; }
+int g1_fold_apply(cudaStream_t st, const uint16_t* d_sel, uint4* a, uint32_t split, const uint4* mult) {
+  if (fold_lanes(split) == 8) LAUNCH(k_fold_apply_g1<8>, cdiv((uint64_t)split * 8, 128), 128, st, a, split, d_sel, mult);
+  else LAUNCH(k_fold_apply_g1<32>, cdiv((uint64_t)split * 32, 128), 128, st, a, split, d_sel, mult);
+  return 0;
+}
 int g1_fold_glv(cudaStream_t st, const uint32_t* d_scaler, int mont, uint32_t* d_digits, uint4* a, uint32_t split) {
   LAUNCH(k_glv2_digits, 1, 32, st, d_scaler, mont, d_digits);
   LAUNCH(k_compress_g1_glv, cdiv(split, 128), 128, st, a, split, d_digits);
@@ -151,7 +164,28 @@ int tb200_mipp_g2_begin(const uint64_t* h_vec, size_t n, unsigned flags, tb200_m
   if (e == cudaSuccess) e = cudaMallocHost((void**)&m->scal_host, 64 * 32);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->h, h_vec, n * 192, cudaMemcpyHostToDevice, m_st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(m_st);  // h_vec is only borrowed for the duration of the call
+  if (e == cudaSuccess && n >= 2 && g2_fold_mult_bytes(n) <= FOLD_MULT_BYTES_MAX) {
+    // two-phase fold: the multiples of the first round's right half start right away, next to the first cross values
+    e = cudaMalloc((void**)&m->mult, g2_fold_mult_bytes(n));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->pre_st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_pre, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_fold, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&m->sel, 64 * glv::SEL_MAX * 2);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&m->sel_host, 64 * glv::SEL_MAX * 2);
+    if (e == cudaSuccess) {
+      k_fold_pre_g2<<<cdiv(n / 2, 64), 64, 0, m->pre_st>>>(m->h, (uint32_t)(n / 2), (uint32_t)(n / 2), m->mult);
+      g_launches++;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(m->ev_pre, m->pre_st);
+  }
   if (e != cudaSuccess) {
+    cudaFree(m->mult);
+    cudaFree(m->sel);
+    cudaFreeHost(m->sel_host);
+    if (m->pre_st) cudaStreamDestroy(m->pre_st);
+    if (m->ev_pre) cudaEventDestroy(m->ev_pre);
+    if (m->ev_fold) cudaEventDestroy(m->ev_fold);
     cudaFree(m->h);
     cudaFree(m->scal);
     cudaFree(m->digits);
@@ -174,12 +208,31 @@ int tb200_mipp_g2_fold(tb200_mipp_g2_t h, const uint64_t c_inv[4]) {
   CU(cudaSetDevice(primary().device));
   const uint32_t split = h->n / 2;
   cudaStream_t m_st = h->st;
-  memcpy(h->scal_host + 8 * h->round, c_inv, 32);
-  CU(cudaMemcpyAsync(h->scal + 8 * h->round, h->scal_host + 8 * h->round, 32, cudaMemcpyHostToDevice, m_st));
-  // 4-dimensional decomposition over the twisted Frobenius (kernels_pairing.cuh): 64 doublings instead of 253
-  LAUNCH(k_glv4_digits, 1, 32, m_st, h->scal + 8 * h->round, (h->flags & TB200_SCALARS_MONT) ? 1 : 0,
-         h->digits + 8 * h->round);
-  LAUNCH(k_compress_g2_glv4w, cdiv(split, 32), 128, m_st, h->h, split, h->digits + 8 * h->round);
+  if (h->mult) {
+    // the scalar is decomposed on the host (one value per round): the device gets the list of stored multiples to add
+    uint16_t* hs = h->sel_host + (size_t)glv::SEL_MAX * h->round;
+    uint16_t* ds = h->sel + (size_t)glv::SEL_MAX * h->round;
+    glv::select_g2(c_inv, (h->flags & TB200_SCALARS_MONT) != 0, hs);
+    CU(cudaMemcpyAsync(ds, hs, (size_t)(hs[0] + 1) * 2, cudaMemcpyHostToDevice, m_st));
+    CU(cudaStreamWaitEvent(m_st, h->ev_pre, 0));             // the multiples of this round's right half
+    if (fold_lanes(split) == 8)
+      LAUNCH(k_fold_apply_g2<8>, cdiv((uint64_t)split * 8, 64), 64, m_st, h->h, split, ds, h->mult);
+    else
+      LAUNCH(k_fold_apply_g2<32>, cdiv((uint64_t)split * 32, 64), 64, m_st, h->h, split, ds, h->mult);
+    if (split >= 2) {                                        // phase A of the next round, off the critical path
+      CU(cudaEventRecord(h->ev_fold, m_st));
+      CU(cudaStreamWaitEvent(h->pre_st, h->ev_fold, 0));
+      LAUNCH(k_fold_pre_g2, cdiv(split / 2, 64), 64, h->pre_st, h->h, split / 2, split / 2, h->mult);
+      CU(cudaEventRecord(h->ev_pre, h->pre_st));
+    }
+  } else {
+    memcpy(h->scal_host + 8 * h->round, c_inv, 32);
+    CU(cudaMemcpyAsync(h->scal + 8 * h->round, h->scal_host + 8 * h->round, 32, cudaMemcpyHostToDevice, m_st));
+    // 4-dimensional decomposition over the twisted Frobenius (kernels_pairing.cuh): 64 doublings instead of 253
+    LAUNCH(k_glv4_digits, 1, 32, m_st, h->scal + 8 * h->round, (h->flags & TB200_SCALARS_MONT) ? 1 : 0,
+           h->digits + 8 * h->round);
+    LAUNCH(k_compress_g2_glv4w, cdiv(split, 32), 128, m_st, h->h, split, h->digits + 8 * h->round);
+  }
   h->round++;
   h->n = split;
   return 0;
@@ -201,6 +254,15 @@ int tb200_mipp_g2_end(tb200_mipp_g2_t h) {
   if (E.ready) {
     cudaSetDevice(primary().device);
     cudaStreamSynchronize(h->st);
+    if (h->pre_st) {
+      cudaStreamSynchronize(h->pre_st);
+      cudaStreamDestroy(h->pre_st);
+      cudaEventDestroy(h->ev_pre);
+      cudaEventDestroy(h->ev_fold);
+    }
+    cudaFree(h->mult);
+    cudaFree(h->sel);
+    cudaFreeHost(h->sel_host);
     cudaFree(h->h);
     cudaFree(h->scal);
     cudaFree(h->digits);

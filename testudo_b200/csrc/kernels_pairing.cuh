@@ -932,6 +932,152 @@ __global__ void __launch_bounds__(128) k_compress_g1_glv(uint4* __restrict__ a, 
   store_affine(a + 6 * (uint64_t)i, o);
 }
 
+// ---- two-phase folds: the doubling chain leaves the critical path of a MIPP round ----------------------------------------
+// A round is   cross values (MSMs, Miller loops, final exponentiations) -> challenge c -> fold -> next round,   and the
+// fold used to be a 127-step (G1) / 64-step (G2) doubling chain per element that starts only once c is known: 3.6-4.3 ms
+// of a 7 ms round. The multiples 2^j * a_r[i] do NOT depend on c: phase A computes them on a side stream while the
+// round's Miller loops run (those are latency-bound and leave the SMs mostly idle); phase B -- after c is known -- adds
+// the multiples c selects. c is ONE scalar for the whole vector, so the selection is the same for every element: the
+// host decomposes c over the endomorphism (glv_host.h) into a list of (bit position j, endomorphism power d) pairs,
+// T lanes share an element and split the list evenly (no lane is predicated off), a shuffle tree combines their partial
+// sums, lane 0 adds a_l[i] and normalises. T = 32 for the short vectors of the late rounds (latency: ~4 + 5 additions),
+// T = 8 for long ones (throughput: 4 elements per warp). The endomorphisms are applied on the fly:
+// phi(X, Y, ZZ, ZZZ) = (beta X, Y, ZZ, ZZZ), psi as xyzz2_psi. Precondition as for the one-phase kernels: the points lie
+// in the order-r subgroups.
+constexpr int FOLD_G1_STEPS = 127;   // k0, k1 < 2^127
+constexpr int FOLD_G2_STEPS = 64;    // base-x digits < 2^64
+
+// phase A, G1: mult[i * 127 + j] = 2^j * a[first + i] as lazily reduced XYZZ (identity stays the identity)
+__global__ void __launch_bounds__(128) k_fold_pre_g1(const uint4* __restrict__ a, uint32_t first, uint32_t count,
+                                                     uint4* __restrict__ mult) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Affine r;
+  load_affine(r, a + 6 * ((uint64_t)first + i));
+  Xyzz t;
+  xyzz_set_inf(t);
+  xyzz_madd_fast_ni(&t, &r);
+  uint4* dst = mult + (uint64_t)i * FOLD_G1_STEPS * 12;
+  for (int j = 0; j < FOLD_G1_STEPS; j++) {
+    store_xyzz(dst + 12 * j, t);
+    if (j + 1 < FOLD_G1_STEPS) xyzz_dbl_fast_ni(&t);
+  }
+}
+
+template <int T>
+__device__ __forceinline__ void xyzz_shfl_down(Xyzz& o, const Xyzz& p, int off) {
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int i = 0; i < 48; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], off, T);
+}
+
+// phase B, G1: a[i] <- a[i] + (k0 + k1 lambda) * a[split + i] from the stored multiples; T lanes per element.
+// sel[0] = number of entries, sel[1..] = j | (d << 8). Launched with ceil(split T / 128) CTAs of 128 threads.
+template <int T>
+__global__ void __launch_bounds__(128) k_fold_apply_g1(uint4* __restrict__ a, uint32_t split,
+                                                       const uint16_t* __restrict__ sel,
+                                                       const uint4* __restrict__ mult) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t e = tid / T;
+  const int lane = tid % T;
+  const bool live = e < split;             // dead lane groups only take part in the shuffles
+  const int count = sel[0];
+  const Fq beta = fq_from_table(FQ12_C(G1_BETA));
+  Xyzz acc;
+  xyzz_set_inf(acc);
+  if (live) {
+    const uint4* src = mult + (uint64_t)e * FOLD_G1_STEPS * 12;
+    for (int idx = lane; idx < count; idx += T) {
+      const uint32_t ent = sel[1 + idx];
+      Xyzz t;
+      load_xyzz(t, src + 12 * (ent & 255u));
+      if (ent >> 8) t.x = fq_mul_call(t.x, beta);   // phi: X < 2q, inside the lazy invariant
+      xyzz_add_fast_ni(&acc, &t);
+    }
+  }
+#pragma unroll
+  for (int off = T / 2; off >= 1; off >>= 1) {
+    Xyzz o;
+    xyzz_shfl_down<T>(o, acc, off);
+    if (lane < off) xyzz_add_fast_ni(&acc, &o);
+  }
+  if (lane != 0 || !live) return;
+  Affine l, out;
+  load_affine(l, a + 6 * (uint64_t)e);
+  xyzz_madd_fast_ni(&acc, &l);
+  xyzz_canon(acc);
+  xyzz_to_affine_ni(&out, &acc);
+  store_affine(a + 6 * (uint64_t)e, out);
+}
+
+// phase A, G2: mult[i * 64 + j] = 2^j * h[first + i] as (canonical) XYZZ over Fq2
+__global__ void __launch_bounds__(64) k_fold_pre_g2(const uint4* __restrict__ h, uint32_t first, uint32_t count,
+                                                    uint4* __restrict__ mult) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Affine2 r;
+  load_affine2(r, h + 12 * ((uint64_t)first + i));
+  Xyzz2 t;
+  xyzz2_set_inf(t);
+  xyzz2_madd_ni(&t, &r);
+  uint4* dst = mult + (uint64_t)i * FOLD_G2_STEPS * 24;
+  for (int j = 0; j < FOLD_G2_STEPS; j++) {
+    store_xyzz2(dst + 24 * j, t);
+    if (j + 1 < FOLD_G2_STEPS) xyzz2_dbl_ni(&t);
+  }
+}
+
+template <int T>
+__device__ __forceinline__ void xyzz2_shfl_down(Xyzz2& o, const Xyzz2& p, int off) {
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&p);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll 8
+  for (int i = 0; i < 96; i++) d[i] = __shfl_down_sync(0xffffffffu, s[i], off, T);
+}
+static __device__ __noinline__ void xyzz2_psi_ni(Xyzz2* p) {
+  Xyzz2 r;
+  xyzz2_psi(r, *p);
+  *p = r;
+}
+
+// phase B, G2: h[i] <- h[i] + (k0 + k1 x + k2 x^2 + k3 x^3) * h[split + i]; T lanes per element, list as for G1 with
+// d = the power of psi. Launched with ceil(split T / 64) CTAs of 64 threads.
+template <int T>
+__global__ void __launch_bounds__(64) k_fold_apply_g2(uint4* __restrict__ h, uint32_t split,
+                                                      const uint16_t* __restrict__ sel,
+                                                      const uint4* __restrict__ mult) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t e = tid / T;
+  const int lane = tid % T;
+  const bool live = e < split;
+  const int count = sel[0];
+  Xyzz2 acc;
+  xyzz2_set_inf(acc);
+  if (live) {
+    const uint4* src = mult + (uint64_t)e * FOLD_G2_STEPS * 24;
+    for (int idx = lane; idx < count; idx += T) {
+      const uint32_t ent = sel[1 + idx];
+      Xyzz2 t;
+      load_xyzz2(t, src + 24 * (ent & 255u));
+      for (uint32_t d = 0; d < (ent >> 8); d++) xyzz2_psi_ni(&t);
+      xyzz2_add_ni(&acc, &t);
+    }
+  }
+#pragma unroll 1
+  for (int off = T / 2; off >= 1; off >>= 1) {
+    Xyzz2 o;
+    xyzz2_shfl_down<T>(o, acc, off);
+    if (lane < off) xyzz2_add_ni(&acc, &o);
+  }
+  if (lane != 0 || !live) return;
+  Affine2 l, out;
+  load_affine2(l, h + 12 * (uint64_t)e);
+  xyzz2_madd_ni(&acc, &l);
+  xyzz2_to_affine_ni(&out, &acc);
+  store_affine2(h + 12 * (uint64_t)e, out);
+}
+
 // test hook: one Fq12 operation per thread (tests/test_gpu_pairing.py drives every op against the oracle)
 //   0 mul(a,b)  1 sqr(a)  2 inv(a)  3 frobenius(a,1)  4 frobenius(a,2)  5 cyclotomic_sqr(a)  6 exp_by_x(a)
 //   7 final_exp(a)  8 mul_by_034(a; b = l0 || l3 || l4)  9 miller(a = G1 affine || G2 affine)
