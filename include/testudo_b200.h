@@ -285,6 +285,25 @@ int tb200_mipp_cross_all(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_u_l[12
 void tb200_set_pairing_coop_max(int n);
 int tb200_gt_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned flags, uint64_t* out);
 
+/* ---- Poseidon sponge of the Fiat-Shamir transcript (HOST code, as in the reference) ----------------
+ * Restates ark-crypto-primitives 0.4 `PoseidonSponge<F>` behind `PoseidonTranscript<F>` (src/poseidon_transcript.rs:12-125).
+ * field: 0 = BLS12-377 Fr (benches/pst.rs:23,57), 1 = BLS12-377 Fq (`PoseidonTranscript<E::BaseField>`, src/mipp.rs:32,
+ * src/sqrt_pst.rs:170,325). ark / mds: (full + partial) x (rate + capacity) round constants and the square MDS matrix,
+ * canonical little-endian limbs of `field` (4 or 6 u64 each), row-major -- `PoseidonConfig::new(full, partial, alpha, mds,
+ * ark, rate, capacity)`, src/parameters.rs:156-185. absorb_bytes = `sponge.absorb(&Vec<u8>)` (what `append` does with the
+ * uncompressed serialisation, :21-27), absorb_native = `absorb(&F)`, squeeze_fr = `challenge_scalar::<Fr>` (:29-31; the
+ * foreign-field squeeze when the sponge is over Fq), canonical limbs. No CUDA involved; usable before tb200_init. */
+typedef struct tb200_poseidon* tb200_poseidon_t;
+int tb200_poseidon_new(int field, unsigned full_rounds, unsigned partial_rounds, uint64_t alpha, unsigned rate,
+                       unsigned capacity, const uint64_t* ark, const uint64_t* mds, tb200_poseidon_t* out);
+int tb200_poseidon_reset(tb200_poseidon_t h);
+int tb200_poseidon_absorb_bytes(tb200_poseidon_t h, const uint8_t* data, size_t len);
+int tb200_poseidon_absorb_native(tb200_poseidon_t h, const uint64_t* elems, size_t n);
+int tb200_poseidon_squeeze_native(tb200_poseidon_t h, uint64_t* out, size_t n);
+int tb200_poseidon_squeeze_fr(tb200_poseidon_t h, uint64_t out[4]);
+int tb200_poseidon_limbs(tb200_poseidon_t h);
+int tb200_poseidon_free(tb200_poseidon_t h);
+
 #ifdef __cplusplus
 }
 #endif

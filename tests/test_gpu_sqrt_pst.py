@@ -342,3 +342,49 @@ def test_commit_open_bit_exact_vs_oracle_prover(engine, nv):
     assert np.array_equal(mp.final_h, np.array(o2.affine_to_words(o_mipp["final_h"]), dtype=np.uint64))
     assert np.array_equal(mp.pst_proof_h, h.pts_to_np(o_mipp["pst_proof_h"]))
     ck.close()
+
+
+@pytest.mark.parametrize("nv", [5, 6])
+def test_roundtrip_with_the_poseidon_transcript(engine, nv):
+    """check_sqrt_poly_commit (src/sqrt_pst.rs:297-342) with the reference's OWN transcript on both sides: the prover
+    mirror draws its challenges from `PoseidonTranscript<Fq>` (C++ sponge, serialize.py encodings), the oracle verifier
+    from the independent Python sponge and its own encodings (oracle/poseidon.py). It only verifies if both sides
+    absorbed identical bytes and every prover value is right."""
+    from oracle import bls12_377_g2 as o2
+    from oracle import pairing as pr
+    from oracle import poseidon as op
+    from oracle import verifier as ver
+    from testudo_b200 import poseidon_transcript as pt
+
+    m_col = nv // 2
+    m_row = nv - m_col
+    t = o.rand_scalars(m_row, 2900 + nv)
+    g_levels = _crs_levels(engine, t, False)
+    h_levels = _crs_levels(engine, t, True)
+    vk = ver.setup_vk(t)
+    z = o.rand_scalars(1 << nv, 2910 + nv)
+    r = o.rand_scalars(nv, 2920 + nv)
+    poly = sqrt_pst.Polynomial.from_evaluations(h.scalars_to_np(z, mont=True))
+    v = poly.eval(r)
+    ck = sqrt_pst.CommitterKey.from_points(g_levels[0]).with_levels(g_levels, h_levels)
+    comm_list, t_gt = poly.commit(ck)
+    prover = pt.PoseidonTranscript("fq")
+    opened = poly.open(prover.as_challenge(), comm_list, ck, r, t_gt)
+    mp = opened.mipp
+    proof = {
+        "comms_u": [(h.pt_from_np(l), h.pt_from_np(rr)) for l, rr in mp.comms_u],
+        "comms_t": [(pr.from_words(l), pr.from_words(rr)) for l, rr in mp.comms_t],
+        "final_a": h.pt_from_np(mp.final_a),
+        "final_h": o2.affine_from_words(mp.final_h),
+        "pst_proof_h": [h.pt_from_np(p) for p in mp.pst_proof_h],
+    }
+    U = h.pt_from_np(opened.u)
+    pst_proof = [o2.affine_from_words(p) for p in opened.pst_proof]
+    T = pr.from_words(t_gt)
+    ark, mds = pt.reference_parameters()
+    assert ver.sqrt_pst_verify(vk, op.OracleTranscript(ark, mds).challenge, U, r, v, pst_proof, proof, T) is True
+    assert all(0 < c < o.R_ORDER for c in mp.xs_inv) and len(set(mp.xs_inv)) == len(mp.xs_inv)
+    bad = dict(proof)
+    bad["comms_u"] = [(proof["comms_u"][0][1], proof["comms_u"][0][0])] + proof["comms_u"][1:]
+    assert ver.sqrt_pst_verify(vk, op.OracleTranscript(ark, mds).challenge, U, r, v, pst_proof, bad, T) is False
+    ck.close()

@@ -108,6 +108,15 @@ SIGNATURES = {
     "tb200_test_g2_add": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "tb200_test_fq12_op": (c_int, [c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tb200_test_g2_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tb200_poseidon_new": (c_int, [c_int, c_uint, c_uint, ctypes.c_uint64, c_uint, c_uint, c_void_p, c_void_p,
+                                   ctypes.POINTER(c_void_p)]),
+    "tb200_poseidon_reset": (c_int, [c_void_p]),
+    "tb200_poseidon_absorb_bytes": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "tb200_poseidon_absorb_native": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "tb200_poseidon_squeeze_native": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "tb200_poseidon_squeeze_fr": (c_int, [c_void_p, c_void_p]),
+    "tb200_poseidon_limbs": (c_int, [c_void_p]),
+    "tb200_poseidon_free": (c_int, [c_void_p]),
 }
 
 

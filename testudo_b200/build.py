@@ -23,6 +23,7 @@ UNITS = {
     "engine_g1.cu": _FIELD + ["kernels_smem.cuh", "kernels_small.cuh"],
     "engine_g2.cu": _G2,
     "engine_pairing.cu": _G2 + ["fq12.cuh", "fq12_consts.inc", "kernels_pairing.cuh"],
+    "poseidon_host.cpp": [],   # host-only: the Fiat-Shamir sponge (CPU code in the reference too)
 }
 COMMON = ["engine.h", "glv_host.h", API_HEADER]
 NVCC_FLAGS = [
@@ -40,7 +41,7 @@ def nvcc() -> str:
 
 
 def _obj(unit: str) -> str:
-    return os.path.join(OBJ_DIR, unit.replace(".cu", ".o"))
+    return os.path.join(OBJ_DIR, os.path.splitext(unit)[0] + ".o")
 
 
 def _unit_stale(unit: str) -> bool:

@@ -1,0 +1,375 @@
+// Host-side Poseidon sponge for the Fiat-Shamir transcript of `Polynomial::open` / `MippProof::prove`
+// (src/poseidon_transcript.rs:12-125). The transcript is CPU code in the reference as well (a few
+// dozen permutations per MIPP round between GPU calls); it lives in the library so that a host in any language gets the
+// same challenges without re-implementing the sponge, and so that the Python mirror does not spend ~3 ms per round in
+// big-integer arithmetic. This is NOT a CPU path for the MSM engine: nothing here touches group arithmetic.
+//
+// Restates ark-crypto-primitives 0.4.0 `sponge::poseidon::PoseidonSponge` (dependency of the reference, Cargo.toml:28,
+// un-vendored) from its published source:
+//   * state = [capacity | rate] field elements, all zero; mode Absorbing{next_absorb_index = 0}
+//   * permute: R_F/2 full rounds, R_P partial rounds, R_F/2 full rounds; a round = add round constants, S-box x^alpha on
+//     every element (full) or on element 0 (partial), multiply by the MDS matrix (new[i] = sum_j state[j] mds[i][j])
+//   * absorb(elements): when squeezing, permute first and restart at rate index 0; when the absorb index reached the
+//     rate, permute first; then add elements into state[capacity + index ..], permuting whenever the rate is full
+//   * squeeze_native_field_elements(n): when absorbing, permute first; when the squeeze index reached the rate, permute
+//     first; then read state[capacity + index ..], permuting between full rates (not after the last read)
+//   * absorb(&Vec<u8>) = absorb(pack(le64(len) || bytes)) with (MODULUS_BIT_SIZE - 1) / 8 bytes per element, little endian
+//   * squeeze_field_elements::<F2>(1) for a foreign field F2 = squeeze_bits(F2::MODULUS_BIT_SIZE - 1): the low
+//     MODULUS_BIT_SIZE - 1 bits (little endian) of ceil(bits / usable) native elements, as an integer mod F2's modulus
+// PARITY UNPINNED against the arkworks binary except for the parameters, which reproduce the reference's
+// constants (tests/test_poseidon_transcript.py); ffi/kat/ prints known answers from a Rust run for tests/test_ark_kat.py.
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/testudo_b200.h"
+
+namespace {
+
+typedef unsigned __int128 u128;
+
+// Montgomery arithmetic over an odd modulus of N 64-bit limbs (N = 4: Fr, N = 6: Fq)
+template <int N>
+struct Field {
+  uint64_t p[N], r2[N], one[N], inv;  // inv = -p^-1 mod 2^64
+  static bool geq(const uint64_t* a, const uint64_t* b) {
+    for (int i = N - 1; i >= 0; i--)
+      if (a[i] != b[i]) return a[i] > b[i];
+    return true;
+  }
+  static uint64_t sub_n(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+    uint64_t borrow = 0;
+    for (int i = 0; i < N; i++) {
+      const u128 d = (u128)a[i] - b[i] - borrow;
+      r[i] = (uint64_t)d;
+      borrow = (uint64_t)(d >> 64) & 1;
+    }
+    return borrow;
+  }
+  void add(uint64_t* r, const uint64_t* a, const uint64_t* b) const {
+    uint64_t carry = 0;
+    for (int i = 0; i < N; i++) {
+      const u128 s = (u128)a[i] + b[i] + carry;
+      r[i] = (uint64_t)s;
+      carry = (uint64_t)(s >> 64);
+    }
+    if (carry || geq(r, p)) sub_n(r, r, p);
+  }
+  void mul(uint64_t* r, const uint64_t* a, const uint64_t* b) const {  // CIOS
+    uint64_t t[N + 2] = {0};
+    for (int i = 0; i < N; i++) {
+      uint64_t carry = 0;
+      for (int j = 0; j < N; j++) {
+        const u128 s = (u128)a[j] * b[i] + t[j] + carry;
+        t[j] = (uint64_t)s;
+        carry = (uint64_t)(s >> 64);
+      }
+      u128 s = (u128)t[N] + carry;
+      t[N] = (uint64_t)s;
+      t[N + 1] = (uint64_t)(s >> 64);
+      const uint64_t m = t[0] * inv;
+      s = (u128)m * p[0] + t[0];
+      carry = (uint64_t)(s >> 64);
+      for (int j = 1; j < N; j++) {
+        s = (u128)m * p[j] + t[j] + carry;
+        t[j - 1] = (uint64_t)s;
+        carry = (uint64_t)(s >> 64);
+      }
+      s = (u128)t[N] + carry;
+      t[N - 1] = (uint64_t)s;
+      t[N] = t[N + 1] + (uint64_t)(s >> 64);
+    }
+    if (t[N] || geq(t, p)) sub_n(t, t, p);
+    memcpy(r, t, N * 8);
+  }
+  void to_mont(uint64_t* r, const uint64_t* a) const { mul(r, a, r2); }
+  void from_mont(uint64_t* r, const uint64_t* a) const {
+    uint64_t o[N] = {1};
+    mul(r, a, o);
+  }
+  void init(const uint64_t* modulus) {
+    memcpy(p, modulus, N * 8);
+    uint64_t x = 1;  // Newton: x = p^-1 mod 2^64
+    for (int i = 0; i < 6; i++) x *= 2 - p[0] * x;
+    inv = (uint64_t)(0 - x);
+    // R mod p and R^2 mod p by repeated doubling of 1
+    uint64_t v[N] = {1};
+    for (int i = 0; i < 2 * 64 * N; i++) {
+      uint64_t carry = 0;
+      for (int j = 0; j < N; j++) {
+        const uint64_t nv = (v[j] << 1) | carry;
+        carry = v[j] >> 63;
+        v[j] = nv;
+      }
+      if (carry || geq(v, p)) sub_n(v, v, p);
+      if (i == 64 * N - 1) memcpy(one, v, N * 8);
+    }
+    memcpy(r2, v, N * 8);
+  }
+};
+
+const uint64_t FR_MOD[4] = {0x0a11800000000001ull, 0x59aa76fed0000001ull, 0x60b44d1e5c37b001ull, 0x12ab655e9a2ca556ull};
+const uint64_t FQ_MOD[6] = {0x8508c00000000001ull, 0x170b5d4430000000ull, 0x1ef3622fba094800ull,
+                            0x1a22d9f300f5138full, 0xc63b05c06ca1493bull, 0x01ae3a4617c510eaull};
+
+struct SpongeBase {
+  virtual ~SpongeBase() {}
+  virtual void reset() = 0;
+  virtual void absorb_bytes(const uint8_t* data, size_t len) = 0;
+  virtual int absorb_native(const uint64_t* canonical, size_t n) = 0;
+  virtual void squeeze_native(uint64_t* canonical, size_t n) = 0;
+  virtual void squeeze_fr(uint64_t out[4]) = 0;
+  virtual int limbs() const = 0;
+};
+
+template <int N>
+struct Sponge : SpongeBase {
+  Field<N> F;
+  unsigned full, partial, rate, cap, width, bits;  // bits = MODULUS_BIT_SIZE
+  uint64_t alpha;
+  std::vector<uint64_t> ark, mds, state;  // Montgomery form
+  bool absorbing = true;
+  unsigned index = 0;  // next_absorb_index / next_squeeze_index
+
+  int limbs() const override { return N; }
+  uint64_t* st(unsigned i) { return state.data() + (size_t)N * i; }
+  void reset() override {
+    std::fill(state.begin(), state.end(), 0);
+    absorbing = true;
+    index = 0;
+  }
+  void sbox(uint64_t* x) const {
+    uint64_t acc[N], base[N];
+    memcpy(base, x, N * 8);
+    memcpy(acc, F.one, N * 8);
+    for (uint64_t e = alpha; e; e >>= 1) {
+      if (e & 1) F.mul(acc, acc, base);
+      if (e >> 1) F.mul(base, base, base);
+    }
+    memcpy(x, acc, N * 8);
+  }
+  void permute() {
+    std::vector<uint64_t> nxt((size_t)N * width);
+    const unsigned half = full / 2;
+    for (unsigned r = 0; r < full + partial; r++) {
+      for (unsigned i = 0; i < width; i++) F.add(st(i), st(i), ark.data() + (size_t)N * (r * width + i));
+      const bool is_full = r < half || r >= half + partial;
+      if (is_full)
+        for (unsigned i = 0; i < width; i++) sbox(st(i));
+      else
+        sbox(st(0));
+      for (unsigned i = 0; i < width; i++) {
+        uint64_t acc[N] = {0}, t[N];
+        for (unsigned j = 0; j < width; j++) {
+          F.mul(t, st(j), mds.data() + (size_t)N * (i * width + j));
+          F.add(acc, acc, t);
+        }
+        memcpy(nxt.data() + (size_t)N * i, acc, N * 8);
+      }
+      state = nxt;
+    }
+  }
+  // `absorb` of a slice of native elements given in Montgomery form
+  void absorb_mont(const uint64_t* elems, size_t n) {
+    if (n == 0) return;
+    unsigned start;
+    if (absorbing) {
+      start = index;
+      if (start == rate) {
+        permute();
+        start = 0;
+      }
+    } else {
+      permute();
+      start = 0;
+    }
+    size_t done = 0;
+    for (;;) {
+      if (start + (n - done) <= rate) {
+        for (size_t i = 0; done + i < n; i++) F.add(st(cap + start + (unsigned)i), st(cap + start + (unsigned)i), elems + N * (done + i));
+        absorbing = true;
+        index = start + (unsigned)(n - done);
+        return;
+      }
+      const unsigned take = rate - start;
+      for (unsigned i = 0; i < take; i++) F.add(st(cap + start + i), st(cap + start + i), elems + N * (done + i));
+      permute();
+      done += take;
+      start = 0;
+    }
+  }
+  int absorb_native(const uint64_t* canonical, size_t n) override {
+    std::vector<uint64_t> m((size_t)N * n);
+    for (size_t i = 0; i < n; i++) {
+      if (Field<N>::geq(canonical + N * i, F.p)) return TB200_E_ARG;
+      F.to_mont(m.data() + N * i, canonical + N * i);
+    }
+    absorb_mont(m.data(), n);
+    return 0;
+  }
+  void absorb_bytes(const uint8_t* data, size_t len) override {
+    // Absorb for Vec<u8>: le64(len) || bytes, packed (MODULUS_BIT_SIZE - 1) / 8 bytes per element, little endian
+    std::vector<uint8_t> buf(8 + len);
+    const uint64_t l = (uint64_t)len;
+    for (int i = 0; i < 8; i++) buf[i] = (uint8_t)(l >> (8 * i));
+    if (len) memcpy(buf.data() + 8, data, len);
+    const size_t chunk = (bits - 1) / 8;
+    const size_t n = (buf.size() + chunk - 1) / chunk;
+    std::vector<uint64_t> m((size_t)N * n, 0);
+    for (size_t i = 0; i < n; i++) {
+      uint8_t tmp[N * 8] = {0};
+      const size_t take = std::min(chunk, buf.size() - i * chunk);
+      memcpy(tmp, buf.data() + i * chunk, take);
+      uint64_t v[N];
+      for (int k = 0; k < N; k++) {
+        v[k] = 0;
+        for (int b = 0; b < 8; b++) v[k] |= (uint64_t)tmp[8 * k + b] << (8 * b);
+      }
+      F.to_mont(m.data() + N * i, v);  // chunk < modulus: at most MODULUS_BIT_SIZE - 1 bits
+    }
+    absorb_mont(m.data(), n);
+  }
+  void squeeze_native(uint64_t* canonical, size_t n) override {
+    if (n == 0) return;
+    unsigned start;
+    if (absorbing) {
+      permute();
+      start = 0;
+    } else {
+      start = index;
+      if (start == rate) {
+        permute();
+        start = 0;
+      }
+    }
+    size_t done = 0;
+    for (;;) {
+      if (start + (n - done) <= rate) {
+        for (size_t i = 0; done + i < n; i++) F.from_mont(canonical + N * (done + i), st(cap + start + (unsigned)i));
+        absorbing = false;
+        index = start + (unsigned)(n - done);
+        return;
+      }
+      const unsigned take = rate - start;
+      for (unsigned i = 0; i < take; i++) F.from_mont(canonical + N * (done + i), st(cap + start + i));
+      // ark: "Unless we are done with squeezing in this call, permute" -- its test compares the length of the output
+      // slice BEFORE the elements just read are cut off (so a read that starts mid-rate with exactly `rate` elements left
+      // continues without a permutation); restated as it is
+      if (n - done != rate) permute();
+      done += take;
+      start = 0;
+    }
+  }
+  // challenge_scalar::<Fr>: native when the sponge is over Fr, else the foreign-field path through squeeze_bits
+  void squeeze_fr(uint64_t out[4]) override {
+    if (N == 4) {
+      squeeze_native(out, 1);
+      return;
+    }
+    const unsigned want = 253 - 1;                       // FieldElementSize::Full for Fr
+    const unsigned usable = bits - 1;
+    const unsigned cnt = (want + usable - 1) / usable;   // 1 for Fq
+    std::vector<uint64_t> e((size_t)N * cnt);
+    squeeze_native(e.data(), cnt);
+    uint64_t v[4] = {0, 0, 0, 0};                        // the low 252 bits of the first element: < 2^252 < r
+    for (unsigned b = 0; b < want; b++)
+      if ((e[b >> 6] >> (b & 63)) & 1) v[b >> 6] |= 1ull << (b & 63);
+    memcpy(out, v, 32);
+  }
+};
+
+template <int N>
+SpongeBase* make(const uint64_t* modulus, unsigned bits, unsigned full, unsigned partial, uint64_t alpha, unsigned rate,
+                 unsigned cap, const uint64_t* ark, const uint64_t* mds) {
+  Sponge<N>* s = new Sponge<N>();
+  s->F.init(modulus);
+  s->full = full;
+  s->partial = partial;
+  s->alpha = alpha;
+  s->rate = rate;
+  s->cap = cap;
+  s->width = rate + cap;
+  s->bits = bits;
+  const size_t na = (size_t)(full + partial) * s->width, nm = (size_t)s->width * s->width;
+  s->ark.resize(N * na);
+  s->mds.resize(N * nm);
+  for (size_t i = 0; i < na; i++) {
+    if (Field<N>::geq(ark + N * i, s->F.p)) {
+      delete s;
+      return nullptr;
+    }
+    s->F.to_mont(s->ark.data() + N * i, ark + N * i);
+  }
+  for (size_t i = 0; i < nm; i++) {
+    if (Field<N>::geq(mds + N * i, s->F.p)) {
+      delete s;
+      return nullptr;
+    }
+    s->F.to_mont(s->mds.data() + N * i, mds + N * i);
+  }
+  s->state.assign((size_t)N * s->width, 0);
+  return s;
+}
+
+}  // namespace
+
+struct tb200_poseidon {
+  SpongeBase* s = nullptr;
+  std::mutex mu;
+};
+
+extern "C" {
+
+int tb200_poseidon_new(int field, unsigned full_rounds, unsigned partial_rounds, uint64_t alpha, unsigned rate,
+                       unsigned capacity, const uint64_t* ark, const uint64_t* mds, tb200_poseidon_t* out) {
+  if (!out || !ark || !mds || rate == 0 || capacity == 0 || (full_rounds & 1) || alpha == 0 || rate + capacity > 16 ||
+      full_rounds + partial_rounds == 0 || full_rounds + partial_rounds > 4096)
+    return TB200_E_ARG;
+  SpongeBase* s = nullptr;
+  if (field == 0) s = make<4>(FR_MOD, 253, full_rounds, partial_rounds, alpha, rate, capacity, ark, mds);
+  else if (field == 1) s = make<6>(FQ_MOD, 377, full_rounds, partial_rounds, alpha, rate, capacity, ark, mds);
+  if (!s) return TB200_E_ARG;
+  tb200_poseidon* h = new tb200_poseidon();
+  h->s = s;
+  *out = h;
+  return 0;
+}
+int tb200_poseidon_reset(tb200_poseidon_t h) {
+  if (!h) return TB200_E_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->s->reset();
+  return 0;
+}
+int tb200_poseidon_absorb_bytes(tb200_poseidon_t h, const uint8_t* data, size_t len) {
+  if (!h || (len && !data)) return TB200_E_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->s->absorb_bytes(data, len);
+  return 0;
+}
+int tb200_poseidon_absorb_native(tb200_poseidon_t h, const uint64_t* elems, size_t n) {
+  if (!h || (n && !elems)) return TB200_E_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  return h->s->absorb_native(elems, n);
+}
+int tb200_poseidon_squeeze_native(tb200_poseidon_t h, uint64_t* out, size_t n) {
+  if (!h || (n && !out)) return TB200_E_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->s->squeeze_native(out, n);
+  return 0;
+}
+int tb200_poseidon_squeeze_fr(tb200_poseidon_t h, uint64_t out[4]) {
+  if (!h || !out) return TB200_E_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->s->squeeze_fr(out);
+  return 0;
+}
+int tb200_poseidon_limbs(tb200_poseidon_t h) { return h ? h->s->limbs() : 0; }
+int tb200_poseidon_free(tb200_poseidon_t h) {
+  if (!h) return TB200_E_ARG;
+  delete h->s;
+  delete h;
+  return 0;
+}
+
+}  // extern "C"
