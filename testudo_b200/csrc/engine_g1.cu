@@ -569,36 +569,37 @@ int tb200_mipp_g1_begin(const uint64_t* a_xy, const uint64_t* y, size_t n, unsig
   tb200_mipp* h = new tb200_mipp();
   h->n = (uint32_t)n;
   h->flags = flags;
-  cudaError_t e = cudaMalloc((void**)&h->a, n * 96);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&h->y, n * 32);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&h->scal, 64 * 64);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&h->digits, 64 * 32);
+  cudaError_t e = cudaMallocAsync((void**)&h->a, n * 96, g.stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&h->y, n * 32, g.stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&h->scal, 64 * 64, g.stream);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&h->digits, 64 * 32, g.stream);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&h->scal_host, 64 * 64);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->a, a_xy, n * 96, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h->y, y, n * 32, cudaMemcpyHostToDevice, g.stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
   if (e == cudaSuccess && n >= 2 && g1_fold_mult_bytes(n) <= FOLD_MULT_BYTES_MAX) {
     // two-phase fold (kernels_pairing.cuh): the multiples of the first round's right half start right away
-    e = cudaMalloc((void**)&h->mult, g1_fold_mult_bytes(n));
+    e = cudaMallocAsync((void**)&h->mult, g1_fold_mult_bytes(n), g.stream);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->pre_st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_pre, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fold, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&h->sel, 64 * glv::SEL_MAX * 2);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&h->sel, 64 * glv::SEL_MAX * 2, g.stream);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&h->sel_host, 64 * glv::SEL_MAX * 2);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);   // the stream-ordered allocations exist for every stream
     if (e == cudaSuccess && g1_fold_pre(h->pre_st, h->a, (uint32_t)(n / 2), (uint32_t)(n / 2), h->mult)) e = cudaErrorUnknown;
     if (e == cudaSuccess) e = cudaEventRecord(h->ev_pre, h->pre_st);
   }
   if (e != cudaSuccess) {
-    cudaFree(h->mult);
-    cudaFree(h->sel);
+    cudaFreeAsync(h->mult, g.stream);
+    cudaFreeAsync(h->sel, g.stream);
     cudaFreeHost(h->sel_host);
     if (h->pre_st) cudaStreamDestroy(h->pre_st);
     if (h->ev_pre) cudaEventDestroy(h->ev_pre);
     if (h->ev_fold) cudaEventDestroy(h->ev_fold);
-    cudaFree(h->a);
-    cudaFree(h->y);
-    cudaFree(h->scal);
-    cudaFree(h->digits);
+    cudaFreeAsync(h->a, g.stream);
+    cudaFreeAsync(h->y, g.stream);
+    cudaFreeAsync(h->scal, g.stream);
+    cudaFreeAsync(h->digits, g.stream);
     cudaFreeHost(h->scal_host);
     delete h;
     return fail((int)e, "MIPP upload failed: %s", cudaGetErrorString(e));
@@ -701,13 +702,13 @@ int tb200_mipp_g1_end(tb200_mipp_t h) {
       cudaEventDestroy(h->ev_pre);
       cudaEventDestroy(h->ev_fold);
     }
-    cudaFree(h->mult);
-    cudaFree(h->sel);
+    cudaFreeAsync(h->mult, g.stream);
+    cudaFreeAsync(h->sel, g.stream);
     cudaFreeHost(h->sel_host);
-    cudaFree(h->a);
-    cudaFree(h->y);
-    cudaFree(h->scal);
-    cudaFree(h->digits);
+    cudaFreeAsync(h->a, g.stream);
+    cudaFreeAsync(h->y, g.stream);
+    cudaFreeAsync(h->scal, g.stream);
+    cudaFreeAsync(h->digits, g.stream);
     cudaFreeHost(h->scal_host);
   }
   delete h;

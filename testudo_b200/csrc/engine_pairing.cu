@@ -158,20 +158,21 @@ int tb200_mipp_g2_begin(const uint64_t* h_vec, size_t n, unsigned flags, tb200_m
   m->flags = flags;
   cudaError_t e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
   cudaStream_t m_st = m->st;
-  if (e == cudaSuccess) e = cudaMalloc((void**)&m->h, n * 192);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&m->scal, 64 * 32);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&m->digits, 64 * 32);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&m->h, n * 192, m_st);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&m->scal, 64 * 32, m_st);
+  if (e == cudaSuccess) e = cudaMallocAsync((void**)&m->digits, 64 * 32, m_st);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&m->scal_host, 64 * 32);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->h, h_vec, n * 192, cudaMemcpyHostToDevice, m_st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(m_st);  // h_vec is only borrowed for the duration of the call
   if (e == cudaSuccess && n >= 2 && g2_fold_mult_bytes(n) <= FOLD_MULT_BYTES_MAX) {
     // two-phase fold: the multiples of the first round's right half start right away, next to the first cross values
-    e = cudaMalloc((void**)&m->mult, g2_fold_mult_bytes(n));
+    e = cudaMallocAsync((void**)&m->mult, g2_fold_mult_bytes(n), m_st);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->pre_st, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_pre, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_fold, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&m->sel, 64 * glv::SEL_MAX * 2);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&m->sel, 64 * glv::SEL_MAX * 2, m_st);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&m->sel_host, 64 * glv::SEL_MAX * 2);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(m_st);   // the stream-ordered allocations exist for every stream
     if (e == cudaSuccess) {
       k_fold_pre_g2<<<cdiv(n / 2, 64), 64, 0, m->pre_st>>>(m->h, (uint32_t)(n / 2), (uint32_t)(n / 2), m->mult);
       g_launches++;
@@ -180,15 +181,15 @@ int tb200_mipp_g2_begin(const uint64_t* h_vec, size_t n, unsigned flags, tb200_m
     if (e == cudaSuccess) e = cudaEventRecord(m->ev_pre, m->pre_st);
   }
   if (e != cudaSuccess) {
-    cudaFree(m->mult);
-    cudaFree(m->sel);
+    cudaFreeAsync(m->mult, m_st);
+    cudaFreeAsync(m->sel, m_st);
     cudaFreeHost(m->sel_host);
     if (m->pre_st) cudaStreamDestroy(m->pre_st);
     if (m->ev_pre) cudaEventDestroy(m->ev_pre);
     if (m->ev_fold) cudaEventDestroy(m->ev_fold);
-    cudaFree(m->h);
-    cudaFree(m->scal);
-    cudaFree(m->digits);
+    cudaFreeAsync(m->h, m_st);
+    cudaFreeAsync(m->scal, m_st);
+    cudaFreeAsync(m->digits, m_st);
     cudaFreeHost(m->scal_host);
     if (m->st) cudaStreamDestroy(m->st);
     delete m;
@@ -260,12 +261,12 @@ int tb200_mipp_g2_end(tb200_mipp_g2_t h) {
       cudaEventDestroy(h->ev_pre);
       cudaEventDestroy(h->ev_fold);
     }
-    cudaFree(h->mult);
-    cudaFree(h->sel);
+    cudaFreeAsync(h->mult, h->st);
+    cudaFreeAsync(h->sel, h->st);
     cudaFreeHost(h->sel_host);
-    cudaFree(h->h);
-    cudaFree(h->scal);
-    cudaFree(h->digits);
+    cudaFreeAsync(h->h, h->st);
+    cudaFreeAsync(h->scal, h->st);
+    cudaFreeAsync(h->digits, h->st);
     cudaFreeHost(h->scal_host);
     cudaStreamDestroy(h->st);
   }
