@@ -113,6 +113,15 @@ int tb200_pst_open_g1(const uint64_t* evals, size_t nv, const uint64_t* point, c
                       unsigned flags, uint64_t* proofs);
 int tb200_pst_open_g2(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
                       unsigned flags, uint64_t* proofs);
+/* The same in two halves: _begin uploads and ENQUEUES the whole opening (nv >= 1) on streams of its own and returns;
+ * _end waits, writes the proofs and releases the handle. `Polynomial::open` uses it to run the G2 opening of q
+ * (src/sqrt_pst.rs:218-225), which does not depend on the MIPP transcript, NEXT TO the MIPP rounds (src/sqrt_pst.rs:212). */
+typedef struct tb200_pst_open* tb200_pst_open_t;
+int tb200_pst_open_g1_begin(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                            unsigned flags, tb200_pst_open_t* out);
+int tb200_pst_open_g2_begin(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                            unsigned flags, tb200_pst_open_t* out);
+int tb200_pst_open_end(tb200_pst_open_t h, uint64_t* proofs);
 
 /* ---- shared-base (SRS) batched MSM -------------------------------------------------------------------
  * Replaces the row fan-out `self.polys.par_iter().map(|p| MultilinearPC::commit(ck, p))`
@@ -237,6 +246,10 @@ void tb200_set_shard_min(size_t units);
  * following chunk (one partial product per chunk); 0 (default) = all Miller loops behind the row stage. See DESIGN.md
  * (multi-GPU) for the measurements behind the default. */
 void tb200_set_commit_pipeline(int enabled);
+/* single G1 MSMs of up to `n` points (default and maximum 1024; 0 disables) skip the sort pipeline: Straus with radix-16
+ * signed digits, a quad of lanes per point, 8 points per one-warp CTA: `commit_scalar` (src/commitments.rs:70-77), the bullet rounds
+ * (src/nizk/bullet.rs:93-118), the last MIPP rounds (src/mipp.rs:77-85). Identical results. */
+void tb200_set_small_msm_max(int n);
 /* integer-pipe microbenchmark: runs `iters` dependent-chain iterations of wide MACs on every SM and returns the
  * achieved 32x32->64 multiply-accumulates per second in *out_macs_per_s (kind: 0 = IMAD.WIDE.U32 reg-reg,
  * 1 = IMAD (32-bit lo), 2 = full Fq Montgomery multiplications per second). */

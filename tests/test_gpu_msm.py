@@ -25,7 +25,7 @@ def test_msm_seeded_golden(engine, case):
     assert h.pt_from_np(msm.msm_unchecked(h.pts_to_np(pts), h.scalars_to_np(sc, mont=True))) == exp
 
 
-@pytest.mark.parametrize("mode", [1, 3, 5])
+@pytest.mark.parametrize("mode", [0, 3])
 @pytest.mark.parametrize("case", GOLD["explicit"] + GOLD["edge"], ids=lambda c: c.get("name", "explicit"))
 def test_msm_explicit_and_edge_golden(engine, case, mode):
     pts = [h.pt_unhex(p) for p in case["points"]]
@@ -49,7 +49,7 @@ def test_msm_empty_and_length_rules(engine):
     assert h.pt_from_np(msm.msm_bigint(B[:0], S[:0])) is None            # n == 0 -> identity
 
 
-@pytest.mark.parametrize("mode", [1, 3, 5])
+@pytest.mark.parametrize("mode", [0, 3])
 @pytest.mark.parametrize("c", [3, 5, 8, 11, 13, 16])
 def test_msm_every_window_width(engine, oracle_c, c, mode):
     engine.tb200_set_accumulate_mode(mode)
@@ -87,7 +87,7 @@ def test_msm_vs_c_oracle_and_dlog(engine, oracle_c, logn):
     assert h.pt_from_np(got) == o.mul(sum(s * (a + step * k) for k, s in enumerate(ints)) % o.R_ORDER, o.G)
 
 
-@pytest.mark.parametrize("mode", [1, 3, 5])
+@pytest.mark.parametrize("mode", [0, 3])
 def test_msm_skewed_scalars_heavy_buckets(engine, oracle_c, mode):
     engine.tb200_set_accumulate_mode(mode)
     try:
@@ -125,31 +125,11 @@ def test_msm_linearity_property(engine, oracle_c):
     assert h.pt_from_np(r3) == o.mul(sum((x + y) * (7 + 11 * k) for k, (x, y) in enumerate(zip(i1, i2))) % o.R_ORDER, o.G)
 
 
-# ---- batched-affine accumulation (mode 2) must give the same points as the XYZZ path and the oracles --------------
-@pytest.fixture
-def affine_mode(engine):
-    engine.tb200_set_accumulate_mode(2)
-    yield engine
-    engine.tb200_set_accumulate_mode(0)
-
-
-@pytest.mark.parametrize("case", GOLD["explicit"] + GOLD["edge"], ids=lambda c: c.get("name", "explicit"))
-def test_affine_mode_edge_golden(affine_mode, case):
-    pts = [h.pt_unhex(p) for p in case["points"]]
-    sc = [int(s, 16) for s in case["scalars"]]
-    assert h.pt_from_np(msm.msm_bigint(h.pts_to_np(pts), h.scalars_to_np(sc))) == h.pt_unhex(case["result"])
-
-
-@pytest.mark.parametrize("case", GOLD["seeded"], ids=lambda c: f"n{c['n']}")
-def test_affine_mode_seeded_golden(affine_mode, case):
-    pts, _ = o.rand_points(case["n"], case["points_seed"])
-    sc = o.rand_scalars(case["n"], case["scalars_seed"])
-    assert h.pt_from_np(msm.msm_bigint(h.pts_to_np(pts), h.scalars_to_np(sc))) == h.pt_unhex(case["result"])
-
-
+# ---- heavy / degenerate bucket contents through both accumulate variants (0 / 4: fused Y3, 3: plain CIOS products) ----------
+@pytest.mark.parametrize("mode", [0, 3])
 @pytest.mark.parametrize("c", [3, 6, 11, 16])
-def test_affine_mode_skewed_duplicates_identities(affine_mode, oracle_c, c):
-    """Heavy buckets, repeated bases (P + P inside a round), P + (-P), identity bases, zero scalars."""
+def test_skewed_duplicates_identities(engine, oracle_c, c, mode):
+    """Heavy buckets, repeated bases (P + P inside a segment), P + (-P), identity bases, zero scalars."""
     n = 1 << 14
     bases = oracle_c.gen_points(h.pts_to_np([o.mul(99, o.G)])[0], h.pts_to_np([o.mul(31337, o.G)])[0], n)
     bases[1000:1200] = bases[1000]
@@ -161,25 +141,66 @@ def test_affine_mode_skewed_duplicates_identities(affine_mode, oracle_c, c):
     sc[kind == 2] = np.array([1, 0, 0, 0], dtype=np.uint64)
     sc[1000:1200] = np.array([7, 0, 0, 0], dtype=np.uint64)
     sc[3000:3100:2] = np.array([7, 0, 0, 0], dtype=np.uint64)
-    affine_mode.tb200_set_window_bits(c)
+    engine.tb200_set_window_bits(c)
+    engine.tb200_set_accumulate_mode(mode)
     try:
         got = msm.msm_bigint(bases, sc)
     finally:
-        affine_mode.tb200_set_window_bits(0)
+        engine.tb200_set_window_bits(0)
+        engine.tb200_set_accumulate_mode(0)
     assert np.array_equal(got, oracle_c.msm_g1(bases, sc))
 
 
-def test_affine_mode_equals_xyzz_mode_large(engine, oracle_c):
+def test_accumulate_variants_agree_large(engine, oracle_c):
     n = 1 << 18
     bases = oracle_c.gen_points(h.pts_to_np([o.mul(3, o.G)])[0], h.pts_to_np([o.mul(5, o.G)])[0], n)
     sc = h.np_rand_scalars(n, 77)
-    engine.tb200_set_accumulate_mode(1)
     a = msm.msm_bigint(bases, sc)
-    engine.tb200_set_accumulate_mode(2)
-    b = msm.msm_bigint(bases, sc)
     engine.tb200_set_accumulate_mode(3)
-    c3 = msm.msm_bigint(bases, sc)
-    engine.tb200_set_accumulate_mode(0)
-    assert np.array_equal(a, b) and np.array_equal(a, c3)
+    try:
+        c3 = msm.msm_bigint(bases, sc)
+    finally:
+        engine.tb200_set_accumulate_mode(0)
+    assert np.array_equal(a, c3)
     ints = h.np_scalars_to_ints(sc)
     assert h.pt_from_np(a) == o.mul(sum(s * (3 + 5 * k) for k, s in enumerate(ints)) % o.R_ORDER, o.G)
+
+
+# ---- small-n fast path (kernels_small.cuh: one CTA, a quad of lanes per point) -----------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 8, 9, 31, 33, 63, 64, 65, 257, 1000, 1024])
+def test_small_path_vs_oracle_and_pipeline(engine, oracle_c, n):
+    """n <= 1024 takes the Straus path (8 points per one-warp CTA); tb200_set_small_msm_max(0) sends the same inputs through the sort pipeline: same
+    points, both equal to the C oracle. Montgomery and canonical scalars."""
+    bases = oracle_c.gen_points(h.pts_to_np([o.mul(1000 + n, o.G)])[0], h.pts_to_np([o.mul(77, o.G)])[0], n)
+    sc = h.np_rand_scalars(n, 900 + n)
+    want = oracle_c.msm_g1(bases, sc)
+    assert np.array_equal(msm.msm_bigint(bases, sc), want)
+    ints = h.np_scalars_to_ints(sc)
+    assert np.array_equal(msm.msm_unchecked(bases, h.scalars_to_np(ints, mont=True)), want)
+    engine.tb200_set_small_msm_max(0)
+    try:
+        assert np.array_equal(msm.msm_bigint(bases, sc), want)
+    finally:
+        engine.tb200_set_small_msm_max(-1)
+
+
+def test_small_path_exceptional_cases(engine, oracle_c):
+    """Identity bases, zero scalars, r - 1, 2^252, the same point many times (partial sums that coincide: the tree's
+    doubling branch), P and -P with equal scalars (sum = identity), scalars whose radix-16 digits are all +-8 / 0."""
+    r = o.R_ORDER
+    P1, P2 = o.mul(5, o.G), o.mul(11, o.G)
+    cases = [
+        ([P1, P1], [7, 7]),
+        ([P1, o.neg(P1)], [9, 9]),
+        ([P1, o.neg(P1), P2], [9, 9, 3]),
+        ([None, P1, None], [5, 6, 7]),
+        ([P1, P2], [0, 0]),
+        ([P1, P2, P1], [r - 1, 1 << 252, r - 2]),
+        ([P1] * 64, [3] * 64),
+        ([P1] * 5, [0x8888888888888888, 0x0808080808080808, 8, 0x80, (1 << 252) + 0x88]),
+        ([o.G], [1]),
+        ([P2], [r - 1]),
+    ]
+    for pts, sc in cases:
+        got = msm.msm_bigint(h.pts_to_np(pts), h.scalars_to_np(sc))
+        assert h.pt_from_np(got) == o.msm_naive(pts, sc), (pts, sc)

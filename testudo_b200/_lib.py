@@ -80,6 +80,9 @@ SIGNATURES = {
     "tb200_gt_pow": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
     "tb200_pst_open_g1": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_uint, c_void_p]),
     "tb200_pst_open_g2": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_uint, c_void_p]),
+    "tb200_pst_open_g1_begin": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_uint, ctypes.POINTER(c_void_p)]),
+    "tb200_pst_open_g2_begin": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_uint, ctypes.POINTER(c_void_p)]),
+    "tb200_pst_open_end": (c_int, [c_void_p, c_void_p]),
     "tb200_dev_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
     "tb200_dev_free": (c_int, [c_void_p]),
     "tb200_dev_upload": (c_int, [c_void_p, c_void_p, c_size_t]),
@@ -100,6 +103,7 @@ SIGNATURES = {
     "tb200_set_pass_entries_max": (None, [ctypes.c_uint64]),
     "tb200_set_shard_min": (None, [c_size_t]),
     "tb200_set_commit_pipeline": (None, [c_int]),
+    "tb200_set_small_msm_max": (None, [c_int]),
     "tb200_int_pipe_peak": (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_double)]),
     "tb200_test_fq_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "tb200_test_fq_addsub": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),

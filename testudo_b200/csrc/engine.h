@@ -133,6 +133,7 @@ struct Engine {
   size_t host_chunk_min = size_t(1) << 21;  // host-facing single MSMs: chunked upload/compute overlap from here
   size_t shard_min = size_t(1) << 18;       // host-facing single MSMs are sharded over the GPUs from ndev * this
   int pairing_coop_max = 2048;              // Miller loops: CTA-per-pair up to this many pairs, lanes-per-pair above
+  int small_msm_max = 1024;                  // single G1 MSMs of up to this many points run in one CTA (kernels_small.cuh)
   int commit_pipeline = 0;                  // tb200_sqrt_pst_commit: Miller loops of a row chunk next to the next chunk's MSMs
   int acc_mode = 0;                         // 0 / 4: fused-Y3 XYZZ segments (default); 3: plain CIOS products
   uint64_t pass_entries_max = (1ull << 32) - 1024;  // sorted entries one pipeline pass can index (tests lower it)

@@ -498,6 +498,7 @@ void tb200_set_pass_entries_max(uint64_t entries) {
 }
 void tb200_set_shard_min(size_t units) { E.shard_min = units ? units : (size_t(1) << 18); }
 void tb200_set_commit_pipeline(int enabled) { E.commit_pipeline = enabled ? 1 : 0; }
+void tb200_set_small_msm_max(int n) { E.small_msm_max = n < 0 ? 1024 : std::min(n, 1024); }
 
 // ---- device / pinned host buffers for hosts without a CUDA runtime of their own ------------------------------------------
 int tb200_dev_alloc(size_t bytes, void** out) {

@@ -7,6 +7,7 @@
 #include "engine.h"
 #include "glv_host.h"
 #include "kernels_smem.cuh"
+#include "kernels_small.cuh"
 
 using namespace tb;
 
@@ -257,6 +258,27 @@ int msm_dev(Ctx& g, const void* d_bases, const void* d_scalars, size_t n, unsign
   if (((uintptr_t)d_bases | (uintptr_t)d_scalars | (uintptr_t)d_out) & 15)
     return fail(TB200_E_ARG, "device pointers must be 16-byte aligned");
   g.marks.clear();
+  if (!g2 && n >= 1 && n <= (size_t)E.small_msm_max && !E.forced_c) {   // a forced window width means: the pipeline
+    // small-n fast path (kernels_small.cuh): a quad of lanes per point, 8 points per one-warp CTA, no sort pipeline
+    const uint32_t nblk = cdiv(n, SMALL_QUADS);
+    uint4* scratch = nullptr;
+    if (nblk > 1) {
+      CU(cudaMallocAsync((void**)&scratch, ((size_t)nblk * 12 + 1) * 16, st));
+      CU(cudaMemsetAsync(scratch + (size_t)nblk * 12, 0, 16, st));
+    }
+    if (points_ready) CU(cudaStreamWaitEvent(st, points_ready, 0));
+    if (mark(g, st, "begin")) return 1;
+    LAUNCH(k_msm_small, nblk, 4 * SMALL_QUADS, st, (const uint4*)d_bases, (const uint32_t*)d_scalars, (uint32_t)n,
+           (flags & TB200_SCALARS_MONT) ? 1 : 0, scratch, (uint4*)d_out);
+    if (scratch) CU(cudaFreeAsync(scratch, st));
+    if (mark(g, st, "accumulate")) return 1;
+    g.last_c = 4;
+    g.last_W = SMALL_DIGITS;
+    g.last_K = 0;
+    g.last_entries = n * SMALL_DIGITS;
+    g.last_buckets = 0;
+    return finish ? finish_marks(g, st) : 0;
+  }
   Arena& arena = arena_p ? *arena_p : g.arena;
   const int c = pick_c_single(std::max<size_t>(n, 1));
   const uint64_t W = (uint64_t)num_windows(c);
@@ -470,79 +492,164 @@ int tb200_msm_g1_batch_dev(tb200_srs_t srs, const void* d_scalars, size_t rows, 
 }
 
 // ---- MultilinearPC::open (G2 proofs) / open_g1 (G1 proofs): quotient loop on the device, one MSM per variable ---------
-static int pst_open_locked(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
-                           unsigned flags, uint64_t* proofs, bool g2) {
-  if (!evals || !point || !level_bases || !proofs) return fail(TB200_E_ARG, "null pointer");
-  if (nv == 0) return 0;
-  if (nv > 28) return fail(TB200_E_LIMIT, "nv = %zu: at most 2^28 evaluations", nv);
+}  // extern "C"
+
+// One PST opening in flight: everything is ENQUEUED by pst_open_enqueue (uploads and the quotient loop on the job's own
+// stream, the per-variable MSMs on the context's side streams), pst_open_finish waits and downloads the proofs. The
+// blocking entry points run the two back to back; tb200_pst_open_g2_begin / _end expose them separately so that the G2
+// opening of q (src/sqrt_pst.rs:225), which does not depend on the MIPP transcript, runs NEXT TO the MIPP rounds.
+struct tb200_pst_open {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev = nullptr;
+  uint32_t *d_r0 = nullptr, *d_r1 = nullptr, *d_q = nullptr, *d_p = nullptr;
+  uint4 *d_bases = nullptr, *d_proofs = nullptr;
+  size_t nv = 0, pt = 0;
+};
+
+namespace {
+void pst_open_release(tb200_pst_open* j) {
+  if (!j) return;
+  if (j->st) {
+    for (void* p : {(void*)j->d_r0, (void*)j->d_r1, (void*)j->d_q, (void*)j->d_p, (void*)j->d_bases, (void*)j->d_proofs})
+      if (p) cudaFreeAsync(p, j->st);
+    cudaStreamDestroy(j->st);
+  }
+  if (j->ev) cudaEventDestroy(j->ev);
+  delete j;
+}
+
+int pst_open_enqueue(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                     unsigned flags, bool g2, tb200_pst_open** out) {
+  if (!evals || !point || !level_bases || !out) return fail(TB200_E_ARG, "null pointer");
+  if (nv == 0 || nv > 28) return fail(nv ? TB200_E_LIMIT : TB200_E_ARG, "nv = %zu: between 1 and 28 variables", nv);
   for (size_t i = 0; i < nv; i++)
     if (!level_bases[i]) return fail(TB200_E_ARG, "level_bases[%zu] is null", i);
   Ctx& g = primary();
   const size_t n = size_t(1) << nv, pt = g2 ? 192 : 96;
-  uint32_t *d_r0 = nullptr, *d_r1 = nullptr, *d_q = nullptr, *d_p = nullptr;
-  uint4 *d_bases = nullptr, *d_proofs = nullptr;
+  tb200_pst_open* j = new tb200_pst_open();
+  j->nv = nv;
+  j->pt = pt;
+  auto bail = [&](int rc) {
+    if (j->st) cudaStreamSynchronize(j->st);
+    pst_open_release(j);
+    return rc;
+  };
+#define CUJ(expr)                                                                                                    \
+  do {                                                                                                               \
+    cudaError_t e__ = (expr);                                                                                        \
+    if (e__ != cudaSuccess) return bail(fail((int)e__, "%s failed: %s", #expr, cudaGetErrorString(e__)));            \
+  } while (0)
+  CUJ(cudaStreamCreateWithFlags(&j->st, cudaStreamNonBlocking));
+  CUJ(cudaEventCreateWithFlags(&j->ev, cudaEventDisableTiming));
+  cudaStream_t st = j->st;
   // level i occupies [off_i, off_i + 2^(nv-i)) of d_q / d_bases, off_i = 2^(nv+1) - 2^(nv-i+1)
-  CU(cudaMallocAsync((void**)&d_r0, n * 32, g.stream));
-  CU(cudaMallocAsync((void**)&d_r1, std::max<size_t>(n / 2, 1) * 32, g.stream));
-  CU(cudaMallocAsync((void**)&d_q, 2 * n * 32, g.stream));
-  CU(cudaMallocAsync((void**)&d_p, nv * 32, g.stream));
-  CU(cudaMallocAsync((void**)&d_bases, 2 * n * pt, g.stream));
-  CU(cudaMallocAsync((void**)&d_proofs, nv * pt, g.stream));
-  CU(cudaMemcpyAsync(d_r0, evals, n * 32, cudaMemcpyHostToDevice, g.stream));
-  CU(cudaMemcpyAsync(d_p, point, nv * 32, cudaMemcpyHostToDevice, g.stream));
+  CUJ(cudaMallocAsync((void**)&j->d_r0, n * 32, st));
+  CUJ(cudaMallocAsync((void**)&j->d_r1, std::max<size_t>(n / 2, 1) * 32, st));
+  CUJ(cudaMallocAsync((void**)&j->d_q, 2 * n * 32, st));
+  CUJ(cudaMallocAsync((void**)&j->d_p, nv * 32, st));
+  CUJ(cudaMallocAsync((void**)&j->d_bases, 2 * n * pt, st));
+  CUJ(cudaMallocAsync((void**)&j->d_proofs, nv * pt, st));
+  CUJ(cudaMemcpyAsync(j->d_r0, evals, n * 32, cudaMemcpyHostToDevice, st));
+  CUJ(cudaMemcpyAsync(j->d_p, point, nv * 32, cudaMemcpyHostToDevice, st));
   if (!(flags & TB200_SCALARS_MONT)) {
-    LAUNCH(k_fr_to_mont, cdiv(n, 128), 128, g.stream, d_r0, (uint32_t)n);
-    LAUNCH(k_fr_to_mont, cdiv(nv, 128), 128, g.stream, d_p, (uint32_t)nv);
+    k_fr_to_mont<<<cdiv(n, 128), 128, 0, st>>>(j->d_r0, (uint32_t)n);
+    k_fr_to_mont<<<cdiv(nv, 128), 128, 0, st>>>(j->d_p, (uint32_t)nv);
+    g_launches += 2;
   }
   // the quotient loop is a cheap sequential chain; the nv MSMs that consume it are independent of each other and
   // latency-bound (Horner chain + inversion), so they run concurrently on side streams with their own workspaces
   std::vector<size_t> off(nv);
-  uint32_t *r_in = d_r0, *r_out = d_r1;
+  uint32_t *r_in = j->d_r0, *r_out = j->d_r1;
   size_t o = 0;
   for (size_t i = 0; i < nv; i++) {
     const size_t half = size_t(1) << (nv - i - 1);
     off[i] = o;
-    CU(cudaMemcpyAsync((char*)d_bases + o * pt, level_bases[i], 2 * half * pt, cudaMemcpyHostToDevice, g.stream));
-    LAUNCH(k_pst_level, cdiv(half, 128), 128, g.stream, r_in, (uint32_t)half, d_p + 8 * i, r_out, d_q + 8 * o);
+    CUJ(cudaMemcpyAsync((char*)j->d_bases + o * pt, level_bases[i], 2 * half * pt, cudaMemcpyHostToDevice, st));
+    k_pst_level<<<cdiv(half, 128), 128, 0, st>>>(r_in, (uint32_t)half, j->d_p + 8 * i, r_out, j->d_q + 8 * o);
+    g_launches++;
     std::swap(r_in, r_out);
     o += 2 * half;
   }
-  CU(cudaEventRecord(g.ev_join, g.stream));
+  CUJ(cudaGetLastError());
+  CUJ(cudaEventRecord(j->ev, st));
   const bool prof = g.profiling;
   g.profiling = false;
   int rc = 0;
   for (size_t i = 0; i < nv && rc == 0; i++) {
     const int sl = (int)(i % Ctx::SIDE);
     if (!g.side_stream[sl]) {
-      CU(cudaStreamCreateWithFlags(&g.side_stream[sl], cudaStreamNonBlocking));
-      CU(cudaEventCreateWithFlags(&g.side_done[sl], cudaEventDisableTiming));
+      cudaError_t e = cudaStreamCreateWithFlags(&g.side_stream[sl], cudaStreamNonBlocking);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g.side_done[sl], cudaEventDisableTiming);
+      if (e != cudaSuccess) {
+        rc = fail((int)e, "side stream creation failed: %s", cudaGetErrorString(e));
+        break;
+      }
     }
-    if (i < (size_t)Ctx::SIDE) CU(cudaStreamWaitEvent(g.side_stream[sl], g.ev_join, 0));
-    rc = msm_dev(g, (char*)d_bases + off[i] * pt, d_q + 8 * off[i], size_t(1) << (nv - i), TB200_SCALARS_MONT,
-                 (char*)d_proofs + i * pt, g.side_stream[sl], nullptr, &g.side_arena[sl], false, g2);
+    if (i < (size_t)Ctx::SIDE) cudaStreamWaitEvent(g.side_stream[sl], j->ev, 0);
+    rc = msm_dev(g, (char*)j->d_bases + off[i] * pt, j->d_q + 8 * off[i], size_t(1) << (nv - i), TB200_SCALARS_MONT,
+                 (char*)j->d_proofs + i * pt, g.side_stream[sl], nullptr, &g.side_arena[sl], false, g2);
   }
   g.profiling = prof;
+  g.marks.clear();
   for (int sl = 0; sl < Ctx::SIDE && sl < (int)nv; sl++) {
     if (!g.side_stream[sl]) continue;
     cudaEventRecord(g.side_done[sl], g.side_stream[sl]);
-    cudaStreamWaitEvent(g.stream, g.side_done[sl], 0);
+    cudaStreamWaitEvent(st, g.side_done[sl], 0);
   }
-  if (rc == 0) {
-    cudaError_t e = cudaMemcpyAsync(proofs, d_proofs, nv * pt, cudaMemcpyDeviceToHost, g.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
-    if (e != cudaSuccess) rc = fail((int)e, "proof copy failed: %s", cudaGetErrorString(e));
-  } else {
-    cudaStreamSynchronize(g.stream);
-  }
-  g.marks.clear();
-  cudaFreeAsync(d_r0, g.stream);
-  cudaFreeAsync(d_r1, g.stream);
-  cudaFreeAsync(d_q, g.stream);
-  cudaFreeAsync(d_p, g.stream);
-  cudaFreeAsync(d_bases, g.stream);
-  cudaFreeAsync(d_proofs, g.stream);
+  if (rc) return bail(rc);
+#undef CUJ
+  *out = j;
+  return 0;
+}
+
+int pst_open_finish(tb200_pst_open* j, uint64_t* proofs) {
+  cudaError_t e = cudaSuccess;
+  if (proofs) e = cudaMemcpyAsync(proofs, j->d_proofs, j->nv * j->pt, cudaMemcpyDeviceToHost, j->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(j->st);
+  int rc = e == cudaSuccess ? 0 : fail((int)e, "proof copy failed: %s", cudaGetErrorString(e));
+  pst_open_release(j);
   return rc;
 }
+
+int pst_open_locked(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                    unsigned flags, uint64_t* proofs, bool g2) {
+  if (!proofs) return fail(TB200_E_ARG, "null pointer");
+  if (nv == 0) return (evals && point && level_bases) ? 0 : fail(TB200_E_ARG, "null pointer");
+  tb200_pst_open* j = nullptr;
+  if (int rc = pst_open_enqueue(evals, nv, point, level_bases, flags, g2, &j)) return rc;
+  return pst_open_finish(j, proofs);
+}
+}  // namespace
+
+extern "C" {
+
+/* asynchronous form: _begin returns once everything is enqueued (the host buffers may be reused when it returns: the
+ * uploads are staged), _end waits and writes the nv proofs */
+int tb200_pst_open_g2_begin(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                            unsigned flags, tb200_pst_open_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  CU(cudaSetDevice(primary().device));
+  return pst_open_enqueue(evals, nv, point, level_bases, flags, true, out);
+}
+int tb200_pst_open_g1_begin(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
+                            unsigned flags, tb200_pst_open_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  CU(cudaSetDevice(primary().device));
+  return pst_open_enqueue(evals, nv, point, level_bases, flags, false, out);
+}
+int tb200_pst_open_end(tb200_pst_open_t h, uint64_t* proofs) {
+  if (!h) return fail(TB200_E_ARG, "null handle");
+  if (need_ready()) return TB200_E_STATE;
+  // no library lock while waiting: the point of the asynchronous form is that other calls run meanwhile
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    CU(cudaSetDevice(primary().device));
+  }
+  return pst_open_finish(h, proofs);
+}
+
 int tb200_pst_open_g1(const uint64_t* evals, size_t nv, const uint64_t* point, const uint64_t* const* level_bases,
                       unsigned flags, uint64_t* proofs) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -21,7 +21,28 @@ import numpy as np
 from . import _lib
 
 
-def _open(level_bases: Sequence[np.ndarray], evals, point, mont: bool, g2: bool) -> np.ndarray:
+class PendingOpen:
+    """An opening in flight (tb200_pst_open_g1/g2_begin): `wait()` returns the proofs."""
+
+    def __init__(self, handle, nv: int, width: int):
+        self._h, self._nv, self._width = handle, nv, width
+
+    def wait(self) -> np.ndarray:
+        out = np.zeros((self._nv, self._width), dtype=np.uint64)
+        if self._h is not None:
+            h, self._h = self._h, None
+            _lib.check(_lib.engine().tb200_pst_open_end(h, out.ctypes.data_as(ctypes.c_void_p)))
+        return out
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.engine().tb200_pst_open_end(self._h, None)
+        except Exception:
+            pass
+
+
+def _open(level_bases: Sequence[np.ndarray], evals, point, mont: bool, g2: bool, asynchronous: bool = False):
     width = 24 if g2 else 12
     ev = np.ascontiguousarray(evals, dtype=np.uint64).reshape(-1, 4)
     pt = np.ascontiguousarray(point, dtype=np.uint64).reshape(-1, 4)
@@ -35,6 +56,14 @@ def _open(level_bases: Sequence[np.ndarray], evals, point, mont: bool, g2: bool)
         if len(b) != 1 << (nv - i):
             raise ValueError(f"CRS level {i} must hold 2^{nv - i} points")
     ptrs = (ctypes.c_void_p * max(nv, 1))(*[b.ctypes.data for b in levels])
+    if asynchronous:
+        if nv == 0:
+            return PendingOpen(None, 0, width)
+        handle = ctypes.c_void_p()
+        fn = _lib.engine().tb200_pst_open_g2_begin if g2 else _lib.engine().tb200_pst_open_g1_begin
+        _lib.check(fn(ev.ctypes.data_as(ctypes.c_void_p), nv, pt.ctypes.data_as(ctypes.c_void_p),
+                      ctypes.cast(ptrs, ctypes.c_void_p), _lib.SCALARS_MONT if mont else 0, ctypes.byref(handle)))
+        return PendingOpen(handle, nv, width)
     out = np.zeros((nv, width), dtype=np.uint64)
     fn = _lib.engine().tb200_pst_open_g2 if g2 else _lib.engine().tb200_pst_open_g1
     _lib.check(fn(ev.ctypes.data_as(ctypes.c_void_p), nv, pt.ctypes.data_as(ctypes.c_void_p),
@@ -51,3 +80,8 @@ def open(level_bases_h: Sequence[np.ndarray], evals, point, mont: bool = True) -
 def open_g1(level_bases_g: Sequence[np.ndarray], evals, point, mont: bool = True) -> np.ndarray:
     """Fork API `MultilinearPC::open_g1(ck, polynomial, point)` -> `ProofG1{proofs: Vec<G1Affine>}` as [nv, 12]."""
     return _open(level_bases_g, evals, point, mont, False)
+
+
+def open_begin(level_bases_h: Sequence[np.ndarray], evals, point, mont: bool = True) -> PendingOpen:
+    """`MultilinearPC::open` started without waiting: the caller overlaps it with other work and calls `.wait()`."""
+    return _open(level_bases_h, evals, point, mont, True, asynchronous=True)

@@ -252,9 +252,12 @@ class Polynomial:
         assert np.array_equal(c_u, comm_q), "debug_assert!(c_u == comm.g_product) (src/sqrt_pst.rs:206)"
         h_vec = ck.powers_of_h[self.odd] if ck.powers_of_h is not None else None     # src/sqrt_pst.rs:207
         g_levels = ck.powers_of_g[self.odd:] if ck.powers_of_g is not None else None  # variable CRS: off = ck.nv - m
-        proof = mipp.MippProofG1.prove(challenge, comm_list, self.chis_b, c_u, h_vec, g_levels)   # :212-213
-        pst_proof = None
+        # The reference computes the PST proof of q AFTER the MIPP proof (:218-225), but it depends only on q and the
+        # point, not on the transcript: it is started here and runs on streams of its own next to the MIPP rounds.
+        pending = None
         if ck.powers_of_h is not None:
             a_rev = list(point[: self.m + self.odd])[::-1]                        # :218-222
-            pst_proof = multilinear_pc.open(ck.powers_of_h, self.q, curve.scalars_to_words(a_rev, mont=True))  # :225
+            pending = multilinear_pc.open_begin(ck.powers_of_h, self.q, curve.scalars_to_words(a_rev, mont=True))  # :225
+        proof = mipp.MippProofG1.prove(challenge, comm_list, self.chis_b, c_u, h_vec, g_levels)   # :212-213
+        pst_proof = pending.wait() if pending is not None else None
         return OpenG1(u=c_u, comm_q=comm_q, mipp=proof, pst_proof=pst_proof)
