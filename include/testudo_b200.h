@@ -250,6 +250,14 @@ void tb200_set_commit_pipeline(int enabled);
  * signed digits, a quad of lanes per point, 8 points per one-warp CTA: `commit_scalar` (src/commitments.rs:70-77), the bullet rounds
  * (src/nizk/bullet.rs:93-118), the last MIPP rounds (src/mipp.rs:77-85). Identical results. */
 void tb200_set_small_msm_max(int n);
+/* large single G1 MSMs: 1 = the pipeline runs as three staggered window ranges on three streams (device-resident inputs)
+ * resp. sorts the next point-range chunk next to the accumulation of the current one (host inputs), so that the
+ * memory-bound sort stages and the latency-bound reduction tails could hide behind the integer-pipe-bound accumulation;
+ * 0 (default) = everything on one stream. Identical results. Measured on B200: 84.2 -> 84.0 ms resident, 92.6 -> 91.4 ms
+ * from host buffers at 2^24 points -- the accumulation fills the register file (4 CTAs x 128 threads x 128 registers per
+ * SM), so the side streams' CTAs only displace accumulation CTAs; kept as an option, off by default.
+ * Ignored while stage profiling is on. */
+void tb200_set_msm_overlap(int enabled);
 /* integer-pipe microbenchmark: runs `iters` dependent-chain iterations of wide MACs on every SM and returns the
  * achieved 32x32->64 multiply-accumulates per second in *out_macs_per_s (kind: 0 = IMAD.WIDE.U32 reg-reg,
  * 1 = IMAD (32-bit lo), 2 = full Fq Montgomery multiplications per second). */

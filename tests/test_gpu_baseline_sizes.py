@@ -264,3 +264,29 @@ def test_sqrt_pst_nv26_commit_open_accepted_by_oracle_verifier(engine):
     assert ver.sqrt_pst_verify(vk, verifier_transcript(), U, r, v, pst_proof, proof, T) is True
     assert ver.sqrt_pst_verify(vk, verifier_transcript(), U, r, (v + 1) % R, pst_proof, proof, T) is False
     ck.close()
+
+
+def test_msm_overlap_option_gives_the_same_point(engine, oracle_c):
+    """tb200_set_msm_overlap(1): window ranges on three streams (resident inputs) and chunk sorts on a side stream (host
+    inputs) -- off by default (no measurable gain), but the results must be the points the default path gives."""
+    import torch
+
+    n = 1 << 21
+    seed = 2121
+    bases = synthetic.make_bases_dev(n, seed=seed, multiples_of_g=oracle_multiples(oracle_c))
+    sc = synthetic.make_scalars_dev(n, seed=seed + 1, skew=True)
+    want = o.mul(synthetic.expected_dlog(sc, n, seed=seed), o.G)
+    out = torch.zeros(12, dtype=torch.int64, device="cuda")
+    engine.tb200_set_msm_overlap(1)
+    try:
+        for _ in range(2):                                    # twice: the side arenas and events are reused
+            _lib.check(engine.tb200_msm_g1_dev(ctypes.c_void_p(bases.data_ptr()), ctypes.c_void_p(sc.data_ptr()), n, 0,
+                                               ctypes.c_void_p(out.data_ptr()), None))
+            _lib.check(engine.tb200_stream_sync())
+            assert h.pt_from_np(out.cpu().numpy().view(np.uint64)) == want
+            got = msm.msm_bigint(bases.cpu().numpy().view(np.uint64), sc.cpu().numpy().view(np.uint64))
+            assert h.pt_from_np(got) == want
+    finally:
+        engine.tb200_set_msm_overlap(0)
+    del bases, sc
+    torch.cuda.empty_cache()

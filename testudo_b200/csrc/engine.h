@@ -95,6 +95,10 @@ struct Ctx {
   cudaEvent_t ev_points = nullptr;
   cudaStream_t stream2 = nullptr;      // second pipeline for independent small MSMs (MIPP cross commitments)
   cudaEvent_t ev_join = nullptr;
+  // large single MSMs: phases of different window ranges / point-range chunks side by side (engine_g1.cu)
+  cudaStream_t split_stream[2] = {};   // high priority: their memory-bound sort kernels slip in next to an accumulation
+  Arena split_arena[2];
+  cudaEvent_t ev_split[4] = {};
   cudaStream_t pair_stream = nullptr;  // pairing products of a MIPP round, next to its cross MSMs
   cudaEvent_t ev_pair = nullptr, ev_pair2 = nullptr;
   Arena arena, arena2;
@@ -133,6 +137,8 @@ struct Engine {
   size_t host_chunk_min = size_t(1) << 21;  // host-facing single MSMs: chunked upload/compute overlap from here
   size_t shard_min = size_t(1) << 18;       // host-facing single MSMs are sharded over the GPUs from ndev * this
   int pairing_coop_max = 2048;              // Miller loops: CTA-per-pair up to this many pairs, lanes-per-pair above
+  int msm_overlap = 0;                      // large single MSMs: window ranges / chunk sorts on side streams (engine_g1.cu);
+                                            // measured neutral (84.2 -> 84.0 ms resident, 92.6 -> 91.4 ms from host): opt-in
   int small_msm_max = 1024;                  // single G1 MSMs of up to this many points run in one CTA (kernels_small.cuh)
   int commit_pipeline = 0;                  // tb200_sqrt_pst_commit: Miller loops of a row chunk next to the next chunk's MSMs
   int acc_mode = 0;                         // 0 / 4: fused-Y3 XYZZ segments (default); 3: plain CIOS products

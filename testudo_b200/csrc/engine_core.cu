@@ -330,6 +330,12 @@ static int ctx_create(Ctx& g, int device) {
   CU(cudaEventCreateWithFlags(&g.ev_points, cudaEventDisableTiming));
   CU(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
   CU(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
+  {
+    int lo = 0, hi = 0;  // numerically lowest = greatest priority
+    CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithPriority(&g.split_stream[i], cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 4; i++) CU(cudaEventCreateWithFlags(&g.ev_split[i], cudaEventDisableTiming));
+  }
   CU(cudaMalloc((void**)&g.d_result, Ctx::RES_BYTES));
   CU(cudaMallocHost((void**)&g.h_result, Ctx::RES_BYTES));
   g.profiling = E.profiling;
@@ -348,6 +354,12 @@ static void ctx_destroy(Ctx& g) {
   cudaDeviceSynchronize();
   g.arena.destroy();
   g.arena2.destroy();
+  for (int i = 0; i < 2; i++) {
+    g.split_arena[i].destroy();
+    if (g.split_stream[i]) cudaStreamDestroy(g.split_stream[i]);
+  }
+  for (int i = 0; i < 4; i++)
+    if (g.ev_split[i]) cudaEventDestroy(g.ev_split[i]);
   for (int i = 0; i < Ctx::SIDE; i++) {
     if (g.side_stream[i]) {
       cudaStreamDestroy(g.side_stream[i]);
@@ -498,6 +510,7 @@ void tb200_set_pass_entries_max(uint64_t entries) {
 }
 void tb200_set_shard_min(size_t units) { E.shard_min = units ? units : (size_t(1) << 18); }
 void tb200_set_commit_pipeline(int enabled) { E.commit_pipeline = enabled ? 1 : 0; }
+void tb200_set_msm_overlap(int enabled) { E.msm_overlap = enabled ? 1 : 0; }
 void tb200_set_small_msm_max(int n) { E.small_msm_max = n < 0 ? 1024 : std::min(n, 1024); }
 
 // ---- device / pinned host buffers for hosts without a CUDA runtime of their own ------------------------------------------

@@ -63,7 +63,7 @@ struct ChunkCtl {
 };
 
 static int make_plan(const Ctx& g, Plan& p, uint32_t rows, uint32_t cols, long long rs, long long cs, int c, int batch,
-                     unsigned flags, bool g2 = false) {
+                     unsigned flags, bool g2 = false, int w_lo = 0, int w_hi = -1) {
   MsmGeom& q = p.geo;
   p.g2 = g2;
   const size_t pw = g2 ? 2 : 1;  // point width relative to G1
@@ -76,9 +76,11 @@ static int make_plan(const Ctx& g, Plan& p, uint32_t rows, uint32_t cols, long l
   q.W = num_windows(c);
   q.nb = 1u << (c - 1);
   q.batch = batch;
-  q.groups = batch ? rows : (uint32_t)q.W;
+  q.w_lo = w_lo;
+  q.w_hi = w_hi < 0 ? q.W : w_hi;
+  q.groups = batch ? rows : (uint32_t)(q.w_hi - q.w_lo);
   q.mont = (flags & TB200_SCALARS_MONT) ? 1 : 0;
-  p.M_max = (uint64_t)rows * cols * q.W;
+  p.M_max = (uint64_t)rows * cols * (batch ? q.W : (q.w_hi - q.w_lo));
   p.B = (uint64_t)q.groups * q.nb;
   if (p.M_max > E.pass_entries_max || p.B >= (1ull << 31))
     return fail(TB200_E_LIMIT, "MSM too large for one pass: %llu entries, %llu buckets", (unsigned long long)p.M_max,
@@ -103,7 +105,7 @@ static int make_plan(const Ctx& g, Plan& p, uint32_t rows, uint32_t cols, long l
   b += Arena::pad((size_t)p.ntiles * 4 + 4);
   b += Arena::pad(std::max<uint64_t>(p.M_max, 1) * 4);  // entries
   b += Arena::pad(p.B * 192 * pw);                      // buckets
-  b += Arena::pad((size_t)p.S_max * 192 * pw) + Arena::pad((size_t)p.S_max * 4);
+  b += Arena::pad((size_t)p.S_max * 192 * pw) + Arena::pad((size_t)p.S_max * 4) + Arena::pad(64 * 4);
   uint64_t n = p.B;
   for (uint32_t L : p.Ls) {
     n /= L;
@@ -115,37 +117,33 @@ static int make_plan(const Ctx& g, Plan& p, uint32_t rows, uint32_t cols, long l
   return 0;
 }
 
-// Runs the whole pipeline on `st`. d_points: affine points indexed by entry refs. d_out: groups*96 B (batch) or 96 B.
-// The caller has acquired `arena` for `st` (Arena::acquire) and releases it afterwards.
-static int run_pipeline(Ctx& g, const Plan& p, const uint32_t* d_scalars, const uint4* d_points, uint4* d_out,
-                        cudaStream_t st, cudaEvent_t points_ready, Arena& arena, const ChunkCtl* chunk = nullptr) {
-  MsmGeom q = p.geo;
-  if (chunk) q.ref_base = chunk->ref_base;
+// The pipeline in four phases, so that callers can put them on different streams (msm_dev: window ranges side by side;
+// msm_host_enqueue: the sort of chunk k+1 next to the accumulation of chunk k). `arena` holds the phase's scratch; the
+// caller has acquired it for `st` (Arena::acquire) and releases it after the last phase that uses the buffers.
+struct PipeBufs {
+  uint32_t *counts = nullptr, *starts = nullptr, *cursors = nullptr, *tile_sums = nullptr, *entries = nullptr;
+  uint4 *buckets = nullptr, *heads = nullptr;
+  int32_t* head_bucket = nullptr;
+  uint32_t* need = nullptr;   // 64 words: which fix-up rounds have work (k_fixup_round)
+};
+
+// digits -> scan -> scatter. Needs only the scalars.
+static int pipe_sort(Ctx& g, const Plan& p, const MsmGeom& q, const uint32_t* d_scalars, cudaStream_t st, Arena& arena,
+                     const ChunkCtl* chunk, PipeBufs& b) {
   const size_t pw = p.g2 ? 2 : 1;
   int rc = arena.reserve(p.bytes);
   if (rc) return fail(rc, "workspace allocation of %zu bytes failed: %s", p.bytes, cudaGetErrorString((cudaError_t)rc));
   arena.reset();
-  uint32_t* counts = arena.take<uint32_t>(p.B + 1);
-  uint32_t* starts = arena.take<uint32_t>(p.B + 1);
-  uint32_t* cursors = arena.take<uint32_t>(p.B);
-  uint32_t* tile_sums = arena.take<uint32_t>(p.ntiles + 1);
-  uint32_t* entries = arena.take<uint32_t>(std::max<uint64_t>(p.M_max, 1));
-  uint4* buckets = chunk ? chunk->buckets : arena.take<uint4>(p.B * 12 * pw);
-  uint4* heads = arena.take<uint4>((size_t)p.S_max * 12 * pw);
-  int32_t* head_bucket = arena.take<int32_t>(p.S_max);
-
-  g.last_c = q.c;
-  g.last_W = q.W;
-  g.last_K = (int)p.K;
-  g.last_entries = p.M_max;
-  g.last_buckets = p.B;
-
+  b.counts = arena.take<uint32_t>(p.B + 1);
+  b.starts = arena.take<uint32_t>(p.B + 1);
+  b.cursors = arena.take<uint32_t>(p.B);
+  b.tile_sums = arena.take<uint32_t>(p.ntiles + 1);
+  b.entries = arena.take<uint32_t>(std::max<uint64_t>(p.M_max, 1));
+  b.buckets = chunk ? chunk->buckets : arena.take<uint4>(p.B * 12 * pw);
+  b.heads = arena.take<uint4>((size_t)p.S_max * 12 * pw);
+  b.head_bucket = arena.take<int32_t>(p.S_max);
+  b.need = arena.take<uint32_t>(64);
   const uint64_t items = (uint64_t)q.rows * q.cols;
-  if (items == 0) {
-    uint32_t cnt = q.batch ? q.rows : 1;
-    if (cnt) LAUNCH(k_write_identity, cdiv(cnt * 6 * pw, 128), 128, st, d_out, (uint32_t)(cnt * pw));
-    return 0;
-  }
   if (mark(g, st, "begin")) return 1;
   const uint32_t dig_grid = (uint32_t)std::min<uint64_t>(cdiv(items, 256), (uint64_t)g.sms * 16);
   // batches with enough rows to fill the GPU sort each row inside one CTA's shared memory
@@ -156,32 +154,38 @@ static int run_pipeline(Ctx& g, const Plan& p, const uint32_t* d_scalars, const 
   if (row_sort) {
     CU(cudaFuncSetAttribute(k_batch_digits<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_launch));
     CU(cudaFuncSetAttribute(k_batch_digits<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_launch));
-    LAUNCH_SMEM(k_batch_digits<false>, q.rows, 1024, row_smem_launch, st, d_scalars, q, counts, (uint32_t*)nullptr);
+    LAUNCH_SMEM(k_batch_digits<false>, q.rows, 1024, row_smem_launch, st, d_scalars, q, b.counts, (uint32_t*)nullptr);
   } else {
-    CU(cudaMemsetAsync(counts, 0, (p.B + 1) * 4, st));
-    LAUNCH(k_digits<false>, dig_grid, 256, st, d_scalars, q, counts, (uint32_t*)nullptr, -1);
+    CU(cudaMemsetAsync(b.counts, 0, (p.B + 1) * 4, st));
+    LAUNCH(k_digits<false>, dig_grid, 256, st, d_scalars, q, b.counts, (uint32_t*)nullptr, -1);
   }
   if (mark(g, st, "digits")) return 1;
-  LAUNCH(k_scan_tile_sums, p.ntiles, SCAN_THREADS, st, counts, (uint32_t)p.B, tile_sums);
-  LAUNCH(k_scan_tile_offsets, 1, SCAN_THREADS, st, tile_sums, p.ntiles, tile_sums + p.ntiles);
-  LAUNCH(k_scan_apply, p.ntiles, SCAN_THREADS, st, counts, (uint32_t)p.B, tile_sums, starts, cursors);
+  LAUNCH(k_scan_tile_sums, p.ntiles, SCAN_THREADS, st, b.counts, (uint32_t)p.B, b.tile_sums);
+  LAUNCH(k_scan_tile_offsets, 1, SCAN_THREADS, st, b.tile_sums, p.ntiles, b.tile_sums + p.ntiles);
+  LAUNCH(k_scan_apply, p.ntiles, SCAN_THREADS, st, b.counts, (uint32_t)p.B, b.tile_sums, b.starts, b.cursors);
   if (mark(g, st, "scan")) return 1;
   if (row_sort) {
-    LAUNCH_SMEM(k_batch_digits<true>, q.rows, 1024, row_smem_launch, st, d_scalars, q, starts, entries);
+    LAUNCH_SMEM(k_batch_digits<true>, q.rows, 1024, row_smem_launch, st, d_scalars, q, b.starts, b.entries);
   } else {
     // large single MSMs: one pass per window keeps the writes of a pass inside an L2-sized slice of entries[]
     const bool per_window = !q.batch && q.c >= 19 && (uint64_t)q.cols * 4 * q.W > (64ull << 20);
     if (per_window) {
-      for (int w = 0; w < q.W; w++) LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, cursors, entries, w);
+      for (int w = q.w_lo; w < q.w_hi; w++) LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, b.cursors, b.entries, w);
     } else {
-      LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, cursors, entries, -1);
+      LAUNCH(k_digits<true>, dig_grid, 256, st, d_scalars, q, b.cursors, b.entries, -1);
     }
   }
   if (mark(g, st, "scatter")) return 1;
+  return 0;
+}
+
+// accumulate -> fix-up. Needs the points (`points_ready`, if given, is awaited first).
+static int pipe_accumulate(Ctx& g, const Plan& p, const MsmGeom& q, const PipeBufs& b, const uint4* d_points, cudaStream_t st,
+                           cudaEvent_t points_ready, const ChunkCtl* chunk) {
   if (points_ready) CU(cudaStreamWaitEvent(st, points_ready, 0));  // bases may still be in flight until here
   // M is only known on the device (starts[B]); launch for the upper bound, surplus threads exit immediately
   if (p.g2) {
-    if (int r = g2_accumulate(st, p.S_max, entries, starts, (uint32_t)p.B, p.K, d_points, buckets, heads, head_bucket))
+    if (int r = g2_accumulate(st, p.S_max, b.entries, b.starts, (uint32_t)p.B, p.K, d_points, b.buckets, b.heads, b.head_bucket))
       return r;
   } else {
     // operands in shared-memory slots (kernels_smem.cuh). acc_mode 3: plain CIOS products; 0 / 4: Y3 as one fused sum
@@ -189,12 +193,12 @@ static int run_pipeline(Ctx& g, const Plan& p, const uint32_t* d_scalars, const 
     const dim3 grid(cdiv(p.S_max, ACCS_THREADS));
     if (E.acc_mode == 3) {
       CU(cudaFuncSetAttribute(k_accumulate_s<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACCS_SMEM));
-      LAUNCH_SMEM(k_accumulate_s<0>, grid, ACCS_THREADS, ACCS_SMEM, st, entries, starts, (uint32_t)p.B, p.K, d_points,
-                  buckets, heads, head_bucket, chunk ? 1 : 0);
+      LAUNCH_SMEM(k_accumulate_s<0>, grid, ACCS_THREADS, ACCS_SMEM, st, b.entries, b.starts, (uint32_t)p.B, p.K, d_points,
+                  b.buckets, b.heads, b.head_bucket, chunk ? 1 : 0);
     } else {
       CU(cudaFuncSetAttribute(k_accumulate_s<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ACCS_SMEM));
-      LAUNCH_SMEM(k_accumulate_s<2>, grid, ACCS_THREADS, ACCS_SMEM, st, entries, starts, (uint32_t)p.B, p.K, d_points,
-                  buckets, heads, head_bucket, chunk ? 1 : 0);
+      LAUNCH_SMEM(k_accumulate_s<2>, grid, ACCS_THREADS, ACCS_SMEM, st, b.entries, b.starts, (uint32_t)p.B, p.K, d_points,
+                  b.buckets, b.heads, b.head_bucket, chunk ? 1 : 0);
     }
   }
   if (mark(g, st, "accumulate")) return 1;
@@ -204,21 +208,27 @@ static int run_pipeline(Ctx& g, const Plan& p, const uint32_t* d_scalars, const 
   const uint64_t max_span = std::min<uint64_t>(p.S_max, max_bucket / p.K + 2);
   if (p.g2) {
     for (uint32_t round = 0; (1ull << round) < max_span; round++)
-      if (int r = g2_fixup_round(st, p.S_max, starts, (uint32_t)p.B, p.K, round, heads, head_bucket)) return r;
-    if (int r = g2_fixup_final(st, p.S_max, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket)) return r;
+      if (int r = g2_fixup_round(st, p.S_max, b.starts, (uint32_t)p.B, p.K, round, b.heads, b.head_bucket)) return r;
+    if (int r = g2_fixup_final(st, p.S_max, b.starts, (uint32_t)p.B, p.K, b.buckets, b.heads, b.head_bucket)) return r;
   } else {
-    for (uint32_t round = 0; (1ull << round) < max_span; round++)
-      LAUNCH(k_fixup_round, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, round, heads, head_bucket);
-    LAUNCH(k_fixup_final, cdiv(p.S_max, 128), 128, st, starts, (uint32_t)p.B, p.K, buckets, heads, head_bucket);
+    CU(cudaMemsetAsync(b.need, 0, 64 * 4, st));
+    for (uint32_t round = 0; (1ull << round) < max_span && round < 62; round++)
+      LAUNCH(k_fixup_round, cdiv(p.S_max, 128), 128, st, b.starts, (uint32_t)p.B, p.K, round, b.heads, b.head_bucket, b.need);
+    LAUNCH(k_fixup_final, cdiv(p.S_max, 128), 128, st, b.starts, (uint32_t)p.B, p.K, b.buckets, b.heads, b.head_bucket);
   }
   if (mark(g, st, "fixup")) return 1;
-  if (chunk && !chunk->last) return 0;  // later point-range chunks continue in the same buckets
-  // hierarchical bucket reduction
+  return 0;
+}
+
+// hierarchical bucket reduction: one (S, W) pair per group; *group_w = the groups' sums (XYZZ, q.groups entries)
+static int pipe_reduce(Ctx& g, const Plan& p, const MsmGeom& q, const PipeBufs& b, cudaStream_t st, Arena& arena,
+                       const ChunkCtl* chunk, const uint4** group_w) {
+  const size_t pw = p.g2 ? 2 : 1;
   // chunked runs: emptiness is per chunk; the persistent buckets carry the identity (all zero) instead
-  const uint4 *inS = buckets, *inW = nullptr;
+  const uint4 *inS = b.buckets, *inW = nullptr;
   uint64_t n = p.B;
   int log2_ell = 0;
-  const uint32_t* level0 = chunk ? nullptr : starts;
+  const uint32_t* level0 = chunk ? nullptr : b.starts;
   for (size_t li = 0; li < p.Ls.size(); li++) {
     const uint32_t L = p.Ls[li];
     n /= L;
@@ -234,8 +244,15 @@ static int run_pipeline(Ctx& g, const Plan& p, const uint32_t* d_scalars, const 
     level0 = nullptr;
     for (uint32_t v = L; v > 1; v >>= 1) log2_ell++;
   }
-  const uint4* group_w = inW;  // nb >= 4 (c >= 3): at least one reduction level has run
+  *group_w = inW;  // nb >= 4 (c >= 3): at least one reduction level has run
+  (void)q;
   if (mark(g, st, "reduce")) return 1;
+  return 0;
+}
+
+// window combine (single MSM: `W` window sums at group_w) or per-row normalisation (batch)
+static int pipe_finalize(Ctx& g, const Plan& p, const MsmGeom& q, const uint4* group_w, uint4* d_out, cudaStream_t st,
+                         Arena& arena) {
   if (p.g2 && q.W <= 96) {
     // window combine over the twisted Frobenius: 4 W parallel 64-doubling chains + a tree instead of ~250 serial doublings
     uint4* fin = arena.take<uint4>((size_t)4 * q.W * 24);
@@ -249,6 +266,37 @@ static int run_pipeline(Ctx& g, const Plan& p, const uint32_t* d_scalars, const 
   }
   if (mark(g, st, "finalize")) return 1;
   return 0;
+}
+
+static void note_geometry(Ctx& g, const Plan& p, uint64_t entries, uint64_t buckets) {
+  g.last_c = p.geo.c;
+  g.last_W = p.geo.W;
+  g.last_K = (int)p.K;
+  g.last_entries = entries;
+  g.last_buckets = buckets;
+}
+
+// Runs the whole pipeline on `st`. d_points: affine points indexed by entry refs. d_out: groups*96 B (batch) or 96 B.
+// The caller has acquired `arena` for `st` (Arena::acquire) and releases it afterwards.
+static int run_pipeline(Ctx& g, const Plan& p, const uint32_t* d_scalars, const uint4* d_points, uint4* d_out,
+                        cudaStream_t st, cudaEvent_t points_ready, Arena& arena, const ChunkCtl* chunk = nullptr) {
+  MsmGeom q = p.geo;
+  if (chunk) q.ref_base = chunk->ref_base;
+  const size_t pw = p.g2 ? 2 : 1;
+  note_geometry(g, p, p.M_max, p.B);
+  const uint64_t items = (uint64_t)q.rows * q.cols;
+  if (items == 0) {
+    uint32_t cnt = q.batch ? q.rows : 1;
+    if (cnt) LAUNCH(k_write_identity, cdiv(cnt * 6 * pw, 128), 128, st, d_out, (uint32_t)(cnt * pw));
+    return 0;
+  }
+  PipeBufs b;
+  if (int rc = pipe_sort(g, p, q, d_scalars, st, arena, chunk, b)) return rc;
+  if (int rc = pipe_accumulate(g, p, q, b, d_points, st, points_ready, chunk)) return rc;
+  if (chunk && !chunk->last) return 0;  // later point-range chunks continue in the same buckets
+  const uint4* group_w = nullptr;
+  if (int rc = pipe_reduce(g, p, q, b, st, arena, chunk, &group_w)) return rc;
+  return pipe_finalize(g, p, q, group_w, d_out, st, arena);
 }
 
 // ---- single MSM over device pointers ------------------------------------------------------------------------------
@@ -285,7 +333,52 @@ int msm_dev(Ctx& g, const void* d_bases, const void* d_scalars, size_t n, unsign
   const uint64_t pass_pts = std::max<uint64_t>(E.pass_entries_max / W, 1);
   int rc = arena.acquire(st);
   if (rc) return rc;
-  if (n <= pass_pts) {
+  const bool overlap = E.msm_overlap && !g2 && !arena_p && !g.profiling && n >= (size_t(1) << 20) && n <= pass_pts && W >= 6;
+  if (overlap) {
+    // Three window ranges on three streams. The sort stages (HBM / L2 bound) of a range and the latency-bound tail of
+    // its reduction hide behind another range's accumulation (integer-pipe bound); the first range is ONE window so
+    // that an accumulation is running ~2 ms into the call. The side streams have high priority: their short CTAs take
+    // the SM slots an accumulation frees before its own next wave does.
+    const int Wn = (int)W, cut[4] = {0, 1, 1 + (Wn - 1) / 2, Wn};
+    cudaStream_t ss[3] = {st, g.split_stream[0], g.split_stream[1]};
+    Arena* as[3] = {&arena, &g.split_arena[0], &g.split_arena[1]};
+    uint4* gw_all = nullptr;
+    CU(cudaMallocAsync((void**)&gw_all, (size_t)Wn * 192, st));
+    CU(cudaEventRecord(g.ev_split[0], st));              // inputs of this call are ordered behind st's earlier work
+    Plan plans[3];
+    for (int r = 0; r < 3 && rc == 0; r++) {
+      rc = make_plan(g, plans[r], 1, (uint32_t)n, 0, 1, c, 0, flags, false, cut[r], cut[r + 1]);
+      if (rc) break;
+      if (r > 0) {
+        CU(cudaStreamWaitEvent(ss[r], g.ev_split[0], 0));
+        rc = as[r]->acquire(ss[r]);
+        if (rc) break;
+      }
+      const MsmGeom q = plans[r].geo;
+      PipeBufs b;
+      // staggered: range r is sorted WHILE range r-1 accumulates (its sort waits for the sort of r-1 to finish, i.e.
+      // for that accumulation to start); started together, all three sorts would run up front with nothing to hide behind
+      if (r > 0) CU(cudaStreamWaitEvent(ss[r], g.ev_split[3], 0));
+      rc = pipe_sort(g, plans[r], q, (const uint32_t*)d_scalars, ss[r], *as[r], nullptr, b);
+      if (rc == 0 && r < 2) CU(cudaEventRecord(g.ev_split[3], ss[r]));
+      if (rc == 0) rc = pipe_accumulate(g, plans[r], q, b, (const uint4*)d_bases, ss[r], points_ready, nullptr);
+      const uint4* gw = nullptr;
+      if (rc == 0) rc = pipe_reduce(g, plans[r], q, b, ss[r], *as[r], nullptr, &gw);
+      if (rc) break;
+      CU(cudaMemcpyAsync(gw_all + 12 * (size_t)cut[r], gw, (size_t)q.groups * 192, cudaMemcpyDeviceToDevice, ss[r]));
+      if (r > 0) {
+        rc = as[r]->release(ss[r]);
+        if (rc) break;
+        CU(cudaEventRecord(g.ev_split[r], ss[r]));
+        CU(cudaStreamWaitEvent(st, g.ev_split[r], 0));
+      }
+    }
+    if (rc == 0) {
+      note_geometry(g, plans[1], (uint64_t)n * W, W << (c - 1));
+      rc = pipe_finalize(g, plans[0], plans[0].geo, gw_all, (uint4*)d_out, st, arena);
+    }
+    cudaFreeAsync(gw_all, st);
+  } else if (n <= pass_pts) {
     Plan p;
     rc = make_plan(g, p, 1, (uint32_t)n, 0, 1, c, 0, flags, g2);
     if (rc) return rc;
@@ -390,15 +483,45 @@ int msm_host_enqueue(Ctx& g, const uint64_t* bases_xy, const uint64_t* scalars, 
     CU(cudaEventRecord(g.chunk_ev[2 * k + 1], g.copy_stream));
   }
   g.marks.clear();
-  if (int rc = g.arena.acquire(g.stream)) return rc;
-  for (int k = 0; k < C; k++) {
-    CU(cudaStreamWaitEvent(g.stream, g.chunk_ev[2 * k], 0));
-    ChunkCtl ctl{(uint32_t)cut[k], d_buckets, k == C - 1};
-    int rc = run_pipeline(g, plans[k], (const uint32_t*)d_s + 8 * cut[k], d_b, g.d_result, g.stream, g.chunk_ev[2 * k + 1],
-                          g.arena, &ctl);
-    if (rc) return rc;
+  if (!E.msm_overlap || g.profiling) {
+    if (int rc = g.arena.acquire(g.stream)) return rc;
+    for (int k = 0; k < C; k++) {
+      CU(cudaStreamWaitEvent(g.stream, g.chunk_ev[2 * k], 0));
+      ChunkCtl ctl{(uint32_t)cut[k], d_buckets, k == C - 1};
+      int rc = run_pipeline(g, plans[k], (const uint32_t*)d_s + 8 * cut[k], d_b, g.d_result, g.stream, g.chunk_ev[2 * k + 1],
+                            g.arena, &ctl);
+      if (rc) return rc;
+    }
+    return g.arena.release(g.stream);
   }
-  return g.arena.release(g.stream);
+  // Chunks alternate between the main stream and a high-priority side stream: the sort of chunk k+1 (memory bound) runs
+  // next to the accumulation of chunk k (integer-pipe bound). The accumulations themselves stay in chunk order -- they
+  // update the same persistent buckets -- through the ev_split events.
+  CU(cudaEventRecord(g.ev_split[2], g.stream));          // the bucket array is zeroed
+  CU(cudaStreamWaitEvent(g.split_stream[0], g.ev_split[2], 0));
+  note_geometry(g, plans[C - 1], (uint64_t)n * W, B);
+  for (int k = 0; k < C; k++) {
+    cudaStream_t s = (k & 1) ? g.split_stream[0] : g.stream;
+    Arena& ar = (k & 1) ? g.split_arena[0] : g.arena;
+    CU(cudaStreamWaitEvent(s, g.chunk_ev[2 * k], 0));
+    if (int rc = ar.acquire(s)) return rc;
+    ChunkCtl ctl{(uint32_t)cut[k], d_buckets, k == C - 1};
+    MsmGeom q = plans[k].geo;
+    q.ref_base = ctl.ref_base;
+    PipeBufs b;
+    if (int rc = pipe_sort(g, plans[k], q, (const uint32_t*)d_s + 8 * cut[k], s, ar, &ctl, b)) return rc;
+    if (k > 0) CU(cudaStreamWaitEvent(s, g.ev_split[(k - 1) & 1], 0));   // the previous chunk's buckets are final
+    if (int rc = pipe_accumulate(g, plans[k], q, b, d_b, s, g.chunk_ev[2 * k + 1], &ctl)) return rc;
+    if (k == C - 1) {
+      const uint4* gw = nullptr;
+      if (int rc = pipe_reduce(g, plans[k], q, b, s, ar, &ctl, &gw)) return rc;
+      if (int rc = pipe_finalize(g, plans[k], q, gw, g.d_result, s, ar)) return rc;
+    }
+    if (int rc = ar.release(s)) return rc;
+    CU(cudaEventRecord(g.ev_split[k & 1], s));
+  }
+  if ((C - 1) & 1) CU(cudaStreamWaitEvent(g.stream, g.ev_split[(C - 1) & 1], 0));   // the result is ordered into g.stream
+  return 0;
 }
 
 // ---- shared-base batch ------------------------------------------------------------------------------------------------

@@ -107,6 +107,7 @@ struct MsmGeom {
   int batch;                    // 1: shared-base batch (group = row, ref = w*cols + j); 0: single (group = w, ref = j)
   int mont;                     // scalars are Montgomery-form Fr
   uint32_t ref_base;            // single MSM processed in point-range chunks: entry ref = ref_base + col
+  int w_lo, w_hi;               // single MSM: the windows [w_lo, w_hi) this pass sorts (group = w - w_lo); batch: 0, W
 };
 
 // Translation units that only need the device functions of this header (engine_g2.cu, engine_pairing.cu) define
@@ -145,11 +146,11 @@ __global__ void __launch_bounds__(256) k_digits(const uint32_t* __restrict__ sca
     }
     if ((s[0] | s[1] | s[2] | s[3] | s[4] | s[5] | s[6] | s[7]) == 0) continue;  // zero scalar: nothing to add
     DigitIter it(s, g.c);
-    for (int w = 0; w < g.W; w++) {
+    for (int w = 0; w < g.w_hi; w++) {       // the carry chain starts at window 0 whatever the range
       int32_t d = it.next(w == g.W - 1);
-      if (d == 0 || (only_window >= 0 && w != only_window)) continue;
+      if (d == 0 || w < g.w_lo || (only_window >= 0 && w != only_window)) continue;
       uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-      uint32_t group = g.batch ? row : (uint32_t)w;
+      uint32_t group = g.batch ? row : (uint32_t)(w - g.w_lo);
       uint32_t bucket = group * g.nb + (mag - 1);
       if (SCATTER) {
         uint32_t ref = g.batch ? (uint32_t)w * g.cols + col : g.ref_base + col;
@@ -360,9 +361,15 @@ __global__ void __launch_bounds__(ACC_THREADS, 3)
 // `first + i + 2^r` (if it belongs to the same bucket). After ceil(log2(#heads)) rounds heads[first] holds the sum;
 // k_fixup_final adds it to buckets[b]. Heavy buckets (skewed witnesses: most scalars 0/1; degenerate top
 // windows) therefore cost log-depth instead of a sequential walk over thousands of partial sums.
+// `need` (one word per round, zeroed by the host; may be null): rounds are ENQUEUED for the largest bucket that could
+// exist (log2 of n / K), but with well-spread scalars no bucket has more than a few heads. Round r tells round r+1 whether
+// any bucket still has a partner at distance 2^(r+1); rounds that are not needed return after one load (17 launches:
+// 1.17 ms -> ~0.2 ms per pass; it is paid once per point-range chunk of a host-facing MSM).
 __global__ void __launch_bounds__(128) k_fixup_round(const uint32_t* __restrict__ bucket_start, uint32_t B,
                                                      uint32_t K, uint32_t round, uint4* __restrict__ heads,
-                                                     const int32_t* __restrict__ head_bucket) {
+                                                     const int32_t* __restrict__ head_bucket,
+                                                     uint32_t* __restrict__ need) {
+  if (need && round > 0 && __ldcg(need + round) == 0) return;
   const uint32_t M = bucket_start[B];
   const uint64_t S = ((uint64_t)M + K - 1) / K;
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,7 +381,10 @@ __global__ void __launch_bounds__(128) k_fixup_round(const uint32_t* __restrict_
   const uint64_t stride = 1ull << round;
   if (i & (2 * stride - 1)) return;
   const uint64_t u = t + stride;
-  if (u >= S || u * K >= bucket_start[hb + 1]) return;  // partner is not a head of this bucket
+  const uint32_t bucket_end = bucket_start[hb + 1];
+  if (u >= S || u * K >= bucket_end) return;  // partner is not a head of this bucket
+  const uint64_t u2 = t + 2 * stride;
+  if (need && u2 < S && u2 * K < bucket_end) need[round + 1] = 1u;   // some bucket has a head 2^(r+1) further on
   Xyzz acc, h;
   load_xyzz(acc, heads + 12 * t);
   load_xyzz(h, heads + 12 * u);
