@@ -124,13 +124,19 @@ class MippProofG1:
             # debug_assert cross-check (:133-134) -- executed, like there
             evals = polynomial_evaluations_from_transcript(out.xs_inv)
             ev_w = curve.scalars_to_words(evals, mont=True)
-            c_h = msm_g2.msm_unchecked(h_key, ev_w)
-            assert np.array_equal(c_h, out.final_h), "debug_assert!(c.h_product == final_h) (src/mipp.rs:134)"
+            # The reference computes commit_g2 (its debug_assert cross-check, :133-134) and then open_g1 (:144); neither
+            # feeds the other, and the challenges rs do not depend on commit_g2: open_g1 is STARTED first (it runs on the
+            # library's side streams) and commit_g2 runs next to it.
+            pending = None
             if powers_of_g_levels is not None:
                 m = len(out.xs_inv)
                 out.rs = [challenge(b"random_point", []) % fr.R for _ in range(m)]          # :138-141
                 rs_w = curve.scalars_to_words(out.rs, mont=True) if m else np.zeros((0, 4), dtype=np.uint64)
-                out.pst_proof_h = multilinear_pc.open_g1(powers_of_g_levels, ev_w, rs_w)   # :144
+                pending = multilinear_pc.open_g1_begin(powers_of_g_levels, ev_w, rs_w)     # :144
+            c_h = msm_g2.msm_unchecked(h_key, ev_w)
+            assert np.array_equal(c_h, out.final_h), "debug_assert!(c.h_product == final_h) (src/mipp.rs:134)"
+            if pending is not None:
+                out.pst_proof_h = pending.wait()
         return out
 
 

@@ -85,3 +85,8 @@ def open_g1(level_bases_g: Sequence[np.ndarray], evals, point, mont: bool = True
 def open_begin(level_bases_h: Sequence[np.ndarray], evals, point, mont: bool = True) -> PendingOpen:
     """`MultilinearPC::open` started without waiting: the caller overlaps it with other work and calls `.wait()`."""
     return _open(level_bases_h, evals, point, mont, True, asynchronous=True)
+
+
+def open_g1_begin(level_bases_g: Sequence[np.ndarray], evals, point, mont: bool = True) -> PendingOpen:
+    """`open_g1` started without waiting (tb200_pst_open_g1_begin)."""
+    return _open(level_bases_g, evals, point, mont, False, asynchronous=True)
