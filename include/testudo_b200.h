@@ -208,6 +208,10 @@ int tb200_host_unregister(void* h_ptr);
 /* ---- sqrt_pst scalar work on the device (Fr values in ark Montgomery form) ---------------
  * chis_out[i] = prod_j (bit(i, m-1-j) ? b[j] : 1 - b[j]), i < 2^m  -- `Polynomial::get_chi_i`, src/sqrt_pst.rs:152-166 */
 int tb200_fr_chis(const uint64_t* b, size_t m, uint64_t* chis_out);
+/* out[i] = prod_{j : bit(i, m-1-j) set} b[j], i < 2^m -- `MippProof::polynomial_evaluations_from_transcript(cs_inv)`
+ * (src/mipp.rs:159-180) with b = cs_inv: the evaluations of the structured polynomial behind final_h, produced directly in
+ * ark's Montgomery form for commit_g2 / open_g1 (src/mipp.rs:128-144). */
+int tb200_fr_subset_products(const uint64_t* b, size_t m, uint64_t* out);
 /* out[j] = sum_i Z[j*cols + i] * v[i], j < rows -- `get_q` (src/sqrt_pst.rs:81-101) with Z[(j << m_col) | i], v = chis,
  * and `eval` (src/sqrt_pst.rs:105-115) with rows = 1. HBM-bound: 32 B per multiply-add. */
 int tb200_fr_matvec(const uint64_t* Z, size_t rows, size_t cols, const uint64_t* v, uint64_t* out);

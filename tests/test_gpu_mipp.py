@@ -130,3 +130,17 @@ def test_mipp_round_entry_points_agree(engine):
     finally:
         engine.tb200_mipp_g1_end(ha)
         engine.tb200_mipp_g2_end(hh)
+
+
+@pytest.mark.parametrize("m", [0, 1, 2, 5, 13])
+def test_structured_polynomial_on_device_equals_the_reference_loop(engine, m):
+    """`polynomial_evaluations_from_transcript` (src/mipp.rs:159-180) computed by tb200_fr_subset_products, in ark's
+    Montgomery form, against the integer loop."""
+    from testudo_b200 import fr
+
+    cs_inv = o.rand_scalars(m, 3100 + m)
+    want = mipp.polynomial_evaluations_from_transcript(cs_inv)
+    got = fr.from_mont_words(mipp.polynomial_evaluations_words(cs_inv))
+    assert got == want
+    if m:
+        assert want[1] == cs_inv[m - 1] and want[1 << (m - 1)] == cs_inv[0]      # bit j from the lsb selects cs_inv[m-j-1]

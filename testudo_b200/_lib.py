@@ -89,6 +89,7 @@ SIGNATURES = {
     "tb200_dev_download": (c_int, [c_void_p, c_void_p, c_size_t]),
     "tb200_stream_sync": (c_int, []),
     "tb200_fr_chis": (c_int, [c_void_p, c_size_t, c_void_p]),
+    "tb200_fr_subset_products": (c_int, [c_void_p, c_size_t, c_void_p]),
     "tb200_fr_matvec": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p]),
     "tb200_fr_matvec_dev": (c_int, [c_void_p, c_size_t, c_size_t, c_void_p, c_void_p, c_void_p]),
     "tb200_g1_sum": (c_int, [c_void_p, c_size_t, c_void_p]),

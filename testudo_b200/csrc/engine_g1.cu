@@ -968,9 +968,7 @@ int tb200_compress_g1(uint64_t* vec_xy, size_t split, const uint64_t scaler[4], 
 }
 
 // ---- sqrt_pst scalar work on the device -------------------------------------------------------------------------------
-int tb200_fr_chis(const uint64_t* b, size_t m, uint64_t* chis_out) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (need_ready()) return TB200_E_STATE;
+static int fr_chis_locked(const uint64_t* b, size_t m, uint64_t* chis_out, int subset) {
   if (!chis_out || (m && !b) || m > 28) return fail(TB200_E_ARG, "bad arguments (m = %zu)", m);
   Ctx& g = primary();
   CU(cudaSetDevice(g.device));
@@ -979,12 +977,22 @@ int tb200_fr_chis(const uint64_t* b, size_t m, uint64_t* chis_out) {
   CU(cudaMallocAsync((void**)&d_b, std::max<size_t>(m, 1) * 32, g.stream));
   CU(cudaMallocAsync((void**)&d_o, n * 32, g.stream));
   if (m) CU(cudaMemcpyAsync(d_b, b, m * 32, cudaMemcpyHostToDevice, g.stream));
-  LAUNCH(k_fr_chis, cdiv(n, 128), 128, g.stream, d_b, (uint32_t)m, d_o);
+  LAUNCH(k_fr_chis, cdiv(n, 128), 128, g.stream, d_b, (uint32_t)m, d_o, subset);
   CU(cudaMemcpyAsync(chis_out, d_o, n * 32, cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
   cudaFreeAsync(d_b, g.stream);
   cudaFreeAsync(d_o, g.stream);
   return 0;
+}
+int tb200_fr_chis(const uint64_t* b, size_t m, uint64_t* chis_out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  return fr_chis_locked(b, m, chis_out, 0);
+}
+int tb200_fr_subset_products(const uint64_t* b, size_t m, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  return fr_chis_locked(b, m, out, 1);
 }
 static int fr_matvec_enqueue(Ctx& g, const void* d_Z, size_t rows, size_t cols, const void* d_v, void* d_out, cudaStream_t st) {
   if (rows >= (1ull << 31) || cols >= (1ull << 31)) return fail(TB200_E_LIMIT, "matrix too large");

@@ -669,7 +669,10 @@ __global__ void __launch_bounds__(128) k_compress_fr(uint32_t* __restrict__ y, u
 // sqrt_pst scalar work: chi products, q = Z * chi, dot product -- Fr, Montgomery form
 // ------------------------------------------------------------------------------------------------------------
 // chis[i] = prod_j (bit_{m-1-j}(i) ? b[j] : 1 - b[j])   (Polynomial::get_chi_i, src/sqrt_pst.rs:152-166)
-__global__ void __launch_bounds__(128) k_fr_chis(const uint32_t* __restrict__ b, uint32_t m, uint32_t* __restrict__ out) {
+// subset != 0: the clear bits contribute 1 instead of 1 - b[j]: out[i] = prod_{j : bit_{m-1-j}(i)} b[j], the structured
+// polynomial of MIPP (`polynomial_evaluations_from_transcript`, src/mipp.rs:159-180, with b = cs_inv)
+__global__ void __launch_bounds__(128) k_fr_chis(const uint32_t* __restrict__ b, uint32_t m, uint32_t* __restrict__ out,
+                                                 int subset) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (1u << m)) return;
   uint32_t prod[8], one[8];
@@ -679,7 +682,10 @@ __global__ void __launch_bounds__(128) k_fr_chis(const uint32_t* __restrict__ b,
     uint32_t f[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) f[k] = b[8 * j + k];
-    if (!((i >> (m - j - 1)) & 1)) mod_sub<FrParams>(f, one, f);
+    if (!((i >> (m - j - 1)) & 1)) {
+      if (subset) continue;
+      mod_sub<FrParams>(f, one, f);
+    }
     mont_mul<FrParams>(prod, prod, f);
   }
 #pragma unroll
