@@ -94,8 +94,11 @@ static int make_plan(const Ctx& g, Plan& p, uint32_t rows, uint32_t cols, long l
   // Fan-in 32 at level 0 (throughput-bound: millions of buckets). The levels above it of a SINGLE MSM hold few
   // elements and are latency-bound (2L - 1 sequential additions + log2(ell) doublings per thread): fan-in 8 there
   // (measured at 2^24, c = 20: 3.5 -> 1.9 ms for the upper levels). Batches keep 32: thousands of rows fill the GPU.
+  // Small single MSMs (G2 always: sqrt(n)-sized, ~50 us per addition) are latency-bound at level 0 as well: with
+  // fan-in 8 everywhere a 2^13-point G2 MSM reduces in 54 sequential group operations instead of 99.
+  const bool small_single = !batch && p.B < (1ull << 17);
   for (uint32_t n = q.nb; n > 1;) {
-    uint32_t L = std::min<uint32_t>(n, (batch || p.Ls.empty()) ? 32 : 8);
+    uint32_t L = std::min<uint32_t>(n, (batch || (p.Ls.empty() && !small_single)) ? 32 : 8);
     p.Ls.push_back(L);
     n /= L;
   }
