@@ -262,6 +262,11 @@ void tb200_set_small_msm_max(int n);
  * SM), so the side streams' CTAs only displace accumulation CTAs; kept as an option, off by default.
  * Ignored while stage profiling is on. */
 void tb200_set_msm_overlap(int enabled);
+/* host-facing single MSMs of >= 2^23 points per GPU are uploaded in point-range chunks. pace != 0 (default): chunk k is
+ * uploaded once chunk k-2 has been accumulated (double buffering) instead of as early as the copy engine allows, so that
+ * GPUs behind a fast host link do not take bandwidth from the ones behind a slow link up front. `sixteenths`: the chunk
+ * sizes in sixteenths of the points (count <= 16, sum 16); count = 0 restores the built-in schedule. */
+int tb200_set_host_upload(int pace, const int* sixteenths, int count);
 /* integer-pipe microbenchmark: runs `iters` dependent-chain iterations of wide MACs on every SM and returns the
  * achieved 32x32->64 multiply-accumulates per second in *out_macs_per_s (kind: 0 = IMAD.WIDE.U32 reg-reg,
  * 1 = IMAD (32-bit lo), 2 = full Fq Montgomery multiplications per second). */

@@ -106,6 +106,7 @@ SIGNATURES = {
     "tb200_set_commit_pipeline": (None, [c_int]),
     "tb200_set_small_msm_max": (None, [c_int]),
     "tb200_set_msm_overlap": (None, [c_int]),
+    "tb200_set_host_upload": (c_int, [c_int, ctypes.POINTER(c_int), c_int]),
     "tb200_int_pipe_peak": (c_int, [c_int, c_int, ctypes.POINTER(ctypes.c_double)]),
     "tb200_test_fq_mul": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "tb200_test_fq_addsub": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),

@@ -137,6 +137,9 @@ struct Engine {
   size_t host_chunk_min = size_t(1) << 21;  // host-facing single MSMs: chunked upload/compute overlap from here
   size_t shard_min = size_t(1) << 18;       // host-facing single MSMs are sharded over the GPUs from ndev * this
   int pairing_coop_max = 2048;              // Miller loops: CTA-per-pair up to this many pairs, lanes-per-pair above
+  int host_upload_pace = 1;                 // host-facing single MSMs: upload chunk k once chunk k-2 is accumulated
+  int host_chunk_count = 0;                 // tuning: chunk sizes in sixteenths of the points (0 = built-in schedule)
+  int host_chunk_frac[16] = {};
   int msm_overlap = 0;                      // large single MSMs: window ranges / chunk sorts on side streams (engine_g1.cu);
                                             // measured neutral (84.2 -> 84.0 ms resident, 92.6 -> 91.4 ms from host): opt-in
   int small_msm_max = 1024;                  // single G1 MSMs of up to this many points run in one CTA (kernels_small.cuh)
@@ -213,8 +216,9 @@ int msm_dev(Ctx& g, const void* d_bases, const void* d_scalars, size_t n, unsign
             cudaEvent_t points_ready = nullptr, Arena* arena = nullptr, bool finish = true, bool g2 = false);
 // host-facing single MSM of THIS device's share: uploads (chunked, overlapped), computes, leaves the affine result at
 // g.d_result (device) -- the caller decides whether to download or all-gather it. Enqueue only; no synchronisation.
+// `sharing` = the number of GPUs that pull from the same host during this call (picks the upload chunk schedule)
 int msm_host_enqueue(Ctx& g, const uint64_t* bases_xy, const uint64_t* scalars, size_t n, unsigned flags,
-                     std::vector<void*>& to_free);
+                     std::vector<void*>& to_free, int sharing = 1);
 // shared-base batch over device scalars; rows are processed in chunks that respect the per-pass limits
 int batch_dev(Ctx& g, const uint4* table, int c, int W, uint32_t srs_n, const uint32_t* d_scalars, size_t rows,
               size_t cols, long long rs, long long cs, unsigned flags, uint4* d_out, cudaStream_t st);

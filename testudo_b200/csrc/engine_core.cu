@@ -511,6 +511,19 @@ void tb200_set_pass_entries_max(uint64_t entries) {
 void tb200_set_shard_min(size_t units) { E.shard_min = units ? units : (size_t(1) << 18); }
 void tb200_set_commit_pipeline(int enabled) { E.commit_pipeline = enabled ? 1 : 0; }
 void tb200_set_msm_overlap(int enabled) { E.msm_overlap = enabled ? 1 : 0; }
+int tb200_set_host_upload(int pace, const int* sixteenths, int count) {
+  if (count < 0 || count > 16 || (count && !sixteenths)) return fail(TB200_E_ARG, "at most 16 chunks");
+  int sum = 0;
+  for (int i = 0; i < count; i++) {
+    if (sixteenths[i] < 1) return fail(TB200_E_ARG, "chunk sizes are positive sixteenths");
+    sum += sixteenths[i];
+  }
+  if (count && sum != 16) return fail(TB200_E_ARG, "chunk sizes must add up to 16 sixteenths (got %d)", sum);
+  E.host_upload_pace = pace ? 1 : 0;
+  E.host_chunk_count = count;
+  for (int i = 0; i < count; i++) E.host_chunk_frac[i] = sixteenths[i];
+  return 0;
+}
 void tb200_set_small_msm_max(int n) { E.small_msm_max = n < 0 ? 1024 : std::min(n, 1024); }
 
 // ---- device / pinned host buffers for hosts without a CUDA runtime of their own ------------------------------------------
@@ -689,7 +702,7 @@ int tb200_msm_g1(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, un
     rc = for_each_device([&](Ctx& g) {
       size_t lo, hi;
       shard_range(n, nd, g.slot, &lo, &hi);
-      return msm_host_enqueue(g, bases_xy + 12 * lo, scalars + 4 * lo, hi - lo, flags, to_free[g.slot]);
+      return msm_host_enqueue(g, bases_xy + 12 * lo, scalars + 4 * lo, hi - lo, flags, to_free[g.slot], nd);
     });
     if (rc == 0) {
       std::vector<void*> send(nd), recv(nd);

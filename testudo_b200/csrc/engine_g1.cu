@@ -420,7 +420,7 @@ int msm_dev(Ctx& g, const void* d_bases, const void* d_scalars, size_t n, unsign
 // reduction / finalisation run once after the last chunk. Without it the accumulation waits for the whole 96 n byte
 // base upload (~37 ms at 2^24 over PCIe Gen5) with the GPU idle.
 int msm_host_enqueue(Ctx& g, const uint64_t* bases_xy, const uint64_t* scalars, size_t n, unsigned flags,
-                     std::vector<void*>& to_free) {
+                     std::vector<void*>& to_free, int sharing) {
   CU(cudaSetDevice(g.device));
   if (n >= (size_t(1) << 31)) return fail(TB200_E_LIMIT, "n = %zu exceeds 2^31 - 1 points per call", n);
   if (n == 0) return msm_dev(g, g.d_result, g.d_result, 0, flags, g.d_result, g.stream, nullptr, nullptr, false);
@@ -447,11 +447,19 @@ int msm_host_enqueue(Ctx& g, const uint64_t* bases_xy, const uint64_t* scalars, 
   // pull 23-35 GB/s each instead of 55, profiles/r02_h2d_probe_8gpu.txt) and everything after the last byte has
   // arrived -- the last chunk's sort and accumulation -- is exposed. Below 2^23 points four chunks keep the number of
   // pipeline passes (fix-up rounds, launch gaps) down.
-  static const int big[] = {1, 2, 4, 4, 3, 1, 1}, small[] = {2, 4, 4, 6};
+  // With four or more GPUs pulling from one host the call IS upload-bound on this box (measured at 8 GPUs, 2^24 points
+  // each: 122.7 ms with the schedule above, 111.9 with ten chunks, 107.7 with sixteen equal ones, all paced): equal
+  // sixteenths keep every upload behind a compute step of the same size and the exposed tail at one sixteenth. Alone
+  // on the link the extra passes cost 2.8 ms (95.4 vs 92.6 ms), so one or two GPUs keep the seven-chunk schedule.
+  static const int big[] = {1, 2, 4, 4, 3, 1, 1}, small[] = {2, 4, 4, 6}, shared[] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
   const bool many = n >= (size_t(1) << 23);
-  const int C = many ? 7 : 4;
-  const int* frac = many ? big : small;
-  constexpr int CMAX = 7;
+  constexpr int CMAX = 16;
+  int C = many ? (sharing >= 4 ? 16 : 7) : 4;
+  const int* frac = many ? (sharing >= 4 ? shared : big) : small;
+  if (many && E.host_chunk_count > 0) {   // tuning hook: tb200_set_host_upload
+    C = E.host_chunk_count;
+    frac = E.host_chunk_frac;
+  }
   const size_t unit = ((n + 15) / 16 + 31) & ~size_t(31);
   size_t cut[CMAX + 1] = {0};
   for (int k = 0, acc = 0; k < C; k++) {
@@ -471,32 +479,42 @@ int msm_host_enqueue(Ctx& g, const uint64_t* bases_xy, const uint64_t* scalars, 
   CU(cudaMemsetAsync(d_buckets, 0, B * 192, g.stream));
   CU(cudaEventRecord(g.ev_points, g.stream));  // allocations exist
   CU(cudaStreamWaitEvent(g.copy_stream, g.ev_points, 0));
-  while (g.chunk_ev.size() < 2 * (size_t)C) {
+  while (g.chunk_ev.size() < 3 * (size_t)C) {
     cudaEvent_t e;
     CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     g.chunk_ev.push_back(e);
   }
-  for (int k = 0; k < C; k++) {
+  // PACED uploads (double buffering): chunk k is uploaded once chunk k-2 has been accumulated, not as early as the copy
+  // engine could. A GPU with a fast host link otherwise drains its whole 2 GiB up front and takes bandwidth from the
+  // GPUs behind a slower link exactly when those are the ones the call waits for (8 GPUs of this box: 35 vs 23 GB/s
+  // when all pull at once, but 29 GB/s for the slow four once the fast four pull at their compute rate only).
+  auto upload = [&](int k, bool pace) -> int {
     const size_t lo = cut[k], cnt = cut[k + 1] - cut[k];
+    if (pace && k >= 2) CU(cudaStreamWaitEvent(g.copy_stream, g.chunk_ev[2 * C + k - 2], 0));
     CU(cudaMemcpyAsync((char*)d_s + lo * 32, (const char*)scalars + lo * 32, cnt * 32, cudaMemcpyHostToDevice,
                        g.copy_stream));
     CU(cudaEventRecord(g.chunk_ev[2 * k], g.copy_stream));
     CU(cudaMemcpyAsync((char*)d_b + lo * 96, (const char*)bases_xy + lo * 96, cnt * 96, cudaMemcpyHostToDevice,
                        g.copy_stream));
     CU(cudaEventRecord(g.chunk_ev[2 * k + 1], g.copy_stream));
-  }
+    return 0;
+  };
   g.marks.clear();
   if (!E.msm_overlap || g.profiling) {
     if (int rc = g.arena.acquire(g.stream)) return rc;
     for (int k = 0; k < C; k++) {
+      if (int rc = upload(k, E.host_upload_pace != 0)) return rc;
       CU(cudaStreamWaitEvent(g.stream, g.chunk_ev[2 * k], 0));
       ChunkCtl ctl{(uint32_t)cut[k], d_buckets, k == C - 1};
       int rc = run_pipeline(g, plans[k], (const uint32_t*)d_s + 8 * cut[k], d_b, g.d_result, g.stream, g.chunk_ev[2 * k + 1],
                             g.arena, &ctl);
       if (rc) return rc;
+      CU(cudaEventRecord(g.chunk_ev[2 * C + k], g.stream));   // chunk k is in the buckets
     }
     return g.arena.release(g.stream);
   }
+  for (int k = 0; k < C; k++)   // the overlap variant orders its accumulations itself: uploads as early as possible
+    if (int rc = upload(k, false)) return rc;
   // Chunks alternate between the main stream and a high-priority side stream: the sort of chunk k+1 (memory bound) runs
   // next to the accumulation of chunk k (integer-pipe bound). The accumulations themselves stay in chunk order -- they
   // update the same persistent buckets -- through the ev_split events.
