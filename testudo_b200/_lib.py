@@ -76,6 +76,7 @@ SIGNATURES = {
     "tb200_gt_product_final_exp_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "tb200_mipp_pairing_cross": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "tb200_set_pairing_coop_max": (None, [c_int]),
+    "tb200_set_pairing_team": (None, [c_int]),
     "tb200_mipp_cross_all": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "tb200_gt_pow": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
     "tb200_pst_open_g1": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_uint, c_void_p]),

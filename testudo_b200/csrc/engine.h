@@ -136,12 +136,14 @@ struct Engine {
   int forced_c = 0;
   size_t host_chunk_min = size_t(1) << 21;  // host-facing single MSMs: chunked upload/compute overlap from here
   size_t shard_min = size_t(1) << 18;       // host-facing single MSMs are sharded over the GPUs from ndev * this
+  int pairing_team = 0;                     // lanes of a cooperative Fq12 team: 0 = by size (engine_pairing.cu), 32 or 64 forced
   int pairing_coop_max = 2048;              // Miller loops: CTA-per-pair up to this many pairs, lanes-per-pair above
   int host_upload_pace = 1;                 // host-facing single MSMs: upload chunk k once chunk k-2 is accumulated
   int host_chunk_count = 0;                 // tuning: chunk sizes in sixteenths of the points (0 = built-in schedule)
   int host_chunk_frac[16] = {};
   int msm_overlap = 0;                      // large single MSMs: window ranges / chunk sorts on side streams (engine_g1.cu);
                                             // measured neutral (84.2 -> 84.0 ms resident, 92.6 -> 91.4 ms from host): opt-in
+  int mipp_cross_small_max = 64;            // tb200_mipp_cross_all: Straus path for the cross MSMs up to this many points
   int small_msm_max = 1024;                  // single G1 MSMs of up to this many points run in one CTA (kernels_small.cuh)
   int commit_pipeline = 0;                  // tb200_sqrt_pst_commit: Miller loops of a row chunk next to the next chunk's MSMs
   int acc_mode = 0;                         // 0 / 4: fused-Y3 XYZZ segments (default); 3: plain CIOS products

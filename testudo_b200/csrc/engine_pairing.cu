@@ -55,21 +55,26 @@ int pairing_products(Ctx& g, const uint4* d_g1, const uint4* d_g2, uint32_t n, u
   if (mark(g, st, "pairing_begin")) return 1;
   // below ~2 waves of resident CTAs one CTA per pair (latency-bound); above, one thread per pair
   const bool coop = n <= (uint32_t)E.pairing_coop_max;
+  // Team size of the cooperative kernels (measured, scripts/time_pairing_team.py): two warps are faster while the chain's
+  // LATENCY counts (Miller 1.77 vs 2.1 ms for <= 256 pairs, final exponentiation 1.82 vs 1.92 ms); one warp per pair
+  // doubles the resident pairs and wins once the Miller stage is throughput-bound (1024 pairs: 3.6 vs 5.0 ms, 2048: 6.8 vs 8.8).
+  const int miller_team = E.pairing_team ? E.pairing_team : (n > 512 ? 32 : 64);
+  const int chain_team = E.pairing_team ? E.pairing_team : 64;
   if (d_gt_in) CU(cudaMemcpyAsync(buf_a, d_gt_in, (size_t)n * 576, cudaMemcpyDeviceToDevice, st));
-  else if (coop) LAUNCH(k_miller_coop, n, W12_THREADS, st, d_g1, d_g2, xor_mask, buf_a);
+  else if (coop) LAUNCH(k_miller_coop, n, miller_team, st, d_g1, d_g2, xor_mask, buf_a);
   else LAUNCH(k_miller, cdiv(n, 32), 32, st, d_g1, d_g2, n, xor_mask, buf_a);
   if (after_miller) CU(cudaEventRecord(after_miller, st));
   if (mark(g, st, "miller")) return 1;
   uint4 *cur = buf_a, *nxt = buf_b;
   while (len > 1) {
     const uint32_t m = cdiv(len, FQ12_FAN);
-    if ((uint64_t)m * segs <= 4096) LAUNCH(k_fq12_prod_level_coop, dim3(m, segs), W12_THREADS, st, cur, len, m, nxt);
+    if ((uint64_t)m * segs <= 4096) LAUNCH(k_fq12_prod_level_coop, dim3(m, segs), chain_team, st, cur, len, m, nxt);
     else LAUNCH(k_fq12_prod_level, dim3(cdiv(m, 32), segs), 32, st, cur, len, m, nxt);
     std::swap(cur, nxt);
     len = m;
   }
   if (mark(g, st, "gt_product")) return 1;
-  if (final_exp) LAUNCH(k_final_exp, segs, W12_THREADS, st, cur, d_out);
+  if (final_exp) LAUNCH(k_final_exp, segs, chain_team, st, cur, d_out);
   else CU(cudaMemcpyAsync(d_out, cur, (size_t)segs * 576, cudaMemcpyDeviceToDevice, st));
   if (mark(g, st, "final_exp")) return 1;
   CU(cudaFreeAsync(buf_a, st));
@@ -337,10 +342,15 @@ int tb200_mipp_cross_all(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_u_l[12
     cudaError_t e = cudaStreamWaitEvent(h->st, g.ev_pair, 0);  // later G2 folds rewrite h: behind this round's Miller kernel
     if (e != cudaSuccess) rc = fail((int)e, "event wait failed: %s", cudaGetErrorString(e));
   }
-  // cross MSMs as in tb200_mipp_g1_cross
+  // cross MSMs as in tb200_mipp_g1_cross. They are off the round's critical path (the Miller loops and the final
+  // exponentiation next to them take longer), so what matters is how little they disturb those: above 64 points the sort
+  // pipeline (a handful of resident warps) is used instead of the Straus path (one long-running warp per 8 points).
+  const int small_keep = E.small_msm_max;
+  E.small_msm_max = std::min(small_keep, E.mipp_cross_small_max);
   if (rc == 0) rc = msm_dev(g, a->a, a->y + 8 * (size_t)split, split, a->flags, g.d_result, g.stream, nullptr, nullptr, false);
   if (rc == 0)
     rc = msm_dev(g, a->a + 6 * (size_t)split, a->y, split, a->flags, g.d_result + 6, g.stream2, nullptr, &g.arena2, false);
+  E.small_msm_max = small_keep;
   g.profiling = prof;
   if (rc == 0) {
     cudaError_t e = cudaEventRecord(g.ev_join, g.stream2);
@@ -396,7 +406,7 @@ int tb200_test_fq12_op(int op, const uint64_t* a, const uint64_t* b, size_t n, u
   cudaStream_t st = primary().stream;
   return with_buffers(a, n * 576, b, n * 576, out, n * 576, nullptr, 0, [&](char* da, char* db, char* d1, char*) {
     if (op >= 20 && op < 100)
-      LAUNCH(k_test_w12_op, (uint32_t)n, W12_THREADS, st, op, (const uint4*)da, (const uint4*)db, (uint4*)d1);
+      LAUNCH(k_test_w12_op, (uint32_t)n, E.pairing_team == 32 ? 32 : 64, st, op, (const uint4*)da, (const uint4*)db, (uint4*)d1);
     else
       LAUNCH(k_test_fq12_op, cdiv(n, 32), 32, st, op, (const uint4*)da, (const uint4*)db, (uint32_t)n, (uint4*)d1);
     return 0;

@@ -80,8 +80,16 @@ __global__ void __launch_bounds__(32) k_fq12_prod_level(const uint4* __restrict_
 // per lane, 18 lanes of one warp: ncu showed one instruction per 3.9 cycles, `wait` the only stall, ~5 200 instructions on
 // the critical lane per Fq12 product; per-Fq lanes cut that to ~1 700.) Phases are separated by __syncthreads(); every
 // function must be called by all 64 threads of the CTA. Pointers are shared-memory objects; dst may alias the inputs.
-constexpr int W12_THREADS = 64;
-#define W12_SYNC() __syncthreads()
+// Team size (round 2): the routines run with blockDim.x = 64 (two warps, every phase one item per lane, phases separated by
+// __syncthreads) OR 32 (one warp: the 54 / 36-item phases take two passes, the phase boundaries become __syncwarp).
+// Measured: the one-warp team is 15-20 % SLOWER per pair (the second pass of products costs more than the barriers
+// save) but twice as many pairs are resident, so it wins when the Miller stage is throughput-bound (> 512 pairs).
+constexpr int W12_THREADS = 64;   // the largest team
+__device__ __forceinline__ void w12_sync() {
+  if (blockDim.x > 32) __syncthreads();
+  else __syncwarp();
+}
+#define W12_SYNC() w12_sync()
 struct WScratch {
   Fq xy[2][3][3][2];   // materialised Fq6 operands X_i, Y_i (i < 3) of up to three Fq6 products, [t][c] = Fq2 coefficient t, part c
   Fq kar[54];          // [product 0..17][a0 b0, a1 b1, (a0 + a1)(b0 + b1)]
@@ -127,7 +135,8 @@ __device__ __forceinline__ void w_fq2_from_kar(Fq& o, const Fq* kar, int c) {
 static __device__ __noinline__ void w_fq6_products(WScratch* w, int count) {
   const int tid = threadIdx.x;
   W12_SYNC();
-  if (tid < 18 * count) {
+  for (int tid_ = threadIdx.x; tid_ < 18 * count; tid_ += blockDim.x) {
+    const int tid = tid_;
     const int pr = tid / 3, part = tid % 3, i = pr / 6, j = pr % 6;
     const int t0 = (j < 3) ? j : (j == 3 ? 1 : 0);
     const int t1 = (j == 4) ? 1 : 2;
@@ -137,7 +146,8 @@ static __device__ __noinline__ void w_fq6_products(WScratch* w, int count) {
     fq_mul_ol(&w->kar[tid], &a, &b);
   }
   W12_SYNC();
-  if (tid < 12 * count) {
+  for (int tid_ = threadIdx.x; tid_ < 12 * count; tid_ += blockDim.x) {
+    const int tid = tid_;
     Fq o;
     w_fq2_from_kar(o, &w->kar[3 * (tid / 2)], tid & 1);
     w->prod[tid / 2][tid & 1] = o;
@@ -178,7 +188,8 @@ __device__ __forceinline__ void w_mul_v_coeff(Fq& o, const Fq (*R)[2], int t, in
 static __device__ __noinline__ void w12_mul(Fq12* dst, const Fq12* a, const Fq12* b, WScratch* w) {
   const int tid = threadIdx.x;
   W12_SYNC();
-  if (tid < 36) {
+  for (int tid_ = threadIdx.x; tid_ < 36; tid_ += blockDim.x) {
+    const int tid = tid_;
     const int which = tid / 18, rem = tid % 18, i = rem / 6, t = (rem % 6) / 2, c = rem & 1;
     const Fq* src = w12_q(which ? b : a);
     Fq v;
@@ -605,7 +616,7 @@ __global__ void __launch_bounds__(W12_THREADS, 8) k_miller_coop(const uint4* __r
   w_miller_loop(&s);
   W12_SYNC();
   const uint4* f4 = reinterpret_cast<const uint4*>(&s.f);
-  for (int i = lane; i < 36; i += W12_THREADS) f_out[36 * (size_t)j + i] = f4[i];
+  for (int i = lane; i < 36; i += blockDim.x) f_out[36 * (size_t)j + i] = f4[i];
 }
 
 // product tree level, one CTA per output: out[s][t] = prod_k in[s][t + k m]
@@ -618,17 +629,17 @@ __global__ void __launch_bounds__(W12_THREADS) k_fq12_prod_level_coop(const uint
   const uint4* src = in + 36 * (size_t)blockIdx.y * len;
   uint4* a4 = reinterpret_cast<uint4*>(&acc);
   uint4* x4 = reinterpret_cast<uint4*>(&x);
-  for (int i = lane; i < 36; i += W12_THREADS) a4[i] = src[36 * (size_t)t + i];
+  for (int i = lane; i < 36; i += blockDim.x) a4[i] = src[36 * (size_t)t + i];
   for (int k = 1; k < FQ12_FAN; k++) {
     const uint64_t idx = (uint64_t)t + (uint64_t)k * m;
     if (idx >= len) break;
     W12_SYNC();
-    for (int i = lane; i < 36; i += W12_THREADS) x4[i] = src[36 * idx + i];
+    for (int i = lane; i < 36; i += blockDim.x) x4[i] = src[36 * idx + i];
     W12_SYNC();
     w12_mul(&acc, &acc, &x, &w);
   }
   W12_SYNC();
-  for (int i = lane; i < 36; i += W12_THREADS) out[36 * ((size_t)blockIdx.y * m + t) + i] = a4[i];
+  for (int i = lane; i < 36; i += blockDim.x) out[36 * ((size_t)blockIdx.y * m + t) + i] = a4[i];
 }
 
 // out[b] = final_exponentiation(in[b]); one CTA per product
@@ -636,11 +647,11 @@ __global__ void __launch_bounds__(W12_THREADS) k_final_exp(const uint4* __restri
   __shared__ WFinalExp s;
   const int lane = threadIdx.x;
   uint4* f4 = reinterpret_cast<uint4*>(&s.f);
-  for (int i = lane; i < 36; i += W12_THREADS) f4[i] = in[36 * (size_t)blockIdx.x + i];
+  for (int i = lane; i < 36; i += blockDim.x) f4[i] = in[36 * (size_t)blockIdx.x + i];
   W12_SYNC();
   w12_final_exp(&s);
   const uint4* r4 = reinterpret_cast<const uint4*>(&s.r);
-  for (int i = lane; i < 36; i += W12_THREADS) out[36 * (size_t)blockIdx.x + i] = r4[i];
+  for (int i = lane; i < 36; i += blockDim.x) out[36 * (size_t)blockIdx.x + i] = r4[i];
 }
 
 // out[b] = in[b] with no pairs at all (n == 0): the empty product
@@ -1088,7 +1099,7 @@ __global__ void __launch_bounds__(W12_THREADS) k_test_w12_op(int op, const uint4
   const int lane = threadIdx.x;
   uint4* f4 = reinterpret_cast<uint4*>(&s.f);
   uint4* g4 = reinterpret_cast<uint4*>(&s.f2);
-  for (int i = lane; i < 36; i += W12_THREADS) {
+  for (int i = lane; i < 36; i += blockDim.x) {
     f4[i] = a[36 * (size_t)blockIdx.x + i];
     g4[i] = b[36 * (size_t)blockIdx.x + i];
   }
@@ -1117,7 +1128,7 @@ __global__ void __launch_bounds__(W12_THREADS) k_test_w12_op(int op, const uint4
   }
   W12_SYNC();
   const uint4* r4 = reinterpret_cast<const uint4*>(&s.r);
-  for (int i = lane; i < 36; i += W12_THREADS) out[36 * (size_t)blockIdx.x + i] = r4[i];
+  for (int i = lane; i < 36; i += blockDim.x) out[36 * (size_t)blockIdx.x + i] = r4[i];
 }
 
 __global__ void __launch_bounds__(32) k_test_fq12_op(int op, const uint4* a, const uint4* b, uint32_t n, uint4* out) {
