@@ -18,6 +18,7 @@
 #include <sys/mman.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "engine.h"
 
@@ -1037,6 +1038,9 @@ int commit_rows_locked(tb200_srs_t srs, const RowSource& src, unsigned flags, ui
                        uint64_t* out_t) {
   Ctx& g0 = primary();
   CU(cudaSetDevice(g0.device));
+  static const bool trace = getenv("TB200_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
   const size_t rows = src.rows;
   const ShardPlan sp = plan_rows(rows, src.cols);
   const int nd = sp.nd;
@@ -1062,6 +1066,7 @@ int commit_rows_locked(tb200_srs_t srs, const RowSource& src, unsigned flags, ui
         const bool pipelined = h_vec && E.commit_pipeline != 0;
         int r = batch_share_enqueue(g, srs, src, lo, hi, flags, &d_out[g.slot], to_free[g.slot], pipelined ? &pipe : nullptr);
         if (r) return r;
+        if (trace) fprintf(stderr, "[tb200] slot %d: rows enqueued at %.2f ms\n", g.slot, since());
         if (hi > lo)
           CU(cudaMemcpyAsync(out_xy + 12 * lo, d_out[g.slot], (hi - lo) * 96, cudaMemcpyDeviceToHost, g.stream));
         if (h_vec) {
@@ -1102,14 +1107,18 @@ int commit_rows_locked(tb200_srs_t srs, const RowSource& src, unsigned flags, ui
       if (e != cudaSuccess) rc = fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
     }
   }
+  if (trace) fprintf(stderr, "[tb200] all shares enqueued at %.2f ms\n", since());
   for (int i = 0; i < nd; i++) {
     Ctx& g = *E.devs[i];
     cudaSetDevice(g.device);
     cudaError_t e = cudaStreamSynchronize(g.copy_stream);
+    if (trace) fprintf(stderr, "[tb200] slot %d: uploads done at %.2f ms\n", i, since());
     if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (trace) fprintf(stderr, "[tb200] slot %d: compute done at %.2f ms\n", i, since());
     if (e != cudaSuccess && rc == 0) rc = fail((int)e, "device %d failed: %s", g.device, cudaGetErrorString(e));
     free_all(g, to_free[i]);
   }
+  if (trace) fprintf(stderr, "[tb200] freed at %.2f ms\n", since());
   cudaSetDevice(g0.device);
   if (rc == 0) rc = finish_marks(g0, g0.stream);
   return rc;
