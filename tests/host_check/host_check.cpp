@@ -6,6 +6,7 @@
 #include "../../testudo_b200/csrc/experimental/mont_kara.cuh"
 #include "../../testudo_b200/csrc/g2.cuh"
 #include "../../testudo_b200/csrc/fq12.cuh"
+#include "../../testudo_b200/csrc/fq12_coop.cuh"
 using namespace tb;
 extern "C" {
 void hc_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul<FqParams>(r, a, b); }
@@ -159,4 +160,229 @@ void hc_miller_loop(const uint32_t* p_aff, const uint32_t* q_aff, uint32_t* r) {
   miller_loop(f, p, q); memcpy(r, &f, 576);
 }
 void hc_final_exp(const uint32_t* a, uint32_t* r) { Fq12 x, y; memcpy(&x, a, 576); fq12_final_exp(y, x); memcpy(r, &y, 576); }
+
+// ---- the cooperative engine's lazily reduced per-item bodies (fq12_coop.cuh), run item by item in sequence -----------------
+}  // extern "C"
+namespace {
+void hcw_fq6_products(WScratch* w, int count) {
+  for (int t = 0; t < 18 * count; t++) wp_kar(w, t);
+  for (int t = 0; t < 12 * count; t++) wp_fq2(w, t);
+  for (int t = 0; t < 6 * count; t++) wp_fq6(w, t);
+}
+void hcw_mul(Fq12* dst, const Fq12* a, const Fq12* b) {
+  WScratch w;
+  for (int t = 0; t < 36; t++) wp_mul_xy(&w, a, b, t);
+  hcw_fq6_products(&w, 3);
+  for (int t = 0; t < 12; t++) wp_mul_out(dst, &w, t);
+}
+void hcw_sqr(Fq12* dst, const Fq12* a) {
+  WScratch w;
+  for (int t = 0; t < 24; t++) wp_sqr_xy(&w, a, t);
+  hcw_fq6_products(&w, 2);
+  for (int t = 0; t < 12; t++) wp_sqr_out(dst, &w, t);
+}
+void hcw_cyc(Fq12* dst, const Fq12* a) {
+  WScratch w;
+  for (int t = 0; t < 18; t++) wp_cyc_kar(&w, a, t);
+  for (int t = 0; t < 12; t++) wp_cyc_fq2(&w, t);
+  for (int t = 0; t < 12; t++) wp_cyc_out(dst, a, &w, t);
+}
+void hcw_conj(Fq12* dst, const Fq12* a) {
+  Fq v[12];
+  for (int t = 0; t < 12; t++) v[t] = wp_conj(a, t);
+  for (int t = 0; t < 12; t++) w12_q(dst)[t] = v[t];
+}
+void hcw_frob(Fq12* dst, const Fq12* a, int k) {
+  Fq v[12];
+  for (int t = 0; t < 12; t++) v[t] = wp_frobenius(a, k, t);
+  for (int t = 0; t < 12; t++) w12_q(dst)[t] = v[t];
+}
+void hcw_canon(Fq12* a) {
+  for (int t = 0; t < 12; t++) lz_canon(w12_q(a)[t]);
+}
+void hcw_exp_by_x(Fq12* dst, const Fq12* a) {
+  Fq12 acc = *a;
+  for (int bit = 62; bit >= 0; bit--) {
+    hcw_cyc(&acc, &acc);
+    if ((BLS_X >> bit) & 1) hcw_mul(&acc, &acc, a);
+  }
+  *dst = acc;
+}
+// mirrors w12_final_exp (kernels_pairing.cuh)
+void hcw_final_exp(Fq12* out, const Fq12* in) {
+  Fq12 f = *in, r, f2, y0, y1, y2;
+  hcw_conj(&r, &f);
+  fq12_inv(f2, f);
+  hcw_mul(&r, &r, &f2);
+  f2 = r;
+  hcw_frob(&r, &r, 2);
+  hcw_mul(&r, &r, &f2);
+  hcw_cyc(&y0, &r);
+  hcw_exp_by_x(&y1, &r);
+  hcw_conj(&y2, &r);
+  hcw_mul(&y1, &y1, &y2);
+  hcw_exp_by_x(&y2, &y1);
+  hcw_conj(&y1, &y1);
+  hcw_mul(&y1, &y1, &y2);
+  hcw_exp_by_x(&y2, &y1);
+  hcw_frob(&y1, &y1, 1);
+  hcw_mul(&y1, &y1, &y2);
+  hcw_mul(&r, &r, &y0);
+  hcw_exp_by_x(&y0, &y1);
+  hcw_exp_by_x(&y2, &y0);
+  hcw_frob(&y0, &y1, 2);
+  hcw_conj(&y1, &y1);
+  hcw_mul(&y1, &y1, &y2);
+  hcw_mul(&y1, &y1, &y0);
+  hcw_mul(&r, &r, &y1);
+  hcw_canon(&r);
+  *out = r;
+}
+void hcw_double_step(WDouble* d, Fq12* line) {
+  for (int t = 0; t < 11; t++) wp_dbl_r1(d, t);
+  for (int t = 0; t < 12; t++) wp_dbl_p2(d, t);
+  for (int t = 0; t < 10; t++) wp_dbl_p3(d, t);
+  for (int t = 0; t < 14; t++) wp_dbl_r2(d, t);
+  for (int t = 0; t < 12; t++) wp_dbl_p5(d, line, t);
+}
+}  // namespace
+extern "C" {
+// op: 0 mul, 1 sqr, 2 cyclotomic sqr, 3 frobenius 1, 4 frobenius 2, 5 conj, 6 the chain ((a b)^2 a)^2 conj, 7 exp_by_x,
+// 8 final exponentiation. a, b: raw 12-limb coefficients (any representative < 1.02 q); r canonical.
+void hc_coop_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+  Fq12 x, y, z;
+  memcpy(&x, a, 576);
+  memcpy(&y, b, 576);
+  switch (op) {
+    case 0: hcw_mul(&z, &x, &y); break;
+    case 1: hcw_sqr(&z, &x); break;
+    case 2: hcw_cyc(&z, &x); break;
+    case 3: hcw_frob(&z, &x, 1); break;
+    case 4: hcw_frob(&z, &x, 2); break;
+    case 5: hcw_conj(&z, &x); break;
+    case 6:
+      hcw_mul(&z, &x, &y);
+      hcw_sqr(&z, &z);
+      hcw_mul(&z, &z, &x);
+      hcw_sqr(&z, &z);
+      hcw_conj(&z, &z);
+      break;
+    case 7: hcw_exp_by_x(&z, &x); break;
+    default: hcw_final_exp(&z, &x); break;
+  }
+  hcw_canon(&z);
+  memcpy(r, &z, 576);
+}
+// the largest top limb over the 12 output coefficients of op BEFORE canonicalisation (the invariant: < 1.02 q)
+uint32_t hc_coop_op_top(int op, const uint32_t* a, const uint32_t* b) {
+  Fq12 x, y, z;
+  memcpy(&x, a, 576);
+  memcpy(&y, b, 576);
+  if (op == 0) hcw_mul(&z, &x, &y);
+  else if (op == 1) hcw_sqr(&z, &x);
+  else if (op == 2) hcw_cyc(&z, &x);
+  else if (op == 3) hcw_frob(&z, &x, 1);
+  else if (op == 4) hcw_frob(&z, &x, 2);
+  else hcw_conj(&z, &x);
+  uint32_t top = 0;
+  for (int t = 0; t < 12; t++) top = w12_q(&z)[t].l[11] > top ? w12_q(&z)[t].l[11] : top;
+  return top;
+}
+// lazily reduced doubling step vs the canonical g2_double_line on the same inputs: r (3 Fq2, canonical), px, py.
+// Writes both results (r: 3 Fq2, line: l0, l3, l4) and returns 1 when they agree.
+int hc_coop_double_step(const uint32_t* r_in, const uint32_t* px, const uint32_t* py, uint32_t* r_out, uint32_t* line_out) {
+  WDouble d;
+  Fq12 line;
+  memset(&line, 0, sizeof line);
+  memcpy(&d.r, r_in, 288);
+  memcpy(&d.px, px, 48);
+  memcpy(&d.py, py, 48);
+  hcw_double_step(&d, &line);
+  G2Hom r;
+  memcpy(&r, r_in, 288);
+  Fq2 l0, l3, l4;
+  Fq x, y;
+  memcpy(&x, px, 48);
+  memcpy(&y, py, 48);
+  g2_double_line(r, l0, l3, l4, x, y);
+  memcpy(r_out, &d.r, 288);
+  memcpy(line_out, w12_c(&line, 0), 96);
+  memcpy(line_out + 24, w12_c(&line, 3), 96);
+  memcpy(line_out + 48, w12_c(&line, 4), 96);
+  return memcmp(&r, &d.r, 288) == 0 && memcmp(&l0, w12_c(&line, 0), 96) == 0 && memcmp(&l3, w12_c(&line, 3), 96) == 0 &&
+         memcmp(&l4, w12_c(&line, 4), 96) == 0;
+}
+// the cooperative Miller loop as w_miller_loop runs it (kernels_pairing.cuh), item by item
+void hc_coop_miller(const uint32_t* p_aff, const uint32_t* q_aff, uint32_t* out) {
+  Affine p;
+  Affine2 q;
+  memcpy(&p, p_aff, 96);
+  memcpy(&q, q_aff, 192);
+  Fq12 f = fq12_one(), line;
+  memset(&line, 0, sizeof line);
+  if (!(affine_is_inf(p) || affine2_is_inf(q))) {
+    WDouble d;
+    d.r.x = q.x;
+    d.r.y = q.y;
+    d.r.z = fq2_one();
+    d.px = p.x;
+    d.py = p.y;
+    for (int bit = 62; bit >= 0; bit--) {
+      if (bit != 62) hcw_sqr(&f, &f);
+      hcw_double_step(&d, &line);
+      hcw_mul(&f, &f, &line);
+      if ((BLS_X >> bit) & 1) {
+        Fq2 l0, l3, l4;
+        g2_add_line(d.r, l0, l3, l4, q, p.x, p.y);
+        *w12_c(&line, 0) = l0;
+        *w12_c(&line, 3) = l3;
+        *w12_c(&line, 4) = l4;
+        hcw_mul(&f, &f, &line);
+      }
+    }
+  }
+  hcw_canon(&f);
+  memcpy(out, &f, 576);
+}
+// `iters` random products / squarings / doubling steps on representatives biased towards the extremes (0, q - 1, q,
+// 1.02 q - 1): lazily reduced bodies vs the canonical tower. Returns the number of mismatches.
+int hc_coop_stress(uint64_t seed, int iters) {
+  auto next = [&]() { seed ^= seed << 13; seed ^= seed >> 7; seed ^= seed << 17; return seed; };
+  Fq qm1, top, qq;
+  for (int i = 0; i < 12; i++) qq.l[i] = FqParams::p(i);
+  qm1 = qq; qm1.l[0] -= 1;
+  // top = q + floor(q / 64) - 1 < 1.02 q
+  { Fq sh; for (int i = 0; i < 11; i++) sh.l[i] = (qq.l[i] >> 6) | (qq.l[i + 1] << 26); sh.l[11] = qq.l[11] >> 6; lz_add(top, qq, sh); top.l[0] -= 2; }
+  auto rnd = [&](Fq& v) {
+    const uint64_t sel = next() % 8;
+    if (sel == 0) v = fq_zero();
+    else if (sel == 1) v = qm1;
+    else if (sel == 2) v = qq;
+    else if (sel == 3) v = top;
+    else { for (int i = 0; i < 12; i++) v.l[i] = (uint32_t)next(); v.l[11] %= 0x01ae3a46u; }
+  };
+  int bad = 0;
+  for (int it = 0; it < iters; it++) {
+    Fq12 a, b, ca, cb, z, ref;
+    for (int t = 0; t < 12; t++) { rnd(w12_q(&a)[t]); rnd(w12_q(&b)[t]); }
+    ca = a; cb = b;
+    hcw_canon(&ca); hcw_canon(&cb);
+    hcw_mul(&z, &a, &b); hcw_canon(&z);
+    fq12_mul(ref, ca, cb);
+    bad += memcmp(&z, &ref, 576) != 0;
+    hcw_sqr(&z, &a); hcw_canon(&z);
+    fq12_sqr(ref, ca);
+    bad += memcmp(&z, &ref, 576) != 0;
+    // doubling step on canonical inputs
+    WDouble d; Fq12 line; memset(&line, 0, sizeof line);
+    memcpy(&d.r, &ca, 288); d.px = w12_q(&cb)[0]; d.py = w12_q(&cb)[1];
+    G2Hom r; memcpy(&r, &ca, 288);
+    Fq2 l0, l3, l4;
+    hcw_double_step(&d, &line);
+    g2_double_line(r, l0, l3, l4, w12_q(&cb)[0], w12_q(&cb)[1]);
+    bad += !(memcmp(&r, &d.r, 288) == 0 && memcmp(&l0, w12_c(&line, 0), 96) == 0 && memcmp(&l3, w12_c(&line, 3), 96) == 0 &&
+             memcmp(&l4, w12_c(&line, 4), 96) == 0);
+  }
+  return bad;
+}
 }

@@ -231,18 +231,18 @@ def test_sharded_pairing_product_entry_points(engine):
 
 @pytest.mark.parametrize("n", [3, 600])
 def test_pairing_team_sizes_agree(engine, n):
-    """The cooperative kernels with a two-warp and a one-warp team (tb200_set_pairing_team) give the same GT value; 600
-    pairs take the one-warp Miller kernel by default."""
+    """The cooperative kernels with a two-warp team, a one-warp team and the pipelined three-warp Miller kernel
+    (tb200_set_pairing_team) give the same GT value; 600 pairs take the one-warp Miller kernel by default, 3 the pipelined."""
     gp = pairing
     ps, _ = o.rand_points(8, 71)
     qs, _ = o2.rand_points(8, 72)
     a = np.tile(np.array([o.affine_to_words(p) for p in ps], dtype=np.uint64).reshape(-1, 12), ((n + 7) // 8, 1))[:n].copy()
     b = np.tile(np.array([o2.affine_to_words(q) for q in qs], dtype=np.uint64).reshape(-1, 24), ((n + 7) // 8, 1))[:n].copy()
     outs = []
-    for team in (64, 32, 0):
+    for team in (64, 32, 96, 0):
         engine.tb200_set_pairing_team(team)
         outs.append(gp.multi_pairing(a, b))
     engine.tb200_set_pairing_team(0)
-    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    assert all(np.array_equal(outs[0], x) for x in outs[1:])
     if n == 3:
         assert pr.from_words(outs[0]) == pr.multi_pairing(ps[:3], qs[:3])

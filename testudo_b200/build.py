@@ -22,7 +22,7 @@ UNITS = {
     "engine_core.cu": [],
     "engine_g1.cu": _FIELD + ["kernels_smem.cuh", "kernels_small.cuh"],
     "engine_g2.cu": _G2,
-    "engine_pairing.cu": _G2 + ["fq12.cuh", "fq12_consts.inc", "kernels_pairing.cuh"],
+    "engine_pairing.cu": _G2 + ["fq12.cuh", "fq12_coop.cuh", "fq12_consts.inc", "kernels_pairing.cuh"],
     "poseidon_host.cpp": [],   # host-only: the Fiat-Shamir sponge (CPU code in the reference too)
 }
 COMMON = ["engine.h", "glv_host.h", API_HEADER]

@@ -55,12 +55,14 @@ int pairing_products(Ctx& g, const uint4* d_g1, const uint4* d_g2, uint32_t n, u
   if (mark(g, st, "pairing_begin")) return 1;
   // below ~2 waves of resident CTAs one CTA per pair (latency-bound); above, one thread per pair
   const bool coop = n <= (uint32_t)E.pairing_coop_max;
-  // Team size of the cooperative kernels (measured, scripts/time_pairing_team.py): two warps are faster while the chain's
-  // LATENCY counts (Miller 1.77 vs 2.1 ms for <= 256 pairs, final exponentiation 1.82 vs 1.92 ms); one warp per pair
-  // doubles the resident pairs and wins once the Miller stage is throughput-bound (1024 pairs: 3.6 vs 5.0 ms, 2048: 6.8 vs 8.8).
-  const int miller_team = E.pairing_team ? E.pairing_team : (n > 512 ? 32 : 64);
-  const int chain_team = E.pairing_team ? E.pairing_team : 64;
+  // Miller kernels (measured, scripts/time_pairing_team.py): up to 512 pairs the loop's LATENCY counts and the pipelined
+  // kernel is used (three warps per pair: the point chain next to the f chain); above, a one-warp team per pair doubles
+  // the resident pairs and wins once the stage is throughput-bound (1024 pairs: 3.6 vs 5.0 ms with two warps). The chain
+  // kernels (product tree, final exponentiation) keep two warps. tb200_set_pairing_team forces 32 / 64 / 96 (pipelined).
+  const int miller_team = E.pairing_team ? E.pairing_team : (n > 512 ? 32 : 96);
+  const int chain_team = (E.pairing_team == 32 || E.pairing_team == 64) ? E.pairing_team : 64;
   if (d_gt_in) CU(cudaMemcpyAsync(buf_a, d_gt_in, (size_t)n * 576, cudaMemcpyDeviceToDevice, st));
+  else if (coop && miller_team == 96) LAUNCH(k_miller_pipe, n, MP_THREADS, st, d_g1, d_g2, xor_mask, buf_a);
   else if (coop) LAUNCH(k_miller_coop, n, miller_team, st, d_g1, d_g2, xor_mask, buf_a);
   else LAUNCH(k_miller, cdiv(n, 32), 32, st, d_g1, d_g2, n, xor_mask, buf_a);
   if (after_miller) CU(cudaEventRecord(after_miller, st));

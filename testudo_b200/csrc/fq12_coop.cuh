@@ -1,0 +1,575 @@
+// Lane-parallel Fq12 arithmetic with LAZY field reduction: the per-item bodies of the cooperative pairing engine.
+//
+// kernels_pairing.cuh runs every Fq12 operation of a final exponentiation / a Miller loop on a team of lanes: the 54
+// (36, 18) independent Fq products of a Karatsuba Fq12 product, one per lane, and the linear recombinations one Fq
+// coefficient per lane, phases separated by a team barrier. ncu (profiles/r01_summary.md 5b) showed ~1 600 instructions
+// on the critical lane of one Fq12 product of which only ~400 belong to the Montgomery product: the canonical linear
+// operations (add + conditional subtraction 38 instructions, 5 a = three of those, -5 a = four) were the chain.
+//
+// Here nothing between two products is reduced to [0, q). Fq is 377 bits in a 384-bit container: 2^384 = 152.3 q, so
+//   * lz_add / lz_sub / lz_mul5 / lz_dbl are plain 384-bit operations (12, 12, 24, 12 instructions), wrapping mod 2^384;
+//   * a chain with subtractions is made non-negative by ONE constant k q added per lane and phase (lz_add_kq<k>, k q an
+//     immediate): the TRUE value of every stored quantity lies in [0, 2^384), so the wrapped arithmetic is exact;
+//   * the multiplier is mont_mul_lazy without its conditional subtraction: a < A q, b < B q  ->  < (1 + A B / 152.3) q;
+//   * lz_reduce subtracts floor(top limb / (top limb of q + 1)) q: any value < 2^384 -> < (1 + 2^-16) q, ~40 instructions.
+//     It runs twice per Fq12 operation (after the Fq6 recombination and on the 12 output coefficients).
+// Every function below documents the bound (in multiples of q) of what it reads and writes; tests/test_coop_lazy.py runs
+// these same bodies on the host (tests/host_check) over extreme inputs with an overflow detector, against the oracle.
+//
+// INVARIANT of an Fq12 value in shared memory between operations: every coefficient < 1.02 q (RHO). Values that leave a
+// kernel are canonicalised (lz_canon).
+//
+// The bodies are __host__ __device__ and take the item index t: the device drivers (kernels_pairing.cuh) call them as
+//   for (t = lane; t < items; t += team) body(..., t);   barrier;
+// the host check calls them for t = 0 .. items-1 in sequence -- equivalent because a phase only reads what earlier
+// phases wrote (the in-place phases read into registers, pass a barrier, then write).
+#pragma once
+#include "fq12.cuh"
+
+namespace tb {
+
+// ---- lazily reduced Fq operations ------------------------------------------------------------------------------------------
+struct KQ {
+  uint32_t l[12];
+};
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+constexpr KQ make_kq(unsigned k) {
+  constexpr uint32_t Q[12] = {0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u, 0xba094800u, 0x1ef3622fu,
+                              0x00f5138fu, 0x1a22d9f3u, 0x6ca1493bu, 0xc63b05c0u, 0x17c510eau, 0x01ae3a46u};
+  KQ r{};
+  uint64_t c = 0;
+  for (int j = 0; j < 12; j++) {
+    const uint64_t t = (uint64_t)Q[j] * k + c;
+    r.l[j] = (uint32_t)t;
+    c = t >> 32;
+  }
+  return r;
+}
+TB_HD void lz_add(Fq& r, const Fq& a, const Fq& b) {
+  Carry c;
+  r.l[0] = add_cc(a.l[0], b.l[0], c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) r.l[i] = addc_cc(a.l[i], b.l[i], c);
+}
+TB_HD void lz_sub(Fq& r, const Fq& a, const Fq& b) {   // wraps mod 2^384
+  Carry c;
+  r.l[0] = sub_cc(a.l[0], b.l[0], c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) r.l[i] = subc_cc(a.l[i], b.l[i], c);
+}
+TB_HD void lz_dbl(Fq& r, const Fq& a) { lz_add(r, a, a); }
+TB_HD void lz_mul5(Fq& r, const Fq& a) {   // 4 a (funnel shifts: no carry chain) + a
+  Fq t;
+#pragma unroll
+  for (int i = 11; i >= 1; i--) t.l[i] = (a.l[i] << 2) | (a.l[i - 1] >> 30);
+  t.l[0] = a.l[0] << 2;
+  lz_add(r, t, a);
+}
+TB_HD void lz_mul3(Fq& r, const Fq& a) {
+  Fq t;
+  lz_dbl(t, a);
+  lz_add(r, t, a);
+}
+template <unsigned K>
+TB_HD void lz_add_kq(Fq& r) {
+  constexpr KQ kq = make_kq(K);
+  Carry c;
+  r.l[0] = add_cc(r.l[0], kq.l[0], c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) r.l[i] = addc_cc(r.l[i], kq.l[i], c);
+}
+// r = k q - a (a <= k q)
+template <unsigned K>
+TB_HD void lz_neg_kq(Fq& r, const Fq& a) {
+  constexpr KQ kq = make_kq(K);
+  Carry c;
+  r.l[0] = sub_cc(kq.l[0], a.l[0], c);
+#pragma unroll
+  for (int i = 1; i < 12; i++) r.l[i] = subc_cc(kq.l[i], a.l[i], c);
+}
+// any a < 2^384  ->  a - floor(a_11 / (q_11 + 1)) q  <  (1 + 2^-16) q:  with D = q_11 + 1 the quotient digit never exceeds
+// a / q, and  a - t q < q (1 - 1/D) + 2^352 + a_11 2^352 / D.
+TB_HD void lz_reduce(Fq& a) {
+  const uint32_t t = a.l[11] / 0x01ae3a47u;   // <= 152; a constant divisor: multiply-high + shift
+  uint32_t y[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) y[i] = mul_lo(t, FqParams::p(i));
+  Carry c;
+  y[1] = add_cc(y[1], mul_hi(t, FqParams::p(0)), c);
+#pragma unroll
+  for (int i = 2; i < 12; i++) y[i] = addc_cc(y[i], mul_hi(t, FqParams::p(i - 1)), c);
+  Carry d;
+  a.l[0] = sub_cc(a.l[0], y[0], d);
+#pragma unroll
+  for (int i = 1; i < 12; i++) a.l[i] = subc_cc(a.l[i], y[i], d);
+}
+TB_HD void lz_canon(Fq& a) {   // any a < 2^384 -> [0, q)
+  lz_reduce(a);
+  mod_reduce_once<FqParams>(a.l);
+}
+// (a + (a odd ? q : 0)) / 2 for a + q < 2^384: < (a + q) / 2
+TB_HD void lz_halve(Fq& r, const Fq& a) { fq_halve(r, a); }
+
+// the one out-of-line multiplier of the cooperative engine; operands and result in registers.
+// a < A q, b < B q (A, B <= 150)  ->  r < (1 + A B / 152.3) q
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ Fq fq_mul_lz(Fq a, Fq b) {
+  Fq r;
+  mont_mul_lazy<FqParams>(r.l, a.l, b.l);
+  return r;
+}
+#else
+inline Fq fq_mul_lz(Fq a, Fq b) {
+  Fq r;
+  mont_mul_lazy<FqParams>(r.l, a.l, b.l);
+  return r;
+}
+#endif
+
+// ---- shared-memory scratch of one team -----------------------------------------------------------------------------------
+struct WScratch {
+  Fq xy[2][3][3][2];   // materialised Fq6 operands X_i, Y_i (i < 3) of up to three Fq6 products, [t][c] = Fq2 coefficient t, part c
+  Fq kar[54];          // [product 0..17][a0 b0, a1 b1, (a0 + a1)(b0 + b1)]
+  Fq prod[18][2];      // Fq2 products: [i][j], j = 0..5 -> x0y0, x1y1, x2y2, (x1+x2)(y1+y2), (x0+x1)(y0+y1), (x0+x2)(y0+y2)
+  Fq r6[3][3][2];      // the three Fq6 results
+};
+TB_HD Fq* w12_q(Fq12* a) { return reinterpret_cast<Fq*>(a); }              // [2 * slot + c]
+TB_HD const Fq* w12_q(const Fq12* a) { return reinterpret_cast<const Fq*>(a); }
+TB_HD Fq2* w12_c(Fq12* a, int idx) { return reinterpret_cast<Fq2*>(a) + idx; }
+TB_HD const Fq2* w12_c(const Fq12* a, int idx) { return reinterpret_cast<const Fq2*>(a) + idx; }
+
+// lane `part` of the Karatsuba split of the Fq2 value v (or v0 + v1): c0, c1 or c0 + c1. Bound: the sum of the bounds.
+TB_HD void wl_kar_operand(Fq& o, const Fq* v0, const Fq* v1, bool two, int part) {
+  if (part < 2) {
+    o = v0[part];
+    if (two) lz_add(o, o, v1[part]);
+  } else {
+    lz_add(o, v0[0], v0[1]);
+    if (two) {
+      lz_add(o, o, v1[0]);
+      lz_add(o, o, v1[1]);
+    }
+  }
+}
+// kar[0..2] (each < K q) -> coefficient c of the Fq2 product:  c0 = v0 - 5 v1 + O0 q,  c1 = m - v0 - v1 + O1 q.
+// Needs O0 >= 5 K, O1 >= 2 K; result < (K + O0) q resp. (K + O1) q.
+template <unsigned O0, unsigned O1>
+TB_HD void wl_fq2_from_kar(Fq& o, const Fq* kar, int c) {
+  if (c == 0) {
+    Fq t;
+    lz_mul5(t, kar[1]);
+    lz_sub(o, kar[0], t);
+    lz_add_kq<O0>(o);
+  } else {
+    lz_sub(o, kar[2], kar[0]);
+    lz_sub(o, o, kar[1]);
+    lz_add_kq<O1>(o);
+  }
+}
+
+// ---- the three phases shared by every Fq6-product based operation ---------------------------------------------------------
+// Operand bounds (checked per caller): X side <= 8.2 q, Y side <= 13.2 q per lane  =>  kar < KMAX q = 1.75 q.
+// phase 1, item t < 18 * count: one Fq product
+TB_HD void wp_kar(WScratch* w, int t) {
+  const int pr = t / 3, part = t % 3, i = pr / 6, j = pr % 6;
+  const int t0 = (j < 3) ? j : (j == 3 ? 1 : 0);
+  const int t1 = (j == 4) ? 1 : 2;
+  Fq a, b;
+  wl_kar_operand(a, w->xy[0][i][t0], w->xy[0][i][t1], j >= 3, part);
+  wl_kar_operand(b, w->xy[1][i][t0], w->xy[1][i][t1], j >= 3, part);
+  w->kar[t] = fq_mul_lz(a, b);
+}
+// phase 2, item t < 12 * count: coefficient t & 1 of Fq2 product t / 2.  prod[.][0] < 10.75 q, prod[.][1] < 5.75 q
+TB_HD void wp_fq2(WScratch* w, int t) {
+  Fq o;
+  wl_fq2_from_kar<9, 4>(o, &w->kar[3 * (t / 2)], t & 1);
+  w->prod[t / 2][t & 1] = o;
+}
+// phase 3, item t < 6 * count: coefficient (tt, c) of Fq6 result i, REDUCED (< 1.00002 q).
+// With P0 = 10.75, P1 = 5.75 (bounds of prod[.][0], prod[.][1]):
+//   tt = 0: v0 + xi (m12 - v1 - v2):  c0 = p0.0 - 5 (p3.1 - p1.1 - p2.1) + 29 q < 97.3 q;  c1 = p0.1 + p3.0 - p1.0 - p2.0 + 22 q < 38.5 q
+//   tt = 1: m01 - v0 - v1 + xi v2:    c0 = p4.0 - p0.0 - p1.0 - 5 p2.1 + 51 q < 61.8 q;     c1 = p4.1 - p0.1 - p1.1 + p2.0 + 12 q < 28.5 q
+//   tt = 2: m02 - v0 - v2 + v1:       c0 = ... + 22 q < 43.5 q;                             c1 = ... + 12 q < 23.5 q
+TB_HD void wp_fq6(WScratch* w, int t) {
+  const int i = t / 6, tt = (t % 6) / 2, c = t & 1;
+  const Fq(*p)[2] = &w->prod[6 * i];
+  Fq r, m;
+  if (tt == 0) {
+    lz_sub(m, p[3][1 - c], p[1][1 - c]);
+    lz_sub(m, m, p[2][1 - c]);
+    if (c == 0) {
+      lz_mul5(m, m);
+      lz_sub(r, p[0][0], m);
+      lz_add_kq<29>(r);
+    } else {
+      lz_add(r, p[0][1], m);
+      lz_add_kq<22>(r);
+    }
+  } else if (tt == 1) {
+    lz_sub(r, p[4][c], p[0][c]);
+    lz_sub(r, r, p[1][c]);
+    if (c == 0) {
+      lz_mul5(m, p[2][1]);
+      lz_sub(r, r, m);
+      lz_add_kq<51>(r);
+    } else {
+      lz_add(r, r, p[2][0]);
+      lz_add_kq<12>(r);
+    }
+  } else {
+    lz_sub(r, p[5][c], p[0][c]);
+    lz_sub(r, r, p[2][c]);
+    lz_add(r, r, p[1][c]);
+    if (c == 0) lz_add_kq<22>(r);
+    else lz_add_kq<12>(r);
+  }
+  lz_reduce(r);
+  w->r6[i][tt][c] = r;
+}
+
+// ---- dst = a * b -------------------------------------------------------------------------------------------------------------
+// X = {a0, a1, a0 + a1}, Y = {b0, b1, b0 + b1}; C0 = R0 + v R1, C1 = R2 - R0 - R1.
+// item t < 36: xy coefficient; inputs < RHO q = 1.02 q -> xy < 2.04 q -> product operands < 8.16 q (A B < 67)
+TB_HD void wp_mul_xy(WScratch* w, const Fq12* a, const Fq12* b, int t) {
+  const int which = t / 18, rem = t % 18, i = rem / 6, tt = (rem % 6) / 2, c = rem & 1;
+  const Fq* src = w12_q(which ? b : a);
+  Fq v;
+  if (i < 2) v = src[2 * (3 * i + tt) + c];
+  else lz_add(v, src[2 * tt + c], src[2 * (3 + tt) + c]);
+  w->xy[which][i][tt][c] = v;
+}
+// item t < 12: output coefficient, reduced. r6 < 1.00002 q:  slot 0 c 0: R0 - 5 R1.2.1 + 6 q < 7.1 q; C1: R2 - R0 - R1 + 3 q < 4.1 q
+TB_HD void wp_mul_out(Fq12* dst, const WScratch* w, int t) {
+  const int slot = t / 2, c = t & 1;
+  Fq r, m;
+  if (slot == 0 && c == 0) {
+    lz_mul5(m, w->r6[1][2][1]);
+    lz_sub(r, w->r6[0][0][0], m);
+    lz_add_kq<6>(r);
+  } else if (slot < 3) {
+    lz_add(r, w->r6[0][slot][c], slot == 0 ? w->r6[1][2][0] : w->r6[1][slot - 1][c]);
+  } else {
+    lz_sub(r, w->r6[2][slot - 3][c], w->r6[0][slot - 3][c]);
+    lz_sub(r, r, w->r6[1][slot - 3][c]);
+    lz_add_kq<3>(r);
+  }
+  lz_reduce(r);
+  w12_q(dst)[t] = r;
+}
+
+// ---- dst = a^2 (complex squaring) -------------------------------------------------------------------------------------------
+// R0 = a0 a1, R1 = (a0 + a1)(a0 + v a1); C0 = R1 - R0 - v R0, C1 = 2 R0.
+// item t < 24. X0 = a0, Y0 = a1 (< 1.02 q), X1 = a0 + a1 (< 2.04 q), Y1 = a0 + v a1: coefficient (0, 0) = a0.0.0 - 5 a1.2.1
+// + 6 q < 7.02 q, the others < 2.04 q  =>  X-side operands < 8.16 q, Y-side < 13.14 q, A B < 107.3, kar < 1.705 q
+TB_HD void wp_sqr_xy(WScratch* w, const Fq12* a, int t) {
+  const int which = t / 12, rem = t % 12, i = rem / 6, tt = (rem % 6) / 2, c = rem & 1;
+  const Fq* src = w12_q(a);
+  Fq v;
+  if (i == 0) v = src[2 * (3 * which + tt) + c];
+  else if (which == 0) lz_add(v, src[2 * tt + c], src[2 * (3 + tt) + c]);
+  else if (tt == 0 && c == 0) {
+    Fq m;
+    lz_mul5(m, src[6 + 2 * 2 + 1]);
+    lz_sub(v, src[0], m);
+    lz_add_kq<6>(v);
+  } else {
+    lz_add(v, src[2 * tt + c], tt == 0 ? src[6 + 2 * 2 + 0] : src[6 + 2 * (tt - 1) + c]);
+  }
+  w->xy[which][i][tt][c] = v;
+}
+// item t < 12, reduced. slot s < 3: R1.s - R0.s - (v R0).s: s = 0, c = 0: R1 - R0 + 5 R0.2.1 + 2 q < 8.1 q; otherwise + 3 q < 4.1 q;
+// slot >= 3: 2 R0 < 2.1 q
+TB_HD void wp_sqr_out(Fq12* dst, const WScratch* w, int t) {
+  const int slot = t / 2, c = t & 1;
+  Fq r, m;
+  if (slot == 0 && c == 0) {
+    lz_mul5(m, w->r6[0][2][1]);
+    lz_sub(r, w->r6[1][0][0], w->r6[0][0][0]);
+    lz_add(r, r, m);
+    lz_add_kq<2>(r);
+  } else if (slot < 3) {
+    lz_sub(r, w->r6[1][slot][c], w->r6[0][slot][c]);
+    lz_sub(r, r, slot == 0 ? w->r6[0][2][0] : w->r6[0][slot - 1][c]);
+    lz_add_kq<3>(r);
+  } else {
+    lz_dbl(r, w->r6[0][slot - 3][c]);
+  }
+  lz_reduce(r);
+  w12_q(dst)[t] = r;
+}
+
+// ---- dst = a^2 for a unitary a (Granger-Scott) ----------------------------------------------------------------------------------
+// tower slot of z_k: z0 = c[0], z1 = c[4], z2 = c[3], z3 = c[2], z4 = c[1], z5 = c[5]. Six Fq2 products = 18 Fq products:
+// pair p = (za, zb) = (z_{2p}, z_{2p+1}); even product: za zb, odd product: (za + zb)(za + xi zb).
+TB_HD int w12_cyc_slot(int k) { return k == 0 ? 0 : k == 1 ? 4 : k == 2 ? 3 : k == 3 ? 2 : k == 4 ? 1 : 5; }
+// item t < 18. Inputs < 1.02 q: operands < 4.08 q and < 9.06 q (B.0 = za.0 - 5 zb.1 + 6 q < 7.02 q), A B < 37: kar < 1.25 q
+TB_HD void wp_cyc_kar(WScratch* w, const Fq12* a, int t) {
+  const int l = t / 3, part = t % 3, p = l >> 1;
+  const Fq* za = w12_q(a) + 2 * w12_cyc_slot(2 * p);
+  const Fq* zb = w12_q(a) + 2 * w12_cyc_slot(2 * p + 1);
+  Fq x, y;
+  if ((l & 1) == 0) {
+    wl_kar_operand(x, za, za, false, part);
+    wl_kar_operand(y, zb, zb, false, part);
+  } else {
+    wl_kar_operand(x, za, zb, true, part);
+    Fq B[2], m;
+    lz_mul5(m, zb[1]);
+    lz_sub(B[0], za[0], m);
+    lz_add_kq<6>(B[0]);
+    lz_add(B[1], za[1], zb[0]);
+    wl_kar_operand(y, B, B, false, part);
+  }
+  w->kar[t] = fq_mul_lz(x, y);
+}
+// item t < 12: prod[t / 2][t & 1]; prod[.][0] < 8.25 q, prod[.][1] < 4.25 q
+TB_HD void wp_cyc_fq2(WScratch* w, int t) {
+  Fq o;
+  wl_fq2_from_kar<7, 3>(o, &w->kar[3 * (t / 2)], t & 1);
+  w->prod[t / 2][t & 1] = o;
+}
+// item t < 12: z_k' = 3 t_k -/+ 2 z_k with t = t0, t1, xi t5, t4, t2, t3 for k = 0..5, where t_{2p} = prod[2p+1] - tmp - xi tmp and
+// t_{2p+1} = 2 tmp (tmp = prod[2p]). With P0 = 8.25, P1 = 4.25:
+//   even, c0: P.0 - tmp.0 + 5 tmp.1 + 9 q < 38.5 q;  c1: P.1 - tmp.1 - tmp.0 + 13 q < 17.3 q;  odd: < 16.5 q / 8.5 q
+//   k = 2: c0 = -5 (2 tmp.1) + 43 q < 43 q;  c1 = 2 tmp.0 < 16.5 q
+//   output 3 t + 2 z < 131.1 q (k = 2) or 3 t - 2 z + 3 q < 118.5 q, reduced
+// Each item rewrites only the coefficient it read: dst may alias a.
+TB_HD void wp_cyc_out(Fq12* dst, const Fq12* a, const WScratch* w, int t) {
+  const int k = t / 2, c = t & 1;
+  const int ti = k == 0 ? 0 : k == 1 ? 1 : k == 2 ? 5 : k == 3 ? 4 : k == 4 ? 2 : 3;
+  const int p = ti >> 1;
+  Fq tv;
+  if (k == 2) {            // xi t5, t5 = 2 prod[4]
+    if (c == 0) {
+      Fq u;
+      lz_dbl(u, w->prod[4][1]);
+      lz_mul5(u, u);
+      lz_neg_kq<43>(tv, u);
+    } else {
+      lz_dbl(tv, w->prod[4][0]);
+    }
+  } else if ((ti & 1) == 0) {
+    if (c == 0) {
+      Fq m;
+      lz_mul5(m, w->prod[2 * p][1]);
+      lz_sub(tv, w->prod[2 * p + 1][0], w->prod[2 * p][0]);
+      lz_add(tv, tv, m);
+      lz_add_kq<9>(tv);
+    } else {
+      lz_sub(tv, w->prod[2 * p + 1][1], w->prod[2 * p][1]);
+      lz_sub(tv, tv, w->prod[2 * p][0]);
+      lz_add_kq<13>(tv);
+    }
+  } else {
+    lz_dbl(tv, w->prod[2 * p][c]);
+  }
+  const int slot = w12_cyc_slot(k);
+  const Fq z = w12_q(a)[2 * slot + c];
+  Fq o;
+  if (k == 0 || k == 3 || k == 4) {
+    lz_sub(o, tv, z);
+    lz_dbl(o, o);
+    lz_add(o, o, tv);
+    lz_add_kq<3>(o);
+  } else {
+    lz_add(o, tv, z);
+    lz_dbl(o, o);
+    lz_add(o, o, tv);
+  }
+  lz_reduce(o);
+  w12_q(dst)[2 * slot + c] = o;
+}
+
+// ---- unary operations, item t < 12: value computed here, stored by the caller after a barrier ----------------------------------
+// conjugation: coefficients 6..11 negated (2 q - v, one conditional subtraction: <= q)
+TB_HD Fq wp_conj(const Fq12* a, int t) {
+  Fq v = w12_q(a)[t];
+  if (t >= 6) {
+    lz_neg_kq<2>(v, v);
+    mod_reduce_once<FqParams>(v.l);
+  }
+  return v;
+}
+// a^(q^k), k = 1, 2: tower slot idx holds the coefficient of w^e, e = 2 idx (idx < 3) or 2 (idx - 3) + 1; every Frobenius
+// coefficient u^(e (q^k - 1)/6) lies in Fq (tests/test_oracle_pairing.py): 12 independent Fq products. Output < 1.02 q.
+TB_HD Fq wp_frobenius(const Fq12* a, int k, int t) {
+  const int sl = t / 2;
+  const int e = sl < 3 ? 2 * sl : 2 * (sl - 3) + 1;
+  Fq c = w12_q(a)[t];
+  if (k == 1 && (t & 1)) lz_neg_kq<2>(c, c);      // < 2 q
+  if (e > 0) {
+    const Fq g = fq_from_table(k == 1 ? FQ12_C(FROB1)[e - 1][0] : FQ12_C(FROB2)[e - 1]);
+    c = fq_mul_lz(c, g);                             // < (1 + 2 / 152) q
+  } else if (k == 1 && (t & 1)) {
+    mod_reduce_once<FqParams>(c.l);
+  }
+  return c;
+}
+
+// ---- doubling step of the Miller loop (ark `double_in_place`, see g2_double_line) on parallel lanes -------------------------------
+// r = (x, y, z) canonical on entry and on exit; px, py canonical. Products in two rounds (11 and 14 lanes) plus the twist
+// coefficient; squarings of v = v0 + v1 u use (v0 + v1)(v0 - 5 v1) = s0 and v0 v1 = s1:  v^2 = (s0 + 4 s1) + 2 s1 u.
+struct WDouble {
+  G2Hom r;
+  Fq px, py;
+  Fq kar[16];        // Fq products of the current round
+  Fq v[11][2];       // Fq2 intermediates
+};
+enum { WD_A = 0, WD_B, WD_C, WD_YZ, WD_J, WD_E, WD_D, WD_G, WD_H, WD_NH, WD_J3 };
+// operands of the squaring products: which = 0 -> (v0 + v1, v0 - 5 v1 + OFF q), 1 -> (v0, v1)
+template <unsigned OFF>
+TB_HD void wl_sqr_operands(Fq& a, Fq& b, const Fq* v, int which) {
+  if (which == 0) {
+    Fq t;
+    lz_add(a, v[0], v[1]);
+    lz_mul5(t, v[1]);
+    lz_sub(b, v[0], t);
+    lz_add_kq<OFF>(b);
+  } else {
+    a = v[0];
+    b = v[1];
+  }
+}
+TB_HD void wl_sqr_asm(Fq& o, const Fq& s0, const Fq& s1, int c) {   // (s0 + 4 s1, 2 s1)
+  Fq t;
+  lz_dbl(t, s1);
+  if (c == 0) {
+    lz_dbl(t, t);
+    lz_add(o, s0, t);
+  } else {
+    o = t;
+  }
+}
+// round 1, item t < 11: 0-2 x y (Karatsuba), 3-4 y^2, 5-6 z^2, 7-8 (y+z)^2, 9-10 x^2.
+// operands < 4 q and < 12 q (v0 - 5 v1 + 10 q with v < 2 q): kar < 1.32 q
+TB_HD void wp_dbl_r1(WDouble* s, int t) {
+  const Fq* rx = reinterpret_cast<const Fq*>(&s->r.x);
+  const Fq* ry = reinterpret_cast<const Fq*>(&s->r.y);
+  const Fq* rz = reinterpret_cast<const Fq*>(&s->r.z);
+  Fq a, b;
+  if (t < 3) {
+    wl_kar_operand(a, rx, rx, false, t);
+    wl_kar_operand(b, ry, ry, false, t);
+  } else {
+    const int q = (t - 3) >> 1;
+    Fq w[2];
+    const Fq* src = q == 1 ? rz : (q == 3 ? rx : ry);
+    w[0] = src[0];
+    w[1] = src[1];
+    if (q == 2) {
+      lz_add(w[0], w[0], rz[0]);
+      lz_add(w[1], w[1], rz[1]);
+    }
+    wl_sqr_operands<10>(a, b, w, (t - 3) & 1);
+  }
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 12: a = x y / 2 (< 4.7 q, 2.7 q); b, c, (y+z)^2, j (< 6.6 q, 2.64 q); e = B' 3 c with B' = (0, b1), b1 = -1/5:
+// e.0 = 3 c.1 (< 7.92 q), e.1 = b1 * 3 c.0 (operand < 19.8 q: < 1.14 q)
+TB_HD void wp_dbl_p2(WDouble* s, int t) {
+  const int c = t & 1;
+  Fq o;
+  if (t < 2) {
+    wl_fq2_from_kar<7, 3>(o, &s->kar[0], c);
+    lz_halve(o, o);
+    s->v[WD_A][c] = o;
+  } else if (t < 10) {
+    const int q = (t - 2) >> 1;
+    wl_sqr_asm(o, s->kar[3 + 2 * q], s->kar[4 + 2 * q], c);
+    s->v[WD_B + q][c] = o;
+  } else {
+    Fq cc, tt;
+    wl_sqr_asm(cc, s->kar[5], s->kar[6], 1 - c);
+    lz_mul3(tt, cc);
+    if (c == 0) o = tt;
+    else o = fq_mul_lz(tt, fq_from_table(FQ12_C(TWIST_B1)));
+    s->v[WD_E][c] = o;
+  }
+}
+// item t < 10: d = b - 3 e + 24 q (< 30.6 q), g = (b + 3 e) / 2 (< 15.7 q), h = (y+z)^2 - b - c + 14 q (< 20.6 q),
+// -h = b + c - (y+z)^2 + 7 q (< 20.2 q), 3 j (< 19.8 q)
+TB_HD void wp_dbl_p3(WDouble* s, int t) {
+  const int c = t & 1, q = t >> 1;
+  Fq(*v)[2] = s->v;
+  Fq o, tt;
+  if (q < 2) {
+    lz_mul3(tt, v[WD_E][c]);
+    if (q == 0) {
+      lz_sub(o, v[WD_B][c], tt);
+      lz_add_kq<24>(o);
+    } else {
+      lz_add(o, v[WD_B][c], tt);
+      lz_halve(o, o);
+    }
+    v[WD_D + q][c] = o;
+  } else if (q == 2) {
+    lz_sub(o, v[WD_YZ][c], v[WD_B][c]);
+    lz_sub(o, o, v[WD_C][c]);
+    lz_add_kq<14>(o);
+    v[WD_H][c] = o;
+  } else if (q == 3) {
+    lz_add(o, v[WD_B][c], v[WD_C][c]);
+    lz_sub(o, o, v[WD_YZ][c]);
+    lz_add_kq<7>(o);
+    v[WD_NH][c] = o;
+  } else {
+    lz_mul3(o, v[WD_J][c]);
+    v[WD_J3][c] = o;
+  }
+}
+// round 2, item t < 14: 0-2 a d, 3-4 g^2, 5-6 e^2, 7-9 b h, 10-11 (-h) py, 12-13 (3 j) px.
+// a d: 7.4 q x 57.3 q -> < 3.8 q; g^2: 19.3 q x 33.7 q -> < 5.3 q (v0 - 5 v1 + 18 q); b h: 9.3 q x 37.3 q -> < 3.3 q
+TB_HD void wp_dbl_r2(WDouble* s, int t) {
+  Fq(*v)[2] = s->v;
+  Fq a, b;
+  if (t < 3) {
+    wl_kar_operand(a, v[WD_A], v[WD_A], false, t);
+    wl_kar_operand(b, v[WD_D], v[WD_D], false, t);
+  } else if (t < 7) {
+    wl_sqr_operands<18>(a, b, t < 5 ? v[WD_G] : v[WD_E], (t - 3) & 1);
+  } else if (t < 10) {
+    wl_kar_operand(a, v[WD_B], v[WD_B], false, t - 7);
+    wl_kar_operand(b, v[WD_H], v[WD_H], false, t - 7);
+  } else if (t < 12) {
+    a = v[WD_NH][t - 10];
+    b = s->py;
+  } else {
+    a = v[WD_J3][t - 12];
+    b = s->px;
+  }
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 12: x' = a d, y' = g^2 - 3 e^2 + 21 q (< 31.7 q), z' = b h (Fq2 from kar < 3.8 q: + 19 q / + 8 q), l0 = -h py,
+// l3 = 3 j px, l4 = e - b + 7 q (< 15 q); all canonicalised. r was last read in round 1.
+TB_HD void wp_dbl_p5(WDouble* s, Fq12* line, int t) {
+  const int c = t & 1, q = t >> 1;
+  Fq(*v)[2] = s->v;
+  Fq o;
+  if (q == 0) wl_fq2_from_kar<19, 8>(o, &s->kar[0], c);
+  else if (q == 1) {
+    Fq g2v, e2v, tt;
+    wl_sqr_asm(g2v, s->kar[3], s->kar[4], c);
+    wl_sqr_asm(e2v, s->kar[5], s->kar[6], c);
+    lz_mul3(tt, e2v);
+    lz_sub(o, g2v, tt);
+    lz_add_kq<21>(o);
+  } else if (q == 2) wl_fq2_from_kar<19, 8>(o, &s->kar[7], c);
+  else if (q == 3) o = s->kar[10 + c];
+  else if (q == 4) o = s->kar[12 + c];
+  else {
+    lz_sub(o, v[WD_E][c], v[WD_B][c]);
+    lz_add_kq<7>(o);
+  }
+  lz_canon(o);
+  Fq* dst = q == 0 ? reinterpret_cast<Fq*>(&s->r.x)
+          : q == 1 ? reinterpret_cast<Fq*>(&s->r.y)
+          : q == 2 ? reinterpret_cast<Fq*>(&s->r.z)
+          : q == 3 ? w12_q(line) + 0       // line = (l0, 0, 0) + (l3, l4, 0) w: tower slots 0, 3, 4
+          : q == 4 ? w12_q(line) + 6
+                   : w12_q(line) + 8;
+  dst[c] = o;
+}
+
+}  // namespace tb

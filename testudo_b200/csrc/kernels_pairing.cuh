@@ -9,7 +9,7 @@
 // dependent chain and runs on one thread per product (the two products of a MIPP round side by side).
 // Fq12 values are 576 B (36 uint4) in ark's in-memory order.
 #pragma once
-#include "fq12.cuh"
+#include "fq12_coop.cuh"
 #include "kernels_g2.cuh"
 
 namespace tb {
@@ -71,298 +71,111 @@ __global__ void __launch_bounds__(32) k_fq12_prod_level(const uint4* __restrict_
   store_fq12(out + 36 * ((size_t)blockIdx.y * m + t), acc);
 }
 
-// ---- block-cooperative Fq12 arithmetic (two warps, one Fq product per lane) ------------------------------------------------
+// ---- block-cooperative Fq12 arithmetic (a team of lanes, one Fq product per lane) ------------------------------------------
 // A final exponentiation is ONE dependent chain of ~315 cyclotomic squarings and ~45 Fq12 products; run by a single
-// thread it took 20 ms (31 idle lanes, every product in sequence). Here a 64-thread CTA owns the chain: the Fq12 values
+// thread it took 20 ms (31 idle lanes, every product in sequence). Here a team of lanes owns the chain: the Fq12 values
 // live in shared memory and the 54 (36, 18) independent Fq products inside every Karatsuba Fq12 product (complex squaring,
 // Granger-Scott squaring) run on 54 lanes at once -- one 276-MAC Montgomery product per lane; the linear recombinations
-// are spread the same way, one Fq coefficient per lane. (First version: one Fq2 product = three interleaved Fq products
-// per lane, 18 lanes of one warp: ncu showed one instruction per 3.9 cycles, `wait` the only stall, ~5 200 instructions on
-// the critical lane per Fq12 product; per-Fq lanes cut that to ~1 700.) Phases are separated by __syncthreads(); every
-// function must be called by all 64 threads of the CTA. Pointers are shared-memory objects; dst may alias the inputs.
-// Team size (round 2): the routines run with blockDim.x = 64 (two warps, every phase one item per lane, phases separated by
-// __syncthreads) OR 32 (one warp: the 54 / 36-item phases take two passes, the phase boundaries become __syncwarp).
-// Measured: the one-warp team is 15-20 % SLOWER per pair (the second pass of products costs more than the barriers
-// save) but twice as many pairs are resident, so it wins when the Miller stage is throughput-bound (> 512 pairs).
+// are spread the same way, one Fq coefficient per lane. The per-item bodies, with LAZY field reduction, are in
+// fq12_coop.cuh (round 2: the canonical linear operations were ~3/4 of the instructions on the critical lane); this file
+// holds the drivers: `for (t = lane; t < items; t += team) body(t); barrier`.
+// Teams: 64 lanes = a whole two-warp CTA (__syncthreads), 32 lanes = a one-warp CTA (__syncwarp: the 54 / 36-item phases
+// take two passes; 15-20 % slower per pair but twice as many pairs are resident, so it wins when the Miller stage is
+// throughput-bound), or -- in the pipelined Miller kernel -- warps 0-1 of a three-warp CTA (named barrier 1) next to a
+// one-warp team on warp 2.
+// Every function must be called by all lanes of the team. Pointers are shared-memory objects; dst may alias the inputs.
 constexpr int W12_THREADS = 64;   // the largest team
-__device__ __forceinline__ void w12_sync() {
-  if (blockDim.x > 32) __syncthreads();
-  else __syncwarp();
-}
-#define W12_SYNC() w12_sync()
-struct WScratch {
-  Fq xy[2][3][3][2];   // materialised Fq6 operands X_i, Y_i (i < 3) of up to three Fq6 products, [t][c] = Fq2 coefficient t, part c
-  Fq kar[54];          // [product 0..17][a0 b0, a1 b1, (a0 + a1)(b0 + b1)]
-  Fq prod[18][2];      // Fq2 products: [i][j], j = 0..5 -> x0y0, x1y1, x2y2, (x1+x2)(y1+y2), (x0+x1)(y0+y1), (x0+x2)(y0+y2)
-  Fq r6[3][3][2];      // the three Fq6 results
+struct Team {
+  int tid, size, mode;            // mode 0: __syncthreads, 1: __syncwarp, 2: bar.sync 1, 64
 };
-__device__ __forceinline__ Fq* w12_q(Fq12* a) { return reinterpret_cast<Fq*>(a); }              // [2 * slot + c]
-__device__ __forceinline__ const Fq* w12_q(const Fq12* a) { return reinterpret_cast<const Fq*>(a); }
-__device__ __forceinline__ Fq2* w12_c(Fq12* a, int idx) { return reinterpret_cast<Fq2*>(a) + idx; }
-__device__ __forceinline__ const Fq2* w12_c(const Fq12* a, int idx) { return reinterpret_cast<const Fq2*>(a) + idx; }
-__device__ __forceinline__ void fq_mul5_neg(Fq& r, const Fq& a) {   // -5 a
-  Fq t;
-  fq_mul5(t, a);
-  fq_neg(r, t);
+__device__ __forceinline__ Team team_cta() {
+  Team t;
+  t.tid = threadIdx.x;
+  t.size = blockDim.x;
+  t.mode = blockDim.x > 32 ? 0 : 1;
+  return t;
 }
-// lane `part` of the Karatsuba split of the Fq2 value v: c0, c1 or c0 + c1
-__device__ __forceinline__ void w_kar_operand(Fq& o, const Fq* v0, const Fq* v1, bool two, int part) {
-  if (part < 2) {
-    o = v0[part];
-    if (two) fq_add(o, o, v1[part]);
-  } else {
-    fq_add(o, v0[0], v0[1]);
-    if (two) {
-      fq_add(o, o, v1[0]);
-      fq_add(o, o, v1[1]);
-    }
-  }
-}
-// kar[3 pr + 0..2] -> the Fq2 product pr, coefficient c:  c0 = v0 - 5 v1,  c1 = m - v0 - v1
-__device__ __forceinline__ void w_fq2_from_kar(Fq& o, const Fq* kar, int c) {
-  if (c == 0) {
-    Fq t;
-    fq_mul5(t, kar[1]);
-    fq_sub(o, kar[0], t);
-  } else {
-    fq_sub(o, kar[2], kar[0]);
-    fq_sub(o, o, kar[1]);
-  }
+__device__ __forceinline__ void team_sync(const Team& t) {
+  if (t.mode == 0) __syncthreads();
+  else if (t.mode == 1) __syncwarp();
+  else asm volatile("bar.sync 1, 64;" ::: "memory");
 }
 
 // phases 1-3 of every product: 18 * count lanes multiply, 12 * count lanes assemble the Fq2 products, 6 * count lanes
-// assemble coefficient (t, c) of Fq6 result i. `count` = number of Fq6 products (1..3).
-static __device__ __noinline__ void w_fq6_products(WScratch* w, int count) {
-  const int tid = threadIdx.x;
-  W12_SYNC();
-  for (int tid_ = threadIdx.x; tid_ < 18 * count; tid_ += blockDim.x) {
-    const int tid = tid_;
-    const int pr = tid / 3, part = tid % 3, i = pr / 6, j = pr % 6;
-    const int t0 = (j < 3) ? j : (j == 3 ? 1 : 0);
-    const int t1 = (j == 4) ? 1 : 2;
-    Fq a, b;
-    w_kar_operand(a, w->xy[0][i][t0], w->xy[0][i][t1], j >= 3, part);
-    w_kar_operand(b, w->xy[1][i][t0], w->xy[1][i][t1], j >= 3, part);
-    fq_mul_ol(&w->kar[tid], &a, &b);
-  }
-  W12_SYNC();
-  for (int tid_ = threadIdx.x; tid_ < 12 * count; tid_ += blockDim.x) {
-    const int tid = tid_;
-    Fq o;
-    w_fq2_from_kar(o, &w->kar[3 * (tid / 2)], tid & 1);
-    w->prod[tid / 2][tid & 1] = o;
-  }
-  W12_SYNC();
-  if (tid < 6 * count) {
-    const int i = tid / 6, t = (tid % 6) / 2, c = tid & 1;
-    const Fq(*p)[2] = &w->prod[6 * i];
-    Fq r, m;
-    if (t == 0) {          // v0 + xi (m12 - v1 - v2);  (xi z).c0 = -5 z.c1, (xi z).c1 = z.c0
-      fq_sub(m, p[3][1 - c], p[1][1 - c]);
-      fq_sub(m, m, p[2][1 - c]);
-      if (c == 0) fq_mul5_neg(m, m);
-      fq_add(r, p[0][c], m);
-    } else if (t == 1) {   // m01 - v0 - v1 + xi v2
-      fq_sub(r, p[4][c], p[0][c]);
-      fq_sub(r, r, p[1][c]);
-      if (c == 0) fq_mul5_neg(m, p[2][1]);
-      else m = p[2][0];
-      fq_add(r, r, m);
-    } else {               // m02 - v0 - v2 + v1
-      fq_sub(r, p[5][c], p[0][c]);
-      fq_sub(r, r, p[2][c]);
-      fq_add(r, r, p[1][c]);
-    }
-    w->r6[i][t][c] = r;
-  }
-  W12_SYNC();
+// assemble (and reduce) coefficient (t, c) of Fq6 result i. `count` = number of Fq6 products (1..3).
+static __device__ __noinline__ void w_fq6_products(WScratch* w, int count, Team tm) {
+  team_sync(tm);
+  for (int t = tm.tid; t < 18 * count; t += tm.size) wp_kar(w, t);
+  team_sync(tm);
+  for (int t = tm.tid; t < 12 * count; t += tm.size) wp_fq2(w, t);
+  team_sync(tm);
+  if (tm.tid < 6 * count) wp_fq6(w, tm.tid);
+  team_sync(tm);
 }
-// coefficient (t, c) of v * R for an Fq6 value R[3][2]: v (x0, x1, x2) = (xi x2, x0, x1)
-__device__ __forceinline__ void w_mul_v_coeff(Fq& o, const Fq (*R)[2], int t, int c) {
-  if (t > 0) o = R[t - 1][c];
-  else if (c == 0) fq_mul5_neg(o, R[2][1]);
-  else o = R[2][0];
+static __device__ __noinline__ void w12_mul(Fq12* dst, const Fq12* a, const Fq12* b, WScratch* w, Team tm) {
+  team_sync(tm);
+  for (int t = tm.tid; t < 36; t += tm.size) wp_mul_xy(w, a, b, t);
+  w_fq6_products(w, 3, tm);
+  if (tm.tid < 12) wp_mul_out(dst, w, tm.tid);
+  team_sync(tm);
 }
-
-// dst = a * b: X = {a0, a1, a0 + a1}, Y = {b0, b1, b0 + b1}; C0 = R0 + v R1, C1 = R2 - R0 - R1
-static __device__ __noinline__ void w12_mul(Fq12* dst, const Fq12* a, const Fq12* b, WScratch* w) {
-  const int tid = threadIdx.x;
-  W12_SYNC();
-  for (int tid_ = threadIdx.x; tid_ < 36; tid_ += blockDim.x) {
-    const int tid = tid_;
-    const int which = tid / 18, rem = tid % 18, i = rem / 6, t = (rem % 6) / 2, c = rem & 1;
-    const Fq* src = w12_q(which ? b : a);
-    Fq v;
-    if (i < 2) v = src[2 * (3 * i + t) + c];
-    else fq_add(v, src[2 * t + c], src[2 * (3 + t) + c]);
-    w->xy[which][i][t][c] = v;
-  }
-  w_fq6_products(w, 3);
-  if (tid < 12) {
-    const int slot = tid / 2, c = tid & 1;
-    Fq r, m;
-    if (slot < 3) {
-      w_mul_v_coeff(m, w->r6[1], slot, c);
-      fq_add(r, w->r6[0][slot][c], m);
-    } else {
-      fq_sub(r, w->r6[2][slot - 3][c], w->r6[0][slot - 3][c]);
-      fq_sub(r, r, w->r6[1][slot - 3][c]);
-    }
-    w12_q(dst)[tid] = r;
-  }
-  W12_SYNC();
+static __device__ __noinline__ void w12_sqr(Fq12* dst, const Fq12* a, WScratch* w, Team tm) {
+  team_sync(tm);
+  if (tm.tid < 24) wp_sqr_xy(w, a, tm.tid);
+  w_fq6_products(w, 2, tm);
+  if (tm.tid < 12) wp_sqr_out(dst, w, tm.tid);
+  team_sync(tm);
 }
-
-// dst = a^2 (complex squaring): R0 = a0 a1, R1 = (a0 + a1)(a0 + v a1); C0 = R1 - R0 - v R0, C1 = 2 R0
-static __device__ __noinline__ void w12_sqr(Fq12* dst, const Fq12* a, WScratch* w) {
-  const int tid = threadIdx.x;
-  W12_SYNC();
-  if (tid < 24) {
-    const int which = tid / 12, rem = tid % 12, i = rem / 6, t = (rem % 6) / 2, c = rem & 1;
-    const Fq* src = w12_q(a);
-    Fq v;
-    if (i == 0) v = src[2 * (3 * which + t) + c];                            // X0 = a0, Y0 = a1
-    else if (which == 0) fq_add(v, src[2 * t + c], src[2 * (3 + t) + c]);    // X1 = a0 + a1
-    else {                                                                   // Y1 = a0 + v a1
-      Fq m;
-      w_mul_v_coeff(m, reinterpret_cast<const Fq(*)[2]>(src + 6), t, c);
-      fq_add(v, src[2 * t + c], m);
-    }
-    w->xy[which][i][t][c] = v;
-  }
-  w_fq6_products(w, 2);
-  if (tid < 12) {
-    const int slot = tid / 2, c = tid & 1;
-    Fq r, m;
-    if (slot < 3) {
-      w_mul_v_coeff(m, w->r6[0], slot, c);
-      fq_sub(r, w->r6[1][slot][c], w->r6[0][slot][c]);
-      fq_sub(r, r, m);
-    } else {
-      fq_dbl(r, w->r6[0][slot - 3][c]);
-    }
-    w12_q(dst)[tid] = r;
-  }
-  W12_SYNC();
+static __device__ __noinline__ void w12_cyclotomic_sqr(Fq12* dst, const Fq12* a, WScratch* w, Team tm) {
+  team_sync(tm);
+  if (tm.tid < 18) wp_cyc_kar(w, a, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 12) wp_cyc_fq2(w, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 12) wp_cyc_out(dst, a, w, tm.tid);
+  team_sync(tm);
 }
-
-// dst = a^2 for a unitary a (Granger-Scott, as fq12_cyclotomic_sqr_ol): six Fq2 products = 18 Fq products on 18 lanes.
-// tower slot of z_k: z0 = c[0], z1 = c[4], z2 = c[3], z3 = c[2], z4 = c[1], z5 = c[5]
-static __device__ __noinline__ void w12_cyclotomic_sqr(Fq12* dst, const Fq12* a, WScratch* w) {
-  const int tid = threadIdx.x;
-  constexpr int slot[6] = {0, 4, 3, 2, 1, 5};
-  W12_SYNC();
-  if (tid < 18) {
-    const int l = tid / 3, part = tid % 3, p = l >> 1;
-    const Fq* za = w12_q(a) + 2 * slot[2 * p];
-    const Fq* zb = w12_q(a) + 2 * slot[2 * p + 1];
-    Fq x, y;
-    if ((l & 1) == 0) {                         // tmp = za zb
-      w_kar_operand(x, za, za, false, part);
-      w_kar_operand(y, zb, zb, false, part);
-    } else {                                    // (za + zb)(za + xi zb)
-      w_kar_operand(x, za, zb, true, part);
-      Fq B[2], m;
-      fq_mul5_neg(m, zb[1]);
-      fq_add(B[0], za[0], m);
-      fq_add(B[1], za[1], zb[0]);
-      w_kar_operand(y, B, B, false, part);
-    }
-    fq_mul_ol(&w->kar[tid], &x, &y);
-  }
-  W12_SYNC();
-  if (tid < 12) {
-    Fq o;
-    w_fq2_from_kar(o, &w->kar[3 * (tid / 2)], tid & 1);
-    w->prod[tid / 2][tid & 1] = o;
-  }
-  W12_SYNC();
-  if (tid < 12) {
-    // z_k' = 3 t - 2 z_k (k = 0, 3, 4) or 3 t + 2 z_k (k = 1, 2, 5), with t = t0, t1, xi t5, t4, t2, t3 for k = 0..5 where
-    // t_{2p} = prod[2p+1] - tmp - xi tmp and t_{2p+1} = 2 tmp (tmp = prod[2p])
-    constexpr int tsel[6] = {0, 1, 5, 4, 2, 3};
-    const int k = tid / 2, c = tid & 1;
-    const int ti = tsel[k], p = ti >> 1;
-    // coefficient cc of t_{ti}
-    auto tcoef = [&](Fq& o, int cc) {
-      if ((ti & 1) == 0) {
-        Fq m;
-        fq_sub(o, w->prod[2 * p + 1][cc], w->prod[2 * p][cc]);
-        if (cc == 0) fq_mul5_neg(m, w->prod[2 * p][1]);
-        else m = w->prod[2 * p][0];
-        fq_sub(o, o, m);
-      } else {
-        fq_dbl(o, w->prod[2 * p][cc]);
-      }
-    };
-    Fq t;
-    if (k == 2) {                               // xi t5
-      Fq u;
-      tcoef(u, 1 - c);
-      if (c == 0) fq_mul5_neg(t, u);
-      else t = u;
-    } else {
-      tcoef(t, c);
-    }
-    const Fq z = w12_q(a)[2 * slot[k] + c];
-    Fq o;
-    if (k == 0 || k == 3 || k == 4) fq_sub(o, t, z);
-    else fq_add(o, t, z);
-    fq_dbl(o, o);
-    fq_add(o, o, t);
-    w12_q(dst)[2 * slot[k] + c] = o;            // each lane rewrites only the coefficient it read: dst may alias a
-  }
-  W12_SYNC();
-}
-
-__device__ __forceinline__ void w12_copy(Fq12* dst, const Fq12* a) {
-  const int tid = threadIdx.x;
-  W12_SYNC();
+__device__ __forceinline__ void w12_copy(Fq12* dst, const Fq12* a, Team tm) {
+  team_sync(tm);
   Fq v;
-  if (tid < 12) v = w12_q(a)[tid];
-  W12_SYNC();
-  if (tid < 12) w12_q(dst)[tid] = v;
-  W12_SYNC();
+  if (tm.tid < 12) v = w12_q(a)[tm.tid];
+  team_sync(tm);
+  if (tm.tid < 12) w12_q(dst)[tm.tid] = v;
+  team_sync(tm);
 }
-__device__ __forceinline__ void w12_conj(Fq12* dst, const Fq12* a) {
-  const int tid = threadIdx.x;
-  W12_SYNC();
+__device__ __forceinline__ void w12_conj(Fq12* dst, const Fq12* a, Team tm) {
+  team_sync(tm);
   Fq v;
-  if (tid < 12) {
-    v = w12_q(a)[tid];
-    if (tid >= 6) fq_neg(v, v);
-  }
-  W12_SYNC();
-  if (tid < 12) w12_q(dst)[tid] = v;
-  W12_SYNC();
+  if (tm.tid < 12) v = wp_conj(a, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 12) w12_q(dst)[tm.tid] = v;
+  team_sync(tm);
 }
-// a^(q^k), k = 1, 2: tower slot idx holds the coefficient of w^e, e = 2 idx (idx < 3) or 2 (idx - 3) + 1; every
-// Frobenius coefficient u^(e (q^k - 1)/6) lies in Fq (tests/test_oracle_pairing.py), so this is 12 independent Fq products
-static __device__ __noinline__ void w12_frobenius(Fq12* dst, const Fq12* a, int k) {
-  const int tid = threadIdx.x;
-  W12_SYNC();
+static __device__ __noinline__ void w12_frobenius(Fq12* dst, const Fq12* a, int k, Team tm) {
+  team_sync(tm);
   Fq c;
-  if (tid < 12) {
-    const int sl = tid / 2;
-    const int e = sl < 3 ? 2 * sl : 2 * (sl - 3) + 1;
-    c = w12_q(a)[tid];
-    if (k == 1 && (tid & 1)) fq_neg(c, c);
-    if (e > 0) {
-      const Fq g = fq_from_table(k == 1 ? FQ12_C(FROB1)[e - 1][0] : FQ12_C(FROB2)[e - 1]);
-      fq_mul_ol(&c, &c, &g);
-    }
-  }
-  W12_SYNC();
-  if (tid < 12) w12_q(dst)[tid] = c;
-  W12_SYNC();
+  if (tm.tid < 12) c = wp_frobenius(a, k, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 12) w12_q(dst)[tm.tid] = c;
+  team_sync(tm);
 }
-static __device__ __noinline__ void w12_exp_by_x(Fq12* dst, const Fq12* a, Fq12* acc, WScratch* w) {
-  w12_copy(acc, a);
-  for (int bit = 62; bit >= 0; bit--) {
-    w12_cyclotomic_sqr(acc, acc, w);
-    if ((BLS_X >> bit) & 1) w12_mul(acc, acc, a, w);
+// every coefficient to [0, q): values that leave the kernel
+__device__ __forceinline__ void w12_canon(Fq12* a, Team tm) {
+  team_sync(tm);
+  if (tm.tid < 12) {
+    Fq v = w12_q(a)[tm.tid];
+    lz_canon(v);
+    w12_q(a)[tm.tid] = v;
   }
-  w12_copy(dst, acc);
+  team_sync(tm);
+}
+static __device__ __noinline__ void w12_exp_by_x(Fq12* dst, const Fq12* a, Fq12* acc, WScratch* w, Team tm) {
+  w12_copy(acc, a, tm);
+  for (int bit = 62; bit >= 0; bit--) {
+    w12_cyclotomic_sqr(acc, acc, w, tm);
+    if ((BLS_X >> bit) & 1) w12_mul(acc, acc, a, w, tm);
+  }
+  w12_copy(dst, acc, tm);
 }
 
 struct WFinalExp {
@@ -370,253 +183,223 @@ struct WFinalExp {
   WScratch w;
 };
 
-// the chain of fq12_final_exp_ol (ark `final_exponentiation`), one CTA; s->f holds the input, the result lands in s->r
-static __device__ __noinline__ void w12_final_exp(WFinalExp* s) {
+// the chain of fq12_final_exp_ol (ark `final_exponentiation`), one team; s->f holds the (canonical) input, the canonical
+// result lands in s->r
+static __device__ __noinline__ void w12_final_exp(WFinalExp* s, Team tm) {
   WScratch* w = &s->w;
-  w12_conj(&s->r, &s->f);
-  if (threadIdx.x == 0) fq12_inv_ol(&s->f2, &s->f);      // one inversion per product
-  W12_SYNC();
-  w12_mul(&s->r, &s->r, &s->f2, w);
-  w12_copy(&s->f2, &s->r);
-  w12_frobenius(&s->r, &s->r, 2);
-  w12_mul(&s->r, &s->r, &s->f2, w);
-  w12_cyclotomic_sqr(&s->y0, &s->r, w);
-  w12_exp_by_x(&s->y1, &s->r, &s->acc, w);
-  w12_conj(&s->y2, &s->r);
-  w12_mul(&s->y1, &s->y1, &s->y2, w);
-  w12_exp_by_x(&s->y2, &s->y1, &s->acc, w);
-  w12_conj(&s->y1, &s->y1);
-  w12_mul(&s->y1, &s->y1, &s->y2, w);
-  w12_exp_by_x(&s->y2, &s->y1, &s->acc, w);
-  w12_frobenius(&s->y1, &s->y1, 1);
-  w12_mul(&s->y1, &s->y1, &s->y2, w);
-  w12_mul(&s->r, &s->r, &s->y0, w);
-  w12_exp_by_x(&s->y0, &s->y1, &s->acc, w);
-  w12_exp_by_x(&s->y2, &s->y0, &s->acc, w);
-  w12_frobenius(&s->y0, &s->y1, 2);
-  w12_conj(&s->y1, &s->y1);
-  w12_mul(&s->y1, &s->y1, &s->y2, w);
-  w12_mul(&s->y1, &s->y1, &s->y0, w);
-  w12_mul(&s->r, &s->r, &s->y1, w);
+  w12_conj(&s->r, &s->f, tm);
+  if (tm.tid == 0) fq12_inv_ol(&s->f2, &s->f);      // one inversion per product
+  team_sync(tm);
+  w12_mul(&s->r, &s->r, &s->f2, w, tm);
+  w12_copy(&s->f2, &s->r, tm);
+  w12_frobenius(&s->r, &s->r, 2, tm);
+  w12_mul(&s->r, &s->r, &s->f2, w, tm);
+  w12_cyclotomic_sqr(&s->y0, &s->r, w, tm);
+  w12_exp_by_x(&s->y1, &s->r, &s->acc, w, tm);
+  w12_conj(&s->y2, &s->r, tm);
+  w12_mul(&s->y1, &s->y1, &s->y2, w, tm);
+  w12_exp_by_x(&s->y2, &s->y1, &s->acc, w, tm);
+  w12_conj(&s->y1, &s->y1, tm);
+  w12_mul(&s->y1, &s->y1, &s->y2, w, tm);
+  w12_exp_by_x(&s->y2, &s->y1, &s->acc, w, tm);
+  w12_frobenius(&s->y1, &s->y1, 1, tm);
+  w12_mul(&s->y1, &s->y1, &s->y2, w, tm);
+  w12_mul(&s->r, &s->r, &s->y0, w, tm);
+  w12_exp_by_x(&s->y0, &s->y1, &s->acc, w, tm);
+  w12_exp_by_x(&s->y2, &s->y0, &s->acc, w, tm);
+  w12_frobenius(&s->y0, &s->y1, 2, tm);
+  w12_conj(&s->y1, &s->y1, tm);
+  w12_mul(&s->y1, &s->y1, &s->y2, w, tm);
+  w12_mul(&s->y1, &s->y1, &s->y0, w, tm);
+  w12_mul(&s->r, &s->r, &s->y1, w, tm);
+  w12_canon(&s->r, tm);
 }
 
-// ---- warp-cooperative Miller loop (one warp per pair) --------------------------------------------------------------
+// ---- cooperative Miller loop (one team per pair) ----------------------------------------------------------------------------
 // Thread-per-pair keeps the integer pipe fed only when there are thousands of pairs; the MIPP rounds of the reference
 // issue products of 2^12 ... 1 pairs and every one of them waits for a full 10 ms single-thread Miller loop. Below ~2^11
-// pairs one warp owns a pair: f^2 and f * line are the cooperative Fq12 operations above, the doubling step runs its
-// five + six independent Fq2 products on parallel lanes, and only the six addition steps of the loop are serial.
+// pairs a team owns a pair: f^2 and f * line are the cooperative Fq12 operations above, the doubling step runs its
+// 11 + 14 independent Fq products on parallel lanes (fq12_coop.cuh), and only the six addition steps of the loop are serial.
 struct WMiller {
   Fq12 f, line;      // line = (l0, 0, 0) + (l3, l4, 0) w in tower slots 0, 3, 4; slots 1, 2, 5 stay zero
-  G2Hom r;
+  WDouble d;         // the running point r, P's coordinates, the doubling step's scratch
   Affine2 q;
   Affine p;
-  Fq kar[16];        // Fq products of the doubling step
-  Fq v[11][2];       // its Fq2 intermediates (a, b, c, (y+z)^2, j, e, d, g, h, -h, 3j)
   WScratch w;
 };
 
-// ark `double_in_place` (see g2_double_line) on parallel lanes; updates s->r and the line coefficients in s->line.
-// SIMT rule that shaped it: lanes of a warp that take DIFFERENT branches run one after the other, so a first version with
-// one Fq2 product per lane in lane-specific branches took 44 us per step. Here every expensive operation (the Montgomery
-// products) is ONE uniform call whose operands were selected per lane beforehand; only cheap additions sit in
-// lane-specific branches. Three rounds of products: {x y, y^2, z^2, (y+z)^2, x^2} (11 Fq products), the twist
-// coefficient, {a (b-3e), g^2, e^2, b h, -h py, 3j px} (14 Fq products). Squarings use (v0 + v1)(v0 - 5 v1), v0 v1.
-__device__ __forceinline__ void w_sqr_asm(Fq& o, const Fq& s0, const Fq& s1, int c) {   // (s0 + 4 s1, 2 s1)
-  Fq t;
-  fq_dbl(t, s1);
-  if (c == 0) {
-    fq_dbl(t, t);
-    fq_add(o, s0, t);
-  } else {
-    o = t;
-  }
+// SIMT rule that shaped the doubling step: lanes of a warp that take DIFFERENT branches run one after the other, so a first
+// version with one Fq2 product per lane in lane-specific branches took 44 us per step. Every expensive operation (the
+// Montgomery products) is ONE uniform call whose operands were selected per lane beforehand; only cheap additions sit in
+// lane-specific branches.
+static __device__ __noinline__ void w_double_step(WDouble* d, Fq12* line, Team tm) {
+  team_sync(tm);
+  if (tm.tid < 11) wp_dbl_r1(d, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 12) wp_dbl_p2(d, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 10) wp_dbl_p3(d, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 14) wp_dbl_r2(d, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 12) wp_dbl_p5(d, line, tm.tid);
+  team_sync(tm);
 }
-__device__ __forceinline__ void w_sqr_operands(Fq& a, Fq& b, const Fq* v, int which) {   // which: 0 -> s0, 1 -> s1
-  if (which == 0) {
-    Fq t;
-    fq_add(a, v[0], v[1]);
-    fq_mul5(t, v[1]);
-    fq_sub(b, v[0], t);
-  } else {
-    a = v[0];
-    b = v[1];
+// the serial addition step (six per loop) on one lane of the team: canonical arithmetic on the canonical r
+__device__ __forceinline__ void w_add_step(WDouble* d, const Affine2* q, Fq12* line, Team tm) {
+  if (tm.tid == 0) {
+    Fq2 l0, l3, l4;
+    G2Hom r = d->r;
+    g2_add_line(r, l0, l3, l4, *q, d->px, d->py);
+    d->r = r;
+    *w12_c(line, 0) = l0;
+    *w12_c(line, 3) = l3;
+    *w12_c(line, 4) = l4;
   }
-}
-static __device__ __noinline__ void w_double_step(WMiller* s) {
-  const int lane = threadIdx.x;
-  enum { VA = 0, VB, VC, VYZ, VJ, VE, VD, VG, VH, VNH, VJ3 };
-  Fq(*v)[2] = s->v;
-  const Fq* rx = reinterpret_cast<const Fq*>(&s->r.x);
-  const Fq* ry = reinterpret_cast<const Fq*>(&s->r.y);
-  const Fq* rz = reinterpret_cast<const Fq*>(&s->r.z);
-  W12_SYNC();
-  // round 1: 0-2 x y (Karatsuba), 3-4 y^2, 5-6 z^2, 7-8 (y+z)^2, 9-10 x^2
-  if (lane < 11) {
-    Fq a, b;
-    if (lane < 3) {
-      w_kar_operand(a, rx, rx, false, lane);
-      w_kar_operand(b, ry, ry, false, lane);
-    } else {
-      const int q = (lane - 3) >> 1;
-      Fq w[2];
-      const Fq* src = q == 0 ? ry : (q == 1 ? rz : (q == 3 ? rx : ry));
-      w[0] = src[0];
-      w[1] = src[1];
-      if (q == 2) {
-        fq_add(w[0], w[0], rz[0]);
-        fq_add(w[1], w[1], rz[1]);
-      }
-      w_sqr_operands(a, b, w, (lane - 3) & 1);
-    }
-    fq_mul_ol(&s->kar[lane], &a, &b);
-  }
-  W12_SYNC();
-  if (lane < 12) {
-    const int c = lane & 1;
-    Fq o;
-    if (lane < 2) {                 // a = x y / 2
-      w_fq2_from_kar(o, &s->kar[0], c);
-      fq_halve(o, o);
-      v[VA][c] = o;
-    } else if (lane < 10) {         // b, c, (y+z)^2, j
-      const int q = (lane - 2) >> 1;
-      w_sqr_asm(o, s->kar[3 + 2 * q], s->kar[4 + 2 * q], c);
-      v[VB + q][c] = o;
-    } else {                        // e = B' 3 c with B' = (0, -1/5): e.c0 = 3 c.c1, e.c1 = b1 * 3 c.c0
-      Fq cc, t;
-      w_sqr_asm(cc, s->kar[5], s->kar[6], 1 - c);
-      fq_dbl(t, cc);
-      fq_add(t, t, cc);
-      if (c == 0) o = t;
-      else {
-        const Fq b1 = fq_from_table(FQ12_C(TWIST_B1));
-        fq_mul_ol(&o, &t, &b1);
-      }
-      v[VE][c] = o;
-    }
-  }
-  W12_SYNC();
-  if (lane < 10) {                  // d = b - 3e, g = (b + 3e)/2, h = (y+z)^2 - b - c, -h, 3j
-    const int c = lane & 1, q = lane >> 1;
-    Fq o, t;
-    if (q < 2) {
-      fq_dbl(t, v[VE][c]);
-      fq_add(t, t, v[VE][c]);
-      if (q == 0) fq_sub(o, v[VB][c], t);
-      else {
-        fq_add(o, v[VB][c], t);
-        fq_halve(o, o);
-      }
-      v[VD + q][c] = o;
-    } else if (q < 4) {
-      fq_sub(o, v[VYZ][c], v[VB][c]);
-      fq_sub(o, o, v[VC][c]);
-      if (q == 3) fq_neg(o, o);
-      v[VH + (q - 2)][c] = o;
-    } else {
-      fq_dbl(t, v[VJ][c]);
-      fq_add(o, t, v[VJ][c]);
-      v[VJ3][c] = o;
-    }
-  }
-  W12_SYNC();
-  // round 2: 0-2 a d, 3-4 g^2, 5-6 e^2, 7-9 b h, 10-11 (-h) py, 12-13 (3 j) px
-  if (lane < 14) {
-    Fq a, b;
-    if (lane < 3) {
-      w_kar_operand(a, v[VA], v[VA], false, lane);
-      w_kar_operand(b, v[VD], v[VD], false, lane);
-    } else if (lane < 7) {
-      w_sqr_operands(a, b, lane < 5 ? v[VG] : v[VE], (lane - 3) & 1);
-    } else if (lane < 10) {
-      w_kar_operand(a, v[VB], v[VB], false, lane - 7);
-      w_kar_operand(b, v[VH], v[VH], false, lane - 7);
-    } else if (lane < 12) {
-      a = v[VNH][lane - 10];
-      b = s->p.y;
-    } else {
-      a = v[VJ3][lane - 12];
-      b = s->p.x;
-    }
-    fq_mul_ol(&s->kar[lane], &a, &b);
-  }
-  W12_SYNC();
-  if (lane < 12) {
-    const int c = lane & 1, q = lane >> 1;
-    Fq o;
-    if (q == 0) w_fq2_from_kar(o, &s->kar[0], c);            // x' = a (b - 3 e)
-    else if (q == 1) {                                       // y' = g^2 - 3 e^2
-      Fq g2v, e2v, t;
-      w_sqr_asm(g2v, s->kar[3], s->kar[4], c);
-      w_sqr_asm(e2v, s->kar[5], s->kar[6], c);
-      fq_dbl(t, e2v);
-      fq_add(t, t, e2v);
-      fq_sub(o, g2v, t);
-    } else if (q == 2) w_fq2_from_kar(o, &s->kar[7], c);     // z' = b h
-    else if (q == 3) o = s->kar[10 + c];                     // l0 = -h py
-    else if (q == 4) o = s->kar[12 + c];                     // l3 = 3 j px
-    else fq_sub(o, v[VE][c], v[VB][c]);                      // l4 = e - b
-    Fq* dst = q == 0 ? reinterpret_cast<Fq*>(&s->r.x)
-            : q == 1 ? reinterpret_cast<Fq*>(&s->r.y)
-            : q == 2 ? reinterpret_cast<Fq*>(&s->r.z)
-            : q == 3 ? w12_q(&s->line) + 0
-            : q == 4 ? w12_q(&s->line) + 6
-                     : w12_q(&s->line) + 8;
-    dst[c] = o;                                              // r was last read in round 1
-  }
-  W12_SYNC();
+  team_sync(tm);
 }
 
-// s->p, s->q loaded; result in s->f
-static __device__ __noinline__ void w_miller_loop(WMiller* s) {
-  const int lane = threadIdx.x;
-  W12_SYNC();
-  if (lane < 6) {
-    *w12_c(&s->f, lane) = lane == 0 ? fq2_one() : fq2_zero();
-    *w12_c(&s->line, lane) = fq2_zero();
+// s->p, s->q loaded; result in s->f (canonical)
+static __device__ __noinline__ void w_miller_loop(WMiller* s, Team tm) {
+  team_sync(tm);
+  if (tm.tid < 6) {
+    *w12_c(&s->f, tm.tid) = tm.tid == 0 ? fq2_one() : fq2_zero();
+    *w12_c(&s->line, tm.tid) = fq2_zero();
   }
-  if (lane == 6) {
-    s->r.x = s->q.x;
-    s->r.y = s->q.y;
-    s->r.z = fq2_one();
+  if (tm.tid == 6) {
+    s->d.r.x = s->q.x;
+    s->d.r.y = s->q.y;
+    s->d.r.z = fq2_one();
+    s->d.px = s->p.x;
+    s->d.py = s->p.y;
   }
-  W12_SYNC();
-  if (affine_is_inf(s->p) || affine2_is_inf(s->q)) return;   // uniform across the warp
+  team_sync(tm);
+  if (affine_is_inf(s->p) || affine2_is_inf(s->q)) return;   // uniform across the team
   for (int bit = 62; bit >= 0; bit--) {
-    if (bit != 62) w12_sqr(&s->f, &s->f, &s->w);
-    w_double_step(s);
-    w12_mul(&s->f, &s->f, &s->line, &s->w);
+    if (bit != 62) w12_sqr(&s->f, &s->f, &s->w, tm);
+    w_double_step(&s->d, &s->line, tm);
+    w12_mul(&s->f, &s->f, &s->line, &s->w, tm);
     if ((BLS_X >> bit) & 1) {
-      if (lane == 0) {
-        Fq2 l0, l3, l4;
-        G2Hom r = s->r;
-        g2_add_line(r, l0, l3, l4, s->q, s->p.x, s->p.y);
-        s->r = r;
-        *w12_c(&s->line, 0) = l0;
-        *w12_c(&s->line, 3) = l3;
-        *w12_c(&s->line, 4) = l4;
-      }
-      W12_SYNC();
-      w12_mul(&s->f, &s->f, &s->line, &s->w);
+      w_add_step(&s->d, &s->q, &s->line, tm);
+      w12_mul(&s->f, &s->f, &s->line, &s->w, tm);
     }
   }
+  w12_canon(&s->f, tm);
 }
 
-// f[j] = Miller(g1[j], g2[j ^ xor_mask]), one 64-thread CTA per pair
+// f[j] = Miller(g1[j], g2[j ^ xor_mask]), one CTA (64 or 32 threads) per pair
 __global__ void __launch_bounds__(W12_THREADS, 8) k_miller_coop(const uint4* __restrict__ g1, const uint4* __restrict__ g2,
                                                     uint32_t xor_mask, uint4* __restrict__ f_out) {
   __shared__ WMiller s;
+  const Team tm = team_cta();
   const int lane = threadIdx.x;
   const uint32_t j = blockIdx.x;
   uint4* p4 = reinterpret_cast<uint4*>(&s.p);
   uint4* q4 = reinterpret_cast<uint4*>(&s.q);
   if (lane < 6) p4[lane] = g1[6 * (size_t)j + lane];
   if (lane >= 8 && lane < 20) q4[lane - 8] = g2[12 * (size_t)(j ^ xor_mask) + (lane - 8)];
-  W12_SYNC();
-  w_miller_loop(&s);
-  W12_SYNC();
+  team_sync(tm);
+  w_miller_loop(&s, tm);
+  team_sync(tm);
   const uint4* f4 = reinterpret_cast<const uint4*>(&s.f);
   for (int i = lane; i < 36; i += blockDim.x) f_out[36 * (size_t)j + i] = f4[i];
+}
+
+// ---- pipelined Miller loop: the point chain and the f chain on different warps ----------------------------------------------
+// The line functions depend on (P, Q) only: r -> 2 r (+ Q) never looks at f. In the sequential loop above a round is
+// f^2 | doubling step | f * line, one after the other on the same lanes -- and the doubling step (three dependent product
+// rounds) is the longest of the three. Here warp 2 of a three-warp CTA runs the point chain on its own (doubling and
+// addition steps, one-warp team) and hands the lines to warps 0-1 through a ring of MP_RING slots; warps 0-1 run
+// f <- f^2 * line. The two chains overlap completely; the loop takes max(point chain, f chain) instead of their sum.
+// Hand-over with named barriers, the producer / consumer pattern of bar.arrive + bar.sync: barrier 2 + b = "slot b is
+// full" (warp 2 arrives, warps 0-1 wait), 2 + MP_RING + b = "slot b is free" (warps 0-1 arrive, warp 2 waits); barrier 1
+// is the f team's own.
+constexpr int MP_RING = 4;
+constexpr int MP_THREADS = 96;
+constexpr int mp_events() {
+  int e = 0;
+  for (int bit = 62; bit >= 0; bit--) e += 1 + (int)((BLS_X >> bit) & 1);
+  return e;
+}
+constexpr int MP_EVENTS = mp_events();
+struct WMillerPipe {
+  Fq12 f;
+  Fq12 line[MP_RING];   // slots 1, 2, 5 of every entry stay zero
+  WDouble d;
+  Affine2 q;
+  Affine p;
+  WScratch w;
+};
+__device__ __forceinline__ void mp_bar_sync(int id) { asm volatile("bar.sync %0, 96;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void mp_bar_arrive(int id) {
+  __threadfence_block();
+  asm volatile("bar.arrive %0, 96;" ::"r"(id) : "memory");
+}
+__global__ void __launch_bounds__(MP_THREADS, 5) k_miller_pipe(const uint4* __restrict__ g1, const uint4* __restrict__ g2,
+                                                               uint32_t xor_mask, uint4* __restrict__ f_out) {
+  __shared__ WMillerPipe s;
+  const int tid = threadIdx.x;
+  const uint32_t j = blockIdx.x;
+  uint4* p4 = reinterpret_cast<uint4*>(&s.p);
+  uint4* q4 = reinterpret_cast<uint4*>(&s.q);
+  if (tid < 6) p4[tid] = g1[6 * (size_t)j + tid];
+  if (tid >= 8 && tid < 20) q4[tid - 8] = g2[12 * (size_t)(j ^ xor_mask) + (tid - 8)];
+  uint4* l4 = reinterpret_cast<uint4*>(&s.line[0]);
+  for (int i = tid; i < 36 * MP_RING; i += MP_THREADS) l4[i] = make_uint4(0, 0, 0, 0);
+  if (tid >= 32 && tid < 38) *w12_c(&s.f, tid - 32) = tid == 32 ? fq2_one() : fq2_zero();
+  __syncthreads();
+  if (affine_is_inf(s.p) || affine2_is_inf(s.q)) {   // uniform across the CTA: the Miller value is 1
+    const uint4* f4 = reinterpret_cast<const uint4*>(&s.f);
+    for (int i = tid; i < 36; i += MP_THREADS) f_out[36 * (size_t)j + i] = f4[i];
+    return;
+  }
+  if (tid >= 64) {
+    // the point chain
+    Team tm;
+    tm.tid = tid - 64;
+    tm.size = 32;
+    tm.mode = 1;
+    if (tm.tid == 0) {
+      s.d.r.x = s.q.x;
+      s.d.r.y = s.q.y;
+      s.d.r.z = fq2_one();
+      s.d.px = s.p.x;
+      s.d.py = s.p.y;
+    }
+    __syncwarp();
+    int e = 0;
+    for (int bit = 62; bit >= 0; bit--) {
+      if (e >= MP_RING) mp_bar_sync(2 + MP_RING + e % MP_RING);
+      w_double_step(&s.d, &s.line[e % MP_RING], tm);
+      mp_bar_arrive(2 + e % MP_RING);
+      e++;
+      if ((BLS_X >> bit) & 1) {
+        if (e >= MP_RING) mp_bar_sync(2 + MP_RING + e % MP_RING);
+        w_add_step(&s.d, &s.q, &s.line[e % MP_RING], tm);
+        mp_bar_arrive(2 + e % MP_RING);
+        e++;
+      }
+    }
+  } else {
+    // the f chain
+    Team tm;
+    tm.tid = tid;
+    tm.size = 64;
+    tm.mode = 2;
+    int e = 0;
+    for (int bit = 62; bit >= 0; bit--) {
+      if (bit != 62) w12_sqr(&s.f, &s.f, &s.w, tm);
+      for (int step = 0; step <= (int)((BLS_X >> bit) & 1); step++) {
+        mp_bar_sync(2 + e % MP_RING);
+        w12_mul(&s.f, &s.f, &s.line[e % MP_RING], &s.w, tm);
+        if (e + MP_RING < MP_EVENTS) mp_bar_arrive(2 + MP_RING + e % MP_RING);
+        e++;
+      }
+    }
+    w12_canon(&s.f, tm);
+    const uint4* f4 = reinterpret_cast<const uint4*>(&s.f);
+    if (tid < 36) f_out[36 * (size_t)j + tid] = f4[tid];
+  }
 }
 
 // product tree level, one CTA per output: out[s][t] = prod_k in[s][t + k m]
@@ -624,6 +407,7 @@ __global__ void __launch_bounds__(W12_THREADS) k_fq12_prod_level_coop(const uint
                                                              uint4* __restrict__ out) {
   __shared__ Fq12 acc, x;
   __shared__ WScratch w;
+  const Team tm = team_cta();
   const int lane = threadIdx.x;
   const uint32_t t = blockIdx.x;
   const uint4* src = in + 36 * (size_t)blockIdx.y * len;
@@ -633,23 +417,24 @@ __global__ void __launch_bounds__(W12_THREADS) k_fq12_prod_level_coop(const uint
   for (int k = 1; k < FQ12_FAN; k++) {
     const uint64_t idx = (uint64_t)t + (uint64_t)k * m;
     if (idx >= len) break;
-    W12_SYNC();
+    team_sync(tm);
     for (int i = lane; i < 36; i += blockDim.x) x4[i] = src[36 * idx + i];
-    W12_SYNC();
-    w12_mul(&acc, &acc, &x, &w);
+    team_sync(tm);
+    w12_mul(&acc, &acc, &x, &w, tm);
   }
-  W12_SYNC();
+  w12_canon(&acc, tm);
   for (int i = lane; i < 36; i += blockDim.x) out[36 * ((size_t)blockIdx.y * m + t) + i] = a4[i];
 }
 
 // out[b] = final_exponentiation(in[b]); one CTA per product
 __global__ void __launch_bounds__(W12_THREADS) k_final_exp(const uint4* __restrict__ in, uint4* __restrict__ out) {
   __shared__ WFinalExp s;
+  const Team tm = team_cta();
   const int lane = threadIdx.x;
   uint4* f4 = reinterpret_cast<uint4*>(&s.f);
   for (int i = lane; i < 36; i += blockDim.x) f4[i] = in[36 * (size_t)blockIdx.x + i];
-  W12_SYNC();
-  w12_final_exp(&s);
+  team_sync(tm);
+  w12_final_exp(&s, tm);
   const uint4* r4 = reinterpret_cast<const uint4*>(&s.r);
   for (int i = lane; i < 36; i += blockDim.x) out[36 * (size_t)blockIdx.x + i] = r4[i];
 }
@@ -1096,6 +881,7 @@ __global__ void __launch_bounds__(64) k_fold_apply_g2(uint4* __restrict__ h, uin
 //   (warp-cooperative versions: element i is processed by the whole warp of block i / launched with n blocks)
 __global__ void __launch_bounds__(W12_THREADS) k_test_w12_op(int op, const uint4* a, const uint4* b, uint4* out) {
   __shared__ WFinalExp s;
+  const Team tm = team_cta();
   const int lane = threadIdx.x;
   uint4* f4 = reinterpret_cast<uint4*>(&s.f);
   uint4* g4 = reinterpret_cast<uint4*>(&s.f2);
@@ -1103,30 +889,38 @@ __global__ void __launch_bounds__(W12_THREADS) k_test_w12_op(int op, const uint4
     f4[i] = a[36 * (size_t)blockIdx.x + i];
     g4[i] = b[36 * (size_t)blockIdx.x + i];
   }
-  W12_SYNC();
+  team_sync(tm);
   switch (op) {
-    case 20: w12_mul(&s.r, &s.f, &s.f2, &s.w); break;
-    case 21: w12_sqr(&s.r, &s.f, &s.w); break;
-    case 22: w12_cyclotomic_sqr(&s.r, &s.f, &s.w); break;
-    case 23: w12_final_exp(&s); break;
-    case 24: w12_frobenius(&s.r, &s.f, 1); break;
-    case 25: w12_frobenius(&s.r, &s.f, 2); break;
-    case 26: w12_mul(&s.f, &s.f, &s.f, &s.w); w12_copy(&s.r, &s.f); break;     // aliasing
+    case 20: w12_mul(&s.r, &s.f, &s.f2, &s.w, tm); break;
+    case 21: w12_sqr(&s.r, &s.f, &s.w, tm); break;
+    case 22: w12_cyclotomic_sqr(&s.r, &s.f, &s.w, tm); break;
+    case 23: w12_final_exp(&s, tm); break;
+    case 24: w12_frobenius(&s.r, &s.f, 1, tm); break;
+    case 25: w12_frobenius(&s.r, &s.f, 2, tm); break;
+    case 26: w12_mul(&s.f, &s.f, &s.f, &s.w, tm); w12_copy(&s.r, &s.f, tm); break;     // aliasing
     case 28: {                                                                  // cooperative Miller loop: a = G1 || G2
       __shared__ WMiller ms;
       uint4* p4 = reinterpret_cast<uint4*>(&ms.p);
       uint4* q4 = reinterpret_cast<uint4*>(&ms.q);
       if (lane < 6) p4[lane] = a[36 * (size_t)blockIdx.x + lane];
       if (lane >= 8 && lane < 20) q4[lane - 8] = a[36 * (size_t)blockIdx.x + 6 + (lane - 8)];
-      W12_SYNC();
-      w_miller_loop(&ms);
-      w12_copy(&s.r, &ms.f);
+      team_sync(tm);
+      w_miller_loop(&ms, tm);
+      w12_copy(&s.r, &ms.f, tm);
       break;
     }
-    case 27: w12_cyclotomic_sqr(&s.f, &s.f, &s.w); w12_conj(&s.r, &s.f); break;
+    case 27: w12_cyclotomic_sqr(&s.f, &s.f, &s.w, tm); w12_conj(&s.r, &s.f, tm); break;
+    case 29: {                                                                  // a chain: ((a b)^2 a)^2 conj, lazily reduced throughout
+      w12_mul(&s.r, &s.f, &s.f2, &s.w, tm);
+      w12_sqr(&s.r, &s.r, &s.w, tm);
+      w12_mul(&s.r, &s.r, &s.f, &s.w, tm);
+      w12_sqr(&s.r, &s.r, &s.w, tm);
+      w12_conj(&s.r, &s.r, tm);
+      break;
+    }
     default: break;
   }
-  W12_SYNC();
+  w12_canon(&s.r, tm);
   const uint4* r4 = reinterpret_cast<const uint4*>(&s.r);
   for (int i = lane; i < 36; i += blockDim.x) out[36 * (size_t)blockIdx.x + i] = r4[i];
 }
