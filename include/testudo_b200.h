@@ -311,7 +311,7 @@ int tb200_mipp_cross_all(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_u_l[12
                          uint64_t comm_t_l[72], uint64_t comm_t_r[72]);
 /* out[i] = base[i] ^ exps[i] in GT (the verifier's `tx.pow(c)`, src/mipp.rs:252-255); exponents are Fr values
  * (canonical, or Montgomery with TB200_SCALARS_MONT). */
-/* tuning/test hook: pairing products of up to `n` pairs run one WARP per Miller loop, larger ones one THREAD (default 2048) */
+/* tuning/test hook: pairing products of up to `n` pairs run one WARP per Miller loop, larger ones one THREAD (default 8192) */
 void tb200_set_pairing_coop_max(int n);
 /* lanes of a cooperative Fq12 team (CTA-per-pair Miller loops, product tree, final exponentiation): 64 = two warps, one
  * item per lane in every phase; 32 = one warp per pair (twice the resident pairs: higher throughput); 96 = the pipelined

@@ -28,4 +28,4 @@ for n in (256, 512, 1024, 2048, 4096, 8192, 16384):
         assert ref is None or np.array_equal(ref, out)
         ref = out
     print(f"n={n}: miller thread-per-pair {row[0]} ms, CTA-per-pair {row[1]} ms", flush=True)
-lib.tb200_set_pairing_coop_max(2048)
+lib.tb200_set_pairing_coop_max(8192)

@@ -245,8 +245,35 @@ void hcw_double_step(WDouble* d, Fq12* line) {
   for (int t = 0; t < 14; t++) wp_dbl_r2(d, t);
   for (int t = 0; t < 12; t++) wp_dbl_p5(d, line, t);
 }
+void hcw_add_step(WDouble* d, const Affine2* q, Fq12* line) {
+  for (int t = 0; t < 6; t++) wp_add_rA(d, q, t);
+  for (int t = 0; t < 4; t++) wp_add_pA(d, t);
+  for (int t = 0; t < 14; t++) wp_add_rB(d, q, t);
+  for (int t = 0; t < 10; t++) wp_add_pB(d, line, t);
+  for (int t = 0; t < 9; t++) wp_add_rC(d, t);
+  for (int t = 0; t < 6; t++) wp_add_pC(d, t);
+  for (int t = 0; t < 12; t++) wp_add_rD(d, t);
+  for (int t = 0; t < 6; t++) wp_add_pD(d, t);
+}
 }  // namespace
 extern "C" {
+// lazily reduced addition step vs the canonical g2_add_line: r (3 Fq2), q (2 Fq2), px, py canonical; 1 when they agree
+int hc_coop_add_step(const uint32_t* r_in, const uint32_t* q_in, const uint32_t* px, const uint32_t* py) {
+  WDouble d;
+  Fq12 line;
+  memset(&line, 0, sizeof line);
+  Affine2 q;
+  memcpy(&d.r, r_in, 288);
+  memcpy(&q, q_in, 192);
+  memcpy(&d.px, px, 48);
+  memcpy(&d.py, py, 48);
+  G2Hom r = d.r;
+  hcw_add_step(&d, &q, &line);
+  Fq2 l0, l3, l4;
+  g2_add_line(r, l0, l3, l4, q, d.px, d.py);
+  return memcmp(&r, &d.r, 288) == 0 && memcmp(&l0, w12_c(&line, 0), 96) == 0 && memcmp(&l3, w12_c(&line, 3), 96) == 0 &&
+         memcmp(&l4, w12_c(&line, 4), 96) == 0;
+}
 // op: 0 mul, 1 sqr, 2 cyclotomic sqr, 3 frobenius 1, 4 frobenius 2, 5 conj, 6 the chain ((a b)^2 a)^2 conj, 7 exp_by_x,
 // 8 final exponentiation. a, b: raw 12-limb coefficients (any representative < 1.02 q); r canonical.
 void hc_coop_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
@@ -332,11 +359,7 @@ void hc_coop_miller(const uint32_t* p_aff, const uint32_t* q_aff, uint32_t* out)
       hcw_double_step(&d, &line);
       hcw_mul(&f, &f, &line);
       if ((BLS_X >> bit) & 1) {
-        Fq2 l0, l3, l4;
-        g2_add_line(d.r, l0, l3, l4, q, p.x, p.y);
-        *w12_c(&line, 0) = l0;
-        *w12_c(&line, 3) = l3;
-        *w12_c(&line, 4) = l4;
+        hcw_add_step(&d, &q, &line);
         hcw_mul(&f, &f, &line);
       }
     }
@@ -380,6 +403,14 @@ int hc_coop_stress(uint64_t seed, int iters) {
     Fq2 l0, l3, l4;
     hcw_double_step(&d, &line);
     g2_double_line(r, l0, l3, l4, w12_q(&cb)[0], w12_q(&cb)[1]);
+    bad += !(memcmp(&r, &d.r, 288) == 0 && memcmp(&l0, w12_c(&line, 0), 96) == 0 && memcmp(&l3, w12_c(&line, 3), 96) == 0 &&
+             memcmp(&l4, w12_c(&line, 4), 96) == 0);
+    // addition step: r = the first three Fq2 of ca, q = the next two
+    Affine2 q; memcpy(&q, w12_c(&ca, 3), 192);
+    memcpy(&d.r, &ca, 288); memcpy(&r, &ca, 288);
+    memset(&line, 0, sizeof line);
+    hcw_add_step(&d, &q, &line);
+    g2_add_line(r, l0, l3, l4, q, d.px, d.py);
     bad += !(memcmp(&r, &d.r, 288) == 0 && memcmp(&l0, w12_c(&line, 0), 96) == 0 && memcmp(&l3, w12_c(&line, 3), 96) == 0 &&
              memcmp(&l4, w12_c(&line, 4), 96) == 0);
   }

@@ -114,7 +114,7 @@ def test_cooperative_miller_loop_and_both_launch_modes(engine):
         engine.tb200_set_pairing_coop_max(1 << 20)
         warp_mode = pairing.multi_pairing(A, B)
     finally:
-        engine.tb200_set_pairing_coop_max(2048)
+        engine.tb200_set_pairing_coop_max(8192)
     assert np.array_equal(thread_mode, warp_mode)
     assert pr.from_words(warp_mode) == pr.multi_pairing(ps, qs)
 

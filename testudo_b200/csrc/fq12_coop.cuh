@@ -572,4 +572,203 @@ TB_HD void wp_dbl_p5(WDouble* s, Fq12* line, int t) {
   dst[c] = o;
 }
 
+// ---- addition step of the Miller loop (ark `add_in_place`, see g2_add_line) on parallel lanes ----------------------------------
+// r = r + q and the line (l0, l3, l4) = (lambda py, -theta px, theta q.x - lambda q.y). On one thread the step is ~30
+// dependent Fq products (~60 us); here four product rounds (6, 14, 9, 12 lanes) with the recombinations in between.
+// r, q, px, py canonical on entry; r canonical and the line coefficients canonical on exit. Uses WDouble's scratch.
+enum { WA_TH = 0, WA_LA, WA_C, WA_D, WA_E, WA_H, WA_GMH };
+// S = kar[2] - kar[0] - kar[1] (wrapping): the u coefficient of a Karatsuba Fq2 product
+TB_HD void wl_kar_c1(Fq& o, const Fq* kar) {
+  lz_sub(o, kar[2], kar[0]);
+  lz_sub(o, o, kar[1]);
+}
+// round A, item t < 6: q.y r.z (0-2), q.x r.z (3-5); operands < 2 q: kar < 1.03 q
+TB_HD void wp_add_rA(WDouble* s, const Affine2* q, int t) {
+  const Fq* rz = reinterpret_cast<const Fq*>(&s->r.z);
+  const Fq* qc = reinterpret_cast<const Fq*>(t < 3 ? &q->y : &q->x);
+  Fq a, b;
+  wl_kar_operand(a, qc, qc, false, t % 3);
+  wl_kar_operand(b, rz, rz, false, t % 3);
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 4: theta = r.y - q.y r.z, lambda = r.x - q.x r.z:  c0 = src.0 - k0 + 5 k1 + 2 q < 8.2 q,  c1 = src.1 - S + 2 q < 5.1 q
+TB_HD void wp_add_pA(WDouble* s, int t) {
+  const int which = t >> 1, c = t & 1;
+  const Fq* src = reinterpret_cast<const Fq*>(which == 0 ? &s->r.y : &s->r.x);
+  const Fq* k = &s->kar[3 * which];
+  Fq o, m;
+  if (c == 0) {
+    lz_mul5(m, k[1]);
+    lz_sub(o, src[0], k[0]);
+    lz_add(o, o, m);
+  } else {
+    wl_kar_c1(m, k);
+    lz_sub(o, src[1], m);
+  }
+  lz_add_kq<2>(o);
+  s->v[WA_TH + which][c] = o;
+}
+// round B, item t < 14: 0-1 theta^2, 2-3 lambda^2 (operands < 13.3 q, < 34.2 q: kar < 4 q / < 1.28 q), 4-6 theta q.x,
+// 7-9 lambda q.y (< 1.18 q), 10-11 lambda py, 12-13 theta px (< 1.06 q)
+TB_HD void wp_add_rB(WDouble* s, const Affine2* q, int t) {
+  Fq(*v)[2] = s->v;
+  Fq a, b;
+  if (t < 4) {
+    wl_sqr_operands<26>(a, b, v[WA_TH + (t >> 1)], t & 1);
+  } else if (t < 10) {
+    const int which = (t - 4) / 3, part = (t - 4) % 3;
+    const Fq* qc = reinterpret_cast<const Fq*>(which == 0 ? &q->x : &q->y);
+    wl_kar_operand(a, v[WA_TH + which], v[WA_TH + which], false, part);
+    wl_kar_operand(b, qc, qc, false, part);
+  } else if (t < 12) {
+    a = v[WA_LA][t - 10];
+    b = s->py;
+  } else {
+    a = v[WA_TH][t - 12];
+    b = s->px;
+  }
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 10: 0-3 c = theta^2, d = lambda^2 (< 9.1 q, 2.6 q); 4-5 l4 = theta q.x - lambda q.y; 6-7 l0 = lambda py;
+// 8-9 l3 = -theta px; the line coefficients canonical
+TB_HD void wp_add_pB(WDouble* s, Fq12* line, int t) {
+  const int c = t & 1;
+  Fq o, m;
+  if (t < 4) {
+    const int which = t >> 1;
+    wl_sqr_asm(o, s->kar[2 * which], s->kar[2 * which + 1], c);
+    s->v[WA_C + which][c] = o;
+    return;
+  }
+  if (t < 6) {
+    const Fq* ka = &s->kar[4];   // theta q.x
+    const Fq* kb = &s->kar[7];   // lambda q.y
+    if (c == 0) {                // ka0 - kb0 + 5 (kb1 - ka1) + 8 q < 15.1 q
+      lz_sub(m, kb[1], ka[1]);
+      lz_mul5(m, m);
+      lz_sub(o, ka[0], kb[0]);
+      lz_add(o, o, m);
+      lz_add_kq<8>(o);
+    } else {                     // S(a) - S(b) + 4 q < 7.6 q
+      wl_kar_c1(o, ka);
+      wl_kar_c1(m, kb);
+      lz_sub(o, o, m);
+      lz_add_kq<4>(o);
+    }
+    lz_canon(o);
+    w12_q(line)[8 + c] = o;
+  } else if (t < 8) {
+    o = s->kar[10 + c];
+    lz_canon(o);
+    w12_q(line)[0 + c] = o;
+  } else {
+    lz_neg_kq<2>(o, s->kar[12 + c]);
+    lz_canon(o);
+    w12_q(line)[6 + c] = o;
+  }
+}
+// round C, item t < 9: e = lambda d (0-2: < 2.02 q), f = r.z c (3-5: < 1.16 q), g = r.x d (6-8: < 1.16 q)
+TB_HD void wp_add_rC(WDouble* s, int t) {
+  Fq(*v)[2] = s->v;
+  const int pr = t / 3, part = t % 3;
+  const Fq* x = pr == 0 ? v[WA_LA] : reinterpret_cast<const Fq*>(pr == 1 ? &s->r.z : &s->r.x);
+  const Fq* y = pr == 1 ? v[WA_C] : v[WA_D];
+  Fq a, b;
+  wl_kar_operand(a, x, x, false, part);
+  wl_kar_operand(b, y, y, false, part);
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 6: e (< 13.1 q, 7.1 q), h = e + f - 2 g (reduced), g - h = 3 g - e - f (reduced), straight from the products:
+//   with X_i = ke_i + kf_i - 2 kg_i:   h.0 = X_0 - 5 X_1 + 19 q < 33.8 q,   h.1 = S(e) + S(f) - 2 S(g) + 9 q < 16.9 q
+//   with Y_i = 3 kg_i - ke_i - kf_i:   (g-h).0 = Y_0 - 5 Y_1 + 21 q < 40.4 q,   (g-h).1 = 3 S(g) - S(e) - S(f) + 11 q < 20.9 q
+TB_HD void wp_add_pC(WDouble* s, int t) {
+  const int what = t >> 1, c = t & 1;
+  const Fq* ke = &s->kar[0];
+  const Fq* kf = &s->kar[3];
+  const Fq* kg = &s->kar[6];
+  Fq o;
+  if (what == 0) {
+    wl_fq2_from_kar<11, 5>(o, ke, c);
+    s->v[WA_E][c] = o;
+    return;
+  }
+  Fq xe, xf, xg, m;
+  if (c == 0) {
+    Fq x0, x1;
+    if (what == 1) {
+      lz_dbl(m, kg[0]);
+      lz_add(x0, ke[0], kf[0]);
+      lz_sub(x0, x0, m);
+      lz_dbl(m, kg[1]);
+      lz_add(x1, ke[1], kf[1]);
+      lz_sub(x1, x1, m);
+    } else {
+      lz_mul3(m, kg[0]);
+      lz_sub(x0, m, ke[0]);
+      lz_sub(x0, x0, kf[0]);
+      lz_mul3(m, kg[1]);
+      lz_sub(x1, m, ke[1]);
+      lz_sub(x1, x1, kf[1]);
+    }
+    lz_mul5(x1, x1);
+    lz_sub(o, x0, x1);
+    if (what == 1) lz_add_kq<19>(o);
+    else lz_add_kq<21>(o);
+  } else {
+    wl_kar_c1(xe, ke);
+    wl_kar_c1(xf, kf);
+    wl_kar_c1(xg, kg);
+    if (what == 1) {
+      lz_dbl(m, xg);
+      lz_add(o, xe, xf);
+      lz_sub(o, o, m);
+      lz_add_kq<9>(o);
+    } else {
+      lz_mul3(m, xg);
+      lz_sub(o, m, xe);
+      lz_sub(o, o, xf);
+      lz_add_kq<11>(o);
+    }
+  }
+  lz_reduce(o);
+  s->v[what == 1 ? WA_H : WA_GMH][c] = o;
+}
+// round D, item t < 12: lambda h (0-2), theta (g - h) (3-5): < 1.18 q; e r.y (6-8), r.z e (9-11): < 1.27 q
+TB_HD void wp_add_rD(WDouble* s, int t) {
+  Fq(*v)[2] = s->v;
+  const int pr = t / 3, part = t % 3;
+  const Fq* x = pr == 0 ? v[WA_LA] : pr == 1 ? v[WA_TH] : v[WA_E];
+  const Fq* y = pr == 0 ? v[WA_H] : pr == 1 ? v[WA_GMH] : reinterpret_cast<const Fq*>(pr == 2 ? &s->r.y : &s->r.z);
+  Fq a, b;
+  wl_kar_operand(a, x, x, false, part);
+  wl_kar_operand(b, y, y, false, part);
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 6: r.x = lambda h, r.y = theta (g - h) - e r.y, r.z = r.z e; canonical
+TB_HD void wp_add_pD(WDouble* s, int t) {
+  const int which = t >> 1, c = t & 1;
+  Fq o, m;
+  if (which == 0) wl_fq2_from_kar<7, 3>(o, &s->kar[0], c);
+  else if (which == 2) wl_fq2_from_kar<7, 3>(o, &s->kar[9], c);
+  else {
+    const Fq* ka = &s->kar[3];
+    const Fq* kb = &s->kar[6];
+    if (c == 0) {                // ka0 - kb0 + 5 (kb1 - ka1) + 8 q < 15.6 q
+      lz_sub(m, kb[1], ka[1]);
+      lz_mul5(m, m);
+      lz_sub(o, ka[0], kb[0]);
+      lz_add(o, o, m);
+      lz_add_kq<8>(o);
+    } else {                     // S(a) - S(b) + 4 q < 7.7 q
+      wl_kar_c1(o, ka);
+      wl_kar_c1(m, kb);
+      lz_sub(o, o, m);
+      lz_add_kq<4>(o);
+    }
+  }
+  lz_canon(o);
+  Fq* dst = reinterpret_cast<Fq*>(which == 0 ? &s->r.x : which == 1 ? &s->r.y : &s->r.z);
+  dst[c] = o;
+}
+
 }  // namespace tb

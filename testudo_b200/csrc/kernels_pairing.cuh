@@ -219,7 +219,7 @@ static __device__ __noinline__ void w12_final_exp(WFinalExp* s, Team tm) {
 // Thread-per-pair keeps the integer pipe fed only when there are thousands of pairs; the MIPP rounds of the reference
 // issue products of 2^12 ... 1 pairs and every one of them waits for a full 10 ms single-thread Miller loop. Below ~2^11
 // pairs a team owns a pair: f^2 and f * line are the cooperative Fq12 operations above, the doubling step runs its
-// 11 + 14 independent Fq products on parallel lanes (fq12_coop.cuh), and only the six addition steps of the loop are serial.
+// 11 + 14 independent Fq products on parallel lanes (fq12_coop.cuh), and so do the six addition steps of the loop.
 struct WMiller {
   Fq12 f, line;      // line = (l0, 0, 0) + (l3, l4, 0) w in tower slots 0, 3, 4; slots 1, 2, 5 stay zero
   WDouble d;         // the running point r, P's coordinates, the doubling step's scratch
@@ -245,17 +245,25 @@ static __device__ __noinline__ void w_double_step(WDouble* d, Fq12* line, Team t
   if (tm.tid < 12) wp_dbl_p5(d, line, tm.tid);
   team_sync(tm);
 }
-// the serial addition step (six per loop) on one lane of the team: canonical arithmetic on the canonical r
-__device__ __forceinline__ void w_add_step(WDouble* d, const Affine2* q, Fq12* line, Team tm) {
-  if (tm.tid == 0) {
-    Fq2 l0, l3, l4;
-    G2Hom r = d->r;
-    g2_add_line(r, l0, l3, l4, *q, d->px, d->py);
-    d->r = r;
-    *w12_c(line, 0) = l0;
-    *w12_c(line, 3) = l3;
-    *w12_c(line, 4) = l4;
-  }
+// the addition step (six per loop), four product rounds on parallel lanes (fq12_coop.cuh); on one thread it was ~30
+// dependent Fq products, ~60 us of a 1.15 ms loop each
+static __device__ __noinline__ void w_add_step(WDouble* d, const Affine2* q, Fq12* line, Team tm) {
+  team_sync(tm);
+  if (tm.tid < 6) wp_add_rA(d, q, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 4) wp_add_pA(d, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 14) wp_add_rB(d, q, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 10) wp_add_pB(d, line, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 9) wp_add_rC(d, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 6) wp_add_pC(d, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 12) wp_add_rD(d, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 6) wp_add_pD(d, tm.tid);
   team_sync(tm);
 }
 
