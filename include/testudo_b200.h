@@ -313,10 +313,10 @@ int tb200_mipp_cross_all(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_u_l[12
  * (canonical, or Montgomery with TB200_SCALARS_MONT). */
 /* tuning/test hook: pairing products of up to `n` pairs run one WARP per Miller loop, larger ones one THREAD (default 8192) */
 void tb200_set_pairing_coop_max(int n);
-/* lanes of a cooperative Fq12 team (CTA-per-pair Miller loops, product tree, final exponentiation): 64 = two warps, one
- * item per lane in every phase; 32 = one warp per pair (twice the resident pairs: higher throughput); 96 = the pipelined
- * Miller kernel (the point chain on a third warp next to the f chain: lowest latency; the chain kernels keep two warps);
- * 0 (default) = by size: 32 for Miller stages of more than 512 pairs, 96 otherwise. Identical results. */
+/* tuning/test hook, the Miller kernel of the cooperative pairing engine: 96 = pipelined (three warps per pair, the point
+ * chain next to the f chain: lowest latency), 64 / 32 = one pair per two-warp / one-warp CTA, 33 = two pairs per warp with
+ * a shared accumulator (highest throughput; even products only); the product tree and the final exponentiation run on
+ * two warps unless 32 is forced. 0 (default) = by size: 96 up to 512 pairs, 33 above. Identical results. */
 void tb200_set_pairing_team(int lanes);
 int tb200_gt_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned flags, uint64_t* out);
 

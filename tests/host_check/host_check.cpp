@@ -1,6 +1,7 @@
 // Test-only shim: compiles the product's __host__ __device__ field/group headers with g++ (carry chains
 // emulated) so the algorithm structure can be checked on a CPU-only box. Not part of the product library.
 #include <cstring>
+#include <initializer_list>
 #include "../../testudo_b200/csrc/g1_fast.cuh"
 #include "../../testudo_b200/csrc/digits.cuh"
 #include "../../testudo_b200/csrc/experimental/mont_kara.cuh"
@@ -212,7 +213,18 @@ void hcw_exp_by_x(Fq12* dst, const Fq12* a) {
 void hcw_final_exp(Fq12* out, const Fq12* in) {
   Fq12 f = *in, r, f2, y0, y1, y2;
   hcw_conj(&r, &f);
-  fq12_inv(f2, f);
+  hcw_mul(&y0, &f, &r);
+  {
+    WScratch w;
+    for (int t = 0; t < 18; t++) wp_inv6_r1(&w, &y0, t);
+    for (int t = 0; t < 12; t++) wp_inv6_p1(&w, t);
+    for (int t = 0; t < 6; t++) wp_inv6_p2(&w, t);
+    for (int t = 0; t < 9; t++) wp_inv6_r2(&w, &y0, t);
+    wp_inv6_d(&w);
+    for (int t = 0; t < 9; t++) wp_inv6_r3(&w, t);
+    for (int t = 0; t < 12; t++) wp_inv6_out(&f2, &w, t);
+  }
+  hcw_sqr(&r, &r);
   hcw_mul(&r, &r, &f2);
   f2 = r;
   hcw_frob(&r, &r, 2);
@@ -257,6 +269,21 @@ void hcw_add_step(WDouble* d, const Affine2* q, Fq12* line) {
 }
 }  // namespace
 extern "C" {
+// product of two line values (tower slots 0, 3, 4 of a and b; the other slots are ignored) vs the general product
+int hc_coop_line_mul(const uint32_t* a, const uint32_t* b) {
+  Fq12 x, y, z, ref;
+  memcpy(&x, a, 576);
+  memcpy(&y, b, 576);
+  for (int sl : {1, 2, 5}) { *w12_c(&x, sl) = fq2_zero(); *w12_c(&y, sl) = fq2_zero(); }
+  WScratch w;
+  for (int t = 0; t < 12; t++) wp_ll_xy(&w, &x, &y, t);
+  for (int t = 0; t < 18; t++) wp_kar(&w, t);
+  for (int t = 0; t < 12; t++) wp_fq2(&w, t);
+  for (int t = 0; t < 12; t++) wp_ll_out(&z, &w, t);
+  hcw_canon(&z);
+  fq12_mul(ref, x, y);
+  return memcmp(&z, &ref, 576) == 0;
+}
 // lazily reduced addition step vs the canonical g2_add_line: r (3 Fq2), q (2 Fq2), px, py canonical; 1 when they agree
 int hc_coop_add_step(const uint32_t* r_in, const uint32_t* q_in, const uint32_t* px, const uint32_t* py) {
   WDouble d;

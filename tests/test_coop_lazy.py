@@ -118,6 +118,10 @@ def test_lazy_cyclotomic_chain_and_final_exponentiation(hc):
         x = tuple((rng.randrange(Q), rng.randrange(Q)) for _ in range(6))
         raw = f12_to_raw(x)
         assert run(hc, 8, raw) == pr.final_exponentiation(x)
+    # degenerate shapes for the cooperative Fq6 inversion of the easy part: 1, an element of Fq6, of Fq2, a pure w multiple
+    z = (0, 0)
+    for x in (pr.F12_ONE, ((3, 5), z, (7, 11), z, (13, 17), z), ((Q - 1, Q - 2), z, z, z, z, z), (z, (Q - 1, 1), z, z, z, z)):
+        assert run(hc, 8, f12_to_raw(x)) == pr.final_exponentiation(x)
 
 
 def g2hom_words(pt):
@@ -166,3 +170,12 @@ def test_lazy_miller_loop_on_the_host(hc):
 def test_lazy_bodies_stress_against_the_canonical_tower(hc):
     """4000 products, squarings and doubling steps on representatives biased to 0, q - 1, q and 1.02 q - 1"""
     assert hc.hc_coop_stress(ctypes.c_uint64(0x9E3779B97F4A7C15), 4000) == 0
+
+
+def test_lazy_line_product(hc):
+    """(l0, 0, 0, l3, l4, 0) * (m0, 0, 0, m3, m4, 0) with 18 Fq products == the general Fq12 product"""
+    rng = random.Random(59)
+    cases = [[rng.randrange(Q) for _ in range(12)] for _ in range(8)] + [[Q - 1] * 12, [0] * 12, [1] * 12]
+    for a in cases:
+        for b in cases[::2]:
+            assert hc.hc_coop_line_mul(P(raw_words(a)), P(raw_words(b))) == 1

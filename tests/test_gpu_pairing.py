@@ -239,7 +239,7 @@ def test_pairing_team_sizes_agree(engine, n):
     a = np.tile(np.array([o.affine_to_words(p) for p in ps], dtype=np.uint64).reshape(-1, 12), ((n + 7) // 8, 1))[:n].copy()
     b = np.tile(np.array([o2.affine_to_words(q) for q in qs], dtype=np.uint64).reshape(-1, 24), ((n + 7) // 8, 1))[:n].copy()
     outs = []
-    for team in (64, 32, 96, 0):
+    for team in (64, 32, 33, 96, 0):
         engine.tb200_set_pairing_team(team)
         outs.append(gp.multi_pairing(a, b))
     engine.tb200_set_pairing_team(0)

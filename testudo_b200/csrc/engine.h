@@ -136,7 +136,7 @@ struct Engine {
   int forced_c = 0;
   size_t host_chunk_min = size_t(1) << 21;  // host-facing single MSMs: chunked upload/compute overlap from here
   size_t shard_min = size_t(1) << 18;       // host-facing single MSMs are sharded over the GPUs from ndev * this
-  int pairing_team = 0;                     // lanes of a cooperative Fq12 team: 0 = by size (engine_pairing.cu), 32 / 64 / 96 (pipelined Miller) forced
+  int pairing_team = 0;                     // lanes of a cooperative Fq12 team: 0 = by size (engine_pairing.cu), 32 / 33 (two pairs per warp) / 64 / 96 (pipelined Miller) forced
   int pairing_coop_max = 8192;              // Miller loops: CTA-per-pair up to this many pairs, lanes-per-pair above
   int host_upload_pace = 1;                 // host-facing single MSMs: upload chunk k once chunk k-2 is accumulated
   int host_chunk_count = 0;                 // tuning: chunk sizes in sixteenths of the points (0 = built-in schedule)

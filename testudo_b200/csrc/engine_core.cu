@@ -504,7 +504,7 @@ int tb200_last_geometry(int* c, int* windows, uint64_t* entries, uint64_t* bucke
   return 0;
 }
 void tb200_set_pairing_coop_max(int n) { E.pairing_coop_max = n < 0 ? 0 : n; }
-void tb200_set_pairing_team(int lanes) { E.pairing_team = (lanes == 96 || lanes == 64 || lanes == 32) ? lanes : 0; }
+void tb200_set_pairing_team(int lanes) { E.pairing_team = (lanes == 96 || lanes == 64 || lanes == 33 || lanes == 32) ? lanes : 0; }
 void tb200_set_window_bits(int c) { E.forced_c = (c >= 3 && c <= 22) ? c : 0; }
 void tb200_set_accumulate_mode(int mode) { E.acc_mode = (mode == 3 || mode == 4) ? mode : 0; }
 void tb200_set_pass_entries_max(uint64_t entries) {

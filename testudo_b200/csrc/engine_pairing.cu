@@ -55,15 +55,21 @@ int pairing_products(Ctx& g, const uint4* d_g1, const uint4* d_g2, uint32_t n, u
   if (mark(g, st, "pairing_begin")) return 1;
   // below ~2 waves of resident CTAs one CTA per pair (latency-bound); above, one thread per pair
   const bool coop = n <= (uint32_t)E.pairing_coop_max;
-  // Miller kernels (measured, scripts/time_pairing_team.py): up to 512 pairs the loop's LATENCY counts and the pipelined
-  // kernel is used (three warps per pair: the point chain next to the f chain); above, a one-warp team per pair doubles
-  // the resident pairs and wins once the stage is throughput-bound (1024 pairs: 3.6 vs 5.0 ms with two warps). The chain
-  // kernels (product tree, final exponentiation) keep two warps. tb200_set_pairing_team forces 32 / 64 / 96 (pipelined).
-  const int miller_team = E.pairing_team ? E.pairing_team : (n > 512 ? 32 : 96);
-  const int chain_team = (E.pairing_team == 32 || E.pairing_team == 64) ? E.pairing_team : 64;
+  // Miller kernels (measured, scripts/time_pairing.py): up to 512 pairs the loop's LATENCY counts and the pipelined
+  // kernel is used (three warps per pair: the point chain next to the f chain, 0.50 ms); above, the stage is
+  // throughput-bound and one warp takes TWO pairs with a shared accumulator (k_miller_duo; needs an even segment length).
+  // The chain kernels (product tree, final exponentiation) keep two warps. tb200_set_pairing_team forces 96 (pipelined),
+  // 64 / 32 (one pair per two-warp / one-warp CTA, sequential loop) or 33 (two pairs per warp).
+  const int forced = E.pairing_team;
+  int miller_team = forced ? forced : (n > 512 ? 33 : 96);
+  if (miller_team == 33 && (len & 1)) miller_team = 32;
+  const int chain_team = (forced == 32 || forced == 64) ? forced : 64;
   if (d_gt_in) CU(cudaMemcpyAsync(buf_a, d_gt_in, (size_t)n * 576, cudaMemcpyDeviceToDevice, st));
   else if (coop && miller_team == 96) LAUNCH(k_miller_pipe, n, MP_THREADS, st, d_g1, d_g2, xor_mask, buf_a);
-  else if (coop) LAUNCH(k_miller_coop, n, miller_team, st, d_g1, d_g2, xor_mask, buf_a);
+  else if (coop && miller_team == 33) {
+    LAUNCH(k_miller_duo, n / 2, 32, st, d_g1, d_g2, n, xor_mask, buf_a);
+    len /= 2;   // one value per two pairs; pairs 2b, 2b + 1 lie in the same segment
+  } else if (coop) LAUNCH(k_miller_coop, n, miller_team, st, d_g1, d_g2, xor_mask, buf_a);
   else LAUNCH(k_miller, cdiv(n, 32), 32, st, d_g1, d_g2, n, xor_mask, buf_a);
   if (after_miller) CU(cudaEventRecord(after_miller, st));
   if (mark(g, st, "miller")) return 1;

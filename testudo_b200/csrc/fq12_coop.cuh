@@ -771,4 +771,168 @@ TB_HD void wp_add_pD(WDouble* s, int t) {
   dst[c] = o;
 }
 
+// ---- f^(q^6 - 1) = conj(f) / f without a serial Fq12 inversion ----------------------------------------------------------------
+// With g = conj(f):  g / f = g^2 / (f g)  and  f g = a0^2 - v a1^2 = N lies in Fq6 (f = a0 + a1 w). The drivers compute
+// n12 = f g and g^2 with the cooperative product / squaring; the bodies below invert N in Fq6 on parallel lanes:
+//   t0 = n0^2 - xi n1 n2,  t1 = xi n2^2 - n0 n1,  t2 = n1^2 - n0 n2,   d = xi (n2 t1 + n1 t2) + n0 t0  (in Fq2),
+//   N^-1 = (t0, t1, t2) / d,   1 / d = conj(d) / (d0^2 + 5 d1^2)
+// -- three product rounds and ONE Fq inversion (binary Euclid, one lane) instead of ~150 dependent products and the
+// inversion on one thread (a third of the final exponentiation's time). N's coefficients are read from tower slots
+// 0..2 of n12 (< 1.02 q); the result is written to slots 0..2 of `out`, slots 3..5 are zeroed.
+// round 1, item t < 18: Fq2 products 0: n0 n0, 1: n1 n2, 2: n2 n2, 3: n0 n1, 4: n1 n1, 5: n0 n2 (operands < 2.04 q: kar < 1.03 q)
+TB_HD void wp_inv6_r1(WScratch* w, const Fq12* n12, int t) {
+  const int pr = t / 3, part = t % 3;
+  const int ia = pr == 0 ? 0 : pr == 1 ? 1 : pr == 2 ? 2 : pr == 3 ? 0 : pr == 4 ? 1 : 0;
+  const int ib = pr == 0 ? 0 : pr == 1 ? 2 : pr == 2 ? 2 : pr == 3 ? 1 : pr == 4 ? 1 : 2;
+  const Fq* x = w12_q(n12) + 2 * ia;
+  const Fq* y = w12_q(n12) + 2 * ib;
+  Fq a, b;
+  wl_kar_operand(a, x, x, false, part);
+  wl_kar_operand(b, y, y, false, part);
+  w->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 12: prod[t / 2][t & 1] (< 7.03 q, < 4.03 q)
+TB_HD void wp_inv6_p1(WScratch* w, int t) {
+  Fq o;
+  wl_fq2_from_kar<6, 3>(o, &w->kar[3 * (t / 2)], t & 1);
+  w->prod[t / 2][t & 1] = o;
+}
+// item t < 6: t_i coefficient c -> r6[0][i][c], reduced.  (xi z).0 = -5 z.1, (xi z).1 = z.0
+//   t0 = P0 - xi P1: (P0.0 + 5 P1.1 < 27.2 q,  P0.1 - P1.0 + 8 q < 12.1 q)
+//   t1 = xi P2 - P3: (-5 P2.1 - P3.0 + 28 q < 28 q,  P2.0 - P3.1 + 5 q < 12.1 q)
+//   t2 = P4 - P5:    (+ 8 q < 15.1 q,  + 5 q < 9.1 q)
+TB_HD void wp_inv6_p2(WScratch* w, int t) {
+  const int i = t >> 1, c = t & 1;
+  const Fq(*P)[2] = w->prod;
+  Fq o, m;
+  if (i == 0) {
+    if (c == 0) {
+      lz_mul5(m, P[1][1]);
+      lz_add(o, P[0][0], m);
+    } else {
+      lz_sub(o, P[0][1], P[1][0]);
+      lz_add_kq<8>(o);
+    }
+  } else if (i == 1) {
+    if (c == 0) {
+      lz_mul5(m, P[2][1]);
+      lz_add(m, m, P[3][0]);
+      lz_neg_kq<28>(o, m);
+    } else {
+      lz_sub(o, P[2][0], P[3][1]);
+      lz_add_kq<5>(o);
+    }
+  } else {
+    lz_sub(o, P[4][c], P[5][c]);
+    if (c == 0) lz_add_kq<8>(o);
+    else lz_add_kq<5>(o);
+  }
+  lz_reduce(o);
+  w->r6[0][i][c] = o;
+}
+// round 2, item t < 9: Fq2 products 0: n2 t1, 1: n1 t2, 2: n0 t0 (kar < 1.03 q)
+TB_HD void wp_inv6_r2(WScratch* w, const Fq12* n12, int t) {
+  const int pr = t / 3, part = t % 3;
+  const Fq* x = w12_q(n12) + 2 * (2 - pr);
+  const Fq* y = w->r6[0][pr == 0 ? 1 : pr == 1 ? 2 : 0];
+  Fq a, b;
+  wl_kar_operand(a, x, x, false, part);
+  wl_kar_operand(b, y, y, false, part);
+  w->kar[t] = fq_mul_lz(a, b);
+}
+// ONE item (the team's lane 0): d = xi (Q0 + Q1) + Q2, then 1 / d = (d0, -d1) / (d0^2 + 5 d1^2) -> r6[1][0][0..1], canonical.
+//   d.0 = k6 - 5 k7 - 5 (S0 + S1) + 16 q < 37.8 q,   d.1 = (k0 - 5 k1) + (k3 - 5 k4) + S2 + 13 q < 16.2 q
+TB_HD void wp_inv6_d(WScratch* w) {
+  const Fq* k = w->kar;
+  Fq d0, d1, m, s;
+  wl_kar_c1(m, k + 0);
+  wl_kar_c1(s, k + 3);
+  lz_add(m, m, s);
+  lz_add(m, m, k[7]);
+  lz_mul5(m, m);
+  lz_sub(d0, k[6], m);
+  lz_add_kq<16>(d0);
+  lz_canon(d0);
+  lz_add(m, k[1], k[4]);
+  lz_mul5(m, m);
+  wl_kar_c1(s, k + 6);
+  lz_add(d1, k[0], k[3]);
+  lz_add(d1, d1, s);
+  lz_sub(d1, d1, m);
+  lz_add_kq<13>(d1);
+  lz_canon(d1);
+  Fq n, t5, ni;
+  fq_mul(n, d0, d0);
+  fq_mul(m, d1, d1);
+  fq_mul5(t5, m);
+  fq_add(n, n, t5);
+  fq_inv(ni, n);
+  fq_mul(w->r6[1][0][0], d0, ni);
+  fq_mul(m, d1, ni);
+  fq_neg(w->r6[1][0][1], m);
+}
+// round 3, item t < 9: Fq2 products t_i * (1 / d), i = t / 3
+TB_HD void wp_inv6_r3(WScratch* w, int t) {
+  const int pr = t / 3, part = t % 3;
+  Fq a, b;
+  wl_kar_operand(a, w->r6[0][pr], w->r6[0][pr], false, part);
+  wl_kar_operand(b, w->r6[1][0], w->r6[1][0], false, part);
+  w->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 12: coefficient t of `out`: slots 0..2 = N^-1 (reduced), slots 3..5 = 0
+TB_HD void wp_inv6_out(Fq12* out, const WScratch* w, int t) {
+  Fq o;
+  if (t < 6) {
+    wl_fq2_from_kar<6, 3>(o, &w->kar[3 * (t / 2)], t & 1);
+    lz_reduce(o);
+  } else {
+    o = fq_zero();
+  }
+  w12_q(out)[t] = o;
+}
+
+// ---- L = line_a * line_b for two line values (l0, 0, 0) + (l3, l4, 0) w ------------------------------------------------------
+// With x = (a0, a3, a4), y = (b0, b3, b4) the product is
+//   (x0 y0 + xi x2 y2,  x1 y1,  x1 y2 + x2 y1)  +  (x0 y1 + x1 y0,  x0 y2 + x2 y0,  0) w
+// -- the six Fq2 products of one Karatsuba Fq6 product (wp_kar / wp_fq2 with count = 1), 18 Fq products instead of the 54
+// of a general product. Used where two pairs share one Miller accumulator: f <- f^2 * (line_a line_b).
+// item t < 12: operands from the (canonical) line coefficients
+TB_HD void wp_ll_xy(WScratch* w, const Fq12* la, const Fq12* lb, int t) {
+  const int which = t / 6, rem = t % 6, tt = rem / 2, c = rem & 1;
+  const Fq* src = w12_q(which ? lb : la);
+  const int slot = tt == 0 ? 0 : tt == 1 ? 3 : 4;
+  w->xy[which][0][tt][c] = src[2 * slot + c];
+}
+// item t < 12: coefficient t of L, reduced. prod (P0 < 10.1 q, P1 < 5.1 q; operands < 4 q, kar < 1.11 q):
+//   slot 0 = p0 + xi p2 (c0: p0.0 - 5 p2.1 + 26 q < 36.1 q; c1: p0.1 + p2.0 < 15.2 q), slot 1 = p1,
+//   slot 2 = p3 - p1 - p2, slot 3 = p4 - p0 - p1, slot 4 = p5 - p0 - p2 (+ 21 q < 31.1 q / + 11 q < 16.1 q), slot 5 = 0
+TB_HD void wp_ll_out(Fq12* L, const WScratch* w, int t) {
+  const int slot = t / 2, c = t & 1;
+  const Fq(*p)[2] = w->prod;
+  Fq o, m;
+  if (slot == 0) {
+    if (c == 0) {
+      lz_mul5(m, p[2][1]);
+      lz_sub(o, p[0][0], m);
+      lz_add_kq<26>(o);
+    } else {
+      lz_add(o, p[0][1], p[2][0]);
+    }
+  } else if (slot == 1) {
+    o = p[1][c];
+  } else if (slot == 5) {
+    o = fq_zero();
+  } else {
+    const int hi = slot == 2 ? 3 : slot == 3 ? 4 : 5;
+    const int s1 = slot == 2 ? 1 : 0;
+    const int s2 = slot == 3 ? 1 : 2;
+    lz_sub(o, p[hi][c], p[s1][c]);
+    lz_sub(o, o, p[s2][c]);
+    if (c == 0) lz_add_kq<21>(o);
+    else lz_add_kq<11>(o);
+  }
+  lz_reduce(o);
+  w12_q(L)[t] = o;
+}
+
 }  // namespace tb

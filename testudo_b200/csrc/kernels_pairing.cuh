@@ -169,6 +169,24 @@ __device__ __forceinline__ void w12_canon(Fq12* a, Team tm) {
   }
   team_sync(tm);
 }
+// out = (N^-1, 0) for the Fq6 element N in tower slots 0..2 of n12 (fq12_coop.cuh); out must not alias n12
+static __device__ __noinline__ void w12_inv_fq6(Fq12* out, const Fq12* n12, WScratch* w, Team tm) {
+  team_sync(tm);
+  if (tm.tid < 18) wp_inv6_r1(w, n12, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 12) wp_inv6_p1(w, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 6) wp_inv6_p2(w, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 9) wp_inv6_r2(w, n12, tm.tid);
+  team_sync(tm);
+  if (tm.tid == 0) wp_inv6_d(w);
+  team_sync(tm);
+  if (tm.tid < 9) wp_inv6_r3(w, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 12) wp_inv6_out(out, w, tm.tid);
+  team_sync(tm);
+}
 static __device__ __noinline__ void w12_exp_by_x(Fq12* dst, const Fq12* a, Fq12* acc, WScratch* w, Team tm) {
   w12_copy(acc, a, tm);
   for (int bit = 62; bit >= 0; bit--) {
@@ -187,9 +205,10 @@ struct WFinalExp {
 // result lands in s->r
 static __device__ __noinline__ void w12_final_exp(WFinalExp* s, Team tm) {
   WScratch* w = &s->w;
-  w12_conj(&s->r, &s->f, tm);
-  if (tm.tid == 0) fq12_inv_ol(&s->f2, &s->f);      // one inversion per product
-  team_sync(tm);
+  w12_conj(&s->r, &s->f, tm);                       // f^(q^6 - 1) = conj(f)^2 / (f conj(f)), the divisor in Fq6
+  w12_mul(&s->y0, &s->f, &s->r, w, tm);
+  w12_inv_fq6(&s->f2, &s->y0, w, tm);
+  w12_sqr(&s->r, &s->r, w, tm);
   w12_mul(&s->r, &s->r, &s->f2, w, tm);
   w12_copy(&s->f2, &s->r, tm);
   w12_frobenius(&s->r, &s->r, 2, tm);
@@ -311,6 +330,118 @@ __global__ void __launch_bounds__(W12_THREADS, 8) k_miller_coop(const uint4* __r
   team_sync(tm);
   const uint4* f4 = reinterpret_cast<const uint4*>(&s.f);
   for (int i = lane; i < 36; i += blockDim.x) f_out[36 * (size_t)j + i] = f4[i];
+}
+
+// ---- two pairs per warp with one shared accumulator -----------------------------------------------------------------------
+// prod_j f_j = the Miller value of a product: pairs may share the accumulator, f <- f^2 * line_a * line_b (ark's
+// multi_miller_loop does the same over chunks of four). In the throughput regime (> 512 pairs) what counts is the number
+// of product passes and linear phases a warp issues per pair (ncu, profiles/r02_summary.md: the integer pipe is 47 %
+// busy with 11 of 32 lanes active on average). One warp, two pairs:
+//   f^2 once (2 passes)  |  BOTH doubling steps in the same three passes (lanes 0-15 pair a, 16-31 pair b)  |
+//   line_a * line_b as one sparse product (1 pass, 18 Fq products)  |  f * L (2 passes)
+// = 8 passes per iteration for two pairs where the one-pair kernel needs 7 per pair; the linear phases shrink the same way.
+// An identity point or a missing second pair (odd count) leaves that pair's line at 1.
+struct WMillerDuo {
+  Fq12 f, L;
+  Fq12 line[2];
+  WDouble d[2];
+  Affine2 q[2];
+  Affine p[2];
+  WScratch w;
+};
+// L = la * lb for line-shaped la, lb (fq12_coop.cuh); L must not alias them
+static __device__ __noinline__ void w12_line_mul(Fq12* L, const Fq12* la, const Fq12* lb, WScratch* w, Team tm) {
+  team_sync(tm);
+  if (tm.tid < 12) wp_ll_xy(w, la, lb, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 18) wp_kar(w, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 12) wp_fq2(w, tm.tid);
+  team_sync(tm);
+  if (tm.tid < 12) wp_ll_out(L, w, tm.tid);
+  team_sync(tm);
+}
+// the doubling / addition step of both pairs at once: lane = 16 * pair + item; `on` = this lane's pair is live
+static __device__ __noinline__ void w_double_step2(WDouble* d, Fq12* line, bool on) {
+  const int t = threadIdx.x & 15;
+  __syncwarp();
+  if (on && t < 11) wp_dbl_r1(d, t);
+  __syncwarp();
+  if (on && t < 12) wp_dbl_p2(d, t);
+  __syncwarp();
+  if (on && t < 10) wp_dbl_p3(d, t);
+  __syncwarp();
+  if (on && t < 14) wp_dbl_r2(d, t);
+  __syncwarp();
+  if (on && t < 12) wp_dbl_p5(d, line, t);
+  __syncwarp();
+}
+static __device__ __noinline__ void w_add_step2(WDouble* d, const Affine2* q, Fq12* line, bool on) {
+  const int t = threadIdx.x & 15;
+  __syncwarp();
+  if (on && t < 6) wp_add_rA(d, q, t);
+  __syncwarp();
+  if (on && t < 4) wp_add_pA(d, t);
+  __syncwarp();
+  if (on && t < 14) wp_add_rB(d, q, t);
+  __syncwarp();
+  if (on && t < 10) wp_add_pB(d, line, t);
+  __syncwarp();
+  if (on && t < 9) wp_add_rC(d, t);
+  __syncwarp();
+  if (on && t < 6) wp_add_pC(d, t);
+  __syncwarp();
+  if (on && t < 12) wp_add_rD(d, t);
+  __syncwarp();
+  if (on && t < 6) wp_add_pD(d, t);
+  __syncwarp();
+}
+// f_out[b] = Miller(pair 2b) * Miller(pair 2b + 1); n pairs, ceil(n / 2) one-warp CTAs. Pair j takes g2[j ^ xor_mask].
+__global__ void __launch_bounds__(32, 16) k_miller_duo(const uint4* __restrict__ g1, const uint4* __restrict__ g2, uint32_t n,
+                                                       uint32_t xor_mask, uint4* __restrict__ f_out) {
+  __shared__ WMillerDuo s;
+  Team tm;
+  tm.tid = threadIdx.x;
+  tm.size = 32;
+  tm.mode = 1;
+  const int lane = threadIdx.x, pi = lane >> 4, t = lane & 15;
+  const uint32_t j = 2 * blockIdx.x + pi;
+  const bool present = j < n;
+  uint4* p4 = reinterpret_cast<uint4*>(&s.p[pi]);
+  uint4* q4 = reinterpret_cast<uint4*>(&s.q[pi]);
+  if (present) {
+    if (t < 6) p4[t] = g1[6 * (size_t)j + t];
+    if (t < 12) q4[t] = g2[12 * (size_t)(j ^ xor_mask) + t];
+  }
+  if (t < 6) {
+    *w12_c(&s.line[pi], t) = t == 0 ? fq2_one() : fq2_zero();
+    if (pi == 0) *w12_c(&s.f, t) = t == 0 ? fq2_one() : fq2_zero();
+  }
+  __syncwarp();
+  const bool on = present && !(affine_is_inf(s.p[pi]) || affine2_is_inf(s.q[pi]));
+  WDouble* d = &s.d[pi];
+  if (on && t == 0) {
+    d->r.x = s.q[pi].x;
+    d->r.y = s.q[pi].y;
+    d->r.z = fq2_one();
+    d->px = s.p[pi].x;
+    d->py = s.p[pi].y;
+  }
+  __syncwarp();
+  for (int bit = 62; bit >= 0; bit--) {
+    if (bit != 62) w12_sqr(&s.f, &s.f, &s.w, tm);
+    w_double_step2(d, &s.line[pi], on);
+    w12_line_mul(&s.L, &s.line[0], &s.line[1], &s.w, tm);
+    w12_mul(&s.f, &s.f, &s.L, &s.w, tm);
+    if ((BLS_X >> bit) & 1) {
+      w_add_step2(d, &s.q[pi], &s.line[pi], on);
+      w12_line_mul(&s.L, &s.line[0], &s.line[1], &s.w, tm);
+      w12_mul(&s.f, &s.f, &s.L, &s.w, tm);
+    }
+  }
+  w12_canon(&s.f, tm);
+  const uint4* f4 = reinterpret_cast<const uint4*>(&s.f);
+  for (int i = lane; i < 36; i += 32) f_out[36 * (size_t)blockIdx.x + i] = f4[i];
 }
 
 // ---- pipelined Miller loop: the point chain and the f chain on different warps ----------------------------------------------
