@@ -87,12 +87,18 @@ __global__ void __launch_bounds__(32) k_fq12_prod_level(const uint4* __restrict_
 constexpr int W12_THREADS = 64;   // the largest team
 struct Team {
   int tid, size, mode;            // mode 0: __syncthreads, 1: __syncwarp, 2: bar.sync 1, 64
+  // Item index of the LINEAR phases. Their items are numbered (coefficient, c) with c in the lowest bit, and the c = 0 and
+  // c = 1 recombinations are different code (lanes of one warp that diverge run one after the other): a two-warp team puts
+  // the c = 0 items on warp 0 and the c = 1 items on warp 1, which halves the number of paths each warp walks through.
+  int lin;
 };
+__device__ __forceinline__ int team_lin(int tid, int size) { return size == 64 ? (((tid & 31) << 1) | (tid >> 5)) : tid; }
 __device__ __forceinline__ Team team_cta() {
   Team t;
   t.tid = threadIdx.x;
   t.size = blockDim.x;
   t.mode = blockDim.x > 32 ? 0 : 1;
+  t.lin = team_lin(t.tid, t.size);
   return t;
 }
 __device__ __forceinline__ void team_sync(const Team& t) {
@@ -107,32 +113,32 @@ static __device__ __noinline__ void w_fq6_products(WScratch* w, int count, Team 
   team_sync(tm);
   for (int t = tm.tid; t < 18 * count; t += tm.size) wp_kar(w, t);
   team_sync(tm);
-  for (int t = tm.tid; t < 12 * count; t += tm.size) wp_fq2(w, t);
+  for (int t = tm.lin; t < 12 * count; t += tm.size) wp_fq2(w, t);
   team_sync(tm);
-  if (tm.tid < 6 * count) wp_fq6(w, tm.tid);
+  if (tm.lin < 6 * count) wp_fq6(w, tm.lin);
   team_sync(tm);
 }
 static __device__ __noinline__ void w12_mul(Fq12* dst, const Fq12* a, const Fq12* b, WScratch* w, Team tm) {
   team_sync(tm);
-  for (int t = tm.tid; t < 36; t += tm.size) wp_mul_xy(w, a, b, t);
+  for (int t = tm.lin; t < 36; t += tm.size) wp_mul_xy(w, a, b, t);
   w_fq6_products(w, 3, tm);
-  if (tm.tid < 12) wp_mul_out(dst, w, tm.tid);
+  if (tm.lin < 12) wp_mul_out(dst, w, tm.lin);
   team_sync(tm);
 }
 static __device__ __noinline__ void w12_sqr(Fq12* dst, const Fq12* a, WScratch* w, Team tm) {
   team_sync(tm);
-  if (tm.tid < 24) wp_sqr_xy(w, a, tm.tid);
+  if (tm.lin < 24) wp_sqr_xy(w, a, tm.lin);
   w_fq6_products(w, 2, tm);
-  if (tm.tid < 12) wp_sqr_out(dst, w, tm.tid);
+  if (tm.lin < 12) wp_sqr_out(dst, w, tm.lin);
   team_sync(tm);
 }
 static __device__ __noinline__ void w12_cyclotomic_sqr(Fq12* dst, const Fq12* a, WScratch* w, Team tm) {
   team_sync(tm);
   if (tm.tid < 18) wp_cyc_kar(w, a, tm.tid);
   team_sync(tm);
-  if (tm.tid < 12) wp_cyc_fq2(w, tm.tid);
+  if (tm.lin < 12) wp_cyc_fq2(w, tm.lin);
   team_sync(tm);
-  if (tm.tid < 12) wp_cyc_out(dst, a, w, tm.tid);
+  if (tm.lin < 12) wp_cyc_out(dst, a, w, tm.lin);
   team_sync(tm);
 }
 __device__ __forceinline__ void w12_copy(Fq12* dst, const Fq12* a, Team tm) {
@@ -146,17 +152,17 @@ __device__ __forceinline__ void w12_copy(Fq12* dst, const Fq12* a, Team tm) {
 __device__ __forceinline__ void w12_conj(Fq12* dst, const Fq12* a, Team tm) {
   team_sync(tm);
   Fq v;
-  if (tm.tid < 12) v = wp_conj(a, tm.tid);
+  if (tm.lin < 12) v = wp_conj(a, tm.lin);
   team_sync(tm);
-  if (tm.tid < 12) w12_q(dst)[tm.tid] = v;
+  if (tm.lin < 12) w12_q(dst)[tm.lin] = v;
   team_sync(tm);
 }
 static __device__ __noinline__ void w12_frobenius(Fq12* dst, const Fq12* a, int k, Team tm) {
   team_sync(tm);
   Fq c;
-  if (tm.tid < 12) c = wp_frobenius(a, k, tm.tid);
+  if (tm.lin < 12) c = wp_frobenius(a, k, tm.lin);
   team_sync(tm);
-  if (tm.tid < 12) w12_q(dst)[tm.tid] = c;
+  if (tm.lin < 12) w12_q(dst)[tm.lin] = c;
   team_sync(tm);
 }
 // every coefficient to [0, q): values that leave the kernel
@@ -174,9 +180,9 @@ static __device__ __noinline__ void w12_inv_fq6(Fq12* out, const Fq12* n12, WScr
   team_sync(tm);
   if (tm.tid < 18) wp_inv6_r1(w, n12, tm.tid);
   team_sync(tm);
-  if (tm.tid < 12) wp_inv6_p1(w, tm.tid);
+  if (tm.lin < 12) wp_inv6_p1(w, tm.lin);
   team_sync(tm);
-  if (tm.tid < 6) wp_inv6_p2(w, tm.tid);
+  if (tm.lin < 6) wp_inv6_p2(w, tm.lin);
   team_sync(tm);
   if (tm.tid < 9) wp_inv6_r2(w, n12, tm.tid);
   team_sync(tm);
@@ -184,7 +190,7 @@ static __device__ __noinline__ void w12_inv_fq6(Fq12* out, const Fq12* n12, WScr
   team_sync(tm);
   if (tm.tid < 9) wp_inv6_r3(w, tm.tid);
   team_sync(tm);
-  if (tm.tid < 12) wp_inv6_out(out, w, tm.tid);
+  if (tm.lin < 12) wp_inv6_out(out, w, tm.lin);
   team_sync(tm);
 }
 static __device__ __noinline__ void w12_exp_by_x(Fq12* dst, const Fq12* a, Fq12* acc, WScratch* w, Team tm) {
@@ -255,13 +261,13 @@ static __device__ __noinline__ void w_double_step(WDouble* d, Fq12* line, Team t
   team_sync(tm);
   if (tm.tid < 11) wp_dbl_r1(d, tm.tid);
   team_sync(tm);
-  if (tm.tid < 12) wp_dbl_p2(d, tm.tid);
+  if (tm.lin < 12) wp_dbl_p2(d, tm.lin);
   team_sync(tm);
-  if (tm.tid < 10) wp_dbl_p3(d, tm.tid);
+  if (tm.lin < 10) wp_dbl_p3(d, tm.lin);
   team_sync(tm);
   if (tm.tid < 14) wp_dbl_r2(d, tm.tid);
   team_sync(tm);
-  if (tm.tid < 12) wp_dbl_p5(d, line, tm.tid);
+  if (tm.lin < 12) wp_dbl_p5(d, line, tm.lin);
   team_sync(tm);
 }
 // the addition step (six per loop), four product rounds on parallel lanes (fq12_coop.cuh); on one thread it was ~30
@@ -270,19 +276,19 @@ static __device__ __noinline__ void w_add_step(WDouble* d, const Affine2* q, Fq1
   team_sync(tm);
   if (tm.tid < 6) wp_add_rA(d, q, tm.tid);
   team_sync(tm);
-  if (tm.tid < 4) wp_add_pA(d, tm.tid);
+  if (tm.lin < 4) wp_add_pA(d, tm.lin);
   team_sync(tm);
   if (tm.tid < 14) wp_add_rB(d, q, tm.tid);
   team_sync(tm);
-  if (tm.tid < 10) wp_add_pB(d, line, tm.tid);
+  if (tm.lin < 10) wp_add_pB(d, line, tm.lin);
   team_sync(tm);
   if (tm.tid < 9) wp_add_rC(d, tm.tid);
   team_sync(tm);
-  if (tm.tid < 6) wp_add_pC(d, tm.tid);
+  if (tm.lin < 6) wp_add_pC(d, tm.lin);
   team_sync(tm);
   if (tm.tid < 12) wp_add_rD(d, tm.tid);
   team_sync(tm);
-  if (tm.tid < 6) wp_add_pD(d, tm.tid);
+  if (tm.lin < 6) wp_add_pD(d, tm.lin);
   team_sync(tm);
 }
 
@@ -352,13 +358,13 @@ struct WMillerDuo {
 // L = la * lb for line-shaped la, lb (fq12_coop.cuh); L must not alias them
 static __device__ __noinline__ void w12_line_mul(Fq12* L, const Fq12* la, const Fq12* lb, WScratch* w, Team tm) {
   team_sync(tm);
-  if (tm.tid < 12) wp_ll_xy(w, la, lb, tm.tid);
+  if (tm.lin < 12) wp_ll_xy(w, la, lb, tm.lin);
   team_sync(tm);
   if (tm.tid < 18) wp_kar(w, tm.tid);
   team_sync(tm);
-  if (tm.tid < 12) wp_fq2(w, tm.tid);
+  if (tm.lin < 12) wp_fq2(w, tm.lin);
   team_sync(tm);
-  if (tm.tid < 12) wp_ll_out(L, w, tm.tid);
+  if (tm.lin < 12) wp_ll_out(L, w, tm.lin);
   team_sync(tm);
 }
 // the doubling / addition step of both pairs at once: lane = 16 * pair + item; `on` = this lane's pair is live
@@ -404,6 +410,7 @@ __global__ void __launch_bounds__(32, 16) k_miller_duo(const uint4* __restrict__
   tm.tid = threadIdx.x;
   tm.size = 32;
   tm.mode = 1;
+  tm.lin = threadIdx.x;
   const int lane = threadIdx.x, pi = lane >> 4, t = lane & 15;
   const uint32_t j = 2 * blockIdx.x + pi;
   const bool present = j < n;
@@ -498,6 +505,7 @@ __global__ void __launch_bounds__(MP_THREADS, 5) k_miller_pipe(const uint4* __re
     tm.tid = tid - 64;
     tm.size = 32;
     tm.mode = 1;
+    tm.lin = tm.tid;
     if (tm.tid == 0) {
       s.d.r.x = s.q.x;
       s.d.r.y = s.q.y;
@@ -525,6 +533,7 @@ __global__ void __launch_bounds__(MP_THREADS, 5) k_miller_pipe(const uint4* __re
     tm.tid = tid;
     tm.size = 64;
     tm.mode = 2;
+    tm.lin = team_lin(tid, 64);
     int e = 0;
     for (int bit = 62; bit >= 0; bit--) {
       if (bit != 62) w12_sqr(&s.f, &s.f, &s.w, tm);
