@@ -248,8 +248,6 @@ class Polynomial:
         assert self.chis_b is not None, "chis(b) should have been computed for q"
         assert len(self.chis_b) == len(comm_list)                      # src/sqrt_pst.rs:194
         c_u = msm.msm_unchecked(comm_list, self.chis_b)                # M2, src/sqrt_pst.rs:198
-        comm_q = pc_commit(ck, self.q)                                 # M3, src/sqrt_pst.rs:205
-        assert np.array_equal(c_u, comm_q), "debug_assert!(c_u == comm.g_product) (src/sqrt_pst.rs:206)"
         h_vec = ck.powers_of_h[self.odd] if ck.powers_of_h is not None else None     # src/sqrt_pst.rs:207
         g_levels = ck.powers_of_g[self.odd:] if ck.powers_of_g is not None else None  # variable CRS: off = ck.nv - m
         # The reference computes the PST proof of q AFTER the MIPP proof (:218-225), but it depends only on q and the
@@ -258,6 +256,9 @@ class Polynomial:
         if ck.powers_of_h is not None:
             a_rev = list(point[: self.m + self.odd])[::-1]                        # :218-222
             pending = multilinear_pc.open_begin(ck.powers_of_h, self.q, curve.scalars_to_words(a_rev, mont=True))  # :225
+        # M3 only feeds the reference's debug_assert (:205-206): it runs while the G2 opening above keeps the GPU busy
+        comm_q = pc_commit(ck, self.q)                                 # M3, src/sqrt_pst.rs:205
+        assert np.array_equal(c_u, comm_q), "debug_assert!(c_u == comm.g_product) (src/sqrt_pst.rs:206)"
         proof = mipp.MippProofG1.prove(challenge, comm_list, self.chis_b, c_u, h_vec, g_levels)   # :212-213
         pst_proof = pending.wait() if pending is not None else None
         return OpenG1(u=c_u, comm_q=comm_q, mipp=proof, pst_proof=pst_proof)
