@@ -269,6 +269,47 @@ void hcw_add_step(WDouble* d, const Affine2* q, Fq12* line) {
 }
 }  // namespace
 extern "C" {
+// lane-parallel XYZZ arithmetic over Fq2 (window combine of a G2 MSM) vs the canonical routines. p, e: XYZZ (4 Fq2 each),
+// canonical; op 0: p = 2 p, 1: p += e. Returns 1 when the canonicalised results agree.
+int hc_coop_g2_op(int op, const uint32_t* p_in, const uint32_t* e_in, uint32_t* out) {
+  WG2 s;
+  memcpy(&s.p, p_in, 384);
+  memcpy(&s.e, e_in, 384);
+  Xyzz2 ref = s.p;
+  if (op == 0) {
+    xyzz2_dbl(ref);
+    for (int t = 0; t < 4; t++) wp_g2dbl_r1(&s, t);
+    for (int t = 0; t < 6; t++) wp_g2dbl_p1(&s, t);
+    for (int t = 0; t < 11; t++) wp_g2dbl_r2(&s, t);
+    for (int t = 0; t < 8; t++) wp_g2dbl_p2(&s, t);
+    for (int t = 0; t < 9; t++) wp_g2dbl_r3(&s, t);
+    for (int t = 0; t < 4; t++) wp_g2dbl_p3(&s, t);
+  } else {
+    xyzz2_add(ref, s.e);
+    wp_g2add_flags(&s);
+    if (s.flag == 2) s.p = s.e;
+    if (s.flag == 0) {
+      for (int t = 0; t < 12; t++) wp_g2add_r1(&s, t);
+      for (int t = 0; t < 8; t++) wp_g2add_p1(&s, t);
+      wp_g2add_check(&s);
+    }
+    if (s.flag == 0) {
+      for (int t = 0; t < 10; t++) wp_g2add_r2(&s, t);
+      for (int t = 0; t < 8; t++) wp_g2add_p2(&s, t);
+      for (int t = 0; t < 9; t++) wp_g2add_r3(&s, t);
+      for (int t = 0; t < 8; t++) wp_g2add_p3(&s, t);
+      for (int t = 0; t < 9; t++) wp_g2add_r4(&s, t);
+      for (int t = 0; t < 4; t++) wp_g2add_p4(&s, t);
+    }
+  }
+  for (int t = 0; t < 8; t++) lz_canon(reinterpret_cast<Fq*>(&s.p)[t]);
+  memcpy(out, &s.p, 384);
+  // compare as points: both to canonical affine (the XYZZ representatives agree too, but affine is what leaves the kernel)
+  Affine2 a, b;
+  xyzz2_to_affine(a, s.p);
+  xyzz2_to_affine(b, ref);
+  return memcmp(&a, &b, 192) == 0 && (op == 1 && s.flag == 3 ? 1 : memcmp(&s.p, &ref, 384) == 0 || xyzz2_is_inf(ref));
+}
 // product of two line values (tower slots 0, 3, 4 of a and b; the other slots are ignored) vs the general product
 int hc_coop_line_mul(const uint32_t* a, const uint32_t* b) {
   Fq12 x, y, z, ref;

@@ -179,3 +179,51 @@ def test_lazy_line_product(hc):
     for a in cases:
         for b in cases[::2]:
             assert hc.hc_coop_line_mul(P(raw_words(a)), P(raw_words(b))) == 1
+
+
+def test_lazy_g2_xyzz_group_law(hc):
+    """The lane-parallel XYZZ doubling / addition over Fq2 (window combine of a G2 MSM) against the canonical routines and
+    the oracle's curve arithmetic: chains with non-trivial ZZ, equal operands, opposite operands, identities."""
+    pts, _ = o2.rand_points(3, 61)
+    P0, Q0, R0 = pts
+
+    def xyzz(pt):
+        if pt is None:
+            return np.zeros(48, dtype=np.uint64)
+        w = list(o2.affine_to_words(pt))
+        one = [(R384 % Q >> (64 * i)) & (2**64 - 1) for i in range(6)]
+        return np.array(w + one + [0] * 6 + one + [0] * 6, dtype=np.uint64)
+
+    def op(code, a, b=None):
+        out = np.zeros(48, dtype=np.uint64)
+        assert hc.hc_coop_g2_op(code, P(a), P(b if b is not None else a), P(out)) == 1
+        return out
+
+    def to_affine(v):
+        """canonical XYZZ words -> oracle affine point"""
+        vals = [sum(int(v[6 * k + i]) << (64 * i) for i in range(6)) * RINV % Q for k in range(8)]
+        x, y, zz, zzz = (vals[0], vals[1]), (vals[2], vals[3]), (vals[4], vals[5]), (vals[6], vals[7])
+        if zz == (0, 0):
+            return None
+        return (o2.f2_mul(x, o2.f2_inv(zz)), o2.f2_mul(y, o2.f2_inv(zzz)))
+
+    a = xyzz(P0)
+    a = op(0, a)                                   # 2 P
+    a = op(0, a)                                   # 4 P, ZZ != 1
+    assert to_affine(a) == o2.mul(4, P0)
+    b = op(1, a, xyzz(Q0))                         # 4 P + Q
+    assert to_affine(b) == o2.add(o2.mul(4, P0), Q0)
+    c = op(0, xyzz(R0))
+    d = op(1, b, c)                                # both with ZZ != 1
+    assert to_affine(d) == o2.add(o2.add(o2.mul(4, P0), Q0), o2.mul(2, R0))
+    assert to_affine(op(1, d, d)) == o2.mul(2, to_affine(d))            # equal operands: the exact path doubles
+    neg = d.copy()
+    y0 = sum(int(d[12 + i]) << (64 * i) for i in range(6)); y1 = sum(int(d[18 + i]) << (64 * i) for i in range(6))
+    for i in range(6):
+        neg[12 + i] = ((Q - y0) % Q >> (64 * i)) & (2**64 - 1)
+        neg[18 + i] = ((Q - y1) % Q >> (64 * i)) & (2**64 - 1)
+    assert to_affine(op(1, d, neg)) is None                            # P + (-P)
+    inf = xyzz(None)
+    assert to_affine(op(1, inf, xyzz(Q0))) == Q0
+    assert to_affine(op(1, d, inf)) == to_affine(d)
+    assert to_affine(op(0, inf)) is None

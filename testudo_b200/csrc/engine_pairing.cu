@@ -4,6 +4,7 @@
 #define TB_NO_G1_KERNELS
 #define TB_NO_G2_KERNELS
 #include <algorithm>
+#include <cstring>
 
 #include "engine.h"
 #include "glv_host.h"
@@ -14,7 +15,10 @@ using namespace tb;
 namespace tbe {
 
 int g2_finalize_single_glv(cudaStream_t st, const uint4* group_w, int W, int c, uint4* fin_scratch, uint4* d_out) {
-  LAUNCH(k_finalize_single_g2_glv, 1, 384, st, group_w, W, c, fin_scratch, d_out);
+  // TB200_G2_COMBINE=psi selects the earlier kernel (four endomorphism dimensions per window, single-thread group law)
+  static const bool psi = getenv("TB200_G2_COMBINE") && !strcmp(getenv("TB200_G2_COMBINE"), "psi");
+  if (psi) LAUNCH(k_finalize_single_g2_glv, 1, 384, st, group_w, W, c, fin_scratch, d_out);
+  else LAUNCH(k_finalize_single_g2_coop, 1, 32, st, group_w, W, c, d_out);
   return 0;
 }
 

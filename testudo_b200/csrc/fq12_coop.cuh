@@ -935,4 +935,302 @@ TB_HD void wp_ll_out(Fq12* L, const WScratch* w, int t) {
   w12_q(L)[t] = o;
 }
 
+// ---- XYZZ arithmetic over Fq2 on parallel lanes (the window combine of a single G2 MSM) ---------------------------------------
+// The Horner form sum_w 2^(c w) S_w is ~253 dependent doublings + W additions: on one thread 27 / 46 us each. Here the
+// Fq2 products of a doubling (dbl-2008-s-1) run as three rounds of 4 / 11 / 9 Fq products, those of an addition
+// (add-2008-s) as four rounds of 12 / 10 / 9 / 9, with the lazily reduced recombinations in between.
+// Accumulator p: coefficients < 1.01 q between operations (identity <=> ZZ = 0 mod q); operand e canonical.
+struct WG2 {
+  Xyzz2 p, e;
+  Fq kar[12];
+  Fq v[9][2];
+  int flag;          // addition: 0 = generic, 1 = e is the identity, 2 = p is the identity, 3 = equal x (exact path)
+};
+enum { G2V_U = 0, G2V_V, G2V_M, G2V_W, G2V_T, G2V_S1, G2V_PP, G2V_ZZ12, G2V_ZZZ12 };
+// (k0 - 5 k1) - (k0' - 5 k1') and S(k) - S(k') of two Karatsuba triples, + OFF q
+template <unsigned O0, unsigned O1>
+TB_HD void wl_fq2_diff_from_kar(Fq& o, const Fq* ka, const Fq* kb, int c) {
+  Fq m;
+  if (c == 0) {
+    lz_sub(m, kb[1], ka[1]);
+    lz_mul5(m, m);
+    lz_sub(o, ka[0], kb[0]);
+    lz_add(o, o, m);
+    lz_add_kq<O0>(o);
+  } else {
+    wl_kar_c1(o, ka);
+    wl_kar_c1(m, kb);
+    lz_sub(o, o, m);
+    lz_add_kq<O1>(o);
+  }
+}
+// doubling, round 1, item t < 4: U^2 (U = 2 Y: operands < 4.1 q, < 13.2 q) and X^2 as (v0 + v1)(v0 - 5 v1), v0 v1
+TB_HD void wp_g2dbl_r1(WG2* s, int t) {
+  const Fq* y = reinterpret_cast<const Fq*>(&s->p.y);
+  const Fq* x = reinterpret_cast<const Fq*>(&s->p.x);
+  Fq a, b;
+  if (t < 2) {
+    Fq w[2];
+    lz_dbl(w[0], y[0]);
+    lz_dbl(w[1], y[1]);
+    wl_sqr_operands<11>(a, b, w, t & 1);
+  } else {
+    wl_sqr_operands<6>(a, b, x, t & 1);
+  }
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 6: V = U^2 (< 5.6 q, 2.1 q), M = 3 X^2 (< 15.5 q, 6.1 q), U = 2 Y
+TB_HD void wp_g2dbl_p1(WG2* s, int t) {
+  const int c = t & 1, what = t >> 1;
+  Fq o;
+  if (what == 0) wl_sqr_asm(o, s->kar[0], s->kar[1], c);
+  else if (what == 1) {
+    wl_sqr_asm(o, s->kar[2], s->kar[3], c);
+    lz_mul3(o, o);
+  } else {
+    lz_dbl(o, reinterpret_cast<const Fq*>(&s->p.y)[c]);
+  }
+  s->v[what == 0 ? G2V_V : what == 1 ? G2V_M : G2V_U][c] = o;
+}
+// round 2, item t < 11: 0-2 W = U V (< 1.22 q), 3-5 S = X V (< 1.12 q), 6-7 M^2 (operands < 21.6 q, < 46.5 q: < 7.6 q; m0 m1
+// < 1.63 q), 8-10 V ZZ (< 1.12 q)
+TB_HD void wp_g2dbl_r2(WG2* s, int t) {
+  Fq(*v)[2] = s->v;
+  Fq a, b;
+  if (t < 3) {
+    wl_kar_operand(a, v[G2V_U], v[G2V_U], false, t);
+    wl_kar_operand(b, v[G2V_V], v[G2V_V], false, t);
+  } else if (t < 6) {
+    const Fq* x = reinterpret_cast<const Fq*>(&s->p.x);
+    wl_kar_operand(a, x, x, false, t - 3);
+    wl_kar_operand(b, v[G2V_V], v[G2V_V], false, t - 3);
+  } else if (t < 8) {
+    wl_sqr_operands<31>(a, b, v[G2V_M], t & 1);
+  } else {
+    const Fq* zz = reinterpret_cast<const Fq*>(&s->p.zz);
+    wl_kar_operand(a, v[G2V_V], v[G2V_V], false, t - 8);
+    wl_kar_operand(b, zz, zz, false, t - 8);
+  }
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 8: X' = M^2 - 2 S (reduced), T = S - X' = 3 S - M^2 (< 34.5 q, 13.5 q), W (< 8.3 q, 4.3 q), ZZ' = V ZZ (reduced).
+// With M^2 = (Q0, Q1) = (s0 + 4 s1, 2 s1) < (14.2 q, 3.3 q) and S from kar[3..5]:
+//   X'.0 = Q0 - 2 k3 + 10 k4 + 3 q < 28.3 q,   X'.1 = Q1 - 2 S(k3..5) + 3 q < 10.8 q
+//   T.0 = 3 k3 - 15 k4 - Q0 + 31 q,           T.1 = 3 S(k3..5) - Q1 + 10 q
+TB_HD void wp_g2dbl_p2(WG2* s, int t) {
+  const int c = t & 1, what = t >> 1;
+  const Fq* ks = &s->kar[3];
+  Fq o, m, q;
+  if (what < 2) {
+    wl_sqr_asm(q, s->kar[6], s->kar[7], c);
+    if (c == 0) {                       // sv = k3 - 5 k4 (wrapping)
+      lz_mul5(m, ks[1]);
+      lz_sub(m, ks[0], m);
+    } else {
+      wl_kar_c1(m, ks);
+    }
+    if (what == 0) {
+      lz_dbl(m, m);
+      lz_sub(o, q, m);
+      lz_add_kq<3>(o);
+      lz_reduce(o);
+      reinterpret_cast<Fq*>(&s->p.x)[c] = o;
+    } else {
+      lz_mul3(m, m);
+      lz_sub(o, m, q);
+      if (c == 0) lz_add_kq<31>(o);
+      else lz_add_kq<10>(o);
+      s->v[G2V_T][c] = o;
+    }
+  } else if (what == 2) {
+    wl_fq2_from_kar<7, 3>(o, &s->kar[0], c);
+    s->v[G2V_W][c] = o;
+  } else {
+    wl_fq2_from_kar<6, 3>(o, &s->kar[8], c);
+    lz_reduce(o);
+    reinterpret_cast<Fq*>(&s->p.zz)[c] = o;
+  }
+}
+// round 3, item t < 9: 0-2 M T (< 7.8 q), 3-5 W Y (< 1.18 q), 6-8 W ZZZ (< 1.18 q)
+TB_HD void wp_g2dbl_r3(WG2* s, int t) {
+  Fq(*v)[2] = s->v;
+  const int pr = t / 3, part = t % 3;
+  const Fq* x = pr == 0 ? v[G2V_M] : v[G2V_W];
+  const Fq* y = pr == 0 ? v[G2V_T] : reinterpret_cast<const Fq*>(pr == 1 ? &s->p.y : &s->p.zzz);
+  Fq a, b;
+  wl_kar_operand(a, x, x, false, part);
+  wl_kar_operand(b, y, y, false, part);
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 4: Y' = M T - W Y (+ 40 q < 53.7 q / + 17 q < 27.2 q), ZZZ' = W ZZZ; reduced
+TB_HD void wp_g2dbl_p3(WG2* s, int t) {
+  const int c = t & 1;
+  Fq o;
+  if (t < 2) {
+    wl_fq2_diff_from_kar<40, 17>(o, &s->kar[0], &s->kar[3], c);
+    lz_reduce(o);
+    reinterpret_cast<Fq*>(&s->p.y)[c] = o;
+  } else {
+    wl_fq2_from_kar<6, 3>(o, &s->kar[6], c);
+    lz_reduce(o);
+    reinterpret_cast<Fq*>(&s->p.zzz)[c] = o;
+  }
+}
+
+// addition p += e. ONE item first: the exceptional shapes (identity operands), decided on canonical values
+TB_HD void wp_g2add_flags(WG2* s) {
+  Fq2 pz = s->p.zz;
+  lz_canon(pz.c0);
+  lz_canon(pz.c1);
+  s->flag = fq2_is_zero(s->e.zz) ? 1 : (fq2_is_zero(pz) ? 2 : 0);
+}
+// round 1, item t < 12: U1 = X1 ZZ2 (0-2), U2 = X2 ZZ1 (3-5), S1 = Y1 ZZZ2 (6-8), S2 = Y2 ZZZ1 (9-11); kar < 1.03 q
+TB_HD void wp_g2add_r1(WG2* s, int t) {
+  const int pr = t / 3, part = t % 3;
+  const Fq2* xa = pr == 0 ? &s->p.x : pr == 1 ? &s->e.x : pr == 2 ? &s->p.y : &s->e.y;
+  const Fq2* xb = pr == 0 ? &s->e.zz : pr == 1 ? &s->p.zz : pr == 2 ? &s->e.zzz : &s->p.zzz;
+  const Fq* x = reinterpret_cast<const Fq*>(xa);
+  const Fq* y = reinterpret_cast<const Fq*>(xb);
+  Fq a, b;
+  wl_kar_operand(a, x, x, false, part);
+  wl_kar_operand(b, y, y, false, part);
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 8: P = U2 - U1 -> v[T] (canonical), R = S2 - S1 -> v[M] (canonical), U1 -> v[U], S1 -> v[S1] (< 7.1 q, 4.1 q)
+TB_HD void wp_g2add_p1(WG2* s, int t) {
+  const int c = t & 1, what = t >> 1;
+  Fq o;
+  if (what == 0) {
+    wl_fq2_diff_from_kar<7, 4>(o, &s->kar[3], &s->kar[0], c);
+    lz_canon(o);
+    s->v[G2V_T][c] = o;
+  } else if (what == 1) {
+    wl_fq2_diff_from_kar<7, 4>(o, &s->kar[9], &s->kar[6], c);
+    lz_canon(o);
+    s->v[G2V_M][c] = o;
+  } else if (what == 2) {
+    wl_fq2_from_kar<6, 3>(o, &s->kar[0], c);
+    s->v[G2V_U][c] = o;
+  } else {
+    wl_fq2_from_kar<6, 3>(o, &s->kar[6], c);
+    s->v[G2V_S1][c] = o;
+  }
+}
+// ONE item: equal x coordinates (P = 0): doubling or the identity, exactly, with the canonical routines
+TB_HD void wp_g2add_check(WG2* s) {
+  Fq2 pv;
+  pv.c0 = s->v[G2V_T][0];
+  pv.c1 = s->v[G2V_T][1];
+  if (!fq2_is_zero(pv)) return;
+  s->flag = 3;
+  Xyzz2 a = s->p;
+  lz_canon(a.x.c0); lz_canon(a.x.c1); lz_canon(a.y.c0); lz_canon(a.y.c1);
+  lz_canon(a.zz.c0); lz_canon(a.zz.c1); lz_canon(a.zzz.c0); lz_canon(a.zzz.c1);
+  xyzz2_add(a, s->e);
+  s->p = a;
+}
+// round 2, item t < 10: 0-1 P^2, 2-3 R^2 (< 1.1 q), 4-6 ZZ1 ZZ2, 7-9 ZZZ1 ZZZ2 (< 1.03 q)
+TB_HD void wp_g2add_r2(WG2* s, int t) {
+  Fq(*v)[2] = s->v;
+  Fq a, b;
+  if (t < 4) {
+    wl_sqr_operands<6>(a, b, t < 2 ? v[G2V_T] : v[G2V_M], t & 1);
+  } else {
+    const int part = (t - 4) % 3;
+    const Fq* x = reinterpret_cast<const Fq*>(t < 7 ? &s->p.zz : &s->p.zzz);
+    const Fq* y = reinterpret_cast<const Fq*>(t < 7 ? &s->e.zz : &s->e.zzz);
+    wl_kar_operand(a, x, x, false, part);
+    wl_kar_operand(b, y, y, false, part);
+  }
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 8: PP -> v[PP] (< 5.2 q, 2.1 q), RR -> v[V], ZZ1 ZZ2 -> v[ZZ12], ZZZ1 ZZZ2 -> v[ZZZ12] (< 7.1 q, 4.1 q)
+TB_HD void wp_g2add_p2(WG2* s, int t) {
+  const int c = t & 1, what = t >> 1;
+  Fq o;
+  if (what == 0) wl_sqr_asm(o, s->kar[0], s->kar[1], c);
+  else if (what == 1) wl_sqr_asm(o, s->kar[2], s->kar[3], c);
+  else if (what == 2) wl_fq2_from_kar<6, 3>(o, &s->kar[4], c);
+  else wl_fq2_from_kar<6, 3>(o, &s->kar[7], c);
+  s->v[what == 0 ? G2V_PP : what == 1 ? G2V_V : what == 2 ? G2V_ZZ12 : G2V_ZZZ12][c] = o;
+}
+// round 3, item t < 9: 0-2 PPP = P PP (< 1.1 q), 3-5 Q = U1 PP (< 1.53 q), 6-8 ZZ' = ZZ12 PP (< 1.53 q)
+TB_HD void wp_g2add_r3(WG2* s, int t) {
+  Fq(*v)[2] = s->v;
+  const int pr = t / 3, part = t % 3;
+  const Fq* x = pr == 0 ? v[G2V_T] : pr == 1 ? v[G2V_U] : v[G2V_ZZ12];
+  Fq a, b;
+  wl_kar_operand(a, x, x, false, part);
+  wl_kar_operand(b, v[G2V_PP], v[G2V_PP], false, part);
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 8: X' = RR - PPP - 2 Q (reduced -> p.x), T = Q - X' = 3 Q + PPP - RR -> v[T], PPP -> v[W] (< 7.1 q, 4.1 q),
+// ZZ' (reduced -> p.zz). With PPP from kar[0..2] (< 1.1 q), Q from kar[3..5] (< 1.53 q), RR = v[V]:
+//   X'.0 = RR.0 - k0 - 2 k3 + 5 k1 + 10 k4 + 5 q < 30.9 q,     X'.1 = RR.1 - S(k0..2) - 2 S(k3..5) + 5 q < 15.4 q
+//   T.0 = 3 k3 - 15 k4 + k0 - 5 k1 - RR.0 + 34 q < 39.8 q,     T.1 = 3 S(k3..5) + S(k0..2) - RR.1 + 14 q < 19.8 q
+TB_HD void wp_g2add_p3(WG2* s, int t) {
+  const int c = t & 1, what = t >> 1;
+  const Fq* kp = &s->kar[0];
+  const Fq* kq = &s->kar[3];
+  Fq o, a, b;
+  if (what < 2) {
+    if (c == 0) {                       // a = PPP.0, b = Q.0 (wrapping, no offsets)
+      lz_mul5(a, kp[1]);
+      lz_sub(a, kp[0], a);
+      lz_mul5(b, kq[1]);
+      lz_sub(b, kq[0], b);
+    } else {
+      wl_kar_c1(a, kp);
+      wl_kar_c1(b, kq);
+    }
+    if (what == 0) {
+      lz_sub(o, s->v[G2V_V][c], a);
+      lz_dbl(b, b);
+      lz_sub(o, o, b);
+      lz_add_kq<5>(o);
+      lz_reduce(o);
+      reinterpret_cast<Fq*>(&s->p.x)[c] = o;
+    } else {
+      lz_mul3(b, b);
+      lz_add(o, b, a);
+      lz_sub(o, o, s->v[G2V_V][c]);
+      if (c == 0) lz_add_kq<34>(o);
+      else lz_add_kq<14>(o);
+      s->v[G2V_T][c] = o;
+    }
+  } else if (what == 2) {
+    wl_fq2_from_kar<6, 3>(o, kp, c);
+    s->v[G2V_W][c] = o;
+  } else {
+    wl_fq2_from_kar<8, 4>(o, &s->kar[6], c);
+    lz_reduce(o);
+    reinterpret_cast<Fq*>(&s->p.zz)[c] = o;
+  }
+}
+// round 4, item t < 9: 0-2 R T (< 1.79 q), 3-5 S1 PPP (< 1.82 q), 6-8 ZZZ' = ZZZ12 PPP (< 1.82 q)
+TB_HD void wp_g2add_r4(WG2* s, int t) {
+  Fq(*v)[2] = s->v;
+  const int pr = t / 3, part = t % 3;
+  const Fq* x = pr == 0 ? v[G2V_M] : pr == 1 ? v[G2V_S1] : v[G2V_ZZZ12];
+  const Fq* y = pr == 0 ? v[G2V_T] : v[G2V_W];
+  Fq a, b;
+  wl_kar_operand(a, x, x, false, part);
+  wl_kar_operand(b, y, y, false, part);
+  s->kar[t] = fq_mul_lz(a, b);
+}
+// item t < 4: Y' = R T - S1 PPP (+ 11 q < 21.9 q / + 6 q < 11.5 q), ZZZ'; reduced
+TB_HD void wp_g2add_p4(WG2* s, int t) {
+  const int c = t & 1;
+  Fq o;
+  if (t < 2) {
+    wl_fq2_diff_from_kar<11, 6>(o, &s->kar[0], &s->kar[3], c);
+    lz_reduce(o);
+    reinterpret_cast<Fq*>(&s->p.y)[c] = o;
+  } else {
+    wl_fq2_from_kar<10, 4>(o, &s->kar[6], c);
+    lz_reduce(o);
+    reinterpret_cast<Fq*>(&s->p.zzz)[c] = o;
+  }
+}
+
 }  // namespace tb

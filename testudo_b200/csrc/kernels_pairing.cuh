@@ -795,6 +795,81 @@ __global__ void __launch_bounds__(384) k_finalize_single_g2_glv(const uint4* __r
   }
 }
 
+// Window combine of a single G2 MSM as a Horner chain on ONE warp with lane-parallel group operations (fq12_coop.cuh:
+// wp_g2dbl_*, wp_g2add_*): ~253 doublings of 3 product rounds + W additions of 4. The psi-based kernel above needs only 64
+// doublings per thread but runs them with single-thread Fq2 arithmetic (27 us per doubling, 46 us per addition: ~5 ms for
+// a 2^13-point MSM); the chain here is four times as long and each link eight times as fast. It also accepts ANY curve
+// point (no subgroup precondition).
+static __device__ __noinline__ void w_g2_double(WG2* s) {
+  const int t = threadIdx.x;
+  __syncwarp();
+  if (t < 4) wp_g2dbl_r1(s, t);
+  __syncwarp();
+  if (t < 6) wp_g2dbl_p1(s, t);
+  __syncwarp();
+  if (t < 11) wp_g2dbl_r2(s, t);
+  __syncwarp();
+  if (t < 8) wp_g2dbl_p2(s, t);
+  __syncwarp();
+  if (t < 9) wp_g2dbl_r3(s, t);
+  __syncwarp();
+  if (t < 4) wp_g2dbl_p3(s, t);
+  __syncwarp();
+}
+static __device__ __noinline__ void w_g2_add(WG2* s) {
+  const int t = threadIdx.x;
+  __syncwarp();
+  if (t == 0) wp_g2add_flags(s);
+  __syncwarp();
+  if (s->flag == 1) return;                      // uniform: s->flag is shared
+  if (s->flag == 2) {
+    if (t < 24) reinterpret_cast<uint4*>(&s->p)[t] = reinterpret_cast<const uint4*>(&s->e)[t];
+    __syncwarp();
+    return;
+  }
+  if (t < 12) wp_g2add_r1(s, t);
+  __syncwarp();
+  if (t < 8) wp_g2add_p1(s, t);
+  __syncwarp();
+  if (t == 0) wp_g2add_check(s);
+  __syncwarp();
+  if (s->flag == 3) return;
+  if (t < 10) wp_g2add_r2(s, t);
+  __syncwarp();
+  if (t < 8) wp_g2add_p2(s, t);
+  __syncwarp();
+  if (t < 9) wp_g2add_r3(s, t);
+  __syncwarp();
+  if (t < 8) wp_g2add_p3(s, t);
+  __syncwarp();
+  if (t < 9) wp_g2add_r4(s, t);
+  __syncwarp();
+  if (t < 4) wp_g2add_p4(s, t);
+  __syncwarp();
+}
+__global__ void __launch_bounds__(32) k_finalize_single_g2_coop(const uint4* __restrict__ group_w, int W, int c,
+                                                                uint4* __restrict__ out_affine) {
+  __shared__ WG2 s;
+  const int t = threadIdx.x;
+  if (t < 24) reinterpret_cast<uint4*>(&s.p)[t] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  for (int w = W - 1; w >= 0; w--) {
+    if (t < 24) reinterpret_cast<uint4*>(&s.e)[t] = group_w[24 * w + t];
+    __syncwarp();
+    w_g2_add(&s);
+    if (w > 0)
+      for (int k = 0; k < c; k++) w_g2_double(&s);
+  }
+  __syncwarp();
+  if (t < 8) lz_canon(reinterpret_cast<Fq*>(&s.p)[t]);
+  __syncwarp();
+  if (t == 0) {
+    Affine2 a;
+    xyzz2_to_affine_ni(&a, &s.p);
+    store_affine2(out_affine, a);
+  }
+}
+
 // G1 fold over phi(x, y) = (beta x, y) = [lambda](x, y), lambda = x^2 - 1 < 2^127: k = k1 lambda + k0 with k0 < lambda and
 // k1 = floor(k / lambda) < 2^127 (r < lambda^2 + lambda + 1), then a 2-way simultaneous multiplication, 127 doublings.
 // digits[0..3] = k0, digits[4..7] = k1 (128 bits each). Same precondition: the points lie in G1's order-r subgroup.
