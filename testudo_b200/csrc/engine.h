@@ -238,6 +238,8 @@ int g2_fixup_round(cudaStream_t st, uint32_t S_max, const uint32_t* starts, uint
                    uint4* heads, const int32_t* head_bucket);
 int g2_fixup_final(cudaStream_t st, uint32_t S_max, const uint32_t* starts, uint32_t B, uint32_t K, uint4* buckets,
                    const uint4* heads, const int32_t* head_bucket);
+int g2_reduce_pass_coop(cudaStream_t st, const uint4* inS, const uint4* inW, const uint32_t* level0, uint4* outS,
+                        uint4* outW, uint32_t L, int log2_ell, uint64_t n);   // engine_pairing.cu
 int g2_reduce_pass(cudaStream_t st, const uint4* inS, const uint4* inW, const uint32_t* level0, uint4* outS, uint4* outW,
                    uint32_t L, int log2_ell, uint64_t n);
 int g2_finalize_single(cudaStream_t st, const uint4* group_w, int W, int c, uint4* d_out);

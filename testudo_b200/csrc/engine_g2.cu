@@ -1,6 +1,8 @@
 // G2 unit of the engine: the point-touching stages of the MSM pipeline over Fq2 coordinates (kernels_g2.cuh) and the G2
 // entry points. The sort stages (digits / scan / scatter) are shared with G1 and live in engine_g1.cu.
 #define TB_NO_G1_KERNELS
+#include <cstring>
+
 #include "engine.h"
 #include "kernels_g2.cuh"
 
@@ -25,6 +27,9 @@ int g2_fixup_final(cudaStream_t st, uint32_t S_max, const uint32_t* starts, uint
 }
 int g2_reduce_pass(cudaStream_t st, const uint4* inS, const uint4* inW, const uint32_t* level0, uint4* outS, uint4* outW,
                    uint32_t L, int log2_ell, uint64_t n) {
+  // few outputs (every single G2 MSM of the reference: sqrt(n)-sized): one warp per output with the lane-parallel group law
+  if (n <= 8192 && !(getenv("TB200_G2_COMBINE") && !strcmp(getenv("TB200_G2_COMBINE"), "psi")))
+    return g2_reduce_pass_coop(st, inS, inW, level0, outS, outW, L, log2_ell, n);
   LAUNCH(k_reduce_pass_g2, cdiv(n, 64), 64, st, inS, inW, level0, outS, outW, L, log2_ell, n);
   return 0;
 }

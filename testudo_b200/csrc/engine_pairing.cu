@@ -22,6 +22,12 @@ int g2_finalize_single_glv(cudaStream_t st, const uint4* group_w, int W, int c, 
   return 0;
 }
 
+int g2_reduce_pass_coop(cudaStream_t st, const uint4* inS, const uint4* inW, const uint32_t* level0, uint4* outS,
+                        uint4* outW, uint32_t L, int log2_ell, uint64_t n) {
+  LAUNCH(k_reduce_pass_g2_coop, (uint32_t)n, 32, st, inS, inW, level0, outS, outW, L, log2_ell, n);
+  return 0;
+}
+
 int g1_fold_pre(cudaStream_t st, const uint4* a, uint32_t first, uint32_t count, uint4* mult) {
   LAUNCH(k_fold_pre_g1, cdiv(count, 128), 128, st, a, first, count, mult);
   return 0;

@@ -939,8 +939,8 @@ TB_HD void wp_ll_out(Fq12* L, const WScratch* w, int t) {
 // The Horner form sum_w 2^(c w) S_w is ~253 dependent doublings + W additions: on one thread 27 / 46 us each. Here the
 // Fq2 products of a doubling (dbl-2008-s-1) run as three rounds of 4 / 11 / 9 Fq products, those of an addition
 // (add-2008-s) as four rounds of 12 / 10 / 9 / 9, with the lazily reduced recombinations in between.
-// Accumulator p: coefficients < 1.01 q between operations (identity <=> ZZ = 0 mod q); operand e canonical.
-struct WG2 {
+// Accumulator p and operand e: coefficients < 1.01 q (identity <=> ZZ = 0 mod q; any representative of 0).
+struct alignas(16) WG2 {
   Xyzz2 p, e;
   Fq kar[12];
   Fq v[9][2];
@@ -1079,10 +1079,12 @@ TB_HD void wp_g2dbl_p3(WG2* s, int t) {
 
 // addition p += e. ONE item first: the exceptional shapes (identity operands), decided on canonical values
 TB_HD void wp_g2add_flags(WG2* s) {
-  Fq2 pz = s->p.zz;
+  Fq2 pz = s->p.zz, ez = s->e.zz;
   lz_canon(pz.c0);
   lz_canon(pz.c1);
-  s->flag = fq2_is_zero(s->e.zz) ? 1 : (fq2_is_zero(pz) ? 2 : 0);
+  lz_canon(ez.c0);
+  lz_canon(ez.c1);
+  s->flag = fq2_is_zero(ez) ? 1 : (fq2_is_zero(pz) ? 2 : 0);
 }
 // round 1, item t < 12: U1 = X1 ZZ2 (0-2), U2 = X2 ZZ1 (3-5), S1 = Y1 ZZZ2 (6-8), S2 = Y2 ZZZ1 (9-11); kar < 1.03 q
 TB_HD void wp_g2add_r1(WG2* s, int t) {
@@ -1123,10 +1125,12 @@ TB_HD void wp_g2add_check(WG2* s) {
   pv.c1 = s->v[G2V_T][1];
   if (!fq2_is_zero(pv)) return;
   s->flag = 3;
-  Xyzz2 a = s->p;
-  lz_canon(a.x.c0); lz_canon(a.x.c1); lz_canon(a.y.c0); lz_canon(a.y.c1);
-  lz_canon(a.zz.c0); lz_canon(a.zz.c1); lz_canon(a.zzz.c0); lz_canon(a.zzz.c1);
-  xyzz2_add(a, s->e);
+  Xyzz2 a = s->p, e = s->e;
+  for (int i = 0; i < 8; i++) {
+    lz_canon(reinterpret_cast<Fq*>(&a)[i]);
+    lz_canon(reinterpret_cast<Fq*>(&e)[i]);
+  }
+  xyzz2_add(a, e);
   s->p = a;
 }
 // round 2, item t < 10: 0-1 P^2, 2-3 R^2 (< 1.1 q), 4-6 ZZ1 ZZ2, 7-9 ZZZ1 ZZZ2 (< 1.03 q)

@@ -870,6 +870,66 @@ __global__ void __launch_bounds__(32) k_finalize_single_g2_coop(const uint4* __r
   }
 }
 
+// One level of the hierarchical bucket reduction of a G2 MSM (as k_reduce_pass_g2: running sums S, weighted sums W), one
+// WARP per output with the lane-parallel group law: these levels hold few elements (sqrt(n)-sized MSMs) and a thread of
+// k_reduce_pass_g2 walks through 2 L + log2(ell) dependent group operations of ~50 us each (2.8 of the 6 ms of a
+// 2^13-point MSM).
+__global__ void __launch_bounds__(32) k_reduce_pass_g2_coop(const uint4* __restrict__ inS, const uint4* __restrict__ inW,
+                                                            const uint32_t* __restrict__ bucket_start,
+                                                            uint4* __restrict__ outS, uint4* __restrict__ outW, uint32_t L,
+                                                            int log2_ell, uint64_t total_out) {
+  __shared__ WG2 run, acc;      // run.p = running sum, acc.p = weighted sum
+  const int lane = threadIdx.x;
+  const uint64_t t = blockIdx.x;
+  if (t >= total_out) return;
+  uint4* rp = reinterpret_cast<uint4*>(&run.p);
+  uint4* re = reinterpret_cast<uint4*>(&run.e);
+  uint4* ap = reinterpret_cast<uint4*>(&acc.p);
+  uint4* ae = reinterpret_cast<uint4*>(&acc.e);
+  if (lane < 24) {
+    rp[lane] = make_uint4(0, 0, 0, 0);
+    ap[lane] = make_uint4(0, 0, 0, 0);
+  }
+  __syncwarp();
+  for (int i = (int)L - 1; i >= 0; i--) {
+    const uint64_t idx = t * L + i;
+    bool empty = false;
+    if (bucket_start) empty = bucket_start[idx + 1] == bucket_start[idx];
+    if (!empty) {
+      if (lane < 24) re[lane] = inS[24 * idx + lane];
+      __syncwarp();
+      w_g2_add(&run);
+    }
+    if (i > 0) {
+      if (lane < 24) ae[lane] = rp[lane];
+      __syncwarp();
+      w_g2_add(&acc);
+    }
+  }
+  __syncwarp();
+  if (lane < 8) lz_canon(reinterpret_cast<Fq*>(&run.p)[lane]);
+  __syncwarp();
+  if (lane < 24) outS[24 * t + lane] = rp[lane];
+  for (int k = 0; k < log2_ell; k++) w_g2_double(&acc);
+  if (inW) {
+    if (lane < 24) rp[lane] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    for (int i = 0; i < (int)L; i++) {
+      if (lane < 24) re[lane] = inW[24 * (t * L + i) + lane];
+      __syncwarp();
+      w_g2_add(&run);
+    }
+  }
+  __syncwarp();
+  if (lane < 24) ae[lane] = rp[lane];
+  __syncwarp();
+  w_g2_add(&acc);
+  __syncwarp();
+  if (lane < 8) lz_canon(reinterpret_cast<Fq*>(&acc.p)[lane]);
+  __syncwarp();
+  if (lane < 24) outW[24 * t + lane] = ap[lane];
+}
+
 // G1 fold over phi(x, y) = (beta x, y) = [lambda](x, y), lambda = x^2 - 1 < 2^127: k = k1 lambda + k0 with k0 < lambda and
 // k1 = floor(k / lambda) < 2^127 (r < lambda^2 + lambda + 1), then a 2-way simultaneous multiplication, 127 doublings.
 // digits[0..3] = k0, digits[4..7] = k1 (128 bits each). Same precondition: the points lie in G1's order-r subgroup.
