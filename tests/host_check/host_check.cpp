@@ -19,6 +19,11 @@ void hc_fq_inv(const uint32_t* a, uint32_t* r) { Fq x, y; memcpy(x.l, a, 48); fq
 void hc_fq_inv_fermat(const uint32_t* a, uint32_t* r) { Fq x, y; memcpy(x.l, a, 48); fq_inv_fermat(y, x); memcpy(r, y.l, 48); }
 void hc_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { mont_mul<FrParams>(r, a, b); }
 void hc_fr_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { mod_add<FrParams>(r, a, b); }
+// (a b + c d) R^-1 with ONE reduction, then one conditional subtraction: the pair product of k_fr_matvec
+void hc_fr_mul2(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* r) {
+  mont_mul2_lazy<FrParams>(r, a, b, c, d);
+  mod_reduce_once<FrParams>(r);
+}
 void hc_fr_to_canonical(const uint32_t* a, uint32_t* r) { mont_to_canonical<FrParams>(r, a); }
 void hc_consts(uint32_t* q, uint32_t* q_one, uint32_t* q_r2, uint32_t* r, uint32_t* r_one, uint32_t* r_r2) {
   for (int i = 0; i < 12; i++) { q[i] = FqParams::p(i); q_one[i] = FqParams::one(i); q_r2[i] = FqParams::r2(i); }

@@ -227,3 +227,23 @@ def test_lazy_g2_xyzz_group_law(hc):
     assert to_affine(op(1, inf, xyzz(Q0))) == Q0
     assert to_affine(op(1, d, inf)) == to_affine(d)
     assert to_affine(op(0, inf)) is None
+
+
+def test_fr_pair_product_with_one_reduction(hc):
+    """mont_mul2_lazy<Fr> + one conditional subtraction (the pair product of k_fr_matvec) on extreme and random operands:
+    Fr has only 3 spare bits, so b + d + r < 2^256 is the bound that matters"""
+    R = o.R_ORDER
+    RR = 1 << 256
+    rinv = pow(RR, -1, R)
+    rng = random.Random(67)
+    ext = [0, 1, R - 1, R - 2, 1 << 252, (1 << 252) - 1, R >> 1]
+
+    def w(v):
+        return np.array([(v >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=np.uint32)
+
+    for it in range(3000):
+        a, b, c, d = ([R - 1] * 4 if it == 0 else
+                      [rng.choice(ext) if rng.random() < 0.4 else rng.randrange(R) for _ in range(4)])
+        out = np.zeros(8, dtype=np.uint32)
+        hc.hc_fr_mul2(P(w(a)), P(w(b)), P(w(c)), P(w(d)), P(out))
+        assert sum(int(out[i]) << (32 * i) for i in range(8)) == (a * b + c * d) * rinv % R

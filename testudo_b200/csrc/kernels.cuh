@@ -701,14 +701,33 @@ __device__ __forceinline__ void fr_warp_sum(uint32_t* acc) {  // butterfly sum o
   }
 }
 // q[j] = sum_i Z[j * cols + i] * v[i]  (get_q, src/sqrt_pst.rs:81-101: Z[(j << m_col) | i] * chis[i]); one warp per j,
-// lanes read 32 consecutive scalars (1 KiB) per step. HBM-bound: 32 B per multiply-add.
+// lanes read 32 consecutive scalars (1 KiB) per step.
 __global__ void __launch_bounds__(256) k_fr_matvec(const uint32_t* __restrict__ Z, uint32_t rows, uint32_t cols,
                                                    const uint32_t* __restrict__ v, uint32_t* __restrict__ out) {
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t j = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (j >= rows) return;
+  // The kernel moves 32 B per product but a canonical Fr product is 120 wide MACs: at 2^26 products that is 0.9 ms of the
+  // integer pipe against 0.33 ms of HBM time -- the pipe, not the memory, is the bound. Two products share ONE
+  // Montgomery reduction (mont_mul2_lazy: 184 instead of 240 wide MACs per pair; b + d + r < 2^256 holds for canonical
+  // operands, the result is below 1.15 r: one conditional subtraction).
   uint32_t acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (uint32_t i = lane; i < cols; i += 32) {
+  uint32_t i = lane;
+  for (; i + 32 < cols; i += 64) {
+    const uint4* zp = reinterpret_cast<const uint4*>(Z + 8 * (j * cols + i));
+    const uint4* vp = reinterpret_cast<const uint4*>(v + 8 * (uint64_t)i);
+    const uint4 z0 = __ldg(zp), z1 = __ldg(zp + 1), v0 = __ldg(vp), v1 = __ldg(vp + 1);
+    const uint4 y0 = __ldg(zp + 64), y1 = __ldg(zp + 65), w0 = __ldg(vp + 64), w1 = __ldg(vp + 65);   // element i + 32
+    uint32_t a[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+    uint32_t c[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint32_t b[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+    uint32_t d[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    uint32_t t[8];
+    mont_mul2_lazy<FrParams>(t, a, c, b, d);
+    mod_reduce_once<FrParams>(t);
+    mod_add<FrParams>(acc, acc, t);
+  }
+  for (; i < cols; i += 32) {
     const uint4* zp = reinterpret_cast<const uint4*>(Z + 8 * (j * cols + i));
     const uint4* vp = reinterpret_cast<const uint4*>(v + 8 * (uint64_t)i);
     uint4 z0 = __ldg(zp), z1 = __ldg(zp + 1), v0 = __ldg(vp), v1 = __ldg(vp + 1);
