@@ -218,6 +218,13 @@ int tb200_fr_matvec(const uint64_t* Z, size_t rows, size_t cols, const uint64_t*
 int tb200_fr_matvec_dev(const void* d_Z, size_t rows, size_t cols, const void* d_v, void* d_out, void* stream);
 
 /* ---- group utilities ------------------------------------------------------------------------------------ */
+/* `rows` INDEPENDENT tiny MSMs in one launch: out[i] = sum_{j < per_row} scalars[i*per_row + j] * bases[i*per_row + j],
+ * per_row <= 8 (one warp per row, a quad of lanes per point, the small-n Straus kernel). The verifier side of the path:
+ * ark-poly-commit 0.4 `MultilinearPC::check` forms `commitment - g*value` and `g_mask_random[i] - g*point[i]` for every
+ * variable (reached from `Polynomial::verify`, src/sqrt_pst.rs:262) -- nv + 1 two-point MSMs for the latency of one.
+ * Accepts any curve point; scalars canonical, or Montgomery with TB200_SCALARS_MONT; (0, 0) in / out = identity. */
+int tb200_msm_g1_each(const uint64_t* bases_xy, const uint64_t* scalars, size_t rows, size_t per_row, unsigned flags,
+                      uint64_t* out_xy);
 /* out = sum of n affine points (combining per-GPU partial results after the NCCL all-gather) */
 int tb200_g1_sum(const uint64_t* pts_xy, size_t n, uint64_t out_xy[12]);
 int tb200_g1_sum_dev(const void* d_pts_xy, size_t n, void* d_out_xy, void* stream);
@@ -290,6 +297,12 @@ int tb200_test_fq12_op(int op, const uint64_t* a, const uint64_t* b, size_t n, u
  * `pairings_product`, src/mipp.rs:396-398. Pairs with an identity on either side contribute 1, as in ark; n == 0
  * yields 1. */
 int tb200_multi_pairing(const uint64_t* g1_xy, const uint64_t* g2, size_t n, uint64_t out[72]);
+/* `products` independent pairing products of `pairs_each` pairs each in ONE pass of the pairing engine; product p takes the
+ * pairs [p * pairs_each, (p + 1) * pairs_each) and lands at out + 72 p. Identity pairs contribute 1, so shorter products
+ * are padded with (0, 0) points. The verifier side of the path evaluates five products -- `E::pairing(final_a, final_h)`
+ * (src/mipp.rs:320), both sides of `check_2` (:313) and of `MultilinearPC::check` (src/sqrt_pst.rs:262) -- for the latency
+ * of one. */
+int tb200_multi_pairing_batch(const uint64_t* g1_xy, const uint64_t* g2, size_t products, size_t pairs_each, uint64_t* out);
 /* Same with DEVICE pointers; d_out receives 576 bytes; returns after enqueueing on `stream` (NULL = library stream). */
 int tb200_multi_pairing_dev(const void* d_g1_xy, const void* d_g2, size_t n, void* d_out, void* stream);
 /* Sharded pairing product (one process per GPU): each rank reduces ITS slice of the pairs to one partial
@@ -319,6 +332,11 @@ void tb200_set_pairing_coop_max(int n);
  * two warps unless 32 is forced. 0 (default) = by size: 96 up to 512 pairs, 33 above. Identical results. */
 void tb200_set_pairing_team(int lanes);
 int tb200_gt_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned flags, uint64_t* out);
+/* out = prod_i bases[i] ^ exps[i] in GT: the TC half of the verifier's parallel fold / reduce over `MippTU`
+ * (src/mipp.rs:238-271: `tx.pow(c)`, `res.tc.mul_assign(&tx)`, `merge`) in one call -- every power on its own team of
+ * lanes, then the product tree of the pairing engine. Generic field arithmetic (proof values need not be unitary);
+ * n == 0 yields 1. Exponents as for tb200_gt_pow. */
+int tb200_gt_multi_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned flags, uint64_t out[72]);
 
 /* ---- Poseidon sponge of the Fiat-Shamir transcript (HOST code, as in the reference) ----------------
  * Restates ark-crypto-primitives 0.4 `PoseidonSponge<F>` behind `PoseidonTranscript<F>` (src/poseidon_transcript.rs:12-125).

@@ -373,6 +373,22 @@ void hc_coop_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
   hcw_canon(&z);
   memcpy(r, &z, 576);
 }
+// the chain of k_fq12_pow_coop: a^e by square-and-multiply from the top set bit with the GENERIC lazily reduced square /
+// product (e: 8 canonical 32-bit limbs, not zero); r canonical
+void hc_coop_pow(const uint32_t* a, const uint32_t* e, uint32_t* r) {
+  Fq12 x, z;
+  memcpy(&x, a, 576);
+  int top = -1;
+  for (int i = 7; i >= 0 && top < 0; i--)
+    if (e[i]) top = 32 * i + 31 - __builtin_clz(e[i]);
+  z = x;
+  for (int bit = top - 1; bit >= 0; bit--) {
+    hcw_sqr(&z, &z);
+    if ((e[bit >> 5] >> (bit & 31)) & 1) hcw_mul(&z, &z, &x);
+  }
+  hcw_canon(&z);
+  memcpy(r, &z, 576);
+}
 // the largest top limb over the 12 output coefficients of op BEFORE canonicalisation (the invariant: < 1.02 q)
 uint32_t hc_coop_op_top(int op, const uint32_t* a, const uint32_t* b) {
   Fq12 x, y, z;

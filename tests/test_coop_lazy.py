@@ -124,6 +124,21 @@ def test_lazy_cyclotomic_chain_and_final_exponentiation(hc):
         assert run(hc, 8, f12_to_raw(x)) == pr.final_exponentiation(x)
 
 
+def test_lazy_generic_power_chain(hc):
+    """The chain of k_fq12_pow_coop (the verifier's `tx.pow(c)`, src/mipp.rs:252-255): ~253 generic lazily reduced squarings
+    with a product after every set bit, on arbitrary field elements (proof values are not known to be unitary)."""
+    rng = random.Random(47)
+    cases = [(tuple((rng.randrange(Q), rng.randrange(Q)) for _ in range(6)), e)
+             for e in (1, 2, 3, o.R_ORDER - 1, (1 << 253) - 1, rng.randrange(1, o.R_ORDER), 1 << 252, (1 << 256) - 1)]
+    cases.append((tuple((Q - 1, Q - 1) for _ in range(6)), rng.randrange(1, o.R_ORDER)))
+    for x, e in cases:
+        A = raw_words(f12_to_raw(x))
+        ew = np.array([(e >> (32 * i)) & 0xFFFFFFFF for i in range(8)], dtype=np.uint32)
+        out = np.zeros(72, dtype=np.uint64)
+        hc.hc_coop_pow(P(A), P(ew), P(out))
+        assert pr.from_words(out) == pr.f12_pow(x, e)
+
+
 def g2hom_words(pt):
     out = []
     for c in pt:

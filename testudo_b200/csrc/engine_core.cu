@@ -1289,5 +1289,43 @@ int tb200_miller_product(const uint64_t* g1_xy, const uint64_t* g2, size_t n, ui
   if (n >= (1u << 26)) return fail(TB200_E_LIMIT, "too many pairs");
   return pairing_host_locked(g1_xy, g2, n, out, 1);
 }
+// `products` independent pairing products of `pairs_each` pairs in ONE pass of the pairing engine (the Miller loops of
+// all products in one launch, one product tree per segment, the final exponentiations side by side): a verifier's five
+// products cost the latency of one. Shorter products are padded with identity pairs, which contribute 1.
+int tb200_multi_pairing_batch(const uint64_t* g1_xy, const uint64_t* g2, size_t products, size_t pairs_each, uint64_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (products == 0) return 0;
+  if (!out || (pairs_each && (!g1_xy || !g2))) return fail(TB200_E_ARG, "null pointer");
+  if (products > 4096 || pairs_each >= (1u << 20) || products * pairs_each >= (1u << 22))
+    return fail(TB200_E_LIMIT, "batch of pairing products too large");
+  if (pairs_each == 0 && products > 32) return fail(TB200_E_LIMIT, "more than 32 empty products");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  g.marks.clear();
+  const size_t n = products * pairs_each;
+  uint4 *d_p = nullptr, *d_q = nullptr, *d_o = nullptr;
+  std::vector<void*> to_free;
+  CU(cudaMallocAsync((void**)&d_o, products * 576, g.stream));
+  to_free.push_back(d_o);
+  if (n) {
+    CU(cudaMallocAsync((void**)&d_p, n * 96, g.stream));
+    to_free.push_back(d_p);
+    CU(cudaMallocAsync((void**)&d_q, n * 192, g.stream));
+    to_free.push_back(d_q);
+    CU(cudaMemcpyAsync(d_p, g1_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(d_q, g2, n * 192, cudaMemcpyHostToDevice, g.stream));
+  }
+  int rc = pairing_products(g, d_p, d_q, (uint32_t)n, 0, (uint32_t)products, d_o, g.stream, nullptr, nullptr, true);
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(out, d_o, products * 576, cudaMemcpyDeviceToHost, g.stream);
+    if (e != cudaSuccess) rc = fail((int)e, "pairing result copy failed: %s", cudaGetErrorString(e));
+  }
+  cudaError_t e = cudaStreamSynchronize(g.stream);
+  if (e != cudaSuccess && rc == 0) rc = fail((int)e, "device %d failed: %s", g.device, cudaGetErrorString(e));
+  free_all(g, to_free);
+  if (rc == 0) rc = finish_marks(g, g.stream);
+  return rc;
+}
 
 }  // extern "C"

@@ -320,7 +320,7 @@ int msm_dev(Ctx& g, const void* d_bases, const void* d_scalars, size_t n, unsign
     if (points_ready) CU(cudaStreamWaitEvent(st, points_ready, 0));
     if (mark(g, st, "begin")) return 1;
     LAUNCH(k_msm_small, nblk, 4 * SMALL_QUADS, st, (const uint4*)d_bases, (const uint32_t*)d_scalars, (uint32_t)n,
-           (flags & TB200_SCALARS_MONT) ? 1 : 0, scratch, (uint4*)d_out);
+           (flags & TB200_SCALARS_MONT) ? 1 : 0, scratch, (uint4*)d_out, 0u);
     if (scratch) CU(cudaFreeAsync(scratch, st));
     if (mark(g, st, "accumulate")) return 1;
     g.last_c = 4;
@@ -1078,6 +1078,35 @@ int tb200_g1_sum(const uint64_t* pts_xy, size_t n, uint64_t out_xy[12]) {
   CU(cudaMemcpyAsync(g.h_result, g.d_result, 96, cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
   memcpy(out_xy, g.h_result, 96);
+  return 0;
+}
+// `rows` independent MSMs of `per_row` (1..8) points each in ONE launch of the Straus kernel: out[i] = sum_j
+// scalars[i][j] * bases[i][j]. The verifier's `g_mask[i] - z_i g` (ark-poly-commit `check`) and `C - v g`.
+int tb200_msm_g1_each(const uint64_t* bases_xy, const uint64_t* scalars, size_t rows, size_t per_row, unsigned flags,
+                      uint64_t* out_xy) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (rows == 0) return 0;
+  if (!bases_xy || !scalars || !out_xy) return fail(TB200_E_ARG, "null pointer");
+  if (per_row == 0 || per_row > (size_t)SMALL_QUADS) return fail(TB200_E_ARG, "per_row = %zu: between 1 and %d", per_row, SMALL_QUADS);
+  if (rows > (1u << 16)) return fail(TB200_E_LIMIT, "tb200_msm_g1_each takes at most 65536 rows");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  const size_t n = rows * per_row;
+  uint4 *d_b = nullptr, *d_o = nullptr;
+  uint32_t* d_s = nullptr;
+  CU(cudaMallocAsync((void**)&d_b, n * 96, g.stream));
+  CU(cudaMallocAsync((void**)&d_s, n * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_o, rows * 96, g.stream));
+  CU(cudaMemcpyAsync(d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
+  CU(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, g.stream));
+  LAUNCH(k_msm_small, (uint32_t)rows, 4 * SMALL_QUADS, g.stream, d_b, d_s, (uint32_t)n, (flags & TB200_SCALARS_MONT) ? 1 : 0,
+         (uint4*)nullptr, d_o, (uint32_t)per_row);
+  CU(cudaMemcpyAsync(out_xy, d_o, rows * 96, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  cudaFreeAsync(d_b, g.stream);
+  cudaFreeAsync(d_s, g.stream);
+  cudaFreeAsync(d_o, g.stream);
   return 0;
 }
 int tb200_g1_outer_sum_dev(const void* d_a_xy, size_t na, const void* d_b_xy, size_t nb, void* d_out_xy, void* stream) {

@@ -1208,6 +1208,53 @@ __global__ void __launch_bounds__(W12_THREADS) k_test_w12_op(int op, const uint4
   for (int i = lane; i < 36; i += blockDim.x) out[36 * (size_t)blockIdx.x + i] = r4[i];
 }
 
+// a^e for GT elements on ONE TEAM per element (the verifier's `tx.pow(c)`, src/mipp.rs:252-255): the thread-per-element
+// kernel above walks ~380 Fq12 operations of 36-54 serial Fq products each (~17 ms whatever n is); the verifier raises 2 m
+// <= 28 values, so the chain's latency is all that counts: square-and-multiply from the top set bit with the cooperative
+// Fq12 square / product (54 / 36 lanes busy per phase). Generic squarings: the inputs are proof values, nothing says they
+// lie in the cyclotomic subgroup. Canonical input, canonical output.
+struct WPow {
+  Fq12 base, acc;
+  WScratch w;
+  uint32_t e[8];
+};
+__global__ void __launch_bounds__(W12_THREADS) k_fq12_pow_coop(const uint4* __restrict__ in,
+                                                               const uint32_t* __restrict__ exps, int exps_mont,
+                                                               uint4* __restrict__ out) {
+  __shared__ WPow s;
+  const Team tm = team_cta();
+  const int lane = threadIdx.x;
+  uint4* b4 = reinterpret_cast<uint4*>(&s.base);
+  for (int i = lane; i < 36; i += blockDim.x) b4[i] = in[36 * (size_t)blockIdx.x + i];
+  if (lane == 0) {
+    uint32_t e[8];
+    bool zero = true;
+    for (int i = 0; i < 8; i++) {
+      e[i] = exps[8 * (size_t)blockIdx.x + i];
+      zero = zero && e[i] == 0;
+    }
+    if (exps_mont && !zero) mont_to_canonical<FrParams>(e, e);
+    for (int i = 0; i < 8; i++) s.e[i] = e[i];
+  }
+  team_sync(tm);
+  int top = -1;                                     // team-uniform: every lane reads the same shared words
+  for (int i = 7; i >= 0 && top < 0; i--)
+    if (s.e[i]) top = 32 * i + 31 - __clz(s.e[i]);
+  if (top < 0) {                                    // a^0 = 1
+    if (lane < 12) w12_q(&s.acc)[lane] = lane == 0 ? fq_one() : fq_zero();
+    team_sync(tm);
+  } else {
+    w12_copy(&s.acc, &s.base, tm);
+    for (int bit = top - 1; bit >= 0; bit--) {
+      w12_sqr(&s.acc, &s.acc, &s.w, tm);
+      if ((s.e[bit >> 5] >> (bit & 31)) & 1) w12_mul(&s.acc, &s.acc, &s.base, &s.w, tm);
+    }
+  }
+  w12_canon(&s.acc, tm);
+  const uint4* r4 = reinterpret_cast<const uint4*>(&s.acc);
+  for (int i = lane; i < 36; i += blockDim.x) out[36 * (size_t)blockIdx.x + i] = r4[i];
+}
+
 __global__ void __launch_bounds__(32) k_test_fq12_op(int op, const uint4* a, const uint4* b, uint32_t n, uint4* out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;

@@ -243,9 +243,13 @@ __device__ __forceinline__ int quad_table_slot(int k) { return QS_SLOTS + 4 * (k
 
 // out = sum_i scalars[i] * bases[i], n <= SMALL_MAX_POINTS. Grid = ceil(n / 8) CTAs of 32 threads. scratch: gridDim.x XYZZ
 // partial sums (12 uint4 each) followed by one uint4 whose .x is the ticket counter (zeroed by the caller).
+// `per_row` > 0 (<= 8): gridDim.x INDEPENDENT MSMs of per_row points each -- CTA b multiplies points
+// [b * per_row, (b + 1) * per_row) and writes its own affine result to out_affine + 6 b; no cross-CTA sum, no scratch
+// (the verifier's g_mask[i] - z_i g, ark-poly-commit `check`: nv two-point MSMs for the latency of one).
 __global__ void __launch_bounds__(4 * SMALL_QUADS) k_msm_small(const uint4* __restrict__ bases,
                                                                const uint32_t* __restrict__ scalars, uint32_t n, int mont,
-                                                               uint4* __restrict__ scratch, uint4* __restrict__ out_affine) {
+                                                               uint4* __restrict__ scratch, uint4* __restrict__ out_affine,
+                                                               uint32_t per_row) {
   __shared__ uint4 small_sm[SMALL_SLOTS_PER_QUAD * 3 * SMALL_QUADS + (SMALL_QUADS * SMALL_DIGITS + SMALL_QUADS * 4 + 16) / 16];
   __shared__ int is_last;
   constexpr int nq = SMALL_QUADS;
@@ -254,11 +258,12 @@ __global__ void __launch_bounds__(4 * SMALL_QUADS) k_msm_small(const uint4* __re
   c.nq = nq;
   c.quad = threadIdx.x >> 2;
   c.role = threadIdx.x & 3;
-  const uint32_t pt = blockIdx.x * nq + c.quad;      // this quad's point
+  const uint32_t per = per_row ? per_row : (uint32_t)nq;
+  const uint32_t pt = blockIdx.x * per + c.quad;     // this quad's point
   int8_t* digits = reinterpret_cast<int8_t*>(small_sm + (size_t)SMALL_SLOTS_PER_QUAD * 3 * nq);   // [nq][64]
   int* quad_flag = reinterpret_cast<int*>(digits + (size_t)nq * SMALL_DIGITS);                    // [nq]
   if (threadIdx.x == 0) is_last = 0;
-  const bool live = pt < n;
+  const bool live = (uint32_t)c.quad < per && pt < n;
   // ---- per point: digits, table entry 1 = the point itself (or the identity), accumulator = identity --------------------
   bool any = false;
   if (c.role == 0) {
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(4 * SMALL_QUADS) k_msm_small(const uint4* __re
       store_xyzz(tree + 12 * c.quad, acc);
     }
   }
-  const uint32_t nb = gridDim.x;
+  const uint32_t nb = per_row ? 1u : gridDim.x;
   if (nb > 1) {
     if (threadIdx.x == 0) {
       store_xyzz(scratch + 12 * (size_t)blockIdx.x, acc);
@@ -385,7 +390,7 @@ __global__ void __launch_bounds__(4 * SMALL_QUADS) k_msm_small(const uint4* __re
     xyzz_canon(acc);
     Affine o;
     xyzz_to_affine_ni(&o, &acc);
-    store_affine(out_affine, o);
+    store_affine(out_affine + (per_row ? 6 * (size_t)blockIdx.x : 0), o);
   }
 }
 

@@ -139,6 +139,60 @@ class MippProofG1:
         return out
 
 
+    def verify_begin(self, vk: "multilinear_pc.VerifierKey", challenge: Callable[[bytes, List[np.ndarray]], int],
+                     point: List[int], U, T):
+        """Everything of `MippProof::verify` (src/mipp.rs:182-333) up to the pairings: the transcript replay, the TC fold
+        `T * prod comm_t_l^(c_inv) comm_t_r^(c)` (one tb200_gt_multi_pow), the UC fold `U + sum c_inv comm_u_l + c
+        comm_u_r` (one MSM), final_u, and the OPERANDS of the three pairing products still to evaluate -- so that a caller
+        (`Polynomial.verify`) can run them in one pass together with its own. Returns None when a challenge has no
+        inverse (the reference panics), else (check_u, tc, [final_t, check_2 left, check_2 right])."""
+        from . import pairing
+        m = len(self.comms_u)
+        if len(self.comms_t) != m or len(point) < m:
+            raise ValueError("one (comm_u, comm_t) pair and one point coordinate per round")
+        U = np.ascontiguousarray(U, dtype=np.uint64).reshape(12)
+        T = np.ascontiguousarray(T, dtype=np.uint64).reshape(pairing.GT_WORDS)
+        xs, xs_inv, final_y = [], [], 1
+        challenge(b"U", [U])                                                     # :198
+        for i, ((ul, ur), (tl, tr)) in enumerate(zip(self.comms_u, self.comms_t)):
+            c_inv = challenge(b"challenge_i", [ul, ur, tl, tr]) % fr.R          # :207-211
+            if c_inv == 0:
+                return None                                                      # `c_inv.inverse().unwrap()`, :213
+            xs.append(fr.inverse(c_inv))
+            xs_inv.append(c_inv)
+            final_y = final_y * (1 + c_inv * point[i] - point[i]) % fr.R        # :221
+        # :238-277, the fold / reduce over MippTU seeded with (T, U): exponent 1 for the seeds
+        t_bases = np.stack([T] + [t for tl, tr in self.comms_t for t in (tl, tr)])
+        u_bases = np.stack([U] + [u for ul, ur in self.comms_u for u in (ul, ur)])
+        exps = curve.scalars_to_words([1] + [e for c, ci in zip(xs, xs_inv) for e in (ci, c)])
+        tc = pairing.gt_multi_pow(t_bases, exps)
+        uc = msm.msm_bigint(u_bases, exps)
+        rs = [challenge(b"random_point", []) % fr.R for _ in range(m)]           # :281-285
+        v = 1
+        for i in range(m):
+            v = v * (1 + rs[i] * xs_inv[m - i - 1] - rs[i]) % fr.R              # :294-297
+        final_u = msm.msm_bigint(np.asarray(self.final_a).reshape(1, 12), curve.scalars_to_words([final_y]))   # :311
+        check_u = bool(np.array_equal(uc, final_u))                              # :317
+        products = [(np.asarray(self.final_a).reshape(1, 12), np.asarray(self.final_h).reshape(1, 24))]   # final_t, :312
+        products += multilinear_pc.check_2_products(vk, self.final_h, rs, v, self.pst_proof_h)            # check_h, :308
+        return check_u, tc, products
+
+    def verify(self, vk: "multilinear_pc.VerifierKey", challenge: Callable[[bytes, List[np.ndarray]], int],
+               point: List[int], U, T) -> bool:
+        """`MippProof::verify(vk, transcript, proof, point, U, T)` (src/mipp.rs:182-333) for this proof (comms_u, comms_t,
+        final_a, final_h, pst_proof_h). `challenge` replays the transcript exactly as `prove` drove it; all group and
+        pairing work runs on the GPU; the reference's asserts become a False result."""
+        from . import pairing
+        parts = self.verify_begin(vk, challenge, point, U, T)
+        if parts is None:
+            return False
+        check_u, tc, products = parts
+        final_t, left, right = pairing.multi_pairing_batch(products)
+        check_t = bool(np.array_equal(tc, final_t))                              # :314
+        check_h = bool(np.array_equal(left, right))                              # :308-309
+        return check_h and check_t and check_u
+
+
 def polynomial_evaluations_words(cs_inv: List[int]) -> np.ndarray:
     """The same evaluations as [2^m, 4] Montgomery words, computed on the device (tb200_fr_subset_products): the Python
     loop below plus the conversion of 2^13 integers costs ~12 ms of host time per proof, the kernel nothing."""

@@ -63,3 +63,17 @@ def g1_sum(points) -> np.ndarray:
     out = np.zeros(12, dtype=np.uint64)
     _lib.check(_lib.engine().tb200_g1_sum(_ptr(p), len(p), _ptr(out)))
     return out
+
+
+def msm_each(bases, bigints, per_row: int) -> np.ndarray:
+    """`rows` independent MSMs of `per_row` (<= 8) points each in one launch (tb200_msm_g1_each): bases [rows * per_row, 12],
+    canonical scalars [rows * per_row, 4] -> [rows, 12]. The verifier's `commitment - g*value` and
+    `g_mask_random[i] - g*point[i]` (ark-poly-commit `MultilinearPC::check`)."""
+    b = _u64(bases, 12)
+    s = _u64(bigints, 4)
+    if len(b) != len(s) or per_row <= 0 or len(b) % per_row:
+        raise ValueError("bases and scalars must hold rows * per_row entries")
+    rows = len(b) // per_row
+    out = np.zeros((rows, 12), dtype=np.uint64)
+    _lib.check(_lib.engine().tb200_msm_g1_each(_ptr(b), _ptr(s), rows, per_row, 0, _ptr(out)))
+    return out

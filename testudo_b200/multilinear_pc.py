@@ -14,11 +14,12 @@ Montgomery-form field elements by default (ark's `Fr`), canonical with mont=Fals
 from __future__ import annotations
 
 import ctypes
+from dataclasses import dataclass
 from typing import Sequence
 
 import numpy as np
 
-from . import _lib
+from . import _lib, curve, msm, msm_g2, pairing
 
 
 class PendingOpen:
@@ -90,3 +91,96 @@ def open_begin(level_bases_h: Sequence[np.ndarray], evals, point, mont: bool = T
 def open_g1_begin(level_bases_g: Sequence[np.ndarray], evals, point, mont: bool = True) -> PendingOpen:
     """`open_g1` started without waiting (tb200_pst_open_g1_begin)."""
     return _open(level_bases_g, evals, point, mont, False, asynchronous=True)
+
+
+# ---- verifier side: `MultilinearPC::check` (ark-poly-commit 0.4) and the fork's `check_2` ---------------------------------
+@dataclass
+class VerifierKey:
+    """ark-poly-commit `VerifierKey<E>{nv, g, h, g_mask_random}` plus the fork's `h_mask_random` (SURVEY.md App. A.3;
+    field usage at src/circuit_verifier.rs:188-232,258-281). `MultilinearPC::trim` yields it next to the committer key:
+    g_mask_random[i] = t_i g, h_mask_random[i] = t_i h for the trapdoor t. Arrays in ark's in-memory layout."""
+    nv: int
+    g: np.ndarray                  # [12]
+    h: np.ndarray                  # [24]
+    g_mask_random: np.ndarray      # [nv, 12]
+    h_mask_random: np.ndarray      # [nv, 24]
+
+    def __post_init__(self):
+        self.g = np.ascontiguousarray(self.g, dtype=np.uint64).reshape(12)
+        self.h = np.ascontiguousarray(self.h, dtype=np.uint64).reshape(24)
+        self.g_mask_random = np.ascontiguousarray(self.g_mask_random, dtype=np.uint64).reshape(-1, 12)
+        self.h_mask_random = np.ascontiguousarray(self.h_mask_random, dtype=np.uint64).reshape(-1, 24)
+        if len(self.g_mask_random) != self.nv or len(self.h_mask_random) != self.nv:
+            raise ValueError("the verifier key holds one mask per variable")
+
+
+_ONE = np.array([1, 0, 0, 0], dtype=np.uint64)
+
+
+def _neg_words(values: Sequence[int]) -> np.ndarray:
+    """canonical limbs of -v mod r (scalar arithmetic stays on the host, as in the reference)"""
+    return curve.scalars_to_words([(-int(v)) % curve.R_ORDER for v in values])
+
+
+def check_products(vk: VerifierKey, commitment, point: Sequence[int], value: int, proofs):
+    """The two pairing products of `check` as operand lists [(g1s, g2s) left, (g1s, g2s) right]: the nv + 1 G1 values are
+    two-point MSMs ({C, g} x {1, -v}; {g_mask_i, g} x {1, -z_i}) -- ark builds them from a fixed-base table of g -- and run
+    as ONE launch (tb200_msm_g1_each)."""
+    c = np.ascontiguousarray(commitment, dtype=np.uint64).reshape(12)
+    pi = np.ascontiguousarray(proofs, dtype=np.uint64).reshape(-1, 24)
+    nv = vk.nv
+    if len(point) != nv or len(pi) != nv:
+        raise ValueError("point and proof must have vk.nv entries")          # the reference indexes 0..vk.nv (panics)
+    bases = np.zeros((nv + 1, 2, 12), dtype=np.uint64)
+    bases[0, 0] = c
+    bases[1:, 0] = vk.g_mask_random
+    bases[:, 1] = vk.g
+    scalars = np.zeros((nv + 1, 2, 4), dtype=np.uint64)
+    scalars[:, 0] = _ONE
+    scalars[:, 1] = _neg_words([value] + list(point))
+    pts = msm.msm_each(bases.reshape(-1, 12), scalars.reshape(-1, 4), 2)
+    return [(pts[:1], vk.h.reshape(1, 24)), (pts[1:], pi)]
+
+
+def check(vk: VerifierKey, commitment, point: Sequence[int], value: int, proofs) -> bool:
+    """`MultilinearPC::check(vk, commitment, point, value, proof)` (ark-poly-commit 0.4 multilinear_pc/mod.rs; called at
+    src/sqrt_pst.rs:262; gadget form src/circuit_verifier.rs:244-312):
+
+        e(C - v g, h) == prod_i e(g_mask_random[i] - point[i] g, proof_i)
+
+    Both sides are pairing products on the GPU (one pass for the two), compared as field elements -- exactly the
+    reference's `left == right`."""
+    left, right = pairing.multi_pairing_batch(check_products(vk, commitment, point, value, proofs))
+    return bool(np.array_equal(left, right))
+
+
+def check_2_products(vk: VerifierKey, commitment_h, point: Sequence[int], value: int, proofs_g1):
+    """The two pairing products of `check_2` as operand lists [left, right] (see `check_2` for the form of the right one)."""
+    ch = np.ascontiguousarray(commitment_h, dtype=np.uint64).reshape(24)
+    pi = np.ascontiguousarray(proofs_g1, dtype=np.uint64).reshape(-1, 12)
+    m = len(point)
+    off = vk.nv - m
+    if off < 0 or len(pi) != m:
+        raise ValueError("point longer than the key, or one proof per variable missing")
+    left_q = msm_g2.msm_bigint(np.stack([ch, vk.h]), np.stack([_ONE, _neg_words([value])[0]]))
+    left = (vk.g.reshape(1, 12), left_q.reshape(1, 24))
+    if m == 0:
+        return [left, (np.zeros((0, 12), dtype=np.uint64), np.zeros((0, 24), dtype=np.uint64))]
+    folded = msm.msm_bigint(pi, _neg_words(point))
+    return [left, (np.concatenate([pi, folded.reshape(1, 12)]),
+                   np.concatenate([vk.h_mask_random[off:off + m], vk.h.reshape(1, 24)]))]
+
+
+def check_2(vk: VerifierKey, commitment_h, point: Sequence[int], value: int, proofs_g1) -> bool:
+    """The fork's `MultilinearPC::check_2(vk, &CommitmentG2, point, value, &ProofG1)` (src/mipp.rs:313; gadget form
+    src/circuit_verifier.rs:170-241), the mirror image of `check` for a G2 commitment with G1 proofs:
+
+        e(g, C_h - v h) == prod_i e(proof_i, h_mask_random[off + i] - point[i] h),   off = vk.nv - len(point)
+
+    Left: the G2 value is a two-point G2 MSM. Right: the G2 operands are combinations of the KEY's points (h and its
+    masks, order r), so bilinearity in the second argument is exact for any first argument on the curve and
+        prod_i e(proof_i, h_mask_i - z_i h) = prod_i e(proof_i, h_mask_i) * e(-sum_i z_i proof_i, h):
+    the same GT element with ONE small G1 MSM instead of m scalar multiplications in G2 (~3 ms each). `check` cannot be
+    rewritten this way: its G2 operands are the untrusted proof."""
+    left, right = pairing.multi_pairing_batch(check_2_products(vk, commitment_h, point, value, proofs_g1))
+    return bool(np.array_equal(left, right))

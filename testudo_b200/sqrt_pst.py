@@ -262,3 +262,23 @@ class Polynomial:
         proof = mipp.MippProofG1.prove(challenge, comm_list, self.chis_b, c_u, h_vec, g_levels)   # :212-213
         pst_proof = pending.wait() if pending is not None else None
         return OpenG1(u=c_u, comm_q=comm_q, mipp=proof, pst_proof=pst_proof)
+
+    @staticmethod
+    def verify(challenge: Callable[[bytes, List[np.ndarray]], int], vk: "multilinear_pc.VerifierKey", U, point: List[int],
+               v: int, pst_proof, mipp_proof: "mipp.MippProofG1", T) -> bool:
+        """src/sqrt_pst.rs:232-267: `MippProof::verify` (U = A^y for the opening vector A of T) then
+        `MultilinearPC::check(vk, U, a_rev, v, pst_proof)`. `U` is the `g_product` of the commitment `open` returned.
+        The five pairing products of the two checks -- e(final_a, final_h), both sides of check_2, both sides of check --
+        are evaluated in ONE pass of the pairing engine (tb200_multi_pairing_batch)."""
+        n = len(point)
+        odd = n % 2
+        a = list(point[: n // 2 + odd])
+        b = list(point[n // 2 + odd:])
+        parts = mipp_proof.verify_begin(vk, challenge, b, U, T)             # :248
+        if parts is None:
+            return False
+        check_u, tc, products = parts
+        products += multilinear_pc.check_products(vk, U, a[::-1], v, pst_proof)          # :254-262
+        final_t, l2, r2, l1, r1 = pairing.multi_pairing_batch(products)
+        res_mipp = check_u and bool(np.array_equal(tc, final_t)) and bool(np.array_equal(l2, r2))   # :249
+        return res_mipp and bool(np.array_equal(l1, r1))
