@@ -124,6 +124,43 @@ pub fn multi_pairing(a: &[G1Affine], b: &[G2Affine]) -> PairingOutput<Bls12_377>
     PairingOutput(unpack_gt(&t))
 }
 
+// ---- the verifier side: `MippProof::verify` (src/mipp.rs:182-333), `MultilinearPC::check` (src/sqrt_pst.rs:262) ------------
+fn pack_gt(v: &[Fq12]) -> Vec<u64> {
+    let mut w = Vec::with_capacity(72 * v.len());
+    for f in v {
+        for c6 in [&f.c0, &f.c1] { for c2 in [&c6.c0, &c6.c1, &c6.c2] { w.extend_from_slice(&c2.c0.0 .0); w.extend_from_slice(&c2.c1.0 .0); } }
+    }
+    w
+}
+/// prod_i bases[i].pow(exps[i]): the TC half of the fold / reduce over `MippTU` (src/mipp.rs:238-271) in one call
+pub fn gt_multi_pow(bases: &[Fq12], exps: &[Fr]) -> Fq12 {
+    assert_eq!(bases.len(), exps.len());
+    let (b, mut out) = (pack_gt(bases), [0u64; 72]);
+    check(unsafe { sys::tb200_gt_multi_pow(b.as_ptr(), fr_limbs(exps), bases.len(), sys::TB200_SCALARS_MONT, out.as_mut_ptr()) });
+    unpack_gt(&out)
+}
+/// `rows` independent MSMs of `per_row` (<= 8) points each in one launch: `commitment - g*value`, `g_mask[i] - g*point[i]`
+pub fn msm_g1_each(bases: &[G1Affine], scalars: &[Fr], per_row: usize) -> Vec<G1Affine> {
+    assert!(per_row > 0 && bases.len() == scalars.len() && bases.len() % per_row == 0);
+    let rows = bases.len() / per_row;
+    let (b, mut out) = (pack_g1(bases), vec![0u64; 12 * rows]);
+    check(unsafe { sys::tb200_msm_g1_each(b.as_ptr(), fr_limbs(scalars), rows, per_row, sys::TB200_SCALARS_MONT, out.as_mut_ptr()) });
+    out.chunks(12).map(unpack_g1).collect()
+}
+/// several `E::multi_pairing` in ONE pass of the pairing engine; shorter products are padded with identity pairs
+pub fn multi_pairing_batch(products: &[(&[G1Affine], &[G2Affine])]) -> Vec<PairingOutput<Bls12_377>> {
+    let width = products.iter().map(|(a, b)| a.len().min(b.len())).max().unwrap_or(0).max(1);
+    let (mut pa, mut pb) = (vec![0u64; 12 * width * products.len()], vec![0u64; 24 * width * products.len()]);
+    for (i, (a, b)) in products.iter().enumerate() {
+        let n = a.len().min(b.len());
+        pa[12 * width * i..12 * (width * i + n)].copy_from_slice(&pack_g1(&a[..n]));
+        pb[24 * width * i..24 * (width * i + n)].copy_from_slice(&pack_g2(&b[..n]));
+    }
+    let mut out = vec![0u64; 72 * products.len()];
+    check(unsafe { sys::tb200_multi_pairing_batch(pa.as_ptr(), pb.as_ptr(), products.len(), width, out.as_mut_ptr()) });
+    out.chunks(72).map(|w| PairingOutput(unpack_gt(w.try_into().unwrap()))).collect()
+}
+
 // ---- `MippProof::prove` (src/mipp.rs:31-153): vectors resident on the GPU across rounds ------------------------------------
 pub struct Mipp { a: *mut sys::tb200_mipp, h: *mut sys::tb200_mipp_g2 }
 pub struct Round { pub comm_u_l: G1Affine, pub comm_u_r: G1Affine, pub comm_t_l: Fq12, pub comm_t_r: Fq12 }

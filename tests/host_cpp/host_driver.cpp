@@ -62,7 +62,8 @@ static int run_g2(const char* fin, const char* fout) {
 }
 
 // in: n, n G1 points, n G2 points, one Fr exponent -> out: multi_pairing, pairing of the first pair, its power, and
-// multi_pairing with the G2 side one element shorter (zip semantics)
+// multi_pairing with the G2 side one element shorter (zip semantics), the length-rule flag, (t * first)^e by multi_pow,
+// and {multi_pairing, first pairing} again through multi_pairing_batch
 static int run_pairing(const char* fin, const char* fout) {
   std::ifstream in(fin, std::ios::binary);
   uint64_t n;
@@ -83,6 +84,11 @@ static int run_pairing(const char* fin, const char* fout) {
   uint64_t threw = 0;
   try { pairing::ipp_commitment(a, shorter); } catch (const std::invalid_argument&) { threw = 1; }
   wr(out, &threw, 1);
+  // the verifier's primitives: t^e * one^e in one call, and two products (all pairs / the first pair) in one pass
+  Gt mp = pairing::multi_pow({t, one}, {e[0], e[0]});
+  wr(out, &mp, 1);
+  auto batch = pairing::multi_pairing_batch({{a, b}, {{a[0]}, {b[0]}}});
+  wr(out, batch.data(), batch.size());
   return 0;
 }
 

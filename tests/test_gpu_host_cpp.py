@@ -165,3 +165,6 @@ def test_cpp_host_mirror_pairing(engine, driver, tmp_path):
     assert gts[2] == pr.f12_pow(first, e)
     assert gts[3] == pr.multi_pairing(ps[:-1], qs[:-1])
     assert int(data[288]) == 1
+    more = [pr.from_words(data[289 + 72 * i: 289 + 72 * i + 72]) for i in range(3)]
+    assert more[0] == pr.f12_pow(pr.f12_mul(gts[0], first), e)          # pairing::multi_pow (tb200_gt_multi_pow)
+    assert more[1] == gts[0] and more[2] == first                       # pairing::multi_pairing_batch

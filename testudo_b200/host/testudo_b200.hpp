@@ -9,6 +9,7 @@
 // reference computes on the CPU (chi products, q = Z*chi, challenge inversion) uses the same Montgomery code as the
 // kernels through its host path (csrc/mont.cuh).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -381,6 +382,30 @@ inline Gt pairing(const G1Affine& p, const G2Affine& q) { return multi_pairing({
 inline Gt pow(const Gt& base, const Fr& exp) {
   Gt out;
   check(tb200_gt_pow(base.w, exp.l, 1, TB200_SCALARS_MONT, out.w));
+  return out;
+}
+// prod_i bases[i].pow(exps[i]): the TC half of the verifier's fold / reduce over MippTU (src/mipp.rs:238-271) in one call
+inline Gt multi_pow(const std::vector<Gt>& bases, const std::vector<Fr>& exps) {
+  if (bases.size() != exps.size()) throw std::invalid_argument("bases and exponents differ in length");
+  Gt out;
+  check(tb200_gt_multi_pow((const uint64_t*)bases.data(), (const uint64_t*)exps.data(), bases.size(), TB200_SCALARS_MONT, out.w));
+  return out;
+}
+// several independent pairing products in ONE pass (the verifier's five: src/mipp.rs:313,320, src/sqrt_pst.rs:262);
+// shorter products are padded with identity pairs, which contribute 1 as in ark
+inline std::vector<Gt> multi_pairing_batch(const std::vector<std::pair<std::vector<G1Affine>, std::vector<G2Affine>>>& products) {
+  size_t width = 1;
+  for (const auto& p : products) width = std::max(width, std::min(p.first.size(), p.second.size()));
+  std::vector<G1Affine> a(products.size() * width, G1Affine{});
+  std::vector<G2Affine> b(products.size() * width, G2Affine{});
+  for (size_t i = 0; i < products.size(); i++) {
+    const size_t n = std::min(products[i].first.size(), products[i].second.size());
+    std::copy_n(products[i].first.begin(), n, a.begin() + i * width);
+    std::copy_n(products[i].second.begin(), n, b.begin() + i * width);
+  }
+  std::vector<Gt> out(products.size());
+  check(tb200_multi_pairing_batch((const uint64_t*)a.data(), (const uint64_t*)b.data(), products.size(), width,
+                                  (uint64_t*)out.data()));
   return out;
 }
 // the IPP commitment of Polynomial::commit: t = multi_pairing(comm_list, ck.powers_of_h[odd])  (src/sqrt_pst.rs:128-143)
