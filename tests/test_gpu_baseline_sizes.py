@@ -263,6 +263,17 @@ def test_sqrt_pst_nv26_commit_open_accepted_by_oracle_verifier(engine):
 
     assert ver.sqrt_pst_verify(vk, verifier_transcript(), U, r, v, pst_proof, proof, T) is True
     assert ver.sqrt_pst_verify(vk, verifier_transcript(), U, r, (v + 1) % R, pst_proof, proof, T) is False
+    # the engine's own `Polynomial::verify` (src/sqrt_pst.rs:232-267) on the same proof at this size: 27 GT powers, the
+    # 27-point UC fold, five pairing products of up to 14 pairs -- the same verdicts as the oracle verifier
+    from testudo_b200 import multilinear_pc
+    vk_e = multilinear_pc.VerifierKey(
+        nv=m_row, g=h.pts_to_np([vk["g"]])[0], h=np.array(o2.affine_to_words(vk["h"]), dtype=np.uint64),
+        g_mask_random=h.pts_to_np(vk["g_mask"]),
+        h_mask_random=np.array([o2.affine_to_words(p) for p in vk["h_mask"]], dtype=np.uint64))
+    same = transcript(b"nv26-roundtrip")
+    assert sqrt_pst.Polynomial.verify(same, vk_e, opened.u, r, v, opened.pst_proof, mp, t_gt) is True
+    same = transcript(b"nv26-roundtrip")
+    assert sqrt_pst.Polynomial.verify(same, vk_e, opened.u, r, (v + 1) % R, opened.pst_proof, mp, t_gt) is False
     ck.close()
 
 

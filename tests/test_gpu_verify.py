@@ -198,6 +198,13 @@ def test_engine_verifier_agrees_with_the_oracle_verifier(engine, nv):
         yield "T", copy.deepcopy(opened), v, r, gt_np(pr.f12_sqr(pr.from_words(t_gt)))
         yield "point", copy.deepcopy(opened), v, [(r[0] + 1) % o.R_ORDER] + list(r[1:]), t_gt
 
+    # over the wire: compressed `Proof` / `MippProof` / `Commitment` bytes (benches/pst.rs:64-74) -> deserialised -> verified
+    from testudo_b200 import mipp, serialize
+    wire_mipp = mipp.MippProofG1.from_bytes(opened.mipp.to_bytes())
+    wire_pst = serialize.pst_proof_from_bytes(serialize.pst_proof_bytes(opened.pst_proof))
+    _, wire_u = serialize.commitment_from_bytes(serialize.commitment_bytes(nv - nv // 2, opened.u))
+    assert sqrt_pst.Polynomial.verify(pt.PoseidonTranscript("fq").as_challenge(), vk_np(vk), wire_u, r, v, wire_pst,
+                                      wire_mipp, t_gt) is True
     b = list(r[nv // 2 + nv % 2:])
     assert opened.mipp.verify(vk_np(vk), pt.PoseidonTranscript("fq").as_challenge(), b, opened.u, t_gt) is True   # src/mipp.rs:182
     for what, d, vv, rr, tt in damaged():

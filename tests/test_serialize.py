@@ -74,3 +74,37 @@ def test_gt_fr_and_proof_structs():
     mp = ser.mipp_proof_bytes([(w, w)], [(g1w[0], g1w[1])], g1w[2], pst[0], g1w[:1])
     assert len(mp) == (8 + 2 * 576) + (8 + 2 * 48) + 48 + 96 + (8 + 48)
     assert mp[:8] == (1).to_bytes(8, "little")
+
+
+@pytest.mark.parametrize("compress", [True, False])
+def test_proof_structs_round_trip_through_bytes(compress):
+    """`CanonicalDeserialize` of `Commitment`, `Proof` and `MippProof` (what `Polynomial::verify` receives, benches/pst.rs:
+    64-90): bytes -> words -> bytes is the identity, identity points included; truncated and over-long inputs are errors."""
+    from testudo_b200.mipp import MippProofG1
+
+    rng = random.Random(77)
+    gts = [np.array(pr.to_words(tuple((rng.randrange(o.Q), rng.randrange(o.Q)) for _ in range(6))), dtype=np.uint64)
+           for _ in range(4)]
+    pts, _ = o.rand_points(7, 78)
+    pts[3] = None                                           # an identity among comms_u
+    qs, _ = o2.rand_points(4, 79)
+    g1w = h.pts_to_np(pts)
+    g2s = np.array([o2.affine_to_words(q) for q in qs], dtype=np.uint64)
+    proof = MippProofG1(comms_u=[(g1w[0], g1w[1]), (g1w[2], g1w[3])], comms_t=[(gts[0], gts[1]), (gts[2], gts[3])],
+                        final_a=g1w[4], final_h=g2s[0], pst_proof_h=g1w[5:7])
+    data = proof.to_bytes(compress)
+    back = MippProofG1.from_bytes(data, compress)
+    assert back.to_bytes(compress) == data
+    assert all(np.array_equal(a, b) for pa, pb in zip(back.comms_u, proof.comms_u) for a, b in zip(pa, pb))
+    assert all(np.array_equal(a, b) for pa, pb in zip(back.comms_t, proof.comms_t) for a, b in zip(pa, pb))
+    assert np.array_equal(back.final_a, g1w[4]) and np.array_equal(back.final_h, g2s[0])
+    assert np.array_equal(back.pst_proof_h, g1w[5:7])
+    pst = ser.pst_proof_bytes(g2s[1:], compress)
+    assert np.array_equal(ser.pst_proof_from_bytes(pst, compress), g2s[1:])
+    nv, gp = ser.commitment_from_bytes(ser.commitment_bytes(13, g1w[6], compress), compress)
+    assert nv == 13 and np.array_equal(gp, g1w[6])
+    for bad in (data[:-1], data + b"\0"):
+        with pytest.raises(ValueError):
+            MippProofG1.from_bytes(bad, compress)
+    with pytest.raises(ValueError):
+        ser.pst_proof_from_bytes(pst[:-3], compress)

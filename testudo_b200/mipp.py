@@ -57,6 +57,18 @@ class MippProofG1:
     pst_proof_h: np.ndarray = None      # [m, 12] `ProofG1.proofs`, when the CRS levels were passed
     rs: List[int] = field(default_factory=list)
 
+    def to_bytes(self, compress: bool = True) -> bytes:
+        """`MippProof::serialize_with_mode` (benches/pst.rs:70-72)"""
+        from . import serialize
+        return serialize.mipp_proof_bytes(self.comms_t, self.comms_u, self.final_a, self.final_h, self.pst_proof_h, compress)
+
+    @classmethod
+    def from_bytes(cls, data: bytes, compress: bool = True) -> "MippProofG1":
+        """`MippProof::deserialize_with_mode`: the proof as a verifier receives it (prover-side scratch fields stay empty)"""
+        from . import serialize
+        t, u, fa, fh, ph = serialize.mipp_proof_from_bytes(data, compress)
+        return cls(comms_u=u, comms_t=t, final_a=fa, final_h=fh, pst_proof_h=ph)
+
     @classmethod
     def prove(cls, challenge: Callable[[bytes, List[np.ndarray]], int], a, y_mont, U, h=None,
               powers_of_g_levels=None) -> "MippProofG1":

@@ -200,6 +200,70 @@ def mipp_proof_bytes(comms_t, comms_u, final_a, final_h, pst_proof_h, compress: 
     return out
 
 
+# ---- `CanonicalDeserialize` of the same structs: what a verifier receives ------------------------------------------------
+def _take(data: bytes, pos: int, n: int) -> Tuple[bytes, int]:
+    if pos + n > len(data):
+        raise ValueError("truncated input")
+    return data[pos:pos + n], pos + n
+
+
+def _take_len(data: bytes, pos: int) -> Tuple[int, int]:
+    raw, pos = _take(data, pos, 8)
+    return int.from_bytes(raw, "little"), pos
+
+
+def commitment_from_bytes(data: bytes, compress: bool = True) -> Tuple[int, np.ndarray]:
+    """-> (nv, g_product)"""
+    nv, pos = _take_len(data, 0)
+    raw, pos = _take(data, pos, 48 if compress else 96)
+    if pos != len(data):
+        raise ValueError("trailing bytes")
+    return nv, g1_from_bytes(raw, compress)
+
+
+def pst_proof_from_bytes(data: bytes, compress: bool = True) -> np.ndarray:
+    """`Proof<E>` -> [nv, 24]"""
+    n, pos = _take_len(data, 0)
+    size = 96 if compress else 192
+    out = np.zeros((n, 24), dtype=np.uint64)
+    for i in range(n):
+        raw, pos = _take(data, pos, size)
+        out[i] = g2_from_bytes(raw, compress)
+    if pos != len(data):
+        raise ValueError("trailing bytes")
+    return out
+
+
+def mipp_proof_from_bytes(data: bytes, compress: bool = True):
+    """`MippProof<E>` (src/mipp.rs:21-28) -> (comms_t, comms_u, final_a, final_h, pst_proof_h) as `mipp_proof_bytes` takes
+    them: lists of (left, right) pairs, [12], [24], [m, 12]."""
+    g1 = 48 if compress else 96
+    n, pos = _take_len(data, 0)
+    comms_t = []
+    for _ in range(n):
+        l, pos = _take(data, pos, 576)
+        r, pos = _take(data, pos, 576)
+        comms_t.append((gt_from_bytes(l), gt_from_bytes(r)))
+    n, pos = _take_len(data, pos)
+    comms_u = []
+    for _ in range(n):
+        l, pos = _take(data, pos, g1)
+        r, pos = _take(data, pos, g1)
+        comms_u.append((g1_from_bytes(l, compress), g1_from_bytes(r, compress)))
+    raw, pos = _take(data, pos, g1)
+    final_a = g1_from_bytes(raw, compress)
+    raw, pos = _take(data, pos, 2 * g1)
+    final_h = g2_from_bytes(raw, compress)
+    n, pos = _take_len(data, pos)
+    pst_proof_h = np.zeros((n, 12), dtype=np.uint64)
+    for i in range(n):
+        raw, pos = _take(data, pos, g1)
+        pst_proof_h[i] = g1_from_bytes(raw, compress)
+    if pos != len(data):
+        raise ValueError("trailing bytes")
+    return comms_t, comms_u, final_a, final_h, pst_proof_h
+
+
 def proof_size(pst_proof, mipp) -> int:
     """`br.proof_size = p1.len() + p2.len()` of benches/pst.rs:64-74 (both compressed); `mipp` is a MippProofG1."""
     p1 = pst_proof_bytes(pst_proof, True)
