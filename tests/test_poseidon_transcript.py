@@ -65,6 +65,24 @@ def test_cpp_sponge_equals_python_restatement(field):
             assert t.challenge_scalar(b"c") == want, step
 
 
+@pytest.mark.parametrize("field", ["fr", "fq"])
+def test_cpp_sponge_on_extreme_field_elements(field):
+    """The host multiplier (interleaved CIOS on two carry words, three-term dot product with one reduction) on operands at
+    the edges: p - 1, p - 2, 2^k - 1, all-ones limbs -- long absorb / squeeze chains against the Python restatement."""
+    import random
+    rng = random.Random(5 if field == "fr" else 6)
+    t = pt.PoseidonTranscript(field)
+    s = _oracle_sponge(field)
+    p = o.R_ORDER if field == "fr" else curve.Q
+    edge = [p - 1, p - 2, 1, 0, (1 << (p.bit_length() - 1)) - 1, (1 << 64) - 1, ((1 << 128) - 1) << 64, p >> 1, (p >> 1) + 1]
+    edge += [(rng.randrange(p) | ((1 << 64) - 1)) % p for _ in range(8)]
+    for rep in range(8):
+        vals = edge[rep:] + edge[:rep]
+        t.append_scalar_vector(b"", vals)
+        s.absorb_elements(vals)
+        assert t.squeeze_native(3) == s.squeeze_native(3), rep
+
+
 def test_transcript_encodings_and_flow():
     """The appends of one MIPP round (src/mipp.rs:56,97-101): uncompressed G1 (96 B), GT (576 B), then a challenge."""
     from oracle import bls12_377_g2 as o2

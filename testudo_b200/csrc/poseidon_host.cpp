@@ -33,6 +33,7 @@ typedef unsigned __int128 u128;
 template <int N>
 struct Field {
   uint64_t p[N], r2[N], one[N], inv;  // inv = -p^-1 mod 2^64
+  bool nocarry = false;               // top bit of p clear: the interleaved CIOS of mul() applies
   static bool geq(const uint64_t* a, const uint64_t* b) {
     for (int i = N - 1; i >= 0; i--)
       if (a[i] != b[i]) return a[i] > b[i];
@@ -56,7 +57,50 @@ struct Field {
     }
     if (carry || geq(r, p)) sub_n(r, r, p);
   }
-  void mul(uint64_t* r, const uint64_t* a, const uint64_t* b) const {  // CIOS
+  // lo(a b + c + d), hi in `hi`: never overflows 128 bits
+  static inline uint64_t mac(uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t& hi) {
+    const u128 s = (u128)a * b + c + d;
+    hi = (uint64_t)(s >> 64);
+    return (uint64_t)s;
+  }
+  // t (N limbs, < 2p) -> r = t mod p without a branch on the data
+  void reduce_once(uint64_t* r, const uint64_t* t) const {
+    uint64_t s[N], borrow = 0;
+#pragma GCC unroll 8
+    for (int j = 0; j < N; j++) {
+      const u128 d = (u128)t[j] - p[j] - borrow;
+      s[j] = (uint64_t)d;
+      borrow = (uint64_t)(d >> 64) & 1;
+    }
+#pragma GCC unroll 8
+    for (int j = 0; j < N; j++) r[j] = borrow ? t[j] : s[j];
+  }
+  // CIOS with the multiplication and the reduction row interleaved on two carry words (A, C). The top bit of the
+  // modulus' top limb is clear for both fields (Fq: 377 of 384 bits, Fr: 253 of 256), so the running value stays inside
+  // N limbs (t[N-1] = A + C cannot overflow) -- checked in init(), which falls back to mul_generic otherwise. Fully
+  // unrolled: ~2x the speed of the generic loop (the sponge spends all its time here: ~630 products per permutation).
+  void mul(uint64_t* r, const uint64_t* x, const uint64_t* y) const {
+    if (!nocarry) return mul_generic(r, x, y);
+    uint64_t t[N];
+#pragma GCC unroll 8
+    for (int j = 0; j < N; j++) t[j] = 0;
+#pragma GCC unroll 8
+    for (int i = 0; i < N; i++) {
+      uint64_t A, C;
+      const uint64_t yi = y[i];
+      const uint64_t t0 = mac(x[0], yi, t[0], 0, A);
+      const uint64_t m = t0 * inv;
+      (void)mac(m, p[0], t0, 0, C);
+#pragma GCC unroll 8
+      for (int j = 1; j < N; j++) {
+        const uint64_t tj = mac(x[j], yi, t[j], A, A);
+        t[j - 1] = mac(m, p[j], tj, C, C);
+      }
+      t[N - 1] = C + A;
+    }
+    reduce_once(r, t);
+  }
+  void mul_generic(uint64_t* r, const uint64_t* a, const uint64_t* b) const {  // CIOS, any odd modulus
     uint64_t t[N + 2] = {0};
     for (int i = 0; i < N; i++) {
       uint64_t carry = 0;
@@ -118,6 +162,38 @@ struct Field {
     while (t[N] || geq(t, p)) t[N] -= sub_n(t, t, p);   // the total is below (K + 1) p
     memcpy(r, t, N * 8);
   }
+  // the same for exactly three terms (the MDS row of the reference's width-3 sponge), fully unrolled
+  void dot3(uint64_t* r, const uint64_t* a0, const uint64_t* b0, const uint64_t* a1, const uint64_t* b1, const uint64_t* a2,
+            const uint64_t* b2) const {
+    uint64_t t[N + 2];
+#pragma GCC unroll 8
+    for (int j = 0; j < N + 2; j++) t[j] = 0;
+#pragma GCC unroll 8
+    for (int i = 0; i < N; i++) {
+      uint64_t c0 = 0, c1 = 0, c2 = 0;
+      const uint64_t y0 = b0[i], y1 = b1[i], y2 = b2[i];
+#pragma GCC unroll 8
+      for (int j = 0; j < N; j++) {
+        uint64_t v = mac(a0[j], y0, t[j], c0, c0);
+        v = mac(a1[j], y1, v, c1, c1);
+        t[j] = mac(a2[j], y2, v, c2, c2);
+      }
+      u128 top = (u128)t[N] + c0 + c1 + c2;
+      t[N] = (uint64_t)top;
+      t[N + 1] += (uint64_t)(top >> 64);
+      const uint64_t m = t[0] * inv;
+      uint64_t C;
+      (void)mac(m, p[0], t[0], 0, C);
+#pragma GCC unroll 8
+      for (int j = 1; j < N; j++) t[j - 1] = mac(m, p[j], t[j], C, C);
+      top = (u128)t[N] + C;
+      t[N - 1] = (uint64_t)top;
+      t[N] = t[N + 1] + (uint64_t)(top >> 64);
+      t[N + 1] = 0;
+    }
+    while (t[N] || geq(t, p)) t[N] -= sub_n(t, t, p);   // the total is below 4 p
+    memcpy(r, t, N * 8);
+  }
   void to_mont(uint64_t* r, const uint64_t* a) const { mul(r, a, r2); }
   void from_mont(uint64_t* r, const uint64_t* a) const {
     uint64_t o[N] = {1};
@@ -125,6 +201,7 @@ struct Field {
   }
   void init(const uint64_t* modulus) {
     memcpy(p, modulus, N * 8);
+    nocarry = (p[N - 1] >> 63) == 0;
     uint64_t x = 1;  // Newton: x = p^-1 mod 2^64
     for (int i = 0; i < 6; i++) x *= 2 - p[0] * x;
     inv = (uint64_t)(0 - x);
@@ -201,7 +278,8 @@ struct Sponge : SpongeBase {
       for (unsigned j = 0; j < width; j++) sp[j] = st(j);
       for (unsigned i = 0; i < width; i++) {               // row i of the MDS matrix: one reduction for the whole row
         for (unsigned j = 0; j < width; j++) mp[j] = mds.data() + (size_t)N * (i * width + j);
-        F.dot(nxt.data() + (size_t)N * i, sp, mp, width);
+        if (width == 3) F.dot3(nxt.data() + (size_t)N * i, sp[0], mp[0], sp[1], mp[1], sp[2], mp[2]);
+        else F.dot(nxt.data() + (size_t)N * i, sp, mp, width);
       }
       state.swap(nxt);
     }

@@ -155,7 +155,7 @@ class MippProofG1:
                      point: List[int], U, T):
         """Everything of `MippProof::verify` (src/mipp.rs:182-333) up to the pairings: the transcript replay, the TC fold
         `T * prod comm_t_l^(c_inv) comm_t_r^(c)` (one tb200_gt_multi_pow), the UC fold `U + sum c_inv comm_u_l + c
-        comm_u_r` (one MSM), final_u, and the OPERANDS of the three pairing products still to evaluate -- so that a caller
+        comm_u_r` against final_u (one MSM), and the OPERANDS of the three pairing products still to evaluate -- so that a caller
         (`Polynomial.verify`) can run them in one pass together with its own. Returns None when a challenge has no
         inverse (the reference panics), else (check_u, tc, [final_t, check_2 left, check_2 right])."""
         from . import pairing
@@ -178,13 +178,15 @@ class MippProofG1:
         u_bases = np.stack([U] + [u for ul, ur in self.comms_u for u in (ul, ur)])
         exps = curve.scalars_to_words([1] + [e for c, ci in zip(xs, xs_inv) for e in (ci, c)])
         tc = pairing.gt_multi_pow(t_bases, exps)
-        uc = msm.msm_bigint(u_bases, exps)
         rs = [challenge(b"random_point", []) % fr.R for _ in range(m)]           # :281-285
         v = 1
         for i in range(m):
             v = v * (1 + rs[i] * xs_inv[m - i - 1] - rs[i]) % fr.R              # :294-297
-        final_u = msm.msm_bigint(np.asarray(self.final_a).reshape(1, 12), curve.scalars_to_words([final_y]))   # :311
-        check_u = bool(np.array_equal(uc, final_u))                              # :317
+        # uc == final_u (:317) with final_u = final_a * final_y (:319), as ONE MSM: uc - final_y final_a is the identity
+        # (the group law is exact on any curve point, so this is the same predicate for the latency of one call less)
+        u_all = np.concatenate([u_bases, np.asarray(self.final_a, dtype=np.uint64).reshape(1, 12)])
+        e_all = np.concatenate([exps, curve.scalars_to_words([(-final_y) % fr.R])])
+        check_u = not msm.msm_bigint(u_all, e_all).any()
         products = [(np.asarray(self.final_a).reshape(1, 12), np.asarray(self.final_h).reshape(1, 24))]   # final_t, :312
         products += multilinear_pc.check_2_products(vk, self.final_h, rs, v, self.pst_proof_h)            # check_h, :308
         return check_u, tc, products
