@@ -225,6 +225,14 @@ int tb200_fr_matvec_dev(const void* d_Z, size_t rows, size_t cols, const void* d
  * Accepts any curve point; scalars canonical, or Montgomery with TB200_SCALARS_MONT; (0, 0) in / out = identity. */
 int tb200_msm_g1_each(const uint64_t* bases_xy, const uint64_t* scalars, size_t rows, size_t per_row, unsigned flags,
                       uint64_t* out_xy);
+/* A single G1 MSM IN FLIGHT next to other calls: _begin uploads and enqueues on a side pipeline of the library (own stream,
+ * own workspace) and returns, _end waits and writes the affine point. The reference runs independent MSMs side by side
+ * (`try_par!` / `rayon::join`, src/macros.rs:1-17) and computes `MultilinearPC::commit(ck, &q)` only to feed a debug_assert
+ * (src/sqrt_pst.rs:205-206) -- nothing on the prover's critical path waits for it. bases / scalars as for tb200_msm_g1;
+ * the host buffers must stay valid until _end returns; _end(job, NULL) discards the result. n < 2^26. */
+typedef struct tb200_msm_job* tb200_msm_job_t;
+int tb200_msm_g1_begin(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, unsigned flags, tb200_msm_job_t* out);
+int tb200_msm_g1_end(tb200_msm_job_t job, uint64_t out_xy[12]);
 /* out = sum of n affine points (combining per-GPU partial results after the NCCL all-gather) */
 int tb200_g1_sum(const uint64_t* pts_xy, size_t n, uint64_t out_xy[12]);
 int tb200_g1_sum_dev(const void* d_pts_xy, size_t n, void* d_out_xy, void* stream);

@@ -204,3 +204,35 @@ def test_small_path_exceptional_cases(engine, oracle_c):
     for pts, sc in cases:
         got = msm.msm_bigint(h.pts_to_np(pts), h.scalars_to_np(sc))
         assert h.pt_from_np(got) == o.msm_naive(pts, sc), (pts, sc)
+
+
+def test_msm_in_flight_next_to_other_calls(engine, oracle_c):
+    """tb200_msm_g1_begin / _end: MSMs of 0, 5, 1000 (Straus path) and 2^14 points (sort pipeline on a side workspace) started,
+    OTHER library calls made while they are in flight (an MSM through the main pipeline, a second job), then collected:
+    every result equals the C oracle's and the blocking entry point's; a discarded job (_end(job, NULL)) leaves the library
+    usable."""
+    import ctypes
+
+    jobs = []
+    for n in (0, 5, 1000, 1 << 14):
+        bases = oracle_c.gen_points(h.pts_to_np([o.mul(4000 + n, o.G)])[0], h.pts_to_np([o.mul(91, o.G)])[0], max(n, 1))[:n]
+        sc = h.scalars_to_np(h.np_scalars_to_ints(h.np_rand_scalars(max(n, 1), 1700 + n))[:n], mont=True).reshape(n, 4)
+        jobs.append((n, bases, sc, msm.msm_unchecked_begin(bases, sc)))
+    n2 = 1 << 15
+    other_b = oracle_c.gen_points(h.pts_to_np([o.mul(5, o.G)])[0], h.pts_to_np([o.mul(7, o.G)])[0], n2)
+    other_s = h.np_rand_scalars(n2, 1800)
+    assert np.array_equal(msm.msm_bigint(other_b, other_s), oracle_c.msm_g1(other_b, other_s))   # while the jobs run
+    for n, bases, sc, job in jobs:
+        got = job.wait()
+        want = msm.msm_unchecked(bases, sc) if n else np.zeros(12, dtype=np.uint64)
+        assert np.array_equal(got, want), n
+        if n:
+            canon = h.scalars_to_np(h.scalars_from_np(sc, mont=True))
+            assert np.array_equal(got, oracle_c.msm_g1(bases, canon)), n
+    handle = ctypes.c_void_p()
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    assert engine.tb200_msm_g1_begin(P(other_b), P(other_s), n2, 0, ctypes.byref(handle)) == 0
+    assert engine.tb200_msm_g1_end(handle, None) == 0                                              # discarded
+    assert engine.tb200_msm_g1_begin(None, None, 3, 0, ctypes.byref(handle)) == -1
+    assert engine.tb200_msm_g1_end(None, None) == -1
+    assert np.array_equal(msm.msm_bigint(other_b, other_s), oracle_c.msm_g1(other_b, other_s))

@@ -809,6 +809,94 @@ int tb200_pst_open_g2(const uint64_t* evals, size_t nv, const uint64_t* point, c
   return pst_open_locked(evals, nv, point, level_bases, flags, proofs, true);
 }
 
+// ---- a single MSM in flight next to other calls ------------------------------------------------------------------------
+// The reference runs independent MSMs side by side (`try_par!` / `rayon::join`, src/macros.rs:1-17, src/mipp.rs:77-85) and
+// computes cross-checks whose result nothing waits for (`MultilinearPC::commit(ck, &q)` for the debug_assert of
+// src/sqrt_pst.rs:205-206). _begin uploads on the job's own stream and enqueues the MSM on a side pipeline (own stream,
+// own workspace); _end waits and downloads the point. The host buffers must stay valid until _end returns.
+}  // extern "C"
+struct tb200_msm_job {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev = nullptr;
+  uint4* d_b = nullptr;
+  uint32_t* d_s = nullptr;
+  uint4* d_out = nullptr;
+};
+namespace {
+void msm_job_release(tb200_msm_job* j) {
+  if (!j) return;
+  if (j->st) {
+    for (void* p : {(void*)j->d_b, (void*)j->d_s, (void*)j->d_out})
+      if (p) cudaFreeAsync(p, j->st);
+    cudaStreamDestroy(j->st);
+  }
+  if (j->ev) cudaEventDestroy(j->ev);
+  delete j;
+}
+}  // namespace
+extern "C" {
+int tb200_msm_g1_begin(const uint64_t* bases_xy, const uint64_t* scalars, size_t n, unsigned flags, tb200_msm_job_t* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (!out || (n && (!bases_xy || !scalars))) return fail(TB200_E_ARG, "null pointer");
+  if (n >= (size_t(1) << 26)) return fail(TB200_E_LIMIT, "tb200_msm_g1_begin is meant for MSMs that run NEXT TO other work (n < 2^26)");
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  constexpr int sl = Ctx::SIDE - 1;   // the side pipeline a concurrent PST opening uses least
+  if (!g.side_stream[sl]) {
+    CU(cudaStreamCreateWithFlags(&g.side_stream[sl], cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&g.side_done[sl], cudaEventDisableTiming));
+  }
+  tb200_msm_job* j = new tb200_msm_job();
+  auto bail = [&](int rc) {
+    if (j->st) cudaStreamSynchronize(j->st);
+    cudaStreamSynchronize(g.side_stream[sl]);
+    msm_job_release(j);
+    return rc;
+  };
+#define CUJ(expr)                                                                                         \
+  do {                                                                                                    \
+    cudaError_t e__ = (expr);                                                                             \
+    if (e__ != cudaSuccess) return bail(fail((int)e__, "%s failed: %s", #expr, cudaGetErrorString(e__))); \
+  } while (0)
+  CUJ(cudaStreamCreateWithFlags(&j->st, cudaStreamNonBlocking));
+  CUJ(cudaEventCreateWithFlags(&j->ev, cudaEventDisableTiming));
+  CUJ(cudaMallocAsync((void**)&j->d_b, std::max<size_t>(n, 1) * 96, j->st));
+  CUJ(cudaMallocAsync((void**)&j->d_s, std::max<size_t>(n, 1) * 32, j->st));
+  CUJ(cudaMallocAsync((void**)&j->d_out, 96, j->st));
+  if (n) {
+    CUJ(cudaMemcpyAsync(j->d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, j->st));
+    CUJ(cudaMemcpyAsync(j->d_s, scalars, n * 32, cudaMemcpyHostToDevice, j->st));
+  }
+  CUJ(cudaEventRecord(j->ev, j->st));
+  CUJ(cudaStreamWaitEvent(g.side_stream[sl], j->ev, 0));
+  const bool prof = g.profiling;
+  g.profiling = false;
+  int rc = msm_dev(g, j->d_b, j->d_s, n, flags, j->d_out, g.side_stream[sl], nullptr, &g.side_arena[sl], false, false);
+  g.profiling = prof;
+  g.marks.clear();
+  if (rc) return bail(rc);
+  CUJ(cudaEventRecord(g.side_done[sl], g.side_stream[sl]));
+  CUJ(cudaStreamWaitEvent(j->st, g.side_done[sl], 0));
+#undef CUJ
+  *out = j;
+  return 0;
+}
+int tb200_msm_g1_end(tb200_msm_job_t job, uint64_t out_xy[12]) {
+  if (!job) return fail(TB200_E_ARG, "null handle");
+  if (need_ready()) return TB200_E_STATE;
+  {   // no library lock while waiting: other calls run meanwhile
+    std::lock_guard<std::mutex> lk(g_mu);
+    CU(cudaSetDevice(primary().device));
+  }
+  cudaError_t e = cudaSuccess;
+  if (out_xy) e = cudaMemcpyAsync(out_xy, job->d_out, 96, cudaMemcpyDeviceToHost, job->st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(job->st);
+  const int rc = e == cudaSuccess ? 0 : fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
+  msm_job_release(job);
+  return rc;
+}
+
 // ---- MIPP (G1 side) ---------------------------------------------------------------------------------------------------
 int tb200_mipp_g1_begin(const uint64_t* a_xy, const uint64_t* y, size_t n, unsigned flags, tb200_mipp_t* out) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -71,10 +71,12 @@ class MippProofG1:
 
     @classmethod
     def prove(cls, challenge: Callable[[bytes, List[np.ndarray]], int], a, y_mont, U, h=None,
-              powers_of_g_levels=None) -> "MippProofG1":
+              powers_of_g_levels=None, on_round: Callable[[int], None] = None) -> "MippProofG1":
         """src/mipp.rs:31-153. `challenge(label, values)` returns the squeezed scalar as an integer mod r after the
         reference would have appended `values` (comm_u_l, comm_u_r, and -- when the G2 key is passed -- comm_t_l, comm_t_r).
-        `h` = `ck.powers_of_h[odd]` ([n, 24]); `powers_of_g_levels[i]` = `ck.powers_of_g[off + i]` for `open_g1`."""
+        `h` = `ck.powers_of_h[odd]` ([n, 24]); `powers_of_g_levels[i]` = `ck.powers_of_g[off + i]` for `open_g1`.
+        `on_round(remaining_length)` is called after every round's folds are enqueued (and once before the first round):
+        the caller's hook for starting independent work at a chosen point of the loop."""
         lib = _lib.engine()
         a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 12)
         y = np.ascontiguousarray(y_mont, dtype=np.uint64).reshape(-1, 4)
@@ -92,6 +94,8 @@ class MippProofG1:
         h_key, h = h, ctypes.c_void_p()
         _lib.check(lib.tb200_mipp_g1_begin(_ptr(a), _ptr(y), len(a), _lib.SCALARS_MONT, ctypes.byref(h)))
         try:
+            if on_round is not None:
+                on_round(len(a))
             while lib.tb200_mipp_g1_len(h) > 1:                          # :58
                 ul = np.zeros(12, dtype=np.uint64)
                 ur = np.zeros(12, dtype=np.uint64)
@@ -114,6 +118,8 @@ class MippProofG1:
                 out.comms_u.append((ul, ur))                             # :117
                 out.xs.append(c)
                 out.xs_inv.append(c_inv)
+                if on_round is not None:
+                    on_round(int(lib.tb200_mipp_g1_len(h)))
             fa = np.zeros((1, 12), dtype=np.uint64)
             fy = np.zeros((1, 4), dtype=np.uint64)
             _lib.check(lib.tb200_mipp_g1_read(h, _ptr(fa), _ptr(fy)))

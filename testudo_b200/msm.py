@@ -77,3 +77,36 @@ def msm_each(bases, bigints, per_row: int) -> np.ndarray:
     out = np.zeros((rows, 12), dtype=np.uint64)
     _lib.check(_lib.engine().tb200_msm_g1_each(_ptr(b), _ptr(s), rows, per_row, 0, _ptr(out)))
     return out
+
+
+class PendingMsm:
+    """An MSM in flight (tb200_msm_g1_begin): `wait()` returns the affine point. Keeps its host inputs alive."""
+
+    def __init__(self, handle, keep):
+        self._h, self._keep = handle, keep
+
+    def wait(self) -> np.ndarray:
+        out = np.zeros(12, dtype=np.uint64)
+        if self._h is not None:
+            h, self._h = self._h, None
+            _lib.check(_lib.engine().tb200_msm_g1_end(h, _ptr(out)))
+            self._keep = None
+        return out
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                _lib.engine().tb200_msm_g1_end(self._h, None)
+        except Exception:
+            pass
+
+
+def msm_unchecked_begin(bases, scalars) -> PendingMsm:
+    """`msm_unchecked` started without waiting: it runs on a side pipeline of the library next to whatever the caller
+    does until `.wait()` (the reference's `try_par!` / `rayon::join` of independent MSMs, src/macros.rs:1-17)."""
+    b = _u64(bases, 12)
+    s = _u64(scalars, 4)
+    n = min(len(b), len(s))
+    handle = ctypes.c_void_p()
+    _lib.check(_lib.engine().tb200_msm_g1_begin(_ptr(b), _ptr(s), n, _lib.SCALARS_MONT, ctypes.byref(handle)))
+    return PendingMsm(handle, (b, s))

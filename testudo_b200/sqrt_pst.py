@@ -28,6 +28,8 @@ import numpy as np
 
 from . import _lib, curve, fr, mipp, msm, multilinear_pc, pairing
 
+PST_START_LEN = 4096     # `open`: the G2 opening of q starts when the MIPP vectors are this short (see `open`)
+
 
 def _ptr(a: np.ndarray):
     return a.ctypes.data_as(ctypes.c_void_p)
@@ -251,16 +253,25 @@ class Polynomial:
         h_vec = ck.powers_of_h[self.odd] if ck.powers_of_h is not None else None     # src/sqrt_pst.rs:207
         g_levels = ck.powers_of_g[self.odd:] if ck.powers_of_g is not None else None  # variable CRS: off = ck.nv - m
         # The reference computes the PST proof of q AFTER the MIPP proof (:218-225), but it depends only on q and the
-        # point, not on the transcript: it is started here and runs on streams of its own next to the MIPP rounds.
-        pending = None
-        if ck.powers_of_h is not None:
-            a_rev = list(point[: self.m + self.odd])[::-1]                        # :218-222
-            pending = multilinear_pc.open_begin(ck.powers_of_h, self.q, curve.scalars_to_words(a_rev, mont=True))  # :225
-        # M3 only feeds the reference's debug_assert (:205-206): it runs while the G2 opening above keeps the GPU busy
-        comm_q = pc_commit(ck, self.q)                                 # M3, src/sqrt_pst.rs:205
+        # point, not on the transcript: it runs on streams of its own NEXT TO the MIPP rounds. It is started once the
+        # folded vectors are down to PST_START_LEN elements: the first round is throughput-bound (8192 Miller loops at
+        # 2^26) and an opening started before it only shares its SMs, the later rounds are latency-bound and leave the GPU
+        # idle (scripts/ab_open.py at 2^26: 73.6 ms started before the loop, 72.2 ms after the first round).
+        pending_box = []
+
+        def start_pst(remaining: int) -> None:
+            if not pending_box and ck.powers_of_h is not None and remaining <= PST_START_LEN:
+                a_rev = list(point[: self.m + self.odd])[::-1]                        # :218-222
+                pending_box.append(multilinear_pc.open_begin(ck.powers_of_h, self.q,
+                                                             curve.scalars_to_words(a_rev, mont=True)))  # :225
+        # M3 only feeds the reference's debug_assert (:205-206) -- nothing on the prover's path waits for it: it is STARTED
+        # here on a side pipeline (tb200_msm_g1_begin) and compared once the MIPP proof is done
+        pending_q = msm.msm_unchecked_begin(ck.powers_of_g0, self.q)   # M3, src/sqrt_pst.rs:205
+        proof = mipp.MippProofG1.prove(challenge, comm_list, self.chis_b, c_u, h_vec, g_levels, on_round=start_pst)   # :212-213
+        start_pst(0)                                                   # vectors of length 1: no round ran
+        comm_q = pending_q.wait()
         assert np.array_equal(c_u, comm_q), "debug_assert!(c_u == comm.g_product) (src/sqrt_pst.rs:206)"
-        proof = mipp.MippProofG1.prove(challenge, comm_list, self.chis_b, c_u, h_vec, g_levels)   # :212-213
-        pst_proof = pending.wait() if pending is not None else None
+        pst_proof = pending_box[0].wait() if pending_box else None
         return OpenG1(u=c_u, comm_q=comm_q, mipp=proof, pst_proof=pst_proof)
 
     @staticmethod
