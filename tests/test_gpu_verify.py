@@ -248,3 +248,33 @@ def test_check_and_check_2_values_equal_the_oracle_s(engine):
     got_right = pairing.multi_pairing(np.concatenate([h.pts_to_np(p1), folded.reshape(1, 12)]),
                                       np.concatenate([vkn.h_mask_random[off:], vkn.h.reshape(1, 24)]))
     assert pr.from_words(got_right) == want_right
+
+
+def test_batched_pairing_and_power_paths_at_larger_sizes(engine):
+    """The branches the verifier's own sizes do not reach: batches above 512 pairs (two pairs per warp, even segment
+    length; the one-pair-per-warp fallback for an odd length) against the single-product entry point (itself pinned to the
+    oracle in tests/test_gpu_pairing.py), and more than 8192 GT powers (thread-per-element kernel) against the same
+    product taken in two halves on the cooperative kernel."""
+    ps, _ = o.rand_points(8, 991)
+    qs = [o2.mul(k, o2.G2) for k in o.rand_scalars(8, 992)]
+    P8, Q8 = h.pts_to_np(ps), g2_np(qs)
+    for each in (300, 201):
+        reps = (each * 3 + 7) // 8
+        A = np.tile(P8, (reps, 1))[: each * 3].copy()
+        B = np.tile(Q8, (reps, 1))[: each * 3].copy()
+        A[5] = 0                                            # an identity inside the first product
+        got = pairing.multi_pairing_batch([(A[i * each:(i + 1) * each], B[i * each:(i + 1) * each]) for i in range(3)])
+        for i in range(3):
+            assert np.array_equal(got[i], pairing.multi_pairing(A[i * each:(i + 1) * each], B[i * each:(i + 1) * each])), (each, i)
+    n = 8200
+    gts = np.stack([pairing.pairing(P8[i], Q8[i]) for i in range(4)])
+    bases = np.tile(gts, (n // 4, 1))
+    exps = h.scalars_to_np([(7 * i + 3) % 65521 for i in range(n)])
+    whole = pairing.gt_multi_pow(bases, exps)
+    lo = pairing.gt_multi_pow(bases[:4100], exps[:4100])
+    hi = pairing.gt_multi_pow(bases[4100:], exps[4100:])
+    both = pairing.gt_multi_pow(np.stack([lo, hi]), h.scalars_to_np([1, 1]))
+    assert np.array_equal(whole, both)
+    k = sum((7 * i + 3) % 65521 for i in range(0, n, 4))   # the exponents that meet base 0: one closed form as a spot check
+    only0 = pairing.gt_multi_pow(bases[::4], exps[::4])
+    assert np.array_equal(only0, pairing.gt_pow(gts[:1], h.scalars_to_np([k % o.R_ORDER]))[0])
