@@ -225,6 +225,12 @@ int tb200_fr_matvec_dev(const void* d_Z, size_t rows, size_t cols, const void* d
  * Accepts any curve point; scalars canonical, or Montgomery with TB200_SCALARS_MONT; (0, 0) in / out = identity. */
 int tb200_msm_g1_each(const uint64_t* bases_xy, const uint64_t* scalars, size_t rows, size_t per_row, unsigned flags,
                       uint64_t* out_xy);
+/* The same for rows of DIFFERENT lengths (0 .. 1024 points each): row i takes the next row_len[i] entries of bases /
+ * scalars. `MippProof::verify` + `MultilinearPC::check` need a (2m + 2)-point fold (src/mipp.rs:238-277,317-319), an
+ * m-point fold (check_2, :313) and nv + 1 two-point rows (src/sqrt_pst.rs:262): three kinds of independent MSMs, one
+ * launch. An empty row yields the identity. */
+int tb200_msm_g1_rows(const uint64_t* bases_xy, const uint64_t* scalars, const size_t* row_len, size_t rows, unsigned flags,
+                      uint64_t* out_xy);
 /* A single G1 MSM IN FLIGHT next to other calls: _begin uploads and enqueues on a side pipeline of the library (own stream,
  * own workspace) and returns, _end waits and writes the affine point. The reference runs independent MSMs side by side
  * (`try_par!` / `rayon::join`, src/macros.rs:1-17) and computes `MultilinearPC::commit(ck, &q)` only to feed a debug_assert

@@ -236,3 +236,34 @@ def test_msm_in_flight_next_to_other_calls(engine, oracle_c):
     assert engine.tb200_msm_g1_begin(None, None, 3, 0, ctypes.byref(handle)) == -1
     assert engine.tb200_msm_g1_end(None, None) == -1
     assert np.array_equal(msm.msm_bigint(other_b, other_s), oracle_c.msm_g1(other_b, other_s))
+
+
+def test_ragged_row_batch_vs_c_oracle(engine, oracle_c):
+    """tb200_msm_g1_rows: independent MSMs of 0, 1, 2, 8, 9, 27, 13, 64, 1000 and 1024 points in ONE launch (rows above 8
+    points span several CTAs and are summed by the last one to finish, one ticket per row) -- every row equals the C oracle's
+    MSM of its slice; an empty row is the identity; a row of 1025 points is refused."""
+    import ctypes
+
+    lens = [0, 1, 2, 8, 9, 27, 13, 64, 1000, 0, 1024, 3]
+    n = sum(lens)
+    bases = oracle_c.gen_points(h.pts_to_np([o.mul(31337, o.G)])[0], h.pts_to_np([o.mul(1009, o.G)])[0], n)
+    sc = h.np_rand_scalars(n, 2222)
+    sc[5] = 0                                               # a zero scalar
+    bases[7] = 0                                            # an identity base
+    got = msm.msm_rows(bases, sc, lens)
+    assert got.shape == (len(lens), 12)
+    pos = 0
+    for i, ln in enumerate(lens):
+        want = oracle_c.msm_g1(bases[pos:pos + ln], sc[pos:pos + ln]) if ln else np.zeros(12, dtype=np.uint64)
+        assert np.array_equal(got[i], want), (i, ln)
+        pos += ln
+    batch = msm.RowBatch()
+    r0 = batch.add(bases[:5], sc[:5])
+    r1 = batch.add(bases[5:40], sc[5:40])
+    pts = batch.run()
+    assert np.array_equal(pts[r0], oracle_c.msm_g1(bases[:5], sc[:5])) and np.array_equal(pts[r1], oracle_c.msm_g1(bases[5:40], sc[5:40]))
+    with pytest.raises(ValueError):
+        msm.msm_rows(bases[:4], sc[:4], [1, 2])
+    too_long = np.array([1025], dtype=np.uint64)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)   # noqa: E731
+    assert engine.tb200_msm_g1_rows(P(bases), P(sc), P(too_long), 1, 0, P(np.zeros(12, dtype=np.uint64))) == -3

@@ -82,6 +82,7 @@ SIGNATURES = {
     "tb200_gt_multi_pow": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
     "tb200_multi_pairing_batch": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_void_p]),
     "tb200_msm_g1_each": (c_int, [c_void_p, c_void_p, c_size_t, c_size_t, c_uint, c_void_p]),
+    "tb200_msm_g1_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
     "tb200_msm_g1_begin": (c_int, [c_void_p, c_void_p, c_size_t, c_uint, c_void_p]),
     "tb200_msm_g1_end": (c_int, [c_void_p, c_void_p]),
     "tb200_pst_open_g1": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_uint, c_void_p]),

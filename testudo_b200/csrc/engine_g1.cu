@@ -320,7 +320,7 @@ int msm_dev(Ctx& g, const void* d_bases, const void* d_scalars, size_t n, unsign
     if (points_ready) CU(cudaStreamWaitEvent(st, points_ready, 0));
     if (mark(g, st, "begin")) return 1;
     LAUNCH(k_msm_small, nblk, 4 * SMALL_QUADS, st, (const uint4*)d_bases, (const uint32_t*)d_scalars, (uint32_t)n,
-           (flags & TB200_SCALARS_MONT) ? 1 : 0, scratch, (uint4*)d_out, 0u);
+           (flags & TB200_SCALARS_MONT) ? 1 : 0, scratch, (uint4*)d_out, 0u, (const uint32_t*)nullptr);
     if (scratch) CU(cudaFreeAsync(scratch, st));
     if (mark(g, st, "accumulate")) return 1;
     g.last_c = 4;
@@ -809,6 +809,59 @@ int tb200_pst_open_g2(const uint64_t* evals, size_t nv, const uint64_t* point, c
   return pst_open_locked(evals, nv, point, level_bases, flags, proofs, true);
 }
 
+// A ragged batch of independent small MSMs in ONE launch of the Straus kernel: row i takes the next row_len[i] points
+// (0 .. 1024 each). The verifier's G1 work -- the 28-point UC fold, the 13-point fold of check_2 and the nv + 1 two-point
+// rows of check -- is three independent MSMs of different lengths: one launch, the latency of one.
+int tb200_msm_g1_rows(const uint64_t* bases_xy, const uint64_t* scalars, const size_t* row_len, size_t rows, unsigned flags,
+                      uint64_t* out_xy) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (need_ready()) return TB200_E_STATE;
+  if (rows == 0) return 0;
+  if (!row_len || !out_xy) return fail(TB200_E_ARG, "null pointer");
+  if (rows > (1u << 16)) return fail(TB200_E_LIMIT, "tb200_msm_g1_rows takes at most 65536 rows");
+  size_t n = 0;
+  std::vector<uint32_t> segs;
+  for (size_t r = 0; r < rows; r++) {
+    const size_t len = row_len[r];
+    if (len > (size_t)SMALL_MAX_POINTS) return fail(TB200_E_LIMIT, "row %zu has %zu points: at most %d per row", r, len, SMALL_MAX_POINTS);
+    const uint32_t ctas = std::max<uint32_t>(1, cdiv(len, SMALL_QUADS)), cta0 = (uint32_t)(segs.size() / SMALL_SEG_WORDS);
+    for (uint32_t k = 0; k < ctas; k++) {
+      const uint32_t cnt = (uint32_t)std::min<size_t>(SMALL_QUADS, len - std::min<size_t>(len, (size_t)k * SMALL_QUADS));
+      const uint32_t d[SMALL_SEG_WORDS] = {(uint32_t)(n + (size_t)k * SMALL_QUADS), cnt, (uint32_t)r, cta0, ctas};
+      segs.insert(segs.end(), d, d + SMALL_SEG_WORDS);
+    }
+    n += len;
+  }
+  if (n && (!bases_xy || !scalars)) return fail(TB200_E_ARG, "null pointer");
+  const size_t nblk = segs.size() / SMALL_SEG_WORDS;
+  Ctx& g = primary();
+  CU(cudaSetDevice(g.device));
+  uint4 *d_b = nullptr, *d_o = nullptr, *scratch = nullptr;
+  uint32_t *d_s = nullptr, *d_segs = nullptr;
+  const size_t ticket_bytes = ((rows * 4 + 15) / 16) * 16;
+  CU(cudaMallocAsync((void**)&d_b, std::max<size_t>(n, 1) * 96, g.stream));
+  CU(cudaMallocAsync((void**)&d_s, std::max<size_t>(n, 1) * 32, g.stream));
+  CU(cudaMallocAsync((void**)&d_o, rows * 96, g.stream));
+  CU(cudaMallocAsync((void**)&d_segs, segs.size() * 4, g.stream));
+  CU(cudaMallocAsync((void**)&scratch, nblk * 192 + ticket_bytes, g.stream));
+  CU(cudaMemsetAsync(scratch + nblk * 12, 0, ticket_bytes, g.stream));
+  if (n) {
+    CU(cudaMemcpyAsync(d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
+    CU(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, g.stream));
+  }
+  CU(cudaMemcpyAsync(d_segs, segs.data(), segs.size() * 4, cudaMemcpyHostToDevice, g.stream));
+  LAUNCH(k_msm_small, (uint32_t)nblk, 4 * SMALL_QUADS, g.stream, d_b, d_s, (uint32_t)n, (flags & TB200_SCALARS_MONT) ? 1 : 0,
+         scratch, d_o, 0u, (const uint32_t*)d_segs);
+  CU(cudaMemcpyAsync(out_xy, d_o, rows * 96, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));   // `segs` (pageable host memory) is consumed by then as well
+  cudaFreeAsync(d_b, g.stream);
+  cudaFreeAsync(d_s, g.stream);
+  cudaFreeAsync(d_o, g.stream);
+  cudaFreeAsync(d_segs, g.stream);
+  cudaFreeAsync(scratch, g.stream);
+  return 0;
+}
+
 // ---- a single MSM in flight next to other calls ------------------------------------------------------------------------
 // The reference runs independent MSMs side by side (`try_par!` / `rayon::join`, src/macros.rs:1-17, src/mipp.rs:77-85) and
 // computes cross-checks whose result nothing waits for (`MultilinearPC::commit(ck, &q)` for the debug_assert of
@@ -1189,7 +1242,7 @@ int tb200_msm_g1_each(const uint64_t* bases_xy, const uint64_t* scalars, size_t 
   CU(cudaMemcpyAsync(d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
   CU(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, g.stream));
   LAUNCH(k_msm_small, (uint32_t)rows, 4 * SMALL_QUADS, g.stream, d_b, d_s, (uint32_t)n, (flags & TB200_SCALARS_MONT) ? 1 : 0,
-         (uint4*)nullptr, d_o, (uint32_t)per_row);
+         (uint4*)nullptr, d_o, (uint32_t)per_row, (const uint32_t*)nullptr);
   CU(cudaMemcpyAsync(out_xy, d_o, rows * 96, cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
   cudaFreeAsync(d_b, g.stream);

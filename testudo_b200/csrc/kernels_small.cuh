@@ -246,10 +246,15 @@ __device__ __forceinline__ int quad_table_slot(int k) { return QS_SLOTS + 4 * (k
 // `per_row` > 0 (<= 8): gridDim.x INDEPENDENT MSMs of per_row points each -- CTA b multiplies points
 // [b * per_row, (b + 1) * per_row) and writes its own affine result to out_affine + 6 b; no cross-CTA sum, no scratch
 // (the verifier's g_mask[i] - z_i g, ark-poly-commit `check`: nv two-point MSMs for the latency of one).
+// `segs` != nullptr: a RAGGED batch of independent MSMs (rows of 0 .. 1024 points) in one launch. CTA b reads its
+// descriptor segs[5 b ..] = {first point, points (<= 8), row, first CTA of the row, CTAs of the row}; the CTAs of a row
+// leave their partial sums at scratch + 12 b, the last one to finish (one ticket per row: the uint32 array behind the
+// gridDim.x partials) adds them and writes out_affine + 6 row.
+constexpr int SMALL_SEG_WORDS = 5;
 __global__ void __launch_bounds__(4 * SMALL_QUADS) k_msm_small(const uint4* __restrict__ bases,
                                                                const uint32_t* __restrict__ scalars, uint32_t n, int mont,
                                                                uint4* __restrict__ scratch, uint4* __restrict__ out_affine,
-                                                               uint32_t per_row) {
+                                                               uint32_t per_row, const uint32_t* __restrict__ segs) {
   __shared__ uint4 small_sm[SMALL_SLOTS_PER_QUAD * 3 * SMALL_QUADS + (SMALL_QUADS * SMALL_DIGITS + SMALL_QUADS * 4 + 16) / 16];
   __shared__ int is_last;
   constexpr int nq = SMALL_QUADS;
@@ -258,8 +263,16 @@ __global__ void __launch_bounds__(4 * SMALL_QUADS) k_msm_small(const uint4* __re
   c.nq = nq;
   c.quad = threadIdx.x >> 2;
   c.role = threadIdx.x & 3;
-  const uint32_t per = per_row ? per_row : (uint32_t)nq;
-  const uint32_t pt = blockIdx.x * per + c.quad;     // this quad's point
+  uint32_t first, per, out_row, row_cta0, nb;        // this CTA's points, its row, and the row's CTAs
+  if (segs) {
+    const uint32_t* sg = segs + (size_t)SMALL_SEG_WORDS * blockIdx.x;
+    first = sg[0]; per = sg[1]; out_row = sg[2]; row_cta0 = sg[3]; nb = sg[4];
+  } else if (per_row) {
+    first = blockIdx.x * per_row; per = per_row; out_row = blockIdx.x; row_cta0 = blockIdx.x; nb = 1;
+  } else {
+    first = blockIdx.x * nq; per = nq; out_row = 0; row_cta0 = 0; nb = gridDim.x;
+  }
+  const uint32_t pt = first + c.quad;                // this quad's point
   int8_t* digits = reinterpret_cast<int8_t*>(small_sm + (size_t)SMALL_SLOTS_PER_QUAD * 3 * nq);   // [nq][64]
   int* quad_flag = reinterpret_cast<int*>(digits + (size_t)nq * SMALL_DIGITS);                    // [nq]
   if (threadIdx.x == 0) is_last = 0;
@@ -351,12 +364,11 @@ __global__ void __launch_bounds__(4 * SMALL_QUADS) k_msm_small(const uint4* __re
       store_xyzz(tree + 12 * c.quad, acc);
     }
   }
-  const uint32_t nb = per_row ? 1u : gridDim.x;
   if (nb > 1) {
     if (threadIdx.x == 0) {
       store_xyzz(scratch + 12 * (size_t)blockIdx.x, acc);
       __threadfence();
-      const uint32_t ticket = atomicAdd(reinterpret_cast<uint32_t*>(scratch + 12 * (size_t)nb), 1u);
+      const uint32_t ticket = atomicAdd(reinterpret_cast<uint32_t*>(scratch + 12 * (size_t)gridDim.x) + out_row, 1u);
       is_last = ticket == nb - 1;
     }
     __syncthreads();
@@ -366,7 +378,7 @@ __global__ void __launch_bounds__(4 * SMALL_QUADS) k_msm_small(const uint4* __re
     xyzz_set_inf(acc);
     for (uint32_t i = threadIdx.x; i < nb; i += 32) {
       Xyzz o;
-      const uint4* src = scratch + 12 * (size_t)i;
+      const uint4* src = scratch + 12 * ((size_t)row_cta0 + i);
       uint32_t* d = reinterpret_cast<uint32_t*>(&o);
       for (int w = 0; w < 12; w++) {
         const uint4 v = __ldcg(src + w);           // written by other CTAs: bypass L1
@@ -390,7 +402,7 @@ __global__ void __launch_bounds__(4 * SMALL_QUADS) k_msm_small(const uint4* __re
     xyzz_canon(acc);
     Affine o;
     xyzz_to_affine_ni(&o, &acc);
-    store_affine(out_affine + (per_row ? 6 * (size_t)blockIdx.x : 0), o);
+    store_affine(out_affine + 6 * (size_t)out_row, o);
   }
 }
 

@@ -157,13 +157,13 @@ class MippProofG1:
         return out
 
 
-    def verify_begin(self, vk: "multilinear_pc.VerifierKey", challenge: Callable[[bytes, List[np.ndarray]], int],
-                     point: List[int], U, T):
-        """Everything of `MippProof::verify` (src/mipp.rs:182-333) up to the pairings: the transcript replay, the TC fold
-        `T * prod comm_t_l^(c_inv) comm_t_r^(c)` (one tb200_gt_multi_pow), the UC fold `U + sum c_inv comm_u_l + c
-        comm_u_r` against final_u (one MSM), and the OPERANDS of the three pairing products still to evaluate -- so that a caller
-        (`Polynomial.verify`) can run them in one pass together with its own. Returns None when a challenge has no
-        inverse (the reference panics), else (check_u, tc, [final_t, check_2 left, check_2 right])."""
+    def verify_prepare(self, vk: "multilinear_pc.VerifierKey", challenge: Callable[[bytes, List[np.ndarray]], int],
+                       point: List[int], U, T, batch: "msm.RowBatch"):
+        """Everything of `MippProof::verify` (src/mipp.rs:182-333) up to the group work that can be batched: the
+        transcript replay, the TC fold `T * prod comm_t_l^(c_inv) comm_t_r^(c)` (one tb200_gt_multi_pow); the UC fold
+        `U + sum c_inv comm_u_l + c comm_u_r` against final_u and the G1 fold of check_2 are QUEUED on `batch` (rows of a
+        ragged MSM batch the caller runs once, together with its own). Returns None when a challenge has no inverse (the
+        reference panics), else `finish(points)` -> (check_u, tc, [final_t, check_2 left, check_2 right] operand lists)."""
         from . import pairing
         m = len(self.comms_u)
         if len(self.comms_t) != m or len(point) < m:
@@ -188,14 +188,18 @@ class MippProofG1:
         v = 1
         for i in range(m):
             v = v * (1 + rs[i] * xs_inv[m - i - 1] - rs[i]) % fr.R              # :294-297
-        # uc == final_u (:317) with final_u = final_a * final_y (:319), as ONE MSM: uc - final_y final_a is the identity
-        # (the group law is exact on any curve point, so this is the same predicate for the latency of one call less)
+        # uc == final_u (:317) with final_u = final_a * final_y (:319), as ONE row: uc - final_y final_a is the identity
+        # (the group law is exact on any curve point, so this is the same predicate for one MSM less)
         u_all = np.concatenate([u_bases, np.asarray(self.final_a, dtype=np.uint64).reshape(1, 12)])
         e_all = np.concatenate([exps, curve.scalars_to_words([(-final_y) % fr.R])])
-        check_u = not msm.msm_bigint(u_all, e_all).any()
-        products = [(np.asarray(self.final_a).reshape(1, 12), np.asarray(self.final_h).reshape(1, 24))]   # final_t, :312
-        products += multilinear_pc.check_2_products(vk, self.final_h, rs, v, self.pst_proof_h)            # check_h, :308
-        return check_u, tc, products
+        u_row = batch.add(u_all, e_all)
+        finish_h = multilinear_pc.check_2_prepare(vk, self.final_h, rs, v, self.pst_proof_h, batch)      # check_h, :308
+        final_t = (np.asarray(self.final_a).reshape(1, 12), np.asarray(self.final_h).reshape(1, 24))     # :312
+
+        def finish(points):
+            check_u = not points[u_row].any()
+            return check_u, tc, [final_t] + finish_h(points)
+        return finish
 
     def verify(self, vk: "multilinear_pc.VerifierKey", challenge: Callable[[bytes, List[np.ndarray]], int],
                point: List[int], U, T) -> bool:
@@ -203,10 +207,11 @@ class MippProofG1:
         final_a, final_h, pst_proof_h). `challenge` replays the transcript exactly as `prove` drove it; all group and
         pairing work runs on the GPU; the reference's asserts become a False result."""
         from . import pairing
-        parts = self.verify_begin(vk, challenge, point, U, T)
-        if parts is None:
+        batch = msm.RowBatch()
+        finish = self.verify_prepare(vk, challenge, point, U, T, batch)
+        if finish is None:
             return False
-        check_u, tc, products = parts
+        check_u, tc, products = finish(batch.run())
         final_t, left, right = pairing.multi_pairing_batch(products)
         check_t = bool(np.array_equal(tc, final_t))                              # :314
         check_h = bool(np.array_equal(left, right))                              # :308-309

@@ -110,3 +110,40 @@ def msm_unchecked_begin(bases, scalars) -> PendingMsm:
     handle = ctypes.c_void_p()
     _lib.check(_lib.engine().tb200_msm_g1_begin(_ptr(b), _ptr(s), n, _lib.SCALARS_MONT, ctypes.byref(handle)))
     return PendingMsm(handle, (b, s))
+
+
+def msm_rows(bases, bigints, row_lengths) -> np.ndarray:
+    """A ragged batch of independent small MSMs (rows of 0 .. 1024 points) in one launch (tb200_msm_g1_rows): row i takes
+    the next row_lengths[i] entries; canonical scalars. Returns [rows, 12]."""
+    b = _u64(bases, 12)
+    s = _u64(bigints, 4)
+    lens = np.ascontiguousarray(row_lengths, dtype=np.uint64).reshape(-1)
+    if len(b) != len(s) or int(lens.sum()) != len(b):
+        raise ValueError("bases and scalars must hold sum(row_lengths) entries")
+    out = np.zeros((len(lens), 12), dtype=np.uint64)
+    if len(lens):
+        _lib.check(_lib.engine().tb200_msm_g1_rows(_ptr(b), _ptr(s), _ptr(lens), len(lens), 0, _ptr(out)))
+    return out
+
+
+class RowBatch:
+    """Independent small MSMs collected from several places and run as ONE launch: `add` returns the row's index in the
+    array `run()` returns."""
+
+    def __init__(self):
+        self._b, self._s, self._len = [], [], []
+
+    def add(self, bases, bigints) -> int:
+        b = _u64(bases, 12)
+        s = _u64(bigints, 4)
+        if len(b) != len(s):
+            raise ValueError("bases and scalars differ in length")
+        self._b.append(b)
+        self._s.append(s)
+        self._len.append(len(b))
+        return len(self._len) - 1
+
+    def run(self) -> np.ndarray:
+        if not self._len:
+            return np.zeros((0, 12), dtype=np.uint64)
+        return msm_rows(np.concatenate(self._b), np.concatenate(self._s), self._len)

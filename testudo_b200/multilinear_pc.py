@@ -122,24 +122,31 @@ def _neg_words(values: Sequence[int]) -> np.ndarray:
     return curve.scalars_to_words([(-int(v)) % curve.R_ORDER for v in values])
 
 
-def check_products(vk: VerifierKey, commitment, point: Sequence[int], value: int, proofs):
-    """The two pairing products of `check` as operand lists [(g1s, g2s) left, (g1s, g2s) right]: the nv + 1 G1 values are
-    two-point MSMs ({C, g} x {1, -v}; {g_mask_i, g} x {1, -z_i}) -- ark builds them from a fixed-base table of g -- and run
-    as ONE launch (tb200_msm_g1_each)."""
+def check_prepare(vk: VerifierKey, commitment, point: Sequence[int], value: int, proofs, batch: "msm.RowBatch"):
+    """First half of `check`: queues its nv + 1 G1 values on `batch` as two-point rows ({C, g} x {1, -v};
+    {g_mask_i, g} x {1, -z_i} -- ark builds them from a fixed-base table of g) and returns `finish(points)`, which turns
+    the batch's results into the operand lists [(g1s, g2s) left, (g1s, g2s) right] of the two pairing products."""
     c = np.ascontiguousarray(commitment, dtype=np.uint64).reshape(12)
     pi = np.ascontiguousarray(proofs, dtype=np.uint64).reshape(-1, 24)
     nv = vk.nv
     if len(point) != nv or len(pi) != nv:
         raise ValueError("point and proof must have vk.nv entries")          # the reference indexes 0..vk.nv (panics)
-    bases = np.zeros((nv + 1, 2, 12), dtype=np.uint64)
-    bases[0, 0] = c
-    bases[1:, 0] = vk.g_mask_random
-    bases[:, 1] = vk.g
-    scalars = np.zeros((nv + 1, 2, 4), dtype=np.uint64)
-    scalars[:, 0] = _ONE
-    scalars[:, 1] = _neg_words([value] + list(point))
-    pts = msm.msm_each(bases.reshape(-1, 12), scalars.reshape(-1, 4), 2)
-    return [(pts[:1], vk.h.reshape(1, 24)), (pts[1:], pi)]
+    neg = _neg_words([value] + list(point))
+    rows = []
+    for i in range(nv + 1):
+        rows.append(batch.add(np.stack([c if i == 0 else vk.g_mask_random[i - 1], vk.g]), np.stack([_ONE, neg[i]])))
+
+    def finish(points):
+        pts = points[rows]
+        return [(pts[:1], vk.h.reshape(1, 24)), (pts[1:], pi)]
+    return finish
+
+
+def check_products(vk: VerifierKey, commitment, point: Sequence[int], value: int, proofs):
+    """The two pairing products of `check` as operand lists [left, right]; the G1 values in ONE launch."""
+    batch = msm.RowBatch()
+    finish = check_prepare(vk, commitment, point, value, proofs, batch)
+    return finish(batch.run())
 
 
 def check(vk: VerifierKey, commitment, point: Sequence[int], value: int, proofs) -> bool:
@@ -154,21 +161,32 @@ def check(vk: VerifierKey, commitment, point: Sequence[int], value: int, proofs)
     return bool(np.array_equal(left, right))
 
 
-def check_2_products(vk: VerifierKey, commitment_h, point: Sequence[int], value: int, proofs_g1):
-    """The two pairing products of `check_2` as operand lists [left, right] (see `check_2` for the form of the right one)."""
+def check_2_prepare(vk: VerifierKey, commitment_h, point: Sequence[int], value: int, proofs_g1, batch: "msm.RowBatch"):
+    """First half of `check_2` (see there for the form of the right-hand side): queues the fold -sum_i z_i proof_i on
+    `batch`, computes C_h - v h, and returns `finish(points)` -> [left, right] operand lists."""
     ch = np.ascontiguousarray(commitment_h, dtype=np.uint64).reshape(24)
     pi = np.ascontiguousarray(proofs_g1, dtype=np.uint64).reshape(-1, 12)
     m = len(point)
     off = vk.nv - m
     if off < 0 or len(pi) != m:
         raise ValueError("point longer than the key, or one proof per variable missing")
+    row = batch.add(pi, _neg_words(point)) if m else None
     left_q = msm_g2.msm_bigint(np.stack([ch, vk.h]), np.stack([_ONE, _neg_words([value])[0]]))
     left = (vk.g.reshape(1, 12), left_q.reshape(1, 24))
-    if m == 0:
-        return [left, (np.zeros((0, 12), dtype=np.uint64), np.zeros((0, 24), dtype=np.uint64))]
-    folded = msm.msm_bigint(pi, _neg_words(point))
-    return [left, (np.concatenate([pi, folded.reshape(1, 12)]),
-                   np.concatenate([vk.h_mask_random[off:off + m], vk.h.reshape(1, 24)]))]
+
+    def finish(points):
+        if m == 0:
+            return [left, (np.zeros((0, 12), dtype=np.uint64), np.zeros((0, 24), dtype=np.uint64))]
+        return [left, (np.concatenate([pi, points[row].reshape(1, 12)]),
+                       np.concatenate([vk.h_mask_random[off:off + m], vk.h.reshape(1, 24)]))]
+    return finish
+
+
+def check_2_products(vk: VerifierKey, commitment_h, point: Sequence[int], value: int, proofs_g1):
+    """The two pairing products of `check_2` as operand lists [left, right]."""
+    batch = msm.RowBatch()
+    finish = check_2_prepare(vk, commitment_h, point, value, proofs_g1, batch)
+    return finish(batch.run())
 
 
 def check_2(vk: VerifierKey, commitment_h, point: Sequence[int], value: int, proofs_g1) -> bool:

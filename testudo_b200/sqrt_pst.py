@@ -279,17 +279,21 @@ class Polynomial:
                v: int, pst_proof, mipp_proof: "mipp.MippProofG1", T) -> bool:
         """src/sqrt_pst.rs:232-267: `MippProof::verify` (U = A^y for the opening vector A of T) then
         `MultilinearPC::check(vk, U, a_rev, v, pst_proof)`. `U` is the `g_product` of the commitment `open` returned.
-        The five pairing products of the two checks -- e(final_a, final_h), both sides of check_2, both sides of check --
-        are evaluated in ONE pass of the pairing engine (tb200_multi_pairing_batch)."""
+        The small G1 MSMs of the two checks run as ONE ragged batch (tb200_msm_g1_rows), their five pairing products --
+        e(final_a, final_h), both sides of check_2, both sides of check -- in ONE pass of the pairing engine
+        (tb200_multi_pairing_batch)."""
         n = len(point)
         odd = n % 2
         a = list(point[: n // 2 + odd])
         b = list(point[n // 2 + odd:])
-        parts = mipp_proof.verify_begin(vk, challenge, b, U, T)             # :248
-        if parts is None:
+        batch = msm.RowBatch()                                              # every small G1 MSM of the two checks: ONE launch
+        finish_mipp = mipp_proof.verify_prepare(vk, challenge, b, U, T, batch)               # :248
+        if finish_mipp is None:
             return False
-        check_u, tc, products = parts
-        products += multilinear_pc.check_products(vk, U, a[::-1], v, pst_proof)          # :254-262
+        finish_check = multilinear_pc.check_prepare(vk, U, a[::-1], v, pst_proof, batch)     # :254-262
+        points = batch.run()
+        check_u, tc, products = finish_mipp(points)
+        products += finish_check(points)
         final_t, l2, r2, l1, r1 = pairing.multi_pairing_batch(products)
         res_mipp = check_u and bool(np.array_equal(tc, final_t)) and bool(np.array_equal(l2, r2))   # :249
         return res_mipp and bool(np.array_equal(l1, r1))
