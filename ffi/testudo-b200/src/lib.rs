@@ -147,6 +147,18 @@ pub fn msm_g1_each(bases: &[G1Affine], scalars: &[Fr], per_row: usize) -> Vec<G1
     check(unsafe { sys::tb200_msm_g1_each(b.as_ptr(), fr_limbs(scalars), rows, per_row, sys::TB200_SCALARS_MONT, out.as_mut_ptr()) });
     out.chunks(12).map(unpack_g1).collect()
 }
+/// a ragged batch of independent small MSMs (rows of 0..1024 points) in one launch: `rows[i]` = (bases, scalars) of row i
+pub fn msm_g1_rows(rows: &[(&[G1Affine], &[Fr])]) -> Vec<G1Affine> {
+    let lens: Vec<usize> = rows.iter().map(|(b, s)| b.len().min(s.len())).collect();
+    let (mut pb, mut ps) = (Vec::new(), Vec::new());
+    for ((b, s), &n) in rows.iter().zip(&lens) {
+        pb.extend(pack_g1(&b[..n]));
+        for k in &s[..n] { ps.extend_from_slice(&k.0 .0); }
+    }
+    let mut out = vec![0u64; 12 * rows.len()];
+    check(unsafe { sys::tb200_msm_g1_rows(pb.as_ptr(), ps.as_ptr(), lens.as_ptr(), rows.len(), sys::TB200_SCALARS_MONT, out.as_mut_ptr()) });
+    out.chunks(12).map(unpack_g1).collect()
+}
 /// several `E::multi_pairing` in ONE pass of the pairing engine; shorter products are padded with identity pairs
 pub fn multi_pairing_batch(products: &[(&[G1Affine], &[G2Affine])]) -> Vec<PairingOutput<Bls12_377>> {
     let width = products.iter().map(|(a, b)| a.len().min(b.len())).max().unwrap_or(0).max(1);

@@ -108,6 +108,17 @@ inline G1Affine msm_unchecked(const G1Affine* bases, const Fr* scalars, size_t n
 inline G1Affine msm_unchecked(const std::vector<G1Affine>& bases, const std::vector<Fr>& scalars) {
   return msm_unchecked(bases.data(), scalars.data(), std::min(bases.size(), scalars.size()));
 }
+// a ragged batch of independent small MSMs (rows of 0..1024 points, Montgomery-form scalars) in one launch
+inline std::vector<G1Affine> msm_rows(const std::vector<G1Affine>& bases, const std::vector<Fr>& scalars,
+                                      const std::vector<size_t>& row_len) {
+  size_t total = 0;
+  for (size_t l : row_len) total += l;
+  if (bases.size() != total || scalars.size() != total) throw std::invalid_argument("bases / scalars must hold sum(row_len) entries");
+  std::vector<G1Affine> out(row_len.size());
+  check(tb200_msm_g1_rows((const uint64_t*)bases.data(), (const uint64_t*)scalars.data(), row_len.data(), row_len.size(),
+                          TB200_SCALARS_MONT, (uint64_t*)out.data()));
+  return out;
+}
 // msm(bases, scalars) -> Result<G1, usize>: .second == true on Ok; on Err .first is unspecified and err_len = min(len)
 struct MsmResult {
   bool ok;
