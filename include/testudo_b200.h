@@ -365,6 +365,11 @@ int tb200_poseidon_new(int field, unsigned full_rounds, unsigned partial_rounds,
                        unsigned capacity, const uint64_t* ark, const uint64_t* mds, tb200_poseidon_t* out);
 int tb200_poseidon_reset(tb200_poseidon_t h);
 int tb200_poseidon_absorb_bytes(tb200_poseidon_t h, const uint8_t* data, size_t len);
+/* `transcript.append(label, &value)` (src/poseidon_transcript.rs:21-27) for a value in the C ABI's word layout: nwords = 4
+ * (Fr), 12 (G1 affine), 24 (G2 affine) or 72 (Fq12 / GT), Montgomery limbs. Encodes the value's uncompressed
+ * `CanonicalSerialize` bytes (ark-serialize 0.4: canonical little-endian coordinates, SWFlags in the last byte) and absorbs
+ * them exactly as tb200_poseidon_absorb_bytes would -- without a round trip through the host language's big integers. */
+int tb200_poseidon_append_words(tb200_poseidon_t h, const uint64_t* words, size_t nwords);
 int tb200_poseidon_absorb_native(tb200_poseidon_t h, const uint64_t* elems, size_t n);
 int tb200_poseidon_squeeze_native(tb200_poseidon_t h, uint64_t* out, size_t n);
 int tb200_poseidon_squeeze_fr(tb200_poseidon_t h, uint64_t out[4]);

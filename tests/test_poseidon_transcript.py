@@ -121,3 +121,39 @@ def test_transcript_encodings_and_flow():
     assert t4.challenge_scalar() == s4.squeeze_native(1)[0]
     inf = pt.encode_uncompressed(np.zeros(12, dtype=np.uint64))
     assert len(inf) == 96 and inf[95] == 0x40 and not any(inf[:95])
+
+
+def test_append_words_equals_the_python_encoding():
+    """tb200_poseidon_append_words (the C++ restatement of the uncompressed `CanonicalSerialize` encodings) against
+    `encode_uncompressed` + absorb_bytes: Fr, G1, G2 (both signs of y, y.c1 = 0 with either sign of c0), GT, the identities
+    -- the two transcripts must squeeze the same challenges."""
+    import random
+    from oracle import bls12_377_g2 as o2
+    from oracle import pairing as pr
+    from testudo_b200 import serialize
+    import helpers as h
+
+    rng = random.Random(8)
+    pts, _ = o.rand_points(4, 21)
+    qs, _ = o2.rand_points(4, 22)
+    values = []
+    for p in pts:
+        values += [h.pts_to_np([p])[0], h.pts_to_np([o.neg(p)])[0]]
+    for q in qs:
+        values += [np.array(o2.affine_to_words(q), dtype=np.uint64), np.array(o2.affine_to_words(o2.neg(q)), dtype=np.uint64)]
+    # a G2-shaped value whose y has c1 = 0 (not on the curve: only the encoder's sign rule is exercised)
+    for c0 in (5, curve.Q - 5):
+        values.append(serialize._fq_words([3, 4, c0, 0]))
+    values += [np.zeros(12, dtype=np.uint64), np.zeros(24, dtype=np.uint64)]
+    values += [np.array(pr.to_words(tuple((rng.randrange(o.Q), rng.randrange(o.Q)) for _ in range(6))), dtype=np.uint64)]
+    values += [h.scalars_to_np([rng.randrange(o.R_ORDER)], mont=True)[0], h.scalars_to_np([0], mont=True)[0]]
+    for field in ("fq", "fr"):
+        a, b = pt.PoseidonTranscript(field), pt.PoseidonTranscript(field)
+        for i, v in enumerate(values):
+            a.append(b"", v)
+            b.append_bytes(b"", pt.encode_uncompressed(v))
+            if i % 3 == 2:
+                assert a.challenge_scalar(b"") == b.challenge_scalar(b""), (field, i)
+        assert a.squeeze_native(2) == b.squeeze_native(2)
+    with pytest.raises(ValueError):
+        pt.PoseidonTranscript("fq").append(b"", np.zeros(5, dtype=np.uint64))

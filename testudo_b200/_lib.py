@@ -126,6 +126,7 @@ SIGNATURES = {
                                    ctypes.POINTER(c_void_p)]),
     "tb200_poseidon_reset": (c_int, [c_void_p]),
     "tb200_poseidon_absorb_bytes": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "tb200_poseidon_append_words": (c_int, [c_void_p, c_void_p, c_size_t]),
     "tb200_poseidon_absorb_native": (c_int, [c_void_p, c_void_p, c_size_t]),
     "tb200_poseidon_squeeze_native": (c_int, [c_void_p, c_void_p, c_size_t]),
     "tb200_poseidon_squeeze_fr": (c_int, [c_void_p, c_void_p]),

@@ -426,6 +426,70 @@ SpongeBase* make(const uint64_t* modulus, unsigned bits, unsigned full, unsigned
   return s;
 }
 
+// ---- `transcript.append(label, &value)` (src/poseidon_transcript.rs:21-27): the value's UNCOMPRESSED CanonicalSerialize
+// bytes (ark-serialize 0.4) from its in-memory words, restated next to the Python encoder (testudo_b200/serialize.py):
+//   Fp: canonical value, little endian (Fq 48 bytes, Fr 32); Fq2 = c0 || c1; Fq12 = twelve Fq in tower order;
+//   SW affine point: x || y with SWFlags in the top bits of the LAST byte -- bit 7: y > -y (Fq2: c1 decides, then c0),
+//   bit 6: the point at infinity (all coordinates written as zero).
+struct WordCodec {
+  Field<6> fq;
+  Field<4> fr;
+  uint64_t half[6];   // (q - 1) / 2: y > -y  <=>  y > half
+  WordCodec() {
+    fq.init(FQ_MOD);
+    fr.init(FR_MOD);
+    for (int i = 0; i < 6; i++) half[i] = (FQ_MOD[i] >> 1) | (i + 1 < 6 ? FQ_MOD[i + 1] << 63 : 0);
+  }
+  static void put(std::vector<uint8_t>& out, const uint64_t* v, int limbs) {
+    for (int i = 0; i < limbs; i++)
+      for (int b = 0; b < 8; b++) out.push_back((uint8_t)(v[i] >> (8 * b)));
+  }
+  bool above_half(const uint64_t* v) const { return !Field<6>::geq(half, v); }   // v > half
+  static bool is_zero(const uint64_t* v, int limbs) {
+    uint64_t acc = 0;
+    for (int i = 0; i < limbs; i++) acc |= v[i];
+    return acc == 0;
+  }
+  // nwords: 4 = Fr, 12 = G1 affine, 24 = G2 affine, 72 = Fq12; false for anything else
+  bool encode(std::vector<uint8_t>& out, const uint64_t* w, size_t nwords) const {
+    uint64_t c[6];
+    if (nwords == 4) {
+      uint64_t v[4];
+      fr.from_mont(v, w);
+      put(out, v, 4);
+      return true;
+    }
+    if (nwords == 72) {
+      for (int i = 0; i < 12; i++) {
+        fq.from_mont(c, w + 6 * i);
+        put(out, c, 6);
+      }
+      return true;
+    }
+    if (nwords != 12 && nwords != 24) return false;
+    const int nc = (int)nwords / 12;                       // Fq coefficients per coordinate
+    if (is_zero(w, (int)nwords)) {                         // the C ABI's identity
+      out.insert(out.end(), nwords * 8, 0);
+      out.back() |= 0x40;
+      return true;
+    }
+    bool neg = false;
+    for (int i = 0; i < 2 * nc; i++) {
+      fq.from_mont(c, w + 6 * i);
+      put(out, c, 6);
+      if (i >= nc) {                                       // y: the HIGHEST non-zero coefficient decides (c1 before c0)
+        if (!is_zero(c, 6)) neg = above_half(c);
+      }
+    }
+    if (neg) out.back() |= 0x80;
+    return true;
+  }
+};
+const WordCodec& codec() {
+  static const WordCodec c;
+  return c;
+}
+
 }  // namespace
 
 struct tb200_poseidon {
@@ -459,6 +523,15 @@ int tb200_poseidon_absorb_bytes(tb200_poseidon_t h, const uint8_t* data, size_t 
   if (!h || (len && !data)) return TB200_E_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   h->s->absorb_bytes(data, len);
+  return 0;
+}
+int tb200_poseidon_append_words(tb200_poseidon_t h, const uint64_t* words, size_t nwords) {
+  if (!h || !words) return TB200_E_ARG;
+  std::vector<uint8_t> bytes;
+  bytes.reserve(nwords * 8);
+  if (!codec().encode(bytes, words, nwords)) return TB200_E_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->s->absorb_bytes(bytes.data(), bytes.size());
   return 0;
 }
 int tb200_poseidon_absorb_native(tb200_poseidon_t h, const uint64_t* elems, size_t n) {
