@@ -2,8 +2,9 @@
 `MippProof::prove` (src/mipp.rs:31-153, 354-394), including -- when the G2 key `h` and the CRS levels are passed --
 the G2 `compress` of the commitment key (:114), the cross pairing products `comms_t` (:87-94, SURVEY.md 8f rank 3:
 tb200_mipp_pairing_cross over the device-resident a and h), the structured polynomial (:128-131, 159-180), `commit_g2`
-(:133) and the `open_g1` proof (:144). The Poseidon transcript is out of scope -- challenges come
-from a callback that receives what the reference appends.
+(:133) and the `open_g1` proof (:144). Challenges come from a `challenge(label, values)` callback that receives what
+the reference appends: `PoseidonTranscript("fq").as_challenge()` (testudo_b200/poseidon_transcript.py) is the reference's own
+transcript. `MippProofG1.verify` mirrors `MippProof::verify` (src/mipp.rs:182-333).
 
 The G1 vectors stay on the GPU across rounds (tb200_mipp_g1_*): upload once, two points back per round.
 """

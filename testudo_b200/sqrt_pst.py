@@ -15,8 +15,12 @@ What runs where:
   * the pairing product `t = multi_pairing(comm_list, powers_of_h[odd])` (src/sqrt_pst.rs:131-144) and MIPP's
     `comms_t` run on the GPU too when ck carries the G2 side; with a G1-only key `commit`
     returns t = None.
-  * the Poseidon transcript is OUT OF SCOPE of this engine: `open` takes the Fiat-Shamir
-    challenges from a callback that receives what the reference appends.
+  * `open` / `verify` take the Fiat-Shamir challenges from a `challenge(label, values)` callback that receives what the
+    reference appends; `PoseidonTranscript("fq").as_challenge()` (poseidon_transcript.py) is the
+    reference's own transcript (host code, as there).
+  * `verify` -- `Polynomial::verify` (src/sqrt_pst.rs:232-267): the GT fold, the small G1 MSMs and the five pairing
+    products of `MippProof::verify` and `MultilinearPC::check` on the GPU (tb200_gt_multi_pow, tb200_msm_g1_rows,
+    tb200_multi_pairing_batch).
 """
 from __future__ import annotations
 
@@ -243,8 +247,8 @@ class Polynomial:
     def open(self, challenge: Callable[[bytes, List[np.ndarray]], int], comm_list: np.ndarray, ck: CommitterKey,
              point: List[int], t: Optional[np.ndarray] = None) -> OpenG1:
         """src/sqrt_pst.rs:168-230 (`t` is accepted and unused, as `_T` in MippProof::prove, src/mipp.rs:38).
-        `challenge(label, appended_values)` stands in for the Poseidon transcript (out of scope): it receives what the
-        reference appends and returns the squeezed scalar."""
+        `challenge(label, appended_values)` receives what the reference appends and returns the squeezed scalar
+        (`PoseidonTranscript("fq").as_challenge()` for the reference's transcript)."""
         if self.q is None:
             self.get_q(point)
         assert self.chis_b is not None, "chis(b) should have been computed for q"
