@@ -57,6 +57,30 @@ extern std::mutex g_mu;  // serialises the C ABI (the reference calls it from ma
 
 inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 
+// Stream-ordered scratch of one host-facing call: everything allocated through it is released when the call returns,
+// on the error paths (the CU() early returns) as well -- after a synchronisation there, since a failed call may still have
+// copies in flight on the stream.
+struct StreamScratch {
+  cudaStream_t st;
+  std::vector<void*> ptrs;
+  bool done = false;   // set once the stream has been synchronised by the call itself
+  explicit StreamScratch(cudaStream_t s) : st(s) {}
+  StreamScratch(const StreamScratch&) = delete;
+  StreamScratch& operator=(const StreamScratch&) = delete;
+  template <class T>
+  cudaError_t alloc(T** out, size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 16, st);
+    if (e == cudaSuccess) ptrs.push_back(p);
+    *out = static_cast<T*>(p);
+    return e;
+  }
+  ~StreamScratch() {
+    if (!done) cudaStreamSynchronize(st);
+    for (void* p : ptrs) cudaFreeAsync(p, st);
+  }
+};
+
 // ---- grow-only device arena: the pipeline carves its scratch out of one allocation (no cudaMalloc on the hot path)
 // Several streams may use one arena one after the other (the *_dev entry points take a caller stream): `last_use`
 // is recorded when a pipeline has been enqueued and awaited by the next user's stream before it touches the scratch.

@@ -836,14 +836,15 @@ int tb200_msm_g1_rows(const uint64_t* bases_xy, const uint64_t* scalars, const s
   const size_t nblk = segs.size() / SMALL_SEG_WORDS;
   Ctx& g = primary();
   CU(cudaSetDevice(g.device));
+  StreamScratch sc(g.stream);
   uint4 *d_b = nullptr, *d_o = nullptr, *scratch = nullptr;
   uint32_t *d_s = nullptr, *d_segs = nullptr;
   const size_t ticket_bytes = ((rows * 4 + 15) / 16) * 16;
-  CU(cudaMallocAsync((void**)&d_b, std::max<size_t>(n, 1) * 96, g.stream));
-  CU(cudaMallocAsync((void**)&d_s, std::max<size_t>(n, 1) * 32, g.stream));
-  CU(cudaMallocAsync((void**)&d_o, rows * 96, g.stream));
-  CU(cudaMallocAsync((void**)&d_segs, segs.size() * 4, g.stream));
-  CU(cudaMallocAsync((void**)&scratch, nblk * 192 + ticket_bytes, g.stream));
+  CU(sc.alloc(&d_b, n * 96));
+  CU(sc.alloc(&d_s, n * 32));
+  CU(sc.alloc(&d_o, rows * 96));
+  CU(sc.alloc(&d_segs, segs.size() * 4));
+  CU(sc.alloc(&scratch, nblk * 192 + ticket_bytes));
   CU(cudaMemsetAsync(scratch + nblk * 12, 0, ticket_bytes, g.stream));
   if (n) {
     CU(cudaMemcpyAsync(d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
@@ -854,11 +855,7 @@ int tb200_msm_g1_rows(const uint64_t* bases_xy, const uint64_t* scalars, const s
          scratch, d_o, 0u, (const uint32_t*)d_segs);
   CU(cudaMemcpyAsync(out_xy, d_o, rows * 96, cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));   // `segs` (pageable host memory) is consumed by then as well
-  cudaFreeAsync(d_b, g.stream);
-  cudaFreeAsync(d_s, g.stream);
-  cudaFreeAsync(d_o, g.stream);
-  cudaFreeAsync(d_segs, g.stream);
-  cudaFreeAsync(scratch, g.stream);
+  sc.done = true;
   return 0;
 }
 
@@ -1234,20 +1231,19 @@ int tb200_msm_g1_each(const uint64_t* bases_xy, const uint64_t* scalars, size_t 
   Ctx& g = primary();
   CU(cudaSetDevice(g.device));
   const size_t n = rows * per_row;
+  StreamScratch sc(g.stream);
   uint4 *d_b = nullptr, *d_o = nullptr;
   uint32_t* d_s = nullptr;
-  CU(cudaMallocAsync((void**)&d_b, n * 96, g.stream));
-  CU(cudaMallocAsync((void**)&d_s, n * 32, g.stream));
-  CU(cudaMallocAsync((void**)&d_o, rows * 96, g.stream));
+  CU(sc.alloc(&d_b, n * 96));
+  CU(sc.alloc(&d_s, n * 32));
+  CU(sc.alloc(&d_o, rows * 96));
   CU(cudaMemcpyAsync(d_b, bases_xy, n * 96, cudaMemcpyHostToDevice, g.stream));
   CU(cudaMemcpyAsync(d_s, scalars, n * 32, cudaMemcpyHostToDevice, g.stream));
   LAUNCH(k_msm_small, (uint32_t)rows, 4 * SMALL_QUADS, g.stream, d_b, d_s, (uint32_t)n, (flags & TB200_SCALARS_MONT) ? 1 : 0,
          (uint4*)nullptr, d_o, (uint32_t)per_row, (const uint32_t*)nullptr);
   CU(cudaMemcpyAsync(out_xy, d_o, rows * 96, cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
-  cudaFreeAsync(d_b, g.stream);
-  cudaFreeAsync(d_s, g.stream);
-  cudaFreeAsync(d_o, g.stream);
+  sc.done = true;
   return 0;
 }
 int tb200_g1_outer_sum_dev(const void* d_a_xy, size_t na, const void* d_b_xy, size_t nb, void* d_out_xy, void* stream) {

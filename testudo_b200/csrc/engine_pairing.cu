@@ -408,19 +408,18 @@ int tb200_gt_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned
   if (n >= (1u << 22)) return fail(TB200_E_LIMIT, "too many elements");
   Ctx& g = primary();
   CU(cudaSetDevice(g.device));
+  StreamScratch sc(g.stream);
   uint4 *d_b = nullptr, *d_o = nullptr;
   uint32_t* d_e = nullptr;
-  CU(cudaMallocAsync((void**)&d_b, n * 576, g.stream));
-  CU(cudaMallocAsync((void**)&d_o, n * 576, g.stream));
-  CU(cudaMallocAsync((void**)&d_e, n * 32, g.stream));
+  CU(sc.alloc(&d_b, n * 576));
+  CU(sc.alloc(&d_o, n * 576));
+  CU(sc.alloc(&d_e, n * 32));
   CU(cudaMemcpyAsync(d_b, bases, n * 576, cudaMemcpyHostToDevice, g.stream));
   CU(cudaMemcpyAsync(d_e, exps, n * 32, cudaMemcpyHostToDevice, g.stream));
   if (int rc = gt_pow_launch(g.stream, d_b, d_e, n, (flags & TB200_SCALARS_MONT) ? 1 : 0, d_o)) return rc;
   CU(cudaMemcpyAsync(out, d_o, n * 576, cudaMemcpyDeviceToHost, g.stream));
   CU(cudaStreamSynchronize(g.stream));
-  cudaFreeAsync(d_b, g.stream);
-  cudaFreeAsync(d_o, g.stream);
-  cudaFreeAsync(d_e, g.stream);
+  sc.done = true;
   return 0;
 }
 
@@ -433,30 +432,23 @@ int tb200_gt_multi_pow(const uint64_t* bases, const uint64_t* exps, size_t n, un
   if (n >= (1u << 20)) return fail(TB200_E_LIMIT, "too many elements");
   Ctx& g = primary();
   CU(cudaSetDevice(g.device));
+  StreamScratch sc(g.stream);
   uint4 *d_b = nullptr, *d_p = nullptr, *d_o = nullptr;
   uint32_t* d_e = nullptr;
-  CU(cudaMallocAsync((void**)&d_o, 576, g.stream));
+  CU(sc.alloc(&d_o, 576));
   if (n) {
-    CU(cudaMallocAsync((void**)&d_b, n * 576, g.stream));
-    CU(cudaMallocAsync((void**)&d_p, n * 576, g.stream));
-    CU(cudaMallocAsync((void**)&d_e, n * 32, g.stream));
+    CU(sc.alloc(&d_b, n * 576));
+    CU(sc.alloc(&d_p, n * 576));
+    CU(sc.alloc(&d_e, n * 32));
     CU(cudaMemcpyAsync(d_b, bases, n * 576, cudaMemcpyHostToDevice, g.stream));
     CU(cudaMemcpyAsync(d_e, exps, n * 32, cudaMemcpyHostToDevice, g.stream));
+    if (int rc = gt_pow_launch(g.stream, d_b, d_e, n, (flags & TB200_SCALARS_MONT) ? 1 : 0, d_p)) return rc;
   }
-  int rc = n ? gt_pow_launch(g.stream, d_b, d_e, n, (flags & TB200_SCALARS_MONT) ? 1 : 0, d_p) : 0;
-  if (rc == 0) rc = pairing_dev_call(nullptr, nullptr, n, d_o, nullptr, d_p, false);
-  if (rc == 0) {
-    cudaError_t e = cudaMemcpyAsync(out, d_o, 576, cudaMemcpyDeviceToHost, g.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
-    if (e != cudaSuccess) rc = fail((int)e, "result copy failed: %s", cudaGetErrorString(e));
-  } else {
-    cudaStreamSynchronize(g.stream);
-  }
-  if (d_b) cudaFreeAsync(d_b, g.stream);
-  if (d_p) cudaFreeAsync(d_p, g.stream);
-  if (d_e) cudaFreeAsync(d_e, g.stream);
-  cudaFreeAsync(d_o, g.stream);
-  return rc;
+  if (int rc = pairing_dev_call(nullptr, nullptr, n, d_o, nullptr, d_p, false)) return rc;
+  CU(cudaMemcpyAsync(out, d_o, 576, cudaMemcpyDeviceToHost, g.stream));
+  CU(cudaStreamSynchronize(g.stream));
+  sc.done = true;
+  return 0;
 }
 
 int tb200_test_fq12_op(int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
