@@ -23,17 +23,119 @@
 #include <mutex>
 #include <vector>
 
+#include <cstdlib>
+
 #include "../../include/testudo_b200.h"
 
 namespace {
 
 typedef unsigned __int128 u128;
 
+// ---- BMI2 / ADX path of the Fq multiplier (6 limbs): each row `t += a * b` is ONE pass of mulx with the low halves on the
+// CF chain (adcx) and the high halves on the OF chain (adox) -- two independent carry chains the compiler cannot express
+// from C. Selected at run time (cpu_has_adx); results are identical to the portable path (tests/test_poseidon_transcript.py
+// runs both against the Python sponge).
+#if defined(__x86_64__) && defined(__GNUC__)
+#define TB200_HAVE_ADX_PATH 1
+static inline void adx_row7(uint64_t& t0, uint64_t& t1, uint64_t& t2, uint64_t& t3, uint64_t& t4, uint64_t& t5, uint64_t& t6, const uint64_t* a, uint64_t b) {
+  uint64_t lo, hi, z;
+  asm(
+    "xorl %k[z], %k[z]\n\t"
+    "mulx 0(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t0]\n\t adox %[hi], %[t1]\n\t"
+    "mulx 8(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t1]\n\t adox %[hi], %[t2]\n\t"
+    "mulx 16(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t2]\n\t adox %[hi], %[t3]\n\t"
+    "mulx 24(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t3]\n\t adox %[hi], %[t4]\n\t"
+    "mulx 32(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t4]\n\t adox %[hi], %[t5]\n\t"
+    "mulx 40(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t5]\n\t adox %[hi], %[t6]\n\t"
+    "adcx %[z], %[t6]\n\t"
+      : [t0] "+r"(t0), [t1] "+r"(t1), [t2] "+r"(t2), [t3] "+r"(t3), [t4] "+r"(t4), [t5] "+r"(t5), [t6] "+r"(t6), [lo] "=&r"(lo), [hi] "=&r"(hi), [z] "=&r"(z)
+      : [a] "r"(a), "d"(b), "m"(*(const uint64_t(*)[6])a)
+      : "cc");
+}
+static inline void adx_row8(uint64_t& t0, uint64_t& t1, uint64_t& t2, uint64_t& t3, uint64_t& t4, uint64_t& t5, uint64_t& t6, uint64_t& t7, const uint64_t* a, uint64_t b) {
+  uint64_t lo, hi, z;
+  asm(
+    "xorl %k[z], %k[z]\n\t"
+    "mulx 0(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t0]\n\t adox %[hi], %[t1]\n\t"
+    "mulx 8(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t1]\n\t adox %[hi], %[t2]\n\t"
+    "mulx 16(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t2]\n\t adox %[hi], %[t3]\n\t"
+    "mulx 24(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t3]\n\t adox %[hi], %[t4]\n\t"
+    "mulx 32(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t4]\n\t adox %[hi], %[t5]\n\t"
+    "mulx 40(%[a]), %[lo], %[hi]\n\t adcx %[lo], %[t5]\n\t adox %[hi], %[t6]\n\t"
+    "adcx %[z], %[t6]\n\t"
+    "adox %[z], %[t7]\n\t adcx %[z], %[t7]\n\t"
+      : [t0] "+r"(t0), [t1] "+r"(t1), [t2] "+r"(t2), [t3] "+r"(t3), [t4] "+r"(t4), [t5] "+r"(t5), [t6] "+r"(t6), [t7] "+r"(t7), [lo] "=&r"(lo), [hi] "=&r"(hi), [z] "=&r"(z)
+      : [a] "r"(a), "d"(b), "m"(*(const uint64_t(*)[6])a)
+      : "cc");
+}
+static inline bool cpu_has_adx() {
+  static const bool yes = __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("adx") && !getenv("TB200_NO_ADX");
+  return yes;
+}
+// r = x * y * R^-1 mod p for the 6-limb field with a clear top bit (no-carry CIOS), r < p
+static inline void adx_mul6(uint64_t* r, const uint64_t* x, const uint64_t* y, const uint64_t* p, uint64_t inv) {
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0;
+#define TB200_ADX_STEP(a0, a1, a2, a3, a4, a5, a6, yi)  \
+  adx_row7(a0, a1, a2, a3, a4, a5, a6, x, yi);          \
+  adx_row7(a0, a1, a2, a3, a4, a5, a6, p, a0 * inv);    \
+  a0 = 0; /* the low limb cancelled: it becomes the (empty) top limb of the next row */
+  TB200_ADX_STEP(t0, t1, t2, t3, t4, t5, t6, y[0])
+  TB200_ADX_STEP(t1, t2, t3, t4, t5, t6, t0, y[1])
+  TB200_ADX_STEP(t2, t3, t4, t5, t6, t0, t1, y[2])
+  TB200_ADX_STEP(t3, t4, t5, t6, t0, t1, t2, y[3])
+  TB200_ADX_STEP(t4, t5, t6, t0, t1, t2, t3, y[4])
+  TB200_ADX_STEP(t5, t6, t0, t1, t2, t3, t4, y[5])
+#undef TB200_ADX_STEP
+  // the value sits in (t6, t0, t1, t2, t3, t4), below 2p: one branch-free subtraction
+  const uint64_t v[6] = {t6, t0, t1, t2, t3, t4};
+  uint64_t s[6], borrow = 0;
+  for (int j = 0; j < 6; j++) {
+    const u128 d = (u128)v[j] - p[j] - borrow;
+    s[j] = (uint64_t)d;
+    borrow = (uint64_t)(d >> 64) & 1;
+  }
+  for (int j = 0; j < 6; j++) r[j] = borrow ? v[j] : s[j];
+}
+// r = (a0 b0 + a1 b1 + a2 b2) * R^-1 mod p with ONE reduction per row (the MDS row of the width-3 sponge), r < p
+static inline void adx_dot3_6(uint64_t* r, const uint64_t* a0, const uint64_t* b0, const uint64_t* a1, const uint64_t* b1,
+                              const uint64_t* a2, const uint64_t* b2, const uint64_t* p, uint64_t inv) {
+  uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0;
+#define TB200_ADX_STEP(c0, c1, c2, c3, c4, c5, c6, c7, i)  \
+  adx_row8(c0, c1, c2, c3, c4, c5, c6, c7, a0, b0[i]);     \
+  adx_row8(c0, c1, c2, c3, c4, c5, c6, c7, a1, b1[i]);     \
+  adx_row8(c0, c1, c2, c3, c4, c5, c6, c7, a2, b2[i]);     \
+  adx_row8(c0, c1, c2, c3, c4, c5, c6, c7, p, c0 * inv);   \
+  c0 = 0;
+  TB200_ADX_STEP(t0, t1, t2, t3, t4, t5, t6, t7, 0)
+  TB200_ADX_STEP(t1, t2, t3, t4, t5, t6, t7, t0, 1)
+  TB200_ADX_STEP(t2, t3, t4, t5, t6, t7, t0, t1, 2)
+  TB200_ADX_STEP(t3, t4, t5, t6, t7, t0, t1, t2, 3)
+  TB200_ADX_STEP(t4, t5, t6, t7, t0, t1, t2, t3, 4)
+  TB200_ADX_STEP(t5, t6, t7, t0, t1, t2, t3, t4, 5)
+#undef TB200_ADX_STEP
+  // the value sits in (t6, t7, t0, t1, t2, t3 | t4), below 4p
+  uint64_t v[7] = {t6, t7, t0, t1, t2, t3, t4};
+  for (;;) {
+    uint64_t s[6], borrow = 0;
+    for (int j = 0; j < 6; j++) {
+      const u128 d = (u128)v[j] - p[j] - borrow;
+      s[j] = (uint64_t)d;
+      borrow = (uint64_t)(d >> 64) & 1;
+    }
+    if (v[6] == 0 && borrow) break;          // v < p
+    v[6] -= borrow;
+    for (int j = 0; j < 6; j++) v[j] = s[j];
+  }
+  for (int j = 0; j < 6; j++) r[j] = v[j];
+}
+#endif
+
 // Montgomery arithmetic over an odd modulus of N 64-bit limbs (N = 4: Fr, N = 6: Fq)
 template <int N>
 struct Field {
   uint64_t p[N], r2[N], one[N], inv;  // inv = -p^-1 mod 2^64
   bool nocarry = false;               // top bit of p clear: the interleaved CIOS of mul() applies
+  bool adx = false;                   // BMI2 + ADX available: the two-carry-chain rows (6-limb field)
   static bool geq(const uint64_t* a, const uint64_t* b) {
     for (int i = N - 1; i >= 0; i--)
       if (a[i] != b[i]) return a[i] > b[i];
@@ -81,6 +183,9 @@ struct Field {
   // unrolled: ~2x the speed of the generic loop (the sponge spends all its time here: ~630 products per permutation).
   void mul(uint64_t* r, const uint64_t* x, const uint64_t* y) const {
     if (!nocarry) return mul_generic(r, x, y);
+#ifdef TB200_HAVE_ADX_PATH
+    if (N == 6 && adx) return adx_mul6(r, x, y, p, inv);
+#endif
     uint64_t t[N];
 #pragma GCC unroll 8
     for (int j = 0; j < N; j++) t[j] = 0;
@@ -165,6 +270,9 @@ struct Field {
   // the same for exactly three terms (the MDS row of the reference's width-3 sponge), fully unrolled
   void dot3(uint64_t* r, const uint64_t* a0, const uint64_t* b0, const uint64_t* a1, const uint64_t* b1, const uint64_t* a2,
             const uint64_t* b2) const {
+#ifdef TB200_HAVE_ADX_PATH
+    if (N == 6 && adx && nocarry) return adx_dot3_6(r, a0, b0, a1, b1, a2, b2, p, inv);
+#endif
     uint64_t t[N + 2];
 #pragma GCC unroll 8
     for (int j = 0; j < N + 2; j++) t[j] = 0;
@@ -202,6 +310,9 @@ struct Field {
   void init(const uint64_t* modulus) {
     memcpy(p, modulus, N * 8);
     nocarry = (p[N - 1] >> 63) == 0;
+#ifdef TB200_HAVE_ADX_PATH
+    adx = cpu_has_adx();
+#endif
     uint64_t x = 1;  // Newton: x = p^-1 mod 2^64
     for (int i = 0; i < 6; i++) x *= 2 - p[0] * x;
     inv = (uint64_t)(0 - x);
