@@ -124,7 +124,7 @@ pub fn multi_pairing(a: &[G1Affine], b: &[G2Affine]) -> PairingOutput<Bls12_377>
     PairingOutput(unpack_gt(&t))
 }
 
-// ---- the verifier side: `MippProof::verify` (src/mipp.rs:182-333), `MultilinearPC::check` (src/sqrt_pst.rs:262) ------------
+// ---- the verifier side: `MippProof::verify` (src/mipp.rs:182-333), `MultilinearPC::check` (src/sqrt_pst.rs:261) ------------
 fn pack_gt(v: &[Fq12]) -> Vec<u64> {
     let mut w = Vec::with_capacity(72 * v.len());
     for f in v {
@@ -132,7 +132,7 @@ fn pack_gt(v: &[Fq12]) -> Vec<u64> {
     }
     w
 }
-/// prod_i bases[i].pow(exps[i]): the TC half of the fold / reduce over `MippTU` (src/mipp.rs:238-271) in one call
+/// prod_i bases[i].pow(exps[i]): the TC half of the fold / reduce over `MippTU` (src/mipp.rs:240-271) in one call
 pub fn gt_multi_pow(bases: &[Fq12], exps: &[Fr]) -> Fq12 {
     assert_eq!(bases.len(), exps.len());
     let (b, mut out) = (pack_gt(bases), [0u64; 72]);

@@ -221,13 +221,13 @@ int tb200_fr_matvec_dev(const void* d_Z, size_t rows, size_t cols, const void* d
 /* `rows` INDEPENDENT tiny MSMs in one launch: out[i] = sum_{j < per_row} scalars[i*per_row + j] * bases[i*per_row + j],
  * per_row <= 8 (one warp per row, a quad of lanes per point, the small-n Straus kernel). The verifier side of the path:
  * ark-poly-commit 0.4 `MultilinearPC::check` forms `commitment - g*value` and `g_mask_random[i] - g*point[i]` for every
- * variable (reached from `Polynomial::verify`, src/sqrt_pst.rs:262) -- nv + 1 two-point MSMs for the latency of one.
+ * variable (reached from `Polynomial::verify`, src/sqrt_pst.rs:261) -- nv + 1 two-point MSMs for the latency of one.
  * Accepts any curve point; scalars canonical, or Montgomery with TB200_SCALARS_MONT; (0, 0) in / out = identity. */
 int tb200_msm_g1_each(const uint64_t* bases_xy, const uint64_t* scalars, size_t rows, size_t per_row, unsigned flags,
                       uint64_t* out_xy);
 /* The same for rows of DIFFERENT lengths (0 .. 1024 points each): row i takes the next row_len[i] entries of bases /
- * scalars. `MippProof::verify` + `MultilinearPC::check` need a (2m + 2)-point fold (src/mipp.rs:238-277,317-319), an
- * m-point fold (check_2, :313) and nv + 1 two-point rows (src/sqrt_pst.rs:262): three kinds of independent MSMs, one
+ * scalars. `MippProof::verify` + `MultilinearPC::check` need a (2m + 2)-point fold (src/mipp.rs:240-276,310-316), an
+ * m-point fold (check_2, :307) and nv + 1 two-point rows (src/sqrt_pst.rs:261): three kinds of independent MSMs, one
  * launch. An empty row yields the identity. */
 int tb200_msm_g1_rows(const uint64_t* bases_xy, const uint64_t* scalars, const size_t* row_len, size_t rows, unsigned flags,
                       uint64_t* out_xy);
@@ -314,7 +314,7 @@ int tb200_multi_pairing(const uint64_t* g1_xy, const uint64_t* g2, size_t n, uin
 /* `products` independent pairing products of `pairs_each` pairs each in ONE pass of the pairing engine; product p takes the
  * pairs [p * pairs_each, (p + 1) * pairs_each) and lands at out + 72 p. Identity pairs contribute 1, so shorter products
  * are padded with (0, 0) points. The verifier side of the path evaluates five products -- `E::pairing(final_a, final_h)`
- * (src/mipp.rs:320), both sides of `check_2` (:313) and of `MultilinearPC::check` (src/sqrt_pst.rs:262) -- for the latency
+ * (src/mipp.rs:311), both sides of `check_2` (:307) and of `MultilinearPC::check` (src/sqrt_pst.rs:261) -- for the latency
  * of one. */
 int tb200_multi_pairing_batch(const uint64_t* g1_xy, const uint64_t* g2, size_t products, size_t pairs_each, uint64_t* out);
 /* Same with DEVICE pointers; d_out receives 576 bytes; returns after enqueueing on `stream` (NULL = library stream). */
@@ -336,7 +336,7 @@ int tb200_mipp_pairing_cross(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_t_
  * pairing products comm_t_l / comm_t_r are enqueued on separate streams and awaited together. */
 int tb200_mipp_cross_all(tb200_mipp_t a, tb200_mipp_g2_t h, uint64_t comm_u_l[12], uint64_t comm_u_r[12],
                          uint64_t comm_t_l[72], uint64_t comm_t_r[72]);
-/* out[i] = base[i] ^ exps[i] in GT (the verifier's `tx.pow(c)`, src/mipp.rs:252-255); exponents are Fr values
+/* out[i] = base[i] ^ exps[i] in GT (the verifier's `tx.pow(c)`, src/mipp.rs:258-261); exponents are Fr values
  * (canonical, or Montgomery with TB200_SCALARS_MONT). */
 /* tuning/test hook: pairing products of up to `n` pairs run one WARP per Miller loop, larger ones one THREAD (default 8192) */
 void tb200_set_pairing_coop_max(int n);
@@ -347,7 +347,7 @@ void tb200_set_pairing_coop_max(int n);
 void tb200_set_pairing_team(int lanes);
 int tb200_gt_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned flags, uint64_t* out);
 /* out = prod_i bases[i] ^ exps[i] in GT: the TC half of the verifier's parallel fold / reduce over `MippTU`
- * (src/mipp.rs:238-271: `tx.pow(c)`, `res.tc.mul_assign(&tx)`, `merge`) in one call -- every power on its own team of
+ * (src/mipp.rs:240-271: `tx.pow(c)`, `res.tc.mul_assign(&tx)`, `merge`) in one call -- every power on its own team of
  * lanes, then the product tree of the pairing engine. Generic field arithmetic (proof values need not be unitary);
  * n == 0 yields 1. Exponents as for tb200_gt_pow. */
 int tb200_gt_multi_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned flags, uint64_t out[72]);

@@ -62,18 +62,18 @@ def mipp_verify(vk: Dict, challenge: Callable, proof: Dict, point: Sequence[int]
         c = pow(c_inv, -1, R)
         xs.append(c)
         xs_inv.append(c_inv)
-        final_y = final_y * (1 + c_inv * point[i] - point[i]) % R                   # :229
+        final_y = final_y * (1 + c_inv * point[i] - point[i]) % R                   # :226
     for (ul, ur), (tl, tr), c, c_inv in zip(proof["comms_u"], proof["comms_t"], xs, xs_inv):
-        tc = pr.f12_mul(tc, pr.f12_mul(pr.f12_pow(tl, c_inv), pr.f12_pow(tr, c)))   # :246-256
+        tc = pr.f12_mul(tc, pr.f12_mul(pr.f12_pow(tl, c_inv), pr.f12_pow(tr, c)))   # :246-265
         uc = g1.add(uc, g1.add(g1.mul(c_inv, ul), g1.mul(c, ur)))
     m = len(xs_inv)
-    rs = [challenge(b"random_point", []) % R for _ in range(m)]                     # :286-290
+    rs = [challenge(b"random_point", []) % R for _ in range(m)]                     # :281-285
     v = 1
     for i in range(m):
-        v = v * (1 + rs[i] * xs_inv[m - i - 1] - rs[i]) % R                         # :299-303
-    check_h = check_2(vk, proof["final_h"], rs, v, proof["pst_proof_h"])            # :313
-    final_u = g1.mul(final_y, proof["final_a"])                                     # :319
-    final_t = pr.pairing(proof["final_a"], proof["final_h"])                        # :320
+        v = v * (1 + rs[i] * xs_inv[m - i - 1] - rs[i]) % R                         # :294-297
+    check_h = check_2(vk, proof["final_h"], rs, v, proof["pst_proof_h"])            # :307
+    final_u = g1.mul(final_y, proof["final_a"])                                     # :310
+    final_t = pr.pairing(proof["final_a"], proof["final_h"])                        # :311
     return check_h and tc == final_t and uc == final_u
 
 

@@ -125,7 +125,7 @@ def test_lazy_cyclotomic_chain_and_final_exponentiation(hc):
 
 
 def test_lazy_generic_power_chain(hc):
-    """The chain of k_fq12_pow_coop (the verifier's `tx.pow(c)`, src/mipp.rs:252-255): ~253 generic lazily reduced squarings
+    """The chain of k_fq12_pow_coop (the verifier's `tx.pow(c)`, src/mipp.rs:258-261): ~253 generic lazily reduced squarings
     with a product after every set bit, on arbitrary field elements (proof values are not known to be unitary)."""
     rng = random.Random(47)
     cases = [(tuple((rng.randrange(Q), rng.randrange(Q)) for _ in range(6)), e)

@@ -423,7 +423,7 @@ int tb200_gt_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned
   return 0;
 }
 
-// prod_i bases[i]^exps[i]: the TC half of the verifier's fold / reduce (src/mipp.rs:238-271) -- the powers on one team
+// prod_i bases[i]^exps[i]: the TC half of the verifier's fold / reduce (src/mipp.rs:240-271) -- the powers on one team
 // each, then the product tree of the pairing engine (no final exponentiation); n == 0 yields 1
 int tb200_gt_multi_pow(const uint64_t* bases, const uint64_t* exps, size_t n, unsigned flags, uint64_t out[72]) {
   std::lock_guard<std::mutex> lk(g_mu);

@@ -595,7 +595,7 @@ __global__ void k_fq12_set_one(uint4* out, uint32_t count) {
   store_fq12(out + 36 * (size_t)t, one);
 }
 
-// a^e for GT elements (the verifier's `tx.pow(c)`, src/mipp.rs:252-255): square-and-multiply over a canonical
+// a^e for GT elements (the verifier's `tx.pow(c)`, src/mipp.rs:258-261): square-and-multiply over a canonical
 // 8-limb exponent, one thread per (element, exponent) pair
 __global__ void __launch_bounds__(32) k_fq12_pow(const uint4* __restrict__ in, const uint32_t* __restrict__ exps,
                                                  uint32_t n, int exps_mont, uint4* __restrict__ out) {
@@ -1208,7 +1208,7 @@ __global__ void __launch_bounds__(W12_THREADS) k_test_w12_op(int op, const uint4
   for (int i = lane; i < 36; i += blockDim.x) out[36 * (size_t)blockIdx.x + i] = r4[i];
 }
 
-// a^e for GT elements on ONE TEAM per element (the verifier's `tx.pow(c)`, src/mipp.rs:252-255): the thread-per-element
+// a^e for GT elements on ONE TEAM per element (the verifier's `tx.pow(c)`, src/mipp.rs:258-261): the thread-per-element
 // kernel above walks ~380 Fq12 operations of 36-54 serial Fq products each (~17 ms whatever n is); the verifier raises 2 m
 // <= 28 values, so the chain's latency is all that counts: square-and-multiply from the top set bit with the cooperative
 // Fq12 square / product (54 / 36 lanes busy per phase). Generic squarings: the inputs are proof values, nothing says they

@@ -389,20 +389,20 @@ inline Gt pairings_product(const std::vector<G1Affine>& gs, const std::vector<G2
   return multi_pairing(gs, hs);
 }
 inline Gt pairing(const G1Affine& p, const G2Affine& q) { return multi_pairing({p}, {q}); }
-// `TargetField::pow(c.into_bigint())` on Montgomery-form exponents (the verifier's tx.pow(c), src/mipp.rs:252-255)
+// `TargetField::pow(c.into_bigint())` on Montgomery-form exponents (the verifier's tx.pow(c), src/mipp.rs:258-261)
 inline Gt pow(const Gt& base, const Fr& exp) {
   Gt out;
   check(tb200_gt_pow(base.w, exp.l, 1, TB200_SCALARS_MONT, out.w));
   return out;
 }
-// prod_i bases[i].pow(exps[i]): the TC half of the verifier's fold / reduce over MippTU (src/mipp.rs:238-271) in one call
+// prod_i bases[i].pow(exps[i]): the TC half of the verifier's fold / reduce over MippTU (src/mipp.rs:240-271) in one call
 inline Gt multi_pow(const std::vector<Gt>& bases, const std::vector<Fr>& exps) {
   if (bases.size() != exps.size()) throw std::invalid_argument("bases and exponents differ in length");
   Gt out;
   check(tb200_gt_multi_pow((const uint64_t*)bases.data(), (const uint64_t*)exps.data(), bases.size(), TB200_SCALARS_MONT, out.w));
   return out;
 }
-// several independent pairing products in ONE pass (the verifier's five: src/mipp.rs:313,320, src/sqrt_pst.rs:262);
+// several independent pairing products in ONE pass (the verifier's five: src/mipp.rs:307,311, src/sqrt_pst.rs:261);
 // shorter products are padded with identity pairs, which contribute 1 as in ark
 inline std::vector<Gt> multi_pairing_batch(const std::vector<std::pair<std::vector<G1Affine>, std::vector<G2Affine>>>& products) {
   size_t width = 1;

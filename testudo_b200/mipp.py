@@ -172,15 +172,15 @@ class MippProofG1:
         U = np.ascontiguousarray(U, dtype=np.uint64).reshape(12)
         T = np.ascontiguousarray(T, dtype=np.uint64).reshape(pairing.GT_WORDS)
         xs, xs_inv, final_y = [], [], 1
-        challenge(b"U", [U])                                                     # :198
+        challenge(b"U", [U])                                                     # :203
         for i, ((ul, ur), (tl, tr)) in enumerate(zip(self.comms_u, self.comms_t)):
-            c_inv = challenge(b"challenge_i", [ul, ur, tl, tr]) % fr.R          # :207-211
+            c_inv = challenge(b"challenge_i", [ul, ur, tl, tr]) % fr.R          # :212-216
             if c_inv == 0:
-                return None                                                      # `c_inv.inverse().unwrap()`, :213
+                return None                                                      # `c_inv.inverse().unwrap()`, :218
             xs.append(fr.inverse(c_inv))
             xs_inv.append(c_inv)
-            final_y = final_y * (1 + c_inv * point[i] - point[i]) % fr.R        # :221
-        # :238-277, the fold / reduce over MippTU seeded with (T, U): exponent 1 for the seeds
+            final_y = final_y * (1 + c_inv * point[i] - point[i]) % fr.R        # :226
+        # :240-276, the fold / reduce over MippTU seeded with (T, U): exponent 1 for the seeds
         t_bases = np.stack([T] + [t for tl, tr in self.comms_t for t in (tl, tr)])
         u_bases = np.stack([U] + [u for ul, ur in self.comms_u for u in (ul, ur)])
         exps = curve.scalars_to_words([1] + [e for c, ci in zip(xs, xs_inv) for e in (ci, c)])
@@ -189,13 +189,13 @@ class MippProofG1:
         v = 1
         for i in range(m):
             v = v * (1 + rs[i] * xs_inv[m - i - 1] - rs[i]) % fr.R              # :294-297
-        # uc == final_u (:317) with final_u = final_a * final_y (:319), as ONE row: uc - final_y final_a is the identity
+        # uc == final_u (:316) with final_u = final_a * final_y (:310), as ONE row: uc - final_y final_a is the identity
         # (the group law is exact on any curve point, so this is the same predicate for one MSM less)
         u_all = np.concatenate([u_bases, np.asarray(self.final_a, dtype=np.uint64).reshape(1, 12)])
         e_all = np.concatenate([exps, curve.scalars_to_words([(-final_y) % fr.R])])
         u_row = batch.add(u_all, e_all)
-        finish_h = multilinear_pc.check_2_prepare(vk, self.final_h, rs, v, self.pst_proof_h, batch)      # check_h, :308
-        final_t = (np.asarray(self.final_a).reshape(1, 12), np.asarray(self.final_h).reshape(1, 24))     # :312
+        finish_h = multilinear_pc.check_2_prepare(vk, self.final_h, rs, v, self.pst_proof_h, batch)      # check_h, :307
+        final_t = (np.asarray(self.final_a).reshape(1, 12), np.asarray(self.final_h).reshape(1, 24))     # :311
 
         def finish(points):
             check_u = not points[u_row].any()
@@ -214,8 +214,8 @@ class MippProofG1:
             return False
         check_u, tc, products = finish(batch.run())
         final_t, left, right = pairing.multi_pairing_batch(products)
-        check_t = bool(np.array_equal(tc, final_t))                              # :314
-        check_h = bool(np.array_equal(left, right))                              # :308-309
+        check_t = bool(np.array_equal(tc, final_t))                              # :313
+        check_h = bool(np.array_equal(left, right))                              # :307-308
         return check_h and check_t and check_u
 
 

@@ -151,7 +151,7 @@ def check_products(vk: VerifierKey, commitment, point: Sequence[int], value: int
 
 def check(vk: VerifierKey, commitment, point: Sequence[int], value: int, proofs) -> bool:
     """`MultilinearPC::check(vk, commitment, point, value, proof)` (ark-poly-commit 0.4 multilinear_pc/mod.rs; called at
-    src/sqrt_pst.rs:262; gadget form src/circuit_verifier.rs:244-312):
+    src/sqrt_pst.rs:261; gadget form src/circuit_verifier.rs:244-312):
 
         e(C - v g, h) == prod_i e(g_mask_random[i] - point[i] g, proof_i)
 
@@ -190,7 +190,7 @@ def check_2_products(vk: VerifierKey, commitment_h, point: Sequence[int], value:
 
 
 def check_2(vk: VerifierKey, commitment_h, point: Sequence[int], value: int, proofs_g1) -> bool:
-    """The fork's `MultilinearPC::check_2(vk, &CommitmentG2, point, value, &ProofG1)` (src/mipp.rs:313; gadget form
+    """The fork's `MultilinearPC::check_2(vk, &CommitmentG2, point, value, &ProofG1)` (src/mipp.rs:307; gadget form
     src/circuit_verifier.rs:170-241), the mirror image of `check` for a G2 commitment with G1 proofs:
 
         e(g, C_h - v h) == prod_i e(proof_i, h_mask_random[off + i] - point[i] h),   off = vk.nv - len(point)

@@ -2,8 +2,8 @@
 `ark_bls12_377::Bls12_377`:
 
     E::multi_pairing(g1s, g2s).0      src/sqrt_pst.rs:143 (the IPP commitment t), src/mipp.rs:396-398 (pairings_product)
-    E::pairing(p, q).0                src/mipp.rs:320 (verifier)
-    TargetField::pow(bigint)          src/mipp.rs:252-255 (verifier); with the products of :256,:268 -> gt_multi_pow
+    E::pairing(p, q).0                src/mipp.rs:311 (verifier)
+    TargetField::pow(bigint)          src/mipp.rs:258-261 (verifier); with the products of :260,:268-271 -> gt_multi_pow
 
 Values are numpy uint64 arrays in ark's in-memory layout: G1 affine [12], G2 affine [24], GT = Fq12 [72] (tower order
 c0.c0.c0 ... c1.c2.c1, Montgomery limbs). Everything runs on the GPU (tb200_multi_pairing / tb200_gt_pow); there is no
@@ -81,7 +81,7 @@ def gt_pow(bases, exps, mont: bool = False) -> np.ndarray:
 
 def gt_multi_pow(bases, exps, mont: bool = False) -> np.ndarray:
     """prod_i base[i].pow(exp[i]) in GT: the TC half of the verifier's fold / reduce over `MippTU`
-    (src/mipp.rs:238-271) in one call; an empty product is 1."""
+    (src/mipp.rs:240-271) in one call; an empty product is 1."""
     b = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, GT_WORDS)
     e = np.ascontiguousarray(exps, dtype=np.uint64).reshape(-1, 4)
     if len(b) != len(e):

@@ -291,13 +291,13 @@ class Polynomial:
         a = list(point[: n // 2 + odd])
         b = list(point[n // 2 + odd:])
         batch = msm.RowBatch()                                              # every small G1 MSM of the two checks: ONE launch
-        finish_mipp = mipp_proof.verify_prepare(vk, challenge, b, U, T, batch)               # :248
+        finish_mipp = mipp_proof.verify_prepare(vk, challenge, b, U, T, batch)               # :249
         if finish_mipp is None:
             return False
-        finish_check = multilinear_pc.check_prepare(vk, U, a[::-1], v, pst_proof, batch)     # :254-262
+        finish_check = multilinear_pc.check_prepare(vk, U, a[::-1], v, pst_proof, batch)     # :254-261
         points = batch.run()
         check_u, tc, products = finish_mipp(points)
         products += finish_check(points)
         final_t, l2, r2, l1, r1 = pairing.multi_pairing_batch(products)
-        res_mipp = check_u and bool(np.array_equal(tc, final_t)) and bool(np.array_equal(l2, r2))   # :249
+        res_mipp = check_u and bool(np.array_equal(tc, final_t)) and bool(np.array_equal(l2, r2))   # :250
         return res_mipp and bool(np.array_equal(l1, r1))
